@@ -1,0 +1,132 @@
+/*
+ * svb200.h — C ABI of libsvb200.so: the B200-native (sm_100a) batched scan path of sudoku-vision.
+ *
+ * The reference has no FFI on this path: its boundary is a set of Python functions that call
+ * OpenCV / PyTorch.  Each entry point below replaces the body of one of those
+ * functions (cited as reference file:line, relative to the reference tree) for a BATCH of n
+ * frames / cells.  The Python drop-in modules (sudoku-vision_b200/dropin/) bind these with ctypes
+ * and keep the reference's signatures; INTEGRATION.md shows the stub a maintainer would add.
+ *
+ * Conventions
+ *  - Plain C types only.  Unless a parameter is named host_*, every pointer is a DEVICE pointer
+ *    to memory owned by the caller; the library never frees or retains caller memory.
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and the call returns
+ *    without synchronising (the *_host convenience calls synchronise before returning).
+ *  - Return value: 0 = SVB_OK, negative = error (svb_last_error() gives the text).  Per-frame
+ *    outcomes such as "no quadrilateral found" (cv/grid.py:71 returns None) are DATA (found[n]),
+ *    not errors.
+ *  - Images are uint8, row-major, tightly packed: frames [n][h][w][3] in BGR order (cv2.imread
+ *    layout), masks / gray [n][h][w].  Cells are [n][81][28][28], row-major by (row, col).
+ *  - There is no CPU fallback: every entry point launches CUDA kernels or fails.
+ */
+#ifndef SVB200_H
+#define SVB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVB_OK 0
+#define SVB_ERR_INVALID (-1)      /* bad argument (null pointer, non-positive size, ...)        */
+#define SVB_ERR_UNSUPPORTED (-2)  /* valid in the reference, not implemented here (non-default
+                                     ksize / block_size ...): the shim raises NotImplementedError */
+#define SVB_ERR_CUDA (-3)         /* a CUDA runtime call failed                                   */
+#define SVB_ERR_NOT_LOADED (-4)   /* classifier weights were not loaded                           */
+
+typedef struct svb_ctx svb_ctx;
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* One context per (host thread, device).  Owns scratch buffers and packed classifier weights.   */
+int svb_create(int device, svb_ctx **out);
+void svb_destroy(svb_ctx *ctx);
+const char *svb_last_error(void);
+int svb_abi_version(void);
+/* Number of kernels this library has launched through `ctx` since creation (bench.py's
+ * gpu_launches claim is read from here). */
+long long svb_launch_count(const svb_ctx *ctx);
+
+/* Per-stage device timing of svb_scan_batch_v1 (bench.py's roofline numbers are taken INSIDE the
+ * timed region with these): when enabled, CUDA events are recorded on the launching stream between
+ * the stages of every scan.  svb_last_stage_ms waits for the last scan's final event and returns the
+ * elapsed milliseconds of its stages: [0] K1 fused preprocess, [1] K2 contour (reset+probe+select),
+ * [2] K3+K4 homography + cells, [3] K5 classifier (+ not-found masking). */
+#define SVB_NUM_STAGES 4
+int svb_stage_timing(svb_ctx *ctx, int enable);
+int svb_last_stage_ms(svb_ctx *ctx, float *ms);
+
+/* ---- P1..P4: cv/preprocess.py ---------------------------------------------------------------- */
+/* grayscale(image)  cv/preprocess.py:15-19  (cv2.cvtColor BGR2GRAY, 15-bit fixed point) */
+int svb_grayscale(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *gray, void *stream);
+/* blur(image, ksize=5)  cv/preprocess.py:22-29  (cv2.GaussianBlur (5,5), sigma 0, REFLECT_101).
+ * ksize != 5 -> SVB_ERR_UNSUPPORTED */
+int svb_blur(svb_ctx *ctx, const uint8_t *gray, int n, int h, int w, int ksize, uint8_t *out, void *stream);
+/* threshold(image, block_size=11, c=2)  cv/preprocess.py:32-54  (adaptiveThreshold GAUSSIAN_C).
+ * inverted != 0: THRESH_BINARY_INV (cv/preprocess.py:51); 0: THRESH_BINARY (pipeline/run.py:87-88).
+ * block_size != 11 or c != 2 -> SVB_ERR_UNSUPPORTED */
+int svb_adaptive_threshold(svb_ctx *ctx, const uint8_t *gray, int n, int h, int w, int block_size, int c,
+                           int inverted, uint8_t *out, void *stream);
+/* preprocess_for_grid_detection(image)  cv/preprocess.py:57-65: one fused kernel, BGR -> mask */
+int svb_preprocess_v1(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *mask, void *stream);
+
+/* ---- G1..G4: cv/grid.py ---------------------------------------------------------------------- */
+/* find_grid_contour(binary, min_area_ratio=0.1)  cv/grid.py:37-71 with approximate_polygon's
+ * epsilon_ratio (cv/grid.py:24-34; the reference always uses 0.02).
+ * corners: int32 [n][4][2] (x, y) in approxPolyDP output order; found: uint8 [n] (0 = None). */
+int svb_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, int w, double min_area_ratio,
+                          double eps_ratio, int32_t *corners, uint8_t *found, void *stream);
+/* order_points + getPerspectiveTransform + warpPerspective  cv/grid.py:74-133 (inset_ratio 0).
+ * board: uint8 [n][out_size][out_size][3]; frames with found == 0 produce an all-zero board.
+ * `found` may be NULL (all frames valid). */
+int svb_warp_perspective(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, const int32_t *corners,
+                         const uint8_t *found, int out_size, uint8_t *board, void *stream);
+
+/* ---- E1: cv/extract.py ----------------------------------------------------------------------- */
+/* extract_cells(grid_image, cell_size=28, margin_ratio=0.1)  cv/extract.py:13-56.
+ * board: [n][size][size][3] BGR (size must be a multiple of 9); cells: uint8 [n][81][28][28]. */
+int svb_extract_cells(svb_ctx *ctx, const uint8_t *board, int n, int size, uint8_t *cells, void *stream);
+
+/* ---- C1/C2: pipeline/run.py ------------------------------------------------------------------ */
+/* preprocess_cell (pipeline/run.py:73-95: CLAHE(2.0,(4,4)) + adaptiveThreshold BINARY 11,2)
+ * followed by predict_cells' invert + /255 + (x-0.5)/0.5 (run.py:129-135).
+ * cells: uint8 [n_cells][28][28].  Outputs (each may be NULL):
+ *   thresh  uint8 [n_cells][28][28]  = preprocess_cell's return value (0/255)
+ *   pm1     float [n_cells][1][28][28] = the tensor fed to the model (exactly -1 / +1) */
+int svb_cell_prep(svb_ctx *ctx, const uint8_t *cells, long long n_cells, uint8_t *thresh, float *pm1,
+                  void *stream);
+
+/* Fused G3+G4+E1+C1+C2 for the batched path: frames + corners -> cells, no 450x450 board in HBM.
+ * cells_u8 (optional): uint8 [n][81][28][28] = extract_cells output.
+ * cells_pm1 (required): float [n][81][28][28] = model input.  Frames with found == 0 are zero-filled. */
+int svb_cells_from_frames(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, const int32_t *corners,
+                          const uint8_t *found, uint8_t *cells_u8, float *cells_pm1, void *stream);
+
+/* ---- M1/M2: ml/model.py, pipeline/run.py:139-150 --------------------------------------------- */
+/* DigitCNN parameters (ml/model.py:22-32), PyTorch layouts, fp32, DEVICE pointers:
+ * conv1.weight (32,1,3,3) conv1.bias (32) conv2.weight (64,32,3,3) conv2.bias (64)
+ * fc1.weight (128,3136) fc1.bias (128) fc2.weight (10,128) fc2.bias (10).  Packs them into the
+ * kernels' layouts inside ctx (replaces load_state_dict at pipeline/run.py:108). */
+int svb_digitcnn_load(svb_ctx *ctx, const float *conv1_w, const float *conv1_b, const float *conv2_w,
+                      const float *conv2_b, const float *fc1_w, const float *fc1_b, const float *fc2_w,
+                      const float *fc2_b, void *stream);
+/* DigitCNN.forward (ml/model.py:34-42), eval mode.  x: float [n][1][28][28]; logits: float [n][10].
+ * Optional epilogue (pipeline/run.py:141-143): digits uint8 [n] = argmax, conf float [n] =
+ * softmax(logits)[argmax]; either may be NULL. */
+int svb_digitcnn_forward(svb_ctx *ctx, const float *x, long long n, float *logits, uint8_t *digits,
+                         float *conf, void *stream);
+
+/* ---- whole path: pipeline/run.py:257-318 (CV + ML sections) for n frames ------------------------ */
+/* Outputs: digits uint8 [n][81], conf float [n][81], logits float [n][81][10] (optional),
+ * corners int32 [n][4][2], found uint8 [n].  Frames with found == 0 get digits 0 / conf 0. */
+int svb_scan_batch_v1(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *digits, float *conf,
+                      float *logits, int32_t *corners, uint8_t *found, void *stream);
+/* Same with HOST buffers (pinned or pageable): copies frames H2D, runs the path, copies results
+ * D2H and synchronises.  This is the end-to-end call bench.py times as `e2e`. */
+int svb_scan_batch_v1_host(svb_ctx *ctx, const uint8_t *host_bgr, int n, int h, int w, uint8_t *host_digits,
+                           float *host_conf, int32_t *host_corners, uint8_t *host_found);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVB200_H */

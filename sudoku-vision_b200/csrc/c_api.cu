@@ -1,0 +1,297 @@
+// c_api.cu — extern "C" entry points of libsvb200.so (include/svb200.h).  Thin: argument checks,
+// scratch slicing, kernel launchers from the other translation units.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace svb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int Scratch::reserve(size_t need) {
+    if (need <= bytes) return SVB_OK;
+    if (ptr) {
+        cudaDeviceSynchronize();  // the old buffer may still be in use by enqueued work
+        cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+    size_t want = need + need / 8 + (1u << 20);
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) {
+        set_error("scratch cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        ptr = nullptr;
+        return SVB_ERR_CUDA;
+    }
+    bytes = want;
+    return SVB_OK;
+}
+void Scratch::release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+}
+
+// launchers defined in the other translation units
+int launch_gray(svb_ctx *, const uint8_t *, int, int, int, uint8_t *, cudaStream_t);
+int launch_blur5(svb_ctx *, const uint8_t *, int, int, int, uint8_t *, cudaStream_t);
+int launch_adaptive(svb_ctx *, const uint8_t *, int, int, int, int, uint8_t *, cudaStream_t);
+bool fused_preprocess_supported(int h, int w);
+int launch_fused_preprocess(svb_ctx *, const uint8_t *, int, int, int, uint8_t *, cudaStream_t);
+int launch_find_grid_contour(svb_ctx *, const uint8_t *, int, int, int, double, double, int32_t *, uint8_t *, cudaStream_t);
+int launch_warp_board(svb_ctx *, const uint8_t *, int, int, int, const int32_t *, const uint8_t *, int, uint8_t *, cudaStream_t);
+int launch_extract_cells(svb_ctx *, const uint8_t *, int, int, uint8_t *, cudaStream_t);
+int launch_cell_prep(svb_ctx *, const uint8_t *, long long, uint8_t *, float *, cudaStream_t);
+int launch_cells_from_frames(svb_ctx *, const uint8_t *, int, int, int, const int32_t *, const uint8_t *, uint8_t *, float *, cudaStream_t);
+int digitcnn_load(svb_ctx *, const float *const w[8], cudaStream_t);
+int launch_digitcnn(svb_ctx *, const float *, long long, float *, uint8_t *, float *, cudaStream_t);
+void digitcnn_free(svb_ctx *);
+int launch_mask_not_found(svb_ctx *, const uint8_t *, int, uint8_t *, float *, cudaStream_t);
+
+}  // namespace svb
+
+using namespace svb;
+
+#define API extern "C" __attribute__((visibility("default")))
+#define GUARD(ctx)                                              \
+    SVB_REQUIRE((ctx) != nullptr, SVB_ERR_INVALID, "null ctx"); \
+    DeviceGuard guard__((ctx)->device);                         \
+    SVB_REQUIRE(guard__.ok, SVB_ERR_CUDA, "cudaSetDevice failed")
+
+static bool dims_ok(int n, int h, int w) { return n > 0 && h > 0 && w > 0 && n <= 65535 && h <= 65535; }
+
+API int svb_abi_version(void) { return 1; }
+API const char *svb_last_error(void) { return g_err; }
+
+API int svb_create(int device, svb_ctx **out) {
+    SVB_REQUIRE(out != nullptr, SVB_ERR_INVALID, "null out");
+    int count = 0;
+    SVB_CUDA_OK(cudaGetDeviceCount(&count));
+    SVB_REQUIRE(device >= 0 && device < count, SVB_ERR_INVALID, "no such CUDA device");
+    DeviceGuard g(device);
+    SVB_REQUIRE(g.ok, SVB_ERR_CUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    SVB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("svb200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+        return SVB_ERR_UNSUPPORTED;
+    }
+    svb_ctx *c = new svb_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    SVB_CUDA_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    *out = c;
+    return SVB_OK;
+}
+
+API void svb_destroy(svb_ctx *ctx) {
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < AR_COUNT; ++i) ctx->arena[i].release();
+    digitcnn_free(ctx);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (auto &e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+API long long svb_launch_count(const svb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+API int svb_stage_timing(svb_ctx *ctx, int enable) {
+    GUARD(ctx);
+    if (enable)
+        for (auto &e : ctx->ev)
+            if (!e) SVB_CUDA_OK(cudaEventCreate(&e));
+    ctx->stage_timing = enable != 0;
+    ctx->ev_valid = false;
+    return SVB_OK;
+}
+
+API int svb_last_stage_ms(svb_ctx *ctx, float *ms) {
+    GUARD(ctx);
+    SVB_REQUIRE(ms != nullptr, SVB_ERR_INVALID, "svb_last_stage_ms: null output");
+    SVB_REQUIRE(ctx->stage_timing && ctx->ev_valid, SVB_ERR_INVALID, "svb_last_stage_ms: no timed scan recorded");
+    SVB_CUDA_OK(cudaEventSynchronize(ctx->ev[SVB_NUM_STAGES]));
+    for (int i = 0; i < SVB_NUM_STAGES; ++i) SVB_CUDA_OK(cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    return SVB_OK;
+}
+
+API int svb_grayscale(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *gray, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(bgr && gray && dims_ok(n, h, w), SVB_ERR_INVALID, "svb_grayscale: bad arguments");
+    return launch_gray(ctx, bgr, n, h, w, gray, (cudaStream_t)stream);
+}
+
+API int svb_blur(svb_ctx *ctx, const uint8_t *gray, int n, int h, int w, int ksize, uint8_t *out, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(gray && out && dims_ok(n, h, w), SVB_ERR_INVALID, "svb_blur: bad arguments");
+    SVB_REQUIRE(ksize == 5, SVB_ERR_UNSUPPORTED, "svb_blur: only ksize=5 (the reference's default) is implemented");
+    SVB_REQUIRE(h >= 3 && w >= 3, SVB_ERR_UNSUPPORTED, "svb_blur: images smaller than 3x3 are not supported");
+    return launch_blur5(ctx, gray, n, h, w, out, (cudaStream_t)stream);
+}
+
+API int svb_adaptive_threshold(svb_ctx *ctx, const uint8_t *gray, int n, int h, int w, int block_size, int c,
+                               int inverted, uint8_t *out, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(gray && out && dims_ok(n, h, w), SVB_ERR_INVALID, "svb_adaptive_threshold: bad arguments");
+    SVB_REQUIRE(block_size == 11 && c == 2, SVB_ERR_UNSUPPORTED,
+                "svb_adaptive_threshold: only block_size=11, c=2 (the reference's defaults) are implemented");
+    return launch_adaptive(ctx, gray, n, h, w, inverted, out, (cudaStream_t)stream);
+}
+
+static int preprocess_any(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *mask, cudaStream_t st) {
+    if (fused_preprocess_supported(h, w) && ((uintptr_t)bgr % 16 == 0) && ((uintptr_t)mask % 4 == 0))
+        return launch_fused_preprocess(ctx, bgr, n, h, w, mask, st);
+    // odd sizes: the three stage kernels back to back (still GPU; no CPU fallback)
+    SVB_REQUIRE(h >= 3 && w >= 3, SVB_ERR_UNSUPPORTED, "preprocess: images smaller than 3x3 are not supported");
+    size_t px = (size_t)n * h * w;
+    if (ctx->arena[AR_STAGE].reserve(2 * px) != SVB_OK) return SVB_ERR_CUDA;
+    uint8_t *g = (uint8_t *)ctx->arena[AR_STAGE].ptr, *b = g + px;
+    int rc = launch_gray(ctx, bgr, n, h, w, g, st);
+    if (rc) return rc;
+    rc = launch_blur5(ctx, g, n, h, w, b, st);
+    if (rc) return rc;
+    return launch_adaptive(ctx, b, n, h, w, 1, mask, st);
+}
+
+API int svb_preprocess_v1(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *mask, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(bgr && mask && dims_ok(n, h, w), SVB_ERR_INVALID, "svb_preprocess_v1: bad arguments");
+    return preprocess_any(ctx, bgr, n, h, w, mask, (cudaStream_t)stream);
+}
+
+API int svb_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, int w, double min_area_ratio,
+                              double eps_ratio, int32_t *corners, uint8_t *found, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(mask && corners && found && dims_ok(n, h, w), SVB_ERR_INVALID, "svb_find_grid_contour: bad arguments");
+    SVB_REQUIRE(w <= 65535, SVB_ERR_UNSUPPORTED, "svb_find_grid_contour: width above 65535");
+    SVB_REQUIRE(min_area_ratio > 0.0 && eps_ratio >= 0.0, SVB_ERR_INVALID, "svb_find_grid_contour: ratios must be positive");
+    return launch_find_grid_contour(ctx, mask, n, h, w, min_area_ratio, eps_ratio, corners, found, (cudaStream_t)stream);
+}
+
+API int svb_warp_perspective(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, const int32_t *corners,
+                             const uint8_t *found, int out_size, uint8_t *board, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(bgr && corners && board && dims_ok(n, h, w) && out_size > 1 && out_size <= 8192, SVB_ERR_INVALID,
+                "svb_warp_perspective: bad arguments");
+    return launch_warp_board(ctx, bgr, n, h, w, corners, found, out_size, board, (cudaStream_t)stream);
+}
+
+API int svb_extract_cells(svb_ctx *ctx, const uint8_t *board, int n, int size, uint8_t *cells, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(board && cells && n > 0 && n <= 65535 && size >= 9, SVB_ERR_INVALID, "svb_extract_cells: bad arguments");
+    return launch_extract_cells(ctx, board, n, size, cells, (cudaStream_t)stream);
+}
+
+API int svb_cell_prep(svb_ctx *ctx, const uint8_t *cells, long long n_cells, uint8_t *thresh, float *pm1, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(cells && n_cells > 0 && (thresh || pm1), SVB_ERR_INVALID, "svb_cell_prep: bad arguments");
+    return launch_cell_prep(ctx, cells, n_cells, thresh, pm1, (cudaStream_t)stream);
+}
+
+API int svb_cells_from_frames(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, const int32_t *corners,
+                              const uint8_t *found, uint8_t *cells_u8, float *cells_pm1, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(bgr && corners && cells_pm1 && dims_ok(n, h, w), SVB_ERR_INVALID, "svb_cells_from_frames: bad arguments");
+    return launch_cells_from_frames(ctx, bgr, n, h, w, corners, found, cells_u8, cells_pm1, (cudaStream_t)stream);
+}
+
+API int svb_digitcnn_load(svb_ctx *ctx, const float *conv1_w, const float *conv1_b, const float *conv2_w,
+                          const float *conv2_b, const float *fc1_w, const float *fc1_b, const float *fc2_w,
+                          const float *fc2_b, void *stream) {
+    GUARD(ctx);
+    const float *w[8] = {conv1_w, conv1_b, conv2_w, conv2_b, fc1_w, fc1_b, fc2_w, fc2_b};
+    for (int i = 0; i < 8; ++i) SVB_REQUIRE(w[i] != nullptr, SVB_ERR_INVALID, "svb_digitcnn_load: null weight pointer");
+    return digitcnn_load(ctx, w, (cudaStream_t)stream);
+}
+
+API int svb_digitcnn_forward(svb_ctx *ctx, const float *x, long long n, float *logits, uint8_t *digits, float *conf,
+                             void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(x && logits && n > 0, SVB_ERR_INVALID, "svb_digitcnn_forward: bad arguments");
+    return launch_digitcnn(ctx, x, n, logits, digits, conf, (cudaStream_t)stream);
+}
+
+// Whole path.  Intermediates (mask, +-1 cells, logits when the caller does not want them) live in the
+// AR_PATH arena; every stage is enqueued on the caller's stream, nothing synchronises.
+static int scan_batch(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *digits, float *conf,
+                      float *logits, int32_t *corners, uint8_t *found, cudaStream_t st) {
+    const size_t px = (size_t)n * h * w;
+    const size_t cells = (size_t)n * 81;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return o;
+    };
+    const size_t o_mask = take(px), o_pm1 = take(cells * 784 * sizeof(float)), o_log = take(cells * 10 * sizeof(float));
+    if (ctx->arena[AR_PATH].reserve(off) != SVB_OK) return SVB_ERR_CUDA;
+    char *base = (char *)ctx->arena[AR_PATH].ptr;
+    uint8_t *mask = (uint8_t *)(base + o_mask);
+    float *pm1 = (float *)(base + o_pm1);
+    float *lg = logits ? logits : (float *)(base + o_log);
+    const bool tm = ctx->stage_timing;
+    auto mark = [&](int i) {
+        if (tm) cudaEventRecord(ctx->ev[i], st);
+    };
+    mark(0);
+    int rc = preprocess_any(ctx, bgr, n, h, w, mask, st);
+    if (rc) return rc;
+    mark(1);
+    rc = launch_find_grid_contour(ctx, mask, n, h, w, 0.1, 0.02, corners, found, st);
+    if (rc) return rc;
+    mark(2);
+    rc = launch_cells_from_frames(ctx, bgr, n, h, w, corners, found, nullptr, pm1, st);
+    if (rc) return rc;
+    mark(3);
+    // frames without a grid have all-zero cell tensors; their digits/conf are forced to 0 below
+    rc = launch_digitcnn(ctx, pm1, (long long)cells, lg, digits, conf, st);
+    if (rc) return rc;
+    rc = launch_mask_not_found(ctx, found, n, digits, conf, st);
+    mark(4);
+    ctx->ev_valid = tm;
+    return rc;
+}
+
+API int svb_scan_batch_v1(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *digits, float *conf,
+                          float *logits, int32_t *corners, uint8_t *found, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(bgr && digits && conf && corners && found && dims_ok(n, h, w), SVB_ERR_INVALID,
+                "svb_scan_batch_v1: bad arguments");
+    SVB_REQUIRE(ctx->cnn.loaded, SVB_ERR_NOT_LOADED, "svb_scan_batch_v1: DigitCNN weights not loaded");
+    return scan_batch(ctx, bgr, n, h, w, digits, conf, logits, corners, found, (cudaStream_t)stream);
+}
+
+API int svb_scan_batch_v1_host(svb_ctx *ctx, const uint8_t *host_bgr, int n, int h, int w, uint8_t *host_digits,
+                               float *host_conf, int32_t *host_corners, uint8_t *host_found) {
+    GUARD(ctx);
+    SVB_REQUIRE(host_bgr && host_digits && host_conf && host_corners && host_found && dims_ok(n, h, w), SVB_ERR_INVALID,
+                "svb_scan_batch_v1_host: bad arguments");
+    SVB_REQUIRE(ctx->cnn.loaded, SVB_ERR_NOT_LOADED, "svb_scan_batch_v1_host: DigitCNN weights not loaded");
+    const size_t in_bytes = (size_t)n * h * w * 3;
+    const size_t o_dig = (in_bytes + 255) & ~(size_t)255, o_conf = o_dig + (((size_t)n * 81 + 255) & ~(size_t)255);
+    const size_t o_cor = o_conf + (((size_t)n * 81 * 4 + 255) & ~(size_t)255), o_fnd = o_cor + (((size_t)n * 32 + 255) & ~(size_t)255);
+    const size_t total = o_fnd + (((size_t)n + 255) & ~(size_t)255);
+    if (ctx->arena[AR_STAGE].reserve(total) != SVB_OK) return SVB_ERR_CUDA;
+    char *d = (char *)ctx->arena[AR_STAGE].ptr;
+    cudaStream_t st = ctx->own_stream;
+    SVB_CUDA_OK(cudaMemcpyAsync(d, host_bgr, in_bytes, cudaMemcpyHostToDevice, st));
+    int rc = scan_batch(ctx, (const uint8_t *)d, n, h, w, (uint8_t *)(d + o_dig), (float *)(d + o_conf), nullptr,
+                        (int32_t *)(d + o_cor), (uint8_t *)(d + o_fnd), st);
+    if (rc) return rc;
+    SVB_CUDA_OK(cudaMemcpyAsync(host_digits, d + o_dig, (size_t)n * 81, cudaMemcpyDeviceToHost, st));
+    SVB_CUDA_OK(cudaMemcpyAsync(host_conf, d + o_conf, (size_t)n * 81 * 4, cudaMemcpyDeviceToHost, st));
+    SVB_CUDA_OK(cudaMemcpyAsync(host_corners, d + o_cor, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    SVB_CUDA_OK(cudaMemcpyAsync(host_found, d + o_fnd, (size_t)n, cudaMemcpyDeviceToHost, st));
+    SVB_CUDA_OK(cudaStreamSynchronize(st));
+    return SVB_OK;
+}

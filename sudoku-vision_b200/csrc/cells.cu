@@ -1,0 +1,438 @@
+// cells.cu — G3/G4 (order_points, getPerspectiveTransform, warpPerspective: cv/grid.py:74-133),
+// E1 (extract_cells: cv/extract.py:13-56) and C1/C2 (preprocess_cell + tensor prep:
+// pipeline/run.py:73-95,129-135) as sm_100a kernels.
+//
+//   K3  homography_kernel        one thread per frame: order the 4 corners, solve the 8x8 system by
+//                                LU with partial pivoting in fp64, invert the 3x3 — explicit
+//                                __dmul_rn/__dadd_rn so the result is the CPU's, bit for bit.
+//   K4  cells_from_frames_kernel one CTA per (frame, cell): samples the 40x40 crop of the cell
+//                                straight from the source frame (fixed-point bilinear, 1/32-px
+//                                coordinates), grays it, resizes to 28x28 (11-bit coefficients),
+//                                applies CLAHE(2.0, 4x4) and the Gaussian adaptive threshold, and
+//                                writes the +-1 classifier input.  The 450x450 board never exists.
+//   stage kernels for the drop-in functions: warp_board_kernel, extract_cells_kernel, cell_prep_kernel
+//   (the latter two are the same device code as K4, entered at a later phase).
+#include "common.cuh"
+
+namespace svb {
+namespace k4 {
+
+constexpr int BOARD = 450;
+constexpr int CELL = 28;
+constexpr int NT = 128;
+
+struct ResizeTab {  // cv2.resize INTER_LINEAR coefficients for `src` -> 28
+    int src;
+    short s0[CELL], a0[CELL], a1[CELL];
+};
+
+// ---- K3 -----------------------------------------------------------------------------------------
+__device__ __forceinline__ double dm(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double da(double a, double b) { return __dadd_rn(a, b); }
+
+// cv/grid.py:74-91 order_points + :123-130 getPerspectiveTransform(src -> [0,s]x[0,s]) + inversion.
+// One thread per frame.  minv: [n][9] doubles (maps board pixel -> source pixel, homogeneous).
+__global__ void homography_kernel(const int32_t *__restrict__ corners, const uint8_t *__restrict__ found, int n,
+                                  int out_size, double *__restrict__ minv) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    double *o = minv + (long long)f * 9;
+    if (found && found[f] != 1) {
+        for (int i = 0; i < 9; ++i) o[i] = 0.0;
+        return;
+    }
+    const int32_t *c = corners + (long long)f * 8;
+    // numpy argmin/argmax: first index wins ties
+    int is_min = 0, is_max = 0, id_min = 0, id_max = 0;
+    for (int i = 1; i < 4; ++i) {
+        const int s = c[2 * i] + c[2 * i + 1], d = c[2 * i + 1] - c[2 * i];
+        if (s < c[2 * is_min] + c[2 * is_min + 1]) is_min = i;
+        if (s > c[2 * is_max] + c[2 * is_max + 1]) is_max = i;
+        if (d < c[2 * id_min + 1] - c[2 * id_min]) id_min = i;
+        if (d > c[2 * id_max + 1] - c[2 * id_max]) id_max = i;
+    }
+    const int order[4] = {is_min, id_min, is_max, id_max};  // TL, TR, BR, BL
+    const double e = (double)(out_size - 1);
+    const double du[4] = {0.0, e, e, 0.0}, dv[4] = {0.0, 0.0, e, e};
+    double A[8][9];
+    for (int i = 0; i < 4; ++i) {
+        const double x = (double)(float)c[2 * order[i]], y = (double)(float)c[2 * order[i] + 1];
+        const double u = du[i], v = dv[i];
+        A[i][0] = x; A[i][1] = y; A[i][2] = 1; A[i][3] = 0; A[i][4] = 0; A[i][5] = 0;
+        A[i][6] = dm(-x, u); A[i][7] = dm(-y, u); A[i][8] = u;
+        A[i + 4][0] = 0; A[i + 4][1] = 0; A[i + 4][2] = 0; A[i + 4][3] = x; A[i + 4][4] = y; A[i + 4][5] = 1;
+        A[i + 4][6] = dm(-x, v); A[i + 4][7] = dm(-y, v); A[i + 4][8] = v;
+    }
+    double M[9];
+    bool singular = false;
+    for (int col = 0; col < 8 && !singular; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < 8; ++r)
+            if (fabs(A[r][col]) > fabs(A[piv][col])) piv = r;
+        if (fabs(A[piv][col]) < 2.220446049250313e-16) { singular = true; break; }
+        if (piv != col)
+            for (int k = 0; k < 9; ++k) { const double t = A[col][k]; A[col][k] = A[piv][k]; A[piv][k] = t; }
+        const double d = -1.0 / A[col][col];
+        for (int r = col + 1; r < 8; ++r) {
+            const double a = dm(A[r][col], d);
+            for (int k = col + 1; k < 9; ++k) A[r][k] = da(A[r][k], dm(a, A[col][k]));
+        }
+    }
+    if (singular) {
+        for (int i = 0; i < 8; ++i) M[i] = 0.0;
+    } else {
+        for (int r = 7; r >= 0; --r) {
+            double s = A[r][8];
+            for (int k = r + 1; k < 8; ++k) s = da(s, -dm(A[r][k], M[k]));
+            M[r] = s / A[r][r];
+        }
+    }
+    M[8] = 1.0;
+    // 3x3 inverse: adjugate / determinant (cv::invert's closed form for 3x3)
+    const double c00 = da(dm(M[4], M[8]), -dm(M[5], M[7]));
+    const double c01 = da(dm(M[3], M[8]), -dm(M[5], M[6]));
+    const double c02 = da(dm(M[3], M[7]), -dm(M[4], M[6]));
+    double det = da(da(dm(M[0], c00), -dm(M[1], c01)), dm(M[2], c02));
+    if (det == 0.0) {
+        for (int i = 0; i < 9; ++i) o[i] = 0.0;
+        return;
+    }
+    det = 1.0 / det;
+    o[0] = dm(c00, det);
+    o[1] = dm(da(dm(M[2], M[7]), -dm(M[1], M[8])), det);
+    o[2] = dm(da(dm(M[1], M[5]), -dm(M[2], M[4])), det);
+    o[3] = dm(da(dm(M[5], M[6]), -dm(M[3], M[8])), det);
+    o[4] = dm(da(dm(M[0], M[8]), -dm(M[2], M[6])), det);
+    o[5] = dm(da(dm(M[2], M[3]), -dm(M[0], M[5])), det);
+    o[6] = dm(c02, det);
+    o[7] = dm(da(dm(M[1], M[6]), -dm(M[0], M[7])), det);
+    o[8] = dm(da(dm(M[0], M[4]), -dm(M[1], M[3])), det);
+}
+
+// ---- warpPerspective sampling (INTER_LINEAR, BORDER_CONSTANT 0), SURVEY App. A4 -----------------------
+struct Tap {
+    int ix, iy;
+    int w00, w01, w10, w11;
+};
+
+// cv2 evaluates the map per destination block of bw0 = min(64, width) columns: row terms at the
+// block's first column bx, then the in-block offset x1 = x - bx (the association decides exact .5 ties).
+__device__ __forceinline__ Tap make_tap(const double *__restrict__ mi, int x, int y, int bw0) {
+    const int bx = (x / bw0) * bw0;
+    const double bxd = (double)bx, x1d = (double)(x - bx), yd = (double)y;
+    const double X0 = da(da(dm(mi[0], bxd), dm(mi[1], yd)), mi[2]);
+    const double Y0 = da(da(dm(mi[3], bxd), dm(mi[4], yd)), mi[5]);
+    const double W0 = da(da(dm(mi[6], bxd), dm(mi[7], yd)), mi[8]);
+    double Wd = da(W0, dm(mi[6], x1d));
+    Wd = (Wd != 0.0) ? 32.0 / Wd : 0.0;
+    double fx = dm(da(X0, dm(mi[0], x1d)), Wd), fy = dm(da(Y0, dm(mi[3], x1d)), Wd);
+    fx = fmin(fmax(fx, -2147483648.0), 2147483647.0);
+    fy = fmin(fmax(fy, -2147483648.0), 2147483647.0);
+    const int X = __double2int_rn(fx), Y = __double2int_rn(fy);
+    Tap t;
+    t.ix = X >> 5;
+    t.iy = Y >> 5;
+    const int ax = X & 31, ay = Y & 31;
+    t.w00 = (32 - ax) * (32 - ay) * 32;
+    t.w01 = ax * (32 - ay) * 32;
+    t.w10 = (32 - ax) * ay * 32;
+    t.w11 = ax * ay * 32;
+    return t;
+}
+
+// returns packed B | G<<8 | R<<16 of the warped pixel
+__device__ __forceinline__ uint32_t sample_bgr(const uint8_t *__restrict__ frame, int h, int w, const Tap &t) {
+    const bool x0 = (unsigned)t.ix < (unsigned)w, x1 = (unsigned)(t.ix + 1) < (unsigned)w;
+    const bool y0 = (unsigned)t.iy < (unsigned)h, y1 = (unsigned)(t.iy + 1) < (unsigned)h;
+    const uint8_t *p = frame + ((long long)t.iy * w + t.ix) * 3;
+    const long long rs = (long long)w * 3;
+    uint32_t out = 0;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const int p00 = (x0 && y0) ? __ldg(p + ch) : 0;
+        const int p01 = (x1 && y0) ? __ldg(p + 3 + ch) : 0;
+        const int p10 = (x0 && y1) ? __ldg(p + rs + ch) : 0;
+        const int p11 = (x1 && y1) ? __ldg(p + rs + 3 + ch) : 0;
+        const int v = (t.w00 * p00 + t.w01 * p01 + t.w10 * p10 + t.w11 * p11 + 16384) >> 15;
+        out |= (uint32_t)v << (8 * ch);
+    }
+    return out;
+}
+
+__global__ void warp_board_kernel(const uint8_t *__restrict__ bgr, int h, int w, const double *__restrict__ minv,
+                                  const uint8_t *__restrict__ found, int out_size, uint8_t *__restrict__ board) {
+    const int f = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= out_size) return;
+    uint8_t *o = board + (((long long)f * out_size + y) * out_size + x) * 3;
+    if (found && found[f] != 1) {
+        o[0] = o[1] = o[2] = 0;
+        return;
+    }
+    const Tap t = make_tap(minv + (long long)f * 9, x, y, min(out_size, 64));
+    const uint32_t v = sample_bgr(bgr + (long long)f * h * w * 3, h, w, t);
+    o[0] = v & 0xff;
+    o[1] = (v >> 8) & 0xff;
+    o[2] = (v >> 16) & 0xff;
+}
+
+// ---- per-cell pipeline in shared memory --------------------------------------------------------------
+struct CellSmem {
+    uint8_t crop[64 * 64];       // gray crop, up to 64x64 (40x40 for the 450 board)
+    uint8_t cell[CELL * CELL];   // extract_cells output
+    uint8_t eq[CELL * CELL];     // CLAHE output
+    uint8_t lut[16][256];
+    int hist[16][256];
+    float rp[CELL * CELL];       // Gaussian row pass
+};
+
+// cv2.resize(crop, (28,28)) INTER_LINEAR, 11-bit fixed point
+__device__ __forceinline__ void resize_phase(CellSmem &s, const ResizeTab &rt) {
+    const int cw = rt.src;
+    for (int i = threadIdx.x; i < CELL * CELL; i += blockDim.x) {
+        const int y = i / CELL, x = i - y * CELL;
+        const int sy = rt.s0[y], sy1 = min(sy + 1, cw - 1), sx = rt.s0[x], sx1 = min(sx + 1, cw - 1);
+        const int b0 = rt.a0[y], b1 = rt.a1[y], a0 = rt.a0[x], a1 = rt.a1[x];
+        const int h0 = s.crop[sy * cw + sx] * a0 + s.crop[sy * cw + sx1] * a1;
+        const int h1 = s.crop[sy1 * cw + sx] * a0 + s.crop[sy1 * cw + sx1] * a1;
+        s.cell[i] = (uint8_t)(((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16)) + 2) >> 2);
+    }
+}
+
+// createCLAHE(2.0,(4,4)).apply on 28x28: 16 tiles of 7x7, clip 1
+__device__ __forceinline__ void clahe_phase(CellSmem &s) {
+    constexpr int TS = 7, NTL = 4, TA = 49;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    for (int i = tid; i < 16 * 256; i += blockDim.x) (&s.hist[0][0])[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < CELL * CELL; i += blockDim.x) {
+        const int y = i / CELL, x = i - y * CELL;
+        atomicAdd(&s.hist[(y / TS) * NTL + (x / TS)][s.cell[i]], 1);
+    }
+    __syncthreads();
+    int clip = (int)(2.0 * TA / 256.0);
+    clip = clip < 1 ? 1 : clip;
+    const float lut_scale = 255.0f / (float)TA;
+    for (int tile = warp; tile < 16; tile += nwarp) {
+        int hv[8];
+        int excess = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int v = s.hist[tile][lane * 8 + k];
+            if (v > clip) { excess += v - clip; v = clip; }
+            hv[k] = v;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) excess += __shfl_xor_sync(0xffffffffu, excess, off);
+        const int batch = excess / 256, resid = excess - batch * 256;
+        const int step = resid > 0 ? max(256 / resid, 1) : 1;
+        int run = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int bin = lane * 8 + k;
+            int v = hv[k] + batch;
+            if (resid > 0 && (bin % step) == 0 && (bin / step) < resid) v += 1;
+            run += v;
+            hv[k] = run;  // inclusive prefix inside the lane
+        }
+        int incl = run;  // warp inclusive scan of lane totals
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        const int base = incl - run;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float v = __fmul_rn((float)(base + hv[k]), lut_scale);
+            s.lut[tile][lane * 8 + k] = (uint8_t)min(max(__float2int_rn(v), 0), 255);
+        }
+    }
+    __syncthreads();
+    const float inv = 1.0f / (float)TS;
+    for (int i = tid; i < CELL * CELL; i += blockDim.x) {
+        const int y = i / CELL, x = i - y * CELL;
+        const float tyf = __fadd_rn(__fmul_rn((float)y, inv), -0.5f);
+        const float txf = __fadd_rn(__fmul_rn((float)x, inv), -0.5f);
+        int ty1 = (int)floorf(tyf), tx1 = (int)floorf(txf);
+        const float ya = __fadd_rn(tyf, -(float)ty1), xa = __fadd_rn(txf, -(float)tx1);
+        const float ya1 = __fadd_rn(1.0f, -ya), xa1 = __fadd_rn(1.0f, -xa);
+        const int ty2 = min(max(ty1 + 1, 0), NTL - 1), tx2 = min(max(tx1 + 1, 0), NTL - 1);
+        ty1 = min(max(ty1, 0), NTL - 1);
+        tx1 = min(max(tx1, 0), NTL - 1);
+        const int v = s.cell[i];
+        const float l11 = (float)s.lut[ty1 * NTL + tx1][v], l12 = (float)s.lut[ty1 * NTL + tx2][v];
+        const float l21 = (float)s.lut[ty2 * NTL + tx1][v], l22 = (float)s.lut[ty2 * NTL + tx2][v];
+        const float top = __fmul_rn(__fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa)), ya1);
+        const float bot = __fmul_rn(__fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa)), ya);
+        s.eq[i] = (uint8_t)min(max(__float2int_rn(__fadd_rn(top, bot)), 0), 255);
+    }
+    __syncthreads();
+}
+
+// adaptiveThreshold(GAUSSIAN_C, BINARY, 11, 2) on the 28x28 CLAHE output, OpenCV's column classes
+// for W = 28 (x < 24: vector body; 24..27: 4x-unrolled scalar -> column pass without FMA).
+// thr (optional) = preprocess_cell's return; pm1 (optional) = (255 - thr)/255 normalised to -1/+1.
+__device__ __forceinline__ void threshold_phase(CellSmem &s, uint8_t *__restrict__ thr, float *__restrict__ pm1) {
+    const float k[11] = {SVB_G11_0, SVB_G11_1, SVB_G11_2, SVB_G11_3, SVB_G11_4, SVB_G11_5,
+                         SVB_G11_4, SVB_G11_3, SVB_G11_2, SVB_G11_1, SVB_G11_0};
+    for (int i = threadIdx.x; i < CELL * CELL; i += blockDim.x) {
+        const int y = i / CELL, x = i - y * CELL;
+        const uint8_t *row = s.eq + y * CELL;
+        float acc = __fmul_rn(k[0], (float)row[max(x - 5, 0)]);
+#pragma unroll
+        for (int t = 1; t < 11; ++t) acc = __fmaf_rn(k[t], (float)row[min(max(x - 5 + t, 0), CELL - 1)], acc);
+        s.rp[i] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CELL * CELL; i += blockDim.x) {
+        const int y = i / CELL, x = i - y * CELL;
+        float acc = __fmul_rn(k[5], s.rp[i]);
+#pragma unroll
+        for (int j = 1; j <= 5; ++j) {
+            const float sum = __fadd_rn(s.rp[min(y + j, CELL - 1) * CELL + x], s.rp[max(y - j, 0) * CELL + x]);
+            if (x < 24) acc = __fmaf_rn(k[5 + j], sum, acc);
+            else acc = __fadd_rn(acc, __fmul_rn(k[5 + j], sum));
+        }
+        const int mean = min(rint_pos(acc), 255);
+        const bool white = ((int)s.eq[i] - mean) > -2;  // THRESH_BINARY
+        if (thr) thr[i] = white ? 255 : 0;
+        if (pm1) pm1[i] = white ? -1.0f : 1.0f;  // invert, /255, (x - 0.5) / 0.5
+    }
+}
+
+// K4: one CTA per (frame, cell)
+__global__ void __launch_bounds__(NT)
+cells_from_frames_kernel(const uint8_t *__restrict__ bgr, int h, int w, const double *__restrict__ minv,
+                         const uint8_t *__restrict__ found, ResizeTab rt, uint8_t *__restrict__ cells_u8,
+                         float *__restrict__ cells_pm1) {
+    __shared__ CellSmem s;
+    const int f = blockIdx.y, cell = blockIdx.x;
+    const long long obase = ((long long)f * 81 + cell) * (CELL * CELL);
+    if (found && found[f] != 1) {
+        for (int i = threadIdx.x; i < CELL * CELL; i += blockDim.x) {
+            if (cells_u8) cells_u8[obase + i] = 0;
+            cells_pm1[obase + i] = 0.0f;
+        }
+        return;
+    }
+    const int r = cell / 9, c = cell - r * 9;
+    const int cs = BOARD / 9, margin = 5, cw = rt.src;  // 50, int(50*0.1), 40
+    const uint8_t *frame = bgr + (long long)f * h * w * 3;
+    __shared__ double mi[9];
+    if (threadIdx.x < 9) mi[threadIdx.x] = minv[(long long)f * 9 + threadIdx.x];
+    __syncthreads();
+    for (int i = threadIdx.x; i < cw * cw; i += blockDim.x) {
+        const int yy = i / cw, xx = i - yy * cw;
+        const Tap t = make_tap(mi, c * cs + margin + xx, r * cs + margin + yy, 64);
+        const uint32_t v = sample_bgr(frame, h, w, t);
+        s.crop[i] = (uint8_t)gray_of(v & 0xff, (v >> 8) & 0xff, (v >> 16) & 0xff);
+    }
+    __syncthreads();
+    resize_phase(s, rt);
+    __syncthreads();
+    if (cells_u8)
+        for (int i = threadIdx.x; i < CELL * CELL; i += blockDim.x) cells_u8[obase + i] = s.cell[i];
+    clahe_phase(s);
+    threshold_phase(s, nullptr, cells_pm1 + obase);
+}
+
+// drop-in extract_cells: board [n][size][size][3] -> cells
+__global__ void __launch_bounds__(NT)
+extract_cells_kernel(const uint8_t *__restrict__ board, int size, ResizeTab rt, uint8_t *__restrict__ cells) {
+    __shared__ CellSmem s;
+    const int f = blockIdx.y, cell = blockIdx.x;
+    const int r = cell / 9, c = cell - r * 9;
+    const int cs = size / 9, margin = (int)(cs * 0.1), cw = rt.src;
+    const uint8_t *b = board + (long long)f * size * size * 3;
+    for (int i = threadIdx.x; i < cw * cw; i += blockDim.x) {
+        const int yy = i / cw, xx = i - yy * cw;
+        const uint8_t *p = b + ((long long)(r * cs + margin + yy) * size + (c * cs + margin + xx)) * 3;
+        s.crop[i] = (uint8_t)gray_of(p[0], p[1], p[2]);
+    }
+    __syncthreads();
+    resize_phase(s, rt);
+    __syncthreads();
+    const long long obase = ((long long)f * 81 + cell) * (CELL * CELL);
+    for (int i = threadIdx.x; i < CELL * CELL; i += blockDim.x) cells[obase + i] = s.cell[i];
+}
+
+// drop-in preprocess_cell (+ tensor prep): cells [n][28][28]
+__global__ void __launch_bounds__(NT)
+cell_prep_kernel(const uint8_t *__restrict__ cells, uint8_t *__restrict__ thr, float *__restrict__ pm1) {
+    __shared__ CellSmem s;
+    const long long base = (long long)blockIdx.x * (CELL * CELL);
+    for (int i = threadIdx.x; i < CELL * CELL; i += blockDim.x) s.cell[i] = cells[base + i];
+    __syncthreads();
+    clahe_phase(s);
+    threshold_phase(s, thr ? thr + base : nullptr, pm1 ? pm1 + base : nullptr);
+}
+
+}  // namespace k4
+
+// ---- host side ---------------------------------------------------------------------------------------
+static bool make_resize_tab(int src, k4::ResizeTab *rt) {
+    if (src < 2 || src > 64 || src == 2 * k4::CELL) return false;  // 2x decimation takes cv2's INTER_AREA path
+    rt->src = src;
+    const double scale = (double)src / k4::CELL;
+    for (int d = 0; d < k4::CELL; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= (float)s;
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= src - 1) { s = src - 1; f = 0.f; }
+        rt->s0[d] = (short)s;
+        rt->a1[d] = (short)nearbyintf(f * 2048.f);
+        rt->a0[d] = (short)nearbyintf((1.f - f) * 2048.f);
+    }
+    return true;
+}
+
+static int homography(svb_ctx *ctx, const int32_t *corners, const uint8_t *found, int n, int out_size, double **minv,
+                      cudaStream_t st) {
+    if (ctx->arena[AR_HOMOG].reserve(sizeof(double) * 9 * (size_t)n) != SVB_OK) return SVB_ERR_CUDA;
+    *minv = (double *)ctx->arena[AR_HOMOG].ptr;
+    k4::homography_kernel<<<(n + 63) / 64, 64, 0, st>>>(corners, found, n, out_size, *minv);
+    return check_launch(ctx, "k4::homography_kernel");
+}
+
+int launch_warp_board(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, const int32_t *corners,
+                      const uint8_t *found, int out_size, uint8_t *board, cudaStream_t st) {
+    double *minv = nullptr;
+    int rc = homography(ctx, corners, found, n, out_size, &minv, st);
+    if (rc) return rc;
+    dim3 grid((out_size + 127) / 128, out_size, n);
+    k4::warp_board_kernel<<<grid, 128, 0, st>>>(bgr, h, w, minv, found, out_size, board);
+    return check_launch(ctx, "k4::warp_board_kernel");
+}
+
+int launch_extract_cells(svb_ctx *ctx, const uint8_t *board, int n, int size, uint8_t *cells, cudaStream_t st) {
+    const int cs = size / 9, margin = (int)(cs * 0.1), cw = cs - 2 * margin;
+    k4::ResizeTab rt;
+    SVB_REQUIRE(make_resize_tab(cw, &rt), SVB_ERR_UNSUPPORTED,
+                "extract_cells: crop size outside [2,64] or exactly 56 (cv2 switches to INTER_AREA) is not implemented");
+    dim3 grid(81, n);
+    k4::extract_cells_kernel<<<grid, k4::NT, 0, st>>>(board, size, rt, cells);
+    return check_launch(ctx, "k4::extract_cells_kernel");
+}
+
+int launch_cell_prep(svb_ctx *ctx, const uint8_t *cells, long long n_cells, uint8_t *thr, float *pm1, cudaStream_t st) {
+    SVB_REQUIRE(n_cells < (1ll << 31), SVB_ERR_INVALID, "cell_prep: too many cells for one launch");
+    k4::cell_prep_kernel<<<(unsigned)n_cells, k4::NT, 0, st>>>(cells, thr, pm1);
+    return check_launch(ctx, "k4::cell_prep_kernel");
+}
+
+// minv_out (optional): where the per-frame inverse homographies were put (for chaining)
+int launch_cells_from_frames(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, const int32_t *corners,
+                             const uint8_t *found, uint8_t *cells_u8, float *cells_pm1, cudaStream_t st) {
+    double *minv = nullptr;
+    int rc = homography(ctx, corners, found, n, k4::BOARD, &minv, st);
+    if (rc) return rc;
+    k4::ResizeTab rt;
+    make_resize_tab(40, &rt);
+    dim3 grid(81, n);
+    k4::cells_from_frames_kernel<<<grid, k4::NT, 0, st>>>(bgr, h, w, minv, found, rt, cells_u8, cells_pm1);
+    return check_launch(ctx, "k4::cells_from_frames_kernel");
+}
+
+}  // namespace svb

@@ -1,0 +1,198 @@
+// contour.cu — K2: find_grid_contour (cv/grid.py:37-71) for a batch of masks, without a labelling
+// pass.
+//
+// Observation: cv/grid.py only ever looks at contours whose area is >= min_area_ratio * H * W.
+// Such a component spans more than P = floor(sqrt(min_area)) pixels in x or y, so its outer border
+// crosses one of the "probe lines" x = kP or y = kP at a background->foreground transition.
+//
+//   K2a probe_trace_kernel   one thread per probe-line pixel.  A thread that sits on a bg->fg
+//        transition follows the border loop through that pixel (Suzuki-Abe order, entered with the
+//        known background neighbour as virtual predecessor, which lands on the same cyclic sequence
+//        cv2 produces), accumulating the shoelace area and the raster-first pixel.  Outer borders
+//        (orientation sign) with |area| >= min_area are appended to a per-frame candidate list.
+//        Thousands of traces per frame run concurrently; the stage is latency-bound (one L1/L2
+//        neighbourhood fetch per border pixel), not bandwidth-bound.
+//   K2b select_quad_kernel   one warp per frame.  De-duplicates candidates (same raster-first
+//        pixel), orders them as Python's stable sort does (area descending, ties in cv2's reverse
+//        raster order), re-traces each from its canonical start with CHAIN_APPROX_SIMPLE compression
+//        into scratch, rejects components nested inside another candidate's hole (RETR_EXTERNAL;
+//        winding number of the encloser's chain around the start pixel), computes arcLength and
+//        runs the closed-curve approxPolyDP with the 32 lanes sharing every farthest-point scan.
+//        The first 4-vertex polygon wins; otherwise found = 0 (the reference's None).
+#include "common.cuh"
+#include "contour_core.cuh"
+
+namespace svb {
+namespace k2 {
+
+using namespace contour;
+
+struct FrameScratch {
+    int *status;       // [n] bit0: candidate overflow, bit1: chain overflow, bit2: trace overflow, bit3: DP stack
+    int *keys;         // [n][MAXC] open-addressed set of candidate start pixels (-1 = empty)
+    Cand *cands;       // [n][MAXC] payload of the slot with the same index
+    uint32_t *chain;   // [n][cap]
+    uint32_t *poly;    // [n][cap]
+    int cap;
+};
+
+__global__ void reset_kernel(int *keys, int *status, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n * MAXC) keys[i] = -1;
+    if (i < n) status[i] = 0;
+}
+
+__global__ void __launch_bounds__(128)
+probe_trace_kernel(const uint8_t *__restrict__ mask, int h, int w, int pitch, int nv, int nh, double min_area,
+                   int max_steps, FrameScratch fs) {
+    const int frame = blockIdx.y;
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = nv * h + nh * w;
+    if (id >= total) return;
+    MaskView m{mask + (long long)frame * h * w, h, w};
+    int x, y, dv;
+    if (id < nv * h) {  // vertical probe line x = k*pitch, scanning down: background above
+        x = (id / h) * pitch;
+        y = id % h;
+        dv = DIR_N;
+        if (!m.fg(x, y) || m.fg(x, y - 1)) return;
+    } else {            // horizontal probe line y = k*pitch, scanning right: background to the left
+        const int j = id - nv * h;
+        y = (j / w) * pitch;
+        x = j % w;
+        dv = DIR_W;
+        if (!m.fg(x, y) || m.fg(x - 1, y)) return;
+    }
+    LoopStats st(w);
+    const int npts = trace_loop(m, x, y, dv, max_steps, st);
+    if (npts < 0) {
+        atomicOr(&fs.status[frame], 4);
+        return;
+    }
+    // Outer borders come out with negative signed area in image coordinates (y down); holes positive.
+    if (st.area2 >= 0) return;
+    const double area = (double)(-st.area2) * 0.5;
+    if (area < min_area) return;
+    // The same border is usually reached from several crossings: insert into a small open-addressed
+    // set keyed by the component's raster-first pixel, so duplicates cost nothing.
+    int *keys = fs.keys + (long long)frame * MAXC;
+    int slot = (int)(((unsigned)st.min_idx * 2654435761u) >> 27) & (MAXC - 1);
+    for (int probe = 0; probe < MAXC; ++probe) {
+        const int old = atomicCAS(&keys[slot], -1, st.min_idx);
+        if (old == st.min_idx) return;  // already recorded by another crossing of the same border
+        if (old == -1) {
+            Cand c;
+            c.area2 = -st.area2;
+            c.min_idx = st.min_idx;
+            c.pad = 0;
+            fs.cands[(long long)frame * MAXC + slot] = c;
+            return;
+        }
+        slot = (slot + 1) & (MAXC - 1);
+    }
+    atomicOr(&fs.status[frame], 1);
+}
+
+struct WarpReduce {
+    static __device__ __forceinline__ int lane() { return threadIdx.x & 31; }
+    static __device__ __forceinline__ int lanes() { return 32; }
+    static __device__ __forceinline__ void argmax_first(double &d, int &ord, int &idx) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, d, off);
+            const int oo = __shfl_xor_sync(0xffffffffu, ord, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+            if (od > d || (od == d && oo < ord)) {
+                d = od;
+                ord = oo;
+                idx = oi;
+            }
+        }
+    }
+    static __device__ __forceinline__ int bcast(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+    static __device__ __forceinline__ double bcast(double v) { return __shfl_sync(0xffffffffu, v, 0); }
+    static __device__ __forceinline__ void sync() { __syncwarp(); }
+};
+
+__global__ void __launch_bounds__(128)
+select_quad_kernel(const uint8_t *__restrict__ mask, int n, int h, int w, double eps_ratio, int max_steps,
+                   FrameScratch fs, int32_t *__restrict__ corners, uint8_t *__restrict__ found) {
+    __shared__ Slice stacks[4][STACK_CAP];
+    __shared__ Cand lists[4][MAXC];
+    __shared__ Cand raws[4][MAXC];
+    __shared__ int nested[4][MAXC];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int frame = blockIdx.x * 4 + warp;
+    if (frame >= n) return;
+    MaskView m{mask + (long long)frame * h * w, h, w};
+    int status = 0;
+    int32_t *out = corners + (long long)frame * 8;
+    // gather the occupied slots of this frame's candidate set (lane i looks at slots i and i+32 ...)
+    int nraw = 0;
+    for (int base = 0; base < MAXC; base += 32) {
+        const int slot = base + lane;
+        const bool occ = slot < MAXC && fs.keys[(long long)frame * MAXC + slot] != -1;
+        const unsigned bal = __ballot_sync(0xffffffffu, occ);
+        if (occ) raws[warp][nraw + __popc(bal & ((1u << lane) - 1))] = fs.cands[(long long)frame * MAXC + slot];
+        nraw += __popc(bal);
+    }
+    __syncwarp();
+    const int got = select_quad<WarpReduce>(m, raws[warp], nraw, lists[warp],
+                                            nested[warp], fs.chain + (long long)frame * fs.cap,
+                                            fs.poly + (long long)frame * fs.cap, fs.cap, stacks[warp], max_steps,
+                                            eps_ratio, out, &status);
+    if (lane == 0) {
+        status |= fs.status[frame];
+        // status != 0: a scratch capacity was hit -> report 2 so that the caller fails loudly
+        found[frame] = got ? 1 : (status ? 2 : 0);
+        fs.status[frame] = status;
+        if (!got)
+            for (int k = 0; k < 8; ++k) out[k] = 0;
+    }
+}
+
+}  // namespace k2
+
+int launch_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, int w, double min_area_ratio,
+                             double eps_ratio, int32_t *corners, uint8_t *found, cudaStream_t st) {
+    using namespace k2;
+    const double min_area = min_area_ratio * (double)((long long)h * w);
+    const int pitch = contour::probe_pitch(min_area);
+    const int nv = (w - 1) / pitch + 1, nh = (h - 1) / pitch + 1;
+    const long long total = (long long)nv * h + (long long)nh * w;
+    SVB_REQUIRE(total < (1ll << 30), SVB_ERR_UNSUPPORTED, "find_grid_contour: min_area_ratio too small for this image size");
+    int cap = 4 * (h + w);
+    cap = cap < 4096 ? 4096 : (cap > 65536 ? 65536 : cap);
+    const int max_steps = (int)min((long long)h * w * 2 + 16, (long long)1 << 26);
+
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return o;
+    };
+    const size_t o_cnt = take(sizeof(int) * (size_t)n * MAXC), o_st = take(sizeof(int) * n);
+    const size_t o_c = take(sizeof(Cand) * (size_t)n * MAXC);
+    const size_t o_ch = take(sizeof(uint32_t) * (size_t)n * cap), o_po = take(sizeof(uint32_t) * (size_t)n * cap);
+    if (ctx->arena[AR_CONTOUR].reserve(off) != SVB_OK) return SVB_ERR_CUDA;
+    char *base = (char *)ctx->arena[AR_CONTOUR].ptr;
+    FrameScratch fs;
+    fs.keys = (int *)(base + o_cnt);
+    fs.status = (int *)(base + o_st);
+    fs.cands = (Cand *)(base + o_c);
+    fs.chain = (uint32_t *)(base + o_ch);
+    fs.poly = (uint32_t *)(base + o_po);
+    fs.cap = cap;
+
+    reset_kernel<<<(n * MAXC + 255) / 256, 256, 0, st>>>(fs.keys, fs.status, n);
+    int rc = check_launch(ctx, "k2::reset_kernel");
+    if (rc) return rc;
+    dim3 grid((unsigned)((total + 127) / 128), n);
+    probe_trace_kernel<<<grid, 128, 0, st>>>(mask, h, w, pitch, nv, nh, min_area, max_steps, fs);
+    rc = check_launch(ctx, "k2::probe_trace_kernel");
+    if (rc) return rc;
+    select_quad_kernel<<<(n + 3) / 4, 128, 0, st>>>(mask, n, h, w, eps_ratio, max_steps, fs, corners, found);
+    return check_launch(ctx, "k2::select_quad_kernel");
+}
+
+}  // namespace svb

@@ -1,0 +1,442 @@
+// contour_core.cuh — border following, contour metrics and closed-curve Douglas-Peucker, written
+// as host+device inline functions so that the very same code that runs inside the CUDA kernels
+// (contour.cu) is unit-tested on the CPU (tests/helpers/contour_host.cpp) against the oracle.
+//
+// Semantics restated: cv2.findContours(RETR_EXTERNAL, CHAIN_APPROX_SIMPLE), cv2.contourArea,
+// cv2.arcLength, cv2.approxPolyDP as called from cv/grid.py:16-71.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SVB_HD __host__ __device__ __forceinline__
+#else
+#define SVB_HD inline
+#endif
+
+namespace svb {
+namespace contour {
+
+// neighbour directions, counter-clockwise on screen (y down): E,NE,N,NW,W,SW,S,SE
+SVB_HD int dir_dx(int d) { return (d == 0 || d == 1 || d == 7) ? 1 : ((d >= 3 && d <= 5) ? -1 : 0); }
+SVB_HD int dir_dy(int d) { return (d >= 1 && d <= 3) ? -1 : ((d >= 5) ? 1 : 0); }
+constexpr int DIR_N = 2, DIR_W = 4;
+
+struct MaskView {
+    const uint8_t *p;
+    int h, w;
+    SVB_HD bool fg(int x, int y) const {
+        return x >= 0 && y >= 0 && x < w && y < h && p[(long long)y * w + x] != 0;
+    }
+    // bit d set <=> neighbour of (x,y) in direction d is foreground
+    SVB_HD unsigned nbits(int x, int y) const {
+        unsigned b = 0;
+        const bool xl = x > 0, xr = x + 1 < w, yu = y > 0, yd = y + 1 < h;
+        const uint8_t *c = p + (long long)y * w + x;
+        if (xr && c[1]) b |= 1u << 0;
+        if (xl && c[-1]) b |= 1u << 4;
+        if (yu) {
+            const uint8_t *u = c - w;
+            if (u[0]) b |= 1u << 2;
+            if (xr && u[1]) b |= 1u << 1;
+            if (xl && u[-1]) b |= 1u << 3;
+        }
+        if (yd) {
+            const uint8_t *d = c + w;
+            if (d[0]) b |= 1u << 6;
+            if (xr && d[1]) b |= 1u << 7;
+            if (xl && d[-1]) b |= 1u << 5;
+        }
+        return b;
+    }
+};
+
+// first set direction scanning counter-clockwise starting just AFTER direction `from`;
+// nb must be non-zero.
+SVB_HD int next_ccw(unsigned nb, int from) {
+    unsigned rot = ((nb | (nb << 8)) >> ((from + 1) & 7)) & 0xffu;  // bit i <=> direction from+1+i
+#if defined(__CUDA_ARCH__)
+    int i = __ffs((int)rot) - 1;
+#else
+    int i = __builtin_ctz(rot);
+#endif
+    return (from + 1 + i) & 7;
+}
+// first set direction scanning clockwise starting AT direction `from`
+SVB_HD int first_cw(unsigned nb, int from) {
+    for (int t = 0; t < 8; ++t) {
+        int d = (from - t) & 7;
+        if (nb & (1u << d)) return d;
+    }
+    return -1;
+}
+
+// Follow the border loop that passes through foreground pixel (qx,qy) with a known background
+// (or out-of-image) neighbour in direction `dv` (N for a vertical probe, W for a horizontal probe
+// or a component's raster-first pixel).  Calls vis.point(x, y, din, dout) for every border pixel in
+// Suzuki-Abe order starting at (qx,qy); din/dout are the incoming/outgoing step directions (0..7),
+// or -1/-1 for an isolated pixel.  Returns the number of points, or -1 if max_steps was exceeded.
+template <class Visitor>
+SVB_HD int trace_loop(const MaskView &m, int qx, int qy, int dv, int max_steps, Visitor &vis) {
+    unsigned nb = m.nbits(qx, qy);
+    if (nb == 0) {
+        vis.point(qx, qy, -1, -1);
+        return 1;
+    }
+    const int m0 = next_ccw(nb, dv);  // first move
+    // last move of the loop arrives from the first foreground neighbour found clockwise from dv
+    const int dlast = first_cw(nb, dv);        // direction from q to its cyclic predecessor
+    int din = (dlast + 4) & 7;                 // step direction predecessor -> q
+    int x = qx, y = qy, dout = m0, n = 0;
+    for (;;) {
+        vis.point(x, y, din, dout);
+        if (++n > max_steps) return -1;
+        x += dir_dx(dout);
+        y += dir_dy(dout);
+        din = dout;
+        nb = m.nbits(x, y);
+        dout = next_ccw(nb, (din + 4) & 7);    // scan starts just after the pixel we came from
+        if (x == qx && y == qy && dout == m0) break;
+    }
+    return n;
+}
+
+// ---- visitors ---------------------------------------------------------------------------------
+// Probe pass: signed shoelace area (x2), raster-min pixel and length of the loop.
+struct LoopStats {
+    long long area2 = 0;  // sum over steps of (x_i * y_{i+1} - x_{i+1} * y_i)
+    int min_idx = 0x7fffffff;
+    int w;
+    SVB_HD explicit LoopStats(int w_) : w(w_) {}
+    SVB_HD void point(int x, int y, int /*din*/, int dout) {
+        int idx = y * w + x;
+        if (idx < min_idx) min_idx = idx;
+        if (dout >= 0) {
+            int nx = x + dir_dx(dout), ny = y + dir_dy(dout);
+            area2 += (long long)x * ny - (long long)nx * y;
+        }
+    }
+};
+
+// Chain pass: CHAIN_APPROX_SIMPLE (keep a pixel iff the step direction changes there), written as
+// packed (x | y << 16) points.  Also accumulates winding numbers of up to NT target points.
+template <int NT>
+struct ChainWriter {
+    uint32_t *pts;
+    int cap, n = 0;
+    bool overflow = false;
+    int ntargets = 0;
+    int tx[NT], ty[NT], wn[NT];
+    SVB_HD ChainWriter(uint32_t *p, int cap_) : pts(p), cap(cap_) {
+        for (int i = 0; i < NT; ++i) tx[i] = ty[i] = wn[i] = 0;
+    }
+    SVB_HD void point(int x, int y, int din, int dout) {
+        if (din != dout || din < 0) {
+            if (n < cap) pts[n] = (uint32_t)x | ((uint32_t)y << 16);
+            else overflow = true;
+            ++n;
+        }
+        if (dout >= 0) {
+            const int nx = x + dir_dx(dout), ny = y + dir_dy(dout);
+            for (int i = 0; i < NT; ++i) {
+                if (i >= ntargets) break;
+                // winding number of the pixel-centre polygon around (tx,ty), Sunday's rule
+                const long long is_left = (long long)(nx - x) * (ty[i] - y) - (long long)(tx[i] - x) * (ny - y);
+                if (y <= ty[i]) {
+                    if (ny > ty[i] && is_left > 0) ++wn[i];
+                } else {
+                    if (ny <= ty[i] && is_left < 0) --wn[i];
+                }
+            }
+        }
+    }
+};
+
+SVB_HD int pt_x(uint32_t p) { return (int)(p & 0xffffu); }
+SVB_HD int pt_y(uint32_t p) { return (int)(p >> 16); }
+
+// cv2.arcLength(closed=True): float sqrt per segment, accumulated in double, starting with the
+// closing segment (last -> first).
+SVB_HD double arc_length_closed(const uint32_t *P, int n) {
+    if (n <= 1) return 0.0;
+    double s = 0.0;
+    float px = (float)pt_x(P[n - 1]), py = (float)pt_y(P[n - 1]);
+    for (int i = 0; i < n; ++i) {
+        float x = (float)pt_x(P[i]), y = (float)pt_y(P[i]);
+        float dx = x - px, dy = y - py;
+#if defined(__CUDA_ARCH__)
+        s += (double)__fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+#else
+        s += (double)sqrtf(dx * dx + dy * dy);
+#endif
+        px = x;
+        py = y;
+    }
+    return s;
+}
+
+// ---- closed-curve approxPolyDP ------------------------------------------------------------------
+// Lane-cooperative: NL lanes scan index ranges in strides and reduce to the FIRST maximum (strict
+// '>' in index order, as cv2 does).  NL = 1 on the host.  `Red` supplies the reduction.
+struct SerialReduce {
+    static SVB_HD int lane() { return 0; }
+    static SVB_HD int lanes() { return 1; }
+    // among lanes, pick max d (ties: smallest ord); returns winner's (d, ord, idx) to all lanes
+    static SVB_HD void argmax_first(double &, int &, int &) {}
+    static SVB_HD int bcast(int v) { return v; }
+    static SVB_HD double bcast(double v) { return v; }
+    static SVB_HD void sync() {}
+};
+
+struct Slice {
+    int s, e;
+};
+
+// Farthest point of P[(s+1)..(e-1)] (cyclic) from segment P[s]P[e]; point-to-SEGMENT distance
+// squared in double.  ord = position along the scan (tie-break).  Returns max d2 and index.
+template <class Red>
+SVB_HD void dp_farthest(const uint32_t *P, int n, int s, int e, double &best, int &best_idx) {
+    const double ax = pt_x(P[s]), ay = pt_y(P[s]);
+    const double ex = pt_x(P[e]), ey = pt_y(P[e]);
+    const double dx = ex - ax, dy = ey - ay;
+    const double L = dx * dx + dy * dy;
+    int len = e - s;
+    if (len < 0) len += n;  // number of steps from s to e; interior points: len - 1
+    double b = 0.0;
+    int bord = 0x7fffffff, bidx = s;
+    for (int k = 1 + Red::lane(); k < len; k += Red::lanes()) {
+        int p = s + k;
+        if (p >= n) p -= n;
+        const double vx = pt_x(P[p]) - ax, vy = pt_y(P[p]) - ay;
+        const double dot = vx * dx + vy * dy;
+        double d2;
+        if (dot <= 0.0) d2 = vx * vx + vy * vy;
+        else if (dot >= L) {
+            const double wx = pt_x(P[p]) - ex, wy = pt_y(P[p]) - ey;
+            d2 = wx * wx + wy * wy;
+        } else {
+            const double cr = vy * dx - vx * dy;
+            d2 = cr * cr / L;
+        }
+        if (d2 > b) {
+            b = d2;
+            bord = k;
+            bidx = p;
+        }
+    }
+    Red::argmax_first(b, bord, bidx);
+    best = b;
+    best_idx = bidx;
+}
+
+// Returns the number of polygon vertices written to `out` (capacity >= n).  All lanes must call it
+// with identical arguments; lane 0 writes `out`.  `stack` holds 2*64 ints (per warp).
+template <class Red>
+SVB_HD int approx_poly_dp_closed(const uint32_t *P, int n, double eps, uint32_t *out, Slice *stack, int stack_cap,
+                                 bool *stack_overflow) {
+    if (n == 0) return 0;
+    const double eps2 = eps * eps;
+    // 1. three rounds of farthest-point seeding
+    int pos = 0, rs = 0;
+    double mx = 0.0;
+    for (int it = 0; it < 3; ++it) {
+        pos = pos + rs;
+        if (pos >= n) pos -= n;
+        const double sx = pt_x(P[pos]), sy = pt_y(P[pos]);
+        double b = 0.0;
+        int bord = 0x7fffffff, bidx = 0;
+        for (int j = 1 + Red::lane(); j < n; j += Red::lanes()) {
+            int q = pos + j;
+            if (q >= n) q -= n;
+            const double ddx = pt_x(P[q]) - sx, ddy = pt_y(P[q]) - sy;
+            const double d = ddx * ddx + ddy * ddy;
+            if (d > b) {
+                b = d;
+                bord = j;
+                bidx = j;
+            }
+        }
+        Red::argmax_first(b, bord, bidx);
+        mx = b;
+        rs = (b > 0.0) ? bidx : 0;
+    }
+    int m = 0;
+    if (mx <= eps2) {
+        if (Red::lane() == 0) out[0] = P[pos];
+        return 1;
+    }
+    // 2. iterative splitting with an explicit stack; (s,e) is processed before (e,s)
+    int sp = 0;
+    int e0 = pos + rs;
+    if (e0 >= n) e0 -= n;
+    stack[sp++] = Slice{e0, pos};
+    stack[sp++] = Slice{pos, e0};
+    while (sp > 0) {
+        const Slice sl = stack[--sp];
+        int nxt = sl.s + 1;
+        if (nxt >= n) nxt -= n;
+        if (nxt == sl.e) {
+            if (Red::lane() == 0) out[m] = P[sl.s];
+            ++m;
+            continue;
+        }
+        double best;
+        int r;
+        dp_farthest<Red>(P, n, sl.s, sl.e, best, r);
+        if (best <= eps2) {
+            if (Red::lane() == 0) out[m] = P[sl.s];
+            ++m;
+        } else {
+            if (sp + 2 > stack_cap) {
+                *stack_overflow = true;
+                return -1;
+            }
+            stack[sp++] = Slice{r, sl.e};
+            stack[sp++] = Slice{sl.s, r};
+        }
+    }
+    return m;
+}
+
+// 3. final clean-up of nearly collinear vertices, in place, exactly as cv2 walks the ring:
+// start_pt = last vertex, pt = first vertex, then each following vertex is end_pt.
+// Single lane.  Returns the new vertex count; the result occupies out[0..count).
+SVB_HD int approx_cleanup(uint32_t *out, int m, double eps) {
+    if (m < 3) return m;
+    const double eps2 = eps * eps;
+    const int count = m;
+    int new_count = m;
+    int rpos = count - 1, wpos;
+    int stx = pt_x(out[rpos]), sty = pt_y(out[rpos]);
+    if (++rpos >= count) rpos = 0;
+    wpos = rpos;
+    int ptx = pt_x(out[rpos]), pty = pt_y(out[rpos]);
+    if (++rpos >= count) rpos = 0;
+    for (int i = 0; i < count && new_count > 2; ++i) {
+        const int ex = pt_x(out[rpos]), ey = pt_y(out[rpos]);
+        if (++rpos >= count) rpos = 0;
+        const double dx = (double)ex - stx, dy = (double)ey - sty;
+        const double dist = fabs(((double)ptx - stx) * dy - ((double)pty - sty) * dx);
+        const double succ = ((double)ptx - stx) * ((double)ex - ptx) + ((double)pty - sty) * ((double)ey - pty);
+        if (dist * dist <= 0.5 * eps2 * (dx * dx + dy * dy) && dx != 0 && dy != 0 && succ >= 0) {
+            new_count--;
+            stx = ex;
+            sty = ey;
+            out[wpos] = (uint32_t)ex | ((uint32_t)ey << 16);
+            if (++wpos >= count) wpos = 0;
+            ptx = pt_x(out[rpos]);
+            pty = pt_y(out[rpos]);
+            if (++rpos >= count) rpos = 0;
+            i++;
+            continue;
+        }
+        stx = ptx;
+        sty = pty;
+        out[wpos] = (uint32_t)ptx | ((uint32_t)pty << 16);
+        if (++wpos >= count) wpos = 0;
+        ptx = ex;
+        pty = ey;
+    }
+    return new_count;
+}
+
+// ---- per-frame candidate selection (cv/grid.py:55-71) ------------------------------------------------
+struct Cand {
+    long long area2;  // |signed shoelace| x 2 of an outer border
+    int min_idx;      // raster index of the component's first pixel (canonical trace start)
+    int pad;
+};
+constexpr int MAXC = 64;       // candidate slots per frame (power of two)
+constexpr int MAXT = 8;        // winding-number targets tracked per trace
+constexpr int STACK_CAP = 96;  // DP slice stack
+// status bits: 1 candidate-list overflow, 2 chain overflow, 4 trace step overflow, 8 DP stack overflow
+
+// raw[0..raw_count): candidates as found by the probe pass (duplicates allowed).  list/nested: MAXC
+// scratch entries shared by the cooperating lanes.  Returns 1 and corners[8] if a 4-gon is found.
+template <class Red>
+SVB_HD int select_quad(const MaskView &m, const Cand *raw, int raw_count, Cand *list, int *nested, uint32_t *chain,
+                       uint32_t *poly, int cap, Slice *stack, int max_steps, double eps_ratio, int32_t *corners,
+                       int *status_out) {
+    const int lane = Red::lane();
+    const int w = m.w;
+    int nc = 0;
+    if (lane == 0) {
+        if (raw_count > MAXC) raw_count = MAXC;
+        for (int i = 0; i < raw_count; ++i) {  // de-duplicate: same component <=> same raster-first pixel
+            const Cand c = raw[i];
+            bool dup = false;
+            for (int j = 0; j < nc; ++j) dup |= (list[j].min_idx == c.min_idx);
+            if (!dup) list[nc++] = c;
+        }
+        // sorted(key=contourArea, reverse=True) is stable: equal areas keep cv2's order, which is
+        // reverse raster order of the start pixel (larger raster index first)
+        for (int i = 1; i < nc; ++i) {
+            const Cand c = list[i];
+            int j = i - 1;
+            while (j >= 0 && (list[j].area2 < c.area2 || (list[j].area2 == c.area2 && list[j].min_idx < c.min_idx))) {
+                list[j + 1] = list[j];
+                --j;
+            }
+            list[j + 1] = c;
+        }
+        for (int i = 0; i < nc; ++i) nested[i] = 0;
+    }
+    nc = Red::bcast(nc);
+    Red::sync();
+    int status = 0, got = 0;
+    for (int ci = 0; ci < nc && !got; ++ci) {
+        int npts = 0;
+        if (lane == 0) {
+            ChainWriter<MAXT> cw(chain, cap);
+            cw.ntargets = nc - ci - 1 < MAXT ? nc - ci - 1 : MAXT;
+            if (nc - ci - 1 > MAXT) status |= 1;
+            for (int k = 0; k < cw.ntargets; ++k) {
+                cw.tx[k] = list[ci + 1 + k].min_idx % w;
+                cw.ty[k] = list[ci + 1 + k].min_idx / w;
+            }
+            const int r = trace_loop(m, list[ci].min_idx % w, list[ci].min_idx / w, DIR_W, max_steps, cw);
+            if (r < 0) status |= 4;
+            if (cw.overflow) status |= 2;
+            npts = (r < 0 || cw.overflow) ? -1 : cw.n;
+            for (int k = 0; k < cw.ntargets; ++k)
+                if (cw.wn[k] != 0) nested[ci + 1 + k] = 1;  // start pixel lies inside this border
+        }
+        npts = Red::bcast(npts);
+        Red::sync();
+        if (npts < 0) break;        // scratch capacity hit: give up on this frame, status says why
+        if (nested[ci]) continue;   // inside another component's hole: RETR_EXTERNAL never returns it
+        double eps = 0.0;
+        if (lane == 0) eps = eps_ratio * arc_length_closed(chain, npts);
+        eps = Red::bcast(eps);
+        bool so = false;
+        int mv = approx_poly_dp_closed<Red>(chain, npts, eps, poly, stack, STACK_CAP, &so);
+        if (so) {
+            status |= 8;
+            break;
+        }
+        Red::sync();
+        if (lane == 0) mv = approx_cleanup(poly, mv, eps);
+        mv = Red::bcast(mv);
+        Red::sync();
+        if (mv == 4) {
+            got = 1;
+            if (lane == 0)
+                for (int k = 0; k < 4; ++k) {
+                    corners[2 * k] = pt_x(poly[k]);
+                    corners[2 * k + 1] = pt_y(poly[k]);
+                }
+        }
+    }
+    *status_out = status;
+    return got;
+}
+
+// Probe-line spacing: every component whose contour area reaches min_area spans more than
+// floor(sqrt(min_area)) pixels in x or in y, hence crosses a line x = k*P or y = k*P.
+SVB_HD int probe_pitch(double min_area) {
+    int p = (int)floor(sqrt(min_area));
+    return p < 1 ? 1 : p;
+}
+
+}  // namespace contour
+}  // namespace svb

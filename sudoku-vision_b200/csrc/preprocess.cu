@@ -1,0 +1,412 @@
+// preprocess.cu — P1..P4 of SURVEY.md §8a: cv/preprocess.py as sm_100a kernels.
+//
+//   * stage kernels (any image size): grayscale, 5x5 binomial blur, 11x11 Gaussian adaptive
+//     threshold — one launch each, used by the drop-in `grayscale/blur/threshold` functions;
+//   * K1, the fused row-streaming kernel: BGR -> gray -> blur5 -> gauss11 mean -> threshold -> mask
+//     in ONE pass over HBM (6.22 MB read + 2.07 MB written per 1080p frame, nothing else).
+//
+// Arithmetic is OpenCV's, bit for bit (oracle/svb_oracle.c states it):
+//   gray  = (3735 B + 19235 G + 9798 R + 2^14) >> 15
+//   blur5 = (sum_ij k_i k_j g + 128) >> 8, k = [1 4 6 4 1], BORDER_REFLECT_101
+//   mean  = rint( G11 (*) float(blur) ), sigma 2, BORDER_REPLICATE of the blurred image,
+//           row pass = FMA chain left to right, column pass = k5*c then fma(k[5+j], up+down, acc)
+//   mask  = 255 if blur - mean <= -2 (BINARY_INV) / > -2 (BINARY)
+#include "common.cuh"
+
+namespace svb {
+
+// ================================================================================================
+// Stage kernels (generic sizes; one thread per pixel; used by the stage-wise drop-in functions)
+// ================================================================================================
+__global__ void gray_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ gray, long long npix) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const uint8_t *p = bgr + 3 * i;
+    gray[i] = (uint8_t)gray_of(p[0], p[1], p[2]);
+}
+
+__global__ void blur5_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int h, int w) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    const uint8_t *img = src + (long long)blockIdx.z * h * w;
+    const int k[5] = {1, 4, 6, 4, 1};
+    int acc = 0;
+#pragma unroll
+    for (int dy = -2; dy <= 2; ++dy) {
+        const uint8_t *row = img + (long long)(h > 1 ? reflect101(y + dy, h) : 0) * w;
+        int s = 0;
+#pragma unroll
+        for (int dx = -2; dx <= 2; ++dx) s += k[dx + 2] * row[w > 1 ? reflect101(x + dx, w) : 0];
+        acc += k[dy + 2] * s;
+    }
+    dst[(long long)blockIdx.z * h * w + (long long)y * w + x] = (uint8_t)((acc + 128) >> 8);
+}
+
+// Row pass of the float Gaussian with OpenCV's column classes (see oracle/svb_oracle.c):
+//   x < W4 : FMA chain;  else: mul+add for taps 1..8, FMA for taps 9,10.
+__device__ __forceinline__ float g11_row(const uint8_t *row, int x, int w, int W4) {
+    const float k[11] = {SVB_G11_0, SVB_G11_1, SVB_G11_2, SVB_G11_3, SVB_G11_4, SVB_G11_5,
+                         SVB_G11_4, SVB_G11_3, SVB_G11_2, SVB_G11_1, SVB_G11_0};
+    float acc = __fmul_rn(k[0], (float)row[clampi(x - 5, 0, w - 1)]);
+#pragma unroll
+    for (int t = 1; t < 11; ++t) {
+        float v = (float)row[clampi(x - 5 + t, 0, w - 1)];
+        if (x < W4 || t >= 9) acc = __fmaf_rn(k[t], v, acc);
+        else acc = __fadd_rn(acc, __fmul_rn(k[t], v));
+    }
+    return acc;
+}
+
+__global__ void g11_rowpass_kernel(const uint8_t *__restrict__ src, float *__restrict__ rp, int h, int w) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    int W8 = w - (w % 8), W4 = (w - W8 >= 4) ? W8 + 4 : W8;
+    long long base = (long long)blockIdx.z * h * w;
+    rp[base + (long long)y * w + x] = g11_row(src + base + (long long)y * w, x, w, W4);
+}
+
+__global__ void g11_colpass_thresh_kernel(const uint8_t *__restrict__ src, const float *__restrict__ rp,
+                                          uint8_t *__restrict__ dst, int h, int w, int inverted) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    const float k[6] = {SVB_G11_5, SVB_G11_4, SVB_G11_3, SVB_G11_2, SVB_G11_1, SVB_G11_0};
+    int W8 = w - (w % 8);
+    long long base = (long long)blockIdx.z * h * w;
+    const float *r = rp + base;
+    float acc = __fmul_rn(k[0], r[(long long)y * w + x]);
+#pragma unroll
+    for (int j = 1; j <= 5; ++j) {
+        float s = __fadd_rn(r[(long long)clampi(y + j, 0, h - 1) * w + x], r[(long long)clampi(y - j, 0, h - 1) * w + x]);
+        if (x < W8) acc = __fmaf_rn(k[j], s, acc);
+        else acc = __fadd_rn(acc, __fmul_rn(k[j], s));
+    }
+    int mean = min(rint_pos(acc), 255);
+    int d = (int)src[base + (long long)y * w + x] - mean;
+    dst[base + (long long)y * w + x] = inverted ? (d <= -2 ? 255 : 0) : (d > -2 ? 255 : 0);
+}
+
+// ================================================================================================
+// K1 — fused, row-streaming preprocess.
+//
+// One CTA of 128 threads owns a vertical strip: 512 gray columns (480 output columns + 16-px
+// halo on each side) and walks down the rows R = 4 at a time.  Raw BGR row segments
+// (512 px * 3 B = 1536 B, 16-byte aligned because strips start at multiples of 16 px) are
+// staged into shared memory by TMA bulk copies (cp.async.bulk + mbarrier), three stages deep,
+// so HBM latency is hidden behind arithmetic.  Every thread owns 4 adjacent columns; the only
+// data exchanged between threads are the gray row (for the horizontal 5-tap) and the blurred row
+// (for the horizontal 11-tap) — two __syncthreads per 4 rows.  All vertical windows (hblur
+// ring, rowpass ring) are thread-private slices of shared memory, read back with 64/128-bit
+// loads, so nothing is recomputed vertically and HBM sees each byte once.
+// ================================================================================================
+namespace k1 {
+constexpr int NT = 128;               // threads per CTA
+constexpr int CPT = 4;                // columns per thread
+constexpr int GW = NT * CPT;          // 512 gray columns staged per strip
+constexpr int HALO = 16;              // px, each side (>= 7 needed; 16 keeps TMA 16-B aligned)
+constexpr int TW = GW - 2 * HALO;     // 480 output columns per strip
+constexpr int R = 4;                  // rows per block iteration
+constexpr int NSTAGE = 3;
+constexpr int RAW_ROW = GW * 3;       // bytes per staged row
+
+struct __align__(128) Smem {
+    uint8_t raw[NSTAGE][R][RAW_ROW];  // TMA destination (18 KB)
+    float4 rp[16][NT];                // rowpass ring, thread-private columns (32 KB)
+    uint2 hb[8][NT];                  // horizontal 5-tap sums (4 x u16), thread-private (8 KB)
+    uint32_t bx[16][NT];              // blurred rows, packed u8x4: ring + exchange (8 KB)
+    uint32_t g[R][NT];                // gray rows, packed u8x4: exchange (2 KB)
+    unsigned long long full[NSTAGE];  // mbarriers
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ float u8f(uint32_t word, int byte) { return (float)((word >> (8 * byte)) & 0xffu); }
+
+template <bool INVERTED>
+__global__ void __launch_bounds__(NT, 3)
+fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ mask, int h, int w, int rows_per_seg) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+
+    const int t = threadIdx.x;
+    const int X0 = blockIdx.x * TW;            // first output column of this strip
+    const int xg0 = X0 - HALO;                 // first staged gray column (may be negative)
+    const int ys = blockIdx.y * rows_per_seg;  // output rows [ys, ye)
+    const int ye = min(ys + rows_per_seg, h);
+    const long long frame_px = (long long)h * w;
+    const uint8_t *frame = bgr + (long long)blockIdx.z * frame_px * 3;
+    uint8_t *out = mask + (long long)blockIdx.z * frame_px;
+
+    const int bs = max(ys - 5, 0), be = min(ye + 5, h);  // blurred rows needed [bs, be)
+    const int gs = max(bs - 2, 0), ge = min(be + 2, h);  // gray rows needed    [gs, ge)
+    const int nblocks = (ge - gs + R - 1) / R;
+
+    // staged column range actually inside the image
+    const int col_lo = max(xg0, 0), col_hi = min(xg0 + GW, w);
+    const uint32_t row_bytes = (uint32_t)(col_hi - col_lo) * 3u;
+    const int dst_off = (col_lo - xg0) * 3;
+
+    if (t == 0) {
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&sm.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int blk) {
+        if (blk >= nblocks) return;
+        const int stage = blk % NSTAGE;
+        const int r0 = gs + blk * R;
+        const int nrows = min(R, ge - r0);
+        mbar_expect_tx(&sm.full[stage], row_bytes * (uint32_t)nrows);
+        for (int r = 0; r < nrows; ++r)
+            tma_load_1d(&sm.raw[stage][r][dst_off], frame + ((long long)(r0 + r) * w + col_lo) * 3, row_bytes,
+                        &sm.full[stage]);
+    };
+    if (t == 0) {
+        issue(0);
+        issue(1);
+    }
+
+    // my 4 columns
+    const int c0 = xg0 + CPT * t;
+    const bool cols_inside = (c0 >= 0) && (c0 + CPT <= w);
+    const bool edge_strip = (xg0 < 0) || (xg0 + GW > w);
+    // thread / byte that holds image column 0 and w-1 (for BORDER_REPLICATE of the blurred row)
+    const int t_left = (0 - xg0) / CPT;
+    const int t_right = (w - 1 - xg0) / CPT;
+    const bool is_out = (t >= 2) && (t < NT - 2) && (c0 >= X0) && (c0 < min(X0 + TW, w));
+
+    const float kf[6] = {SVB_G11_0, SVB_G11_1, SVB_G11_2, SVB_G11_3, SVB_G11_4, SVB_G11_5};
+
+    int b_next = bs;  // next blurred row to produce
+    int y_next = ys;  // next output row to produce
+
+    for (int blk = 0; blk < nblocks; ++blk) {
+        const int stage = blk % NSTAGE;
+        const int r0 = gs + blk * R;
+        const int nrows = min(R, ge - r0);
+        if (t == 0) issue(blk + 2);
+        mbar_wait(&sm.full[stage], (uint32_t)((blk / NSTAGE) & 1));
+
+        // ---- phase 1: raw BGR -> gray (packed u8x4) ------------------------------------------
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (r < nrows) {
+                uint32_t gq;
+                if (cols_inside) {
+                    const uint32_t *p = reinterpret_cast<const uint32_t *>(&sm.raw[stage][r][12 * t]);
+                    uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
+                    uint32_t g0 = gray_of(w0 & 0xff, (w0 >> 8) & 0xff, (w0 >> 16) & 0xff);
+                    uint32_t g1 = gray_of(w0 >> 24, w1 & 0xff, (w1 >> 8) & 0xff);
+                    uint32_t g2 = gray_of((w1 >> 16) & 0xff, w1 >> 24, w2 & 0xff);
+                    uint32_t g3 = gray_of((w2 >> 8) & 0xff, (w2 >> 16) & 0xff, w2 >> 24);
+                    gq = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+                } else {
+                    gq = 0;  // columns outside the image: BORDER_REFLECT_101 of the gray row
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) {
+                        int c = c0 + j;
+                        int cc = (c < 0) ? -c : ((c >= w) ? 2 * (w - 1) - c : c);
+                        cc = clampi(cc, col_lo, col_hi - 1);
+                        const uint8_t *p = &sm.raw[stage][r][(cc - xg0) * 3];
+                        gq |= gray_of(p[0], p[1], p[2]) << (8 * j);
+                    }
+                }
+                sm.g[r][t] = gq;
+            }
+        }
+        __syncthreads();  // (A) gray rows visible
+
+        // ---- phase 2: horizontal 5-tap on gray -> hb ring (u16 x 4) ----------------------------
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (r < nrows) {
+                uint32_t gl = sm.g[r][max(t - 1, 0)], gc = sm.g[r][t], gr = sm.g[r][min(t + 1, NT - 1)];
+                // bytes: v[0..1] = last two of left word, v[2..5] = centre, v[6..7] = first two of right
+                uint32_t v[8];
+                v[0] = (gl >> 16) & 0xff; v[1] = gl >> 24;
+                v[2] = gc & 0xff; v[3] = (gc >> 8) & 0xff; v[4] = (gc >> 16) & 0xff; v[5] = gc >> 24;
+                v[6] = gr & 0xff; v[7] = (gr >> 8) & 0xff;
+                uint32_t hsum[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hsum[j] = v[j] + v[j + 4] + 4u * (v[j + 1] + v[j + 3]) + 6u * v[j + 2];
+                sm.hb[(r0 + r) & 7][t] = make_uint2(hsum[0] | (hsum[1] << 16), hsum[2] | (hsum[3] << 16));
+            }
+        }
+
+        // ---- phase 3: vertical 5-tap -> blurred rows (packed u8x4) into the bx ring -------------
+        const int r_hi = r0 + nrows - 1;                          // newest gray row available
+        const int b_hi = (r_hi >= h - 1) ? (be - 1) : min(be - 1, r_hi - 2);
+        const int b_first = b_next;
+        for (int b = b_first; b <= b_hi; ++b) {
+            uint2 a0 = sm.hb[reflect101(b - 2, h) & 7][t];
+            uint2 a1 = sm.hb[reflect101(b - 1, h) & 7][t];
+            uint2 a2 = sm.hb[b & 7][t];
+            uint2 a3 = sm.hb[reflect101(b + 1, h) & 7][t];
+            uint2 a4 = sm.hb[reflect101(b + 2, h) & 7][t];
+            // packed 2 x u16 arithmetic: max lane value 16*4080 + 128 = 65408 < 65536
+            uint32_t lo = a0.x + a4.x + 4u * (a1.x + a3.x) + 6u * a2.x + 0x00800080u;
+            uint32_t hi = a0.y + a4.y + 4u * (a1.y + a3.y) + 6u * a2.y + 0x00800080u;
+            // >> 8 per lane and pack to u8x4: bytes 1,3 of lo and 1,3 of hi
+            sm.bx[b & 15][t] = __byte_perm(lo, hi, 0x7531);
+        }
+        b_next = b_hi + 1;
+        __syncthreads();  // (B) blurred rows visible
+        if (edge_strip) {
+            // BORDER_REPLICATE of the blurred image in x: columns < 0 take column 0, >= w take w-1
+            for (int b = b_first; b <= b_hi; ++b) {
+                if (c0 < 0) {
+                    uint32_t e = sm.bx[b & 15][t_left] & 0xffu;
+                    sm.bx[b & 15][t] = e * 0x01010101u;
+                } else if (c0 >= w) {
+                    uint32_t e = sm.bx[b & 15][t_right] >> 24;
+                    sm.bx[b & 15][t] = e * 0x01010101u;
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- phase 4: horizontal 11-tap (float FMA chain) -> rowpass ring ------------------------
+        if (is_out) {
+            for (int b = b_first; b <= b_hi; ++b) {
+                const uint32_t *brow = sm.bx[b & 15];
+                uint32_t q0 = brow[t - 2], q1 = brow[t - 1], q2 = brow[t], q3 = brow[t + 1], q4 = brow[t + 2];
+                // f[i] = blurred column (4t - 5 + i), i = 0..13
+                float f[14];
+                f[0] = u8f(q0, 3);
+                f[1] = u8f(q1, 0); f[2] = u8f(q1, 1); f[3] = u8f(q1, 2); f[4] = u8f(q1, 3);
+                f[5] = u8f(q2, 0); f[6] = u8f(q2, 1); f[7] = u8f(q2, 2); f[8] = u8f(q2, 3);
+                f[9] = u8f(q3, 0); f[10] = u8f(q3, 1); f[11] = u8f(q3, 2); f[12] = u8f(q3, 3);
+                f[13] = u8f(q4, 0);
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float acc = __fmul_rn(kf[0], f[j]);
+                    acc = __fmaf_rn(kf[1], f[j + 1], acc);
+                    acc = __fmaf_rn(kf[2], f[j + 2], acc);
+                    acc = __fmaf_rn(kf[3], f[j + 3], acc);
+                    acc = __fmaf_rn(kf[4], f[j + 4], acc);
+                    acc = __fmaf_rn(kf[5], f[j + 5], acc);
+                    acc = __fmaf_rn(kf[4], f[j + 6], acc);
+                    acc = __fmaf_rn(kf[3], f[j + 7], acc);
+                    acc = __fmaf_rn(kf[2], f[j + 8], acc);
+                    acc = __fmaf_rn(kf[1], f[j + 9], acc);
+                    acc = __fmaf_rn(kf[0], f[j + 10], acc);
+                    o[j] = acc;
+                }
+                sm.rp[b & 15][t] = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+
+        // ---- phase 5: vertical 11-tap (symmetric FMA) + rint + threshold -> mask -------------------
+        const int b_last = b_hi;
+        const int y_hi = (b_last >= h - 1) ? (ye - 1) : min(ye - 1, b_last - 5);
+        if (is_out) {
+            for (int y = y_next; y <= y_hi; ++y) {
+                float4 c = sm.rp[y & 15][t];
+                float a0 = __fmul_rn(kf[5], c.x), a1 = __fmul_rn(kf[5], c.y), a2 = __fmul_rn(kf[5], c.z), a3 = __fmul_rn(kf[5], c.w);
+#pragma unroll
+                for (int j = 1; j <= 5; ++j) {
+                    float4 u = sm.rp[clampi(y + j, 0, h - 1) & 15][t];
+                    float4 d = sm.rp[clampi(y - j, 0, h - 1) & 15][t];
+                    const float kk = kf[5 - j];
+                    a0 = __fmaf_rn(kk, __fadd_rn(u.x, d.x), a0);
+                    a1 = __fmaf_rn(kk, __fadd_rn(u.y, d.y), a1);
+                    a2 = __fmaf_rn(kk, __fadd_rn(u.z, d.z), a2);
+                    a3 = __fmaf_rn(kk, __fadd_rn(u.w, d.w), a3);
+                }
+                uint32_t src = sm.bx[y & 15][t];
+                int m0 = rint_pos(a0), m1 = rint_pos(a1), m2 = rint_pos(a2), m3 = rint_pos(a3);
+                // BINARY_INV: 255 iff src - mean <= -2 ; BINARY: 255 iff src - mean > -2
+                bool p0 = (int)(src & 0xff) - m0 <= -2, p1 = (int)((src >> 8) & 0xff) - m1 <= -2;
+                bool p2 = (int)((src >> 16) & 0xff) - m2 <= -2, p3 = (int)(src >> 24) - m3 <= -2;
+                if (!INVERTED) { p0 = !p0; p1 = !p1; p2 = !p2; p3 = !p3; }
+                uint32_t o = (p0 ? 0xffu : 0u) | (p1 ? 0xff00u : 0u) | (p2 ? 0xff0000u : 0u) | (p3 ? 0xff000000u : 0u);
+                *reinterpret_cast<uint32_t *>(out + (long long)y * w + c0) = o;
+            }
+        }
+        y_next = y_hi + 1;
+        // next iteration's phase 1 writes sm.g, whose readers (phase 2) all passed barrier (B).
+    }
+}
+}  // namespace k1
+
+// ================================================================================================
+// Host launchers
+// ================================================================================================
+int launch_gray(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *gray, cudaStream_t st) {
+    long long npix = (long long)n * h * w;
+    int threads = 256;
+    long long blocks = (npix + threads - 1) / threads;
+    gray_kernel<<<(unsigned)blocks, threads, 0, st>>>(bgr, gray, npix);
+    return check_launch(ctx, "gray_kernel");
+}
+
+int launch_blur5(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uint8_t *dst, cudaStream_t st) {
+    dim3 grid((w + 127) / 128, h, n);
+    blur5_kernel<<<grid, 128, 0, st>>>(src, dst, h, w);
+    return check_launch(ctx, "blur5_kernel");
+}
+
+int launch_adaptive(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, int inverted, uint8_t *dst, cudaStream_t st) {
+    size_t need = (size_t)n * h * w * sizeof(float);
+    if (ctx->arena[AR_ADAPT].reserve(need) != SVB_OK) return SVB_ERR_CUDA;
+    float *rp = (float *)ctx->arena[AR_ADAPT].ptr;
+    dim3 grid((w + 127) / 128, h, n);
+    g11_rowpass_kernel<<<grid, 128, 0, st>>>(src, rp, h, w);
+    int rc = check_launch(ctx, "g11_rowpass_kernel");
+    if (rc) return rc;
+    g11_colpass_thresh_kernel<<<grid, 128, 0, st>>>(src, rp, dst, h, w, inverted);
+    return check_launch(ctx, "g11_colpass_thresh_kernel");
+}
+
+bool fused_preprocess_supported(int h, int w) { return (w % 16 == 0) && w >= 64 && h >= 8; }
+
+int launch_fused_preprocess(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *mask, cudaStream_t st) {
+    using namespace k1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SVB_CUDA_OK(cudaFuncSetAttribute(fused_preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(Smem)));
+        attr_set = true;
+    }
+    const int nstrips = (w + TW - 1) / TW;
+    // enough CTAs to fill the machine ~4x over; segments no shorter than 64 rows (14-row warm-up)
+    int want = (ctx->sm_count * 3 * 4 + nstrips * n - 1) / (nstrips * n);
+    int nseg = max(1, min(want, h / 64));
+    int rows_per_seg = (h + nseg - 1) / nseg;
+    nseg = (h + rows_per_seg - 1) / rows_per_seg;
+    dim3 grid(nstrips, nseg, n);
+    fused_preprocess_kernel<true><<<grid, NT, sizeof(Smem), st>>>(bgr, mask, h, w, rows_per_seg);
+    return check_launch(ctx, "fused_preprocess_kernel");
+}
+
+}  // namespace svb

@@ -1,0 +1,250 @@
+"""Batched device-resident API over the C ABI.  Tensors in, tensors out, everything on the caller's
+current CUDA stream; nothing here computes — it only passes pointers."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_WEIGHT_KEYS = ("conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias",
+                "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias")
+_WEIGHT_SHAPES = ((32, 1, 3, 3), (32,), (64, 32, 3, 3), (64,), (128, 3136), (128,), (10, 128), (10,))
+
+
+def default_weights_path() -> str:
+    return os.path.join(_HERE, "weights", "digitcnn_synth.npz")
+
+
+def load_digitcnn_weights(path: str | None = None) -> dict:
+    """state_dict-shaped dict of float32 numpy arrays (keys of ml/model.py:22-32)."""
+    z = np.load(path or default_weights_path())
+    return {k: np.ascontiguousarray(z[k], dtype=np.float32) for k in _WEIGHT_KEYS}
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Scanner:
+    """One context per (process, device): owns scratch and packed weights inside the library."""
+
+    def __init__(self, device: int | None = None, weights: dict | None = None):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.SvbError("svb200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        h = C.c_void_p()
+        _lib.check(self.lib.svb_create(self.device, C.byref(h)), "svb_create")
+        self._h = h
+        self._weights_dev = None
+        if weights is not None:
+            self.load_weights(weights)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.svb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self):
+        return _torch().device("cuda", self.device)
+
+    def _chk_u8(self, t, ndim, what):
+        torch = _torch()
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous()
+                and t.dim() == ndim and t.device.index == self.device):
+            raise ValueError(f"{what}: expected a contiguous uint8 CUDA tensor with {ndim} dims on cuda:{self.device}")
+        return t
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.svb_launch_count(self._h))
+
+    STAGES = ("k1_preprocess", "k2_contour", "k34_cells", "k5_classifier")
+
+    def stage_timing(self, enable: bool = True):
+        _lib.check(self.lib.svb_stage_timing(self._h, int(enable)), "svb_stage_timing")
+
+    def last_stage_ms(self) -> dict:
+        ms = (C.c_float * 4)()
+        _lib.check(self.lib.svb_last_stage_ms(self._h, ms), "svb_last_stage_ms")
+        return dict(zip(self.STAGES, [float(x) for x in ms]))
+
+    # -- classifier ------------------------------------------------------------------------------
+    def load_weights(self, sd: dict):
+        """sd: mapping with the parameter names of ml/model.py (numpy arrays or torch tensors)."""
+        torch = _torch()
+        ts = []
+        for k, shp in zip(_WEIGHT_KEYS, _WEIGHT_SHAPES):
+            v = sd[k]
+            t = v.detach() if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v))
+            t = t.to(device=self._dev(), dtype=torch.float32).contiguous()
+            if tuple(t.shape) != shp:
+                raise ValueError(f"{k}: expected shape {shp}, got {tuple(t.shape)}")
+            ts.append(t)
+        _lib.check(self.lib.svb_digitcnn_load(self._h, *[_ptr(t) for t in ts], self._stream()), "svb_digitcnn_load")
+        self._weights_dev = ts  # keep alive until the pack kernel has run
+        return self
+
+    def digitcnn_forward(self, x, want_digits: bool = False):
+        """x: (B,1,28,28) float32 CUDA -> logits (B,10) [, digits (B,) u8, conf (B,) f32]."""
+        torch = _torch()
+        x = x.to(device=self._dev(), dtype=torch.float32).contiguous()
+        n = x.shape[0]
+        logits = torch.empty((n, 10), dtype=torch.float32, device=x.device)
+        digits = torch.empty((n,), dtype=torch.uint8, device=x.device) if want_digits else None
+        conf = torch.empty((n,), dtype=torch.float32, device=x.device) if want_digits else None
+        _lib.check(self.lib.svb_digitcnn_forward(self._h, _ptr(x), n, _ptr(logits), _ptr(digits), _ptr(conf),
+                                                 self._stream()), "svb_digitcnn_forward")
+        return (logits, digits, conf) if want_digits else logits
+
+    # -- image stages (batched, device tensors) --------------------------------------------------
+    def grayscale(self, bgr):
+        self._chk_u8(bgr, 4, "grayscale")
+        n, h, w, _ = bgr.shape
+        out = _torch().empty((n, h, w), dtype=_torch().uint8, device=bgr.device)
+        _lib.check(self.lib.svb_grayscale(self._h, _ptr(bgr), n, h, w, _ptr(out), self._stream()), "svb_grayscale")
+        return out
+
+    def blur(self, gray, ksize: int = 5):
+        self._chk_u8(gray, 3, "blur")
+        n, h, w = gray.shape
+        out = _torch().empty_like(gray)
+        _lib.check(self.lib.svb_blur(self._h, _ptr(gray), n, h, w, int(ksize), _ptr(out), self._stream()), "svb_blur")
+        return out
+
+    def adaptive_threshold(self, gray, block_size: int = 11, c: int = 2, inverted: bool = True):
+        self._chk_u8(gray, 3, "adaptive_threshold")
+        n, h, w = gray.shape
+        out = _torch().empty_like(gray)
+        _lib.check(self.lib.svb_adaptive_threshold(self._h, _ptr(gray), n, h, w, int(block_size), int(c),
+                                                   int(bool(inverted)), _ptr(out), self._stream()),
+                   "svb_adaptive_threshold")
+        return out
+
+    def preprocess(self, bgr, out=None):
+        self._chk_u8(bgr, 4, "preprocess")
+        n, h, w, _ = bgr.shape
+        if out is None:
+            out = _torch().empty((n, h, w), dtype=_torch().uint8, device=bgr.device)
+        _lib.check(self.lib.svb_preprocess_v1(self._h, _ptr(bgr), n, h, w, _ptr(out), self._stream()),
+                   "svb_preprocess_v1")
+        return out
+
+    def find_grid_contour(self, mask, min_area_ratio: float = 0.1, eps_ratio: float = 0.02):
+        self._chk_u8(mask, 3, "find_grid_contour")
+        torch = _torch()
+        n, h, w = mask.shape
+        corners = torch.empty((n, 4, 2), dtype=torch.int32, device=mask.device)
+        found = torch.empty((n,), dtype=torch.uint8, device=mask.device)
+        _lib.check(self.lib.svb_find_grid_contour(self._h, _ptr(mask), n, h, w, float(min_area_ratio),
+                                                  float(eps_ratio), _ptr(corners), _ptr(found), self._stream()),
+                   "svb_find_grid_contour")
+        return corners, found
+
+    def warp_perspective(self, bgr, corners, found=None, out_size: int = 450):
+        self._chk_u8(bgr, 4, "warp_perspective")
+        torch = _torch()
+        n, h, w, _ = bgr.shape
+        corners = corners.to(device=bgr.device, dtype=torch.int32).contiguous()
+        board = torch.empty((n, out_size, out_size, 3), dtype=torch.uint8, device=bgr.device)
+        _lib.check(self.lib.svb_warp_perspective(self._h, _ptr(bgr), n, h, w, _ptr(corners), _ptr(found),
+                                                 int(out_size), _ptr(board), self._stream()), "svb_warp_perspective")
+        return board
+
+    def extract_cells(self, board):
+        self._chk_u8(board, 4, "extract_cells")
+        torch = _torch()
+        n, s, s2, ch = board.shape
+        if s != s2 or ch != 3:
+            raise ValueError("extract_cells: board must be (n, S, S, 3)")
+        cells = torch.empty((n, 81, 28, 28), dtype=torch.uint8, device=board.device)
+        _lib.check(self.lib.svb_extract_cells(self._h, _ptr(board), n, s, _ptr(cells), self._stream()),
+                   "svb_extract_cells")
+        return cells
+
+    def cell_prep(self, cells, want_thresh: bool = True, want_pm1: bool = True):
+        torch = _torch()
+        if not (cells.is_cuda and cells.dtype == torch.uint8 and cells.is_contiguous() and cells.shape[-2:] == (28, 28)):
+            raise ValueError("cell_prep: expected contiguous uint8 CUDA cells (..., 28, 28)")
+        n = cells.numel() // 784
+        thr = torch.empty_like(cells) if want_thresh else None
+        pm1 = torch.empty(cells.shape, dtype=torch.float32, device=cells.device) if want_pm1 else None
+        _lib.check(self.lib.svb_cell_prep(self._h, _ptr(cells), n, _ptr(thr), _ptr(pm1), self._stream()), "svb_cell_prep")
+        return thr, pm1
+
+    def cells_from_frames(self, bgr, corners, found=None, want_u8: bool = True):
+        self._chk_u8(bgr, 4, "cells_from_frames")
+        torch = _torch()
+        n, h, w, _ = bgr.shape
+        corners = corners.to(device=bgr.device, dtype=torch.int32).contiguous()
+        u8 = torch.empty((n, 81, 28, 28), dtype=torch.uint8, device=bgr.device) if want_u8 else None
+        pm1 = torch.empty((n, 81, 28, 28), dtype=torch.float32, device=bgr.device)
+        _lib.check(self.lib.svb_cells_from_frames(self._h, _ptr(bgr), n, h, w, _ptr(corners), _ptr(found), _ptr(u8),
+                                                  _ptr(pm1), self._stream()), "svb_cells_from_frames")
+        return u8, pm1
+
+    # -- whole path ------------------------------------------------------------------------------
+    def alloc_outputs(self, n: int, want_logits: bool = False):
+        torch = _torch()
+        dev = self._dev()
+        return dict(
+            digits=torch.empty((n, 81), dtype=torch.uint8, device=dev),
+            conf=torch.empty((n, 81), dtype=torch.float32, device=dev),
+            logits=torch.empty((n, 81, 10), dtype=torch.float32, device=dev) if want_logits else None,
+            corners=torch.empty((n, 4, 2), dtype=torch.int32, device=dev),
+            found=torch.empty((n,), dtype=torch.uint8, device=dev),
+        )
+
+    def scan_batch(self, bgr, out: dict | None = None, want_logits: bool = False) -> dict:
+        """pipeline/run.py:257-318 for a device-resident batch (n,H,W,3) u8.  Asynchronous."""
+        self._chk_u8(bgr, 4, "scan_batch")
+        n, h, w, _ = bgr.shape
+        if out is None:
+            out = self.alloc_outputs(n, want_logits)
+        _lib.check(self.lib.svb_scan_batch_v1(self._h, _ptr(bgr), n, h, w, _ptr(out["digits"]), _ptr(out["conf"]),
+                                              _ptr(out.get("logits")), _ptr(out["corners"]), _ptr(out["found"]),
+                                              self._stream()), "svb_scan_batch_v1")
+        return out
+
+    def scan_batch_host(self, frames: np.ndarray, out: dict | None = None) -> dict:
+        """Same through HOST buffers (numpy or pinned torch CPU tensors): H2D + path + D2H, synchronous."""
+        torch = _torch()
+        if isinstance(frames, torch.Tensor):
+            assert frames.device.type == "cpu" and frames.dtype == torch.uint8 and frames.is_contiguous()
+            n, h, w, _ = frames.shape
+            src = C.c_void_p(frames.data_ptr())
+        else:
+            frames = np.ascontiguousarray(frames, dtype=np.uint8)
+            n, h, w, _ = frames.shape
+            src = frames.ctypes.data_as(C.c_void_p)
+        if out is None:
+            out = dict(digits=np.empty((n, 81), np.uint8), conf=np.empty((n, 81), np.float32),
+                       corners=np.empty((n, 4, 2), np.int32), found=np.empty((n,), np.uint8))
+
+        def hp(a):
+            return C.c_void_p(a.data_ptr()) if isinstance(a, torch.Tensor) else a.ctypes.data_as(C.c_void_p)
+
+        _lib.check(self.lib.svb_scan_batch_v1_host(self._h, src, n, h, w, hp(out["digits"]), hp(out["conf"]),
+                                                   hp(out["corners"]), hp(out["found"])), "svb_scan_batch_v1_host")
+        return out

@@ -1,0 +1,84 @@
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "sudoku-vision_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+def has_cuda() -> bool:
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as O
+
+    O.build()
+    return O
+
+
+@pytest.fixture(scope="session")
+def golden():
+    def load(name):
+        return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+    return load
+
+
+@pytest.fixture(scope="session")
+def contour_host():
+    """The product's contour core (csrc/contour_core.cuh) compiled for the host: tests/helpers."""
+    import ctypes as C
+
+    src = os.path.join(ROOT, "tests", "helpers", "contour_host.cpp")
+    out_dir = os.path.join(ROOT, "tests", "helpers", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libcontour_host.so")
+    dep = os.path.join(PKG, "csrc", "contour_core.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(dep)):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-ffp-contract=off", "-o", so, src])
+    lib = C.CDLL(so)
+
+    def find(mask, min_area_ratio=0.1, eps_ratio=0.02):
+        mask = np.ascontiguousarray(mask, np.uint8)
+        c = np.zeros((4, 2), np.int32)
+        f = lib.svbh_find_grid_contour(mask.ctypes.data_as(C.c_void_p), mask.shape[0], mask.shape[1],
+                                       C.c_double(min_area_ratio), C.c_double(eps_ratio),
+                                       c.ctypes.data_as(C.c_void_p), None, None)
+        return f, c
+
+    return find
+
+
+@pytest.fixture(scope="session")
+def scanner():
+    if not has_cuda():
+        pytest.skip("no CUDA device")
+    from svb200 import Scanner, load_digitcnn_weights
+
+    return Scanner(weights=load_digitcnn_weights())
+
+
+@pytest.fixture(scope="session")
+def weights():
+    from svb200 import load_digitcnn_weights
+
+    return load_digitcnn_weights()

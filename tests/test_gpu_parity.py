@@ -1,0 +1,312 @@
+"""GPU tier (-m gpu): every CUDA kernel, called through the C ABI, against the CPU oracle on the same
+seeded inputs and against the golden fixtures.  Bit-exact for all integer/byte/index stages;
+logits within 1e-3 absolute (fp32, the north star's tolerance)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1e-3
+
+
+def _t(a):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _frames(n, h, w, seed, rot=15.0):
+    from svb200 import frames as F
+
+    return F.make_frames(n, h, w, base_seed=seed, max_rot_deg=rot)
+
+
+# ---- P1..P4 ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hw", [(28, 28), (37, 53), (64, 80), (45, 66), (120, 168)])
+def test_stage_kernels_any_size(scanner, oracle, hw):
+    rng = np.random.default_rng(hw[0] * 7 + hw[1])
+    img = rng.integers(0, 256, (2,) + hw + (3,)).astype(np.uint8)
+    g = scanner.grayscale(_t(img))
+    for i in range(2):
+        assert np.array_equal(g[i].cpu().numpy(), oracle.gray(img[i]))
+    b = scanner.blur(g)
+    for i in range(2):
+        assert np.array_equal(b[i].cpu().numpy(), oracle.blur5(g[i].cpu().numpy()))
+    for inv in (True, False):
+        t = scanner.adaptive_threshold(b, inverted=inv)
+        for i in range(2):
+            assert np.array_equal(t[i].cpu().numpy(), oracle.adaptive_gauss11(b[i].cpu().numpy(), inv))
+    # odd sizes take the three-kernel path inside svb_preprocess_v1
+    m = scanner.preprocess(_t(img))
+    for i in range(2):
+        assert np.array_equal(m[i].cpu().numpy(), oracle.preprocess(img[i]))
+
+
+@pytest.mark.parametrize("hw", [(64, 64), (72, 480), (100, 496), (270, 480), (136, 976), (300, 1920), (1080, 1920)])
+def test_fused_preprocess_bit_exact(scanner, oracle, hw):
+    """K1 (TMA-staged, row-streaming): edge strips, partial strips, short segments, full 1080p."""
+    rng = np.random.default_rng(hw[0] + hw[1])
+    n = 3 if hw[0] * hw[1] < 500_000 else 2
+    img = rng.integers(0, 256, (n,) + hw + (3,)).astype(np.uint8)
+    # second image: smooth content with lines, closer to real frames (more rounding ties)
+    yy, xx = np.mgrid[0:hw[0], 0:hw[1]]
+    img[1] = np.stack([(120 + 60 * np.sin(xx / 37.0) + 20 * np.cos(yy / 11.0)), (140 + 50 * np.sin((xx + yy) / 23.0)),
+                       (100 + 80 * np.cos(yy / 51.0))], -1).clip(0, 255).astype(np.uint8)
+    m = scanner.preprocess(_t(img)).cpu().numpy()
+    for i in range(n):
+        want = oracle.preprocess(img[i])
+        bad = np.argwhere(m[i] != want)
+        assert len(bad) == 0, f"{len(bad)} mask pixels differ, first at {bad[:5].tolist()}"
+
+
+def test_fused_preprocess_golden(scanner, golden):
+    for name in ("frame_a", "frame_c"):  # widths 480 / 496: fused path
+        g = golden(name)
+        m = scanner.preprocess(_t(g["bgr"][None])).cpu().numpy()[0]
+        assert np.array_equal(m, g["ref_mask"])
+    for name in ("photo4_dec8", "frame_none"):  # 342 / 320 wide: stage-kernel path
+        g = golden(name)
+        m = scanner.preprocess(_t(g["bgr"][None])).cpu().numpy()[0]
+        assert np.array_equal(m, g["ref_mask"])
+
+
+# ---- G1..G2 ---------------------------------------------------------------------------------------
+def test_find_grid_contour_golden(scanner, golden):
+    for name in ("frame_a", "frame_b", "frame_c", "photo4_dec8", "frame_none"):
+        g = golden(name)
+        c, f = scanner.find_grid_contour(_t(g["ref_mask"][None]))
+        assert int(f[0]) == int(bool(g["ref_found"]))
+        if g["ref_found"]:
+            assert np.array_equal(c[0].cpu().numpy(), g["ref_corners"])
+
+
+def test_find_grid_contour_shapes(scanner, oracle):
+    """Adversarial masks (nesting, frame rings, thin strokes, noise) incl. the None outcome."""
+    rng = np.random.default_rng(23)
+    H, W = 160, 224
+    masks = []
+    for s in range(96):
+        m = np.zeros((H, W), np.uint8)
+        for _ in range(int(rng.integers(1, 8))):
+            x0, x1 = sorted(rng.integers(0, W, 2).tolist())
+            y0, y1 = sorted(rng.integers(0, H, 2).tolist())
+            t = int(rng.integers(1, 4))
+            k = int(rng.integers(0, 3))
+            if k == 0:
+                m[y0:y1 + 1, x0:x1 + 1] = 255
+            elif k == 1:
+                m[y0:y1 + 1, x0:x0 + t] = 255
+                m[y0:y1 + 1, max(x1 - t + 1, 0):x1 + 1] = 255
+                m[y0:y0 + t, x0:x1 + 1] = 255
+                m[max(y1 - t + 1, 0):y1 + 1, x0:x1 + 1] = 255
+            else:
+                for i in range(max(x1 - x0, 1)):  # diagonal stroke, 8-connected only
+                    yy = y0 + (i * (y1 - y0)) // max(x1 - x0, 1)
+                    m[min(yy, H - 1), min(x0 + i, W - 1)] = 255
+        if rng.random() < 0.3:
+            m |= ((rng.random((H, W)) < 0.04) * 255).astype(np.uint8)
+        if rng.random() < 0.25:
+            m[0:2, :] = 255
+            m[-2:, :] = 255
+            m[:, 0:2] = 255
+            m[:, -2:] = 255
+        masks.append(m)
+    masks = np.stack(masks)
+    n_found = 0
+    for ratio in (0.03, 0.1, 0.3):
+        c, f = scanner.find_grid_contour(_t(masks), ratio)
+        c, f = c.cpu().numpy(), f.cpu().numpy()
+        for i in range(len(masks)):
+            want = oracle.find_grid_contour(masks[i], ratio, 0.02)
+            assert f[i] in (0, 1), f"mask {i}: status {f[i]}"
+            assert (want is not None) == bool(f[i]), f"mask {i} ratio {ratio}"
+            if want is not None:
+                n_found += 1
+                assert np.array_equal(c[i], want), f"mask {i} ratio {ratio}: {c[i].tolist()} vs {want.tolist()}"
+    assert n_found > 30
+
+
+def test_find_grid_contour_synthetic_frames(scanner, oracle):
+    imgs, _, _ = _frames(6, 1080, 1920, 9100, rot=40.0)
+    m = scanner.preprocess(_t(imgs))
+    c, f = scanner.find_grid_contour(m)
+    c, f, m = c.cpu().numpy(), f.cpu().numpy(), m.cpu().numpy()
+    for i in range(len(imgs)):
+        want = oracle.find_grid_contour(m[i])
+        assert (want is not None) == (f[i] == 1)
+        if want is not None:
+            assert np.array_equal(c[i], want)
+
+
+# ---- G3/G4, E1, C1/C2 -----------------------------------------------------------------------------
+def test_warp_extract_cellprep_golden(scanner, golden):
+    import torch
+
+    for name in ("frame_a", "frame_b", "frame_c", "photo4_dec8"):
+        g = golden(name)
+        bgr = _t(g["bgr"][None])
+        corners = torch.from_numpy(g["ref_corners"][None]).cuda()
+        board = scanner.warp_perspective(bgr, corners)
+        b = board[0].cpu().numpy()
+        assert hashlib.sha256(b.tobytes()).digest() == g["ref_board_sha256"].tobytes(), name
+        cells = scanner.extract_cells(board)
+        assert np.array_equal(cells[0].cpu().numpy(), g["ref_cells_u8"])
+        thr, pm1 = scanner.cell_prep(cells)
+        assert np.array_equal(thr[0].cpu().numpy(), g["ref_cells_thresh"])
+        want_pm1 = ((255 - g["ref_cells_thresh"]).astype(np.float32) / 255.0 - 0.5) / 0.5
+        assert np.array_equal(pm1[0].cpu().numpy(), want_pm1)
+        # fused kernel: frames + corners -> cells, no board
+        u8, pm1f = scanner.cells_from_frames(bgr, corners)
+        assert np.array_equal(u8[0].cpu().numpy(), g["ref_cells_u8"])
+        assert np.array_equal(pm1f[0].cpu().numpy(), want_pm1)
+
+
+def test_cell_prep_unit_vectors(scanner, golden):
+    u = golden("unit")
+    thr, _ = scanner.cell_prep(_t(u["cells"]))
+    assert np.array_equal(thr.cpu().numpy(), u["ref_cells_thresh"])
+
+
+def test_cells_from_frames_vs_oracle_1080p(scanner, oracle):
+    imgs, _, _ = _frames(4, 1080, 1920, 7700)
+    res = [oracle.scan_frame(im) for im in imgs]
+    import torch
+
+    corners = torch.from_numpy(np.stack([r["corners"] for r in res])).cuda()
+    u8, pm1 = scanner.cells_from_frames(_t(imgs), corners)
+    for i, r in enumerate(res):
+        assert r["found"]
+        assert np.array_equal(u8[i].cpu().numpy(), r["cells_u8"])
+        want = (r["cells_in"].astype(np.float32) / 255.0 - 0.5) / 0.5
+        assert np.array_equal(pm1[i].cpu().numpy(), want)
+
+
+def test_not_found_frames_are_zero_filled(scanner):
+    import torch
+
+    bgr = torch.zeros((2, 64, 64, 3), dtype=torch.uint8, device="cuda")
+    corners = torch.zeros((2, 4, 2), dtype=torch.int32, device="cuda")
+    found = torch.zeros((2,), dtype=torch.uint8, device="cuda")
+    u8, pm1 = scanner.cells_from_frames(bgr, corners, found)
+    assert int(u8.abs().sum()) == 0 and float(pm1.abs().sum()) == 0.0
+
+
+# ---- M1/M2 ----------------------------------------------------------------------------------------
+def test_digitcnn_logits(scanner, oracle, weights, golden):
+    import torch
+
+    g = golden("frame_b")
+    x = ((255 - g["ref_cells_thresh"]).astype(np.float32) / 255.0 - 0.5) / 0.5
+    logits, digits, conf = scanner.digitcnn_forward(torch.from_numpy(x).cuda().unsqueeze(1), want_digits=True)
+    assert np.abs(logits.cpu().numpy() - g["ref_logits"]).max() < LOGIT_TOL
+    assert np.array_equal(digits.cpu().numpy(), g["ref_digits"])
+    assert np.abs(conf.cpu().numpy() - g["ref_conf"]).max() < 1e-4
+    # arbitrary float inputs (the drop-in forward must accept any tensor, not only +-1)
+    rng = np.random.default_rng(5)
+    xr = rng.normal(0, 1, (70, 1, 28, 28)).astype(np.float32)
+    got = scanner.digitcnn_forward(torch.from_numpy(xr).cuda()).cpu().numpy()
+    want = oracle.digitcnn_forward(weights, xr)
+    assert np.abs(got - want).max() < LOGIT_TOL
+
+
+# ---- whole path -----------------------------------------------------------------------------------
+def test_scan_batch_vs_oracle(scanner, oracle, weights):
+    imgs, digits_gt, _ = _frames(5, 1080, 1920, 8800)
+    imgs = np.concatenate([imgs, np.random.default_rng(1).integers(80, 180, (1, 1080, 1920, 3)).astype(np.uint8)])
+    out = scanner.scan_batch(_t(imgs), want_logits=True)
+    found = out["found"].cpu().numpy()
+    for i, im in enumerate(imgs):
+        r = oracle.scan_frame(im)
+        assert bool(found[i] == 1) == r["found"], i
+        if not r["found"]:
+            assert int(out["digits"][i].sum()) == 0
+            continue
+        assert np.array_equal(out["corners"][i].cpu().numpy(), r["corners"])
+        x = (r["cells_in"].astype(np.float32) / 255.0 - 0.5) / 0.5
+        want = oracle.digitcnn_forward(weights, x)
+        assert np.abs(out["logits"][i].cpu().numpy() - want).max() < LOGIT_TOL
+        assert np.array_equal(out["digits"][i].cpu().numpy(), want.argmax(1).astype(np.uint8))
+        assert (out["digits"][i].cpu().numpy().reshape(9, 9) == digits_gt[i]).mean() > 0.95  # and it reads the board
+    assert found[-1] == 0
+
+
+def test_scan_batch_host_equals_device(scanner):
+    imgs, _, _ = _frames(3, 1080, 1920, 6600)
+    dev = scanner.scan_batch(_t(imgs))
+    host = scanner.scan_batch_host(imgs)
+    assert np.array_equal(host["digits"], dev["digits"].cpu().numpy())
+    assert np.array_equal(host["corners"], dev["corners"].cpu().numpy())
+    assert np.array_equal(host["found"], dev["found"].cpu().numpy())
+    assert np.array_equal(host["conf"], dev["conf"].cpu().numpy())
+
+
+def test_scan_batch_properties_full_size(scanner):
+    """BASELINE config 2 shape (1080p, a large batch): size-independent properties — determinism,
+    batch-composition independence (frame i's result does not depend on its neighbours), and
+    permutation equivariance."""
+    import torch
+    from svb200 import frames as F
+
+    clean = np.stack([F.make_frame(5000 + i, 1080, 1920).image for i in range(4)])
+    big = F.noisy_batch_device(torch.from_numpy(clean).cuda(), 96, seed=3)
+    a = scanner.scan_batch(big, want_logits=True)
+    b = scanner.scan_batch(big, want_logits=True)
+    for k in ("digits", "corners", "found", "logits"):
+        assert torch.equal(a[k], b[k]), f"{k} not deterministic"
+    perm = torch.randperm(96, device="cuda")
+    c = scanner.scan_batch(big[perm].contiguous(), want_logits=True)
+    for k in ("digits", "corners", "found", "logits"):
+        assert torch.equal(a[k][perm], c[k]), f"{k} depends on batch order"
+    sub = scanner.scan_batch(big[40:47].contiguous())
+    assert torch.equal(sub["digits"], a["digits"][40:47]) and torch.equal(sub["corners"], a["corners"][40:47])
+    assert int((a["found"] == 1).sum()) >= 90
+
+
+# ---- drop-in modules ------------------------------------------------------------------------------
+def test_dropin_modules_match_golden(golden, weights):
+    import os
+    import sys
+
+    import torch
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "sudoku-vision_b200", "dropin", "cv"))
+    sys.path.insert(0, os.path.join(root, "sudoku-vision_b200", "dropin", "ml"))
+    for m in ("preprocess", "grid", "extract", "model"):
+        sys.modules.pop(m, None)
+    import extract
+    import grid
+    import model
+    import preprocess
+
+    g = golden("frame_b")
+    img = g["bgr"]
+    assert np.array_equal(preprocess.grayscale(img), g["ref_gray"])
+    assert np.array_equal(preprocess.blur(g["ref_gray"]), g["ref_blur"])
+    assert np.array_equal(preprocess.threshold(g["ref_blur"]), g["ref_mask"])
+    binary = preprocess.preprocess_for_grid_detection(img)
+    assert np.array_equal(binary, g["ref_mask"])
+    corners = grid.find_grid_contour(binary)
+    assert corners.dtype == np.int32 and np.array_equal(corners, g["ref_corners"])
+    assert np.array_equal(grid.order_points(corners.astype(np.float32)), g["ref_ordered"])
+    warped = grid.warp_perspective(img, corners)
+    assert warped.shape == (450, 450, 3)
+    cells = extract.extract_cells(warped)
+    assert isinstance(cells, list) and len(cells) == 81 and np.array_equal(np.stack(cells), g["ref_cells_u8"])
+    assert grid.find_grid_contour(golden("frame_none")["ref_mask"]) is None
+    with pytest.raises(NotImplementedError):
+        preprocess.blur(g["ref_gray"], ksize=7)
+    with pytest.raises(NotImplementedError):
+        grid.warp_perspective(img, corners, inset_ratio=0.05)
+    net = model.DigitCNN().to("cuda")
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+    net.eval()
+    assert model.count_parameters(net) == 421642
+    x = ((255 - g["ref_cells_thresh"]).astype(np.float32) / 255.0 - 0.5) / 0.5
+    with torch.no_grad():
+        outs = torch.cat([net(torch.from_numpy(x[i:i + 1]).unsqueeze(0).cuda()) for i in range(0, 81, 9)], 0)
+    assert np.abs(outs.cpu().numpy() - g["ref_logits"][::9]).max() < LOGIT_TOL
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 1, 28, 28))

@@ -1,0 +1,71 @@
+"""CPU tier: the oracle (oracle/svb_oracle.c) against the golden vectors minted from the unmodified
+reference (tests/golden/make_golden.py).  Bit-exact for every integer/byte/index stage; logits
+within 1e-3 (fp32, north-star tolerance)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+FRAMES = ["frame_a", "frame_b", "frame_c", "photo4_dec8", "frame_none"]
+
+
+@pytest.mark.parametrize("name", FRAMES)
+def test_image_stages_bit_exact(oracle, golden, name):
+    g = golden(name)
+    img = g["bgr"]
+    assert np.array_equal(oracle.gray(img), g["ref_gray"])
+    assert np.array_equal(oracle.blur5(g["ref_gray"]), g["ref_blur"])
+    assert np.array_equal(oracle.adaptive_gauss11(g["ref_blur"], True), g["ref_mask"])
+    assert np.array_equal(oracle.preprocess(img), g["ref_mask"])
+    c = oracle.find_grid_contour(g["ref_mask"])
+    assert (c is not None) == bool(g["ref_found"])
+    if c is None:
+        return
+    assert np.array_equal(c, g["ref_corners"])
+    assert np.array_equal(oracle.order_points(c), g["ref_ordered"])
+    board = oracle.warp_perspective(img, c)
+    assert hashlib.sha256(board.tobytes()).digest() == g["ref_board_sha256"].tobytes()
+    cells = oracle.extract_cells(board)
+    assert np.array_equal(cells, g["ref_cells_u8"])
+    assert np.array_equal(255 - oracle.cell_prep(cells), g["ref_cells_thresh"])
+
+
+@pytest.mark.parametrize("name", FRAMES[:4])
+def test_scan_frame_and_logits(oracle, golden, weights, name):
+    g = golden(name)
+    r = oracle.scan_frame(g["bgr"])
+    assert r["found"]
+    assert np.array_equal(r["corners"], g["ref_corners"])
+    assert np.array_equal(r["cells_u8"], g["ref_cells_u8"])
+    assert np.array_equal(255 - r["cells_in"], g["ref_cells_thresh"])
+    x = (r["cells_in"].astype(np.float32) / 255.0 - 0.5) / 0.5
+    assert set(np.unique(x)) <= {-1.0, 1.0}
+    logits = oracle.digitcnn_forward(weights, x)
+    assert np.abs(logits - g["ref_logits"]).max() < 1e-3
+    assert np.array_equal(logits.argmax(1).astype(np.uint8), g["ref_digits"])
+
+
+def test_unit_vectors_awkward_sizes(oracle, golden):
+    """Widths that are not multiples of 8 exercise OpenCV's scalar tail arithmetic (svb_oracle.c)."""
+    u = golden("unit")
+    for i in range(4):
+        g = u[f"g{i}"]
+        assert np.array_equal(oracle.blur5(g), u[f"ref_blur{i}"])
+        assert np.array_equal(oracle.adaptive_gauss11(g, True), u[f"ref_thr_inv{i}"])
+        assert np.array_equal(oracle.adaptive_gauss11(g, False), u[f"ref_thr_bin{i}"])
+    cells = u["cells"]
+    assert np.array_equal(np.stack([oracle.clahe28(c) for c in cells]), u["ref_clahe"])
+    assert np.array_equal(255 - oracle.cell_prep(cells), u["ref_cells_thresh"])
+
+
+def test_gauss_kernel_bits(oracle):
+    import ctypes as C
+
+    k = np.zeros(11, np.float32)
+    oracle.lib().svo_gauss11_kernel(k.ctypes.data_as(C.c_void_p))
+    want = np.array([0x3c10612b, 0x3cde5c35, 0x3d855a85, 0x3df92326, 0x3e353f0f, 0x3e4d6105], np.uint32)
+    assert np.array_equal(k[:6].view(np.uint32), want)
+    assert np.array_equal(k[:5], k[:5:-1])
+    # the constants compiled into the CUDA kernels (csrc/common.cuh)
+    lits = np.array([0.00881222915, 0.0271435771, 0.0651140586, 0.121649072, 0.176998362, 0.200565413], np.float32)
+    assert np.array_equal(lits.view(np.uint32), want)
