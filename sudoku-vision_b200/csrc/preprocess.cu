@@ -278,7 +278,7 @@ fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ m
             // >> 8 per lane and pack to u8x4: bytes 1,3 of lo and 1,3 of hi
             sm.bx[b & 15][t] = __byte_perm(lo, hi, 0x7531);
         }
-        b_next = b_hi + 1;
+        b_next = max(b_next, b_hi + 1);
         __syncthreads();  // (B) blurred rows visible
         if (edge_strip) {
             // BORDER_REPLICATE of the blurred image in x: columns < 0 take column 0, >= w take w-1
@@ -353,7 +353,7 @@ fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ m
                 *reinterpret_cast<uint32_t *>(out + (long long)y * w + c0) = o;
             }
         }
-        y_next = y_hi + 1;
+        y_next = max(y_next, y_hi + 1);
         // next iteration's phase 1 writes sm.g, whose readers (phase 2) all passed barrier (B).
     }
 }
