@@ -116,6 +116,11 @@ int svb_digitcnn_load(svb_ctx *ctx, const float *conv1_w, const float *conv1_b, 
 int svb_digitcnn_forward(svb_ctx *ctx, const float *x, long long n, float *logits, uint8_t *digits,
                          float *conf, void *stream);
 
+/* Classifier implementation used by svb_digitcnn_forward and svb_scan_batch_v1:
+ * 0 (default) = tcgen05/TMEM implicit GEMM with fp16 hi/lo split operands (fp32-grade logits),
+ * 1 = plain fp32 on the CUDA cores (kept as the on-device cross-check). */
+int svb_set_classifier_mode(svb_ctx *ctx, int mode);
+
 /* ---- whole path: pipeline/run.py:257-318 (CV + ML sections) for n frames ------------------------ */
 /* Outputs: digits uint8 [n][81], conf float [n][81], logits float [n][81][10] (optional),
  * corners int32 [n][4][2], found uint8 [n].  Frames with found == 0 get digits 0 / conf 0. */

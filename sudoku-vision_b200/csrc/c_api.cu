@@ -53,6 +53,7 @@ int launch_cells_from_frames(svb_ctx *, const uint8_t *, int, int, int, const in
 int digitcnn_load(svb_ctx *, const float *const w[8], cudaStream_t);
 int launch_digitcnn(svb_ctx *, const float *, long long, float *, uint8_t *, float *, cudaStream_t);
 void digitcnn_free(svb_ctx *);
+int launch_digitcnn_tc(svb_ctx *, const float *, long long, float *, uint8_t *, float *, cudaStream_t);
 int launch_mask_not_found(svb_ctx *, const uint8_t *, int, uint8_t *, float *, cudaStream_t);
 
 }  // namespace svb
@@ -218,7 +219,15 @@ API int svb_digitcnn_forward(svb_ctx *ctx, const float *x, long long n, float *l
                              void *stream) {
     GUARD(ctx);
     SVB_REQUIRE(x && logits && n > 0, SVB_ERR_INVALID, "svb_digitcnn_forward: bad arguments");
-    return launch_digitcnn(ctx, x, n, logits, digits, conf, (cudaStream_t)stream);
+    if (ctx->classifier_mode == 1) return launch_digitcnn(ctx, x, n, logits, digits, conf, (cudaStream_t)stream);
+    return launch_digitcnn_tc(ctx, x, n, logits, digits, conf, (cudaStream_t)stream);
+}
+
+API int svb_set_classifier_mode(svb_ctx *ctx, int mode) {
+    GUARD(ctx);
+    SVB_REQUIRE(mode == 0 || mode == 1, SVB_ERR_INVALID, "svb_set_classifier_mode: mode must be 0 (tcgen05) or 1 (fp32)");
+    ctx->classifier_mode = mode;
+    return SVB_OK;
 }
 
 // Whole path.  Intermediates (mask, +-1 cells, logits when the caller does not want them) live in the
@@ -254,7 +263,8 @@ static int scan_batch(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uin
     if (rc) return rc;
     mark(3);
     // frames without a grid have all-zero cell tensors; their digits/conf are forced to 0 below
-    rc = launch_digitcnn(ctx, pm1, (long long)cells, lg, digits, conf, st);
+    rc = (ctx->classifier_mode == 1) ? launch_digitcnn(ctx, pm1, (long long)cells, lg, digits, conf, st)
+                                     : launch_digitcnn_tc(ctx, pm1, (long long)cells, lg, digits, conf, st);
     if (rc) return rc;
     rc = launch_mask_not_found(ctx, found, n, digits, conf, st);
     mark(4);

@@ -62,6 +62,8 @@ struct svb_ctx {
     long long launches = 0;
     svb::Scratch arena[svb::AR_COUNT];
     svb::DigitCnnWeights cnn;
+    void *cnn_tc = nullptr;    // tensor-core operand images (digitcnn_tc.cu)
+    int classifier_mode = 0;   // 0 = tcgen05 (fp16 hi/lo split), 1 = fp32 CUDA cores
     void *pinned = nullptr;    // host staging for *_host calls
     size_t pinned_bytes = 0;
     cudaStream_t own_stream = nullptr;

@@ -215,7 +215,11 @@ int launch_mask_not_found(svb_ctx *ctx, const uint8_t *found, int n, uint8_t *di
     return check_launch(ctx, "k5::mask_not_found_kernel");
 }
 
+void digitcnn_tc_free(svb_ctx *ctx);
+int digitcnn_tc_load(svb_ctx *ctx, const float *conv2_w, const float *fc1_w, cudaStream_t st);
+
 void digitcnn_free(svb_ctx *ctx) {
+    digitcnn_tc_free(ctx);
     if (ctx->cnn.blob) cudaFree(ctx->cnn.blob);
     ctx->cnn = DigitCnnWeights();
 }
@@ -241,6 +245,8 @@ int digitcnn_load(svb_ctx *ctx, const float *const w[8], cudaStream_t st) {
     SVB_CUDA_OK(cudaMemcpyAsync(c.conv2_b, w[3], 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     SVB_CUDA_OK(cudaMemcpyAsync(c.fc1_b, w[5], 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     SVB_CUDA_OK(cudaMemcpyAsync(c.fc2_b, w[7], 10 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    rc = digitcnn_tc_load(ctx, w[2], w[4], st);
+    if (rc) return rc;
     c.loaded = true;
     return SVB_OK;
 }

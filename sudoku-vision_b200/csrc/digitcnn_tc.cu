@@ -1,0 +1,513 @@
+// digitcnn_tc.cu — K5 on the 5th-generation tensor cores: DigitCNN.forward (ml/model.py:34-42) with
+// conv2 and fc1 as tcgen05.mma (kind::f16) GEMMs whose accumulators live in TMEM.
+//
+// Precision.  The north star asks for logits within 1e-3 of the fp32 reference.  fp16 operands alone
+// (11-bit mantissa) give ~1e-2; so every operand is split x = hi + lo (two fp16 numbers, 22 bits) and
+// each product is issued as three MMAs hi*hi + hi*lo + lo*hi into the same fp32 TMEM accumulator.
+// conv1 (K = 9, 5 % of the MACs) runs in fp32 on the CUDA cores with packed fma.rn.f32x2.
+//
+// tc_conv_kernel (persistent, one CTA per SM, 256 threads), per cell:
+//   1. conv1+bias+ReLU+2x2 max-pool in registers -> pooled activations P[16x16 padded grid][32 ch]
+//      written as fp16 hi/lo into shared memory in the UMMA canonical K-major (no-swizzle) layout,
+//      THREE times, pre-shifted by dx = -1,0,+1 rows.  With the grid flattened to rows m = y*16 + x
+//      (zero halo columns/rows), the im2col operand of tap (dy,dx) is then just the dx-copy viewed
+//      at a row offset of 16*dy (a multiple of the 8-row core matrix): the implicit GEMM needs no
+//      per-tap copies, only a different descriptor start address.
+//   2. one elected thread issues 2 tiles x 3 splits x 9 taps x 2 k-steps = 108 tcgen05.mma
+//      (M=128, N=64, K=16) and one tcgen05.commit; accumulators: 2 x 64 TMEM columns.
+//   3. epilogue: tcgen05.ld (32 lanes x 32 columns per warp), 2x2 max-pool by warp shuffles,
+//      +bias, ReLU, fp16 hi/lo split, 128-byte stores of the 49x64 feature block of the cell
+//      (K order (pixel, channel); fc1's weights are permuted to match at pack time).
+// tc_fc_kernel: [cells x 3136] x [3136 x 128] with the same split, 128-cell tiles, cp.async double
+//   buffering into the canonical layout, then bias+ReLU, fc2 (128x10, CUDA cores), softmax-max/argmax.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace svb {
+namespace k5tc {
+
+constexpr int NT = 256;
+constexpr int PAD = 24;                 // zero rows before/after the 256-row padded grid (>= 17, multiple of 8)
+constexpr int SROWS = 256 + 2 * PAD;    // 304
+constexpr int S_BYTES = SROWS * 64;     // 32 fp16 channels per row
+constexpr int WB_BYTES = 64 * 288 * 2;  // conv2 weights, one fp16 part
+constexpr int WB_SBO = 36 * 128;        // 288/8 k-chunks of 128 B per 8-row group
+
+// ---- PTX helpers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TC_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TC_DONE;\n"
+        "bra TC_WAIT;\n"
+        "TC_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (fp16 operands, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor, version 1):
+// core matrix = 8 rows x 16 bytes; LBO = byte step between the two K chunks of one MMA, SBO = byte
+// step between 8-row groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, both K-major, N at [17,23), M at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_hi_lo(float v, __half &hi, __half &lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+
+// ================================================================================================
+// conv stack
+// ================================================================================================
+struct ConvSmem {
+    alignas(1024) uint8_t S[2][3][S_BYTES];  // [hi/lo][dx+1] pooled conv1 activations, canonical layout
+    alignas(128) uint8_t WB[2][WB_BYTES];    // conv2 weights [hi/lo], canonical layout (N=64 rows, K=288)
+    float w1[9 * 32];                        // conv1 weights [tap][co]
+    float b1[32];
+    float b2[64];
+    float inp[30 * 32];                      // zero-padded input, row pitch 32
+    alignas(8) unsigned long long mbar;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(NT, 1)
+tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__restrict__ w1, const float *__restrict__ b1,
+               const uint8_t *__restrict__ wb_img, const float *__restrict__ b2, __half *__restrict__ feat_hi,
+               __half *__restrict__ feat_lo) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    ConvSmem &s = *reinterpret_cast<ConvSmem *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- one-time setup ------------------------------------------------------------------------------
+    for (int i = tid; i < 2 * 3 * S_BYTES / 16; i += NT) reinterpret_cast<uint4 *>(&s.S[0][0][0])[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 2 * WB_BYTES / 16; i += NT)
+        reinterpret_cast<uint4 *>(&s.WB[0][0])[i] = reinterpret_cast<const uint4 *>(wb_img)[i];
+    for (int i = tid; i < 9 * 32; i += NT) s.w1[i] = w1[i];
+    if (tid < 32) s.b1[tid] = b1[tid];
+    if (tid < 64) s.b2[tid] = b2[tid];
+    for (int i = tid; i < 30 * 32; i += NT) s.inp[i] = 0.f;
+    if (tid == 0) {
+        mbar_init(&s.mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&s.tmem_base, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s.tmem_base;
+    const uint32_t idesc = make_idesc(128, 64);
+    const uint32_t s_base = smem_u32(&s.S[0][0][0]), wb_base = smem_u32(&s.WB[0][0]);
+    uint32_t phase = 0;
+
+    for (long long cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
+        // ---- 1a. stage the input (zero-padded by one pixel) ----------------------------------------------
+        const float *xin = x + cell * 784;
+        for (int i = tid; i < 784; i += NT) s.inp[(i / 28 + 1) * 32 + (i % 28) + 1] = xin[i];
+        __syncthreads();
+        // ---- 1b. conv1 + ReLU + pool -> S (hi/lo, three dx shifts) ------------------------------------------
+        for (int item = tid; item < 196 * 4; item += NT) {
+            const int pp = item >> 2, cg = item & 3, py = pp / 14, px = pp - py * 14;
+            float patch[16];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) patch[r * 4 + c] = s.inp[(2 * py + r) * 32 + 2 * px + c];
+            float2 acc[4][4];  // [channel pair][pool position]
+#pragma unroll
+            for (int cp = 0; cp < 4; ++cp) {
+                const float2 b = make_float2(s.b1[cg * 8 + 2 * cp], s.b1[cg * 8 + 2 * cp + 1]);
+#pragma unroll
+                for (int pos = 0; pos < 4; ++pos) acc[cp][pos] = b;
+            }
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float4 wa = *reinterpret_cast<const float4 *>(&s.w1[t * 32 + cg * 8]);
+                const float4 wb = *reinterpret_cast<const float4 *>(&s.w1[t * 32 + cg * 8 + 4]);
+                const float2 w2[4] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y),
+                                      make_float2(wb.z, wb.w)};
+                const int ky = t / 3, kx = t - ky * 3;
+#pragma unroll
+                for (int pos = 0; pos < 4; ++pos) {
+                    const float v = patch[((pos >> 1) + ky) * 4 + (pos & 1) + kx];
+                    const float2 vv = make_float2(v, v);
+#pragma unroll
+                    for (int cp = 0; cp < 4; ++cp) acc[cp][pos] = __ffma2_rn(w2[cp], vv, acc[cp][pos]);
+                }
+            }
+            __half hi[8], lo[8];
+#pragma unroll
+            for (int cp = 0; cp < 4; ++cp) {
+                const float m0 = fmaxf(fmaxf(fmaxf(acc[cp][0].x, acc[cp][1].x), fmaxf(acc[cp][2].x, acc[cp][3].x)), 0.f);
+                const float m1 = fmaxf(fmaxf(fmaxf(acc[cp][0].y, acc[cp][1].y), fmaxf(acc[cp][2].y, acc[cp][3].y)), 0.f);
+                split_hi_lo(m0, hi[2 * cp], lo[2 * cp]);
+                split_hi_lo(m1, hi[2 * cp + 1], lo[2 * cp + 1]);
+            }
+            const uint4 vh = *reinterpret_cast<const uint4 *>(hi), vl = *reinterpret_cast<const uint4 *>(lo);
+            const int rp = (py + 2) * 16 + px;  // row in the padded 16x16 grid (two halo rows on top)
+#pragma unroll
+            for (int dxi = 0; dxi < 3; ++dxi) {
+                const int row = rp + PAD - (dxi - 1);  // S_dx[r] = P[r - PAD + dx]
+                const int off = (row >> 3) * 512 + cg * 128 + (row & 7) * 16;
+                *reinterpret_cast<uint4 *>(&s.S[0][dxi][off]) = vh;
+                *reinterpret_cast<uint4 *>(&s.S[1][dxi][off]) = vl;
+            }
+        }
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncthreads();
+        // ---- 2. implicit-GEMM conv2 on tcgen05 ---------------------------------------------------------------
+        if (warp == 0) {
+            if (lane == 0) {
+                tc_fence_after();
+#pragma unroll 1
+                for (int j = 0; j < 2; ++j) {
+                    uint32_t accum = 0;
+#pragma unroll 1
+                    for (int combo = 0; combo < 3; ++combo) {
+                        const int pa = (combo == 2) ? 1 : 0, pb = (combo == 1) ? 1 : 0;  // hi*hi, hi*lo, lo*hi
+#pragma unroll 1
+                        for (int t = 0; t < 9; ++t) {
+                            const int dy = t / 3 - 1, dxi = t % 3;
+                            const uint32_t a_addr = s_base + (uint32_t)((pa * 3 + dxi) * S_BYTES) +
+                                                    (uint32_t)(((128 * j + 16 * dy + PAD) >> 3) * 512);
+                            const uint32_t b_addr = wb_base + (uint32_t)(pb * WB_BYTES) + (uint32_t)(t * 4 * 128);
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) {
+                                umma_f16(tmem + (uint32_t)(j * 64), make_desc(a_addr + ks * 256, 128, 512),
+                                         make_desc(b_addr + ks * 256, 128, WB_SBO), idesc, accum);
+                                accum = 1;
+                            }
+                        }
+                    }
+                }
+                umma_commit(&s.mbar);
+            }
+            __syncwarp();
+        }
+        mbar_wait(&s.mbar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // ---- 3. epilogue: TMEM -> pool -> bias/ReLU -> fp16 hi/lo features ---------------------------------------
+        {
+            const int j = warp >> 2, q = warp & 3;
+            const int py = 4 * j + q - 1;  // pooled row produced by this warp (rows y_p = 2(4j+q), +1)
+            const bool writer = (lane < 14) && !(lane & 1) && py >= 0 && py < 7;
+            const int px = lane >> 1;
+            __half *fh = feat_hi + (cell * 49 + (long long)(py * 7 + px)) * 64;
+            __half *fl = feat_lo + (cell * 49 + (long long)(py * 7 + px)) * 64;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 64 + half * 32), v);
+                __half hi[32], lo[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    float f = __uint_as_float(v[c]);
+                    f = fmaxf(f, __shfl_xor_sync(0xffffffffu, f, 1));
+                    f = fmaxf(f, __shfl_xor_sync(0xffffffffu, f, 16));
+                    f = fmaxf(f + s.b2[half * 32 + c], 0.f);
+                    split_hi_lo(f, hi[c], lo[c]);
+                }
+                if (writer) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        reinterpret_cast<uint4 *>(fh + half * 32)[k] = reinterpret_cast<const uint4 *>(hi)[k];
+                        reinterpret_cast<uint4 *>(fl + half * 32)[k] = reinterpret_cast<const uint4 *>(lo)[k];
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();  // TMEM and S may be overwritten by the next cell
+        tc_fence_after();
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// ================================================================================================
+// fc1 (tcgen05) + fc2 + softmax/argmax epilogue
+// ================================================================================================
+constexpr int FC_KC = 64;                       // K chunk per stage (4 MMAs of K=16)
+constexpr int FC_TILE_BYTES = 128 * FC_KC * 2;  // one operand part per stage: 16 KB
+constexpr int FC_NCHUNK = 3136 / FC_KC;         // 49
+
+struct FcSmem {
+    alignas(1024) uint8_t A[2][2][FC_TILE_BYTES];  // [stage][hi/lo]  128 cells x 64 k
+    alignas(1024) uint8_t B[2][2][FC_TILE_BYTES];  // [stage][hi/lo]  128 outputs x 64 k
+    float fb1[128];
+    float fw2[128 * 10];
+    float fb2[16];
+    float part[2][128][10];                        // fc2 partial sums per column half
+    alignas(8) unsigned long long mbar[2];
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(NT, 1)
+tc_fc_kernel(const __half *__restrict__ feat_hi, const __half *__restrict__ feat_lo, long long n_cells,
+             const __half *__restrict__ w_hi, const __half *__restrict__ w_lo, const float *__restrict__ fb1,
+             const float *__restrict__ fw2, const float *__restrict__ fb2, float *__restrict__ logits,
+             uint8_t *__restrict__ digits, float *__restrict__ conf) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    FcSmem &s = *reinterpret_cast<FcSmem *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < 128) s.fb1[tid] = fb1[tid];
+    for (int i = tid; i < 1280; i += NT) s.fw2[i] = fw2[i];
+    if (tid < 10) s.fb2[tid] = fb2[tid];
+    if (tid == 0) {
+        mbar_init(&s.mbar[0], 1);
+        mbar_init(&s.mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&s.tmem_base, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s.tmem_base;
+    const uint32_t idesc = make_idesc(128, 128);
+    uint32_t ph[2] = {0, 0};
+    const long long n_tiles = (n_cells + 127) / 128;
+
+    // each thread moves 16 x 16-byte pieces per chunk: piece id p = it*256 + tid -> (operand, part, row, kc)
+    auto load_chunk = [&](long long m0, int chunk, int stage) {
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            const int p = it * NT + tid;
+            const int opnd = p >> 11, part = (p >> 10) & 1, row = (p >> 3) & 127, kc = p & 7;
+            const int off = (row >> 3) * 1024 + kc * 128 + (row & 7) * 16;
+            if (opnd == 0) {
+                long long r = m0 + row;
+                if (r >= n_cells) r = n_cells - 1;  // clamp: rows past the end are computed and discarded
+                const __half *src = (part ? feat_lo : feat_hi) + r * 3136 + chunk * FC_KC + kc * 8;
+                cp_async16(&s.A[stage][part][off], src);
+            } else {
+                const __half *src = (part ? w_lo : w_hi) + (long long)row * 3136 + chunk * FC_KC + kc * 8;
+                cp_async16(&s.B[stage][part][off], src);
+            }
+        }
+        cp_async_commit();
+    };
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long m0 = tile * 128;
+        load_chunk(m0, 0, 0);
+        for (int c = 0; c < FC_NCHUNK; ++c) {
+            const int st = c & 1;
+            if (c + 1 < FC_NCHUNK) {
+                // stage (c+1)&1 was last read by the MMAs of chunk c-1: wait for their commit
+                if (c >= 1) {
+                    mbar_wait(&s.mbar[st ^ 1], ph[st ^ 1]);
+                    ph[st ^ 1] ^= 1;
+                }
+                load_chunk(m0, c + 1, st ^ 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            fence_proxy_async();
+            __syncthreads();
+            if (warp == 0) {
+                if (lane == 0) {
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(&s.A[st][0][0]), b0 = smem_u32(&s.B[st][0][0]);
+#pragma unroll 1
+                    for (int combo = 0; combo < 3; ++combo) {
+                        const int pa = (combo == 2) ? 1 : 0, pb = (combo == 1) ? 1 : 0;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_f16(tmem, make_desc(a0 + pa * FC_TILE_BYTES + ks * 256, 128, 1024),
+                                     make_desc(b0 + pb * FC_TILE_BYTES + ks * 256, 128, 1024), idesc,
+                                     (c | combo | ks) ? 1u : 0u);
+                    }
+                    umma_commit(&s.mbar[st]);
+                }
+                __syncwarp();
+            }
+        }
+        // drain: the last two commits (chunks 47 and 48) are still pending
+        mbar_wait(&s.mbar[(FC_NCHUNK - 2) & 1], ph[(FC_NCHUNK - 2) & 1]);
+        ph[(FC_NCHUNK - 2) & 1] ^= 1;
+        mbar_wait(&s.mbar[(FC_NCHUNK - 1) & 1], ph[(FC_NCHUNK - 1) & 1]);
+        ph[(FC_NCHUNK - 1) & 1] ^= 1;
+        tc_fence_after();
+        // ---- epilogue --------------------------------------------------------------------------------------
+        const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
+        float acc10[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) acc10[k] = 0.f;
+#pragma unroll 1
+        for (int blk = 0; blk < 2; ++blk) {
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64 + blk * 32), v);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const int k = half * 64 + blk * 32 + c;
+                const float h = fmaxf(__uint_as_float(v[c]) + s.fb1[k], 0.f);
+#pragma unroll
+                for (int o = 0; o < 10; ++o) acc10[o] = fmaf(s.fw2[k * 10 + o], h, acc10[o]);
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < 10; ++o) s.part[half][row][o] = acc10[o];
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid < 128 && m0 + tid < n_cells) {
+            float l[10];
+            float mx = -INFINITY;
+            int am = 0;
+#pragma unroll
+            for (int o = 0; o < 10; ++o) {
+                l[o] = s.part[0][tid][o] + s.part[1][tid][o] + s.fb2[o];
+                logits[(m0 + tid) * 10 + o] = l[o];
+                if (l[o] > mx) { mx = l[o]; am = o; }
+            }
+            float den = 0.f;
+#pragma unroll
+            for (int o = 0; o < 10; ++o) den += expf(l[o] - mx);
+            if (digits) digits[m0 + tid] = (uint8_t)am;
+            if (conf) conf[m0 + tid] = 1.0f / den;
+        }
+        __syncthreads();
+    }
+    if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// ---- weight packing ---------------------------------------------------------------------------------------
+// conv2.weight (64,32,3,3) -> two canonical K-major images (hi, lo): element (n, k = tap*32 + ci) at
+// (n/8)*WB_SBO + (k/8)*128 + (n%8)*16 + (k%8)*2.   fc1.weight (128, 3136 [c*49+p]) -> [o][p*64 + c] hi/lo.
+__global__ void pack_tc_kernel(const float *__restrict__ c2w, const float *__restrict__ f1w, uint8_t *__restrict__ wb_img,
+                               __half *__restrict__ w_hi, __half *__restrict__ w_lo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 64 * 288) {
+        const int n = i / 288, k = i % 288, t = k / 32, ci = k % 32;
+        __half hi, lo;
+        split_hi_lo(c2w[(n * 32 + ci) * 9 + t], hi, lo);
+        const int off = (n >> 3) * WB_SBO + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2;
+        *reinterpret_cast<__half *>(wb_img + off) = hi;
+        *reinterpret_cast<__half *>(wb_img + WB_BYTES + off) = lo;
+    }
+    if (i < 128 * 3136) {
+        const int o = i / 3136, kk = i % 3136, p = kk / 64, c = kk % 64;
+        __half hi, lo;
+        split_hi_lo(f1w[o * 3136 + c * 49 + p], hi, lo);
+        w_hi[i] = hi;
+        w_lo[i] = lo;
+    }
+}
+
+}  // namespace k5tc
+
+// ---- host side ------------------------------------------------------------------------------------------------
+struct TcWeights {
+    uint8_t *wb_img = nullptr;  // 2 * WB_BYTES
+    __half *w_hi = nullptr, *w_lo = nullptr;
+};
+static TcWeights *tcw(svb_ctx *ctx) { return reinterpret_cast<TcWeights *>(ctx->cnn_tc); }
+
+void digitcnn_tc_free(svb_ctx *ctx) {
+    TcWeights *t = tcw(ctx);
+    if (!t) return;
+    if (t->wb_img) cudaFree(t->wb_img);
+    if (t->w_hi) cudaFree(t->w_hi);
+    if (t->w_lo) cudaFree(t->w_lo);
+    delete t;
+    ctx->cnn_tc = nullptr;
+}
+
+// conv2_w / fc1_w: PyTorch layouts, device pointers (called from digitcnn_load)
+int digitcnn_tc_load(svb_ctx *ctx, const float *conv2_w, const float *fc1_w, cudaStream_t st) {
+    using namespace k5tc;
+    if (!ctx->cnn_tc) {
+        TcWeights *t = new TcWeights();
+        SVB_CUDA_OK(cudaMalloc(&t->wb_img, 2 * WB_BYTES));
+        SVB_CUDA_OK(cudaMalloc(&t->w_hi, sizeof(__half) * 128 * 3136));
+        SVB_CUDA_OK(cudaMalloc(&t->w_lo, sizeof(__half) * 128 * 3136));
+        ctx->cnn_tc = t;
+    }
+    TcWeights *t = tcw(ctx);
+    pack_tc_kernel<<<(128 * 3136 + 255) / 256, 256, 0, st>>>(conv2_w, fc1_w, t->wb_img, t->w_hi, t->w_lo);
+    return check_launch(ctx, "k5tc::pack_tc_kernel");
+}
+
+int launch_digitcnn_tc(svb_ctx *ctx, const float *x, long long n, float *logits, uint8_t *digits, float *conf,
+                       cudaStream_t st) {
+    using namespace k5tc;
+    SVB_REQUIRE(ctx->cnn.loaded && ctx->cnn_tc, SVB_ERR_NOT_LOADED, "DigitCNN weights not loaded (svb_digitcnn_load)");
+    const DigitCnnWeights &c = ctx->cnn;
+    TcWeights *t = tcw(ctx);
+    const size_t feat_bytes = (size_t)n * 3136 * sizeof(__half);
+    if (ctx->arena[AR_CNN].reserve(2 * feat_bytes + 512) != SVB_OK) return SVB_ERR_CUDA;
+    __half *fh = (__half *)ctx->arena[AR_CNN].ptr;
+    __half *fl = (__half *)((char *)ctx->arena[AR_CNN].ptr + ((feat_bytes + 255) & ~(size_t)255));
+    SVB_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem)));
+    SVB_CUDA_OK(cudaFuncSetAttribute(tc_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FcSmem)));
+    const int grid = (int)min((long long)ctx->sm_count, n);
+    tc_conv_kernel<<<grid, NT, sizeof(ConvSmem), st>>>(x, n, c.conv1_w, c.conv1_b, t->wb_img, c.conv2_b, fh, fl);
+    int rc = check_launch(ctx, "k5tc::tc_conv_kernel");
+    if (rc) return rc;
+    const long long tiles = (n + 127) / 128;
+    tc_fc_kernel<<<(int)min((long long)ctx->sm_count, tiles), NT, sizeof(FcSmem), st>>>(fh, fl, n, t->w_hi, t->w_lo, c.fc1_b,
+                                                                                       c.fc2_w, c.fc2_b, logits, digits, conf);
+    return check_launch(ctx, "k5tc::tc_fc_kernel");
+}
+
+}  // namespace svb

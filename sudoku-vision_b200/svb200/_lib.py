@@ -34,6 +34,7 @@ SIGNATURES = {
     "svb_cells_from_frames": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "svb_digitcnn_load": (_i, [_p] + [_p] * 8 + [_p]),
     "svb_digitcnn_forward": (_i, [_p, _p, _ll, _p, _p, _p, _p]),
+    "svb_set_classifier_mode": (_i, [_p, _i]),
     "svb_scan_batch_v1": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "svb_scan_batch_v1_host": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
 }

@@ -106,6 +106,10 @@ class Scanner:
         self._weights_dev = ts  # keep alive until the pack kernel has run
         return self
 
+    def set_classifier_mode(self, mode: str):
+        """'tc' = tcgen05/TMEM kernels (default), 'fp32' = CUDA-core fp32 kernels."""
+        _lib.check(self.lib.svb_set_classifier_mode(self._h, {"tc": 0, "fp32": 1}[mode]), "svb_set_classifier_mode")
+
     def digitcnn_forward(self, x, want_digits: bool = False):
         """x: (B,1,28,28) float32 CUDA -> logits (B,10) [, digits (B,) u8, conf (B,) f32]."""
         torch = _torch()

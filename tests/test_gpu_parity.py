@@ -194,9 +194,13 @@ def test_not_found_frames_are_zero_filled(scanner):
 
 
 # ---- M1/M2 ----------------------------------------------------------------------------------------
-def test_digitcnn_logits(scanner, oracle, weights, golden):
+@pytest.mark.parametrize("mode", ["tc", "fp32"])
+def test_digitcnn_logits(scanner, oracle, weights, golden, mode):
+    """Both classifier implementations (tcgen05/TMEM with fp16 hi/lo split, and plain fp32) against
+    the reference's logits (golden) and the oracle, 1e-3 absolute."""
     import torch
 
+    scanner.set_classifier_mode(mode)
     g = golden("frame_b")
     x = ((255 - g["ref_cells_thresh"]).astype(np.float32) / 255.0 - 0.5) / 0.5
     logits, digits, conf = scanner.digitcnn_forward(torch.from_numpy(x).cuda().unsqueeze(1), want_digits=True)
@@ -209,6 +213,12 @@ def test_digitcnn_logits(scanner, oracle, weights, golden):
     got = scanner.digitcnn_forward(torch.from_numpy(xr).cuda()).cpu().numpy()
     want = oracle.digitcnn_forward(weights, xr)
     assert np.abs(got - want).max() < LOGIT_TOL
+    # a batch that is not a multiple of the 128-cell tile, +-1 inputs as the path produces them
+    xb = np.where(rng.random((300, 1, 28, 28)) < 0.2, 1.0, -1.0).astype(np.float32)
+    got = scanner.digitcnn_forward(torch.from_numpy(xb).cuda()).cpu().numpy()
+    want = oracle.digitcnn_forward(weights, xb)
+    assert np.abs(got - want).max() < LOGIT_TOL
+    scanner.set_classifier_mode("tc")
 
 
 # ---- whole path -----------------------------------------------------------------------------------
