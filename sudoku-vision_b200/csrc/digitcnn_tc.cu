@@ -158,94 +158,135 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
     const uint32_t s_base = smem_u32(&s.S[0][0][0]), wb_base = smem_u32(&s.WB[0][0]);
     uint32_t phase = 0;
 
-    for (long long cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
-        // ---- 1a. stage the input (zero-padded by one pixel) ----------------------------------------------
+    // Software pipeline: while the tensor core works on cell i (asynchronously), the CUDA cores stage
+    // and convolve cell i+1 into registers; S is rewritten only after cell i's MMAs have committed.
+    constexpr int ITEMS = (196 * 4 + NT - 1) / NT;  // conv1 work items per thread (pooled pixel x 8 channels)
+    uint4 rh[ITEMS], rl[ITEMS];
+
+    auto stage_input = [&](long long cell) {
         const float *xin = x + cell * 784;
         for (int i = tid; i < 784; i += NT) s.inp[(i / 28 + 1) * 32 + (i % 28) + 1] = xin[i];
-        __syncthreads();
-        // ---- 1b. conv1 + ReLU + pool -> S (hi/lo, three dx shifts) ------------------------------------------
-        for (int item = tid; item < 196 * 4; item += NT) {
-            const int pp = item >> 2, cg = item & 3, py = pp / 14, px = pp - py * 14;
-            float patch[16];
+    };
+    // conv1 + bias + ReLU + 2x2 max-pool for this thread's items -> fp16 hi/lo in registers
+    auto conv1_regs = [&]() {
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
+        for (int it = 0; it < ITEMS; ++it) {
+            const int item = it * NT + tid;
+            if (item < 196 * 4) {
+                const int pp = item >> 2, cg = item & 3, py = pp / 14, px = pp - py * 14;
+                float patch[16];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) patch[r * 4 + c] = s.inp[(2 * py + r) * 32 + 2 * px + c];
-            float2 acc[4][4];  // [channel pair][pool position]
+                for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int cp = 0; cp < 4; ++cp) {
-                const float2 b = make_float2(s.b1[cg * 8 + 2 * cp], s.b1[cg * 8 + 2 * cp + 1]);
+                    for (int c = 0; c < 4; ++c) patch[r * 4 + c] = s.inp[(2 * py + r) * 32 + 2 * px + c];
+                float2 acc[4][4];  // [channel pair][pool position]
 #pragma unroll
-                for (int pos = 0; pos < 4; ++pos) acc[cp][pos] = b;
-            }
+                for (int cp = 0; cp < 4; ++cp) {
+                    const float2 bb = make_float2(s.b1[cg * 8 + 2 * cp], s.b1[cg * 8 + 2 * cp + 1]);
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const float4 wa = *reinterpret_cast<const float4 *>(&s.w1[t * 32 + cg * 8]);
-                const float4 wb = *reinterpret_cast<const float4 *>(&s.w1[t * 32 + cg * 8 + 4]);
-                const float2 w2[4] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y),
-                                      make_float2(wb.z, wb.w)};
-                const int ky = t / 3, kx = t - ky * 3;
-#pragma unroll
-                for (int pos = 0; pos < 4; ++pos) {
-                    const float v = patch[((pos >> 1) + ky) * 4 + (pos & 1) + kx];
-                    const float2 vv = make_float2(v, v);
-#pragma unroll
-                    for (int cp = 0; cp < 4; ++cp) acc[cp][pos] = __ffma2_rn(w2[cp], vv, acc[cp][pos]);
+                    for (int pos = 0; pos < 4; ++pos) acc[cp][pos] = bb;
                 }
-            }
-            __half hi[8], lo[8];
 #pragma unroll
-            for (int cp = 0; cp < 4; ++cp) {
-                const float m0 = fmaxf(fmaxf(fmaxf(acc[cp][0].x, acc[cp][1].x), fmaxf(acc[cp][2].x, acc[cp][3].x)), 0.f);
-                const float m1 = fmaxf(fmaxf(fmaxf(acc[cp][0].y, acc[cp][1].y), fmaxf(acc[cp][2].y, acc[cp][3].y)), 0.f);
-                split_hi_lo(m0, hi[2 * cp], lo[2 * cp]);
-                split_hi_lo(m1, hi[2 * cp + 1], lo[2 * cp + 1]);
-            }
-            const uint4 vh = *reinterpret_cast<const uint4 *>(hi), vl = *reinterpret_cast<const uint4 *>(lo);
-            const int rp = (py + 2) * 16 + px;  // row in the padded 16x16 grid (two halo rows on top)
+                for (int t = 0; t < 9; ++t) {
+                    const float4 wa = *reinterpret_cast<const float4 *>(&s.w1[t * 32 + cg * 8]);
+                    const float4 wb = *reinterpret_cast<const float4 *>(&s.w1[t * 32 + cg * 8 + 4]);
+                    const float2 w2[4] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y),
+                                          make_float2(wb.z, wb.w)};
+                    const int ky = t / 3, kx = t - ky * 3;
 #pragma unroll
-            for (int dxi = 0; dxi < 3; ++dxi) {
-                const int row = rp + PAD - (dxi - 1);  // S_dx[r] = P[r - PAD + dx]
-                const int off = (row >> 3) * 512 + cg * 128 + (row & 7) * 16;
-                *reinterpret_cast<uint4 *>(&s.S[0][dxi][off]) = vh;
-                *reinterpret_cast<uint4 *>(&s.S[1][dxi][off]) = vl;
+                    for (int pos = 0; pos < 4; ++pos) {
+                        const float v = patch[((pos >> 1) + ky) * 4 + (pos & 1) + kx];
+                        const float2 vv = make_float2(v, v);
+#pragma unroll
+                        for (int cp = 0; cp < 4; ++cp) acc[cp][pos] = __ffma2_rn(w2[cp], vv, acc[cp][pos]);
+                    }
+                }
+                __half hi[8], lo[8];
+#pragma unroll
+                for (int cp = 0; cp < 4; ++cp) {
+                    const float m0 = fmaxf(fmaxf(fmaxf(acc[cp][0].x, acc[cp][1].x), fmaxf(acc[cp][2].x, acc[cp][3].x)), 0.f);
+                    const float m1 = fmaxf(fmaxf(fmaxf(acc[cp][0].y, acc[cp][1].y), fmaxf(acc[cp][2].y, acc[cp][3].y)), 0.f);
+                    split_hi_lo(m0, hi[2 * cp], lo[2 * cp]);
+                    split_hi_lo(m1, hi[2 * cp + 1], lo[2 * cp + 1]);
+                }
+                rh[it] = *reinterpret_cast<const uint4 *>(hi);
+                rl[it] = *reinterpret_cast<const uint4 *>(lo);
             }
         }
-        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        __syncthreads();
-        // ---- 2. implicit-GEMM conv2 on tcgen05 ---------------------------------------------------------------
-        if (warp == 0) {
-            if (lane == 0) {
-                tc_fence_after();
-#pragma unroll 1
-                for (int j = 0; j < 2; ++j) {
-                    uint32_t accum = 0;
-#pragma unroll 1
-                    for (int combo = 0; combo < 3; ++combo) {
-                        const int pa = (combo == 2) ? 1 : 0, pb = (combo == 1) ? 1 : 0;  // hi*hi, hi*lo, lo*hi
-#pragma unroll 1
-                        for (int t = 0; t < 9; ++t) {
-                            const int dy = t / 3 - 1, dxi = t % 3;
-                            const uint32_t a_addr = s_base + (uint32_t)((pa * 3 + dxi) * S_BYTES) +
-                                                    (uint32_t)(((128 * j + 16 * dy + PAD) >> 3) * 512);
-                            const uint32_t b_addr = wb_base + (uint32_t)(pb * WB_BYTES) + (uint32_t)(t * 4 * 128);
+    };
+    // registers -> S (three dx-shifted copies, hi and lo)
+    auto write_S = [&]() {
 #pragma unroll
-                            for (int ks = 0; ks < 2; ++ks) {
-                                umma_f16(tmem + (uint32_t)(j * 64), make_desc(a_addr + ks * 256, 128, 512),
-                                         make_desc(b_addr + ks * 256, 128, WB_SBO), idesc, accum);
-                                accum = 1;
-                            }
+        for (int it = 0; it < ITEMS; ++it) {
+            const int item = it * NT + tid;
+            if (item < 196 * 4) {
+                const int pp = item >> 2, cg = item & 3, py = pp / 14, px = pp - py * 14;
+                const int rp = (py + 2) * 16 + px;  // row in the padded 16x16 grid (two halo rows on top)
+#pragma unroll
+                for (int dxi = 0; dxi < 3; ++dxi) {
+                    const int row = rp + PAD - (dxi - 1);  // S_dx[r] = P[r - PAD + dx]
+                    const int off = (row >> 3) * 512 + cg * 128 + (row & 7) * 16;
+                    *reinterpret_cast<uint4 *>(&s.S[0][dxi][off]) = rh[it];
+                    *reinterpret_cast<uint4 *>(&s.S[1][dxi][off]) = rl[it];
+                }
+            }
+        }
+    };
+
+    // descriptor halves that never change: LBO/SBO/version live in the high word
+    // all smem addresses are < 256 KB, so adding (byte offset >> 4) to a descriptor never carries out of
+    // the 14-bit start-address field
+    const uint64_t a_desc0 = make_desc(s_base, 128, 512), b_desc0 = make_desc(wb_base, 128, WB_SBO);
+
+    long long cell = blockIdx.x;
+    if (cell < n_cells) {
+        stage_input(cell);
+        __syncthreads();
+        conv1_regs();
+    }
+    for (; cell < n_cells; cell += gridDim.x) {
+        write_S();
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        tc_fence_before();
+        __syncthreads();      // also: every thread has finished reading TMEM / s.inp of the previous cell
+        // ---- implicit-GEMM conv2 on tcgen05: 2 tiles x 3 splits x 9 taps x 2 k-steps, fully unrolled ------------
+        if (warp == 0) {
+            // The whole warp runs the (uniform) descriptor arithmetic so it stays on the uniform datapath;
+            // only the tcgen05 instructions themselves are predicated on one elected lane.
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                for (int combo = 0; combo < 3; ++combo) {
+                    const int pa = (combo == 2) ? 1 : 0, pb = (combo == 1) ? 1 : 0;  // hi*hi, hi*lo, lo*hi
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const int dy = t / 3 - 1, dxi = t % 3;
+                        const uint32_t a_off = (uint32_t)((pa * 3 + dxi) * S_BYTES + ((128 * j + 16 * dy + PAD) >> 3) * 512);
+                        const uint32_t b_off = (uint32_t)(pb * WB_BYTES + t * 4 * 128);
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) {
+                            const uint64_t ad = a_desc0 + (uint64_t)((a_off + ks * 256) >> 4);
+                            const uint64_t bd = b_desc0 + (uint64_t)((b_off + ks * 256) >> 4);
+                            if (lane == 0) umma_f16(tmem + (uint32_t)(j * 64), ad, bd, idesc, (combo | t | ks) ? 1u : 0u);
                         }
                     }
                 }
-                umma_commit(&s.mbar);
             }
+            if (lane == 0) umma_commit(&s.mbar);
             __syncwarp();
+        }
+        // ---- overlap: stage and convolve the next cell while the MMAs run ---------------------------------------------
+        const long long next = cell + gridDim.x;
+        if (next < n_cells) {
+            stage_input(next);
+            __syncthreads();
+            conv1_regs();
         }
         mbar_wait(&s.mbar, phase);
         phase ^= 1;
         tc_fence_after();
-        // ---- 3. epilogue: TMEM -> pool -> bias/ReLU -> fp16 hi/lo features ---------------------------------------
+        // ---- epilogue: TMEM -> pool -> bias/ReLU -> fp16 hi/lo features -------------------------------------------------
         {
             const int j = warp >> 2, q = warp & 3;
             const int py = 4 * j + q - 1;  // pooled row produced by this warp (rows y_p = 2(4j+q), +1)
@@ -275,10 +316,8 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
                 }
             }
         }
-        tc_fence_before();
-        __syncthreads();  // TMEM and S may be overwritten by the next cell
-        tc_fence_after();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 128);
 }
