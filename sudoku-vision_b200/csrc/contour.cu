@@ -42,14 +42,54 @@ __global__ void reset_kernel(int *keys, int *status, int n) {
     if (i < n) status[i] = 0;
 }
 
+// byte mask -> tiled bit mask (see BitMaskView): one thread per output word (tile, row-in-tile)
+__global__ void pack_bits_kernel(const uint8_t *__restrict__ mask, uint32_t *__restrict__ bits, int h, int w, int tx, int ty,
+                                 long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int r = (int)(i & 31);
+    const long long tile = i >> 5;
+    const int xt = (int)(tile % tx);
+    const long long rest = tile / tx;
+    const int yt = (int)(rest % ty);
+    const long long frame = rest / ty;
+    const int y = (yt - 1) * 32 + r, x0 = (xt - 1) * 32;
+    uint32_t v = 0;
+    if (xt >= 1 && xt < tx - 1 && y >= 0 && y < h) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(mask + (frame * h + y) * w + x0);
+        const uint4 a = __ldg(src), b = __ldg(src + 1);
+        const uint32_t q[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            // each byte is 0 or 255: bit 0 of the four bytes -> 4 mask bits, byte j -> bit j
+            const uint32_t t = q[k] & 0x01010101u;
+            v |= (((t * 0x01020408u) >> 24) & 0xFu) << (4 * k);
+        }
+    }
+    bits[i] = v;
+}
+
+template <class View>
+__device__ __forceinline__ View make_view(const void *base, int frame, int h, int w, int wp);
+template <>
+__device__ __forceinline__ MaskView make_view<MaskView>(const void *base, int frame, int h, int w, int) {
+    return MaskView{(const uint8_t *)base + (long long)frame * h * w, h, w};
+}
+template <>
+__device__ __forceinline__ BitMaskView make_view<BitMaskView>(const void *base, int frame, int h, int w, int wp) {
+    // wp carries the words per frame / 32 = tx * ty; tx is recomputed from w
+    return BitMaskView{(const uint32_t *)base + (long long)frame * wp * 32, h, w, contour::bit_tiles_x(w)};
+}
+
+template <class View>
 __global__ void __launch_bounds__(128)
-probe_trace_kernel(const uint8_t *__restrict__ mask, int h, int w, int pitch, int nv, int nh, double min_area,
+probe_trace_kernel(const void *__restrict__ mask, int h, int w, int wp, int pitch, int nv, int nh, double min_area,
                    int max_steps, FrameScratch fs) {
     const int frame = blockIdx.y;
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     const int total = nv * h + nh * w;
     if (id >= total) return;
-    MaskView m{mask + (long long)frame * h * w, h, w};
+    const View m = make_view<View>(mask, frame, h, w, wp);
     int x, y, dv;
     if (id < nv * h) {  // vertical probe line x = k*pitch, scanning down: background above
         x = (id / h) * pitch;
@@ -114,8 +154,9 @@ struct WarpReduce {
     static __device__ __forceinline__ void sync() { __syncwarp(); }
 };
 
+template <class View>
 __global__ void __launch_bounds__(128)
-select_quad_kernel(const uint8_t *__restrict__ mask, int n, int h, int w, double eps_ratio, int max_steps,
+select_quad_kernel(const void *__restrict__ mask, int n, int h, int w, int wp, double eps_ratio, int max_steps,
                    FrameScratch fs, int32_t *__restrict__ corners, uint8_t *__restrict__ found) {
     __shared__ Slice stacks[4][STACK_CAP];
     __shared__ Cand lists[4][MAXC];
@@ -124,7 +165,7 @@ select_quad_kernel(const uint8_t *__restrict__ mask, int n, int h, int w, double
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int frame = blockIdx.x * 4 + warp;
     if (frame >= n) return;
-    MaskView m{mask + (long long)frame * h * w, h, w};
+    const View m = make_view<View>(mask, frame, h, w, wp);
     int status = 0;
     int32_t *out = corners + (long long)frame * 8;
     // gather the occupied slots of this frame's candidate set (lane i looks at slots i and i+32 ...)
@@ -174,6 +215,11 @@ int launch_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, in
     const size_t o_cnt = take(sizeof(int) * (size_t)n * MAXC), o_st = take(sizeof(int) * n);
     const size_t o_c = take(sizeof(Cand) * (size_t)n * MAXC);
     const size_t o_ch = take(sizeof(uint32_t) * (size_t)n * cap), o_po = take(sizeof(uint32_t) * (size_t)n * cap);
+    // bit-packed copy of the mask (only when rows split evenly into 32-pixel words and are 16-B aligned)
+    const bool use_bits = (w % 32 == 0) && ((uintptr_t)mask % 16 == 0);
+    const int tx = contour::bit_tiles_x(w), ty = contour::bit_tiles_y(h);
+    const int wp = tx * ty;  // tiles per frame
+    const size_t o_bits = use_bits ? take(sizeof(uint32_t) * (size_t)n * wp * 32) : 0;
     if (ctx->arena[AR_CONTOUR].reserve(off) != SVB_OK) return SVB_ERR_CUDA;
     char *base = (char *)ctx->arena[AR_CONTOUR].ptr;
     FrameScratch fs;
@@ -188,10 +234,22 @@ int launch_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, in
     int rc = check_launch(ctx, "k2::reset_kernel");
     if (rc) return rc;
     dim3 grid((unsigned)((total + 127) / 128), n);
-    probe_trace_kernel<<<grid, 128, 0, st>>>(mask, h, w, pitch, nv, nh, min_area, max_steps, fs);
+    if (use_bits) {
+        uint32_t *bits = (uint32_t *)(base + o_bits);
+        const long long words = (long long)n * wp * 32;
+        pack_bits_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(mask, bits, h, w, tx, ty, words);
+        rc = check_launch(ctx, "k2::pack_bits_kernel");
+        if (rc) return rc;
+        probe_trace_kernel<BitMaskView><<<grid, 128, 0, st>>>(bits, h, w, wp, pitch, nv, nh, min_area, max_steps, fs);
+        rc = check_launch(ctx, "k2::probe_trace_kernel<bits>");
+        if (rc) return rc;
+        select_quad_kernel<BitMaskView><<<(n + 3) / 4, 128, 0, st>>>(bits, n, h, w, wp, eps_ratio, max_steps, fs, corners, found);
+        return check_launch(ctx, "k2::select_quad_kernel<bits>");
+    }
+    probe_trace_kernel<MaskView><<<grid, 128, 0, st>>>(mask, h, w, 0, pitch, nv, nh, min_area, max_steps, fs);
     rc = check_launch(ctx, "k2::probe_trace_kernel");
     if (rc) return rc;
-    select_quad_kernel<<<(n + 3) / 4, 128, 0, st>>>(mask, n, h, w, eps_ratio, max_steps, fs, corners, found);
+    select_quad_kernel<MaskView><<<(n + 3) / 4, 128, 0, st>>>(mask, n, h, w, 0, eps_ratio, max_steps, fs, corners, found);
     return check_launch(ctx, "k2::select_quad_kernel");
 }
 

@@ -51,6 +51,48 @@ struct MaskView {
     }
 };
 
+// Bit-packed, TILED mask: one bit per pixel; a tile is 32 px wide x 32 rows = 32 words = one 128-byte
+// cache line, stored contiguously.  A border walk therefore touches a new line only every ~32 steps in
+// any direction (row-major bit rows miss on every vertical step, and the walk is a chain of dependent
+// loads, so each miss costs a full memory latency).  One ring of zero tiles surrounds the image
+// (tx = w/32 + 2 tile columns, ty = ceil(h/32) + 2 tile rows), so no access needs a bounds check.
+SVB_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+#endif
+}
+struct BitMaskView {
+    const uint32_t *p;
+    int h, w, tx;  // tx = tile columns incl. the two pad columns
+    SVB_HD long long word_index(int xt, int yp) const {  // xt: padded tile column, yp: padded row (y + 32)
+        return ((long long)(yp >> 5) * tx + xt) * 32 + (yp & 31);
+    }
+    // bits (x-1, x, x+1) of row y in the low 3 bits; valid for -1 <= y <= h and 0 <= x < w
+    SVB_HD uint32_t row3(int x, int y) const {
+        const uint32_t b = (uint32_t)(x + 31);  // padded bit column of x-1
+        const long long i = word_index((int)(b >> 5), y + 32);
+        const uint32_t sh = b & 31u;
+        const uint32_t lo = p[i];
+        const uint32_t hi = (sh > 29u) ? p[i + 32] : 0u;  // the window spills into the next tile only then
+        return funnel_r(lo, hi, sh) & 7u;
+    }
+    SVB_HD bool fg(int x, int y) const {
+        if ((unsigned)x >= (unsigned)w || (unsigned)y >= (unsigned)h) return false;
+        return (p[word_index((x >> 5) + 1, y + 32)] >> (x & 31)) & 1u;
+    }
+    // bit d set <=> neighbour of (x,y) in direction d (E,NE,N,NW,W,SW,S,SE) is foreground
+    SVB_HD unsigned nbits(int x, int y) const {
+        const uint32_t u = row3(x, y - 1), c = row3(x, y), d = row3(x, y + 1);
+        // u/c/d bit0 = x-1, bit1 = x, bit2 = x+1
+        return ((c >> 2) & 1u) | (((u >> 2) & 1u) << 1) | (((u >> 1) & 1u) << 2) | ((u & 1u) << 3) | ((c & 1u) << 4) |
+               ((d & 1u) << 5) | (((d >> 1) & 1u) << 6) | (((d >> 2) & 1u) << 7);
+    }
+};
+SVB_HD int bit_tiles_x(int w) { return w / 32 + 2; }
+SVB_HD int bit_tiles_y(int h) { return (h + 31) / 32 + 2; }
+
 // first set direction scanning counter-clockwise starting just AFTER direction `from`;
 // nb must be non-zero.
 SVB_HD int next_ccw(unsigned nb, int from) {
@@ -76,8 +118,8 @@ SVB_HD int first_cw(unsigned nb, int from) {
 // or a component's raster-first pixel).  Calls vis.point(x, y, din, dout) for every border pixel in
 // Suzuki-Abe order starting at (qx,qy); din/dout are the incoming/outgoing step directions (0..7),
 // or -1/-1 for an isolated pixel.  Returns the number of points, or -1 if max_steps was exceeded.
-template <class Visitor>
-SVB_HD int trace_loop(const MaskView &m, int qx, int qy, int dv, int max_steps, Visitor &vis) {
+template <class View, class Visitor>
+SVB_HD int trace_loop(const View &m, int qx, int qy, int dv, int max_steps, Visitor &vis) {
     unsigned nb = m.nbits(qx, qy);
     if (nb == 0) {
         vis.point(qx, qy, -1, -1);
@@ -353,8 +395,8 @@ constexpr int STACK_CAP = 96;  // DP slice stack
 
 // raw[0..raw_count): candidates as found by the probe pass (duplicates allowed).  list/nested: MAXC
 // scratch entries shared by the cooperating lanes.  Returns 1 and corners[8] if a 4-gon is found.
-template <class Red>
-SVB_HD int select_quad(const MaskView &m, const Cand *raw, int raw_count, Cand *list, int *nested, uint32_t *chain,
+template <class Red, class View>
+SVB_HD int select_quad(const View &m, const Cand *raw, int raw_count, Cand *list, int *nested, uint32_t *chain,
                        uint32_t *poly, int cap, Slice *stack, int max_steps, double eps_ratio, int32_t *corners,
                        int *status_out) {
     const int lane = Red::lane();

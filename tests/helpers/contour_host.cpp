@@ -9,10 +9,30 @@
 
 using namespace svb::contour;
 
+template <class View>
+static int run(const View &m, int h, int w, double min_area_ratio, double eps_ratio, int32_t *corners, int *n_probe_traces,
+               long long *n_probe_steps);
+
+// use_bits != 0: trace the bit-packed view (w must be a multiple of 32), exactly as the batched GPU path does
 extern "C" __attribute__((visibility("default")))
 int svbh_find_grid_contour(const uint8_t *mask, int h, int w, double min_area_ratio, double eps_ratio,
-                           int32_t *corners, int *n_probe_traces, long long *n_probe_steps) {
-    MaskView m{mask, h, w};
+                           int32_t *corners, int *n_probe_traces, long long *n_probe_steps, int use_bits) {
+    if (use_bits) {
+        if (w % 32) return -1;
+        const int tx = bit_tiles_x(w), ty = bit_tiles_y(h);
+        std::vector<uint32_t> bits((size_t)tx * ty * 32, 0u);
+        BitMaskView v{bits.data(), h, w, tx};
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x)
+                if (mask[(size_t)y * w + x]) bits[(size_t)v.word_index((x >> 5) + 1, y + 32)] |= 1u << (x & 31);
+        return run(v, h, w, min_area_ratio, eps_ratio, corners, n_probe_traces, n_probe_steps);
+    }
+    return run(MaskView{mask, h, w}, h, w, min_area_ratio, eps_ratio, corners, n_probe_traces, n_probe_steps);
+}
+
+template <class View>
+static int run(const View &m, int h, int w, double min_area_ratio, double eps_ratio, int32_t *corners, int *n_probe_traces,
+               long long *n_probe_steps) {
     const double min_area = min_area_ratio * (double)((long long)h * w);
     const int pitch = probe_pitch(min_area);
     const int nv = (w - 1) / pitch + 1, nh = (h - 1) / pitch + 1;

@@ -90,11 +90,12 @@ def test_find_grid_contour_oracle_and_product_core(oracle, contour_host):
     rng = _rng(13)
     hits = 0
     for s in range(150):
-        m = _shapes_mask(rng, int(rng.integers(40, 200)), int(rng.integers(40, 260)))
+        bits = s % 2 == 1  # odd cases: width a multiple of 32, traced through the bit-packed view
+        m = _shapes_mask(rng, int(rng.integers(40, 200)), 32 * int(rng.integers(2, 9)) if bits else int(rng.integers(40, 260)))
         for ratio in (0.03, 0.1, 0.3):
             want = _ref_find(m, ratio)
             got = oracle.find_grid_contour(m, ratio, 0.02)
-            f, c = contour_host(m, ratio, 0.02)
+            f, c = contour_host(m, ratio, 0.02, use_bits=bits)
             assert (want is None) == (got is None)
             assert f in (0, 1) and (f == 1) == (want is not None)
             if want is not None:
