@@ -150,6 +150,157 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 
 __device__ __forceinline__ float u8f(uint32_t word, int byte) { return (float)((word >> (8 * byte)) & 0xffu); }
 
+// ---- fast path: one interior block of 4 rows, all ring slots compile-time (PH = (r0 >> 2) & 3) ----------
+// Same rings and row bookkeeping as the generic block above, so the kernel can switch per block; differences:
+// byte arithmetic through dp2a / dp4a, the vertical 5-tap over 8 shared hb rows, both 11-tap passes in
+// packed fma.rn.f32x2 (row pass pairs two image rows, column pass pairs two columns), the threshold in
+// 16-bit SIMD lanes, and no clamps (the caller guarantees rows r0-12 .. r0+3 are inside the image).
+template <int PH>
+__device__ __forceinline__ void fast_block(Smem &sm, const int stage, const int t, const bool cols_inside,
+                                           const bool edge_strip, const bool is_out, const int c0, const int w,
+                                           const int xg0, const int col_lo, const int col_hi, const int t_left,
+                                           const int t_right, uint8_t *__restrict__ out_y0 /* &out[(r0-7)*w + c0] */) {
+    constexpr uint32_t W_BG = 3735u | (19235u << 16), W_R = 9798u;
+    // ---- phase 1: raw BGR -> gray -----------------------------------------------------------------------
+    uint32_t gq[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (cols_inside) {
+            const uint32_t *p = reinterpret_cast<const uint32_t *>(&sm.raw[stage][r][12 * t]);
+            const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
+            const uint32_t p1 = __funnelshift_r(w0, w1, 24), p2 = __funnelshift_r(w1, w2, 16), p3 = w2 >> 8;
+            const uint32_t g0 = __dp2a_hi(W_R, w0, __dp2a_lo(W_BG, w0, 16384u)) >> 15;
+            const uint32_t g1 = __dp2a_hi(W_R, p1, __dp2a_lo(W_BG, p1, 16384u)) >> 15;
+            const uint32_t g2 = __dp2a_hi(W_R, p2, __dp2a_lo(W_BG, p2, 16384u)) >> 15;
+            const uint32_t g3 = __dp2a_hi(W_R, p3, __dp2a_lo(W_BG, p3, 16384u)) >> 15;
+            gq[r] = __byte_perm(__byte_perm(g0, g1, 0x0040), __byte_perm(g2, g3, 0x0040), 0x5410);
+        } else {
+            uint32_t v = 0;
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const int c = c0 + j;
+                int cc = (c < 0) ? -c : ((c >= w) ? 2 * (w - 1) - c : c);
+                cc = clampi(cc, col_lo, col_hi - 1);
+                const uint8_t *p = &sm.raw[stage][r][(cc - xg0) * 3];
+                v |= gray_of(p[0], p[1], p[2]) << (8 * j);
+            }
+            gq[r] = v;
+        }
+        sm.g[r][t] = gq[r];
+    }
+    __syncthreads();  // (A)
+    // ---- phase 2: horizontal 5-tap (dp4a on byte windows) ----------------------------------------------------
+    uint2 H[8];  // hb rows r0-4 .. r0+3 for this thread's 4 columns (u16 x 4 each)
+    const int tl = max(t - 1, 0), tr = min(t + 1, NT - 1);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t gl = sm.g[r][tl], gc = gq[r], gr = sm.g[r][tr];
+        const uint32_t n0 = __funnelshift_r(gl, gc, 16), n1 = __funnelshift_r(gl, gc, 24), n3 = __funnelshift_r(gc, gr, 8),
+                       n4 = __funnelshift_r(gc, gr, 16);
+        const uint32_t h0 = __dp4a(n1, 0x01000000u, __dp4a(n0, 0x04060401u, 0u));
+        const uint32_t h1 = __dp4a(gc, 0x01000000u, __dp4a(n1, 0x04060401u, 0u));
+        const uint32_t h2 = __dp4a(n3, 0x01000000u, __dp4a(gc, 0x04060401u, 0u));
+        const uint32_t h3 = __dp4a(n4, 0x01000000u, __dp4a(n3, 0x04060401u, 0u));
+        H[4 + r] = make_uint2(__byte_perm(h0, h1, 0x5410), __byte_perm(h2, h3, 0x5410));
+        sm.hb[(4 * PH + r) & 7][t] = H[4 + r];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) H[j] = sm.hb[(4 * PH + 4 + j) & 7][t];  // rows r0-4 .. r0-1 (previous block)
+    // ---- phase 3: vertical 5-tap on packed u16 lanes -> blurred rows b = r0-2 .. r0+1 ---------------------------
+    uint32_t Bq[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t lo = H[i].x + H[i + 4].x + 4u * (H[i + 1].x + H[i + 3].x) + 6u * H[i + 2].x + 0x00800080u;
+        const uint32_t hi = H[i].y + H[i + 4].y + 4u * (H[i + 1].y + H[i + 3].y) + 6u * H[i + 2].y + 0x00800080u;
+        Bq[i] = __byte_perm(lo, hi, 0x7531);
+        sm.bx[(4 * PH + 14 + i) & 15][t] = Bq[i];
+    }
+    __syncthreads();  // (B)
+    if (edge_strip) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (c0 < 0) {
+                Bq[i] = (sm.bx[(4 * PH + 14 + i) & 15][t_left] & 0xffu) * 0x01010101u;
+                sm.bx[(4 * PH + 14 + i) & 15][t] = Bq[i];
+            } else if (c0 >= w) {
+                Bq[i] = (sm.bx[(4 * PH + 14 + i) & 15][t_right] >> 24) * 0x01010101u;
+                sm.bx[(4 * PH + 14 + i) & 15][t] = Bq[i];
+            }
+        }
+        __syncthreads();
+    }
+    if (!is_out) return;
+    // ---- phase 4: horizontal 11-tap, two rows per packed FMA ------------------------------------------------------
+    const float2 k0 = make_float2(SVB_G11_0, SVB_G11_0), k1 = make_float2(SVB_G11_1, SVB_G11_1),
+                 k2 = make_float2(SVB_G11_2, SVB_G11_2), k3 = make_float2(SVB_G11_3, SVB_G11_3),
+                 k4 = make_float2(SVB_G11_4, SVB_G11_4), k5 = make_float2(SVB_G11_5, SVB_G11_5);
+    float4 RPn[4];  // row-pass results of rows r0-2 .. r0+1
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr) {
+        const uint32_t *ra = sm.bx[(4 * PH + 14 + 2 * pr) & 15], *rb = sm.bx[(4 * PH + 15 + 2 * pr) & 15];
+        const uint32_t a0 = ra[t - 2], a1 = ra[t - 1], a2 = Bq[2 * pr], a3 = ra[t + 1], a4 = ra[t + 2];
+        const uint32_t b0 = rb[t - 2], b1 = rb[t - 1], b2 = Bq[2 * pr + 1], b3 = rb[t + 1], b4 = rb[t + 2];
+        float2 f[14];  // f[i] = (row a, row b) at column 4t - 5 + i
+        f[0] = make_float2(u8f(a0, 3), u8f(b0, 3));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            f[1 + k] = make_float2(u8f(a1, k), u8f(b1, k));
+            f[5 + k] = make_float2(u8f(a2, k), u8f(b2, k));
+            f[9 + k] = make_float2(u8f(a3, k), u8f(b3, k));
+        }
+        f[13] = make_float2(u8f(a4, 0), u8f(b4, 0));
+        float2 o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 acc = __fmul2_rn(k0, f[j]);
+            acc = __ffma2_rn(k1, f[j + 1], acc);
+            acc = __ffma2_rn(k2, f[j + 2], acc);
+            acc = __ffma2_rn(k3, f[j + 3], acc);
+            acc = __ffma2_rn(k4, f[j + 4], acc);
+            acc = __ffma2_rn(k5, f[j + 5], acc);
+            acc = __ffma2_rn(k4, f[j + 6], acc);
+            acc = __ffma2_rn(k3, f[j + 7], acc);
+            acc = __ffma2_rn(k2, f[j + 8], acc);
+            acc = __ffma2_rn(k1, f[j + 9], acc);
+            acc = __ffma2_rn(k0, f[j + 10], acc);
+            o[j] = acc;
+        }
+        RPn[2 * pr] = make_float4(o[0].x, o[1].x, o[2].x, o[3].x);
+        RPn[2 * pr + 1] = make_float4(o[0].y, o[1].y, o[2].y, o[3].y);
+        sm.rp[(4 * PH + 14 + 2 * pr) & 15][t] = RPn[2 * pr];
+        sm.rp[(4 * PH + 15 + 2 * pr) & 15][t] = RPn[2 * pr + 1];
+    }
+    // ---- phase 5: vertical 11-tap (symmetric), rint, threshold -> 4 output rows y = r0-7 .. r0-4 -------------------
+    float4 Rw[14];  // row-pass rows r0-12 .. r0+1
+#pragma unroll
+    for (int j = 0; j < 10; ++j) Rw[j] = sm.rp[(4 * PH + 4 + j) & 15][t];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Rw[10 + j] = RPn[j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 c = Rw[i + 5];
+        float2 aL = __fmul2_rn(k5, make_float2(c.x, c.y)), aH = __fmul2_rn(k5, make_float2(c.z, c.w));
+#pragma unroll
+        for (int j = 1; j <= 5; ++j) {
+            const float4 u = Rw[i + 5 + j], d = Rw[i + 5 - j];
+            const float2 kk = (j == 1) ? k4 : (j == 2) ? k3 : (j == 3) ? k2 : (j == 4) ? k1 : k0;
+            aL = __ffma2_rn(kk, __fadd2_rn(make_float2(u.x, u.y), make_float2(d.x, d.y)), aL);
+            aH = __ffma2_rn(kk, __fadd2_rn(make_float2(u.z, u.w), make_float2(d.z, d.w)), aH);
+        }
+        // rint via the 1.5*2^23 magic add: the low byte of the float's bits is the rounded mean (0..255)
+        const float2 magic = make_float2(12582912.0f, 12582912.0f);
+        const float2 mL = __fadd2_rn(aL, magic), mH = __fadd2_rn(aH, magic);
+        const uint32_t m_even = __byte_perm(__float_as_uint(mL.x), __float_as_uint(mH.x), 0x5410);  // mean0 | mean2 << 16
+        const uint32_t m_odd = __byte_perm(__float_as_uint(mL.y), __float_as_uint(mH.y), 0x5410);   // mean1 | mean3 << 16
+        const uint32_t src = sm.bx[(4 * PH + 9 + i) & 15][t];
+        const uint32_t s_even = src & 0x00FF00FFu, s_odd = (src >> 8) & 0x00FF00FFu;
+        // THRESH_BINARY_INV: 255 iff src - mean <= -2  <=>  mean - src - 2 >= 0; per 16-bit lane with a 0x8000 guard
+        const uint32_t d_even = m_even + 0x7FFE7FFEu - s_even, d_odd = m_odd + 0x7FFE7FFEu - s_odd;
+        const uint32_t o = ((d_even >> 15) & 0x00010001u) * 0xFFu + ((d_odd >> 15) & 0x00010001u) * 0xFF00u;
+        *reinterpret_cast<uint32_t *>(out_y0 + (long long)i * w) = o;
+    }
+}
+
 template <bool INVERTED>
 __global__ void __launch_bounds__(NT, 3)
 fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ mask, int h, int w, int rows_per_seg) {
@@ -166,7 +317,7 @@ fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ m
     uint8_t *out = mask + (long long)blockIdx.z * frame_px;
 
     const int bs = max(ys - 5, 0), be = min(ye + 5, h);  // blurred rows needed [bs, be)
-    const int gs = max(bs - 2, 0), ge = min(be + 2, h);  // gray rows needed    [gs, ge)
+    const int gs = max(bs - 2, 0) & ~3, ge = min(be + 2, h);  // gray rows staged [gs, ge); gs % 4 == 0 keeps ring phases to 4
     const int nblocks = (ge - gs + R - 1) / R;
 
     // staged column range actually inside the image
@@ -216,6 +367,20 @@ fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ m
         if (t == 0) issue(blk + 2);
         mbar_wait(&sm.full[stage], (uint32_t)((blk / NSTAGE) & 1));
 
+        // interior block: every row it touches is inside the image and inside this segment's schedule
+        if (INVERTED && nrows == R && blk + 1 < nblocks && r0 >= 12 && b_next == r0 - 2 && y_next == r0 - 7 && r0 + 1 <= be - 1 &&
+            r0 - 4 <= ye - 1 && r0 - 7 >= ys && r0 + 3 <= h - 1) {
+            uint8_t *o0 = out + (long long)(r0 - 7) * w + c0;
+            switch ((r0 >> 2) & 3) {
+                case 0: fast_block<0>(sm, stage, t, cols_inside, edge_strip, is_out, c0, w, xg0, col_lo, col_hi, t_left, t_right, o0); break;
+                case 1: fast_block<1>(sm, stage, t, cols_inside, edge_strip, is_out, c0, w, xg0, col_lo, col_hi, t_left, t_right, o0); break;
+                case 2: fast_block<2>(sm, stage, t, cols_inside, edge_strip, is_out, c0, w, xg0, col_lo, col_hi, t_left, t_right, o0); break;
+                default: fast_block<3>(sm, stage, t, cols_inside, edge_strip, is_out, c0, w, xg0, col_lo, col_hi, t_left, t_right, o0); break;
+            }
+            b_next = r0 + 2;
+            y_next = r0 - 3;
+            continue;
+        }
         // ---- phase 1: raw BGR -> gray (packed u8x4) ------------------------------------------
 #pragma unroll
         for (int r = 0; r < R; ++r) {

@@ -4,12 +4,13 @@ import numpy as np, torch
 from svb200 import Scanner
 from oracle import oracle as O
 sc = Scanner()
-for hw, n in [((64,64),4),((72,480),3),((300,1920),3)]:
+for hw, n in [((72,480),1),((300,1920),2)]:
     rng = np.random.default_rng(hw[0]+hw[1])
     img = rng.integers(0,256,(n,)+hw+(3,)).astype(np.uint8)
-    out = torch.full((n,)+hw, 77, dtype=torch.uint8, device='cuda')
-    m = sc.preprocess(torch.from_numpy(img).cuda(), out=out).cpu().numpy()
+    m = sc.preprocess(torch.from_numpy(img).cuda()).cpu().numpy()
     for i in range(n):
         want = O.preprocess(img[i]); bad = np.argwhere(m[i]!=want)
-        vals = np.unique(m[i][m[i]!=want]) if len(bad) else []
-        print(hw, i, 'nbad', len(bad), 'rows', np.unique(bad[:,0])[:12].tolist(), 'bad values', list(vals)[:5], 'count77', int((m[i]==77).sum()))
+        rows, rc = np.unique(bad[:,0], return_counts=True) if len(bad) else ([],[])
+        print(hw, i, 'nbad', len(bad), 'of', want.size, 'rows', list(zip(rows[:20].tolist(), rc[:20].tolist())), 'cols%4 hist', np.bincount(bad[:,1]%4, minlength=4).tolist() if len(bad) else None)
+        if len(bad):
+            y,x = bad[0]; print('  first', y, x, 'got', m[i][y,x], 'want', want[y,x], 'gray/blur around', O.blur5(O.gray(img[i]))[y, max(x-2,0):x+3].tolist())
