@@ -150,17 +150,23 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 
 __device__ __forceinline__ float u8f(uint32_t word, int byte) { return (float)((word >> (8 * byte)) & 0xffu); }
 
-// ---- fast path: one interior block of 4 rows, all ring slots compile-time (PH = (r0 >> 2) & 3) ----------
+// ---- fast path: one interior block of 4 rows, ring slots at compile-time offsets from per-block slot bases ----
 // Same rings and row bookkeeping as the generic block above, so the kernel can switch per block; differences:
 // byte arithmetic through dp2a / dp4a, the vertical 5-tap over 8 shared hb rows, both 11-tap passes in
 // packed fma.rn.f32x2 (row pass pairs two image rows, column pass pairs two columns), the threshold in
 // 16-bit SIMD lanes, and no clamps (the caller guarantees rows r0-12 .. r0+3 are inside the image).
-template <int PH>
-__device__ __forceinline__ void fast_block(Smem &sm, const int stage, const int t, const bool cols_inside,
+__device__ __forceinline__ void fast_block(Smem &sm, const int q /* r0 >> 2 */, const int stage, const int t, const bool cols_inside,
                                            const bool edge_strip, const bool is_out, const int c0, const int w,
                                            const int xg0, const int col_lo, const int col_hi, const int t_left,
                                            const int t_right, uint8_t *__restrict__ out_y0 /* &out[(r0-7)*w + c0] */) {
     constexpr uint32_t W_BG = 3735u | (19235u << 16), W_R = 9798u;
+    // Rings are addressed in 4-row "block slots": hb by gray row (8 rows = 2 slots), bx / rp by blurred row + 2
+    // (16 rows = 4 slots), so that everything this block touches sits at a compile-time offset from a handful
+    // of slot bases computed once here (one code copy for all ring phases keeps the loop inside the I-cache).
+    uint2 (*hb_cur)[NT] = &sm.hb[4 * (q & 1)], (*hb_old)[NT] = &sm.hb[4 * ((q + 1) & 1)];
+    uint32_t (*bx0)[NT] = &sm.bx[4 * (q & 3)], (*bx1)[NT] = &sm.bx[4 * ((q + 3) & 3)], (*bx2)[NT] = &sm.bx[4 * ((q + 2) & 3)];
+    float4 (*rp0)[NT] = &sm.rp[4 * (q & 3)], (*rp1)[NT] = &sm.rp[4 * ((q + 3) & 3)], (*rp2)[NT] = &sm.rp[4 * ((q + 2) & 3)],
+           (*rp3)[NT] = &sm.rp[4 * ((q + 1) & 3)];
     // ---- phase 1: raw BGR -> gray -----------------------------------------------------------------------
     uint32_t gq[R];
 #pragma unroll
@@ -202,10 +208,10 @@ __device__ __forceinline__ void fast_block(Smem &sm, const int stage, const int 
         const uint32_t h2 = __dp4a(n3, 0x01000000u, __dp4a(gc, 0x04060401u, 0u));
         const uint32_t h3 = __dp4a(n4, 0x01000000u, __dp4a(n3, 0x04060401u, 0u));
         H[4 + r] = make_uint2(__byte_perm(h0, h1, 0x5410), __byte_perm(h2, h3, 0x5410));
-        sm.hb[(4 * PH + r) & 7][t] = H[4 + r];
+        hb_cur[r][t] = H[4 + r];
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) H[j] = sm.hb[(4 * PH + 4 + j) & 7][t];  // rows r0-4 .. r0-1 (previous block)
+    for (int j = 0; j < 4; ++j) H[j] = hb_old[j][t];  // rows r0-4 .. r0-1 (previous block)
     // ---- phase 3: vertical 5-tap on packed u16 lanes -> blurred rows b = r0-2 .. r0+1 ---------------------------
     uint32_t Bq[4];
 #pragma unroll
@@ -213,18 +219,18 @@ __device__ __forceinline__ void fast_block(Smem &sm, const int stage, const int 
         const uint32_t lo = H[i].x + H[i + 4].x + 4u * (H[i + 1].x + H[i + 3].x) + 6u * H[i + 2].x + 0x00800080u;
         const uint32_t hi = H[i].y + H[i + 4].y + 4u * (H[i + 1].y + H[i + 3].y) + 6u * H[i + 2].y + 0x00800080u;
         Bq[i] = __byte_perm(lo, hi, 0x7531);
-        sm.bx[(4 * PH + 14 + i) & 15][t] = Bq[i];
+        bx0[i][t] = Bq[i];  // blurred row r0-2+i lives at ring index (row + 2)
     }
     __syncthreads();  // (B)
     if (edge_strip) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (c0 < 0) {
-                Bq[i] = (sm.bx[(4 * PH + 14 + i) & 15][t_left] & 0xffu) * 0x01010101u;
-                sm.bx[(4 * PH + 14 + i) & 15][t] = Bq[i];
+                Bq[i] = (bx0[i][t_left] & 0xffu) * 0x01010101u;
+                bx0[i][t] = Bq[i];
             } else if (c0 >= w) {
-                Bq[i] = (sm.bx[(4 * PH + 14 + i) & 15][t_right] >> 24) * 0x01010101u;
-                sm.bx[(4 * PH + 14 + i) & 15][t] = Bq[i];
+                Bq[i] = (bx0[i][t_right] >> 24) * 0x01010101u;
+                bx0[i][t] = Bq[i];
             }
         }
         __syncthreads();
@@ -237,7 +243,7 @@ __device__ __forceinline__ void fast_block(Smem &sm, const int stage, const int 
     float4 RPn[4];  // row-pass results of rows r0-2 .. r0+1
 #pragma unroll
     for (int pr = 0; pr < 2; ++pr) {
-        const uint32_t *ra = sm.bx[(4 * PH + 14 + 2 * pr) & 15], *rb = sm.bx[(4 * PH + 15 + 2 * pr) & 15];
+        const uint32_t *ra = bx0[2 * pr], *rb = bx0[2 * pr + 1];
         const uint32_t a0 = ra[t - 2], a1 = ra[t - 1], a2 = Bq[2 * pr], a3 = ra[t + 1], a4 = ra[t + 2];
         const uint32_t b0 = rb[t - 2], b1 = rb[t - 1], b2 = Bq[2 * pr + 1], b3 = rb[t + 1], b4 = rb[t + 2];
         float2 f[14];  // f[i] = (row a, row b) at column 4t - 5 + i
@@ -267,13 +273,18 @@ __device__ __forceinline__ void fast_block(Smem &sm, const int stage, const int 
         }
         RPn[2 * pr] = make_float4(o[0].x, o[1].x, o[2].x, o[3].x);
         RPn[2 * pr + 1] = make_float4(o[0].y, o[1].y, o[2].y, o[3].y);
-        sm.rp[(4 * PH + 14 + 2 * pr) & 15][t] = RPn[2 * pr];
-        sm.rp[(4 * PH + 15 + 2 * pr) & 15][t] = RPn[2 * pr + 1];
+        rp0[2 * pr][t] = RPn[2 * pr];
+        rp0[2 * pr + 1][t] = RPn[2 * pr + 1];
     }
     // ---- phase 5: vertical 11-tap (symmetric), rint, threshold -> 4 output rows y = r0-7 .. r0-4 -------------------
     float4 Rw[14];  // row-pass rows r0-12 .. r0+1
+    Rw[0] = rp3[2][t];  // ring index (row + 2): rows r0-12, r0-11 are entries 2,3 of the slot three blocks back
+    Rw[1] = rp3[3][t];
 #pragma unroll
-    for (int j = 0; j < 10; ++j) Rw[j] = sm.rp[(4 * PH + 4 + j) & 15][t];
+    for (int j = 0; j < 4; ++j) {
+        Rw[2 + j] = rp2[j][t];
+        Rw[6 + j] = rp1[j][t];
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) Rw[10 + j] = RPn[j];
 #pragma unroll
@@ -292,7 +303,7 @@ __device__ __forceinline__ void fast_block(Smem &sm, const int stage, const int 
         const float2 mL = __fadd2_rn(aL, magic), mH = __fadd2_rn(aH, magic);
         const uint32_t m_even = __byte_perm(__float_as_uint(mL.x), __float_as_uint(mH.x), 0x5410);  // mean0 | mean2 << 16
         const uint32_t m_odd = __byte_perm(__float_as_uint(mL.y), __float_as_uint(mH.y), 0x5410);   // mean1 | mean3 << 16
-        const uint32_t src = sm.bx[(4 * PH + 9 + i) & 15][t];
+        const uint32_t src = (i == 0) ? bx2[3][t] : bx1[i - 1][t];  // blurred row r0-7+i at ring index r0-5+i
         const uint32_t s_even = src & 0x00FF00FFu, s_odd = (src >> 8) & 0x00FF00FFu;
         // THRESH_BINARY_INV: 255 iff src - mean <= -2  <=>  mean - src - 2 >= 0; per 16-bit lane with a 0x8000 guard
         const uint32_t d_even = m_even + 0x7FFE7FFEu - s_even, d_odd = m_odd + 0x7FFE7FFEu - s_odd;
@@ -371,12 +382,7 @@ fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ m
         if (INVERTED && nrows == R && blk + 1 < nblocks && r0 >= 12 && b_next == r0 - 2 && y_next == r0 - 7 && r0 + 1 <= be - 1 &&
             r0 - 4 <= ye - 1 && r0 - 7 >= ys && r0 + 3 <= h - 1) {
             uint8_t *o0 = out + (long long)(r0 - 7) * w + c0;
-            switch ((r0 >> 2) & 3) {
-                case 0: fast_block<0>(sm, stage, t, cols_inside, edge_strip, is_out, c0, w, xg0, col_lo, col_hi, t_left, t_right, o0); break;
-                case 1: fast_block<1>(sm, stage, t, cols_inside, edge_strip, is_out, c0, w, xg0, col_lo, col_hi, t_left, t_right, o0); break;
-                case 2: fast_block<2>(sm, stage, t, cols_inside, edge_strip, is_out, c0, w, xg0, col_lo, col_hi, t_left, t_right, o0); break;
-                default: fast_block<3>(sm, stage, t, cols_inside, edge_strip, is_out, c0, w, xg0, col_lo, col_hi, t_left, t_right, o0); break;
-            }
+            fast_block(sm, r0 >> 2, stage, t, cols_inside, edge_strip, is_out, c0, w, xg0, col_lo, col_hi, t_left, t_right, o0);
             b_next = r0 + 2;
             y_next = r0 - 3;
             continue;
@@ -441,7 +447,7 @@ fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ m
             uint32_t lo = a0.x + a4.x + 4u * (a1.x + a3.x) + 6u * a2.x + 0x00800080u;
             uint32_t hi = a0.y + a4.y + 4u * (a1.y + a3.y) + 6u * a2.y + 0x00800080u;
             // >> 8 per lane and pack to u8x4: bytes 1,3 of lo and 1,3 of hi
-            sm.bx[b & 15][t] = __byte_perm(lo, hi, 0x7531);
+            sm.bx[(b + 2) & 15][t] = __byte_perm(lo, hi, 0x7531);
         }
         b_next = max(b_next, b_hi + 1);
         __syncthreads();  // (B) blurred rows visible
@@ -449,11 +455,11 @@ fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ m
             // BORDER_REPLICATE of the blurred image in x: columns < 0 take column 0, >= w take w-1
             for (int b = b_first; b <= b_hi; ++b) {
                 if (c0 < 0) {
-                    uint32_t e = sm.bx[b & 15][t_left] & 0xffu;
-                    sm.bx[b & 15][t] = e * 0x01010101u;
+                    uint32_t e = sm.bx[(b + 2) & 15][t_left] & 0xffu;
+                    sm.bx[(b + 2) & 15][t] = e * 0x01010101u;
                 } else if (c0 >= w) {
-                    uint32_t e = sm.bx[b & 15][t_right] >> 24;
-                    sm.bx[b & 15][t] = e * 0x01010101u;
+                    uint32_t e = sm.bx[(b + 2) & 15][t_right] >> 24;
+                    sm.bx[(b + 2) & 15][t] = e * 0x01010101u;
                 }
             }
             __syncthreads();
@@ -462,7 +468,7 @@ fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ m
         // ---- phase 4: horizontal 11-tap (float FMA chain) -> rowpass ring ------------------------
         if (is_out) {
             for (int b = b_first; b <= b_hi; ++b) {
-                const uint32_t *brow = sm.bx[b & 15];
+                const uint32_t *brow = sm.bx[(b + 2) & 15];
                 uint32_t q0 = brow[t - 2], q1 = brow[t - 1], q2 = brow[t], q3 = brow[t + 1], q4 = brow[t + 2];
                 // f[i] = blurred column (4t - 5 + i), i = 0..13
                 float f[14];
@@ -487,7 +493,7 @@ fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ m
                     acc = __fmaf_rn(kf[0], f[j + 10], acc);
                     o[j] = acc;
                 }
-                sm.rp[b & 15][t] = make_float4(o[0], o[1], o[2], o[3]);
+                sm.rp[(b + 2) & 15][t] = make_float4(o[0], o[1], o[2], o[3]);
             }
         }
 
@@ -496,19 +502,19 @@ fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ m
         const int y_hi = (b_last >= h - 1) ? (ye - 1) : min(ye - 1, b_last - 5);
         if (is_out) {
             for (int y = y_next; y <= y_hi; ++y) {
-                float4 c = sm.rp[y & 15][t];
+                float4 c = sm.rp[(y + 2) & 15][t];
                 float a0 = __fmul_rn(kf[5], c.x), a1 = __fmul_rn(kf[5], c.y), a2 = __fmul_rn(kf[5], c.z), a3 = __fmul_rn(kf[5], c.w);
 #pragma unroll
                 for (int j = 1; j <= 5; ++j) {
-                    float4 u = sm.rp[clampi(y + j, 0, h - 1) & 15][t];
-                    float4 d = sm.rp[clampi(y - j, 0, h - 1) & 15][t];
+                    float4 u = sm.rp[(clampi(y + j, 0, h - 1) + 2) & 15][t];
+                    float4 d = sm.rp[(clampi(y - j, 0, h - 1) + 2) & 15][t];
                     const float kk = kf[5 - j];
                     a0 = __fmaf_rn(kk, __fadd_rn(u.x, d.x), a0);
                     a1 = __fmaf_rn(kk, __fadd_rn(u.y, d.y), a1);
                     a2 = __fmaf_rn(kk, __fadd_rn(u.z, d.z), a2);
                     a3 = __fmaf_rn(kk, __fadd_rn(u.w, d.w), a3);
                 }
-                uint32_t src = sm.bx[y & 15][t];
+                uint32_t src = sm.bx[(y + 2) & 15][t];
                 int m0 = rint_pos(a0), m1 = rint_pos(a1), m2 = rint_pos(a2), m3 = rint_pos(a3);
                 // BINARY_INV: 255 iff src - mean <= -2 ; BINARY: 255 iff src - mean > -2
                 bool p0 = (int)(src & 0xff) - m0 <= -2, p1 = (int)((src >> 8) & 0xff) - m1 <= -2;
