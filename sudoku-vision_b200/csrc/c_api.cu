@@ -96,8 +96,13 @@ API void svb_destroy(svb_ctx *ctx) {
     if (!ctx) return;
     DeviceGuard g(ctx->device);
     cudaDeviceSynchronize();
+    for (auto &wk : ctx->worker)
+        if (wk) {
+            svb_destroy(wk);
+            wk = nullptr;
+        }
     for (int i = 0; i < AR_COUNT; ++i) ctx->arena[i].release();
-    digitcnn_free(ctx);
+    if (!ctx->is_worker) digitcnn_free(ctx);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -281,27 +286,66 @@ API int svb_scan_batch_v1(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w,
     return scan_batch(ctx, bgr, n, h, w, digits, conf, logits, corners, found, (cudaStream_t)stream);
 }
 
+// Host-buffer path.  The frames are split into chunks that alternate between two worker contexts, each with
+// its own stream and scratch arenas: while chunk i is being scanned, chunk i+1 is already crossing PCIe
+// (pinned host memory makes the copies truly asynchronous; pageable memory still works, just serialised).
+static int get_worker(svb_ctx *ctx, int slot, svb_ctx **out) {
+    if (!ctx->worker[slot]) {
+        svb_ctx *w = new svb_ctx();
+        w->device = ctx->device;
+        w->sm_count = ctx->sm_count;
+        w->is_worker = true;
+        SVB_CUDA_OK(cudaStreamCreateWithFlags(&w->own_stream, cudaStreamNonBlocking));
+        ctx->worker[slot] = w;
+    }
+    svb_ctx *w = ctx->worker[slot];
+    w->cnn = ctx->cnn;        // borrowed device pointers (read-only)
+    w->cnn_tc = ctx->cnn_tc;
+    w->classifier_mode = ctx->classifier_mode;
+    *out = w;
+    return SVB_OK;
+}
+
 API int svb_scan_batch_v1_host(svb_ctx *ctx, const uint8_t *host_bgr, int n, int h, int w, uint8_t *host_digits,
                                float *host_conf, int32_t *host_corners, uint8_t *host_found) {
     GUARD(ctx);
     SVB_REQUIRE(host_bgr && host_digits && host_conf && host_corners && host_found && dims_ok(n, h, w), SVB_ERR_INVALID,
                 "svb_scan_batch_v1_host: bad arguments");
     SVB_REQUIRE(ctx->cnn.loaded, SVB_ERR_NOT_LOADED, "svb_scan_batch_v1_host: DigitCNN weights not loaded");
-    const size_t in_bytes = (size_t)n * h * w * 3;
-    const size_t o_dig = (in_bytes + 255) & ~(size_t)255, o_conf = o_dig + (((size_t)n * 81 + 255) & ~(size_t)255);
-    const size_t o_cor = o_conf + (((size_t)n * 81 * 4 + 255) & ~(size_t)255), o_fnd = o_cor + (((size_t)n * 32 + 255) & ~(size_t)255);
-    const size_t total = o_fnd + (((size_t)n + 255) & ~(size_t)255);
-    if (ctx->arena[AR_STAGE].reserve(total) != SVB_OK) return SVB_ERR_CUDA;
-    char *d = (char *)ctx->arena[AR_STAGE].ptr;
-    cudaStream_t st = ctx->own_stream;
-    SVB_CUDA_OK(cudaMemcpyAsync(d, host_bgr, in_bytes, cudaMemcpyHostToDevice, st));
-    int rc = scan_batch(ctx, (const uint8_t *)d, n, h, w, (uint8_t *)(d + o_dig), (float *)(d + o_conf), nullptr,
-                        (int32_t *)(d + o_cor), (uint8_t *)(d + o_fnd), st);
-    if (rc) return rc;
-    SVB_CUDA_OK(cudaMemcpyAsync(host_digits, d + o_dig, (size_t)n * 81, cudaMemcpyDeviceToHost, st));
-    SVB_CUDA_OK(cudaMemcpyAsync(host_conf, d + o_conf, (size_t)n * 81 * 4, cudaMemcpyDeviceToHost, st));
-    SVB_CUDA_OK(cudaMemcpyAsync(host_corners, d + o_cor, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
-    SVB_CUDA_OK(cudaMemcpyAsync(host_found, d + o_fnd, (size_t)n, cudaMemcpyDeviceToHost, st));
-    SVB_CUDA_OK(cudaStreamSynchronize(st));
+    const size_t frame_bytes = (size_t)h * w * 3;
+    // ~200 MB per chunk: long enough to reach PCIe peak, short enough that the last chunk's compute is a small tail
+    int chunk = (int)((size_t)(200u << 20) / frame_bytes);
+    chunk = chunk < 1 ? 1 : (chunk > n ? n : chunk);
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_dig = al(frame_bytes * chunk), o_conf = o_dig + al((size_t)chunk * 81);
+    const size_t o_cor = o_conf + al((size_t)chunk * 81 * 4), o_fnd = o_cor + al((size_t)chunk * 32);
+    const size_t total = o_fnd + al((size_t)chunk);
+    svb_ctx *wk[2];
+    for (int s = 0; s < 2; ++s) {
+        int rc = get_worker(ctx, s, &wk[s]);
+        if (rc) return rc;
+        if (wk[s]->arena[AR_STAGE].reserve(total) != SVB_OK) return SVB_ERR_CUDA;
+    }
+    // the weights may have been packed on another stream just before this call
+    SVB_CUDA_OK(cudaDeviceSynchronize());
+    int i = 0;
+    for (int f0 = 0; f0 < n; f0 += chunk, ++i) {
+        const int m = (n - f0 < chunk) ? n - f0 : chunk;
+        svb_ctx *k = wk[i & 1];
+        cudaStream_t st = k->own_stream;
+        char *d = (char *)k->arena[AR_STAGE].ptr;
+        SVB_CUDA_OK(cudaMemcpyAsync(d, host_bgr + (size_t)f0 * frame_bytes, frame_bytes * m, cudaMemcpyHostToDevice, st));
+        int rc = scan_batch(k, (const uint8_t *)d, m, h, w, (uint8_t *)(d + o_dig), (float *)(d + o_conf), nullptr,
+                            (int32_t *)(d + o_cor), (uint8_t *)(d + o_fnd), st);
+        if (rc) return rc;
+        ctx->launches += k->launches;
+        k->launches = 0;
+        SVB_CUDA_OK(cudaMemcpyAsync(host_digits + (size_t)f0 * 81, d + o_dig, (size_t)m * 81, cudaMemcpyDeviceToHost, st));
+        SVB_CUDA_OK(cudaMemcpyAsync(host_conf + (size_t)f0 * 81, d + o_conf, (size_t)m * 81 * 4, cudaMemcpyDeviceToHost, st));
+        SVB_CUDA_OK(cudaMemcpyAsync(host_corners + (size_t)f0 * 8, d + o_cor, (size_t)m * 32, cudaMemcpyDeviceToHost, st));
+        SVB_CUDA_OK(cudaMemcpyAsync(host_found + f0, d + o_fnd, (size_t)m, cudaMemcpyDeviceToHost, st));
+    }
+    SVB_CUDA_OK(cudaStreamSynchronize(wk[0]->own_stream));
+    SVB_CUDA_OK(cudaStreamSynchronize(wk[1]->own_stream));
     return SVB_OK;
 }

@@ -67,6 +67,8 @@ struct svb_ctx {
     void *pinned = nullptr;    // host staging for *_host calls
     size_t pinned_bytes = 0;
     cudaStream_t own_stream = nullptr;
+    svb_ctx *worker[2] = {nullptr, nullptr};  // per-slot child contexts (own stream + arenas) for the chunked host path
+    bool is_worker = false;                   // workers borrow the parent's weights and never free them
     bool stage_timing = false;
     cudaEvent_t ev[SVB_NUM_STAGES + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
