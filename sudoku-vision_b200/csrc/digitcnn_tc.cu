@@ -129,7 +129,12 @@ struct ConvSmem {
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(NT, 1)
+constexpr int NTC = 512;  // conv kernel: 15 worker warps (conv1, S writes) + 1 MMA-issue warp; all 16 run the epilogue
+constexpr int NWK = 480;  // worker threads
+
+__device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(NWK) : "memory"); }
+
+__global__ void __launch_bounds__(NTC, 1)
 tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__restrict__ w1, const float *__restrict__ b1,
                const uint8_t *__restrict__ wb_img, const float *__restrict__ b2, __half *__restrict__ feat_hi,
                __half *__restrict__ feat_lo) {
@@ -138,13 +143,13 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---- one-time setup ------------------------------------------------------------------------------
-    for (int i = tid; i < 2 * 3 * S_BYTES / 16; i += NT) reinterpret_cast<uint4 *>(&s.S[0][0][0])[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < 2 * WB_BYTES / 16; i += NT)
+    for (int i = tid; i < 2 * 3 * S_BYTES / 16; i += NTC) reinterpret_cast<uint4 *>(&s.S[0][0][0])[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 2 * WB_BYTES / 16; i += NTC)
         reinterpret_cast<uint4 *>(&s.WB[0][0])[i] = reinterpret_cast<const uint4 *>(wb_img)[i];
-    for (int i = tid; i < 9 * 32; i += NT) s.w1[i] = w1[i];
+    for (int i = tid; i < 9 * 32; i += NTC) s.w1[i] = w1[i];
     if (tid < 32) s.b1[tid] = b1[tid];
     if (tid < 64) s.b2[tid] = b2[tid];
-    for (int i = tid; i < 30 * 32; i += NT) s.inp[i] = 0.f;
+    for (int i = tid; i < 30 * 32; i += NTC) s.inp[i] = 0.f;
     if (tid == 0) {
         mbar_init(&s.mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -160,18 +165,18 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
 
     // Software pipeline: while the tensor core works on cell i (asynchronously), the CUDA cores stage
     // and convolve cell i+1 into registers; S is rewritten only after cell i's MMAs have committed.
-    constexpr int ITEMS = (196 * 4 + NT - 1) / NT;  // conv1 work items per thread (pooled pixel x 8 channels)
+    constexpr int ITEMS = (196 * 4 + NWK - 1) / NWK;  // conv1 work items per thread (pooled pixel x 8 channels)
     uint4 rh[ITEMS], rl[ITEMS];
 
     auto stage_input = [&](long long cell) {
         const float *xin = x + cell * 784;
-        for (int i = tid; i < 784; i += NT) s.inp[(i / 28 + 1) * 32 + (i % 28) + 1] = xin[i];
+        for (int i = tid; i < 784; i += NWK) s.inp[(i / 28 + 1) * 32 + (i % 28) + 1] = xin[i];
     };
     // conv1 + bias + ReLU + 2x2 max-pool for this thread's items -> fp16 hi/lo in registers
     auto conv1_regs = [&]() {
 #pragma unroll
         for (int it = 0; it < ITEMS; ++it) {
-            const int item = it * NT + tid;
+            const int item = it * NWK + tid;
             if (item < 196 * 4) {
                 const int pp = item >> 2, cg = item & 3, py = pp / 14, px = pp - py * 14;
                 float patch[16];
@@ -218,7 +223,7 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
     auto write_S = [&]() {
 #pragma unroll
         for (int it = 0; it < ITEMS; ++it) {
-            const int item = it * NT + tid;
+            const int item = it * NWK + tid;
             if (item < 196 * 4) {
                 const int pp = item >> 2, cg = item & 3, py = pp / 14, px = pp - py * 14;
                 const int rp = (py + 2) * 16 + px;  // row in the padded 16x16 grid (two halo rows on top)
@@ -238,19 +243,22 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
     // the 14-bit start-address field
     const uint64_t a_desc0 = make_desc(s_base, 128, 512), b_desc0 = make_desc(wb_base, 128, WB_SBO);
 
+    // warp 15 only issues MMAs (a ~5k-cycle serial instruction stream per cell); keeping it out of the conv1
+    // barriers lets the 15 worker warps convolve the next cell at full speed meanwhile
+    const bool mma_warp = (warp == 15);
     long long cell = blockIdx.x;
-    if (cell < n_cells) {
+    if (cell < n_cells && !mma_warp) {
         stage_input(cell);
-        __syncthreads();
+        bar_workers();
         conv1_regs();
     }
     for (; cell < n_cells; cell += gridDim.x) {
-        write_S();
+        if (!mma_warp) write_S();
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
         tc_fence_before();
         __syncthreads();      // also: every thread has finished reading TMEM / s.inp of the previous cell
         // ---- implicit-GEMM conv2 on tcgen05: 2 tiles x 3 splits x 9 taps x 2 k-steps, fully unrolled ------------
-        if (warp == 0) {
+        if (mma_warp) {
             // The whole warp runs the (uniform) descriptor arithmetic so it stays on the uniform datapath;
             // only the tcgen05 instructions themselves are predicated on one elected lane.
             tc_fence_after();
@@ -278,9 +286,9 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
         }
         // ---- overlap: stage and convolve the next cell while the MMAs run ---------------------------------------------
         const long long next = cell + gridDim.x;
-        if (next < n_cells) {
+        if (next < n_cells && !mma_warp) {
             stage_input(next);
-            __syncthreads();
+            bar_workers();
             conv1_regs();
         }
         mbar_wait(&s.mbar, phase);
@@ -288,14 +296,14 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
         tc_fence_after();
         // ---- epilogue: TMEM -> pool -> bias/ReLU -> fp16 hi/lo features -------------------------------------------------
         {
-            const int j = warp >> 2, q = warp & 3;
+            // 16 warps: TMEM lane quarter q = warp % 4 (hardware rule), tile j, 32-column half of the 64 channels
+            const int j = (warp >> 2) & 1, q = warp & 3, half = warp >> 3;
             const int py = 4 * j + q - 1;  // pooled row produced by this warp (rows y_p = 2(4j+q), +1)
             const bool writer = (lane < 14) && !(lane & 1) && py >= 0 && py < 7;
             const int px = lane >> 1;
             __half *fh = feat_hi + (cell * 49 + (long long)(py * 7 + px)) * 64;
             __half *fl = feat_lo + (cell * 49 + (long long)(py * 7 + px)) * 64;
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
+            {
                 uint32_t v[32];
                 tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 64 + half * 32), v);
                 __half hi[32], lo[32];
@@ -540,7 +548,7 @@ int launch_digitcnn_tc(svb_ctx *ctx, const float *x, long long n, float *logits,
     SVB_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem)));
     SVB_CUDA_OK(cudaFuncSetAttribute(tc_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FcSmem)));
     const int grid = (int)min((long long)ctx->sm_count, n);
-    tc_conv_kernel<<<grid, NT, sizeof(ConvSmem), st>>>(x, n, c.conv1_w, c.conv1_b, t->wb_img, c.conv2_b, fh, fl);
+    tc_conv_kernel<<<grid, NTC, sizeof(ConvSmem), st>>>(x, n, c.conv1_w, c.conv1_b, t->wb_img, c.conv2_b, fh, fl);
     int rc = check_launch(ctx, "k5tc::tc_conv_kernel");
     if (rc) return rc;
     const long long tiles = (n + 127) / 128;
