@@ -19,6 +19,8 @@
 //        winding number of the encloser's chain around the start pixel), computes arcLength and
 //        runs the closed-curve approxPolyDP with the 32 lanes sharing every farthest-point scan.
 //        The first 4-vertex polygon wins; otherwise found = 0 (the reference's None).
+#include <algorithm>
+
 #include "common.cuh"
 #include "contour_core.cuh"
 
@@ -34,12 +36,18 @@ struct FrameScratch {
     uint32_t *chain;   // [n][cap]
     uint32_t *poly;    // [n][cap]
     int cap;
+    int *gcount;       // [1] number of crossings found in the whole batch
+    int2 *glist;       // [gcap] (frame, probe id) of every crossing, densely packed across frames
+    int *map;          // [n][nprobe] probe id -> index into glist/segs (valid only at crossings)
+    Seg *segs;         // [gcap]
+    int gcap, nprobe;
 };
 
-__global__ void reset_kernel(int *keys, int *status, int n) {
+__global__ void reset_kernel(int *keys, int *status, int *gcount, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n * MAXC) keys[i] = -1;
     if (i < n) status[i] = 0;
+    if (i == 0) *gcount = 0;
 }
 
 // byte mask -> tiled bit mask (see BitMaskView): one thread per output word (tile, row-in-tile)
@@ -81,49 +89,94 @@ __device__ __forceinline__ BitMaskView make_view<BitMaskView>(const void *base, 
     return BitMaskView{(const uint32_t *)base + (long long)frame * wp * 32, h, w, contour::bit_tiles_x(w)};
 }
 
+// K2a.1: one thread per probe-line pixel: record the crossings of every frame in ONE dense list
 template <class View>
-__global__ void __launch_bounds__(128)
-probe_trace_kernel(const void *__restrict__ mask, int h, int w, int wp, int pitch, int nv, int nh, double min_area,
-                   int max_steps, FrameScratch fs) {
+__global__ void __launch_bounds__(256)
+find_crossings_kernel(const void *__restrict__ mask, int h, int w, int wp, int pitch, int nv, FrameScratch fs) {
     const int frame = blockIdx.y;
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
-    const int total = nv * h + nh * w;
-    if (id >= total) return;
+    if (id >= fs.nprobe) return;
     const View m = make_view<View>(mask, frame, h, w, wp);
-    int x, y, dv;
+    int x, y;
     if (id < nv * h) {  // vertical probe line x = k*pitch, scanning down: background above
         x = (id / h) * pitch;
         y = id % h;
-        dv = DIR_N;
         if (!m.fg(x, y) || m.fg(x, y - 1)) return;
     } else {            // horizontal probe line y = k*pitch, scanning right: background to the left
         const int j = id - nv * h;
         y = (j / w) * pitch;
         x = j % w;
-        dv = DIR_W;
         if (!m.fg(x, y) || m.fg(x - 1, y)) return;
+        // same walk state as the vertical crossing of this pixel: keep only that one
+        if (x % pitch == 0 && !m.fg(x, y - 1) && !m.fg(x - 1, y - 1)) return;
     }
-    LoopStats st(w);
-    const int npts = trace_loop(m, x, y, dv, max_steps, st);
-    if (npts < 0) {
-        atomicOr(&fs.status[frame], 4);
+    const int g = atomicAdd(fs.gcount, 1);
+    if (g >= fs.gcap) {
+        atomicOr(&fs.status[frame], 1);
         return;
     }
-    // Outer borders come out with negative signed area in image coordinates (y down); holes positive.
-    if (st.area2 >= 0) return;
-    const double area = (double)(-st.area2) * 0.5;
-    if (area < min_area) return;
-    // The same border is usually reached from several crossings: insert into a small open-addressed
-    // set keyed by the component's raster-first pixel, so duplicates cost nothing.
+    fs.glist[g] = make_int2(frame, id);
+    fs.map[(long long)frame * fs.nprobe + id] = g;
+}
+
+// K2a.2: one thread per crossing (dense warps): walk the border until the next crossing
+template <class View>
+__global__ void __launch_bounds__(128)
+trace_segments_kernel(const void *__restrict__ mask, int h, int w, int wp, int pitch, int nv, int max_steps, FrameScratch fs) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= min(*fs.gcount, fs.gcap)) return;
+    const int2 e = fs.glist[g];
+    const int frame = e.x, id = e.y;
+    const View m = make_view<View>(mask, frame, h, w, wp);
+    int x, y, dv;
+    if (id < nv * h) {
+        x = (id / h) * pitch;
+        y = id % h;
+        dv = DIR_N;
+    } else {
+        const int j = id - nv * h;
+        y = (j / w) * pitch;
+        x = j % w;
+        dv = DIR_W;
+    }
+    Seg sg = trace_segment(m, x, y, dv, pitch, nv, max_steps);
+    if (sg.next_id < 0) atomicOr(&fs.status[frame], 4);
+    else sg.next_id = fs.map[(long long)frame * fs.nprobe + sg.next_id];  // probe id -> list index
+    fs.segs[g] = sg;
+}
+
+// K2a.3: one thread per crossing: follow the segment links once around the loop; the loop's smallest list
+// index sums it up and, if it is an outer border (negative signed area, y down) of area >= min_area, records
+// the component (keyed by its raster-first pixel) in the frame's candidate set.
+__global__ void __launch_bounds__(128)
+link_loops_kernel(double min_area, FrameScratch fs) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = min(*fs.gcount, fs.gcap);
+    if (g >= total) return;
+    const int frame = fs.glist[g].x;
+    long long area2 = 0;
+    int min_idx = 0x7fffffff, cur = g;
+    for (int it = 0; it <= total; ++it) {
+        const Seg sg = fs.segs[cur];
+        if (sg.next_id < 0) return;           // broken loop (step limit): status already set
+        area2 += sg.area2;
+        min_idx = min(min_idx, sg.min_idx);
+        cur = sg.next_id;
+        if (cur < g) return;                  // a smaller index on this loop is the leader
+        if (cur == g) break;
+    }
+    if (cur != g) return;
+    if (area2 >= 0) return;
+    if ((double)(-area2) * 0.5 < min_area) return;
     int *keys = fs.keys + (long long)frame * MAXC;
-    int slot = (int)(((unsigned)st.min_idx * 2654435761u) >> 27) & (MAXC - 1);
+    int slot = (int)(((unsigned)min_idx * 2654435761u) >> 26) & (MAXC - 1);
     for (int probe = 0; probe < MAXC; ++probe) {
-        const int old = atomicCAS(&keys[slot], -1, st.min_idx);
-        if (old == st.min_idx) return;  // already recorded by another crossing of the same border
+        const int old = atomicCAS(&keys[slot], -1, min_idx);
+        if (old == min_idx) return;
         if (old == -1) {
             Cand c;
-            c.area2 = -st.area2;
-            c.min_idx = st.min_idx;
+            c.area2 = -area2;
+            c.min_idx = min_idx;
             c.pad = 0;
             fs.cands[(long long)frame * MAXC + slot] = c;
             return;
@@ -220,6 +273,10 @@ int launch_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, in
     const int tx = contour::bit_tiles_x(w), ty = contour::bit_tiles_y(h);
     const int wp = tx * ty;  // tiles per frame
     const size_t o_bits = use_bits ? take(sizeof(uint32_t) * (size_t)n * wp * 32) : 0;
+    const long long gcap_ll = std::min<long long>(std::max<long long>((long long)n * 512, 16384), (long long)n * (total / 2 + 1));
+    const int gcap = (int)std::min<long long>(gcap_ll, 1ll << 26);
+    const size_t o_gc = take(sizeof(int)), o_gl = take(sizeof(int2) * (size_t)gcap), o_sg = take(sizeof(Seg) * (size_t)gcap);
+    const size_t o_map = take(sizeof(int) * (size_t)n * total);
     if (ctx->arena[AR_CONTOUR].reserve(off) != SVB_OK) return SVB_ERR_CUDA;
     char *base = (char *)ctx->arena[AR_CONTOUR].ptr;
     FrameScratch fs;
@@ -229,27 +286,48 @@ int launch_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, in
     fs.chain = (uint32_t *)(base + o_ch);
     fs.poly = (uint32_t *)(base + o_po);
     fs.cap = cap;
+    fs.gcount = (int *)(base + o_gc);
+    fs.glist = (int2 *)(base + o_gl);
+    fs.segs = (Seg *)(base + o_sg);
+    fs.map = (int *)(base + o_map);
+    fs.gcap = gcap;
+    fs.nprobe = (int)total;
 
-    reset_kernel<<<(n * MAXC + 255) / 256, 256, 0, st>>>(fs.keys, fs.status, n);
+    reset_kernel<<<(n * MAXC + 255) / 256, 256, 0, st>>>(fs.keys, fs.status, fs.gcount, n);
     int rc = check_launch(ctx, "k2::reset_kernel");
     if (rc) return rc;
-    dim3 grid((unsigned)((total + 127) / 128), n);
+    const void *view_ptr = mask;
     if (use_bits) {
         uint32_t *bits = (uint32_t *)(base + o_bits);
         const long long words = (long long)n * wp * 32;
         pack_bits_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(mask, bits, h, w, tx, ty, words);
         rc = check_launch(ctx, "k2::pack_bits_kernel");
         if (rc) return rc;
-        probe_trace_kernel<BitMaskView><<<grid, 128, 0, st>>>(bits, h, w, wp, pitch, nv, nh, min_area, max_steps, fs);
-        rc = check_launch(ctx, "k2::probe_trace_kernel<bits>");
-        if (rc) return rc;
-        select_quad_kernel<BitMaskView><<<(n + 3) / 4, 128, 0, st>>>(bits, n, h, w, wp, eps_ratio, max_steps, fs, corners, found);
-        return check_launch(ctx, "k2::select_quad_kernel<bits>");
+        view_ptr = bits;
     }
-    probe_trace_kernel<MaskView><<<grid, 128, 0, st>>>(mask, h, w, 0, pitch, nv, nh, min_area, max_steps, fs);
-    rc = check_launch(ctx, "k2::probe_trace_kernel");
+    dim3 grid1((unsigned)((total + 255) / 256), n);
+    const unsigned gblocks = (unsigned)((gcap + 127) / 128);
+    if (use_bits) {
+        find_crossings_kernel<BitMaskView><<<grid1, 256, 0, st>>>(view_ptr, h, w, wp, pitch, nv, fs);
+        rc = check_launch(ctx, "k2::find_crossings_kernel<bits>");
+        if (rc) return rc;
+        trace_segments_kernel<BitMaskView><<<gblocks, 128, 0, st>>>(view_ptr, h, w, wp, pitch, nv, max_steps, fs);
+        rc = check_launch(ctx, "k2::trace_segments_kernel<bits>");
+    } else {
+        find_crossings_kernel<MaskView><<<grid1, 256, 0, st>>>(view_ptr, h, w, 0, pitch, nv, fs);
+        rc = check_launch(ctx, "k2::find_crossings_kernel");
+        if (rc) return rc;
+        trace_segments_kernel<MaskView><<<gblocks, 128, 0, st>>>(view_ptr, h, w, 0, pitch, nv, max_steps, fs);
+        rc = check_launch(ctx, "k2::trace_segments_kernel");
+    }
     if (rc) return rc;
-    select_quad_kernel<MaskView><<<(n + 3) / 4, 128, 0, st>>>(mask, n, h, w, 0, eps_ratio, max_steps, fs, corners, found);
+    link_loops_kernel<<<gblocks, 128, 0, st>>>(min_area, fs);
+    rc = check_launch(ctx, "k2::link_loops_kernel");
+    if (rc) return rc;
+    if (use_bits)
+        select_quad_kernel<BitMaskView><<<(n + 3) / 4, 128, 0, st>>>(view_ptr, n, h, w, wp, eps_ratio, max_steps, fs, corners, found);
+    else
+        select_quad_kernel<MaskView><<<(n + 3) / 4, 128, 0, st>>>(view_ptr, n, h, w, 0, eps_ratio, max_steps, fs, corners, found);
     return check_launch(ctx, "k2::select_quad_kernel");
 }
 

@@ -18,8 +18,9 @@ namespace svb {
 namespace contour {
 
 // neighbour directions, counter-clockwise on screen (y down): E,NE,N,NW,W,SW,S,SE
-SVB_HD int dir_dx(int d) { return (d == 0 || d == 1 || d == 7) ? 1 : ((d >= 3 && d <= 5) ? -1 : 0); }
-SVB_HD int dir_dy(int d) { return (d >= 1 && d <= 3) ? -1 : ((d >= 5) ? 1 : 0); }
+// (dx+1, dy+1) packed as 2-bit fields per direction: dx = {1,1,0,-1,-1,-1,0,1}, dy = {0,-1,-1,-1,0,1,1,1}
+SVB_HD int dir_dx(int d) { return (int)((0x901Au >> (2 * d)) & 3u) - 1; }
+SVB_HD int dir_dy(int d) { return (int)((0xA901u >> (2 * d)) & 3u) - 1; }
 constexpr int DIR_N = 2, DIR_W = 4;
 
 struct MaskView {
@@ -113,6 +114,68 @@ SVB_HD int first_cw(unsigned nb, int from) {
     return -1;
 }
 
+// ---- cursors: where the walker gets the 8-neighbourhood from ---------------------------------------------------
+struct ByteCursor {  // byte mask: reads memory every step
+    const MaskView *m;
+    SVB_HD void init(const MaskView &v, int, int) { m = &v; }
+    SVB_HD unsigned nbits(int x, int y) const { return m->nbits(x, y); }
+    SVB_HD void moved(int, int, int) {}
+};
+
+// Tiled bit mask with the neighbourhood held in registers.  A border walk is a chain of dependent steps, so its
+// speed is the latency of one step.  A window of 5 rows x 64 bit columns around the cursor lives in ten
+// registers: a horizontal move only changes a shift amount, a vertical move rotates the rows and fetches ONE
+// new row two rows ahead of where it is needed, and the window is re-centred only every >= 16 horizontal steps.
+struct BitCursor {
+    const uint32_t *p;
+    int tx;
+    int wq;                        // padded word column of the window's first word
+    uint32_t l0, l1, l2, l3, l4;   // rows y-2 .. y+2, bits [32*wq, 32*wq + 32)
+    uint32_t h0, h1, h2, h3, h4;   //                  bits [32*wq + 32, 32*wq + 64)
+    SVB_HD void fetch(int yy, uint32_t &lo, uint32_t &hi) const {  // row yy in [-2, h+1]: zero pad rows exist
+        const int yp = yy + 32;
+        const long long i = ((long long)(yp >> 5) * tx + wq) * 32 + (yp & 31);
+        lo = p[i];
+        hi = p[i + 32];
+    }
+    SVB_HD void centre(int x, int y) {
+        wq = (x + 32 - 16) >> 5;  // puts the cursor's padded column in [32*wq + 16, 32*wq + 47]
+        fetch(y - 2, l0, h0);
+        fetch(y - 1, l1, h1);
+        fetch(y, l2, h2);
+        fetch(y + 1, l3, h3);
+        fetch(y + 2, l4, h4);
+    }
+    SVB_HD void init(const BitMaskView &v, int x, int y) {
+        p = v.p;
+        tx = v.tx;
+        centre(x, y);
+    }
+    static SVB_HD uint32_t take3(uint32_t lo, uint32_t hi, uint32_t sh) {  // bits sh, sh+1, sh+2 of the 64-bit row
+        return ((sh < 32u) ? funnel_r(lo, hi, sh) : (hi >> (sh - 32u))) & 7u;
+    }
+    SVB_HD unsigned nbits(int x, int) const {
+        const uint32_t sh = (uint32_t)(x + 31 - 32 * wq);  // window bit of column x-1; always in [0, 61]
+        const uint32_t u = take3(l1, h1, sh), c = take3(l2, h2, sh), d = take3(l3, h3, sh);
+        return ((c >> 2) & 1u) | (((u >> 2) & 1u) << 1) | (((u >> 1) & 1u) << 2) | ((u & 1u) << 3) | ((c & 1u) << 4) |
+               ((d & 1u) << 5) | (((d >> 1) & 1u) << 6) | (((d >> 2) & 1u) << 7);
+    }
+    SVB_HD void moved(int x, int y, int dy) {  // the cursor is now at (x, y), having moved by dy vertically
+        if (dy > 0) {
+            l0 = l1; h0 = h1; l1 = l2; h1 = h2; l2 = l3; h2 = h3; l3 = l4; h3 = h4;
+            fetch(y + 2, l4, h4);
+        } else if (dy < 0) {
+            l4 = l3; h4 = h3; l3 = l2; h3 = h2; l2 = l1; h2 = h1; l1 = l0; h1 = h0;
+            fetch(y - 2, l0, h0);
+        }
+        const int rel = x + 32 - 32 * wq;  // needs rel-1 >= 0 and rel+1 <= 63
+        if (rel < 1 || rel > 62) centre(x, y);
+    }
+};
+template <class View> struct CursorOf;
+template <> struct CursorOf<MaskView> { typedef ByteCursor type; };
+template <> struct CursorOf<BitMaskView> { typedef BitCursor type; };
+
 // Follow the border loop that passes through foreground pixel (qx,qy) with a known background
 // (or out-of-image) neighbour in direction `dv` (N for a vertical probe, W for a horizontal probe
 // or a component's raster-first pixel).  Calls vis.point(x, y, din, dout) for every border pixel in
@@ -120,7 +183,9 @@ SVB_HD int first_cw(unsigned nb, int from) {
 // or -1/-1 for an isolated pixel.  Returns the number of points, or -1 if max_steps was exceeded.
 template <class View, class Visitor>
 SVB_HD int trace_loop(const View &m, int qx, int qy, int dv, int max_steps, Visitor &vis) {
-    unsigned nb = m.nbits(qx, qy);
+    typename CursorOf<View>::type cur;
+    cur.init(m, qx, qy);
+    unsigned nb = cur.nbits(qx, qy);
     if (nb == 0) {
         vis.point(qx, qy, -1, -1);
         return 1;
@@ -133,14 +198,86 @@ SVB_HD int trace_loop(const View &m, int qx, int qy, int dv, int max_steps, Visi
     for (;;) {
         vis.point(x, y, din, dout);
         if (++n > max_steps) return -1;
+        const int dy = dir_dy(dout);
         x += dir_dx(dout);
-        y += dir_dy(dout);
+        y += dy;
         din = dout;
-        nb = m.nbits(x, y);
+        cur.moved(x, y, dy);
+        nb = cur.nbits(x, y);
         dout = next_ccw(nb, (din + 4) & 7);    // scan starts just after the pixel we came from
         if (x == qx && y == qy && dout == m0) break;
     }
     return n;
+}
+
+// ---- probe crossings and segments ----------------------------------------------------------------------------------
+// A "crossing" is a border-walk state on a probe line: pixel (x,y) foreground with x % P == 0 and the N neighbour
+// background (vertical, id = (x/P)*h + y), or y % P == 0 and the W neighbour background (horizontal,
+// id = nv*h + (y/P)*w + x).  Every border loop that matters passes through at least one crossing; walking from
+// each crossing only until the NEXT crossing splits every loop into independent segments, so each loop is walked
+// once in total (not once per crossing) and the longest dependent chain is a segment, not a loop.
+// A horizontal crossing whose N and NW neighbours are background too is the same walk state as the vertical
+// crossing of that pixel: it is an alias and is dropped.
+SVB_HD bool h_crossing_is_alias(unsigned nb, int x, int pitch) {
+    return (x % pitch == 0) && !(nb & (1u << DIR_N)) && !(nb & (1u << 3));
+}
+struct Seg {
+    long long area2;  // sum over the segment's steps of (x_i * y_{i+1} - x_{i+1} * y_i)
+    int next_id;      // probe id of the crossing that ends the segment (-1: step limit hit)
+    int min_idx;      // raster-min pixel of the segment
+    int steps;
+    int pad;
+};
+
+template <class View>
+SVB_HD Seg trace_segment(const View &m, int qx, int qy, int dv, int pitch, int nv, int max_steps) {
+    Seg sg;
+    sg.area2 = 0;
+    sg.min_idx = qy * m.w + qx;
+    sg.steps = 0;
+    sg.pad = 0;
+    const int self = (dv == DIR_N) ? (qx / pitch) * m.h + qy : nv * m.h + (qy / pitch) * m.w + qx;
+    typename CursorOf<View>::type cur;
+    cur.init(m, qx, qy);
+    unsigned nb = cur.nbits(qx, qy);
+    if (nb == 0) {  // isolated pixel: a loop of one point
+        sg.next_id = self;
+        sg.steps = 1;
+        return sg;
+    }
+    int x = qx, y = qy, xr = qx % pitch, yr = qy % pitch, xl = qx / pitch, yl = qy / pitch;
+    int dout = next_ccw(nb, dv);
+    for (;;) {
+        const int dx = dir_dx(dout), dy = dir_dy(dout);
+        const int nx = x + dx, ny = y + dy;
+        sg.area2 += (long long)x * ny - (long long)nx * y;
+        if (++sg.steps > max_steps) {
+            sg.next_id = -1;
+            return sg;
+        }
+        x = nx;
+        y = ny;
+        xr += dx;  // x % pitch and x / pitch, maintained incrementally
+        if (xr == pitch) { xr = 0; ++xl; } else if (xr < 0) { xr = pitch - 1; --xl; }
+        yr += dy;
+        if (yr == pitch) { yr = 0; ++yl; } else if (yr < 0) { yr = pitch - 1; --yl; }
+        const int pd = (dout + 4) & 7;  // direction back to the pixel we came from
+        cur.moved(x, y, dy);
+        nb = cur.nbits(x, y);
+        dout = next_ccw(nb, pd);
+        // is this visit a crossing state?  its background arc is the directions strictly between pd and dout (CCW)
+        const int span = (dout - pd - 1) & 7;
+        if (xr == 0 && ((DIR_N - pd - 1) & 7) < span) {
+            sg.next_id = xl * m.h + y;
+            return sg;
+        }
+        if (yr == 0 && ((DIR_W - pd - 1) & 7) < span) {
+            sg.next_id = nv * m.h + yl * m.w + x;
+            return sg;
+        }
+        const int idx = y * m.w + x;
+        if (idx < sg.min_idx) sg.min_idx = idx;
+    }
 }
 
 // ---- visitors ---------------------------------------------------------------------------------

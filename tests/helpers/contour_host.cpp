@@ -36,32 +36,66 @@ static int run(const View &m, int h, int w, double min_area_ratio, double eps_ra
     const double min_area = min_area_ratio * (double)((long long)h * w);
     const int pitch = probe_pitch(min_area);
     const int nv = (w - 1) / pitch + 1, nh = (h - 1) / pitch + 1;
+    const int nprobe = nv * h + nh * w;
     const int max_steps = h * w * 2 + 16;
-    std::vector<Cand> raw;
     int traces = 0;
     long long steps = 0;
     int status = 0;
-    for (int id = 0; id < nv * h + nh * w; ++id) {
-        int x, y, dv;
+    // K2a.1: crossings (the device packs them with one atomicAdd per crossing)
+    std::vector<int> ids, map(nprobe, -1);
+    for (int id = 0; id < nprobe; ++id) {
+        int x, y;
         if (id < nv * h) {
-            x = (id / h) * pitch; y = id % h; dv = DIR_N;
+            x = (id / h) * pitch; y = id % h;
             if (!m.fg(x, y) || m.fg(x, y - 1)) continue;
         } else {
             int j = id - nv * h;
-            y = (j / w) * pitch; x = j % w; dv = DIR_W;
+            y = (j / w) * pitch; x = j % w;
             if (!m.fg(x, y) || m.fg(x - 1, y)) continue;
+            if (x % pitch == 0 && !m.fg(x, y - 1) && !m.fg(x - 1, y - 1)) continue;  // alias of the vertical crossing
         }
-        LoopStats st(w);
-        int npts = trace_loop(m, x, y, dv, max_steps, st);
-        ++traces; steps += npts;
-        if (npts < 0) { status |= 4; continue; }
-        if (st.area2 >= 0) continue;
-        if ((double)(-st.area2) * 0.5 < min_area) continue;
+        map[id] = (int)ids.size();
+        ids.push_back(id);
+    }
+    // K2a.2: one segment per crossing
+    std::vector<Seg> segs(ids.size());
+    for (size_t g = 0; g < ids.size(); ++g) {
+        const int id = ids[g];
+        int x, y, dv;
+        if (id < nv * h) { x = (id / h) * pitch; y = id % h; dv = DIR_N; }
+        else { int j = id - nv * h; y = (j / w) * pitch; x = j % w; dv = DIR_W; }
+        Seg sg = trace_segment(m, x, y, dv, pitch, nv, max_steps);
+        ++traces; steps += sg.steps;
+        if (sg.next_id < 0) status |= 4;
+        else {
+            if (map[sg.next_id] < 0) return -2;  // a segment ended on a pixel that is not a recorded crossing
+            sg.next_id = map[sg.next_id];
+        }
+        segs[g] = sg;
+    }
+    // K2a.3: link segments into loops; the smallest index of a loop is its leader
+    std::vector<Cand> raw;
+    const int total = (int)ids.size();
+    for (int g = 0; g < total; ++g) {
+        long long area2 = 0;
+        int min_idx = 0x7fffffff, cur = g;
+        bool ok = false;
+        for (int it = 0; it <= total; ++it) {
+            const Seg &sg = segs[cur];
+            if (sg.next_id < 0) break;
+            area2 += sg.area2;
+            if (sg.min_idx < min_idx) min_idx = sg.min_idx;
+            cur = sg.next_id;
+            if (cur < g) break;
+            if (cur == g) { ok = true; break; }
+        }
+        if (!ok || area2 >= 0) continue;
+        if ((double)(-area2) * 0.5 < min_area) continue;
         bool dup = false;
-        for (auto &c : raw) dup |= (c.min_idx == st.min_idx);  // the device uses an atomicCAS set for this
+        for (auto &c : raw) dup |= (c.min_idx == min_idx);  // the device uses an atomicCAS set for this
         if (dup) continue;
         if ((int)raw.size() >= MAXC) { status |= 1; continue; }
-        raw.push_back(Cand{-st.area2, st.min_idx, 0});
+        raw.push_back(Cand{-area2, min_idx, 0});
     }
     if (n_probe_traces) *n_probe_traces = traces;
     if (n_probe_steps) *n_probe_steps = steps;

@@ -69,3 +69,25 @@ def test_gauss_kernel_bits(oracle):
     # the constants compiled into the CUDA kernels (csrc/common.cuh)
     lits = np.array([0.00881222915, 0.0271435771, 0.0651140586, 0.121649072, 0.176998362, 0.200565413], np.float32)
     assert np.array_equal(lits.view(np.uint32), want)
+
+
+def test_product_contour_core_on_frames(oracle, golden, contour_host):
+    """The product's contour core (host build of csrc/contour_core.cuh), byte view and tiled-bit view with the
+    register-window walker, on the golden masks and on a 1080p synthetic frame."""
+    from svb200 import frames as F
+
+    masks = [(golden(n)["ref_mask"], golden(n)) for n in ("frame_a", "frame_b", "frame_c", "frame_none")]
+    for m, g in masks:
+        for bits in ((False, True) if m.shape[1] % 32 == 0 else (False,)):
+            f, c = contour_host(m, 0.1, 0.02, use_bits=bits)
+            assert (f == 1) == bool(g["ref_found"])
+            if f == 1:
+                assert np.array_equal(c, g["ref_corners"])
+    fr = F.make_frame(777, 1080, 1920, 40.0)
+    m = oracle.preprocess(F.add_noise_host(fr.image, 777))
+    want = oracle.find_grid_contour(m)
+    for bits in (False, True):
+        f, c = contour_host(m, 0.1, 0.02, use_bits=bits)
+        assert (f == 1) == (want is not None)
+        if want is not None:
+            assert np.array_equal(c, want)
