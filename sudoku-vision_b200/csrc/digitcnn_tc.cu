@@ -154,7 +154,7 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
         mbar_init(&s.mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) tmem_alloc(&s.tmem_base, 128);
+    if (warp == 0) tmem_alloc(&s.tmem_base, 256);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -246,22 +246,60 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
     // warp 15 only issues MMAs (a ~5k-cycle serial instruction stream per cell); keeping it out of the conv1
     // barriers lets the 15 worker warps convolve the next cell at full speed meanwhile
     const bool mma_warp = (warp == 15);
-    long long cell = blockIdx.x;
+    // epilogue of one cell from TMEM buffer `buf`: TMEM -> 2x2 max-pool (shuffles) -> bias/ReLU -> fp16 hi/lo features.
+    // 16 warps: TMEM lane quarter q = warp % 4 (hardware rule), tile j, 32-column half of the 64 channels.
+    auto epilogue = [&](long long cell_e, int buf) {
+        const int j = (warp >> 2) & 1, q = warp & 3, half = warp >> 3;
+        const int py = 4 * j + q - 1;  // pooled row produced by this warp (rows y_p = 2(4j+q), +1)
+        const bool writer = (lane < 14) && !(lane & 1) && py >= 0 && py < 7;
+        const int px = lane >> 1;
+        __half *fh = feat_hi + (cell_e * 49 + (long long)(py * 7 + px)) * 64;
+        __half *fl = feat_lo + (cell_e * 49 + (long long)(py * 7 + px)) * 64;
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + j * 64 + half * 32), v);
+        __half hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            float f = __uint_as_float(v[c]);
+            f = fmaxf(f, __shfl_xor_sync(0xffffffffu, f, 1));
+            f = fmaxf(f, __shfl_xor_sync(0xffffffffu, f, 16));
+            f = fmaxf(f + s.b2[half * 32 + c], 0.f);
+            split_hi_lo(f, hi[c], lo[c]);
+        }
+        if (writer) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                reinterpret_cast<uint4 *>(fh + half * 32)[k] = reinterpret_cast<const uint4 *>(hi)[k];
+                reinterpret_cast<uint4 *>(fl + half * 32)[k] = reinterpret_cast<const uint4 *>(lo)[k];
+            }
+        }
+    };
+
+    // Pipeline over cells (TMEM double-buffered: two accumulator sets of 128 columns):
+    //   wait MMA(i-1) -> write S(i) -> [barrier] -> MMA(i) issued (async)  ||  epilogue(i-1), then conv1(i+1) in registers
+    long long cell = blockIdx.x, prev_cell = -1;
+    int it = 0;
     if (cell < n_cells && !mma_warp) {
         stage_input(cell);
         bar_workers();
         conv1_regs();
     }
-    for (; cell < n_cells; cell += gridDim.x) {
+    for (; cell < n_cells; cell += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (it > 0) {  // S is read by the previous cell's MMAs until they commit
+            mbar_wait(&s.mbar, phase);
+            phase ^= 1;
+        }
         if (!mma_warp) write_S();
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
         tc_fence_before();
-        __syncthreads();      // also: every thread has finished reading TMEM / s.inp of the previous cell
+        __syncthreads();      // S(i) complete; every epilogue read of TMEM buffer `buf` (cell i-2) has retired
         // ---- implicit-GEMM conv2 on tcgen05: 2 tiles x 3 splits x 9 taps x 2 k-steps, fully unrolled ------------
         if (mma_warp) {
             // The whole warp runs the (uniform) descriptor arithmetic so it stays on the uniform datapath;
             // only the tcgen05 instructions themselves are predicated on one elected lane.
             tc_fence_after();
+            const uint32_t tacc = tmem + (uint32_t)(buf * 128);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
 #pragma unroll
@@ -276,7 +314,7 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
                         for (int ks = 0; ks < 2; ++ks) {
                             const uint64_t ad = a_desc0 + (uint64_t)((a_off + ks * 256) >> 4);
                             const uint64_t bd = b_desc0 + (uint64_t)((b_off + ks * 256) >> 4);
-                            if (lane == 0) umma_f16(tmem + (uint32_t)(j * 64), ad, bd, idesc, (combo | t | ks) ? 1u : 0u);
+                            if (lane == 0) umma_f16(tacc + (uint32_t)(j * 64), ad, bd, idesc, (combo | t | ks) ? 1u : 0u);
                         }
                     }
                 }
@@ -284,50 +322,28 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
             if (lane == 0) umma_commit(&s.mbar);
             __syncwarp();
         }
-        // ---- overlap: stage and convolve the next cell while the MMAs run ---------------------------------------------
+        // ---- overlapped with the MMAs: epilogue of the previous cell, then conv1 of the next one ---------------------
+        if (it > 0) {
+            tc_fence_after();
+            epilogue(prev_cell, buf ^ 1);
+        }
         const long long next = cell + gridDim.x;
         if (next < n_cells && !mma_warp) {
             stage_input(next);
             bar_workers();
             conv1_regs();
         }
+        prev_cell = cell;
+    }
+    if (it > 0) {  // drain: last cell
         mbar_wait(&s.mbar, phase);
         phase ^= 1;
         tc_fence_after();
-        // ---- epilogue: TMEM -> pool -> bias/ReLU -> fp16 hi/lo features -------------------------------------------------
-        {
-            // 16 warps: TMEM lane quarter q = warp % 4 (hardware rule), tile j, 32-column half of the 64 channels
-            const int j = (warp >> 2) & 1, q = warp & 3, half = warp >> 3;
-            const int py = 4 * j + q - 1;  // pooled row produced by this warp (rows y_p = 2(4j+q), +1)
-            const bool writer = (lane < 14) && !(lane & 1) && py >= 0 && py < 7;
-            const int px = lane >> 1;
-            __half *fh = feat_hi + (cell * 49 + (long long)(py * 7 + px)) * 64;
-            __half *fl = feat_lo + (cell * 49 + (long long)(py * 7 + px)) * 64;
-            {
-                uint32_t v[32];
-                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 64 + half * 32), v);
-                __half hi[32], lo[32];
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    float f = __uint_as_float(v[c]);
-                    f = fmaxf(f, __shfl_xor_sync(0xffffffffu, f, 1));
-                    f = fmaxf(f, __shfl_xor_sync(0xffffffffu, f, 16));
-                    f = fmaxf(f + s.b2[half * 32 + c], 0.f);
-                    split_hi_lo(f, hi[c], lo[c]);
-                }
-                if (writer) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        reinterpret_cast<uint4 *>(fh + half * 32)[k] = reinterpret_cast<const uint4 *>(hi)[k];
-                        reinterpret_cast<uint4 *>(fl + half * 32)[k] = reinterpret_cast<const uint4 *>(lo)[k];
-                    }
-                }
-            }
-        }
+        epilogue(prev_cell, (it - 1) & 1);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 128);
+    if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
 // ================================================================================================
