@@ -108,12 +108,12 @@ constexpr int GW = NT * CPT;          // 512 gray columns staged per strip
 constexpr int HALO = 16;              // px, each side (>= 7 needed; 16 keeps TMA 16-B aligned)
 constexpr int TW = GW - 2 * HALO;     // 480 output columns per strip
 constexpr int R = 4;                  // rows per block iteration
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 2;
 constexpr int RAW_ROW = GW * 3;       // bytes per staged row
 
 struct __align__(128) Smem {
     uint8_t raw[NSTAGE][R][RAW_ROW];  // TMA destination (18 KB)
-    float4 rp[16][NT];                // rowpass ring, thread-private columns (32 KB)
+    float4 rp[12][NT];                // rowpass ring (index (row + 2) % 12), thread-private columns (24 KB)
     uint2 hb[8][NT];                  // horizontal 5-tap sums (4 x u16), thread-private (8 KB)
     uint32_t bx[16][NT];              // blurred rows, packed u8x4: ring + exchange (8 KB)
     uint32_t g[R][NT];                // gray rows, packed u8x4: exchange (2 KB)
@@ -165,8 +165,9 @@ __device__ __forceinline__ void fast_block(Smem &sm, const int q /* r0 >> 2 */, 
     // of slot bases computed once here (one code copy for all ring phases keeps the loop inside the I-cache).
     uint2 (*hb_cur)[NT] = &sm.hb[4 * (q & 1)], (*hb_old)[NT] = &sm.hb[4 * ((q + 1) & 1)];
     uint32_t (*bx0)[NT] = &sm.bx[4 * (q & 3)], (*bx1)[NT] = &sm.bx[4 * ((q + 3) & 3)], (*bx2)[NT] = &sm.bx[4 * ((q + 2) & 3)];
-    float4 (*rp0)[NT] = &sm.rp[4 * (q & 3)], (*rp1)[NT] = &sm.rp[4 * ((q + 3) & 3)], (*rp2)[NT] = &sm.rp[4 * ((q + 2) & 3)],
-           (*rp3)[NT] = &sm.rp[4 * ((q + 1) & 3)];
+    // rp ring: 3 slots; the slot written now also still holds rows r0-12, r0-11 (entries 2,3), read first
+    const int q3 = q % 3;
+    float4 (*rp0)[NT] = &sm.rp[4 * q3], (*rp1)[NT] = &sm.rp[4 * ((q3 + 2) % 3)], (*rp2)[NT] = &sm.rp[4 * ((q3 + 1) % 3)];
     // ---- phase 1: raw BGR -> gray -----------------------------------------------------------------------
     uint32_t gq[R];
 #pragma unroll
@@ -240,6 +241,9 @@ __device__ __forceinline__ void fast_block(Smem &sm, const int q /* r0 >> 2 */, 
     const float2 k0 = make_float2(SVB_G11_0, SVB_G11_0), k1 = make_float2(SVB_G11_1, SVB_G11_1),
                  k2 = make_float2(SVB_G11_2, SVB_G11_2), k3 = make_float2(SVB_G11_3, SVB_G11_3),
                  k4 = make_float2(SVB_G11_4, SVB_G11_4), k5 = make_float2(SVB_G11_5, SVB_G11_5);
+    float4 Rw[14];  // row-pass rows r0-12 .. r0+1
+    Rw[0] = rp0[2][t];  // rows r0-12, r0-11: loaded before this block's rows overwrite the slot
+    Rw[1] = rp0[3][t];
     float4 RPn[4];  // row-pass results of rows r0-2 .. r0+1
 #pragma unroll
     for (int pr = 0; pr < 2; ++pr) {
@@ -277,9 +281,6 @@ __device__ __forceinline__ void fast_block(Smem &sm, const int q /* r0 >> 2 */, 
         rp0[2 * pr + 1][t] = RPn[2 * pr + 1];
     }
     // ---- phase 5: vertical 11-tap (symmetric), rint, threshold -> 4 output rows y = r0-7 .. r0-4 -------------------
-    float4 Rw[14];  // row-pass rows r0-12 .. r0+1
-    Rw[0] = rp3[2][t];  // ring index (row + 2): rows r0-12, r0-11 are entries 2,3 of the slot three blocks back
-    Rw[1] = rp3[3][t];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         Rw[2 + j] = rp2[j][t];
@@ -313,7 +314,7 @@ __device__ __forceinline__ void fast_block(Smem &sm, const int q /* r0 >> 2 */, 
 }
 
 template <bool INVERTED>
-__global__ void __launch_bounds__(NT, 3)
+__global__ void __launch_bounds__(NT, 4)
 fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ mask, int h, int w, int rows_per_seg) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
@@ -352,10 +353,7 @@ fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ m
             tma_load_1d(&sm.raw[stage][r][dst_off], frame + ((long long)(r0 + r) * w + col_lo) * 3, row_bytes,
                         &sm.full[stage]);
     };
-    if (t == 0) {
-        issue(0);
-        issue(1);
-    }
+    if (t == 0) issue(0);
 
     // my 4 columns
     const int c0 = xg0 + CPT * t;
@@ -375,7 +373,7 @@ fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ m
         const int stage = blk % NSTAGE;
         const int r0 = gs + blk * R;
         const int nrows = min(R, ge - r0);
-        if (t == 0) issue(blk + 2);
+        if (t == 0) issue(blk + 1);
         mbar_wait(&sm.full[stage], (uint32_t)((blk / NSTAGE) & 1));
 
         // interior block: every row it touches is inside the image and inside this segment's schedule
@@ -465,8 +463,12 @@ fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ m
             __syncthreads();
         }
 
-        // ---- phase 4: horizontal 11-tap (float FMA chain) -> rowpass ring ------------------------
+        // ---- phases 4+5: per new blurred row: horizontal 11-tap -> rowpass ring, then every output row whose
+        //      11-row window is complete (at most 11 ring rows are live at any time: the ring holds 12)
+        const int b_last = b_hi;
+        const int y_hi = (b_last >= h - 1) ? (ye - 1) : min(ye - 1, b_last - 5);
         if (is_out) {
+            int yo = y_next;
             for (int b = b_first; b <= b_hi; ++b) {
                 const uint32_t *brow = sm.bx[(b + 2) & 15];
                 uint32_t q0 = brow[t - 2], q1 = brow[t - 1], q2 = brow[t], q3 = brow[t + 1], q4 = brow[t + 2];
@@ -493,35 +495,31 @@ fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ m
                     acc = __fmaf_rn(kf[0], f[j + 10], acc);
                     o[j] = acc;
                 }
-                sm.rp[(b + 2) & 15][t] = make_float4(o[0], o[1], o[2], o[3]);
-            }
-        }
-
-        // ---- phase 5: vertical 11-tap (symmetric FMA) + rint + threshold -> mask -------------------
-        const int b_last = b_hi;
-        const int y_hi = (b_last >= h - 1) ? (ye - 1) : min(ye - 1, b_last - 5);
-        if (is_out) {
-            for (int y = y_next; y <= y_hi; ++y) {
-                float4 c = sm.rp[(y + 2) & 15][t];
-                float a0 = __fmul_rn(kf[5], c.x), a1 = __fmul_rn(kf[5], c.y), a2 = __fmul_rn(kf[5], c.z), a3 = __fmul_rn(kf[5], c.w);
+                sm.rp[(b + 2) % 12][t] = make_float4(o[0], o[1], o[2], o[3]);
+                // vertical 11-tap (symmetric FMA) + rint + threshold for the rows that became computable
+                while (yo <= y_hi && min(yo + 5, h - 1) <= b) {
+                    const int y = yo++;
+                    float4 c = sm.rp[(y + 2) % 12][t];
+                    float a0 = __fmul_rn(kf[5], c.x), a1 = __fmul_rn(kf[5], c.y), a2 = __fmul_rn(kf[5], c.z), a3 = __fmul_rn(kf[5], c.w);
 #pragma unroll
-                for (int j = 1; j <= 5; ++j) {
-                    float4 u = sm.rp[(clampi(y + j, 0, h - 1) + 2) & 15][t];
-                    float4 d = sm.rp[(clampi(y - j, 0, h - 1) + 2) & 15][t];
-                    const float kk = kf[5 - j];
-                    a0 = __fmaf_rn(kk, __fadd_rn(u.x, d.x), a0);
-                    a1 = __fmaf_rn(kk, __fadd_rn(u.y, d.y), a1);
-                    a2 = __fmaf_rn(kk, __fadd_rn(u.z, d.z), a2);
-                    a3 = __fmaf_rn(kk, __fadd_rn(u.w, d.w), a3);
+                    for (int j = 1; j <= 5; ++j) {
+                        float4 u = sm.rp[(clampi(y + j, 0, h - 1) + 2) % 12][t];
+                        float4 d = sm.rp[(clampi(y - j, 0, h - 1) + 2) % 12][t];
+                        const float kk = kf[5 - j];
+                        a0 = __fmaf_rn(kk, __fadd_rn(u.x, d.x), a0);
+                        a1 = __fmaf_rn(kk, __fadd_rn(u.y, d.y), a1);
+                        a2 = __fmaf_rn(kk, __fadd_rn(u.z, d.z), a2);
+                        a3 = __fmaf_rn(kk, __fadd_rn(u.w, d.w), a3);
+                    }
+                    uint32_t src = sm.bx[(y + 2) & 15][t];
+                    int m0 = rint_pos(a0), m1 = rint_pos(a1), m2 = rint_pos(a2), m3 = rint_pos(a3);
+                    // BINARY_INV: 255 iff src - mean <= -2 ; BINARY: 255 iff src - mean > -2
+                    bool p0 = (int)(src & 0xff) - m0 <= -2, p1 = (int)((src >> 8) & 0xff) - m1 <= -2;
+                    bool p2 = (int)((src >> 16) & 0xff) - m2 <= -2, p3 = (int)(src >> 24) - m3 <= -2;
+                    if (!INVERTED) { p0 = !p0; p1 = !p1; p2 = !p2; p3 = !p3; }
+                    uint32_t o32 = (p0 ? 0xffu : 0u) | (p1 ? 0xff00u : 0u) | (p2 ? 0xff0000u : 0u) | (p3 ? 0xff000000u : 0u);
+                    *reinterpret_cast<uint32_t *>(out + (long long)y * w + c0) = o32;
                 }
-                uint32_t src = sm.bx[(y + 2) & 15][t];
-                int m0 = rint_pos(a0), m1 = rint_pos(a1), m2 = rint_pos(a2), m3 = rint_pos(a3);
-                // BINARY_INV: 255 iff src - mean <= -2 ; BINARY: 255 iff src - mean > -2
-                bool p0 = (int)(src & 0xff) - m0 <= -2, p1 = (int)((src >> 8) & 0xff) - m1 <= -2;
-                bool p2 = (int)((src >> 16) & 0xff) - m2 <= -2, p3 = (int)(src >> 24) - m3 <= -2;
-                if (!INVERTED) { p0 = !p0; p1 = !p1; p2 = !p2; p3 = !p3; }
-                uint32_t o = (p0 ? 0xffu : 0u) | (p1 ? 0xff00u : 0u) | (p2 ? 0xff0000u : 0u) | (p3 ? 0xff000000u : 0u);
-                *reinterpret_cast<uint32_t *>(out + (long long)y * w + c0) = o;
             }
         }
         y_next = max(y_next, y_hi + 1);
