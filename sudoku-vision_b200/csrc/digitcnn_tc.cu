@@ -172,6 +172,18 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
         const float *xin = x + cell * 784;
         for (int i = tid; i < 784; i += NWK) s.inp[(i / 28 + 1) * 32 + (i % 28) + 1] = xin[i];
     };
+    // the same in two halves, so that the global-load latency hides behind other work: each worker thread
+    // owns pixels tid and tid + 480 of the 784
+    float pre0 = 0.f, pre1 = 0.f;
+    auto prefetch_input = [&](long long cell) {
+        const float *xin = x + cell * 784;
+        pre0 = __ldg(xin + tid);
+        if (tid + NWK < 784) pre1 = __ldg(xin + tid + NWK);
+    };
+    auto commit_input = [&]() {
+        s.inp[(tid / 28 + 1) * 32 + (tid % 28) + 1] = pre0;
+        if (tid + NWK < 784) s.inp[((tid + NWK) / 28 + 1) * 32 + ((tid + NWK) % 28) + 1] = pre1;
+    };
     // conv1 + bias + ReLU + 2x2 max-pool for this thread's items -> fp16 hi/lo in registers
     auto conv1_regs = [&]() {
 #pragma unroll
@@ -286,6 +298,8 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
     }
     for (; cell < n_cells; cell += gridDim.x, ++it) {
         const int buf = it & 1;
+        const long long next = cell + gridDim.x;
+        if (next < n_cells && !mma_warp) prefetch_input(next);  // lands while we wait, write S and run the epilogue
         if (it > 0) {  // S is read by the previous cell's MMAs until they commit
             mbar_wait(&s.mbar, phase);
             phase ^= 1;
@@ -327,9 +341,8 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
             tc_fence_after();
             epilogue(prev_cell, buf ^ 1);
         }
-        const long long next = cell + gridDim.x;
         if (next < n_cells && !mma_warp) {
-            stage_input(next);
+            commit_input();
             bar_workers();
             conv1_regs();
         }
