@@ -76,6 +76,13 @@ int svb_preprocess_v1(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uin
  * corners: int32 [n][4][2] (x, y) in approxPolyDP output order; found: uint8 [n] (0 = None). */
 int svb_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, int w, double min_area_ratio,
                           double eps_ratio, int32_t *corners, uint8_t *found, void *stream);
+/* v2 contour method: detect_grid_contour(binary, min_area_ratio=0.1)  cv/grid_v2.py:102-128 — as above, but a
+ * 4-gon must also pass is_valid_quadrilateral (cv/grid_v2.py:64-95: angles in [45,135] deg, longest side <= 2x
+ * shortest) or the search continues with the next contour; corners come back ORDERED (order_points,
+ * cv/grid_v2.py:49-61: TL, TR, BR, BL) as int32 [n][4][2] (the reference returns the same values as float32).
+ * This is method 1 of detect_grid (cv/grid_v2.py:427-437); the Hough / rotation / Harris fallbacks are not built. */
+int svb_detect_grid_contour_v2(svb_ctx *ctx, const uint8_t *mask, int n, int h, int w, double min_area_ratio,
+                               int32_t *corners, uint8_t *found, void *stream);
 /* order_points + getPerspectiveTransform + warpPerspective  cv/grid.py:74-133 (inset_ratio 0).
  * board: uint8 [n][out_size][out_size][3]; frames with found == 0 produce an all-zero board.
  * `found` may be NULL (all frames valid). */

@@ -45,7 +45,7 @@ int launch_blur5(svb_ctx *, const uint8_t *, int, int, int, uint8_t *, cudaStrea
 int launch_adaptive(svb_ctx *, const uint8_t *, int, int, int, int, uint8_t *, cudaStream_t);
 bool fused_preprocess_supported(int h, int w);
 int launch_fused_preprocess(svb_ctx *, const uint8_t *, int, int, int, uint8_t *, cudaStream_t);
-int launch_find_grid_contour(svb_ctx *, const uint8_t *, int, int, int, double, double, int32_t *, uint8_t *, cudaStream_t);
+int launch_find_grid_contour(svb_ctx *, const uint8_t *, int, int, int, double, double, int32_t *, uint8_t *, cudaStream_t, int v2_mode = 0);
 int launch_warp_board(svb_ctx *, const uint8_t *, int, int, int, const int32_t *, const uint8_t *, int, uint8_t *, cudaStream_t);
 int launch_extract_cells(svb_ctx *, const uint8_t *, int, int, uint8_t *, cudaStream_t);
 int launch_cell_prep(svb_ctx *, const uint8_t *, long long, uint8_t *, float *, cudaStream_t);
@@ -182,6 +182,14 @@ API int svb_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, i
     SVB_REQUIRE(w <= 65535, SVB_ERR_UNSUPPORTED, "svb_find_grid_contour: width above 65535");
     SVB_REQUIRE(min_area_ratio > 0.0 && eps_ratio >= 0.0, SVB_ERR_INVALID, "svb_find_grid_contour: ratios must be positive");
     return launch_find_grid_contour(ctx, mask, n, h, w, min_area_ratio, eps_ratio, corners, found, (cudaStream_t)stream);
+}
+
+API int svb_detect_grid_contour_v2(svb_ctx *ctx, const uint8_t *mask, int n, int h, int w, double min_area_ratio,
+                                   int32_t *corners, uint8_t *found, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(mask && corners && found && dims_ok(n, h, w), SVB_ERR_INVALID, "svb_detect_grid_contour_v2: bad arguments");
+    SVB_REQUIRE(w <= 65535 && min_area_ratio > 0.0, SVB_ERR_INVALID, "svb_detect_grid_contour_v2: bad size or ratio");
+    return launch_find_grid_contour(ctx, mask, n, h, w, min_area_ratio, 0.02, corners, found, (cudaStream_t)stream, 1);
 }
 
 API int svb_warp_perspective(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, const int32_t *corners,

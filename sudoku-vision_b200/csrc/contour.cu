@@ -210,7 +210,7 @@ struct WarpReduce {
 template <class View>
 __global__ void __launch_bounds__(128)
 select_quad_kernel(const void *__restrict__ mask, int n, int h, int w, int wp, double eps_ratio, int max_steps,
-                   FrameScratch fs, int32_t *__restrict__ corners, uint8_t *__restrict__ found) {
+                   FrameScratch fs, int32_t *__restrict__ corners, uint8_t *__restrict__ found, int v2_mode) {
     __shared__ Slice stacks[4][STACK_CAP];
     __shared__ Cand lists[4][MAXC];
     __shared__ Cand raws[4][MAXC];
@@ -234,7 +234,7 @@ select_quad_kernel(const void *__restrict__ mask, int n, int h, int w, int wp, d
     const int got = select_quad<WarpReduce>(m, raws[warp], nraw, lists[warp],
                                             nested[warp], fs.chain + (long long)frame * fs.cap,
                                             fs.poly + (long long)frame * fs.cap, fs.cap, stacks[warp], max_steps,
-                                            eps_ratio, out, &status);
+                                            eps_ratio, out, &status, v2_mode);
     if (lane == 0) {
         status |= fs.status[frame];
         // status != 0: a scratch capacity was hit -> report 2 so that the caller fails loudly
@@ -248,7 +248,7 @@ select_quad_kernel(const void *__restrict__ mask, int n, int h, int w, int wp, d
 }  // namespace k2
 
 int launch_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, int w, double min_area_ratio,
-                             double eps_ratio, int32_t *corners, uint8_t *found, cudaStream_t st) {
+                             double eps_ratio, int32_t *corners, uint8_t *found, cudaStream_t st, int v2_mode) {
     using namespace k2;
     const double min_area = min_area_ratio * (double)((long long)h * w);
     const int pitch = contour::probe_pitch(min_area);
@@ -325,9 +325,9 @@ int launch_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, in
     rc = check_launch(ctx, "k2::link_loops_kernel");
     if (rc) return rc;
     if (use_bits)
-        select_quad_kernel<BitMaskView><<<(n + 3) / 4, 128, 0, st>>>(view_ptr, n, h, w, wp, eps_ratio, max_steps, fs, corners, found);
+        select_quad_kernel<BitMaskView><<<(n + 3) / 4, 128, 0, st>>>(view_ptr, n, h, w, wp, eps_ratio, max_steps, fs, corners, found, v2_mode);
     else
-        select_quad_kernel<MaskView><<<(n + 3) / 4, 128, 0, st>>>(view_ptr, n, h, w, 0, eps_ratio, max_steps, fs, corners, found);
+        select_quad_kernel<MaskView><<<(n + 3) / 4, 128, 0, st>>>(view_ptr, n, h, w, 0, eps_ratio, max_steps, fs, corners, found, v2_mode);
     return check_launch(ctx, "k2::select_quad_kernel");
 }
 

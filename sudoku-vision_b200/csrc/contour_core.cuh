@@ -519,6 +519,47 @@ SVB_HD int approx_cleanup(uint32_t *out, int m, double eps) {
     return new_count;
 }
 
+// ---- v2 extras: cv/grid_v2.py:49-95 ----------------------------------------------------------------------------
+// order_points: TL = argmin(x+y), BR = argmax(x+y), TR = argmin(y-x), BL = argmax(y-x); first index wins ties.
+SVB_HD void order_points4(const int32_t *c, int32_t *out) {
+    int is_min = 0, is_max = 0, id_min = 0, id_max = 0;
+    for (int i = 1; i < 4; ++i) {
+        const int s = c[2 * i] + c[2 * i + 1], d = c[2 * i + 1] - c[2 * i];
+        if (s < c[2 * is_min] + c[2 * is_min + 1]) is_min = i;
+        if (s > c[2 * is_max] + c[2 * is_max + 1]) is_max = i;
+        if (d < c[2 * id_min + 1] - c[2 * id_min]) id_min = i;
+        if (d > c[2 * id_max + 1] - c[2 * id_max]) id_max = i;
+    }
+    const int idx[4] = {is_min, id_min, is_max, id_max};
+    for (int i = 0; i < 4; ++i) {
+        out[2 * i] = c[2 * idx[i]];
+        out[2 * i + 1] = c[2 * idx[i] + 1];
+    }
+}
+// is_valid_quadrilateral(corners, 45, 135): every interior angle within [45, 135] degrees and the longest side
+// at most twice the shortest; float32 arithmetic as numpy does it on float32 corners.
+SVB_HD bool quad_is_valid_v2(const int32_t *c) {
+    float side[4];
+    for (int i = 0; i < 4; ++i) {
+        const int i1 = (i + 1) & 3, i2 = (i + 2) & 3;
+        const float v1x = (float)(c[2 * i] - c[2 * i1]), v1y = (float)(c[2 * i + 1] - c[2 * i1 + 1]);
+        const float v2x = (float)(c[2 * i2] - c[2 * i1]), v2y = (float)(c[2 * i2 + 1] - c[2 * i1 + 1]);
+        const float dot = v1x * v2x + v1y * v2y;
+        const float n1 = sqrtf(v1x * v1x + v1y * v1y), n2 = sqrtf(v2x * v2x + v2y * v2y);
+        float cs = dot / (n1 * n2 + 1e-6f);
+        cs = cs < -1.0f ? -1.0f : (cs > 1.0f ? 1.0f : cs);
+        const float angle = acosf(cs) * 57.29577951308232f;
+        if (angle < 45.0f || angle > 135.0f) return false;
+        side[i] = n1;  // |c[i] - c[i+1]|
+    }
+    float mn = side[0], mx = side[0];
+    for (int i = 1; i < 4; ++i) {
+        mn = side[i] < mn ? side[i] : mn;
+        mx = side[i] > mx ? side[i] : mx;
+    }
+    return !(mx > 2.0f * mn);
+}
+
 // ---- per-frame candidate selection (cv/grid.py:55-71) ------------------------------------------------
 struct Cand {
     long long area2;  // |signed shoelace| x 2 of an outer border
@@ -535,7 +576,7 @@ constexpr int STACK_CAP = 96;  // DP slice stack
 template <class Red, class View>
 SVB_HD int select_quad(const View &m, const Cand *raw, int raw_count, Cand *list, int *nested, uint32_t *chain,
                        uint32_t *poly, int cap, Slice *stack, int max_steps, double eps_ratio, int32_t *corners,
-                       int *status_out) {
+                       int *status_out, int v2_mode = 0) {
     const int lane = Red::lane();
     const int w = m.w;
     int nc = 0;
@@ -598,12 +639,19 @@ SVB_HD int select_quad(const View &m, const Cand *raw, int raw_count, Cand *list
         mv = Red::bcast(mv);
         Red::sync();
         if (mv == 4) {
+            int32_t q[8];
+            for (int k = 0; k < 4; ++k) {
+                q[2 * k] = pt_x(poly[k]);
+                q[2 * k + 1] = pt_y(poly[k]);
+            }
+            // v2 (cv/grid_v2.py:102-128): a 4-gon that is not roughly rectangular is skipped, the search goes on
+            if (v2_mode && !quad_is_valid_v2(q)) continue;
             got = 1;
-            if (lane == 0)
-                for (int k = 0; k < 4; ++k) {
-                    corners[2 * k] = pt_x(poly[k]);
-                    corners[2 * k + 1] = pt_y(poly[k]);
-                }
+            if (lane == 0) {
+                if (v2_mode) order_points4(q, corners);
+                else
+                    for (int k = 0; k < 8; ++k) corners[k] = q[k];
+            }
         }
     }
     *status_out = status;

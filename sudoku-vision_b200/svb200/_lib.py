@@ -28,6 +28,7 @@ SIGNATURES = {
     "svb_adaptive_threshold": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "svb_preprocess_v1": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "svb_find_grid_contour": (_i, [_p, _p, _i, _i, _i, _d, _d, _p, _p, _p]),
+    "svb_detect_grid_contour_v2": (_i, [_p, _p, _i, _i, _i, _d, _p, _p, _p]),
     "svb_warp_perspective": (_i, [_p, _p, _i, _i, _i, _p, _p, _i, _p, _p]),
     "svb_extract_cells": (_i, [_p, _p, _i, _i, _p, _p]),
     "svb_cell_prep": (_i, [_p, _p, _ll, _p, _p, _p]),

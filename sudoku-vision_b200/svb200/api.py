@@ -166,6 +166,17 @@ class Scanner:
                    "svb_find_grid_contour")
         return corners, found
 
+    def detect_grid_contour_v2(self, mask, min_area_ratio: float = 0.1):
+        """cv/grid_v2.py:102-128 (method 1 of detect_grid): ordered corners (n,4,2) int32 + found (n,)."""
+        self._chk_u8(mask, 3, "detect_grid_contour_v2")
+        torch = _torch()
+        n, h, w = mask.shape
+        corners = torch.empty((n, 4, 2), dtype=torch.int32, device=mask.device)
+        found = torch.empty((n,), dtype=torch.uint8, device=mask.device)
+        _lib.check(self.lib.svb_detect_grid_contour_v2(self._h, _ptr(mask), n, h, w, float(min_area_ratio), _ptr(corners),
+                                                       _ptr(found), self._stream()), "svb_detect_grid_contour_v2")
+        return corners, found
+
     def warp_perspective(self, bgr, corners, found=None, out_size: int = 450):
         self._chk_u8(bgr, 4, "warp_perspective")
         torch = _torch()

@@ -57,12 +57,12 @@ def contour_host():
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-ffp-contract=off", "-o", so, src])
     lib = C.CDLL(so)
 
-    def find(mask, min_area_ratio=0.1, eps_ratio=0.02, use_bits=False):
+    def find(mask, min_area_ratio=0.1, eps_ratio=0.02, use_bits=False, v2=False):
         mask = np.ascontiguousarray(mask, np.uint8)
         c = np.zeros((4, 2), np.int32)
         f = lib.svbh_find_grid_contour(mask.ctypes.data_as(C.c_void_p), mask.shape[0], mask.shape[1],
                                        C.c_double(min_area_ratio), C.c_double(eps_ratio),
-                                       c.ctypes.data_as(C.c_void_p), None, None, int(use_bits))
+                                       c.ctypes.data_as(C.c_void_p), None, None, int(use_bits) | (2 if v2 else 0))
         return f, c
 
     return find

@@ -106,6 +106,24 @@ def main():
         im = cv2.imread(os.path.join(REF, "data", "test_images", f"sample_{k}.jpg"))
         c = find_grid_contour(preprocess_for_grid_detection(im))
         unit[f"photo{k}_corners"] = np.zeros((0, 2), np.int32) if c is None else c.astype(np.int32)
+    # v2 contour method (cv/grid_v2.py:102-128) on the golden masks and on quadrilaterals that fail its validity test
+    sys.path.insert(0, os.path.join(REF, "cv"))
+    import grid_v2 as ref_v2  # noqa: E402
+    v2 = {}
+    for name in ("frame_a", "frame_b", "frame_c", "photo4_dec8", "frame_none"):
+        m = np.load(os.path.join(HERE, name + ".npz"))["ref_mask"]
+        c = ref_v2.detect_grid_contour(m)
+        v2[f"{name}_corners"] = np.zeros((0, 2), np.float32) if c is None else c
+    shapes = []
+    for k, pts in enumerate(([[20, 30], [200, 25], [210, 60], [15, 70]],          # flat: sides ratio > 2
+                             [[30, 20], [220, 30], [120, 180], [20, 170]],         # sheared: an angle outside [45,135]
+                             [[40, 40], [210, 35], [215, 200], [35, 205]])):       # fine
+        m = np.zeros((240, 256), np.uint8)
+        cv2.polylines(m, [np.array(pts, np.int32)], True, 255, 2)
+        c = ref_v2.detect_grid_contour(m, 0.05)
+        v2[f"shape{k}_mask"] = m
+        v2[f"shape{k}_corners"] = np.zeros((0, 2), np.float32) if c is None else c
+    np.savez_compressed(os.path.join(HERE, "v2.npz"), **v2)
     np.savez_compressed(os.path.join(HERE, "unit.npz"), **unit)
     for fn in sorted(os.listdir(HERE)):
         if fn.endswith(".npz"):

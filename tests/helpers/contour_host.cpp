@@ -9,6 +9,8 @@
 
 using namespace svb::contour;
 
+static int g_v2_mode = 0;
+
 template <class View>
 static int run(const View &m, int h, int w, double min_area_ratio, double eps_ratio, int32_t *corners, int *n_probe_traces,
                long long *n_probe_steps);
@@ -17,6 +19,9 @@ static int run(const View &m, int h, int w, double min_area_ratio, double eps_ra
 extern "C" __attribute__((visibility("default")))
 int svbh_find_grid_contour(const uint8_t *mask, int h, int w, double min_area_ratio, double eps_ratio,
                            int32_t *corners, int *n_probe_traces, long long *n_probe_steps, int use_bits) {
+    const int v2_mode = use_bits >> 1;  // bit 1 of the flag selects the v2 selection rule
+    use_bits &= 1;
+    g_v2_mode = v2_mode;
     if (use_bits) {
         if (w % 32) return -1;
         const int tx = bit_tiles_x(w), ty = bit_tiles_y(h);
@@ -107,7 +112,7 @@ static int run(const View &m, int h, int w, double min_area_ratio, double eps_ra
     Slice stack[STACK_CAP];
     int st2 = 0;
     int got = select_quad<SerialReduce>(m, raw.data(), (int)raw.size(), list, nested, chain.data(), poly.data(), cap,
-                                        stack, max_steps, eps_ratio, corners, &st2);
+                                        stack, max_steps, eps_ratio, corners, &st2, g_v2_mode);
     status |= st2;
     return got ? 1 : (status ? 2 : 0);
 }

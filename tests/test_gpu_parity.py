@@ -140,6 +140,18 @@ def test_find_grid_contour_synthetic_frames(scanner, oracle):
             assert np.array_equal(c[i], want)
 
 
+def test_v2_contour_method(scanner, golden):
+    """svb_detect_grid_contour_v2 vs the reference's cv/grid_v2.detect_grid_contour (golden)."""
+    v = golden("v2")
+    cases = [(golden(n)["ref_mask"], v[f"{n}_corners"], 0.1) for n in ("frame_a", "frame_b", "frame_c", "photo4_dec8", "frame_none")]
+    cases += [(v[f"shape{k}_mask"], v[f"shape{k}_corners"], 0.05) for k in range(3)]
+    for m, want, ratio in cases:
+        c, f = scanner.detect_grid_contour_v2(_t(m[None]), ratio)
+        assert int(f[0]) == (1 if len(want) else 0)
+        if len(want):
+            assert np.array_equal(c[0].cpu().numpy().astype(np.float32), want)
+
+
 # ---- G3/G4, E1, C1/C2 -----------------------------------------------------------------------------
 def test_warp_extract_cellprep_golden(scanner, golden):
     import torch

@@ -91,3 +91,23 @@ def test_product_contour_core_on_frames(oracle, golden, contour_host):
         assert (f == 1) == (want is not None)
         if want is not None:
             assert np.array_equal(c, want)
+
+
+def test_v2_contour_method_golden(oracle, golden, contour_host):
+    """cv/grid_v2.py:102-128 (detect_grid_contour): oracle_v2 and the product's contour core vs the reference."""
+    from oracle import oracle_v2
+
+    v = golden("v2")
+    cases = [(golden(n)["ref_mask"], v[f"{n}_corners"], 0.1) for n in ("frame_a", "frame_b", "frame_c", "photo4_dec8", "frame_none")]
+    cases += [(v[f"shape{k}_mask"], v[f"shape{k}_corners"], 0.05) for k in range(3)]
+    n_none = 0
+    for m, want, ratio in cases:
+        got = oracle_v2.detect_grid_contour(m, ratio)
+        f, c = contour_host(m, ratio, 0.02, use_bits=(m.shape[1] % 32 == 0), v2=True)
+        if len(want) == 0:
+            n_none += 1
+            assert got is None and f == 0
+        else:
+            assert np.array_equal(got, want)
+            assert f == 1 and np.array_equal(c.astype(np.float32), want)
+    assert n_none >= 2
