@@ -123,6 +123,21 @@ int svb_digitcnn_load(svb_ctx *ctx, const float *conv1_w, const float *conv1_b, 
 int svb_digitcnn_forward(svb_ctx *ctx, const float *x, long long n, float *logits, uint8_t *digits,
                          float *conf, void *stream);
 
+/* ---- M3: ml/model_v3.py ------------------------------------------------------------------------------ */
+/* DigitCNNv3 (ml/model_v3.py:95-184), eval mode.  `folded` is a HOST array of 38 DEVICE pointers to fp32 tensors
+ * with BatchNorm already folded into the preceding convolution (w' = w * gamma / sqrt(var + 1e-5),
+ * b' = beta - mean * gamma / sqrt(var + 1e-5); the Python shim does this from the reference's state_dict):
+ *   0 stem.w (32,1,3,3)  1 stem.b (32)
+ *   per layer L = 1..5 in order: conv1.w, conv1.b, conv2.w, conv2.b (PyTorch OIHW), se.excite.0.weight (c/4,c),
+ *   se.excite.2.weight (c,c/4), and for L = 2, 4 additionally shortcut.w (cout,cin,1,1), shortcut.b
+ *   then fc.weight (10,128), fc.bias (10). */
+int svb_digitcnn_v3_load(svb_ctx *ctx, const float *const *folded, int count, void *stream);
+/* forward(x, return_features) ml/model_v3.py:163-184: x float [n][1][28][28] -> logits float [n][10];
+ * optional digits uint8 [n] / conf float [n] (run_v2.py:166-170 softmax-max / argmax) and features float [n][128]
+ * (the return_features=True branch). */
+int svb_digitcnn_v3_forward(svb_ctx *ctx, const float *x, long long n, float *logits, uint8_t *digits, float *conf,
+                            float *features, void *stream);
+
 /* Classifier implementation used by svb_digitcnn_forward and svb_scan_batch_v1:
  * 0 (default) = tcgen05/TMEM implicit GEMM with fp16 hi/lo split operands (fp32-grade logits),
  * 1 = plain fp32 on the CUDA cores (kept as the on-device cross-check). */

@@ -53,6 +53,9 @@ int launch_cells_from_frames(svb_ctx *, const uint8_t *, int, int, int, const in
 int digitcnn_load(svb_ctx *, const float *const w[8], cudaStream_t);
 int launch_digitcnn(svb_ctx *, const float *, long long, float *, uint8_t *, float *, cudaStream_t);
 void digitcnn_free(svb_ctx *);
+void digitcnn_v3_free(svb_ctx *);
+int digitcnn_v3_load(svb_ctx *, const float *const *, int, cudaStream_t);
+int launch_digitcnn_v3(svb_ctx *, const float *, long long, float *, uint8_t *, float *, float *, cudaStream_t);
 int launch_digitcnn_tc(svb_ctx *, const float *, long long, float *, uint8_t *, float *, cudaStream_t);
 int launch_mask_not_found(svb_ctx *, const uint8_t *, int, uint8_t *, float *, cudaStream_t);
 
@@ -102,7 +105,10 @@ API void svb_destroy(svb_ctx *ctx) {
             wk = nullptr;
         }
     for (int i = 0; i < AR_COUNT; ++i) ctx->arena[i].release();
-    if (!ctx->is_worker) digitcnn_free(ctx);
+    if (!ctx->is_worker) {
+        digitcnn_free(ctx);
+        digitcnn_v3_free(ctx);
+    }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -234,6 +240,19 @@ API int svb_digitcnn_forward(svb_ctx *ctx, const float *x, long long n, float *l
     SVB_REQUIRE(x && logits && n > 0, SVB_ERR_INVALID, "svb_digitcnn_forward: bad arguments");
     if (ctx->classifier_mode == 1) return launch_digitcnn(ctx, x, n, logits, digits, conf, (cudaStream_t)stream);
     return launch_digitcnn_tc(ctx, x, n, logits, digits, conf, (cudaStream_t)stream);
+}
+
+API int svb_digitcnn_v3_load(svb_ctx *ctx, const float *const *folded, int count, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(folded != nullptr, SVB_ERR_INVALID, "svb_digitcnn_v3_load: null tensor table");
+    return digitcnn_v3_load(ctx, folded, count, (cudaStream_t)stream);
+}
+
+API int svb_digitcnn_v3_forward(svb_ctx *ctx, const float *x, long long n, float *logits, uint8_t *digits, float *conf,
+                                float *features, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(x && logits && n > 0, SVB_ERR_INVALID, "svb_digitcnn_v3_forward: bad arguments");
+    return launch_digitcnn_v3(ctx, x, n, logits, digits, conf, features, (cudaStream_t)stream);
 }
 
 API int svb_set_classifier_mode(svb_ctx *ctx, int mode) {

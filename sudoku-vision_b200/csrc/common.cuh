@@ -63,6 +63,7 @@ struct svb_ctx {
     svb::Scratch arena[svb::AR_COUNT];
     svb::DigitCnnWeights cnn;
     void *cnn_tc = nullptr;    // tensor-core operand images (digitcnn_tc.cu)
+    void *cnn_v3 = nullptr;    // folded DigitCNNv3 parameters (digitcnn_v3.cu)
     int classifier_mode = 0;   // 0 = tcgen05 (fp16 hi/lo split), 1 = fp32 CUDA cores
     void *pinned = nullptr;    // host staging for *_host calls
     size_t pinned_bytes = 0;

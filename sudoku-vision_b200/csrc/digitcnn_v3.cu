@@ -1,0 +1,258 @@
+// digitcnn_v3.cu — M3: DigitCNNv3.forward (ml/model_v3.py:163-184, eval mode) on the GPU, fp32.
+//
+// First correct version of the v2 pipeline's classifier: BatchNorm folded into the
+// convolutions at load time (running statistics, eps 1e-5), then per layer
+//   conv3x3_kernel   direct convolution, one CTA per (cell, 16 output channels): the cell's whole input
+//                    (all channels, zero-padded) is staged in shared memory once and reused for 16 x 9 x Cin
+//                    multiply-adds per output pixel; stride 1 or 2; optional ReLU
+//   conv1x1s2_kernel the strided 1x1 projection shortcut of layers 2 and 4
+//   se_kernel        squeeze-excite gate: global average -> fc (c -> c/4) -> ReLU -> fc -> sigmoid
+//   combine_kernel   out = ReLU(conv2_out * gate + shortcut)
+//   head_kernel      global average pool -> fc 128 -> 10 (+ softmax-max / argmax epilogue)
+// Activations live in the context's arena, processed in chunks of cells so the footprint stays bounded.
+// CUDA cores, fp32: parity first (logits within 1e-3 of PyTorch-CPU); the tcgen05 version follows the
+// DigitCNN kernels' pattern (digitcnn_tc.cu) and is the next step for this row.
+#include "common.cuh"
+
+namespace svb {
+namespace k6 {
+
+constexpr int NT = 256;
+constexpr int COG = 16;  // output channels per CTA
+
+template <int STRIDE>
+__global__ void __launch_bounds__(NT)
+conv3x3_kernel(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ bias,
+               float *__restrict__ out, int cin, int cout, int hin, int relu) {
+    extern __shared__ float smem[];
+    const int hp = hin + 2;                       // padded input side
+    const int hout = (hin - 1) / STRIDE + 1;      // padding 1, kernel 3
+    float *s_in = smem;                           // [cin][hp][hp]
+    float *s_w = smem + cin * hp * hp;            // [cin*9][COG]
+    const int cell = blockIdx.x, cg = blockIdx.y, tid = threadIdx.x;
+    const float *src = in + (long long)cell * cin * hin * hin;
+    for (int i = tid; i < cin * hp * hp; i += NT) {
+        const int c = i / (hp * hp), r = (i / hp) % hp, x = i % hp;
+        const bool inside = r >= 1 && r <= hin && x >= 1 && x <= hin;
+        s_in[i] = inside ? src[(c * hin + (r - 1)) * hin + (x - 1)] : 0.f;
+    }
+    for (int i = tid; i < cin * 9 * COG; i += NT) {
+        const int k = i / COG, co = i % COG;  // k = ci*9 + tap
+        s_w[i] = w[((long long)(cg * COG + co) * cin) * 9 + k];
+    }
+    __syncthreads();
+    const int npx = hout * hout;
+    for (int p = tid; p < npx; p += NT) {
+        const int oy = p / hout, ox = p - oy * hout;
+        float acc[COG];
+#pragma unroll
+        for (int c = 0; c < COG; ++c) acc[c] = bias[cg * COG + c];
+        const float *base = s_in + (oy * STRIDE) * hp + ox * STRIDE;
+        for (int ci = 0; ci < cin; ++ci) {
+            const float *pin = base + ci * hp * hp;
+            const float *pw = s_w + ci * 9 * COG;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float v = pin[(t / 3) * hp + (t % 3)];
+                const float4 w0 = *reinterpret_cast<const float4 *>(pw + t * COG);
+                const float4 w1 = *reinterpret_cast<const float4 *>(pw + t * COG + 4);
+                const float4 w2 = *reinterpret_cast<const float4 *>(pw + t * COG + 8);
+                const float4 w3 = *reinterpret_cast<const float4 *>(pw + t * COG + 12);
+                acc[0] = fmaf(w0.x, v, acc[0]); acc[1] = fmaf(w0.y, v, acc[1]); acc[2] = fmaf(w0.z, v, acc[2]); acc[3] = fmaf(w0.w, v, acc[3]);
+                acc[4] = fmaf(w1.x, v, acc[4]); acc[5] = fmaf(w1.y, v, acc[5]); acc[6] = fmaf(w1.z, v, acc[6]); acc[7] = fmaf(w1.w, v, acc[7]);
+                acc[8] = fmaf(w2.x, v, acc[8]); acc[9] = fmaf(w2.y, v, acc[9]); acc[10] = fmaf(w2.z, v, acc[10]); acc[11] = fmaf(w2.w, v, acc[11]);
+                acc[12] = fmaf(w3.x, v, acc[12]); acc[13] = fmaf(w3.y, v, acc[13]); acc[14] = fmaf(w3.z, v, acc[14]); acc[15] = fmaf(w3.w, v, acc[15]);
+            }
+        }
+        float *dst = out + ((long long)cell * cout + cg * COG) * npx + p;
+#pragma unroll
+        for (int c = 0; c < COG; ++c) dst[(long long)c * npx] = relu ? fmaxf(acc[c], 0.f) : acc[c];
+    }
+}
+
+// 1x1 convolution, stride 2, no padding (+ folded BN): out[n][co][y][x] = b[co] + sum_ci w[co][ci] * in[n][ci][2y][2x]
+__global__ void conv1x1s2_kernel(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ bias,
+                                 float *__restrict__ out, int cin, int cout, int hin, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int hout = (hin - 1) / 2 + 1;
+    const int x = (int)(i % hout), y = (int)((i / hout) % hout), co = (int)((i / (hout * hout)) % cout);
+    const long long n = i / ((long long)hout * hout * cout);
+    const float *src = in + (n * cin * hin + 2 * y) * hin + 2 * x;
+    float acc = bias[co];
+    for (int ci = 0; ci < cin; ++ci) acc = fmaf(w[co * cin + ci], src[(long long)ci * hin * hin], acc);
+    out[i] = acc;
+}
+
+// squeeze-excite gate per cell: gate[c] = sigmoid(W2 relu(W1 mean_hw(x)))   (ml/model_v3.py:20-37)
+__global__ void __launch_bounds__(128)
+se_kernel(const float *__restrict__ x, const float *__restrict__ w1, const float *__restrict__ w2, float *__restrict__ gate, int c,
+          int hw) {
+    __shared__ float mean[128], hid[32];
+    const int cell = blockIdx.x, tid = threadIdx.x;
+    const float *src = x + (long long)cell * c * hw;
+    for (int ch = tid; ch < c; ch += 128) {
+        float s = 0.f;
+        for (int i = 0; i < hw; ++i) s += src[(long long)ch * hw + i];
+        mean[ch] = s / (float)hw;
+    }
+    __syncthreads();
+    const int cr = c / 4;
+    if (tid < cr) {
+        float s = 0.f;
+        for (int k = 0; k < c; ++k) s = fmaf(w1[tid * c + k], mean[k], s);
+        hid[tid] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    for (int ch = tid; ch < c; ch += 128) {
+        float s = 0.f;
+        for (int k = 0; k < cr; ++k) s = fmaf(w2[ch * cr + k], hid[k], s);
+        gate[(long long)cell * c + ch] = 1.0f / (1.0f + expf(-s));
+    }
+}
+
+// out = relu(y * gate + shortcut)
+__global__ void combine_kernel(const float *__restrict__ y, const float *__restrict__ gate, const float *__restrict__ shortcut,
+                               float *__restrict__ out, int hw, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    out[i] = fmaxf(fmaf(y[i], gate[i / hw], shortcut[i]), 0.f);
+}
+
+// global average pool (7x7) -> fc -> logits (+ argmax / softmax-max)
+__global__ void __launch_bounds__(128)
+head_kernel(const float *__restrict__ x, const float *__restrict__ fw, const float *__restrict__ fb, float *__restrict__ logits,
+            uint8_t *__restrict__ digits, float *__restrict__ conf, float *__restrict__ features) {
+    __shared__ float feat[128], lg[10];
+    const int cell = blockIdx.x, tid = threadIdx.x;
+    const float *src = x + (long long)cell * 128 * 49;
+    float s = 0.f;
+    for (int i = 0; i < 49; ++i) s += src[tid * 49 + i];
+    feat[tid] = s / 49.0f;
+    if (features) features[(long long)cell * 128 + tid] = feat[tid];
+    __syncthreads();
+    if (tid < 10) {
+        float a = fb[tid];
+        for (int k = 0; k < 128; ++k) a = fmaf(fw[tid * 128 + k], feat[k], a);
+        lg[tid] = a;
+        logits[(long long)cell * 10 + tid] = a;
+    }
+    __syncthreads();
+    if (tid == 0 && (digits || conf)) {
+        float mx = lg[0];
+        int am = 0;
+        for (int c = 1; c < 10; ++c)
+            if (lg[c] > mx) { mx = lg[c]; am = c; }
+        float den = 0.f;
+        for (int c = 0; c < 10; ++c) den += expf(lg[c] - mx);
+        if (digits) digits[cell] = (uint8_t)am;
+        if (conf) conf[cell] = 1.0f / den;
+    }
+}
+
+}  // namespace k6
+
+// Folded parameters, in the order svb_digitcnn_v3_load receives them (element counts):
+//  0 stem.w  1 stem.b | layer1: 2 c1.w 3 c1.b 4 c2.w 5 c2.b 6 se.fc1 7 se.fc2 | layer2: 8..13 same, 14 sc.w 15 sc.b |
+//  layer3: 16..21 | layer4: 22..27, 28 sc.w 29 sc.b | layer5: 30..35 | 36 fc.w 37 fc.b
+constexpr int V3_NT = 38;
+static const int V3_COUNTS[V3_NT] = {
+    32 * 9, 32,
+    32 * 32 * 9, 32, 32 * 32 * 9, 32, 8 * 32, 32 * 8,
+    64 * 32 * 9, 64, 64 * 64 * 9, 64, 16 * 64, 64 * 16, 64 * 32, 64,
+    64 * 64 * 9, 64, 64 * 64 * 9, 64, 16 * 64, 64 * 16,
+    128 * 64 * 9, 128, 128 * 128 * 9, 128, 32 * 128, 128 * 32, 128 * 64, 128,
+    128 * 128 * 9, 128, 128 * 128 * 9, 128, 32 * 128, 128 * 32,
+    10 * 128, 10};
+static int v3_count(int i) { return V3_COUNTS[i]; }
+
+struct V3State {
+    float *blob = nullptr;
+    const float *p[V3_NT] = {};
+};
+
+void digitcnn_v3_free(svb_ctx *ctx) {
+    V3State *s = reinterpret_cast<V3State *>(ctx->cnn_v3);
+    if (!s) return;
+    if (s->blob) cudaFree(s->blob);
+    delete s;
+    ctx->cnn_v3 = nullptr;
+}
+
+int digitcnn_v3_load(svb_ctx *ctx, const float *const *tensors, int count, cudaStream_t st) {
+    SVB_REQUIRE(count == V3_NT, SVB_ERR_INVALID, "svb_digitcnn_v3_load: expected 38 folded tensors");
+    V3State *s = reinterpret_cast<V3State *>(ctx->cnn_v3);
+    size_t total = 0;
+    for (int i = 0; i < V3_NT; ++i) total += ((size_t)v3_count(i) + 3) & ~(size_t)3;
+    if (!s) {
+        s = new V3State();
+        SVB_CUDA_OK(cudaMalloc(&s->blob, total * sizeof(float)));
+        ctx->cnn_v3 = s;
+    }
+    size_t off = 0;
+    for (int i = 0; i < V3_NT; ++i) {
+        SVB_REQUIRE(tensors[i] != nullptr, SVB_ERR_INVALID, "svb_digitcnn_v3_load: null tensor");
+        SVB_CUDA_OK(cudaMemcpyAsync(s->blob + off, tensors[i], sizeof(float) * v3_count(i), cudaMemcpyDeviceToDevice, st));
+        s->p[i] = s->blob + off;
+        off += ((size_t)v3_count(i) + 3) & ~(size_t)3;
+    }
+    return SVB_OK;
+}
+
+int launch_digitcnn_v3(svb_ctx *ctx, const float *x, long long n, float *logits, uint8_t *digits, float *conf,
+                       float *features, cudaStream_t st) {
+    using namespace k6;
+    V3State *s = reinterpret_cast<V3State *>(ctx->cnn_v3);
+    SVB_REQUIRE(s != nullptr, SVB_ERR_NOT_LOADED, "DigitCNNv3 weights not loaded (svb_digitcnn_v3_load)");
+    const long long CHUNK = 2048;  // cells per pass: 3 activation buffers of 32x28x28 floats each
+    const size_t plane = (size_t)32 * 784;
+    const size_t buf = (size_t)CHUNK * plane;
+    if (ctx->arena[AR_CNN].reserve((3 * buf + (size_t)CHUNK * 128) * sizeof(float)) != SVB_OK) return SVB_ERR_CUDA;
+    float *A = (float *)ctx->arena[AR_CNN].ptr, *B = A + buf, *Cb = B + buf, *gate = Cb + buf;
+    SVB_CUDA_OK(cudaFuncSetAttribute(conv3x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    SVB_CUDA_OK(cudaFuncSetAttribute(conv3x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    int rc = SVB_OK;
+    auto conv = [&](const float *in, int wi, float *out, int cin, int cout, int hin, int stride, int relu, int m) {
+        const size_t smem = ((size_t)cin * (hin + 2) * (hin + 2) + (size_t)cin * 9 * COG) * sizeof(float);
+        dim3 grid((unsigned)m, cout / COG);
+        if (stride == 1) conv3x3_kernel<1><<<grid, NT, smem, st>>>(in, s->p[wi], s->p[wi + 1], out, cin, cout, hin, relu);
+        else conv3x3_kernel<2><<<grid, NT, smem, st>>>(in, s->p[wi], s->p[wi + 1], out, cin, cout, hin, relu);
+        if (!rc) rc = check_launch(ctx, "k6::conv3x3_kernel");
+    };
+    // one residual block: X (cin,hin) -> result in X's buffer slot returned via pointer swap
+    auto block = [&](float *&X, float *&T1, float *&T2, int wi, int cin, int cout, int hin, int stride, int sc_wi, int m) {
+        const int hout = (hin - 1) / stride + 1, hw = hout * hout;
+        conv(X, wi, T1, cin, cout, hin, stride, 1, m);           // conv1 + bn1 + relu
+        conv(T1, wi + 2, T2, cout, cout, hout, 1, 0, m);         // conv2 + bn2
+        se_kernel<<<(unsigned)m, 128, 0, st>>>(T2, s->p[wi + 4], s->p[wi + 5], gate, cout, hw);
+        if (!rc) rc = check_launch(ctx, "k6::se_kernel");
+        const float *shortcut = X;
+        if (sc_wi >= 0) {  // projection shortcut into T1 (conv1's output is no longer needed)
+            const long long tot = (long long)m * cout * hw;
+            conv1x1s2_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(X, s->p[sc_wi], s->p[sc_wi + 1], T1, cin, cout, hin, tot);
+            if (!rc) rc = check_launch(ctx, "k6::conv1x1s2_kernel");
+            shortcut = T1;
+        }
+        const long long tot = (long long)m * cout * hw;
+        float *dst = (sc_wi >= 0) ? X : T1;  // never alias an input that is still being read elementwise-shifted
+        combine_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(T2, gate, shortcut, dst, hw, tot);
+        if (!rc) rc = check_launch(ctx, "k6::combine_kernel");
+        if (dst != X) { float *t = X; X = T1; T1 = t; }
+    };
+    for (long long c0 = 0; c0 < n && !rc; c0 += CHUNK) {
+        const int m = (int)((n - c0 < CHUNK) ? n - c0 : CHUNK);
+        float *X = A, *T1 = B, *T2 = Cb;
+        conv(x + c0 * 784, 0, X, 1, 32, 28, 1, 1, m);             // stem
+        block(X, T1, T2, 2, 32, 32, 28, 1, -1, m);                // layer1
+        block(X, T1, T2, 8, 32, 64, 28, 2, 14, m);                // layer2 (+ shortcut 14,15)
+        block(X, T1, T2, 16, 64, 64, 14, 1, -1, m);               // layer3
+        block(X, T1, T2, 22, 64, 128, 14, 2, 28, m);              // layer4 (+ shortcut 28,29)
+        block(X, T1, T2, 30, 128, 128, 7, 1, -1, m);              // layer5
+        head_kernel<<<(unsigned)m, 128, 0, st>>>(X, s->p[36], s->p[37], logits + c0 * 10, digits ? digits + c0 : nullptr,
+                                                conf ? conf + c0 : nullptr, features ? features + c0 * 128 : nullptr);
+        if (!rc) rc = check_launch(ctx, "k6::head_kernel");
+    }
+    return rc;
+}
+
+}  // namespace svb

@@ -122,6 +122,50 @@ class Scanner:
                                                  self._stream()), "svb_digitcnn_forward")
         return (logits, digits, conf) if want_digits else logits
 
+    # -- DigitCNNv3 ------------------------------------------------------------------------------------
+    def load_weights_v3(self, sd: dict):
+        """sd: state_dict of ml/model_v3.DigitCNNv3 (torch tensors or numpy).  Folds BatchNorm (running stats,
+        eps 1e-5) into the convolutions — a one-off load-time step — and hands the 38 folded tensors to the library."""
+        torch = _torch()
+
+        def t(k):
+            v = sd[k]
+            v = v.detach() if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v))
+            return v.to(device=self._dev(), dtype=torch.float32)
+
+        def fold(conv, bn):
+            g = t(bn + ".weight") / torch.sqrt(t(bn + ".running_var") + 1e-5)
+            w = t(conv + ".weight") * g.view(-1, 1, 1, 1)
+            b = t(bn + ".bias") - t(bn + ".running_mean") * g
+            return [w.contiguous(), b.contiguous()]
+
+        ts = fold("stem.0", "stem.1")
+        for L in range(1, 6):
+            p = f"layer{L}"
+            ts += fold(p + ".conv1", p + ".bn1") + fold(p + ".conv2", p + ".bn2")
+            ts += [t(p + ".se.excite.0.weight").contiguous(), t(p + ".se.excite.2.weight").contiguous()]
+            if L in (2, 4):
+                ts += fold(p + ".shortcut.0", p + ".shortcut.1")
+        ts += [t("fc.weight").contiguous(), t("fc.bias").contiguous()]
+        arr = (C.c_void_p * len(ts))(*[x.data_ptr() for x in ts])
+        _lib.check(self.lib.svb_digitcnn_v3_load(self._h, arr, len(ts), self._stream()), "svb_digitcnn_v3_load")
+        self._weights_v3_dev = ts
+        return self
+
+    def digitcnn_v3_forward(self, x, want_digits: bool = False, want_features: bool = False):
+        torch = _torch()
+        x = x.to(device=self._dev(), dtype=torch.float32).contiguous()
+        n = x.shape[0]
+        logits = torch.empty((n, 10), dtype=torch.float32, device=x.device)
+        digits = torch.empty((n,), dtype=torch.uint8, device=x.device) if want_digits else None
+        conf = torch.empty((n,), dtype=torch.float32, device=x.device) if want_digits else None
+        feats = torch.empty((n, 128), dtype=torch.float32, device=x.device) if want_features else None
+        _lib.check(self.lib.svb_digitcnn_v3_forward(self._h, _ptr(x), n, _ptr(logits), _ptr(digits), _ptr(conf), _ptr(feats),
+                                                    self._stream()), "svb_digitcnn_v3_forward")
+        if want_features:
+            return feats
+        return (logits, digits, conf) if want_digits else logits
+
     # -- image stages (batched, device tensors) --------------------------------------------------
     def grayscale(self, bgr):
         self._chk_u8(bgr, 4, "grayscale")

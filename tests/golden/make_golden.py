@@ -124,6 +124,18 @@ def main():
         v2[f"shape{k}_mask"] = m
         v2[f"shape{k}_corners"] = np.zeros((0, 2), np.float32) if c is None else c
     np.savez_compressed(os.path.join(HERE, "v2.npz"), **v2)
+    # DigitCNNv3 (ml/model_v3.py), eval mode, deterministic weights/inputs from tests/helpers/v3_weights.py
+    sys.path.insert(0, os.path.join(ROOT, "tests", "helpers"))
+    from v3_weights import make_v3_inputs, make_v3_state  # noqa: E402
+    from model_v3 import DigitCNNv3  # noqa: E402  (reference, via run.py's sys.path entry for ml/)
+    net = DigitCNNv3()
+    missing = net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in make_v3_state().items()}, strict=True)
+    net.eval()
+    xin = torch.from_numpy(make_v3_inputs())
+    with torch.no_grad():
+        np.savez_compressed(os.path.join(HERE, "v3.npz"), ref_logits=net(xin).numpy(),
+                            ref_features=net(xin, return_features=True).numpy(),
+                            n_state_entries=np.array(len(net.state_dict())))
     np.savez_compressed(os.path.join(HERE, "unit.npz"), **unit)
     for fn in sorted(os.listdir(HERE)):
         if fn.endswith(".npz"):

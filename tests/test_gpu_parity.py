@@ -233,6 +233,41 @@ def test_digitcnn_logits(scanner, oracle, weights, golden, mode):
     scanner.set_classifier_mode("tc")
 
 
+def test_digitcnn_v3_logits(scanner, golden):
+    """svb_digitcnn_v3_forward (BN folded at load) vs the reference DigitCNNv3 (golden) and through the drop-in module."""
+    import os
+    import sys
+
+    import torch
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tests", "helpers"))
+    from v3_weights import make_v3_inputs, make_v3_state
+
+    g = golden("v3")
+    sd = make_v3_state()
+    x = torch.from_numpy(make_v3_inputs()).cuda()
+    scanner.load_weights_v3(sd)
+    logits, digits, conf = scanner.digitcnn_v3_forward(x, want_digits=True)
+    assert np.abs(logits.cpu().numpy() - g["ref_logits"]).max() < LOGIT_TOL
+    assert np.array_equal(digits.cpu().numpy(), g["ref_logits"].argmax(1).astype(np.uint8))
+    feats = scanner.digitcnn_v3_forward(x, want_features=True)
+    assert np.abs(feats.cpu().numpy() - g["ref_features"]).max() < LOGIT_TOL
+    sys.path.insert(0, os.path.join(root, "sudoku-vision_b200", "dropin", "ml"))
+    sys.modules.pop("model_v3", None)
+    import model_v3
+
+    net = model_v3.DigitCNNv3().to("cuda")
+    assert len(net.state_dict()) == 91
+    net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    net.eval()
+    with torch.no_grad():
+        out = net(x)
+        pred, cf = net.get_confidence(x)
+    assert np.abs(out.cpu().numpy() - g["ref_logits"]).max() < LOGIT_TOL
+    assert np.array_equal(pred.cpu().numpy(), g["ref_logits"].argmax(1))
+
+
 # ---- whole path -----------------------------------------------------------------------------------
 def test_scan_batch_vs_oracle(scanner, oracle, weights):
     imgs, digits_gt, _ = _frames(5, 1080, 1920, 8800)

@@ -111,3 +111,21 @@ def test_v2_contour_method_golden(oracle, golden, contour_host):
             assert np.array_equal(got, want)
             assert f == 1 and np.array_equal(c.astype(np.float32), want)
     assert n_none >= 2
+
+
+def test_digitcnn_v3_oracle_golden(golden):
+    """oracle/model_v3_oracle.py (torch functional restatement) vs the reference DigitCNNv3 (golden), 1e-4."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "helpers"))
+    from v3_weights import make_v3_inputs, make_v3_state
+
+    from oracle import model_v3_oracle as M
+
+    g = golden("v3")
+    sd = make_v3_state()
+    assert len(sd) == int(g["n_state_entries"]) == 91
+    x = make_v3_inputs()
+    assert np.abs(M.forward(sd, x) - g["ref_logits"]).max() < 1e-4
+    assert np.abs(M.forward(sd, x, return_features=True) - g["ref_features"]).max() < 1e-4
