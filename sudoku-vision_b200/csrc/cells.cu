@@ -159,6 +159,35 @@ __device__ __forceinline__ uint32_t sample_bgr(const uint8_t *__restrict__ frame
     return out;
 }
 
+// Same result, fewer instructions, for the common case of a footprint fully inside the frame: the two pixels of a
+// footprint row are 6 contiguous bytes, fetched as three aligned words and realigned with funnel shifts; since
+// w = cx*cy*32 with cx in {32-ax, ax}, cy in {32-ay, ay}, (sum w p + 2^14) >> 15 == (S + 512) >> 10 with
+// S = (32-ay)*((32-ax)p00 + ax p01) + ay*((32-ax)p10 + ax p11), and the inner sums are 2-way dot products (dp2a).
+__device__ __forceinline__ uint32_t sample_gray_fast(const uint8_t *__restrict__ frame, int h, int w, int ix, int iy, int ax,
+                                                     int ay) {
+    const long long a = ((long long)iy * w + ix) * 3;
+    const uint32_t cx = (uint32_t)(32 - ax) | ((uint32_t)ax << 16);
+    uint32_t rB[2], rG[2], rR[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(frame + a + (long long)r * w * 3);  // frames need not be 4-B aligned
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(addr & 3) * 8u;
+        const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+        const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);  // B0 G0 R0 B1 | G1 R1 . .
+        const uint32_t bg = __byte_perm(lo, hi, 0x4130);  // B0 B1 G0 G1
+        const uint32_t rr = __byte_perm(lo, hi, 0x0052);  // R0 R1 . .
+        rB[r] = __dp2a_lo(cx, bg, 0u);
+        rG[r] = __dp2a_hi(cx, bg, 0u);
+        rR[r] = __dp2a_lo(cx, rr, 0u);
+    }
+    const uint32_t cy0 = (uint32_t)(32 - ay), cy1 = (uint32_t)ay;
+    const uint32_t b = (cy0 * rB[0] + cy1 * rB[1] + 512u) >> 10;
+    const uint32_t g = (cy0 * rG[0] + cy1 * rG[1] + 512u) >> 10;
+    const uint32_t rd = (cy0 * rR[0] + cy1 * rR[1] + 512u) >> 10;
+    return gray_of(b, g, rd);
+}
+
 __global__ void warp_board_kernel(const uint8_t *__restrict__ bgr, int h, int w, const double *__restrict__ minv,
                                   const uint8_t *__restrict__ found, int out_size, uint8_t *__restrict__ board) {
     const int f = blockIdx.z;
@@ -322,11 +351,42 @@ cells_from_frames_kernel(const uint8_t *__restrict__ bgr, int h, int w, const do
     __shared__ double mi[9];
     if (threadIdx.x < 9) mi[threadIdx.x] = minv[(long long)f * 9 + threadIdx.x];
     __syncthreads();
-    for (int i = threadIdx.x; i < cw * cw; i += blockDim.x) {
-        const int yy = i / cw, xx = i - yy * cw;
-        const Tap t = make_tap(mi, c * cs + margin + xx, r * cs + margin + yy, 64);
-        const uint32_t v = sample_bgr(frame, h, w, t);
-        s.crop[i] = (uint8_t)gray_of(v & 0xff, (v >> 8) & 0xff, (v >> 16) & 0xff);
+    // thread -> one crop column (fixed x: its block/offset terms of the map are hoisted) and every third row
+    if (threadIdx.x < 3 * cw) {
+        const int xx = threadIdx.x % cw, rg = threadIdx.x / cw;
+        const int x = c * cs + margin + xx, bx = (x / 64) * 64;
+        const double bxd = (double)bx, x1d = (double)(x - bx);
+        const double cx0 = dm(mi[0], bxd), cy0 = dm(mi[3], bxd), cw0 = dm(mi[6], bxd);
+        const double mx1 = dm(mi[0], x1d), my1 = dm(mi[3], x1d), mw1 = dm(mi[6], x1d);
+        for (int yy = rg; yy < cw; yy += 3) {
+            const double yd = (double)(r * cs + margin + yy);
+            const double X0 = da(da(cx0, dm(mi[1], yd)), mi[2]);
+            const double Y0 = da(da(cy0, dm(mi[4], yd)), mi[5]);
+            const double W0 = da(da(cw0, dm(mi[7], yd)), mi[8]);
+            double Wd = da(W0, mw1);
+            Wd = (Wd != 0.0) ? 32.0 / Wd : 0.0;
+            double fx = dm(da(X0, mx1), Wd), fy = dm(da(Y0, my1), Wd);
+            fx = fmin(fmax(fx, -2147483648.0), 2147483647.0);
+            fy = fmin(fmax(fy, -2147483648.0), 2147483647.0);
+            const int X = __double2int_rn(fx), Y = __double2int_rn(fy);
+            const int ix = X >> 5, iy = Y >> 5, ax = X & 31, ay = Y & 31;
+            uint32_t gv;
+            // footprint inside the frame, and the 12-byte window of its second row inside the buffer
+            if (ix >= 0 && iy >= 0 && ix + 1 < w && iy + 1 < h && (iy + 2 < h || ix + 4 < w)) {
+                gv = sample_gray_fast(frame, h, w, ix, iy, ax, ay);
+            } else {
+                Tap t;
+                t.ix = ix;
+                t.iy = iy;
+                t.w00 = (32 - ax) * (32 - ay) * 32;
+                t.w01 = ax * (32 - ay) * 32;
+                t.w10 = (32 - ax) * ay * 32;
+                t.w11 = ax * ay * 32;
+                const uint32_t v = sample_bgr(frame, h, w, t);
+                gv = gray_of(v & 0xff, (v >> 8) & 0xff, (v >> 16) & 0xff);
+            }
+            s.crop[yy * cw + xx] = (uint8_t)gv;
+        }
     }
     __syncthreads();
     resize_phase(s, rt);
