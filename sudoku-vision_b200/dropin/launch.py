@@ -59,12 +59,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", required=True, help="writable staged copy of the reference tree")
     ap.add_argument("--stage", default=None, help="copy this reference checkout to --ref first")
-    ap.add_argument("script", help="reference script relative to --ref, e.g. pipeline/run.py")
+    ap.add_argument("--stage-only", action="store_true", help="stop after staging (works without a GPU)")
+    ap.add_argument("script", nargs="?", default=None, help="reference script relative to --ref, e.g. pipeline/run.py")
     ap.add_argument("args", nargs=argparse.REMAINDER)
     a = ap.parse_args()
     ref = os.path.abspath(a.ref)
     if a.stage:
         stage(a.stage, ref)
+    if a.stage_only or not a.script:
+        return
     seed_modules()
     script = os.path.join(ref, a.script)
     sys.argv = [script] + a.args
