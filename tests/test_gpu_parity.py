@@ -367,3 +367,84 @@ def test_dropin_modules_match_golden(golden, weights):
     assert np.abs(outs.cpu().numpy() - g["ref_logits"][::9]).max() < LOGIT_TOL
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 1, 28, 28))
+
+
+# ---- edge cases --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hw", [(3, 3), (5, 9), (8, 64), (9, 80), (63, 64), (64, 1024), (17, 2000), (130, 4000)])
+def test_preprocess_edge_sizes(scanner, oracle, hw):
+    """Smallest legal images, heights below one fused segment, widths that force partial strips / the stage path."""
+    rng = np.random.default_rng(hw[0] * 31 + hw[1])
+    img = rng.integers(0, 256, (2,) + hw + (3,)).astype(np.uint8)
+    m = scanner.preprocess(_t(img)).cpu().numpy()
+    for i in range(2):
+        assert np.array_equal(m[i], oracle.preprocess(img[i])), hw
+
+
+def test_contour_degenerate_masks(scanner, oracle):
+    H, W = 96, 128
+    masks = np.zeros((6, H, W), np.uint8)
+    masks[1] = 255                                   # everything foreground: one component touching all borders
+    masks[2, 40, 60] = 255                           # a single pixel
+    masks[3, 0, :] = 255                             # a line on the top border
+    masks[4, 10:80, 10:110] = 255                    # a filled rectangle (a valid quadrilateral)
+    masks[5, 10:80, 10:110] = 255
+    masks[5, 20:70, 20:100] = 0                      # a ring with a nested filled box inside its hole
+    masks[5, 30:60, 30:90] = 255
+    c, f = scanner.find_grid_contour(_t(masks))
+    c, f = c.cpu().numpy(), f.cpu().numpy()
+    for i in range(len(masks)):
+        want = oracle.find_grid_contour(masks[i])
+        assert (want is not None) == (f[i] == 1), i
+        if want is not None:
+            assert np.array_equal(c[i], want), i
+    assert f[0] == 0 and f[2] == 0 and f[4] == 1
+
+
+def test_cells_with_corners_outside_the_frame(scanner, oracle):
+    """Corners beyond the image: taps outside contribute 0 (BORDER_CONSTANT) — exercises the bounds-checked sampler."""
+    import torch
+
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (2, 300, 400, 3)).astype(np.uint8)
+    corners = np.array([[[-20, 30], [40, 340], [430, 250], [300, -15]], [[5, 5], [395, 2], [398, 297], [2, 295]]], np.int32)
+    u8, pm1 = scanner.cells_from_frames(_t(img), torch.from_numpy(corners).cuda())
+    board = scanner.warp_perspective(_t(img), torch.from_numpy(corners).cuda())
+    for i in range(2):
+        want_board = oracle.warp_perspective(img[i], corners[i])
+        assert np.array_equal(board[i].cpu().numpy(), want_board)
+        want_cells = oracle.extract_cells(want_board)
+        assert np.array_equal(u8[i].cpu().numpy(), want_cells)
+        want_in = (oracle.cell_prep(want_cells).astype(np.float32) / 255.0 - 0.5) / 0.5
+        assert np.array_equal(pm1[i].cpu().numpy(), want_in)
+
+
+@pytest.mark.parametrize("n", [1, 2, 127, 129])
+def test_digitcnn_batch_sizes(scanner, oracle, weights, n):
+    import torch
+
+    rng = np.random.default_rng(n)
+    x = np.where(rng.random((n, 1, 28, 28)) < 0.3, 1.0, -1.0).astype(np.float32)
+    got = scanner.digitcnn_forward(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert np.abs(got - oracle.digitcnn_forward(weights, x)).max() < LOGIT_TOL
+
+
+def test_classifier_only_many_cells(scanner, oracle, weights):
+    """BASELINE config 3 in miniature: a large cell batch through the tcgen05 classifier vs its own fp32 CUDA-core
+    twin on all cells (argmax must agree everywhere) and vs the oracle on a subsample."""
+    import torch
+
+    rng = np.random.default_rng(11)
+    n = 50_000
+    x = torch.from_numpy(np.where(rng.random((n, 1, 28, 28)) < 0.22, 1.0, -1.0).astype(np.float32)).cuda()
+    scanner.set_classifier_mode("tc")
+    lt, dt, _ = scanner.digitcnn_forward(x, want_digits=True)
+    scanner.set_classifier_mode("fp32")
+    lf, df, _ = scanner.digitcnn_forward(x, want_digits=True)
+    scanner.set_classifier_mode("tc")
+    assert float((lt - lf).abs().max()) < LOGIT_TOL
+    top2 = lf.topk(2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 2 * LOGIT_TOL  # argmax is only defined up to the tolerance
+    assert torch.equal(dt[decided], df[decided])
+    idx = rng.choice(n, 64, replace=False)
+    want = oracle.digitcnn_forward(weights, x[idx].cpu().numpy())
+    assert np.abs(lt[idx].cpu().numpy() - want).max() < LOGIT_TOL
