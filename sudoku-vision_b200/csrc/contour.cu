@@ -37,7 +37,7 @@ struct FrameScratch {
     uint32_t *poly;    // [n][cap]
     int cap;
     int *gcount;       // [1] number of crossings found in the whole batch
-    int2 *glist;       // [gcap] (frame, probe id) of every crossing, densely packed across frames
+    GEntry *glist;     // [gcap] (frame, probe id) of every crossing, densely packed across frames
     int *map;          // [n][nprobe] probe id -> index into glist/segs (valid only at crossings)
     Seg *segs;         // [gcap]
     int gcap, nprobe;
@@ -115,7 +115,7 @@ find_crossings_kernel(const void *__restrict__ mask, int h, int w, int wp, int p
         atomicOr(&fs.status[frame], 1);
         return;
     }
-    fs.glist[g] = make_int2(frame, id);
+    fs.glist[g] = GEntry{frame, id};
     fs.map[(long long)frame * fs.nprobe + id] = g;
 }
 
@@ -125,20 +125,11 @@ __global__ void __launch_bounds__(128)
 trace_segments_kernel(const void *__restrict__ mask, int h, int w, int wp, int pitch, int nv, int max_steps, FrameScratch fs) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= min(*fs.gcount, fs.gcap)) return;
-    const int2 e = fs.glist[g];
-    const int frame = e.x, id = e.y;
+    const GEntry e = fs.glist[g];
+    const int frame = e.frame, id = e.id;
     const View m = make_view<View>(mask, frame, h, w, wp);
     int x, y, dv;
-    if (id < nv * h) {
-        x = (id / h) * pitch;
-        y = id % h;
-        dv = DIR_N;
-    } else {
-        const int j = id - nv * h;
-        y = (j / w) * pitch;
-        x = j % w;
-        dv = DIR_W;
-    }
+    crossing_xy(id, h, w, pitch, nv, x, y, dv);
     Seg sg = trace_segment(m, x, y, dv, pitch, nv, max_steps);
     if (sg.next_id < 0) atomicOr(&fs.status[frame], 4);
     else sg.next_id = fs.map[(long long)frame * fs.nprobe + sg.next_id];  // probe id -> list index
@@ -153,7 +144,7 @@ link_loops_kernel(double min_area, FrameScratch fs) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int total = min(*fs.gcount, fs.gcap);
     if (g >= total) return;
-    const int frame = fs.glist[g].x;
+    const int frame = fs.glist[g].frame;
     long long area2 = 0;
     int min_idx = 0x7fffffff, cur = g;
     for (int it = 0; it <= total; ++it) {
@@ -177,7 +168,7 @@ link_loops_kernel(double min_area, FrameScratch fs) {
             Cand c;
             c.area2 = -area2;
             c.min_idx = min_idx;
-            c.pad = 0;
+            c.lead = g;
             fs.cands[(long long)frame * MAXC + slot] = c;
             return;
         }
@@ -204,14 +195,20 @@ struct WarpReduce {
     }
     static __device__ __forceinline__ int bcast(int v) { return __shfl_sync(0xffffffffu, v, 0); }
     static __device__ __forceinline__ double bcast(double v) { return __shfl_sync(0xffffffffu, v, 0); }
+    static __device__ __forceinline__ int sum(int v) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        return v;
+    }
     static __device__ __forceinline__ void sync() { __syncwarp(); }
 };
 
 template <class View>
 __global__ void __launch_bounds__(128)
-select_quad_kernel(const void *__restrict__ mask, int n, int h, int w, int wp, double eps_ratio, int max_steps,
-                   FrameScratch fs, int32_t *__restrict__ corners, uint8_t *__restrict__ found, int v2_mode) {
+select_quad_kernel(const void *__restrict__ mask, int n, int h, int w, int wp, int pitch, int nv, double eps_ratio,
+                   int max_steps, FrameScratch fs, int32_t *__restrict__ corners, uint8_t *__restrict__ found, int v2_mode) {
     __shared__ Slice stacks[4][STACK_CAP];
+    __shared__ int segl[4][SEGCAP], segoff[4][SEGCAP];
     __shared__ Cand lists[4][MAXC];
     __shared__ Cand raws[4][MAXC];
     __shared__ int nested[4][MAXC];
@@ -234,7 +231,8 @@ select_quad_kernel(const void *__restrict__ mask, int n, int h, int w, int wp, d
     const int got = select_quad<WarpReduce>(m, raws[warp], nraw, lists[warp],
                                             nested[warp], fs.chain + (long long)frame * fs.cap,
                                             fs.poly + (long long)frame * fs.cap, fs.cap, stacks[warp], max_steps,
-                                            eps_ratio, out, &status, v2_mode);
+                                            eps_ratio, out, &status, v2_mode,
+                                            SegTables{fs.segs, fs.glist, pitch, nv, segl[warp], segoff[warp]});
     if (lane == 0) {
         status |= fs.status[frame];
         // status != 0: a scratch capacity was hit -> report 2 so that the caller fails loudly
@@ -275,7 +273,7 @@ int launch_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, in
     const size_t o_bits = use_bits ? take(sizeof(uint32_t) * (size_t)n * wp * 32) : 0;
     const long long gcap_ll = std::min<long long>(std::max<long long>((long long)n * 512, 16384), (long long)n * (total / 2 + 1));
     const int gcap = (int)std::min<long long>(gcap_ll, 1ll << 26);
-    const size_t o_gc = take(sizeof(int)), o_gl = take(sizeof(int2) * (size_t)gcap), o_sg = take(sizeof(Seg) * (size_t)gcap);
+    const size_t o_gc = take(sizeof(int)), o_gl = take(sizeof(GEntry) * (size_t)gcap), o_sg = take(sizeof(Seg) * (size_t)gcap);
     const size_t o_map = take(sizeof(int) * (size_t)n * total);
     if (ctx->arena[AR_CONTOUR].reserve(off) != SVB_OK) return SVB_ERR_CUDA;
     char *base = (char *)ctx->arena[AR_CONTOUR].ptr;
@@ -287,7 +285,7 @@ int launch_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, in
     fs.poly = (uint32_t *)(base + o_po);
     fs.cap = cap;
     fs.gcount = (int *)(base + o_gc);
-    fs.glist = (int2 *)(base + o_gl);
+    fs.glist = (GEntry *)(base + o_gl);
     fs.segs = (Seg *)(base + o_sg);
     fs.map = (int *)(base + o_map);
     fs.gcap = gcap;
@@ -325,9 +323,9 @@ int launch_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, in
     rc = check_launch(ctx, "k2::link_loops_kernel");
     if (rc) return rc;
     if (use_bits)
-        select_quad_kernel<BitMaskView><<<(n + 3) / 4, 128, 0, st>>>(view_ptr, n, h, w, wp, eps_ratio, max_steps, fs, corners, found, v2_mode);
+        select_quad_kernel<BitMaskView><<<(n + 3) / 4, 128, 0, st>>>(view_ptr, n, h, w, wp, pitch, nv, eps_ratio, max_steps, fs, corners, found, v2_mode);
     else
-        select_quad_kernel<MaskView><<<(n + 3) / 4, 128, 0, st>>>(view_ptr, n, h, w, 0, eps_ratio, max_steps, fs, corners, found, v2_mode);
+        select_quad_kernel<MaskView><<<(n + 3) / 4, 128, 0, st>>>(view_ptr, n, h, w, 0, pitch, nv, eps_ratio, max_steps, fs, corners, found, v2_mode);
     return check_launch(ctx, "k2::select_quad_kernel");
 }
 

@@ -226,58 +226,97 @@ struct Seg {
     int next_id;      // probe id of the crossing that ends the segment (-1: step limit hit)
     int min_idx;      // raster-min pixel of the segment
     int steps;
+    int kept;         // pixels of the segment that CHAIN_APPROX_SIMPLE keeps (step direction changes there)
+    int min_pos;      // index, among the kept pixels, of the raster-min pixel (-1 if SIMPLE drops it)
     int pad;
 };
+struct GEntry {       // one recorded crossing
+    int frame, id;
+};
+SVB_HD void crossing_xy(int id, int h, int w, int pitch, int nv, int &x, int &y, int &dv) {
+    if (id < nv * h) {
+        x = (id / h) * pitch;
+        y = id % h;
+        dv = DIR_N;
+    } else {
+        const int j = id - nv * h;
+        y = (j / w) * pitch;
+        x = j % w;
+        dv = DIR_W;
+    }
+}
 
-template <class View>
-SVB_HD Seg trace_segment(const View &m, int qx, int qy, int dv, int pitch, int nv, int max_steps) {
-    Seg sg;
-    sg.area2 = 0;
-    sg.min_idx = qy * m.w + qx;
-    sg.steps = 0;
-    sg.pad = 0;
+// Walk from the crossing (qx,qy,dv) to the next crossing.  vis.point(x, y, din, dout) is called for every pixel of
+// the segment (start included, terminating crossing excluded).  Returns the probe id of the terminating crossing,
+// or -1 if max_steps was exceeded.
+template <class View, class Vis>
+SVB_HD int walk_segment(const View &m, int qx, int qy, int dv, int pitch, int nv, int max_steps, Vis &vis) {
     const int self = (dv == DIR_N) ? (qx / pitch) * m.h + qy : nv * m.h + (qy / pitch) * m.w + qx;
     typename CursorOf<View>::type cur;
     cur.init(m, qx, qy);
     unsigned nb = cur.nbits(qx, qy);
     if (nb == 0) {  // isolated pixel: a loop of one point
-        sg.next_id = self;
-        sg.steps = 1;
-        return sg;
+        vis.point(qx, qy, -1, -1);
+        return self;
     }
     int x = qx, y = qy, xr = qx % pitch, yr = qy % pitch, xl = qx / pitch, yl = qy / pitch;
+    int din = (first_cw(nb, dv) + 4) & 7;  // step direction from the cyclic predecessor into the start pixel
     int dout = next_ccw(nb, dv);
-    for (;;) {
+    for (int n = 0;;) {
+        vis.point(x, y, din, dout);
+        if (++n > max_steps) return -1;
         const int dx = dir_dx(dout), dy = dir_dy(dout);
-        const int nx = x + dx, ny = y + dy;
-        sg.area2 += (long long)x * ny - (long long)nx * y;
-        if (++sg.steps > max_steps) {
-            sg.next_id = -1;
-            return sg;
-        }
-        x = nx;
-        y = ny;
+        x += dx;
+        y += dy;
         xr += dx;  // x % pitch and x / pitch, maintained incrementally
         if (xr == pitch) { xr = 0; ++xl; } else if (xr < 0) { xr = pitch - 1; --xl; }
         yr += dy;
         if (yr == pitch) { yr = 0; ++yl; } else if (yr < 0) { yr = pitch - 1; --yl; }
+        din = dout;
         const int pd = (dout + 4) & 7;  // direction back to the pixel we came from
         cur.moved(x, y, dy);
         nb = cur.nbits(x, y);
         dout = next_ccw(nb, pd);
         // is this visit a crossing state?  its background arc is the directions strictly between pd and dout (CCW)
         const int span = (dout - pd - 1) & 7;
-        if (xr == 0 && ((DIR_N - pd - 1) & 7) < span) {
-            sg.next_id = xl * m.h + y;
-            return sg;
-        }
-        if (yr == 0 && ((DIR_W - pd - 1) & 7) < span) {
-            sg.next_id = nv * m.h + yl * m.w + x;
-            return sg;
-        }
-        const int idx = y * m.w + x;
-        if (idx < sg.min_idx) sg.min_idx = idx;
+        if (xr == 0 && ((DIR_N - pd - 1) & 7) < span) return xl * m.h + y;
+        if (yr == 0 && ((DIR_W - pd - 1) & 7) < span) return nv * m.h + yl * m.w + x;
     }
+}
+
+struct SegStats {
+    Seg sg;
+    int w;
+    SVB_HD explicit SegStats(int w_) : w(w_) {
+        sg.area2 = 0;
+        sg.next_id = -1;
+        sg.min_idx = 0x7fffffff;
+        sg.steps = 0;
+        sg.kept = 0;
+        sg.min_pos = -1;
+        sg.pad = 0;
+    }
+    SVB_HD void point(int x, int y, int din, int dout) {
+        const int idx = y * w + x;
+        const bool keep = (din != dout) || din < 0;
+        if (idx < sg.min_idx) {
+            sg.min_idx = idx;
+            sg.min_pos = keep ? sg.kept : -1;
+        }
+        if (keep) ++sg.kept;
+        ++sg.steps;
+        if (dout >= 0) {
+            const int nx = x + dir_dx(dout), ny = y + dir_dy(dout);
+            sg.area2 += (long long)x * ny - (long long)nx * y;
+        }
+    }
+};
+
+template <class View>
+SVB_HD Seg trace_segment(const View &m, int qx, int qy, int dv, int pitch, int nv, int max_steps) {
+    SegStats st(m.w);
+    st.sg.next_id = walk_segment(m, qx, qy, dv, pitch, nv, max_steps, st);
+    return st.sg;
 }
 
 // ---- visitors ---------------------------------------------------------------------------------
@@ -331,6 +370,37 @@ struct ChainWriter {
     }
 };
 
+// Segment-parallel variant: this walker's kept pixels go to chain[(base + j) % n], so that segments written by
+// different lanes land in loop order, rotated to start at the component's raster-first pixel.
+template <int NT>
+struct RotWriter {
+    uint32_t *pts;
+    int n, pos;  // pos = destination of the next kept point, always in [0, n)
+    int ntargets = 0;
+    int tx[NT], ty[NT], wn[NT];
+    SVB_HD RotWriter(uint32_t *p, int n_, int base) : pts(p), n(n_), pos(base) {
+        for (int i = 0; i < NT; ++i) tx[i] = ty[i] = wn[i] = 0;
+    }
+    SVB_HD void point(int x, int y, int din, int dout) {
+        if (din != dout || din < 0) {
+            pts[pos] = (uint32_t)x | ((uint32_t)y << 16);
+            if (++pos == n) pos = 0;
+        }
+        if (dout >= 0) {
+            const int nx = x + dir_dx(dout), ny = y + dir_dy(dout);
+            for (int i = 0; i < NT; ++i) {
+                if (i >= ntargets) break;
+                const long long is_left = (long long)(nx - x) * (ty[i] - y) - (long long)(tx[i] - x) * (ny - y);
+                if (y <= ty[i]) {
+                    if (ny > ty[i] && is_left > 0) ++wn[i];
+                } else {
+                    if (ny <= ty[i] && is_left < 0) --wn[i];
+                }
+            }
+        }
+    }
+};
+
 SVB_HD int pt_x(uint32_t p) { return (int)(p & 0xffffu); }
 SVB_HD int pt_y(uint32_t p) { return (int)(p >> 16); }
 
@@ -364,6 +434,7 @@ struct SerialReduce {
     static SVB_HD void argmax_first(double &, int &, int &) {}
     static SVB_HD int bcast(int v) { return v; }
     static SVB_HD double bcast(double v) { return v; }
+    static SVB_HD int sum(int v) { return v; }
     static SVB_HD void sync() {}
 };
 
@@ -564,11 +635,18 @@ SVB_HD bool quad_is_valid_v2(const int32_t *c) {
 struct Cand {
     long long area2;  // |signed shoelace| x 2 of an outer border
     int min_idx;      // raster index of the component's first pixel (canonical trace start)
-    int pad;
+    int lead;         // list index of the loop's leading segment (smallest index on the loop)
 };
 constexpr int MAXC = 64;       // candidate slots per frame (power of two)
 constexpr int MAXT = 8;        // winding-number targets tracked per trace
 constexpr int STACK_CAP = 96;  // DP slice stack
+constexpr int SEGCAP = 96;     // segments of one loop handled by the parallel re-trace (more -> serial re-trace)
+struct SegTables {             // what K2a left behind (contour.cu) / the host harness builds
+    const Seg *segs;
+    const GEntry *glist;
+    int pitch, nv;
+    int *segl, *segoff;        // SEGCAP scratch ints each, shared by the cooperating lanes
+};
 // status bits: 1 candidate-list overflow, 2 chain overflow, 4 trace step overflow, 8 DP stack overflow
 
 // raw[0..raw_count): candidates as found by the probe pass (duplicates allowed).  list/nested: MAXC
@@ -576,7 +654,7 @@ constexpr int STACK_CAP = 96;  // DP slice stack
 template <class Red, class View>
 SVB_HD int select_quad(const View &m, const Cand *raw, int raw_count, Cand *list, int *nested, uint32_t *chain,
                        uint32_t *poly, int cap, Slice *stack, int max_steps, double eps_ratio, int32_t *corners,
-                       int *status_out, int v2_mode = 0) {
+                       int *status_out, int v2_mode, const SegTables &tb) {
     const int lane = Red::lane();
     const int w = m.w;
     int nc = 0;
@@ -606,22 +684,77 @@ SVB_HD int select_quad(const View &m, const Cand *raw, int raw_count, Cand *list
     int status = 0, got = 0;
     for (int ci = 0; ci < nc && !got; ++ci) {
         int npts = 0;
+        // ---- re-trace with CHAIN_APPROX_SIMPLE into `chain`, starting at the raster-first pixel ----------------------
+        // The loop's segments (crossing to crossing) are independent walks: the lanes take one each and write their
+        // kept pixels straight to their final, rotated position.  Lane 0 first lists the segments of the loop.
+        int nseg = 0, rot = 0, ntg = nc - ci - 1 < MAXT ? nc - ci - 1 : MAXT;
         if (lane == 0) {
-            ChainWriter<MAXT> cw(chain, cap);
-            cw.ntargets = nc - ci - 1 < MAXT ? nc - ci - 1 : MAXT;
             if (nc - ci - 1 > MAXT) status |= 1;
-            for (int k = 0; k < cw.ntargets; ++k) {
-                cw.tx[k] = list[ci + 1 + k].min_idx % w;
-                cw.ty[k] = list[ci + 1 + k].min_idx / w;
+            int cur = list[ci].lead, total = 0;
+            bool ok = true;
+            for (;;) {
+                if (nseg >= SEGCAP) { ok = false; break; }
+                const Seg sg = tb.segs[cur];
+                tb.segl[nseg] = cur;
+                tb.segoff[nseg] = total;
+                if (sg.min_idx == list[ci].min_idx) {
+                    if (sg.min_pos < 0) ok = false;  // cannot happen: the raster-first pixel is a convex corner
+                    rot = total + sg.min_pos;
+                }
+                total += sg.kept;
+                ++nseg;
+                cur = sg.next_id;
+                if (cur == list[ci].lead) break;
             }
-            const int r = trace_loop(m, list[ci].min_idx % w, list[ci].min_idx / w, DIR_W, max_steps, cw);
-            if (r < 0) status |= 4;
-            if (cw.overflow) status |= 2;
-            npts = (r < 0 || cw.overflow) ? -1 : cw.n;
-            for (int k = 0; k < cw.ntargets; ++k)
-                if (cw.wn[k] != 0) nested[ci + 1 + k] = 1;  // start pixel lies inside this border
+            npts = ok ? total : -2;
+            if (ok && total > cap) {
+                status |= 2;
+                npts = -1;
+            }
         }
         npts = Red::bcast(npts);
+        nseg = Red::bcast(nseg);
+        rot = Red::bcast(rot);
+        Red::sync();
+        int wn_sum[MAXT];
+        for (int k = 0; k < MAXT; ++k) wn_sum[k] = 0;
+        if (npts >= 0) {
+            for (int k = lane; k < nseg; k += Red::lanes()) {
+                const GEntry e = tb.glist[tb.segl[k]];
+                int x, y, dv;
+                crossing_xy(e.id, m.h, m.w, tb.pitch, tb.nv, x, y, dv);
+                int base = tb.segoff[k] - rot;
+                if (base < 0) base += npts;
+                RotWriter<MAXT> rw(chain, npts, base);
+                rw.ntargets = ntg;
+                for (int q = 0; q < ntg; ++q) {
+                    rw.tx[q] = list[ci + 1 + q].min_idx % w;
+                    rw.ty[q] = list[ci + 1 + q].min_idx / w;
+                }
+                walk_segment(m, x, y, dv, tb.pitch, tb.nv, max_steps, rw);
+                for (int q = 0; q < ntg; ++q) wn_sum[q] += rw.wn[q];
+            }
+        } else if (npts == -2) {
+            // loop with too many segments: serial re-trace from the canonical start (lane 0)
+            if (lane == 0) {
+                ChainWriter<MAXT> cw(chain, cap);
+                cw.ntargets = ntg;
+                for (int q = 0; q < ntg; ++q) {
+                    cw.tx[q] = list[ci + 1 + q].min_idx % w;
+                    cw.ty[q] = list[ci + 1 + q].min_idx / w;
+                }
+                const int r = trace_loop(m, list[ci].min_idx % w, list[ci].min_idx / w, DIR_W, max_steps, cw);
+                if (r < 0) status |= 4;
+                if (cw.overflow) status |= 2;
+                npts = (r < 0 || cw.overflow) ? -1 : cw.n;
+                for (int q = 0; q < ntg; ++q) wn_sum[q] = cw.wn[q];
+            }
+            npts = Red::bcast(npts);
+        }
+        for (int q = 0; q < ntg; ++q) {
+            const int t = Red::sum(wn_sum[q]);
+            if (lane == 0 && t != 0) nested[ci + 1 + q] = 1;  // that start pixel lies inside this border
+        }
         Red::sync();
         if (npts < 0) break;        // scratch capacity hit: give up on this frame, status says why
         if (nested[ci]) continue;   // inside another component's hole: RETR_EXTERNAL never returns it

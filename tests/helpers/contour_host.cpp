@@ -48,6 +48,7 @@ static int run(const View &m, int h, int w, double min_area_ratio, double eps_ra
     int status = 0;
     // K2a.1: crossings (the device packs them with one atomicAdd per crossing)
     std::vector<int> ids, map(nprobe, -1);
+    std::vector<GEntry> glist;
     for (int id = 0; id < nprobe; ++id) {
         int x, y;
         if (id < nv * h) {
@@ -61,14 +62,14 @@ static int run(const View &m, int h, int w, double min_area_ratio, double eps_ra
         }
         map[id] = (int)ids.size();
         ids.push_back(id);
+        glist.push_back(GEntry{0, id});
     }
     // K2a.2: one segment per crossing
     std::vector<Seg> segs(ids.size());
     for (size_t g = 0; g < ids.size(); ++g) {
         const int id = ids[g];
         int x, y, dv;
-        if (id < nv * h) { x = (id / h) * pitch; y = id % h; dv = DIR_N; }
-        else { int j = id - nv * h; y = (j / w) * pitch; x = j % w; dv = DIR_W; }
+        crossing_xy(id, h, w, pitch, nv, x, y, dv);
         Seg sg = trace_segment(m, x, y, dv, pitch, nv, max_steps);
         ++traces; steps += sg.steps;
         if (sg.next_id < 0) status |= 4;
@@ -100,7 +101,7 @@ static int run(const View &m, int h, int w, double min_area_ratio, double eps_ra
         for (auto &c : raw) dup |= (c.min_idx == min_idx);  // the device uses an atomicCAS set for this
         if (dup) continue;
         if ((int)raw.size() >= MAXC) { status |= 1; continue; }
-        raw.push_back(Cand{-area2, min_idx, 0});
+        raw.push_back(Cand{-area2, min_idx, g});
     }
     if (n_probe_traces) *n_probe_traces = traces;
     if (n_probe_steps) *n_probe_steps = steps;
@@ -110,9 +111,11 @@ static int run(const View &m, int h, int w, double min_area_ratio, double eps_ra
     Cand list[MAXC];
     int nested[MAXC];
     Slice stack[STACK_CAP];
+    int segl[SEGCAP], segoff[SEGCAP];
     int st2 = 0;
     int got = select_quad<SerialReduce>(m, raw.data(), (int)raw.size(), list, nested, chain.data(), poly.data(), cap,
-                                        stack, max_steps, eps_ratio, corners, &st2, g_v2_mode);
+                                        stack, max_steps, eps_ratio, corners, &st2, g_v2_mode,
+                                        SegTables{segs.data(), glist.data(), pitch, nv, segl, segoff});
     status |= st2;
     return got ? 1 : (status ? 2 : 0);
 }
