@@ -35,6 +35,9 @@ for p in (ROOT, PKG):
 H, W = 1080, 1920
 METRIC = "frames/sec end-to-end (preprocess->warp->81-cell CNN) at 1080p"
 K1_BYTES_PER_FRAME = 3 * H * W + H * W  # 6,220,800 read + 2,073,600 written
+# dram__bytes_read.sum + dram__bytes_write.sum of k1::fused_preprocess_kernel per 1080p frame, from the ncu --set full
+# capture profiles/r1_prof_k1c_raw.csv (256 frames: 1.6597 GB read + 0.5116 GB written)
+K1_TRAFFIC_PER_FRAME = int((1.659665e9 + 0.511562e9) / 256)
 
 
 def measured_peaks():
@@ -259,7 +262,7 @@ def main():
             "vs_baseline": None, "dtype": "u8+f32", "data": "synthetic",
             "config": {"workload": f"batch of {Fn} synthetic 1080p sudoku frames per GPU (BASELINE configs[1]), "
                                    f"device-resident, whole path K1..K5 per step",
-                       "frame": [H, W, 3], "frames_per_gpu": Fn, "classifier": "DigitCNN (ml/model.py), fp32",
+                       "frame": [H, W, 3], "frames_per_gpu": Fn, "classifier": "DigitCNN (ml/model.py) on tcgen05: fp16 hi+lo split operands, fp32 TMEM accumulators (logits within 1e-3 of fp32)",
                        "l2": f"inputs {Fn * H * W * 3 / 1e9:.1f} GB per step >> 126 MB L2 (no flush needed)",
                        "sharding": f"image-sharded x{world}, no data-path collective", "grids_found": f"{found}/{Fn}"},
             "e2e": {"value": En * world * args.steps / e2e_s, "unit": "frames/s",
@@ -269,7 +272,9 @@ def main():
             "stage_ms_per_step": {k: round(v, 4) for k, v in stage_ms.items()},
             "stage_ms_last_timed_step": {k: round(v, 4) for k, v in last.items()},
             "roofline": {"bound": "hbm", "kernel": "k1::fused_preprocess_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": how,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": K1_TRAFFIC_PER_FRAME * Fn,
+                         "traffic_source": "ncu --set full capture, profiles/r1_prof_k1c_raw.csv, scaled per frame",
+                         "peak_source": how,
                          "algorithmic_bytes_per_launch": K1_BYTES_PER_FRAME * Fn, "launch_ms": k1_ms},
             "cpu_baseline": cpu, "clocks": clocks,
         }
