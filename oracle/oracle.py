@@ -215,3 +215,104 @@ def scan_frame(bgr):
     f = lib().svo_scan_frame(_p(bgr), H, W, _p(mask), _p(corners), _p(ordered), _p(cells_u8), _p(cells_in))
     return dict(found=bool(f), mask=mask, corners=corners if f else None, ordered=ordered if f else None,
                 cells_u8=cells_u8 if f else None, cells_in=cells_in if f else None)
+
+
+# ---- V1: cv/preprocess_v2.py --------------------------------------------------------------------------
+def box_blur(g, k: int):
+    g = _u8(g)
+    out = np.empty_like(g)
+    lib().svo_box_blur_u8(_p(g), g.shape[0], g.shape[1], int(k), _p(out))
+    return out
+
+
+def dilate_ellipse(g, k: int):
+    g = _u8(g)
+    out = np.empty_like(g)
+    lib().svo_dilate_ellipse(_p(g), g.shape[0], g.shape[1], int(k), _p(out))
+    return out
+
+
+def erode_ellipse(g, k: int):
+    g = _u8(g)
+    out = np.empty_like(g)
+    lib().svo_erode_ellipse(_p(g), g.shape[0], g.shape[1], int(k), _p(out))
+    return out
+
+
+def divide_normalize(g, bg):
+    g, bg = _u8(g), _u8(bg)
+    out = np.empty_like(g)
+    lib().svo_divide_normalize(_p(g), _p(bg), C.c_long(g.size), _p(out))
+    return out
+
+
+def gaussian_blur_q8(g, n: int):
+    g = _u8(g)
+    out = np.empty_like(g)
+    lib().svo_gaussian_blur_q8(_p(g), g.shape[0], g.shape[1], int(n), _p(out))
+    return out
+
+
+def clahe_frame(g, tiles: int = 8, clip: float = 2.0):
+    g = _u8(g)
+    out = np.empty_like(g)
+    rc = lib().svo_clahe_frame(_p(g), g.shape[0], g.shape[1], int(tiles), C.c_double(clip), _p(out))
+    assert rc == 0, "frame sides must divide by the CLAHE grid"
+    return out
+
+
+def morph_cleanup(m):
+    m = _u8(m)
+    out = np.empty_like(m)
+    lib().svo_morph_cleanup(_p(m), m.shape[0], m.shape[1], _p(out))
+    return out
+
+
+def morph_ellipse_direct(g, k: int, dilate: bool):
+    g = _u8(g)
+    out = np.empty_like(g)
+    lib().svo_morph_ellipse_direct(_p(g), g.shape[0], g.shape[1], int(k), int(dilate), _p(out))
+    return out
+
+
+def otsu_inv(g):
+    """cv2.threshold(g, 0, 255, THRESH_BINARY_INV + THRESH_OTSU) -> (level, binary)"""
+    g = _u8(g)
+    out = np.empty_like(g)
+    t = lib().svo_threshold_otsu_inv(_p(g), C.c_long(g.size), _p(out))
+    return int(t), out
+
+
+def sauvola(g, window: int = 25, k: float = 0.2):
+    g = _u8(g)
+    out = np.empty_like(g)
+    lib().svo_threshold_sauvola(_p(g), g.shape[0], g.shape[1], int(window), C.c_float(k), _p(out))
+    return out
+
+
+def preprocess_v2(bgr, use_illumination_norm: bool = True, use_shadow_removal: bool = True):
+    """cv/preprocess_v2.py:205-244 -> (mask, has_glare, has_shadow)."""
+    bgr = _u8(bgr)
+    H, W = bgr.shape[:2]
+    out = np.empty((H, W), np.uint8)
+    flags = (C.c_int * 2)()
+    rc = lib().svo_preprocess_v2_opts(_p(bgr), H, W, int(use_illumination_norm), int(use_shadow_removal), _p(out), flags)
+    assert rc == 0, "frame sides must divide by 8"
+    return out, bool(flags[0]), bool(flags[1])
+
+
+METHODS = ("adaptive", "otsu", "sauvola")
+
+
+def preprocess_multi(bgr):
+    """cv/preprocess_v2.py:247-308 -> dict(binary, gray, enhanced, illumination_normalized, has_glare, has_shadow,
+    method_used, otsu_level, scores)."""
+    bgr = _u8(bgr)
+    H, W = bgr.shape[:2]
+    o = [np.empty((H, W), np.uint8) for _ in range(4)]
+    info = (C.c_int * 4)()
+    scores = (C.c_double * 3)()
+    rc = lib().svo_preprocess_multi(_p(bgr), H, W, _p(o[0]), _p(o[1]), _p(o[2]), _p(o[3]), info, scores)
+    assert rc == 0, "frame sides must divide by 8"
+    return dict(binary=o[0], gray=o[1], enhanced=o[2], illumination_normalized=o[3], has_glare=bool(info[0]),
+                has_shadow=bool(info[1]), method_used=METHODS[info[2]], otsu_level=int(info[3]), scores=list(scores))
