@@ -70,6 +70,39 @@ int svb_adaptive_threshold(svb_ctx *ctx, const uint8_t *gray, int n, int h, int 
 /* preprocess_for_grid_detection(image)  cv/preprocess.py:57-65: one fused kernel, BGR -> mask */
 int svb_preprocess_v1(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *mask, void *stream);
 
+/* ---- V1: cv/preprocess_v2.py ------------------------------------------------------------------------- */
+/* Frame sides must divide by 8 (the 8x8 CLAHE tile grid; OpenCV pads other sizes, not implemented -> SVB_ERR_UNSUPPORTED),
+ * be at least 32 px and at most 3990 px.  `channels` = 3 (BGR frames) or 1 (already gray: the reference's grayscale()
+ * passes 2-D input through, cv/preprocess_v2.py:33-37).
+ * info (optional): uint8 [n][4] = {has_glare, has_shadow, method (0 adaptive, 1 otsu, 2 sauvola), Otsu level}.
+ *
+ * preprocess_for_grid_detection(image, use_illumination_norm=True, use_shadow_removal=True)  cv/preprocess_v2.py:205-244:
+ * detect_glare + detect_shadow, remove_shadow on the frames that have one, normalize_illumination (elliptical close with
+ * k = max(h,w)//10 | 1, >= 51), CLAHE 8x8, GaussianBlur 5, adaptive threshold 11/2, 3x3 close + 2x2 open. */
+int svb_preprocess_v2(svb_ctx *ctx, const uint8_t *frames, int n, int h, int w, int channels, int use_illumination_norm,
+                      int use_shadow_removal, uint8_t *mask, uint8_t *info, void *stream);
+/* preprocess_multi_strategy(image)  cv/preprocess_v2.py:247-308 -> PreprocessResult: binary = the best-scoring of the
+ * adaptive / Otsu / Sauvola candidates (required); gray, enhanced, illumination_normalized: uint8 [n][h][w], each optional. */
+int svb_preprocess_multi_v2(svb_ctx *ctx, const uint8_t *frames, int n, int h, int w, int channels, uint8_t *binary,
+                            uint8_t *gray, uint8_t *enhanced, uint8_t *illumination_normalized, uint8_t *info,
+                            void *stream);
+/* The individual functions of cv/preprocess_v2.py on gray / binary images uint8 [n][h][w] (any size the operation
+ * itself allows).  `arg` is the operation's parameter where it has one; `info` as above (only the bytes the op sets). */
+#define SVB_V2_NORMALIZE_ILLUMINATION 1 /* normalize_illumination(gray)           :40-60                          */
+#define SVB_V2_DETECT_GLARE 2           /* detect_glare(gray, threshold=arg|250)   :63-81   dst = glare mask (opt) */
+#define SVB_V2_DETECT_SHADOW 3          /* detect_shadow(gray)                     :84-102  dst = shadow mask (opt)*/
+#define SVB_V2_REMOVE_SHADOW 4          /* remove_shadow(gray)                     :105-119                        */
+#define SVB_V2_CLAHE8 5                 /* apply_clahe(gray, 2.0, 8)               :122-129                        */
+#define SVB_V2_OTSU 6                   /* threshold_otsu(gray)                    :146-149 info[3] = level        */
+#define SVB_V2_SAUVOLA 7                /* threshold_sauvola(gray, 25, 0.2)        :152-175                        */
+#define SVB_V2_CLEANUP 8                /* morphological_cleanup(binary, 3, 2)     :178-202                        */
+#define SVB_V2_DILATE_ELLIPSE 9         /* cv2.dilate(gray, MORPH_ELLIPSE (arg,arg)), arg odd <= 399               */
+#define SVB_V2_ERODE_ELLIPSE 10         /* cv2.erode(...)                                                          */
+#define SVB_V2_BOX_BLUR 11              /* cv2.blur(gray, (arg,arg))               :89                             */
+#define SVB_V2_GAUSS21 12               /* cv2.GaussianBlur(gray, (21,21), 0)      :112                            */
+int svb_v2_stage(svb_ctx *ctx, int op, const uint8_t *src, int n, int h, int w, int arg, uint8_t *dst, uint8_t *info,
+                 void *stream);
+
 /* ---- G1..G4: cv/grid.py ---------------------------------------------------------------------- */
 /* find_grid_contour(binary, min_area_ratio=0.1)  cv/grid.py:37-71 with approximate_polygon's
  * epsilon_ratio (cv/grid.py:24-34; the reference always uses 0.02).

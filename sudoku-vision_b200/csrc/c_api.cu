@@ -57,6 +57,10 @@ void digitcnn_v3_free(svb_ctx *);
 int digitcnn_v3_load(svb_ctx *, const float *const *, int, cudaStream_t);
 int launch_digitcnn_v3(svb_ctx *, const float *, long long, float *, uint8_t *, float *, float *, cudaStream_t);
 int launch_digitcnn_tc(svb_ctx *, const float *, long long, float *, uint8_t *, float *, cudaStream_t);
+int preprocess_v2_run(svb_ctx *, const uint8_t *, const uint8_t *, int, int, int, int, int, uint8_t *, uint8_t *, cudaStream_t);
+int preprocess_multi_run(svb_ctx *, const uint8_t *, const uint8_t *, int, int, int, uint8_t *, uint8_t *, uint8_t *, uint8_t *,
+                         uint8_t *, cudaStream_t);
+int v2_stage(svb_ctx *, int, const uint8_t *, int, int, int, int, uint8_t *, uint8_t *, cudaStream_t);
 int launch_mask_not_found(svb_ctx *, const uint8_t *, int, uint8_t *, float *, cudaStream_t);
 
 }  // namespace svb
@@ -179,6 +183,33 @@ API int svb_preprocess_v1(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w,
     GUARD(ctx);
     SVB_REQUIRE(bgr && mask && dims_ok(n, h, w), SVB_ERR_INVALID, "svb_preprocess_v1: bad arguments");
     return preprocess_any(ctx, bgr, n, h, w, mask, (cudaStream_t)stream);
+}
+
+API int svb_preprocess_v2(svb_ctx *ctx, const uint8_t *frames, int n, int h, int w, int channels, int use_illumination_norm,
+                          int use_shadow_removal, uint8_t *mask, uint8_t *info, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(frames && mask && dims_ok(n, h, w) && (channels == 1 || channels == 3), SVB_ERR_INVALID,
+                "svb_preprocess_v2: bad arguments");
+    return preprocess_v2_run(ctx, channels == 3 ? frames : nullptr, channels == 1 ? frames : nullptr, n, h, w,
+                             use_illumination_norm != 0, use_shadow_removal != 0, mask, info, (cudaStream_t)stream);
+}
+
+API int svb_preprocess_multi_v2(svb_ctx *ctx, const uint8_t *frames, int n, int h, int w, int channels, uint8_t *binary,
+                                uint8_t *gray, uint8_t *enhanced, uint8_t *illumination_normalized, uint8_t *info,
+                                void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(frames && binary && dims_ok(n, h, w) && (channels == 1 || channels == 3), SVB_ERR_INVALID,
+                "svb_preprocess_multi_v2: bad arguments");
+    return preprocess_multi_run(ctx, channels == 3 ? frames : nullptr, channels == 1 ? frames : nullptr, n, h, w, binary, gray,
+                                enhanced, illumination_normalized, info, (cudaStream_t)stream);
+}
+
+API int svb_v2_stage(svb_ctx *ctx, int op, const uint8_t *src, int n, int h, int w, int arg, uint8_t *dst, uint8_t *info,
+                     void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(src && dims_ok(n, h, w), SVB_ERR_INVALID, "svb_v2_stage: bad arguments");
+    SVB_REQUIRE(dst || op == SVB_V2_DETECT_GLARE || op == SVB_V2_DETECT_SHADOW, SVB_ERR_INVALID, "svb_v2_stage: null output");
+    return v2_stage(ctx, op, src, n, h, w, arg, dst, info, (cudaStream_t)stream);
 }
 
 API int svb_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, int w, double min_area_ratio,

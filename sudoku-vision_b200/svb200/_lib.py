@@ -27,6 +27,9 @@ SIGNATURES = {
     "svb_blur": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "svb_adaptive_threshold": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "svb_preprocess_v1": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "svb_preprocess_v2": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "svb_preprocess_multi_v2": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "svb_v2_stage": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p]),
     "svb_find_grid_contour": (_i, [_p, _p, _i, _i, _i, _d, _d, _p, _p, _p]),
     "svb_detect_grid_contour_v2": (_i, [_p, _p, _i, _i, _i, _d, _p, _p, _p]),
     "svb_warp_perspective": (_i, [_p, _p, _i, _i, _i, _p, _p, _i, _p, _p]),

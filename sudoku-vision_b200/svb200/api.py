@@ -199,6 +199,59 @@ class Scanner:
                    "svb_preprocess_v1")
         return out
 
+    # -- cv/preprocess_v2.py (row V1) ----------------------------------------------------------------
+    V2_OPS = dict(normalize_illumination=1, detect_glare=2, detect_shadow=3, remove_shadow=4, clahe8=5, otsu=6,
+                  sauvola=7, cleanup=8, dilate_ellipse=9, erode_ellipse=10, box_blur=11, gauss21=12)
+    V2_METHODS = ("adaptive", "otsu", "sauvola")
+
+    def _frames_nhw(self, frames, what):
+        """(n,H,W,3) BGR or (n,H,W) gray uint8 CUDA -> n, h, w, channels"""
+        if frames.dim() == 4:
+            self._chk_u8(frames, 4, what)
+            if frames.shape[3] != 3:
+                raise ValueError(f"{what}: colour frames must be (n,H,W,3)")
+            return frames.shape[0], frames.shape[1], frames.shape[2], 3
+        self._chk_u8(frames, 3, what)
+        return frames.shape[0], frames.shape[1], frames.shape[2], 1
+
+    def preprocess_v2(self, frames, use_illumination_norm: bool = True, use_shadow_removal: bool = True):
+        """cv/preprocess_v2.py:205-244 for a batch -> (mask (n,H,W) u8, info (n,4) u8 = glare, shadow, -, -)."""
+        torch = _torch()
+        n, h, w, ch = self._frames_nhw(frames, "preprocess_v2")
+        mask = torch.empty((n, h, w), dtype=torch.uint8, device=frames.device)
+        info = torch.empty((n, 4), dtype=torch.uint8, device=frames.device)
+        _lib.check(self.lib.svb_preprocess_v2(self._h, _ptr(frames), n, h, w, ch, int(bool(use_illumination_norm)),
+                                              int(bool(use_shadow_removal)), _ptr(mask), _ptr(info), self._stream()),
+                   "svb_preprocess_v2")
+        return mask, info
+
+    def preprocess_multi(self, frames, want_aux: bool = True) -> dict:
+        """cv/preprocess_v2.py:247-308 for a batch: dict(binary, gray, enhanced, illumination_normalized, info)."""
+        torch = _torch()
+        n, h, w, ch = self._frames_nhw(frames, "preprocess_multi")
+
+        def plane():
+            return torch.empty((n, h, w), dtype=torch.uint8, device=frames.device)
+
+        out = dict(binary=plane(), gray=plane() if want_aux else None, enhanced=plane() if want_aux else None,
+                   illumination_normalized=plane() if want_aux else None,
+                   info=torch.empty((n, 4), dtype=torch.uint8, device=frames.device))
+        _lib.check(self.lib.svb_preprocess_multi_v2(self._h, _ptr(frames), n, h, w, ch, _ptr(out["binary"]), _ptr(out["gray"]),
+                                                    _ptr(out["enhanced"]), _ptr(out["illumination_normalized"]),
+                                                    _ptr(out["info"]), self._stream()), "svb_preprocess_multi_v2")
+        return out
+
+    def v2_stage(self, op: str, src, arg: int = 0, want_image: bool = True):
+        """One function of cv/preprocess_v2.py on (n,H,W) u8 images -> (image or None, info (n,4) u8)."""
+        torch = _torch()
+        self._chk_u8(src, 3, "v2_stage")
+        n, h, w = src.shape
+        dst = torch.empty_like(src) if want_image else None
+        info = torch.zeros((n, 4), dtype=torch.uint8, device=src.device)
+        _lib.check(self.lib.svb_v2_stage(self._h, self.V2_OPS[op], _ptr(src), n, h, w, int(arg), _ptr(dst), _ptr(info),
+                                         self._stream()), f"svb_v2_stage({op})")
+        return dst, info
+
     def find_grid_contour(self, mask, min_area_ratio: float = 0.1, eps_ratio: float = 0.02):
         self._chk_u8(mask, 3, "find_grid_contour")
         torch = _torch()

@@ -1,0 +1,219 @@
+"""GPU tier (-m gpu), row V1: the cv/preprocess_v2.py kernels (csrc/preprocess_v2.cu) through the C ABI against the CPU
+oracle on seeded inputs, against the golden vectors minted from the reference module, and at BASELINE's full frame
+sizes (1080p, 4K).  Everything on this row is byte/integer work or fixed-order float32: bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CASES = [f"{t}_{v}" for t in ("a", "b") for v in ("plain", "shadow", "glare", "flat")]
+
+
+def _t(a):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+def _smooth(rng, h, w):
+    """noise + structure: smooth gradients, dark lines, a bright patch (ties and saturation both occur)"""
+    yy, xx = np.mgrid[0:h, 0:w]
+    g = 130 + 60 * np.sin(xx / 41.0) + 40 * np.cos(yy / 29.0) + rng.normal(0, 6, (h, w))
+    g[:, ::37] -= 90
+    g[::23, :] -= 70
+    g[h // 5: h // 3, w // 2: w // 2 + w // 6] = 255
+    return g.clip(0, 255).astype(np.uint8)
+
+
+@pytest.fixture(scope="module")
+def v2pre(golden):
+    return golden("v2pre")
+
+
+@pytest.mark.parametrize("hw", [(40, 56), (96, 136), (130, 97), (264, 520)])
+def test_primitives_vs_oracle(scanner, oracle, hw):
+    rng = np.random.default_rng(hw[0] * 31 + hw[1])
+    imgs = np.stack([_smooth(rng, *hw), rng.integers(0, 256, hw).astype(np.uint8)])
+    d = _t(imgs)
+    for k in (3, 9, 13, 25):
+        got = _np(scanner.v2_stage("box_blur", d, k)[0])
+        for i in range(2):
+            assert np.array_equal(got[i], oracle.box_blur(imgs[i], k)), f"box blur k={k}"
+    for k in (1, 3, 7, 21, 33):
+        if k // 2 >= min(hw):
+            continue
+        for op, fn in (("dilate_ellipse", oracle.dilate_ellipse), ("erode_ellipse", oracle.erode_ellipse)):
+            got = _np(scanner.v2_stage(op, d, k)[0])
+            for i in range(2):
+                assert np.array_equal(got[i], fn(imgs[i], k)), f"{op} k={k}"
+    got = _np(scanner.v2_stage("gauss21", d)[0])
+    rs = _np(scanner.v2_stage("remove_shadow", d)[0])
+    ni = _np(scanner.v2_stage("normalize_illumination", d)[0])
+    ot, oinfo = scanner.v2_stage("otsu", d)
+    sv = _np(scanner.v2_stage("sauvola", d)[0])
+    ki = max(max(hw) // 10 + (max(hw) // 10 % 2 == 0), 51)  # cv/preprocess_v2.py:46-49
+    for i in range(2):
+        assert np.array_equal(got[i], oracle.gaussian_blur_q8(imgs[i], 21))
+        assert np.array_equal(rs[i], oracle.divide_normalize(imgs[i], oracle.gaussian_blur_q8(oracle.dilate_ellipse(imgs[i], 7), 21)))
+        assert np.array_equal(ni[i], oracle.divide_normalize(imgs[i], oracle.erode_ellipse(oracle.dilate_ellipse(imgs[i], ki), ki)))
+        lvl, want = oracle.otsu_inv(imgs[i])
+        assert int(_np(oinfo)[i, 3]) == lvl and np.array_equal(_np(ot)[i], want)
+        assert np.array_equal(sv[i], oracle.sauvola(imgs[i]))
+    if hw[0] % 8 == 0 and hw[1] % 8 == 0:
+        cl = _np(scanner.v2_stage("clahe8", d)[0])
+        for i in range(2):
+            assert np.array_equal(cl[i], oracle.clahe_frame(imgs[i]))
+    masks = np.stack([((rng.random(hw) < p) * 255).astype(np.uint8) for p in (0.3, 0.7)])
+    cu = _np(scanner.v2_stage("cleanup", _t(masks))[0])
+    for i in range(2):
+        assert np.array_equal(cu[i], oracle.morph_cleanup(masks[i]))
+
+
+def test_ellipse_large_elements_and_wide_frames(scanner, oracle):
+    """k = 193 / 385 (the 1080p / 4K illumination kernels) and frames wider than one 2048-column strip."""
+    rng = np.random.default_rng(77)
+    for (h, w, k) in ((260, 400, 193), (120, 2304, 51), (96, 4100, 33), (400, 420, 385)):
+        img = np.stack([_smooth(rng, h, w)])
+        for op, fn in (("dilate_ellipse", oracle.dilate_ellipse), ("erode_ellipse", oracle.erode_ellipse)):
+            got = _np(scanner.v2_stage(op, _t(img), k)[0])[0]
+            assert np.array_equal(got, fn(img[0], k)), f"{op} k={k} {h}x{w}"
+
+
+def test_detect_glare_and_shadow(scanner, oracle, v2pre):
+    for case in CASES:
+        g = v2pre[case + "_ref_gray"]
+        flags = v2pre[case + "_ref_flags"].tolist()
+        gm, gi = scanner.v2_stage("detect_glare", _t(g[None]))
+        sm, si = scanner.v2_stage("detect_shadow", _t(g[None]))
+        assert [bool(_np(gi)[0, 0]), bool(_np(si)[0, 1])] == flags
+        assert np.array_equal(_np(gm)[0], (g > 250).astype(np.uint8) * 255)
+        k = max(g.shape) // 20
+        k += (k % 2 == 0)
+        want = ((g.astype(np.int32) - oracle.box_blur(g, k).astype(np.int32)) < -30).astype(np.uint8) * 255
+        assert np.array_equal(_np(sm)[0], want)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_golden_preprocess_v2(scanner, v2pre, case):
+    img = _t(v2pre[case + "_bgr"][None])
+    mask, info = scanner.preprocess_v2(img)
+    assert np.array_equal(_np(mask)[0], v2pre[case + "_ref_mask"])
+    assert _np(info)[0, :2].astype(bool).tolist() == v2pre[case + "_ref_flags"].tolist()
+    assert np.array_equal(_np(scanner.preprocess_v2(img, False, True)[0])[0], v2pre[case + "_ref_mask_noillum"])
+    assert np.array_equal(_np(scanner.preprocess_v2(img, True, False)[0])[0], v2pre[case + "_ref_mask_noshadow"])
+    assert np.array_equal(_np(scanner.preprocess_v2(img, False, False)[0])[0].shape, v2pre[case + "_ref_mask"].shape)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_golden_preprocess_multi(scanner, v2pre, case):
+    r = scanner.preprocess_multi(_t(v2pre[case + "_bgr"][None]))
+    for k, ref in (("binary", "_ref_binary"), ("gray", "_ref_gray"), ("enhanced", "_ref_enhanced"),
+                   ("illumination_normalized", "_ref_illum")):
+        assert np.array_equal(_np(r[k])[0], v2pre[case + ref]), k
+    info = _np(r["info"])[0]
+    assert info[:2].astype(bool).tolist() == v2pre[case + "_ref_flags"].tolist()
+    assert scanner.V2_METHODS[int(info[2])] == str(v2pre[case + "_ref_method"])
+
+
+def test_mixed_batch_flags_are_per_frame(scanner, v2pre):
+    """Frames with and without shadow / glare in ONE batch: the conditional remove_shadow and the strategy choice are
+    decided per frame on the device."""
+    names = [c for c in CASES if c.startswith("a_")]
+    batch = np.stack([v2pre[c + "_bgr"] for c in names])
+    r = scanner.preprocess_multi(_t(batch))
+    m, _ = scanner.preprocess_v2(_t(batch))
+    for i, c in enumerate(names):
+        assert np.array_equal(_np(r["binary"])[i], v2pre[c + "_ref_binary"]), c
+        assert np.array_equal(_np(r["illumination_normalized"])[i], v2pre[c + "_ref_illum"]), c
+        assert np.array_equal(_np(m)[i], v2pre[c + "_ref_mask"]), c
+    flags = _np(r["info"])[:, :2].astype(bool)
+    assert flags[:, 1].any() and not flags[:, 1].all()
+
+
+def test_gray_input_passes_through(scanner, oracle, v2pre):
+    g = v2pre["a_plain_ref_gray"]
+    bgr = np.repeat(g[..., None], 3, axis=2)  # gray(B=G=R=g) == g for this fixed-point formula
+    assert np.array_equal(oracle.gray(bgr), g)
+    a, _ = scanner.preprocess_v2(_t(g[None]))
+    b, _ = scanner.preprocess_v2(_t(bgr[None]))
+    assert np.array_equal(_np(a), _np(b))
+
+
+def _full_size_frames(h, w, seed):
+    from svb200 import frames as F
+
+    img = F.add_noise_host(F.make_frame(seed, h, w, 12.0).image, seed)
+    sh = img.copy()  # dark bands a 32nd of the width wide, every fourth one: ~24 % "shadow" pixels -> has_shadow
+    band = (np.arange(w) // (w // 32)) % 4 == 0
+    sh[:, band] = (sh[:, band] * 0.45).astype(np.uint8)
+    return np.stack([img, sh])
+
+
+def test_full_size_1080p(scanner, oracle):
+    batch = _full_size_frames(1080, 1920, 606)
+    r = scanner.preprocess_multi(_t(batch))
+    m, info = scanner.preprocess_v2(_t(batch))
+    shadows = []
+    for i in range(2):
+        o = oracle.preprocess_multi(batch[i])
+        for k in ("binary", "gray", "enhanced", "illumination_normalized"):
+            assert np.array_equal(_np(r[k])[i], o[k]), (i, k)
+        got = _np(r["info"])[i]
+        assert [bool(got[0]), bool(got[1])] == [o["has_glare"], o["has_shadow"]]
+        assert scanner.V2_METHODS[int(got[2])] == o["method_used"] and int(got[3]) == o["otsu_level"]
+        assert np.array_equal(_np(m)[i], oracle.preprocess_v2(batch[i])[0])
+        shadows.append(o["has_shadow"])
+    assert shadows == [False, True]
+
+
+def test_full_size_4k(scanner, oracle):
+    """BASELINE configs[3] frame size: k = 385 elliptical close, 480x270 CLAHE tiles."""
+    batch = _full_size_frames(2160, 3840, 707)[1:]
+    m, info = scanner.preprocess_v2(_t(batch))
+    want, glare, shadow = oracle.preprocess_v2(batch[0])
+    assert np.array_equal(_np(m)[0], want)
+    assert [bool(x) for x in _np(info)[0, :2]] == [glare, shadow] and shadow
+
+
+def test_unsupported_sizes_raise(scanner):
+    import torch
+
+    with pytest.raises(NotImplementedError):
+        scanner.preprocess_v2(torch.zeros((1, 100, 100, 3), dtype=torch.uint8, device="cuda"))  # sides not / 8
+    with pytest.raises(NotImplementedError):
+        scanner.v2_stage("dilate_ellipse", torch.zeros((1, 64, 64), dtype=torch.uint8, device="cuda"), 401)
+
+
+def test_dropin_module_matches_reference_golden(v2pre):
+    """sudoku-vision_b200/dropin/cv/preprocess_v2.py: the reference's names and return types."""
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "sudoku-vision_b200", "dropin"))
+    from cv import preprocess_v2 as P
+
+    c = "a_shadow"
+    img = v2pre[c + "_bgr"]
+    assert np.array_equal(P.preprocess_for_grid_detection(img), v2pre[c + "_ref_mask"])
+    r = P.preprocess_multi_strategy(img)
+    assert isinstance(r, P.PreprocessResult)
+    assert np.array_equal(r.binary, v2pre[c + "_ref_binary"]) and np.array_equal(r.enhanced, v2pre[c + "_ref_enhanced"])
+    assert np.array_equal(r.illumination_normalized, v2pre[c + "_ref_illum"]) and np.array_equal(r.gray, v2pre[c + "_ref_gray"])
+    assert (r.has_glare, r.has_shadow) == tuple(bool(x) for x in v2pre[c + "_ref_flags"]) and r.method_used == str(v2pre[c + "_ref_method"])
+    g = v2pre["u_gray"]
+    assert np.array_equal(P.normalize_illumination(g), v2pre["u_ref_illum"])
+    assert np.array_equal(P.remove_shadow(g), v2pre["u_ref_noshadow"])
+    assert np.array_equal(P.apply_clahe(g), v2pre["u_ref_clahe8"])
+    assert np.array_equal(P.morphological_cleanup(v2pre["u_mask"]), v2pre["u_ref_cleanup"])
+    assert np.array_equal(P.grayscale(img), v2pre[c + "_ref_gray"])
+    has, mask = P.detect_glare(v2pre["a_glare_ref_gray"])
+    assert has is True and mask.dtype == np.uint8
+    with pytest.raises(NotImplementedError):
+        P.apply_clahe(g, clip_limit=3.0)
+    with pytest.raises(NotImplementedError):
+        P.threshold_sauvola(g, window_size=15)
