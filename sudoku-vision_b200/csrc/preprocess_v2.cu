@@ -335,45 +335,38 @@ __global__ void __launch_bounds__(NT) chord_tables_kernel(Params P) {
     }
 }
 
-// (2) chords
-__global__ void __launch_bounds__(NT, 2) ellipse_chords_kernel(Params P, Chords C) {
+// (2) chords.  Per-chord look-up constants and per-row level masks are computed on the host and passed by value
+// (kernel parameter space = constant bank): every index below is warp-uniform, so the class tests run on the uniform
+// datapath and the look-up addresses / byte selectors come from uniform registers.
+constexpr int NULLCLS = 0x7ffffff0;
+struct ClsTab {
+    // entry T-1+di = chord at row offset di - R: {.x identity, .y / .w word-aligned byte offsets of the two windows
+    // relative to the lane's own offset in the row table, .z byte selectors (low 16 bits: first window, high: second)};
+    // entries outside the element have identity NULLCLS and point into the row table's all-zero slot
+    int4 c[2 * (MAXK / 2) + 2 * T];
+    unsigned short need[2 * (MAXK / 2) + T];  // table slots used by a source row at offset i - R from the CTA's first row
+};
+
+__device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 sel) {
+    u32 d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+__global__ void __launch_bounds__(NT, 2) ellipse_chords_kernel(const __grid_constant__ Params P, const __grid_constant__ ClsTab K) {
     extern __shared__ __align__(128) u8 s_raw[];
     const int f = blockIdx.z;
     if (P.only && !P.only[f * 4 + 1]) return;
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * XS, y0 = blockIdx.y * T;
     const int h = P.h, w = P.w, R = P.R, nslots = P.nslots, seg = P.seg, NS = P.nstage;
-    const int rowtab = nslots * seg, stage_bytes = RB * rowtab;
-    // shared memory: [NS stages][RB][nslots][seg] | mbarriers | int4 cls[2R + 2T - 1] | u16 need[2R+T]
+    const int rowtab = (nslots + 1) * seg, stage_bytes = RB * rowtab;
+    // shared memory: [NS stages][RB][nslots + 1][seg] | mbarriers.  The extra slot of every row table stays zero: chords
+    // outside the element (NULLCLS entries) look up there, so the inner loop has no special case.
     unsigned long long *full = (unsigned long long *)(s_raw + (size_t)NS * stage_bytes);
-    int4 *s_cls = (int4 *)(full + 4);  // entry T-1+di: look-up constants of the chord at row offset di - R; NULL outside
-    unsigned short *s_need = (unsigned short *)(s_cls + 2 * R + 2 * T - 1);
-    constexpr int NULLCLS = 0x7ffffff0;
-    for (int i = tid; i < 2 * R + 2 * T - 1; i += NT) {
-        const int di = i - (T - 1);
-        int4 c = make_int4(NULLCLS, 0, 0, 0);
-        if (di >= 0 && di <= 2 * R) {
-            const int cw = C.hw[di];
-            const int l = 31 - __clz(2 * cw + 1);
-            const int base = P.slot_of_level[l] * seg;
-            const int ox = base - cw, oy = base + cw + 1 - (1 << l);  // window starts relative to the lane's offset
-            // byte selectors that expand window bytes (s, s+1 | s+2, s+3) of a word pair into duplicated-byte u16 lanes
-            auto sel = [](int sft) {
-                const u32 lo = sft | (sft << 4) | ((sft + 1) << 8) | ((sft + 1) << 12);
-                const u32 hi = (sft + 2) | ((sft + 2) << 4) | ((sft + 3) << 8) | ((sft + 3) << 12);
-                return lo | (hi << 16);
-            };
-            c = make_int4(ox, oy, (int)sel(ox & 3), (int)sel(oy & 3));  // .x doubles as the chord's identity
-        }
-        s_cls[i] = c;
-    }
-    for (int i = tid; i < 2 * R + T; i += NT) {  // levels needed by a source row at offset d0 = i - R from y0
-        u32 m = 0;
-        for (int t = 0; t < T; ++t) {
-            const int di = i - t;
-            if (di >= 0 && di <= 2 * R) m |= 1u << P.slot_of_level[31 - __clz(2 * C.hw[di] + 1)];
-        }
-        s_need[i] = (unsigned short)m;
+    for (int i = tid; i < NS * RB * (seg >> 4); i += NT) {
+        const int rt = i / (seg >> 4), q = i - rt * (seg >> 4);
+        ((uint4 *)(s_raw + (size_t)rt * rowtab + (size_t)nslots * seg))[q] = make_uint4(0, 0, 0, 0);
     }
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
@@ -391,17 +384,17 @@ __global__ void __launch_bounds__(NT, 2) ellipse_chords_kernel(Params P, Chords 
         for (int rr = 0; rr < RB; ++rr) {
             const int r = r_first + b * RB + rr;
             if (r > r_last) break;
-            total += __popc((u32)s_need[r - y0 + R]) * seg_bytes;
+            total += __popc((u32)K.need[r - y0 + R]) * seg_bytes;
         }
         mbar_expect_tx(&full[stage], total);
         for (int rr = 0; rr < RB; ++rr) {
             const int r = r_first + b * RB + rr;
             if (r > r_last) break;
-            u32 m = s_need[r - y0 + R];
+            u32 m = K.need[r - y0 + R];
             while (m) {
                 const int slot = __ffs(m) - 1;
                 m &= m - 1;
-                tma_load_1d(s_raw + (size_t)stage * stage_bytes + (size_t)(rr * nslots + slot) * seg,
+                tma_load_1d(s_raw + (size_t)stage * stage_bytes + (size_t)rr * rowtab + (size_t)slot * seg,
                             tab_f + ((size_t)r * nslots + slot) * P.rw, seg_bytes, &full[stage]);
             }
         }
@@ -421,31 +414,32 @@ __global__ void __launch_bounds__(NT, 2) ellipse_chords_kernel(Params P, Chords 
             const int r = r_first + b * RB + rr;
             if (r > r_last) break;
             const u8 *tab = s_raw + (size_t)stage * stage_bytes + (size_t)rr * rowtab + o_a;
-            const int4 *cls = s_cls + (r - y0 + R) + (T - 1);  // chord of output row t: cls[-t]
+            const int ci = (r - y0 + R) + (T - 1);  // chord of output row t: K.c[ci - t]
             int cur = NULLCLS;
-            u32 h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+            // the two windows of the current chord, expanded to duplicated-byte u16 lanes (pixels 0,1 | 2,3 of each quad)
+            u32 a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
 #pragma unroll
             for (int t = 0; t < T; ++t) {
-                const int4 c = cls[-t];
+                const int4 c = K.c[ci - t];
                 if (c.x != cur) {
                     cur = c.x;
-                    if (c.x == NULLCLS) {
-                        h0 = h1 = h2 = h3 = 0u;
-                    } else {
-                        const u32 *pa = (const u32 *)(tab + (c.x & ~3)), *pb = (const u32 *)(tab + (c.y & ~3));
-                        const u32 a0 = pa[0], a1 = pa[1], a2 = pa[NT], a3 = pa[NT + 1];
-                        const u32 b0 = pb[0], b1 = pb[1], b2 = pb[NT], b3 = pb[NT + 1];
-                        const u32 sx = (u32)c.z, sy = (u32)c.w;
-                        h0 = max16x2(__byte_perm(a0, a1, sx), __byte_perm(b0, b1, sy));
-                        h1 = max16x2(__byte_perm(a0, a1, sx >> 16), __byte_perm(b0, b1, sy >> 16));
-                        h2 = max16x2(__byte_perm(a2, a3, sx), __byte_perm(b2, b3, sy));
-                        h3 = max16x2(__byte_perm(a2, a3, sx >> 16), __byte_perm(b2, b3, sy >> 16));
-                    }
+                    const u32 *pa = (const u32 *)(tab + c.y), *pb = (const u32 *)(tab + c.w);
+                    const u32 p0 = pa[0], p1 = pa[1], p2 = pa[NT], p3 = pa[NT + 1];
+                    const u32 q0 = pb[0], q1 = pb[1], q2 = pb[NT], q3 = pb[NT + 1];
+                    const u32 sx = (u32)c.z, sy = (u32)c.z >> 16;
+                    a0 = prmt(p0, p1, sx);
+                    a1 = prmt(p0, p1, sx + 0x2222u);
+                    a2 = prmt(p2, p3, sx);
+                    a3 = prmt(p2, p3, sx + 0x2222u);
+                    b0 = prmt(q0, q1, sy);
+                    b1 = prmt(q0, q1, sy + 0x2222u);
+                    b2 = prmt(q2, q3, sy);
+                    b3 = prmt(q2, q3, sy + 0x2222u);
                 }
-                acc[t][0] = max16x2(acc[t][0], h0);
-                acc[t][1] = max16x2(acc[t][1], h1);
-                acc[t][2] = max16x2(acc[t][2], h2);
-                acc[t][3] = max16x2(acc[t][3], h3);
+                acc[t][0] = __vimax3_u16x2(acc[t][0], a0, b0);
+                acc[t][1] = __vimax3_u16x2(acc[t][1], a1, b1);
+                acc[t][2] = __vimax3_u16x2(acc[t][2], a2, b2);
+                acc[t][3] = __vimax3_u16x2(acc[t][3], a3, b3);
             }
         }
         __syncthreads();  // every lane is done with this stage: refill it
@@ -865,10 +859,37 @@ int launch_ellipse_morph(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, 
     P.rw = (P.padl + w + tail + 15) & ~15;
     P.seg = (P.padl + morph::XS + tail + 15) & ~15;
     P.xr = is_dilate ? 0u : 0xffffffffu;
-    const size_t stage_bytes = (size_t)morph::RB * nslots * P.seg;
+    const size_t stage_bytes = (size_t)morph::RB * (nslots + 1) * P.seg;
     int ns = (int)((100u * 1024u) / stage_bytes);
     P.nstage = ns < 2 ? 2 : (ns > 4 ? 4 : ns);
-    const size_t smem_b = (size_t)P.nstage * stage_bytes + 4 * 8 + (size_t)(2 * P.R + 2 * morph::T) * sizeof(int4) + (size_t)(2 * P.R + morph::T) * 2 + 16;
+    const size_t smem_b = (size_t)P.nstage * stage_bytes + 4 * 8 + 16;
+    // per-chord look-up constants (see morph::ClsTab)
+    morph::ClsTab K;
+    memset(&K, 0, sizeof K);
+    auto level_of = [](int cw) {
+        int nn = 2 * cw + 1, ll = 0;
+        while ((2 << ll) <= nn) ++ll;
+        return ll;
+    };
+    auto sel_lo = [](int sft) { return sft | (sft << 4) | ((sft + 1) << 8) | ((sft + 1) << 12); };
+    for (int i = 0; i < 2 * P.R + 2 * morph::T - 1; ++i) {
+        const int di = i - (morph::T - 1);
+        K.c[i] = make_int4(morph::NULLCLS, nslots * P.seg, sel_lo(0) | (sel_lo(0) << 16), nslots * P.seg);
+        if (di >= 0 && di <= 2 * P.R) {
+            const int cw = C.hw[di], l = level_of(cw);
+            const int base = P.slot_of_level[l] * P.seg;
+            const int ox = base - cw, oy = base + cw + 1 - (1 << l);
+            K.c[i] = make_int4(ox, ox & ~3, sel_lo(ox & 3) | (sel_lo(oy & 3) << 16), oy & ~3);
+        }
+    }
+    for (int i = 0; i < 2 * P.R + morph::T; ++i) {
+        unsigned m = 0;
+        for (int t = 0; t < morph::T; ++t) {
+            const int di = i - t;
+            if (di >= 0 && di <= 2 * P.R) m |= 1u << P.slot_of_level[level_of(C.hw[di])];
+        }
+        K.need[i] = (unsigned short)m;
+    }
     const size_t smem_a = (size_t)levels * P.rw;
     SVB_REQUIRE(smem_b <= 220 * 1024 && smem_a <= 220 * 1024, SVB_ERR_UNSUPPORTED, "elliptical morphology: element too large for shared memory");
     SVB_CUDA_OK(cudaFuncSetAttribute(morph::ellipse_chords_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -890,7 +911,7 @@ int launch_ellipse_morph(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, 
         int rc = check_launch(ctx, "chord_tables_kernel");
         if (rc) return rc;
         dim3 grid((w + morph::XS - 1) / morph::XS, (h + morph::T - 1) / morph::T, m);
-        morph::ellipse_chords_kernel<<<grid, morph::NT, smem_b, st>>>(P, C);
+        morph::ellipse_chords_kernel<<<grid, morph::NT, smem_b, st>>>(P, K);
         rc = check_launch(ctx, "ellipse_chords_kernel");
         if (rc) return rc;
     }
