@@ -186,6 +186,18 @@ int svb_scan_batch_v1(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uin
 int svb_scan_batch_v1_host(svb_ctx *ctx, const uint8_t *host_bgr, int n, int h, int w, uint8_t *host_digits,
                            float *host_conf, int32_t *host_corners, uint8_t *host_found);
 
+/* ---- whole v2 path: pipeline/run_v2.py:276-330 for n frames ------------------------------------------ */
+/* preprocess_multi_strategy -> detect_grid method 1 (contour + is_valid_quadrilateral; the Hough / rotation / Harris
+ * fallbacks of cv/grid_v2.py:446-508 and the grid_quality gate of run_v2.py:300-308 are not built: this is
+ * `run_v2.py --no-quality-check` restricted to method 1) -> warp + 81 cells + preprocess_cell -> DigitCNNv3 ->
+ * softmax top-3 (run_v2.py:149-190).  Requires svb_digitcnn_v3_load.
+ * Outputs: digits uint8 [n][81] / conf float [n][81] (best class), alt_digits uint8 [n][81][2] / alt_conf float
+ * [n][81][2] (2nd and 3rd, optional), logits float [n][81][10] (optional), corners int32 [n][4][2] ordered TL,TR,BR,BL,
+ * found uint8 [n], info uint8 [n][4] as svb_preprocess_multi_v2 (optional).  Frames with found == 0 get zeros. */
+int svb_scan_batch_v2(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *digits, float *conf,
+                      uint8_t *alt_digits, float *alt_conf, float *logits, int32_t *corners, uint8_t *found, uint8_t *info,
+                      void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,8 @@ int preprocess_v2_run(svb_ctx *, const uint8_t *, const uint8_t *, int, int, int
 int preprocess_multi_run(svb_ctx *, const uint8_t *, const uint8_t *, int, int, int, uint8_t *, uint8_t *, uint8_t *, uint8_t *,
                          uint8_t *, cudaStream_t);
 int v2_stage(svb_ctx *, int, const uint8_t *, int, int, int, int, uint8_t *, uint8_t *, cudaStream_t);
+int launch_top3(svb_ctx *, const float *, const uint8_t *, long long, uint8_t *, float *, uint8_t *, float *, cudaStream_t);
+bool digitcnn_v3_loaded(const svb_ctx *);
 int launch_mask_not_found(svb_ctx *, const uint8_t *, int, uint8_t *, float *, cudaStream_t);
 
 }  // namespace svb
@@ -342,6 +344,49 @@ API int svb_scan_batch_v1(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w,
                 "svb_scan_batch_v1: bad arguments");
     SVB_REQUIRE(ctx->cnn.loaded, SVB_ERR_NOT_LOADED, "svb_scan_batch_v1: DigitCNN weights not loaded");
     return scan_batch(ctx, bgr, n, h, w, digits, conf, logits, corners, found, (cudaStream_t)stream);
+}
+
+// v2 whole path (pipeline/run_v2.py:276-330 with --no-quality-check): frames are processed in chunks so that the
+// preprocess_v2 planes (about 11 per frame) stay within a few GB whatever n is.
+API int svb_scan_batch_v2(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *digits, float *conf,
+                          uint8_t *alt_digits, float *alt_conf, float *logits, int32_t *corners, uint8_t *found, uint8_t *info,
+                          void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(bgr && digits && conf && corners && found && dims_ok(n, h, w), SVB_ERR_INVALID, "svb_scan_batch_v2: bad arguments");
+    SVB_REQUIRE(digitcnn_v3_loaded(ctx), SVB_ERR_NOT_LOADED, "svb_scan_batch_v2: DigitCNNv3 weights not loaded");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t px = (size_t)h * w;
+    int chunk = (int)(((size_t)6 << 30) / (px * 13 + 81 * 784 * 4 + 81 * 40));
+    chunk = chunk < 1 ? 1 : (chunk > n ? n : chunk);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return o;
+    };
+    const size_t o_bin = take(px * chunk), o_pm1 = take((size_t)chunk * 81 * 784 * sizeof(float));
+    const size_t o_log = take((size_t)chunk * 81 * 10 * sizeof(float));
+    if (ctx->arena[AR_PATH].reserve(off) != SVB_OK) return SVB_ERR_CUDA;
+    char *base = (char *)ctx->arena[AR_PATH].ptr;
+    for (int f0 = 0; f0 < n; f0 += chunk) {
+        const int m = n - f0 < chunk ? n - f0 : chunk;
+        const uint8_t *fr = bgr + (size_t)f0 * px * 3;
+        uint8_t *binary = (uint8_t *)(base + o_bin);
+        float *pm1 = (float *)(base + o_pm1);
+        float *lg = logits ? logits + (size_t)f0 * 810 : (float *)(base + o_log);
+        int rc = preprocess_multi_run(ctx, fr, nullptr, m, h, w, binary, nullptr, nullptr, nullptr, info ? info + (size_t)f0 * 4 : nullptr, st);
+        if (rc) return rc;
+        rc = launch_find_grid_contour(ctx, binary, m, h, w, 0.1, 0.02, corners + (size_t)f0 * 8, found + f0, st, 1);
+        if (rc) return rc;
+        rc = launch_cells_from_frames(ctx, fr, m, h, w, corners + (size_t)f0 * 8, found + f0, nullptr, pm1, st);
+        if (rc) return rc;
+        rc = launch_digitcnn_v3(ctx, pm1, (long long)m * 81, lg, nullptr, nullptr, nullptr, st);
+        if (rc) return rc;
+        rc = launch_top3(ctx, lg, found + f0, (long long)m * 81, digits + (size_t)f0 * 81, conf + (size_t)f0 * 81,
+                         alt_digits ? alt_digits + (size_t)f0 * 162 : nullptr, alt_conf ? alt_conf + (size_t)f0 * 162 : nullptr, st);
+        if (rc) return rc;
+    }
+    return SVB_OK;
 }
 
 // Host-buffer path.  The frames are split into chunks that alternate between two worker contexts, each with

@@ -150,6 +150,57 @@ head_kernel(const float *__restrict__ x, const float *__restrict__ fw, const flo
     }
 }
 
+// predict_cells_with_alternatives (pipeline/run_v2.py:166-180): softmax over the 10 logits, top-3 by probability.
+// One thread per cell.  Frames without a grid (found == 0) get digit 0 / confidence 0 everywhere.
+__global__ void top3_kernel(const float *__restrict__ logits, const uint8_t *__restrict__ found, long long n_cells,
+                            uint8_t *__restrict__ digits, float *__restrict__ conf, uint8_t *__restrict__ alt_digits,
+                            float *__restrict__ alt_conf) {
+    const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= n_cells) return;
+    float p[10];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 10; ++c) {
+        p[c] = logits[cell * 10 + c];
+        mx = fmaxf(mx, p[c]);
+    }
+    float den = 0.f;
+#pragma unroll
+    for (int c = 0; c < 10; ++c) {
+        p[c] = expf(p[c] - mx);
+        den += p[c];
+    }
+    const bool ok = !found || found[cell / 81] == 1;
+    int idx[3];
+    float val[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int best = 0;
+        float bv = -1.f;
+#pragma unroll
+        for (int c = 0; c < 10; ++c)
+            if (p[c] > bv) {  // first maximum wins
+                bv = p[c];
+                best = c;
+            }
+        idx[k] = best;
+        val[k] = bv / den;
+#pragma unroll
+        for (int c = 0; c < 10; ++c)
+            if (c == best) p[c] = -2.f;
+    }
+    digits[cell] = ok ? (uint8_t)idx[0] : 0;
+    conf[cell] = ok ? val[0] : 0.f;
+    if (alt_digits) {
+        alt_digits[cell * 2 + 0] = ok ? (uint8_t)idx[1] : 0;
+        alt_digits[cell * 2 + 1] = ok ? (uint8_t)idx[2] : 0;
+    }
+    if (alt_conf) {
+        alt_conf[cell * 2 + 0] = ok ? val[1] : 0.f;
+        alt_conf[cell * 2 + 1] = ok ? val[2] : 0.f;
+    }
+}
+
 }  // namespace k6
 
 // Folded parameters, in the order svb_digitcnn_v3_load receives them (element counts):
@@ -254,5 +305,13 @@ int launch_digitcnn_v3(svb_ctx *ctx, const float *x, long long n, float *logits,
     }
     return rc;
 }
+
+int launch_top3(svb_ctx *ctx, const float *logits, const uint8_t *found, long long n_cells, uint8_t *digits, float *conf,
+                uint8_t *alt_digits, float *alt_conf, cudaStream_t st) {
+    k6::top3_kernel<<<(unsigned)((n_cells + 127) / 128), 128, 0, st>>>(logits, found, n_cells, digits, conf, alt_digits, alt_conf);
+    return check_launch(ctx, "k6::top3_kernel");
+}
+
+bool digitcnn_v3_loaded(const svb_ctx *ctx) { return ctx->cnn_v3 != nullptr; }
 
 }  // namespace svb

@@ -339,6 +339,27 @@ class Scanner:
                                               self._stream()), "svb_scan_batch_v1")
         return out
 
+    def scan_batch_v2(self, bgr, want_logits: bool = False) -> dict:
+        """pipeline/run_v2.py:276-330 (--no-quality-check, detection method 1) for a device-resident batch (n,H,W,3) u8:
+        preprocess_multi_strategy -> contour + validity -> cells -> DigitCNNv3 -> top-3.  Needs load_weights_v3."""
+        torch = _torch()
+        self._chk_u8(bgr, 4, "scan_batch_v2")
+        n, h, w, _ = bgr.shape
+        dev = bgr.device
+        out = dict(digits=torch.empty((n, 81), dtype=torch.uint8, device=dev),
+                   conf=torch.empty((n, 81), dtype=torch.float32, device=dev),
+                   alt_digits=torch.empty((n, 81, 2), dtype=torch.uint8, device=dev),
+                   alt_conf=torch.empty((n, 81, 2), dtype=torch.float32, device=dev),
+                   logits=torch.empty((n, 81, 10), dtype=torch.float32, device=dev) if want_logits else None,
+                   corners=torch.empty((n, 4, 2), dtype=torch.int32, device=dev),
+                   found=torch.empty((n,), dtype=torch.uint8, device=dev),
+                   info=torch.empty((n, 4), dtype=torch.uint8, device=dev))
+        _lib.check(self.lib.svb_scan_batch_v2(self._h, _ptr(bgr), n, h, w, _ptr(out["digits"]), _ptr(out["conf"]),
+                                              _ptr(out["alt_digits"]), _ptr(out["alt_conf"]), _ptr(out["logits"]),
+                                              _ptr(out["corners"]), _ptr(out["found"]), _ptr(out["info"]), self._stream()),
+                   "svb_scan_batch_v2")
+        return out
+
     def scan_batch_host(self, frames: np.ndarray, out: dict | None = None) -> dict:
         """Same through HOST buffers (numpy or pinned torch CPU tensors): H2D + path + D2H, synchronous."""
         torch = _torch()

@@ -217,3 +217,52 @@ def test_dropin_module_matches_reference_golden(v2pre):
         P.apply_clahe(g, clip_limit=3.0)
     with pytest.raises(NotImplementedError):
         P.threshold_sauvola(g, window_size=15)
+
+
+def test_scan_batch_v2_whole_path(scanner, oracle):
+    """svb_scan_batch_v2 = run_v2.py's CV + ML sections (--no-quality-check, detection method 1): every stage against
+    the oracle's composition on seeded frames; logits within 1e-3, digits / top-3 order identical."""
+    import os
+    import sys
+
+    import torch
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "helpers"))
+    from v3_weights import make_v3_state
+
+    from oracle import model_v3_oracle as M
+    from oracle import oracle_v2
+    from svb200 import frames as F
+
+    sd = make_v3_state()
+    scanner.load_weights_v3(sd)
+    imgs, _, _ = F.make_frames(3, 544, 960, base_seed=808)
+    blank = np.full((1, 544, 960, 3), 127, np.uint8)
+    batch = np.concatenate([imgs, blank])
+    out = scanner.scan_batch_v2(_t(batch), want_logits=True)
+    torch.cuda.synchronize()
+    n_found = 0
+    for i in range(len(batch)):
+        r = oracle.preprocess_multi(batch[i])
+        info = _np(out["info"])[i]
+        assert scanner.V2_METHODS[int(info[2])] == r["method_used"]
+        c = oracle_v2.detect_grid_contour(r["binary"])
+        assert bool(_np(out["found"])[i] == 1) == (c is not None)
+        if c is None:
+            assert not _np(out["digits"])[i].any() and not _np(out["conf"])[i].any()
+            continue
+        n_found += 1
+        assert np.array_equal(_np(out["corners"])[i].astype(np.float32), c)
+        board = oracle.warp_perspective(batch[i], c.astype(np.int32))
+        x = (oracle.cell_prep(oracle.extract_cells(board)).astype(np.float32) / 255.0 - 0.5) / 0.5
+        want = M.forward(sd, x.reshape(81, 1, 28, 28))
+        got = _np(out["logits"])[i]
+        assert np.abs(got - want).max() < 1e-3
+        probs = torch.softmax(torch.from_numpy(want), 1)
+        tp, ti = probs.topk(3)
+        margin_ok = (tp[:, :-1] - tp[:, 1:]).min(1).values.numpy() > 1e-4  # compare order only where it is not a near-tie
+        got_idx = np.concatenate([_np(out["digits"])[i][:, None], _np(out["alt_digits"])[i]], 1)
+        got_p = np.concatenate([_np(out["conf"])[i][:, None], _np(out["alt_conf"])[i]], 1)
+        assert np.array_equal(got_idx[margin_ok], ti.numpy()[margin_ok].astype(np.uint8))
+        assert np.abs(got_p - tp.numpy()).max() < 1e-4
+    assert n_found >= 2
