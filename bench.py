@@ -142,6 +142,47 @@ def run_reference(args, rank: int):
     print(json.dumps(line), flush=True)
 
 
+def other_configs(sc, dev) -> dict:
+    """Bounded device-timed runs of the other BASELINE configs (parity is covered in tests/): classifier-only cells/s
+    (configs[2]) and the v2 path preprocess_multi -> contour+validity -> cells -> DigitCNNv3 -> top-3 (configs[3]) at
+    1080p and 4K.  DigitCNNv3 has no shipped weights: seeded random init, as run_v2.py itself falls back to."""
+    import numpy as np
+    import torch
+    from svb200 import frames as F
+    from svb200.v3_init import random_v3_state
+
+    def timed(fn, iters):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    out = {}
+    sc.load_weights_v3(random_v3_state())
+    g = torch.Generator(device=dev).manual_seed(5)
+    for name, n_cells, fwd in (("digitcnn_tc", 262144, sc.digitcnn_forward), ("digitcnn_v3_fp32", 32768, sc.digitcnn_v3_forward)):
+        x = torch.where(torch.rand((n_cells, 1, 28, 28), device=dev, generator=g) < 0.25, 1.0, -1.0)
+        ms = timed(lambda: fwd(x), 3)
+        out["classifier_only_" + name] = {"cells": n_cells, "ms": round(ms, 3), "cells_per_s": n_cells / (ms * 1e-3)}
+        del x
+    for tag, (hh, ww, n) in {"1080p": (1080, 1920, 64), "4k": (2160, 3840, 16)}.items():
+        clean = torch.from_numpy(np.stack([F.make_frame(41000 + i, hh, ww).image for i in range(2)])).to(dev)
+        batch = F.noisy_batch_device(clean, n, seed=11)
+        ms_pre = timed(lambda: sc.preprocess_multi(batch, want_aux=False), 2)
+        ms_all = timed(lambda: sc.scan_batch_v2(batch), 2)
+        r = sc.scan_batch_v2(batch)
+        out["v2_path_" + tag] = {"frames": n, "frame": [hh, ww, 3], "ms": round(ms_all, 3), "frames_per_s": n / (ms_all * 1e-3),
+                                 "preprocess_multi_ms": round(ms_pre, 3), "grids_found": int((r["found"] == 1).sum().item())}
+        del batch, clean, r
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,6 +194,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the bounded BASELINE configs[2..3] side measurements")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -248,6 +290,11 @@ def main():
         boards = gather_boards(out["digits"], Fn * world)
         assert boards.shape == (Fn * world, 81)
 
+    # ---- side measurements of BASELINE configs[2] and [3] (bounded; N = 1 only; not the headline) --------------
+    other = None
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        other = other_configs(sc, dev)
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         cpu = cpu_leg(batch[:16].cpu().numpy(), args.cpu_seconds, "pool")
@@ -276,7 +323,7 @@ def main():
                          "traffic_source": "ncu --set full capture, profiles/r1_prof_k1c_raw.csv, scaled per frame",
                          "peak_source": how,
                          "algorithmic_bytes_per_launch": K1_BYTES_PER_FRAME * Fn, "launch_ms": k1_ms},
-            "cpu_baseline": cpu, "clocks": clocks,
+            "cpu_baseline": cpu, "clocks": clocks, "other_configs": other,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -217,15 +217,26 @@ static const int V3_COUNTS[V3_NT] = {
     10 * 128, 10};
 static int v3_count(int i) { return V3_COUNTS[i]; }
 
+// tensor-core path (digitcnn_v3_tc.cu)
+int launch_conv3x3_tc(svb_ctx *, const float *, const uint8_t *, const float *, float *, int, int, int, int, int, int, cudaStream_t);
+int pack_conv3x3_tc(svb_ctx *, const float *, uint8_t *, int, int, cudaStream_t);
+
+// the ten 3x3 convolutions of the residual blocks: index of the weight tensor in p[], cin, cout
+static const int V3_TC_CONV[10][3] = {{2, 32, 32}, {4, 32, 32}, {8, 32, 64}, {10, 64, 64}, {16, 64, 64}, {18, 64, 64},
+                                      {22, 64, 128}, {24, 128, 128}, {30, 128, 128}, {32, 128, 128}};
+
 struct V3State {
     float *blob = nullptr;
     const float *p[V3_NT] = {};
+    uint8_t *tc_blob = nullptr;          // prepacked fp16 hi/lo weight slices of the ten block convolutions
+    const uint8_t *tc_img[V3_NT] = {};   // indexed by the weight tensor's index in p[]
 };
 
 void digitcnn_v3_free(svb_ctx *ctx) {
     V3State *s = reinterpret_cast<V3State *>(ctx->cnn_v3);
     if (!s) return;
     if (s->blob) cudaFree(s->blob);
+    if (s->tc_blob) cudaFree(s->tc_blob);
     delete s;
     ctx->cnn_v3 = nullptr;
 }
@@ -238,6 +249,9 @@ int digitcnn_v3_load(svb_ctx *ctx, const float *const *tensors, int count, cudaS
     if (!s) {
         s = new V3State();
         SVB_CUDA_OK(cudaMalloc(&s->blob, total * sizeof(float)));
+        size_t tc_total = 0;
+        for (auto &c : V3_TC_CONV) tc_total += (size_t)36 * c[1] * c[2];
+        SVB_CUDA_OK(cudaMalloc(&s->tc_blob, tc_total));
         ctx->cnn_v3 = s;
     }
     size_t off = 0;
@@ -246,6 +260,13 @@ int digitcnn_v3_load(svb_ctx *ctx, const float *const *tensors, int count, cudaS
         SVB_CUDA_OK(cudaMemcpyAsync(s->blob + off, tensors[i], sizeof(float) * v3_count(i), cudaMemcpyDeviceToDevice, st));
         s->p[i] = s->blob + off;
         off += ((size_t)v3_count(i) + 3) & ~(size_t)3;
+    }
+    size_t tc_off = 0;
+    for (auto &c : V3_TC_CONV) {
+        int rc = pack_conv3x3_tc(ctx, s->p[c[0]], s->tc_blob + tc_off, c[1], c[2], st);
+        if (rc) return rc;
+        s->tc_img[c[0]] = s->tc_blob + tc_off;
+        tc_off += (size_t)36 * c[1] * c[2];
     }
     return SVB_OK;
 }
@@ -263,7 +284,13 @@ int launch_digitcnn_v3(svb_ctx *ctx, const float *x, long long n, float *logits,
     SVB_CUDA_OK(cudaFuncSetAttribute(conv3x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     SVB_CUDA_OK(cudaFuncSetAttribute(conv3x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     int rc = SVB_OK;
+    const bool use_tc = ctx->classifier_mode == 0;
     auto conv = [&](const float *in, int wi, float *out, int cin, int cout, int hin, int stride, int relu, int m) {
+        if (use_tc && s->tc_img[wi]) {  // block convolutions: tcgen05 implicit GEMM (the 1-channel stem stays on the CUDA cores)
+            const int r = launch_conv3x3_tc(ctx, in, s->tc_img[wi], s->p[wi + 1], out, cin, cout, hin, stride, relu, m, st);
+            if (!rc) rc = r;
+            return;
+        }
         const size_t smem = ((size_t)cin * (hin + 2) * (hin + 2) + (size_t)cin * 9 * COG) * sizeof(float);
         dim3 grid((unsigned)m, cout / COG);
         if (stride == 1) conv3x3_kernel<1><<<grid, NT, smem, st>>>(in, s->p[wi], s->p[wi + 1], out, cin, cout, hin, relu);

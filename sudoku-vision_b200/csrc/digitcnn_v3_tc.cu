@@ -1,0 +1,313 @@
+// digitcnn_v3_tc.cu — K6 on the 5th-generation tensor cores: the ten 3x3 convolutions of DigitCNNv3's residual blocks
+// (ml/model_v3.py:40-77, 95-161; 99.7 % of the network's 66 M MACs per cell) as implicit-GEMM tcgen05.mma kernels with
+// fp32 accumulators in TMEM.  Same interface as k6::conv3x3_kernel (fp32 NCHW activations in, conv + folded-BN bias
+// [+ ReLU] out), so the rest of the forward pass (stem, SE gate, residual combine, head: digitcnn_v3.cu) is unchanged
+// and the fp32 CUDA-core kernel stays as the on-device cross-check (svb_set_classifier_mode).
+//
+// Precision: as in digitcnn_tc.cu, every operand is split x = hi + lo (two fp16 numbers) and each product is issued as
+// three MMAs (hi hi + hi lo + lo hi) into the same accumulator — fp32-grade results (logits within 1e-3).
+//
+// Implicit GEMM without im2col.  A pass handles G cells (1 / 2 / 4 for 28^2 / 14^2 / 7^2 inputs).  Their activations
+// are converted to fp16 hi/lo and laid out in shared memory as a zero-haloed grid of width GW (32 / 16 / 8, at least
+// one zero column), flattened to rows r = cell*(H+1)*GW + (y+1)*GW + x + 8, K-chunk-major: element (r, c) at
+// (c/8)*ROWS*16 + r*16 + (c%8)*2.  That is the UMMA canonical K-major no-swizzle layout with SBO = 128 B (8-row groups
+// contiguous) and LBO = ROWS*16 (between the K chunks), so rows are a plain 16-byte-pitch array and the operand of tap
+// (dy, dx) for output rows m0..m0+127 is the SAME buffer viewed at start address + ((1+dy)*GW + dx + m0)*16: nine
+// descriptors, no copies.  Stride-2 convolutions are evaluated at stride 1 and subsampled in the epilogue.
+// Weights are prepacked (hi/lo, canonical layout) in slices of one tap x 64 input channels and streamed through a
+// cp.async double buffer while the previous slice's MMAs run; the epilogue reads TMEM with tcgen05.ld, adds the bias,
+// applies ReLU and writes fp32 NCHW.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace svb {
+namespace k6tc {
+
+constexpr int NT = 512;
+constexpr int OFF = 8;  // zero rows before the first grid row
+
+// ---- PTX helpers (same conventions as digitcnn_tc.cu) ----------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "V3_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra V3_DONE;\n"
+        "bra V3_WAIT;\n"
+        "V3_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: LBO = byte step between the K chunks (8 elements = 16 B) of one
+// MMA, SBO = byte step between 8-row groups
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor: D = f32, A = B = f16, both K-major, N at [17,23), M at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void split_hi_lo(float v, __half &hi, __half &lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+
+// ---- compile-time geometry of one layer shape ---------------------------------------------------------------------------
+template <int CIN, int COUT, int H>
+struct Geo {
+    static constexpr int GW = (H == 28) ? 32 : (H == 14 ? 16 : 8);  // grid width (>= H + 1)
+    static constexpr int G = (H == 28) ? 1 : (H == 14 ? 2 : 4);     // cells per pass
+    static constexpr int CB = (H + 1) * GW;                         // rows per cell block (bottom halo shared with the next top halo)
+    static constexpr int MROWS = (G - 1) * CB + (H - 1) * GW + H;   // output rows that can be valid
+    static constexpr int MT = (MROWS + 127) / 128;                  // M tiles of 128 rows
+    static constexpr int ROWS = (MT * 128 + 2 * GW + 1 + OFF + 7) & ~7;  // rows of the activation buffer
+    static constexpr int NKC = CIN / 8;                             // K chunks
+    static constexpr int PARTB = NKC * ROWS * 16;                   // bytes of one fp16 part of the activations
+    static constexpr int KS = CIN < 64 ? CIN : 64;                  // K of one weight slice
+    static constexpr int NSLICE = 9 * (CIN / KS);
+    static constexpr int SLB = COUT * KS * 2;                       // bytes of one part of one weight slice
+    static constexpr int TCOLS = MT * COUT;                         // TMEM columns used
+    static constexpr int TALLOC = TCOLS <= 32 ? 32 : (TCOLS <= 64 ? 64 : (TCOLS <= 128 ? 128 : (TCOLS <= 256 ? 256 : 512)));
+    static constexpr size_t SMEM = 1024 + 2 * (size_t)PARTB + 2 * 2 * (size_t)SLB + COUT * 4 + 64;
+    static_assert(TCOLS <= 512, "accumulators exceed TMEM");
+    static_assert(H < GW, "grid needs a zero column");
+};
+
+// in: fp32 [n][CIN][H][H]; out: fp32 [n][COUT][HO][HO], HO = (H-1)/STRIDE + 1; wimg: prepacked weight slices
+template <int CIN, int COUT, int H, int STRIDE>
+__global__ void __launch_bounds__(NT, 1)
+conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg, const float *__restrict__ bias,
+                  float *__restrict__ out, int n_cells, int relu) {
+    using GEO = Geo<CIN, COUT, H>;
+    constexpr int GW = GEO::GW, G = GEO::G, CB = GEO::CB, MT = GEO::MT, ROWS = GEO::ROWS, NKC = GEO::NKC, PARTB = GEO::PARTB;
+    constexpr int KS = GEO::KS, NSLICE = GEO::NSLICE, SLB = GEO::SLB, HH = H * H, HO = (H - 1) / STRIDE + 1;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = base;                              // [2 parts][NKC][ROWS][8 fp16]
+    uint8_t *sB = sA + 2 * (size_t)PARTB;            // [2 buffers][2 parts][SLB]
+    float *s_bias = (float *)(sB + 4 * (size_t)SLB);
+    unsigned long long *mbar = (unsigned long long *)(s_bias + COUT);
+    uint32_t *s_tmem = (uint32_t *)(mbar + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    for (int i = tid; i < 2 * PARTB / 16; i += NT) reinterpret_cast<uint4 *>(sA)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < COUT; i += NT) s_bias[i] = bias[i];
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(s_tmem, GEO::TALLOC);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t idesc = make_idesc(128, COUT);
+    const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+    uint32_t ph[2] = {0, 0};
+
+    auto load_slice = [&](int s, int buf) {  // one weight slice (both parts) -> sB[buf]
+        const uint4 *src = reinterpret_cast<const uint4 *>(wimg + (size_t)s * 2 * SLB);
+        uint4 *dst = reinterpret_cast<uint4 *>(sB + (size_t)buf * 2 * SLB);
+        for (int i = tid; i < 2 * SLB / 16; i += NT) cp_async16(dst + i, src + i);
+        cp_async_commit();
+    };
+
+    const int n_pass = (n_cells + G - 1) / G;
+    for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
+        const int c0 = pass * G;
+        load_slice(0, 0);
+        // activations of the pass: fp32 -> fp16 hi/lo, 8 channels (one 16-byte K chunk) of one pixel per item
+        for (int it = tid; it < G * NKC * HH; it += NT) {
+            const int p = it % HH, kc = (it / HH) % NKC, j = it / (HH * NKC);
+            const int cell = c0 + j;
+            if (cell >= n_cells) continue;
+            const float *src = in + ((size_t)cell * CIN + kc * 8) * HH + p;
+            __half hi[8], lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split_hi_lo(__ldg(src + (size_t)e * HH), hi[e], lo[e]);
+            const int y = p / H, x = p - y * H;
+            const int row = j * CB + (y + 1) * GW + x + OFF;
+            const size_t o = (size_t)kc * ROWS * 16 + (size_t)row * 16;
+            *reinterpret_cast<uint4 *>(sA + o) = *reinterpret_cast<const uint4 *>(hi);
+            *reinterpret_cast<uint4 *>(sA + PARTB + o) = *reinterpret_cast<const uint4 *>(lo);
+        }
+        for (int s = 0; s < NSLICE; ++s) {
+            const int st = s & 1;
+            if (s + 1 < NSLICE) {
+                if (s >= 1) {  // buffer st^1 was last read by the MMAs of slice s-1
+                    mbar_wait(&mbar[st ^ 1], ph[st ^ 1]);
+                    ph[st ^ 1] ^= 1;
+                }
+                load_slice(s + 1, st ^ 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            fence_proxy_async();
+            __syncthreads();
+            if (warp == 0) {
+                if (lane == 0) {
+                    tc_fence_after();
+                    const int t = s / (CIN / KS), kb = s % (CIN / KS);
+                    const int dy = t / 3 - 1, dx = t % 3 - 1;
+                    const uint32_t row0 = (uint32_t)((1 + dy) * GW + dx + OFF);
+#pragma unroll 1
+                    for (int tile = 0; tile < MT; ++tile) {
+#pragma unroll
+                        for (int combo = 0; combo < 3; ++combo) {
+                            const int pa = (combo == 2) ? 1 : 0, pb = (combo == 1) ? 1 : 0;  // hi*hi, hi*lo, lo*hi
+#pragma unroll
+                            for (int ks = 0; ks < KS / 16; ++ks) {
+                                const uint32_t a_addr = a_base + (uint32_t)(pa * PARTB) + (uint32_t)((kb * (KS / 8) + ks * 2) * ROWS * 16) +
+                                                        (uint32_t)(tile * 128 + row0) * 16u;
+                                const uint32_t b_addr = b_base + (uint32_t)(st * 2 * SLB + pb * SLB + ks * 256);
+                                umma_f16(tmem + (uint32_t)(tile * COUT), make_desc(a_addr, ROWS * 16, 128),
+                                         make_desc(b_addr, 128, (KS / 8) * 128), idesc, (s | combo | ks) ? 1u : 0u);
+                            }
+                        }
+                    }
+                    umma_commit(&mbar[st]);
+                }
+                __syncwarp();
+            }
+        }
+        // drain: the commits of the last two slices are still pending
+        mbar_wait(&mbar[(NSLICE - 2) & 1], ph[(NSLICE - 2) & 1]);
+        ph[(NSLICE - 2) & 1] ^= 1;
+        mbar_wait(&mbar[(NSLICE - 1) & 1], ph[(NSLICE - 1) & 1]);
+        ph[(NSLICE - 1) & 1] ^= 1;
+        tc_fence_after();
+        // ---- epilogue: TMEM -> + bias -> [ReLU] -> fp32 NCHW (stride-2 layers keep the even rows / columns) -----------
+        {
+            const int q = warp & 3, grp = warp >> 2;  // TMEM lane quarter (hardware rule: warp % 4), work group
+            constexpr int NCB = COUT / 32;
+            for (int blk = grp; blk < MT * NCB; blk += NT / 128) {
+                const int tile = blk / NCB, cb = blk - tile * NCB;
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * COUT + cb * 32), v);
+                const int m = tile * 128 + q * 32 + lane;
+                const int j = m / CB, rem = m - j * CB, y = rem / GW, x = rem - y * GW;
+                const int cell = c0 + j;
+                bool ok = (j < G) && (cell < n_cells) && (y < H) && (x < H);
+                if (STRIDE == 2) ok = ok && !(y & 1) && !(x & 1);
+                if (ok) {
+                    float *dst = out + ((size_t)cell * COUT + cb * 32) * (HO * HO) + (y / STRIDE) * HO + (x / STRIDE);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        float f = __uint_as_float(v[c]) + s_bias[cb * 32 + c];
+                        if (relu) f = fmaxf(f, 0.f);
+                        dst[(size_t)c * (HO * HO)] = f;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();  // TMEM and the activation buffer are free for the next pass
+        tc_fence_after();
+    }
+    if (warp == 0) tmem_dealloc(tmem, GEO::TALLOC);
+}
+
+// weights: folded conv weight w[COUT][CIN][3][3] -> slices s = tap * (CIN/KS) + kblock, each [part][canonical (n, kk)]:
+// element (n, kk) of a part at (n/8)*(KS/8*128) + (kk/8)*128 + (n%8)*16 + (kk%8)*2
+__global__ void pack_v3_kernel(const float *__restrict__ w, uint8_t *__restrict__ img, int cin, int cout) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cout * cin * 9) return;
+    const int t = i % 9, ci = (i / 9) % cin, n = i / (9 * cin);
+    const int ks = cin < 64 ? cin : 64, kb = ci / ks, kk = ci % ks;
+    const int s = t * (cin / ks) + kb;
+    const size_t slb = (size_t)cout * ks * 2;
+    const size_t off = (size_t)(n >> 3) * (ks / 8 * 128) + (size_t)(kk >> 3) * 128 + (n & 7) * 16 + (kk & 7) * 2;
+    __half hi, lo;
+    split_hi_lo(w[i], hi, lo);
+    *reinterpret_cast<__half *>(img + (size_t)s * 2 * slb + off) = hi;
+    *reinterpret_cast<__half *>(img + (size_t)s * 2 * slb + slb + off) = lo;
+}
+
+template <int CIN, int COUT, int H, int STRIDE>
+static int launch_one(svb_ctx *ctx, const float *in, const uint8_t *wimg, const float *bias, float *out, int n, int relu,
+                      cudaStream_t st) {
+    using GEO = Geo<CIN, COUT, H>;
+    auto kern = conv3x3_tc_kernel<CIN, COUT, H, STRIDE>;
+    SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEO::SMEM));
+    const int n_pass = (n + GEO::G - 1) / GEO::G;
+    const int grid = n_pass < ctx->sm_count ? n_pass : ctx->sm_count;
+    kern<<<grid, NT, GEO::SMEM, st>>>(in, wimg, bias, out, n, relu);
+    return check_launch(ctx, "k6tc::conv3x3_tc_kernel");
+}
+
+}  // namespace k6tc
+
+// dispatch on the five layer shapes DigitCNNv3 has (ml/model_v3.py:113-150); anything else -> SVB_ERR_UNSUPPORTED
+int launch_conv3x3_tc(svb_ctx *ctx, const float *in, const uint8_t *wimg, const float *bias, float *out, int cin, int cout,
+                      int hin, int stride, int relu, int n, cudaStream_t st) {
+    using namespace k6tc;
+    if (cin == 32 && cout == 32 && hin == 28 && stride == 1) return launch_one<32, 32, 28, 1>(ctx, in, wimg, bias, out, n, relu, st);
+    if (cin == 32 && cout == 64 && hin == 28 && stride == 2) return launch_one<32, 64, 28, 2>(ctx, in, wimg, bias, out, n, relu, st);
+    if (cin == 64 && cout == 64 && hin == 14 && stride == 1) return launch_one<64, 64, 14, 1>(ctx, in, wimg, bias, out, n, relu, st);
+    if (cin == 64 && cout == 128 && hin == 14 && stride == 2) return launch_one<64, 128, 14, 2>(ctx, in, wimg, bias, out, n, relu, st);
+    if (cin == 128 && cout == 128 && hin == 7 && stride == 1) return launch_one<128, 128, 7, 1>(ctx, in, wimg, bias, out, n, relu, st);
+    set_error("conv3x3_tc: no tensor-core kernel for cin=%d cout=%d h=%d stride=%d", cin, cout, hin, stride);
+    return SVB_ERR_UNSUPPORTED;
+}
+
+int pack_conv3x3_tc(svb_ctx *ctx, const float *w, uint8_t *img, int cin, int cout, cudaStream_t st) {
+    const int tot = cout * cin * 9;
+    k6tc::pack_v3_kernel<<<(tot + 255) / 256, 256, 0, st>>>(w, img, cin, cout);
+    return check_launch(ctx, "k6tc::pack_v3_kernel");
+}
+
+}  // namespace svb

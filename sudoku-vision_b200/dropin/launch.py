@@ -52,6 +52,14 @@ def seed_modules() -> None:
     sys.modules["grid"] = importlib.import_module("cv.grid")
     sys.modules["extract"] = importlib.import_module("cv.extract")
     sys.modules["model"] = ml_model
+    # v2 front ends (pipeline/run_v2.py:37-39, cv/grid_v2.py:534): preprocessing, detection method 1 and the classifier
+    # run on the GPU; cv/grid_quality.py is not built and stays the reference's own module
+    sys.modules["preprocess_v2"] = importlib.import_module("cv.preprocess_v2")
+    sys.modules["grid_v2"] = importlib.import_module("cv.grid_v2")
+    try:
+        sys.modules["model_v3"] = importlib.import_module("ml.model_v3")
+    except ImportError:
+        sys.modules["model_v3"] = importlib.import_module("model_v3")
     sys.modules["cv"] = cv_pkg
 
 
