@@ -70,31 +70,60 @@ conv3x3_kernel(const float *__restrict__ in, const float *__restrict__ w, const 
     }
 }
 
-// 1x1 convolution, stride 2, no padding (+ folded BN): out[n][co][y][x] = b[co] + sum_ci w[co][ci] * in[n][ci][2y][2x]
-__global__ void conv1x1s2_kernel(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ bias,
-                                 float *__restrict__ out, int cin, int cout, int hin, long long total) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int hout = (hin - 1) / 2 + 1;
-    const int x = (int)(i % hout), y = (int)((i / hout) % hout), co = (int)((i / (hout * hout)) % cout);
-    const long long n = i / ((long long)hout * hout * cout);
-    const float *src = in + (n * cin * hin + 2 * y) * hin + 2 * x;
-    float acc = bias[co];
-    for (int ci = 0; ci < cin; ++ci) acc = fmaf(w[co * cin + ci], src[(long long)ci * hin * hin], acc);
-    out[i] = acc;
+// 1x1 convolution, stride 2, no padding (+ folded BN): out[n][co][y][x] = b[co] + sum_ci w[co][ci] * in[n][ci][2y][2x].
+// One CTA per cell: the subsampled input [cin][hout^2] and the transposed weights [cin][cout] sit in shared memory;
+// every thread produces 4 output channels of one pixel per step.
+__global__ void __launch_bounds__(256)
+conv1x1s2_kernel(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ bias,
+                 float *__restrict__ out, int cin, int cout, int hin) {
+    extern __shared__ float smem[];
+    const int hout = (hin - 1) / 2 + 1, hw = hout * hout;
+    float *s_in = smem;             // [cin][hw]
+    float *s_w = smem + cin * hw;   // [cin][cout]
+    const int cell = blockIdx.x, tid = threadIdx.x;
+    const float *src = in + (long long)cell * cin * hin * hin;
+    for (int i = tid; i < cin * hw; i += 256) {
+        const int ci = i / hw, p = i - ci * hw, y = p / hout, x = p - y * hout;
+        s_in[i] = src[(ci * hin + 2 * y) * hin + 2 * x];
+    }
+    for (int i = tid; i < cin * cout; i += 256) {
+        const int co = i / cin, ci = i - co * cin;
+        s_w[ci * cout + co] = w[i];
+    }
+    __syncthreads();
+    float *dst = out + (long long)cell * cout * hw;
+    for (int o = tid; o < (cout / 4) * hw; o += 256) {
+        const int cg = o / hw, p = o - cg * hw;
+        float4 acc = *reinterpret_cast<const float4 *>(bias + cg * 4);
+        for (int ci = 0; ci < cin; ++ci) {
+            const float v = s_in[ci * hw + p];
+            const float4 ww = *reinterpret_cast<const float4 *>(s_w + ci * cout + cg * 4);
+            acc.x = fmaf(ww.x, v, acc.x);
+            acc.y = fmaf(ww.y, v, acc.y);
+            acc.z = fmaf(ww.z, v, acc.z);
+            acc.w = fmaf(ww.w, v, acc.w);
+        }
+        dst[(cg * 4 + 0) * hw + p] = acc.x;
+        dst[(cg * 4 + 1) * hw + p] = acc.y;
+        dst[(cg * 4 + 2) * hw + p] = acc.z;
+        dst[(cg * 4 + 3) * hw + p] = acc.w;
+    }
 }
 
-// squeeze-excite gate per cell: gate[c] = sigmoid(W2 relu(W1 mean_hw(x)))   (ml/model_v3.py:20-37)
-__global__ void __launch_bounds__(128)
+// squeeze-excite gate per cell: gate[c] = sigmoid(W2 relu(W1 mean_hw(x)))   (ml/model_v3.py:20-37).
+// One warp per channel for the spatial mean (coalesced reads, shuffle reduction in a fixed order).
+__global__ void __launch_bounds__(256)
 se_kernel(const float *__restrict__ x, const float *__restrict__ w1, const float *__restrict__ w2, float *__restrict__ gate, int c,
           int hw) {
     __shared__ float mean[128], hid[32];
-    const int cell = blockIdx.x, tid = threadIdx.x;
+    const int cell = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float *src = x + (long long)cell * c * hw;
-    for (int ch = tid; ch < c; ch += 128) {
+    for (int ch = warp; ch < c; ch += 8) {
         float s = 0.f;
-        for (int i = 0; i < hw; ++i) s += src[(long long)ch * hw + i];
-        mean[ch] = s / (float)hw;
+        for (int i = lane; i < hw; i += 32) s += src[(long long)ch * hw + i];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (lane == 0) mean[ch] = s / (float)hw;
     }
     __syncthreads();
     const int cr = c / 4;
@@ -104,7 +133,7 @@ se_kernel(const float *__restrict__ x, const float *__restrict__ w1, const float
         hid[tid] = fmaxf(s, 0.f);
     }
     __syncthreads();
-    for (int ch = tid; ch < c; ch += 128) {
+    for (int ch = tid; ch < c; ch += 256) {
         float s = 0.f;
         for (int k = 0; k < cr; ++k) s = fmaf(w2[ch * cr + k], hid[k], s);
         gate[(long long)cell * c + ch] = 1.0f / (1.0f + expf(-s));
@@ -302,12 +331,12 @@ int launch_digitcnn_v3(svb_ctx *ctx, const float *x, long long n, float *logits,
         const int hout = (hin - 1) / stride + 1, hw = hout * hout;
         conv(X, wi, T1, cin, cout, hin, stride, 1, m);           // conv1 + bn1 + relu
         conv(T1, wi + 2, T2, cout, cout, hout, 1, 0, m);         // conv2 + bn2
-        se_kernel<<<(unsigned)m, 128, 0, st>>>(T2, s->p[wi + 4], s->p[wi + 5], gate, cout, hw);
+        se_kernel<<<(unsigned)m, 256, 0, st>>>(T2, s->p[wi + 4], s->p[wi + 5], gate, cout, hw);
         if (!rc) rc = check_launch(ctx, "k6::se_kernel");
         const float *shortcut = X;
         if (sc_wi >= 0) {  // projection shortcut into T1 (conv1's output is no longer needed)
-            const long long tot = (long long)m * cout * hw;
-            conv1x1s2_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(X, s->p[sc_wi], s->p[sc_wi + 1], T1, cin, cout, hin, tot);
+            const size_t sm1 = ((size_t)cin * hw + (size_t)cin * cout) * sizeof(float);
+            conv1x1s2_kernel<<<(unsigned)m, 256, sm1, st>>>(X, s->p[sc_wi], s->p[sc_wi + 1], T1, cin, cout, hin);
             if (!rc) rc = check_launch(ctx, "k6::conv1x1s2_kernel");
             shortcut = T1;
         }

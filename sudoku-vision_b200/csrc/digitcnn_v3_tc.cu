@@ -120,7 +120,10 @@ struct Geo {
     static constexpr int SLB = COUT * KS * 2;                       // bytes of one part of one weight slice
     static constexpr int TCOLS = MT * COUT;                         // TMEM columns used
     static constexpr int TALLOC = TCOLS <= 32 ? 32 : (TCOLS <= 64 ? 64 : (TCOLS <= 128 ? 128 : (TCOLS <= 256 ? 256 : 512)));
-    static constexpr size_t SMEM = 1024 + 2 * (size_t)PARTB + 2 * 2 * (size_t)SLB + COUT * 4 + 64;
+    // small layers keep every weight slice resident in shared memory; the others stream them through two buffers
+    static constexpr bool RESIDENT = 2 * (size_t)PARTB + (size_t)NSLICE * 2 * SLB <= 200 * 1024;
+    static constexpr int NBUF = RESIDENT ? NSLICE : 2;
+    static constexpr size_t SMEM = 1024 + 2 * (size_t)PARTB + (size_t)NBUF * 2 * SLB + COUT * 4 + 64;
     static_assert(TCOLS <= 512, "accumulators exceed TMEM");
     static_assert(H < GW, "grid needs a zero column");
 };
@@ -136,8 +139,8 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = base;                              // [2 parts][NKC][ROWS][8 fp16]
-    uint8_t *sB = sA + 2 * (size_t)PARTB;            // [2 buffers][2 parts][SLB]
-    float *s_bias = (float *)(sB + 4 * (size_t)SLB);
+    uint8_t *sB = sA + 2 * (size_t)PARTB;            // [NBUF buffers][2 parts][SLB]
+    float *s_bias = (float *)(sB + (size_t)GEO::NBUF * 2 * SLB);
     unsigned long long *mbar = (unsigned long long *)(s_bias + COUT);
     uint32_t *s_tmem = (uint32_t *)(mbar + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -166,9 +169,34 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
     };
 
     const int n_pass = (n_cells + G - 1) / G;
+    if (GEO::RESIDENT) {  // all weight slices once
+        for (int s = 0; s < NSLICE; ++s) load_slice(s, s);
+        cp_async_wait<0>();
+    }
+    // the MMAs of one weight slice (one tap x KS input channels) for every M tile of the pass
+    auto issue_slice = [&](int s, int buf) {
+        const int t = s / (CIN / KS), kb = s % (CIN / KS);
+        const int dy = t / 3 - 1, dx = t % 3 - 1;
+        const uint32_t row0 = (uint32_t)((1 + dy) * GW + dx + OFF);
+#pragma unroll 1
+        for (int tile = 0; tile < MT; ++tile) {
+#pragma unroll
+            for (int combo = 0; combo < 3; ++combo) {
+                const int pa = (combo == 2) ? 1 : 0, pb = (combo == 1) ? 1 : 0;  // hi*hi, hi*lo, lo*hi
+#pragma unroll
+                for (int ks = 0; ks < KS / 16; ++ks) {
+                    const uint32_t a_addr = a_base + (uint32_t)(pa * PARTB) + (uint32_t)((kb * (KS / 8) + ks * 2) * ROWS * 16) +
+                                            (uint32_t)(tile * 128 + row0) * 16u;
+                    const uint32_t b_addr = b_base + (uint32_t)(buf * 2 * SLB + pb * SLB + ks * 256);
+                    umma_f16(tmem + (uint32_t)(tile * COUT), make_desc(a_addr, ROWS * 16, 128),
+                             make_desc(b_addr, 128, (KS / 8) * 128), idesc, (s | combo | ks) ? 1u : 0u);
+                }
+            }
+        }
+    };
     for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
         const int c0 = pass * G;
-        load_slice(0, 0);
+        if (!GEO::RESIDENT) load_slice(0, 0);
         // activations of the pass: fp32 -> fp16 hi/lo, 8 channels (one 16-byte K chunk) of one pixel per item
         for (int it = tid; it < G * NKC * HH; it += NT) {
             const int p = it % HH, kc = (it / HH) % NKC, j = it / (HH * NKC);
@@ -184,51 +212,50 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
             *reinterpret_cast<uint4 *>(sA + o) = *reinterpret_cast<const uint4 *>(hi);
             *reinterpret_cast<uint4 *>(sA + PARTB + o) = *reinterpret_cast<const uint4 *>(lo);
         }
-        for (int s = 0; s < NSLICE; ++s) {
-            const int st = s & 1;
-            if (s + 1 < NSLICE) {
-                if (s >= 1) {  // buffer st^1 was last read by the MMAs of slice s-1
-                    mbar_wait(&mbar[st ^ 1], ph[st ^ 1]);
-                    ph[st ^ 1] ^= 1;
-                }
-                load_slice(s + 1, st ^ 1);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
-            }
+        if (GEO::RESIDENT) {
             fence_proxy_async();
             __syncthreads();
             if (warp == 0) {
                 if (lane == 0) {
                     tc_fence_after();
-                    const int t = s / (CIN / KS), kb = s % (CIN / KS);
-                    const int dy = t / 3 - 1, dx = t % 3 - 1;
-                    const uint32_t row0 = (uint32_t)((1 + dy) * GW + dx + OFF);
 #pragma unroll 1
-                    for (int tile = 0; tile < MT; ++tile) {
-#pragma unroll
-                        for (int combo = 0; combo < 3; ++combo) {
-                            const int pa = (combo == 2) ? 1 : 0, pb = (combo == 1) ? 1 : 0;  // hi*hi, hi*lo, lo*hi
-#pragma unroll
-                            for (int ks = 0; ks < KS / 16; ++ks) {
-                                const uint32_t a_addr = a_base + (uint32_t)(pa * PARTB) + (uint32_t)((kb * (KS / 8) + ks * 2) * ROWS * 16) +
-                                                        (uint32_t)(tile * 128 + row0) * 16u;
-                                const uint32_t b_addr = b_base + (uint32_t)(st * 2 * SLB + pb * SLB + ks * 256);
-                                umma_f16(tmem + (uint32_t)(tile * COUT), make_desc(a_addr, ROWS * 16, 128),
-                                         make_desc(b_addr, 128, (KS / 8) * 128), idesc, (s | combo | ks) ? 1u : 0u);
-                            }
-                        }
-                    }
-                    umma_commit(&mbar[st]);
+                    for (int s = 0; s < NSLICE; ++s) issue_slice(s, s);
+                    umma_commit(&mbar[0]);
                 }
                 __syncwarp();
             }
+            mbar_wait(&mbar[0], ph[0]);
+            ph[0] ^= 1;
+        } else {
+            for (int s = 0; s < NSLICE; ++s) {
+                const int st = s & 1;
+                if (s + 1 < NSLICE) {
+                    if (s >= 1) {  // buffer st^1 was last read by the MMAs of slice s-1
+                        mbar_wait(&mbar[st ^ 1], ph[st ^ 1]);
+                        ph[st ^ 1] ^= 1;
+                    }
+                    load_slice(s + 1, st ^ 1);
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                fence_proxy_async();
+                __syncthreads();
+                if (warp == 0) {
+                    if (lane == 0) {
+                        tc_fence_after();
+                        issue_slice(s, st);
+                        umma_commit(&mbar[st]);
+                    }
+                    __syncwarp();
+                }
+            }
+            // drain: the commits of the last two slices are still pending
+            mbar_wait(&mbar[(NSLICE - 2) & 1], ph[(NSLICE - 2) & 1]);
+            ph[(NSLICE - 2) & 1] ^= 1;
+            mbar_wait(&mbar[(NSLICE - 1) & 1], ph[(NSLICE - 1) & 1]);
+            ph[(NSLICE - 1) & 1] ^= 1;
         }
-        // drain: the commits of the last two slices are still pending
-        mbar_wait(&mbar[(NSLICE - 2) & 1], ph[(NSLICE - 2) & 1]);
-        ph[(NSLICE - 2) & 1] ^= 1;
-        mbar_wait(&mbar[(NSLICE - 1) & 1], ph[(NSLICE - 1) & 1]);
-        ph[(NSLICE - 1) & 1] ^= 1;
         tc_fence_after();
         // ---- epilogue: TMEM -> + bias -> [ReLU] -> fp32 NCHW (stride-2 layers keep the even rows / columns) -----------
         {
