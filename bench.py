@@ -165,7 +165,7 @@ def other_configs(sc, dev) -> dict:
     out = {}
     sc.load_weights_v3(random_v3_state())
     g = torch.Generator(device=dev).manual_seed(5)
-    for name, n_cells, fwd in (("digitcnn_tc", 262144, sc.digitcnn_forward), ("digitcnn_v3_fp32", 32768, sc.digitcnn_v3_forward)):
+    for name, n_cells, fwd in (("digitcnn_tc", 262144, sc.digitcnn_forward), ("digitcnn_v3_tc", 32768, sc.digitcnn_v3_forward)):
         x = torch.where(torch.rand((n_cells, 1, 28, 28), device=dev, generator=g) < 0.25, 1.0, -1.0)
         ms = timed(lambda: fwd(x), 3)
         out["classifier_only_" + name] = {"cells": n_cells, "ms": round(ms, 3), "cells_per_s": n_cells / (ms * 1e-3)}

@@ -268,6 +268,45 @@ def test_digitcnn_v3_logits(scanner, golden):
     assert np.array_equal(pred.cpu().numpy(), g["ref_logits"].argmax(1))
 
 
+@pytest.mark.parametrize("n", [1, 3, 301, 2051])
+def test_digitcnn_v3_tensor_core_vs_fp32_and_oracle(scanner, n):
+    """K6 on tcgen05 (fp16 hi/lo split, digitcnn_v3_tc.cu) against the fp32 CUDA-core kernels (svb_set_classifier_mode)
+    and the CPU oracle: ragged cell counts (partial passes of 1 / 2 / 4 cells, more than one 2048-cell chunk)."""
+    import os
+    import sys
+
+    import torch
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "helpers"))
+    from v3_weights import make_v3_state
+
+    from oracle import model_v3_oracle as M
+
+    sd = make_v3_state(seed=4321)
+    scanner.load_weights_v3(sd)
+    rng = np.random.default_rng(n)
+    x = np.where(rng.random((n, 1, 28, 28)) < 0.3, 1.0, -1.0).astype(np.float32)
+    x[0] = rng.standard_normal((1, 28, 28))  # the drop-in accepts any float tensor, not only +-1
+    xd = torch.from_numpy(x).cuda()
+    try:
+        scanner.set_classifier_mode("fp32")
+        ref = scanner.digitcnn_v3_forward(xd).cpu().numpy()
+    finally:
+        scanner.set_classifier_mode("tc")
+    got, digits, conf = scanner.digitcnn_v3_forward(xd, want_digits=True)
+    got = got.cpu().numpy()
+    assert np.isfinite(got).all()
+    assert np.abs(got - ref).max() < LOGIT_TOL
+    m = min(n, 48)
+    want = M.forward(sd, x[:m])
+    assert np.abs(got[:m] - want).max() < LOGIT_TOL
+    top2 = np.sort(want, 1)
+    clear = (top2[:, -1] - top2[:, -2]) > 10 * LOGIT_TOL
+    assert np.array_equal(digits.cpu().numpy()[:m][clear], want.argmax(1).astype(np.uint8)[clear])
+    feats = scanner.digitcnn_v3_forward(xd[:m], want_features=True).cpu().numpy()
+    assert np.abs(feats - M.forward(sd, x[:m], return_features=True)).max() < LOGIT_TOL
+
+
 # ---- whole path -----------------------------------------------------------------------------------
 def test_scan_batch_vs_oracle(scanner, oracle, weights):
     imgs, digits_gt, _ = _frames(5, 1080, 1920, 8800)
