@@ -44,7 +44,7 @@ int launch_gray(svb_ctx *, const uint8_t *, int, int, int, uint8_t *, cudaStream
 int launch_blur5(svb_ctx *, const uint8_t *, int, int, int, uint8_t *, cudaStream_t);
 int launch_adaptive(svb_ctx *, const uint8_t *, int, int, int, int, uint8_t *, cudaStream_t);
 bool fused_preprocess_supported(int h, int w);
-int launch_fused_preprocess(svb_ctx *, const uint8_t *, int, int, int, uint8_t *, cudaStream_t);
+int launch_fused_preprocess(svb_ctx *, const uint8_t *, int, int, int, uint8_t *, cudaStream_t, int ch = 3);
 int launch_find_grid_contour(svb_ctx *, const uint8_t *, int, int, int, double, double, int32_t *, uint8_t *, cudaStream_t, int v2_mode = 0);
 int launch_warp_board(svb_ctx *, const uint8_t *, int, int, int, const int32_t *, const uint8_t *, int, uint8_t *, cudaStream_t);
 int launch_extract_cells(svb_ctx *, const uint8_t *, int, int, uint8_t *, cudaStream_t);

@@ -155,6 +155,7 @@ __device__ __forceinline__ float u8f(uint32_t word, int byte) { return (float)((
 // byte arithmetic through dp2a / dp4a, the vertical 5-tap over 8 shared hb rows, both 11-tap passes in
 // packed fma.rn.f32x2 (row pass pairs two image rows, column pass pairs two columns), the threshold in
 // 16-bit SIMD lanes, and no clamps (the caller guarantees rows r0-12 .. r0+3 are inside the image).
+template <int CH>
 __device__ __forceinline__ void fast_block(Smem &sm, const int q /* r0 >> 2 */, const int stage, const int t, const bool cols_inside,
                                            const bool edge_strip, const bool is_out, const int c0, const int w,
                                            const int xg0, const int col_lo, const int col_hi, const int t_left,
@@ -172,7 +173,21 @@ __device__ __forceinline__ void fast_block(Smem &sm, const int q /* r0 >> 2 */, 
     uint32_t gq[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        if (cols_inside) {
+        if (CH == 1) {  // gray input (the v2 tail: CLAHE output -> blur -> threshold): nothing to convert
+            if (cols_inside) {
+                gq[r] = *reinterpret_cast<const uint32_t *>(&sm.raw[stage][r][4 * t]);
+            } else {
+                uint32_t v = 0;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    const int c = c0 + j;
+                    int cc = (c < 0) ? -c : ((c >= w) ? 2 * (w - 1) - c : c);
+                    cc = clampi(cc, col_lo, col_hi - 1);
+                    v |= (uint32_t)sm.raw[stage][r][cc - xg0] << (8 * j);
+                }
+                gq[r] = v;
+            }
+        } else if (cols_inside) {
             const uint32_t *p = reinterpret_cast<const uint32_t *>(&sm.raw[stage][r][12 * t]);
             const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
             const uint32_t p1 = __funnelshift_r(w0, w1, 24), p2 = __funnelshift_r(w1, w2, 16), p3 = w2 >> 8;
@@ -313,7 +328,7 @@ __device__ __forceinline__ void fast_block(Smem &sm, const int q /* r0 >> 2 */, 
     }
 }
 
-template <bool INVERTED>
+template <bool INVERTED, int CH>
 __global__ void __launch_bounds__(NT, 4)
 fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ mask, int h, int w, int rows_per_seg) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -325,7 +340,7 @@ fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ m
     const int ys = blockIdx.y * rows_per_seg;  // output rows [ys, ye)
     const int ye = min(ys + rows_per_seg, h);
     const long long frame_px = (long long)h * w;
-    const uint8_t *frame = bgr + (long long)blockIdx.z * frame_px * 3;
+    const uint8_t *frame = bgr + (long long)blockIdx.z * frame_px * CH;
     uint8_t *out = mask + (long long)blockIdx.z * frame_px;
 
     const int bs = max(ys - 5, 0), be = min(ye + 5, h);  // blurred rows needed [bs, be)
@@ -334,8 +349,8 @@ fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ m
 
     // staged column range actually inside the image
     const int col_lo = max(xg0, 0), col_hi = min(xg0 + GW, w);
-    const uint32_t row_bytes = (uint32_t)(col_hi - col_lo) * 3u;
-    const int dst_off = (col_lo - xg0) * 3;
+    const uint32_t row_bytes = (uint32_t)(col_hi - col_lo) * (uint32_t)CH;
+    const int dst_off = (col_lo - xg0) * CH;
 
     if (t == 0) {
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&sm.full[s], 1);
@@ -350,7 +365,7 @@ fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ m
         const int nrows = min(R, ge - r0);
         mbar_expect_tx(&sm.full[stage], row_bytes * (uint32_t)nrows);
         for (int r = 0; r < nrows; ++r)
-            tma_load_1d(&sm.raw[stage][r][dst_off], frame + ((long long)(r0 + r) * w + col_lo) * 3, row_bytes,
+            tma_load_1d(&sm.raw[stage][r][dst_off], frame + ((long long)(r0 + r) * w + col_lo) * CH, row_bytes,
                         &sm.full[stage]);
     };
     if (t == 0) issue(0);
@@ -380,7 +395,7 @@ fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ m
         if (INVERTED && nrows == R && blk + 1 < nblocks && r0 >= 12 && b_next == r0 - 2 && y_next == r0 - 7 && r0 + 1 <= be - 1 &&
             r0 - 4 <= ye - 1 && r0 - 7 >= ys && r0 + 3 <= h - 1) {
             uint8_t *o0 = out + (long long)(r0 - 7) * w + c0;
-            fast_block(sm, r0 >> 2, stage, t, cols_inside, edge_strip, is_out, c0, w, xg0, col_lo, col_hi, t_left, t_right, o0);
+            fast_block<CH>(sm, r0 >> 2, stage, t, cols_inside, edge_strip, is_out, c0, w, xg0, col_lo, col_hi, t_left, t_right, o0);
             b_next = r0 + 2;
             y_next = r0 - 3;
             continue;
@@ -390,7 +405,20 @@ fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ m
         for (int r = 0; r < R; ++r) {
             if (r < nrows) {
                 uint32_t gq;
-                if (cols_inside) {
+                if (CH == 1) {
+                    if (cols_inside) {
+                        gq = *reinterpret_cast<const uint32_t *>(&sm.raw[stage][r][4 * t]);
+                    } else {
+                        gq = 0;
+#pragma unroll
+                        for (int j = 0; j < CPT; ++j) {
+                            int c = c0 + j;
+                            int cc = (c < 0) ? -c : ((c >= w) ? 2 * (w - 1) - c : c);
+                            cc = clampi(cc, col_lo, col_hi - 1);
+                            gq |= (uint32_t)sm.raw[stage][r][cc - xg0] << (8 * j);
+                        }
+                    }
+                } else if (cols_inside) {
                     const uint32_t *p = reinterpret_cast<const uint32_t *>(&sm.raw[stage][r][12 * t]);
                     uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
                     uint32_t g0 = gray_of(w0 & 0xff, (w0 >> 8) & 0xff, (w0 >> 16) & 0xff);
@@ -559,14 +587,12 @@ int launch_adaptive(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, int i
 
 bool fused_preprocess_supported(int h, int w) { return (w % 16 == 0) && w >= 64 && h >= 8; }
 
-int launch_fused_preprocess(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *mask, cudaStream_t st) {
+// ch = 3: BGR frames (cv/preprocess.py:57-65); ch = 1: gray input, i.e. GaussianBlur 5 + adaptive threshold only
+// (the tail of cv/preprocess_v2.py:233-239)
+int launch_fused_preprocess(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uint8_t *mask, cudaStream_t st, int ch) {
     using namespace k1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SVB_CUDA_OK(cudaFuncSetAttribute(fused_preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(Smem)));
-        attr_set = true;
-    }
+    SVB_CUDA_OK(cudaFuncSetAttribute(fused_preprocess_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    SVB_CUDA_OK(cudaFuncSetAttribute(fused_preprocess_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
     const int nstrips = (w + TW - 1) / TW;
     // enough CTAs to fill the machine ~4x over; segments no shorter than 64 rows (14-row warm-up)
     int want = (ctx->sm_count * 3 * 4 + nstrips * n - 1) / (nstrips * n);
@@ -574,7 +600,8 @@ int launch_fused_preprocess(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int 
     int rows_per_seg = (h + nseg - 1) / nseg;
     nseg = (h + rows_per_seg - 1) / rows_per_seg;
     dim3 grid(nstrips, nseg, n);
-    fused_preprocess_kernel<true><<<grid, NT, sizeof(Smem), st>>>(bgr, mask, h, w, rows_per_seg);
+    if (ch == 1) fused_preprocess_kernel<true, 1><<<grid, NT, sizeof(Smem), st>>>(src, mask, h, w, rows_per_seg);
+    else fused_preprocess_kernel<true, 3><<<grid, NT, sizeof(Smem), st>>>(src, mask, h, w, rows_per_seg);
     return check_launch(ctx, "fused_preprocess_kernel");
 }
 

@@ -751,6 +751,96 @@ __global__ void __launch_bounds__(clean::NT) cleanup_kernel(const u8 *__restrict
     }
 }
 
+// The same on 32-bit words (frame width a multiple of 4): binary pixels are 0x00 / 0xff bytes, so 3x3 / 2x2 dilation and
+// erosion are bitwise OR / AND of a word with its byte-shifted neighbours — four pixels per operation.
+namespace cleanw {
+constexpr int TH = 32, TWW = 64, NT = 256;     // tile: 32 rows x 64 words (256 px)
+constexpr int SH = TH + 6, SWW = TWW + 2;      // 4 rows above / 2 below, one halo word (4 px) on each side
+}
+template <int MODE>
+__global__ void __launch_bounds__(cleanw::NT) cleanup_words_kernel(const u8 *__restrict__ src, u8 *__restrict__ dst, int h, int w,
+                                                                   const u8 *__restrict__ info, u32 *__restrict__ counts, int slot) {
+    using namespace cleanw;
+    __shared__ u32 s_a[SH][SWW + 1];
+    __shared__ u32 s_b[SH][SWW + 1];
+    const int f = blockIdx.z, xw0 = blockIdx.x * TWW - 1, y0 = blockIdx.y * TH - 4, tid = threadIdx.x;
+    const int ww = w >> 2;
+    const u32 *img = (const u32 *)(src + (size_t)f * h * w);
+    const u32 level4 = MODE == 1 ? (u32)info[f * 4 + 3] * 0x01010101u : 0u;
+    auto inside = [&](int yy, int xx) { return (y0 + yy) >= 0 && (y0 + yy) < h && (xw0 + xx) >= 0 && (xw0 + xx) < ww; };
+    auto left = [](u32 l, u32 v) { return __funnelshift_r(l, v, 24); };    // pixel x-1 under every byte
+    auto right = [](u32 v, u32 r) { return __funnelshift_r(v, r, 8); };    // pixel x+1
+    // stage 0: source (outside -> 0, ignored by the dilate)
+    for (int i = tid; i < SH * SWW; i += NT) {
+        const int yy = i / SWW, xx = i - yy * SWW;
+        u32 v = 0;
+        if (inside(yy, xx)) {
+            v = img[(size_t)(y0 + yy) * ww + xw0 + xx];
+            if (MODE == 1) v = ~__vcmpgtu4(v, level4);  // THRESH_BINARY_INV: src > level ? 0 : 255
+        }
+        s_a[yy][xx] = v;
+    }
+    __syncthreads();
+    // stage 1: dilate 3x3 -> s_b; outside -> 0xff.. (ignored by the erode)
+    for (int i = tid; i < SH * SWW; i += NT) {
+        const int yy = i / SWW, xx = i - yy * SWW;
+        u32 v = 0xffffffffu;
+        if (yy >= 1 && yy < SH - 1 && inside(yy, xx)) {
+            v = 0;
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+                const u32 c = s_a[yy + dy][xx], l = xx > 0 ? s_a[yy + dy][xx - 1] : 0u, r = xx < SWW - 1 ? s_a[yy + dy][xx + 1] : 0u;
+                v |= c | left(l, c) | right(c, r);
+            }
+        }
+        s_b[yy][xx] = v;
+    }
+    __syncthreads();
+    // stage 2: erode 3x3 -> s_a; outside -> 0xff.. (ignored by the next erode)
+    for (int i = tid; i < SH * SWW; i += NT) {
+        const int yy = i / SWW, xx = i - yy * SWW;
+        u32 v = 0xffffffffu;
+        if (yy >= 2 && yy < SH - 2 && inside(yy, xx)) {
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+                const u32 c = s_b[yy + dy][xx], l = xx > 0 ? s_b[yy + dy][xx - 1] : 0xffffffffu,
+                          r = xx < SWW - 1 ? s_b[yy + dy][xx + 1] : 0xffffffffu;
+                v &= c & left(l, c) & right(c, r);
+            }
+        }
+        s_a[yy][xx] = v;
+    }
+    __syncthreads();
+    // stage 3: erode 2x2 (offsets -1, 0) -> s_b; outside -> 0 (ignored by the dilate)
+    for (int i = tid; i < SH * SWW; i += NT) {
+        const int yy = i / SWW, xx = i - yy * SWW;
+        u32 v = 0;
+        if (yy >= 3 && yy < SH - 2 && inside(yy, xx)) {
+            const u32 c = s_a[yy][xx], l = xx > 0 ? s_a[yy][xx - 1] : 0xffffffffu;
+            const u32 cu = s_a[yy - 1][xx], lu = xx > 0 ? s_a[yy - 1][xx - 1] : 0xffffffffu;
+            v = c & left(l, c) & cu & left(lu, cu);
+        }
+        s_b[yy][xx] = v;
+    }
+    __syncthreads();
+    // stage 4: dilate 2x2 -> output tile rows [4, 4 + TH), words [1, 1 + TWW)
+    int cnt = 0;
+    u32 *out = (u32 *)(dst + (size_t)f * h * w);
+    for (int i = tid; i < TH * TWW; i += NT) {
+        const int yy = i / TWW + 4, xx = (i % TWW) + 1;
+        if (inside(yy, xx)) {
+            const u32 c = s_b[yy][xx], l = s_b[yy][xx - 1], cu = s_b[yy - 1][xx], lu = s_b[yy - 1][xx - 1];
+            const u32 v = c | left(l, c) | cu | left(lu, cu);
+            out[(size_t)(y0 + yy) * ww + xw0 + xx] = v;
+            cnt += __popc(v & 0x01010101u);
+        }
+    }
+    if (counts) {
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if ((tid & 31) == 0 && cnt) atomicAdd(&counts[(size_t)f * CNT_STRIDE + slot], (u32)cnt);
+    }
+}
+
 // THRESH_BINARY_INV + THRESH_OTSU as an image (the stage-wise drop-in call threshold_otsu)
 __global__ void otsu_apply_kernel(const u8 *__restrict__ src, u8 *__restrict__ dst, int px, const u8 *__restrict__ info) {
     const int f = blockIdx.y;
@@ -965,6 +1055,12 @@ int launch_clahe8(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uint8_t
 
 int launch_cleanup(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uint8_t *dst, int otsu_mode, const uint8_t *info,
                    uint32_t *counts, int slot, cudaStream_t st) {
+    if ((w & 3) == 0 && ((((size_t)src) | ((size_t)dst)) & 3) == 0) {  // four pixels per operation
+        dim3 gw(((w >> 2) + cleanw::TWW - 1) / cleanw::TWW, (h + cleanw::TH - 1) / cleanw::TH, n);
+        if (otsu_mode) cleanup_words_kernel<1><<<gw, cleanw::NT, 0, st>>>(src, dst, h, w, info, counts, slot);
+        else cleanup_words_kernel<0><<<gw, cleanw::NT, 0, st>>>(src, dst, h, w, info, counts, slot);
+        return check_launch(ctx, "cleanup_words_kernel");
+    }
     dim3 grid((w + clean::TW - 1) / clean::TW, (h + clean::TH - 1) / clean::TH, n);
     if (otsu_mode) cleanup_kernel<1><<<grid, clean::NT, 0, st>>>(src, dst, h, w, info, counts, slot);
     else cleanup_kernel<0><<<grid, clean::NT, 0, st>>>(src, dst, h, w, info, counts, slot);
@@ -993,9 +1089,22 @@ int launch_sauvola(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uint8_
     return check_launch(ctx, "sauvola_kernel");
 }
 
-// launchers of the v1 stage kernels reused for the tail (preprocess.cu)
+// launchers of the v1 kernels reused for the tail (preprocess.cu)
 int launch_blur5(svb_ctx *, const uint8_t *, int, int, int, uint8_t *, cudaStream_t);
 int launch_adaptive(svb_ctx *, const uint8_t *, int, int, int, int, uint8_t *, cudaStream_t);
+bool fused_preprocess_supported(int h, int w);
+int launch_fused_preprocess(svb_ctx *, const uint8_t *, int, int, int, uint8_t *, cudaStream_t, int ch);
+
+// GaussianBlur(5,5) + adaptiveThreshold(GAUSSIAN_C, BINARY_INV, 11, 2) of a gray image (cv/preprocess_v2.py:233-236):
+// K1's fused row-streaming kernel in its gray-input form when the frame qualifies, else the two stage kernels.
+// `blurred_tmp` is only used by the stage-kernel path.
+static int blur_threshold(svb_ctx *ctx, const uint8_t *gray, int n, int h, int w, uint8_t *blurred_tmp, uint8_t *mask, cudaStream_t st) {
+    if (fused_preprocess_supported(h, w) && (((size_t)gray) & 15) == 0 && (((size_t)mask) & 3) == 0)
+        return launch_fused_preprocess(ctx, gray, n, h, w, mask, st, 1);
+    int rc = launch_blur5(ctx, gray, n, h, w, blurred_tmp, st);
+    if (rc) return rc;
+    return launch_adaptive(ctx, blurred_tmp, n, h, w, 1, mask, st);
+}
 
 static int illum_kernel_size(int h, int w) {  // cv/preprocess_v2.py:46-49
     int k = (h > w ? h : w) / 10;
@@ -1105,11 +1214,9 @@ int preprocess_v2_run(svb_ctx *ctx, const uint8_t *bgr, const uint8_t *gray_in, 
     if (rc) return rc;
     rc = launch_clahe8(ctx, enh, n, h, w, S.lut, a, st);
     if (rc) return rc;
-    rc = launch_blur5(ctx, a, n, h, w, b, st);
+    rc = blur_threshold(ctx, a, n, h, w, b, enh, st);  // enh is free again: CLAHE has consumed it
     if (rc) return rc;
-    rc = launch_adaptive(ctx, b, n, h, w, 1, a, st);
-    if (rc) return rc;
-    rc = launch_cleanup(ctx, a, n, h, w, mask, 0, nullptr, nullptr, 0, st);
+    rc = launch_cleanup(ctx, enh, n, h, w, mask, 0, nullptr, nullptr, 0, st);
     if (rc) return rc;
     if (info_out) SVB_CUDA_OK(cudaMemcpyAsync(info_out, S.info, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
     return SVB_OK;
@@ -1144,8 +1251,8 @@ int preprocess_multi_run(svb_ctx *ctx, const uint8_t *bgr, const uint8_t *gray_i
     if (rc) return rc;
     rc = launch_blur5(ctx, enhanced, n, h, w, bl, st);
     if (rc) return rc;
-    // strategy 1: adaptive
-    rc = launch_adaptive(ctx, bl, n, h, w, 1, a, st);
+    // strategy 1: adaptive (from the enhanced image: the fused kernel blurs it again on the fly)
+    rc = blur_threshold(ctx, enhanced, n, h, w, b, a, st);
     if (rc) return rc;
     rc = launch_cleanup(ctx, a, n, h, w, c0, 0, nullptr, S.counts, 2, st);
     if (rc) return rc;
