@@ -119,7 +119,9 @@ struct Geo {
     static constexpr int NSLICE = 9 * (CIN / KS);
     static constexpr int SLB = COUT * KS * 2;                       // bytes of one part of one weight slice
     static constexpr int TCOLS = MT * COUT;                         // TMEM columns used
-    static constexpr int TALLOC = TCOLS <= 32 ? 32 : (TCOLS <= 64 ? 64 : (TCOLS <= 128 ? 128 : (TCOLS <= 256 ? 256 : 512)));
+    static constexpr bool DB = 2 * TCOLS <= 512;                    // two accumulator sets: epilogue(i-1) under the MMAs of pass i
+    static constexpr int TUSED = DB ? 2 * TCOLS : TCOLS;
+    static constexpr int TALLOC = TUSED <= 32 ? 32 : (TUSED <= 64 ? 64 : (TUSED <= 128 ? 128 : (TUSED <= 256 ? 256 : 512)));
     // small layers keep every weight slice resident in shared memory; the others stream them through two buffers
     static constexpr bool RESIDENT = 2 * (size_t)PARTB + (size_t)NSLICE * 2 * SLB <= 200 * 1024;
     static constexpr int NBUF = RESIDENT ? NSLICE : 2;
@@ -174,7 +176,7 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
         cp_async_wait<0>();
     }
     // the MMAs of one weight slice (one tap x KS input channels) for every M tile of the pass
-    auto issue_slice = [&](int s, int buf) {
+    auto issue_slice = [&](int s, int buf, uint32_t tacc) {
         const int t = s / (CIN / KS), kb = s % (CIN / KS);
         const int dy = t / 3 - 1, dx = t % 3 - 1;
         const uint32_t row0 = (uint32_t)((1 + dy) * GW + dx + OFF);
@@ -188,41 +190,99 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
                     const uint32_t a_addr = a_base + (uint32_t)(pa * PARTB) + (uint32_t)((kb * (KS / 8) + ks * 2) * ROWS * 16) +
                                             (uint32_t)(tile * 128 + row0) * 16u;
                     const uint32_t b_addr = b_base + (uint32_t)(buf * 2 * SLB + pb * SLB + ks * 256);
-                    umma_f16(tmem + (uint32_t)(tile * COUT), make_desc(a_addr, ROWS * 16, 128),
+                    umma_f16(tacc + (uint32_t)(tile * COUT), make_desc(a_addr, ROWS * 16, 128),
                              make_desc(b_addr, 128, (KS / 8) * 128), idesc, (s | combo | ks) ? 1u : 0u);
                 }
             }
         }
     };
-    for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
-        const int c0 = pass * G;
-        if (!GEO::RESIDENT) load_slice(0, 0);
-        // activations of the pass: fp32 -> fp16 hi/lo, 8 channels (one 16-byte K chunk) of one pixel per item
-        for (int it = tid; it < G * NKC * HH; it += NT) {
-            const int p = it % HH, kc = (it / HH) % NKC, j = it / (HH * NKC);
-            const int cell = c0 + j;
-            if (cell >= n_cells) continue;
-            const float *src = in + ((size_t)cell * CIN + kc * 8) * HH + p;
-            __half hi[8], lo[8];
+    // ---- pipeline over passes ------------------------------------------------------------------------------------------
+    //   write A(i) from registers -> [barrier] -> MMAs(i) issued (async)  ||  global loads of pass i+1 into registers,
+    //   epilogue(i-1) when TMEM holds two accumulator sets  -> wait MMAs(i) [-> epilogue(i) otherwise]
+    constexpr int NITEMS = G * NKC * HH;                 // 16-byte K chunks of the pass's activations
+    constexpr int IPT = (NITEMS + NT - 1) / NT;          // per thread
+    constexpr bool DB = GEO::DB;
+    float pre[IPT][8];
+    auto prefetch = [&](int c0) {  // fp32 activations of the pass starting at cell c0: 8 channels of one pixel per item
 #pragma unroll
-            for (int e = 0; e < 8; ++e) split_hi_lo(__ldg(src + (size_t)e * HH), hi[e], lo[e]);
-            const int y = p / H, x = p - y * H;
-            const int row = j * CB + (y + 1) * GW + x + OFF;
-            const size_t o = (size_t)kc * ROWS * 16 + (size_t)row * 16;
-            *reinterpret_cast<uint4 *>(sA + o) = *reinterpret_cast<const uint4 *>(hi);
-            *reinterpret_cast<uint4 *>(sA + PARTB + o) = *reinterpret_cast<const uint4 *>(lo);
+        for (int k = 0; k < IPT; ++k) {
+            const int it = k * NT + tid;
+            const int p = it % HH, kc = (it / HH) % NKC, j = it / (HH * NKC);
+            if (it < NITEMS && c0 + j < n_cells) {
+                const float *src = in + ((size_t)(c0 + j) * CIN + kc * 8) * HH + p;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) pre[k][e] = __ldg(src + (size_t)e * HH);
+            }
         }
+    };
+    auto write_A = [&](int c0) {  // registers -> fp16 hi/lo rows of the activation buffer
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const int it = k * NT + tid;
+            const int p = it % HH, kc = (it / HH) % NKC, j = it / (HH * NKC);
+            if (it < NITEMS && c0 + j < n_cells) {
+                __half hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split_hi_lo(pre[k][e], hi[e], lo[e]);
+                const int y = p / H, x = p - y * H;
+                const int row = j * CB + (y + 1) * GW + x + OFF;
+                const size_t o = (size_t)kc * ROWS * 16 + (size_t)row * 16;
+                *reinterpret_cast<uint4 *>(sA + o) = *reinterpret_cast<const uint4 *>(hi);
+                *reinterpret_cast<uint4 *>(sA + PARTB + o) = *reinterpret_cast<const uint4 *>(lo);
+            }
+        }
+    };
+    // TMEM -> + bias -> [ReLU] -> fp32 NCHW (stride-2 layers keep the even rows / columns)
+    auto epilogue = [&](int c0, uint32_t tacc) {
+        const int q = warp & 3, grp = warp >> 2;  // TMEM lane quarter (hardware rule: warp % 4), work group
+        constexpr int NCB = COUT / 32;
+        for (int blk = grp; blk < MT * NCB; blk += NT / 128) {
+            const int tile = blk / NCB, cb = blk - tile * NCB;
+            uint32_t v[32];
+            tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * COUT + cb * 32), v);
+            const int m = tile * 128 + q * 32 + lane;
+            const int j = m / CB, rem = m - j * CB, y = rem / GW, x = rem - y * GW;
+            const int cell = c0 + j;
+            bool ok = (j < G) && (cell < n_cells) && (y < H) && (x < H);
+            if (STRIDE == 2) ok = ok && !(y & 1) && !(x & 1);
+            if (ok) {
+                float *dst = out + ((size_t)cell * COUT + cb * 32) * (HO * HO) + (y / STRIDE) * HO + (x / STRIDE);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    float f = __uint_as_float(v[c]) + s_bias[cb * 32 + c];
+                    if (relu) f = fmaxf(f, 0.f);
+                    dst[(size_t)c * (HO * HO)] = f;
+                }
+            }
+        }
+    };
+
+    int it = 0, prev_c0 = -1;
+    if ((int)blockIdx.x < n_pass) prefetch((int)blockIdx.x * G);
+    for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x, ++it) {
+        const int c0 = pass * G;
+        const uint32_t tacc = tmem + (DB ? (uint32_t)((it & 1) * GEO::TCOLS) : 0u);
+        const uint32_t tacc_prev = tmem + (DB ? (uint32_t)(((it & 1) ^ 1) * GEO::TCOLS) : 0u);
+        const int next = pass + gridDim.x;
+        if (!GEO::RESIDENT) load_slice(0, 0);
+        write_A(c0);
         if (GEO::RESIDENT) {
             fence_proxy_async();
+            tc_fence_before();
             __syncthreads();
             if (warp == 0) {
                 if (lane == 0) {
                     tc_fence_after();
 #pragma unroll 1
-                    for (int s = 0; s < NSLICE; ++s) issue_slice(s, s);
+                    for (int s = 0; s < NSLICE; ++s) issue_slice(s, s, tacc);
                     umma_commit(&mbar[0]);
                 }
                 __syncwarp();
+            }
+            if (next < n_pass) prefetch(next * G);
+            if (DB && it > 0) {
+                tc_fence_after();
+                epilogue(prev_c0, tacc_prev);
             }
             mbar_wait(&mbar[0], ph[0]);
             ph[0] ^= 1;
@@ -240,14 +300,22 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
                     cp_async_wait<0>();
                 }
                 fence_proxy_async();
+                tc_fence_before();
                 __syncthreads();
                 if (warp == 0) {
                     if (lane == 0) {
                         tc_fence_after();
-                        issue_slice(s, st);
+                        issue_slice(s, st, tacc);
                         umma_commit(&mbar[st]);
                     }
                     __syncwarp();
+                }
+                if (s == 0) {  // overlapped with the tensor core: next pass's loads, previous pass's epilogue
+                    if (next < n_pass) prefetch(next * G);
+                    if (DB && it > 0) {
+                        tc_fence_after();
+                        epilogue(prev_c0, tacc_prev);
+                    }
                 }
             }
             // drain: the commits of the last two slices are still pending
@@ -257,34 +325,15 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
             ph[(NSLICE - 1) & 1] ^= 1;
         }
         tc_fence_after();
-        // ---- epilogue: TMEM -> + bias -> [ReLU] -> fp32 NCHW (stride-2 layers keep the even rows / columns) -----------
-        {
-            const int q = warp & 3, grp = warp >> 2;  // TMEM lane quarter (hardware rule: warp % 4), work group
-            constexpr int NCB = COUT / 32;
-            for (int blk = grp; blk < MT * NCB; blk += NT / 128) {
-                const int tile = blk / NCB, cb = blk - tile * NCB;
-                uint32_t v[32];
-                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * COUT + cb * 32), v);
-                const int m = tile * 128 + q * 32 + lane;
-                const int j = m / CB, rem = m - j * CB, y = rem / GW, x = rem - y * GW;
-                const int cell = c0 + j;
-                bool ok = (j < G) && (cell < n_cells) && (y < H) && (x < H);
-                if (STRIDE == 2) ok = ok && !(y & 1) && !(x & 1);
-                if (ok) {
-                    float *dst = out + ((size_t)cell * COUT + cb * 32) * (HO * HO) + (y / STRIDE) * HO + (x / STRIDE);
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        float f = __uint_as_float(v[c]) + s_bias[cb * 32 + c];
-                        if (relu) f = fmaxf(f, 0.f);
-                        dst[(size_t)c * (HO * HO)] = f;
-                    }
-                }
-            }
-        }
+        if (!DB) epilogue(c0, tacc);
+        prev_c0 = c0;
         tc_fence_before();
-        __syncthreads();  // TMEM and the activation buffer are free for the next pass
+        __syncthreads();  // the activation buffer (and, single-buffered, TMEM) is free for the next pass
         tc_fence_after();
     }
+    if (DB && it > 0) epilogue(prev_c0, tmem + (uint32_t)(((it - 1) & 1) * GEO::TCOLS));
+    tc_fence_before();
+    __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, GEO::TALLOC);
 }
 

@@ -988,6 +988,8 @@ int launch_ellipse_morph(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, 
     const size_t per_frame = (size_t)h * nslots * P.rw;
     int group = (int)((256u << 20) / per_frame);
     group = group < 1 ? 1 : (group > n ? n : group);
+    const int ngroups = (n + group - 1) / group;
+    group = (n + ngroups - 1) / ngroups;  // equal groups: no short last launch
     if (ctx->arena[AR_V2T].reserve(per_frame * group) != SVB_OK) return SVB_ERR_CUDA;
     P.tab = (uint8_t *)ctx->arena[AR_V2T].ptr;
     const size_t px = (size_t)h * w;
