@@ -305,7 +305,9 @@ int launch_digitcnn_v3(svb_ctx *ctx, const float *x, long long n, float *logits,
     using namespace k6;
     V3State *s = reinterpret_cast<V3State *>(ctx->cnn_v3);
     SVB_REQUIRE(s != nullptr, SVB_ERR_NOT_LOADED, "DigitCNNv3 weights not loaded (svb_digitcnn_v3_load)");
-    const long long CHUNK = 2048;  // cells per pass: 3 activation buffers of 32x28x28 floats each
+    // cells per chunk: 16 per SM = whole waves for the tensor-core kernels (1, 2, 4 cells per pass) while the three
+    // activation buffers (32x28x28 floats per cell each) stay bounded (0.7 GB)
+    const long long CHUNK = (long long)ctx->sm_count * 16;
     const size_t plane = (size_t)32 * 784;
     const size_t buf = (size_t)CHUNK * plane;
     if (ctx->arena[AR_CNN].reserve((3 * buf + (size_t)CHUNK * 128) * sizeof(float)) != SVB_OK) return SVB_ERR_CUDA;

@@ -176,22 +176,31 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
         cp_async_wait<0>();
     }
     // the MMAs of one weight slice (one tap x KS input channels) for every M tile of the pass
+    // The MMAs are issued by ONE thread, so the issue loop is a serial instruction stream: everything that does not
+    // depend on the slice is a compile-time constant added to two per-slice base descriptors (all shared-memory
+    // addresses are below 256 KB, so adding (byte offset >> 4) never carries out of the 14-bit start-address field).
     auto issue_slice = [&](int s, int buf, uint32_t tacc) {
         const int t = s / (CIN / KS), kb = s % (CIN / KS);
         const int dy = t / 3 - 1, dx = t % 3 - 1;
-        const uint32_t row0 = (uint32_t)((1 + dy) * GW + dx + OFF);
-#pragma unroll 1
-        for (int tile = 0; tile < MT; ++tile) {
+        const uint64_t ad0 = make_desc(a_base + (uint32_t)(kb * (KS / 8) * ROWS * 16) + (uint32_t)((1 + dy) * GW + dx + OFF) * 16u,
+                                       ROWS * 16, 128);
+        const uint64_t bd0 = make_desc(b_base + (uint32_t)(buf * 2 * SLB), 128, (KS / 8) * 128);
+        const uint32_t acc0 = s ? 1u : 0u;
+        // consecutive MMAs go to DIFFERENT accumulator tiles: back-to-back MMAs into the same TMEM tile serialise on
+        // the accumulator (with N = 32..128 one MMA is short compared with the pipeline's latency)
 #pragma unroll
-            for (int combo = 0; combo < 3; ++combo) {
-                const int pa = (combo == 2) ? 1 : 0, pb = (combo == 1) ? 1 : 0;  // hi*hi, hi*lo, lo*hi
+        for (int combo = 0; combo < 3; ++combo) {
+            const int pa = (combo == 2) ? 1 : 0, pb = (combo == 1) ? 1 : 0;  // hi*hi, hi*lo, lo*hi
 #pragma unroll
-                for (int ks = 0; ks < KS / 16; ++ks) {
-                    const uint32_t a_addr = a_base + (uint32_t)(pa * PARTB) + (uint32_t)((kb * (KS / 8) + ks * 2) * ROWS * 16) +
-                                            (uint32_t)(tile * 128 + row0) * 16u;
-                    const uint32_t b_addr = b_base + (uint32_t)(buf * 2 * SLB + pb * SLB + ks * 256);
-                    umma_f16(tacc + (uint32_t)(tile * COUT), make_desc(a_addr, ROWS * 16, 128),
-                             make_desc(b_addr, 128, (KS / 8) * 128), idesc, (s | combo | ks) ? 1u : 0u);
+            for (int ks = 0; ks < KS / 16; ++ks) {
+#pragma unroll
+                for (int tile = 0; tile < MT; ++tile) {
+                    const uint32_t a_off = (uint32_t)(pa * PARTB + ks * 2 * ROWS * 16 + tile * 128 * 16);
+                    const uint32_t b_off = (uint32_t)(pb * SLB + ks * 256);
+                    // the whole warp runs the (uniform) descriptor arithmetic; only the MMA itself is predicated on one lane
+                    if (lane == 0)
+                        umma_f16(tacc + (uint32_t)(tile * COUT), ad0 + (uint64_t)(a_off >> 4), bd0 + (uint64_t)(b_off >> 4), idesc,
+                                 (combo | ks) ? 1u : acc0);
                 }
             }
         }
@@ -271,12 +280,10 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
             tc_fence_before();
             __syncthreads();
             if (warp == 0) {
-                if (lane == 0) {
-                    tc_fence_after();
+                tc_fence_after();
 #pragma unroll 1
-                    for (int s = 0; s < NSLICE; ++s) issue_slice(s, s, tacc);
-                    umma_commit(&mbar[0]);
-                }
+                for (int s = 0; s < NSLICE; ++s) issue_slice(s, s, tacc);
+                if (lane == 0) umma_commit(&mbar[0]);
                 __syncwarp();
             }
             if (next < n_pass) prefetch(next * G);
@@ -303,11 +310,9 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
                 tc_fence_before();
                 __syncthreads();
                 if (warp == 0) {
-                    if (lane == 0) {
-                        tc_fence_after();
-                        issue_slice(s, st, tacc);
-                        umma_commit(&mbar[st]);
-                    }
+                    tc_fence_after();
+                    issue_slice(s, st, tacc);
+                    if (lane == 0) umma_commit(&mbar[st]);
                     __syncwarp();
                 }
                 if (s == 0) {  // overlapped with the tensor core: next pass's loads, previous pass's epilogue
