@@ -186,17 +186,29 @@ int svb_scan_batch_v1(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uin
 int svb_scan_batch_v1_host(svb_ctx *ctx, const uint8_t *host_bgr, int n, int h, int w, uint8_t *host_digits,
                            float *host_conf, int32_t *host_corners, uint8_t *host_found);
 
+/* ---- cv/grid_quality.py ---------------------------------------------------------------------------------- */
+/* assess_grid_quality(image, binary, corners)  cv/grid_quality.py:228-306.  frames: BGR (channels 3) or gray (1);
+ * binary: the preprocessed mask uint8 [n][h][w]; corners: int32 [n][4][2] in any order (the contour method's corners are
+ * integral); found (optional): frames with found != 1 get zeros.
+ * scores: double [n][6] = overall, sharpness (Laplacian variance), contrast (95 % histogram range), completeness (mask
+ * coverage of the 20 grid-line bands after the 450x450 warp), geometry, size.  The issue / recommendation strings of
+ * QualityScore are host logic on these numbers (drop-in module). */
+int svb_assess_grid_quality(svb_ctx *ctx, const uint8_t *frames, int n, int h, int w, int channels, const uint8_t *binary,
+                            const int32_t *corners, const uint8_t *found, double *scores, void *stream);
+
 /* ---- whole v2 path: pipeline/run_v2.py:276-330 for n frames ------------------------------------------ */
 /* preprocess_multi_strategy -> detect_grid method 1 (contour + is_valid_quadrilateral; the Hough / rotation / Harris
- * fallbacks of cv/grid_v2.py:446-508 and the grid_quality gate of run_v2.py:300-308 are not built: this is
- * `run_v2.py --no-quality-check` restricted to method 1) -> warp + 81 cells + preprocess_cell -> DigitCNNv3 ->
- * softmax top-3 (run_v2.py:149-190).  Requires svb_digitcnn_v3_load.
+ * fallbacks of cv/grid_v2.py:446-508 are not built) -> assess_grid_quality and the min_quality_score gate
+ * (run_v2.py:300-308; min_quality_score < 0 = `--no-quality-check`, the reference's default is 40) -> warp + 81 cells +
+ * preprocess_cell -> DigitCNNv3 -> softmax top-3 (run_v2.py:149-190).  Requires svb_digitcnn_v3_load.
+ * quality (optional): double [n][6] as svb_assess_grid_quality.  found: 0 no grid, 1 scanned, 3 grid found but below
+ * min_quality_score (status 'quality_failed').
  * Outputs: digits uint8 [n][81] / conf float [n][81] (best class), alt_digits uint8 [n][81][2] / alt_conf float
  * [n][81][2] (2nd and 3rd, optional), logits float [n][81][10] (optional), corners int32 [n][4][2] ordered TL,TR,BR,BL,
  * found uint8 [n], info uint8 [n][4] as svb_preprocess_multi_v2 (optional).  Frames with found == 0 get zeros. */
 int svb_scan_batch_v2(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *digits, float *conf,
                       uint8_t *alt_digits, float *alt_conf, float *logits, int32_t *corners, uint8_t *found, uint8_t *info,
-                      void *stream);
+                      double *quality, double min_quality_score, void *stream);
 
 #ifdef __cplusplus
 }

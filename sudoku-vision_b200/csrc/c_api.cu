@@ -61,6 +61,8 @@ int preprocess_v2_run(svb_ctx *, const uint8_t *, const uint8_t *, int, int, int
 int preprocess_multi_run(svb_ctx *, const uint8_t *, const uint8_t *, int, int, int, uint8_t *, uint8_t *, uint8_t *, uint8_t *,
                          uint8_t *, cudaStream_t);
 int v2_stage(svb_ctx *, int, const uint8_t *, int, int, int, int, uint8_t *, uint8_t *, cudaStream_t);
+int launch_grid_quality(svb_ctx *, const uint8_t *, int, int, int, int, const uint8_t *, const int32_t *, const uint8_t *, double *, cudaStream_t);
+int launch_quality_gate(svb_ctx *, const double *, uint8_t *, int, double, cudaStream_t);
 int launch_top3(svb_ctx *, const float *, const uint8_t *, long long, uint8_t *, float *, uint8_t *, float *, cudaStream_t);
 bool digitcnn_v3_loaded(const svb_ctx *);
 int launch_mask_not_found(svb_ctx *, const uint8_t *, int, uint8_t *, float *, cudaStream_t);
@@ -348,9 +350,17 @@ API int svb_scan_batch_v1(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w,
 
 // v2 whole path (pipeline/run_v2.py:276-330 with --no-quality-check): frames are processed in chunks so that the
 // preprocess_v2 planes (about 11 per frame) stay within a few GB whatever n is.
+API int svb_assess_grid_quality(svb_ctx *ctx, const uint8_t *frames, int n, int h, int w, int channels, const uint8_t *binary,
+                                const int32_t *corners, const uint8_t *found, double *scores, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(frames && binary && corners && scores && dims_ok(n, h, w) && (channels == 1 || channels == 3), SVB_ERR_INVALID,
+                "svb_assess_grid_quality: bad arguments");
+    return launch_grid_quality(ctx, frames, n, h, w, channels, binary, corners, found, scores, (cudaStream_t)stream);
+}
+
 API int svb_scan_batch_v2(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *digits, float *conf,
                           uint8_t *alt_digits, float *alt_conf, float *logits, int32_t *corners, uint8_t *found, uint8_t *info,
-                          void *stream) {
+                          double *quality, double min_quality_score, void *stream) {
     GUARD(ctx);
     SVB_REQUIRE(bgr && digits && conf && corners && found && dims_ok(n, h, w), SVB_ERR_INVALID, "svb_scan_batch_v2: bad arguments");
     SVB_REQUIRE(digitcnn_v3_loaded(ctx), SVB_ERR_NOT_LOADED, "svb_scan_batch_v2: DigitCNNv3 weights not loaded");
@@ -366,6 +376,8 @@ API int svb_scan_batch_v2(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w,
     };
     const size_t o_bin = take(px * chunk), o_pm1 = take((size_t)chunk * 81 * 784 * sizeof(float));
     const size_t o_log = take((size_t)chunk * 81 * 10 * sizeof(float));
+    const bool gate = min_quality_score >= 0.0;
+    const size_t o_q = take((size_t)chunk * 6 * sizeof(double));
     if (ctx->arena[AR_PATH].reserve(off) != SVB_OK) return SVB_ERR_CUDA;
     char *base = (char *)ctx->arena[AR_PATH].ptr;
     for (int f0 = 0; f0 < n; f0 += chunk) {
@@ -378,6 +390,15 @@ API int svb_scan_batch_v2(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w,
         if (rc) return rc;
         rc = launch_find_grid_contour(ctx, binary, m, h, w, 0.1, 0.02, corners + (size_t)f0 * 8, found + f0, st, 1);
         if (rc) return rc;
+        if (quality || gate) {  // assess_grid_quality + the min_quality_score gate (run_v2.py:300-308)
+            double *q = quality ? quality + (size_t)f0 * 6 : (double *)(base + o_q);
+            rc = launch_grid_quality(ctx, fr, m, h, w, 3, binary, corners + (size_t)f0 * 8, found + f0, q, st);
+            if (rc) return rc;
+            if (gate) {
+                rc = launch_quality_gate(ctx, q, found + f0, m, min_quality_score, st);
+                if (rc) return rc;
+            }
+        }
         rc = launch_cells_from_frames(ctx, fr, m, h, w, corners + (size_t)f0 * 8, found + f0, nullptr, pm1, st);
         if (rc) return rc;
         rc = launch_digitcnn_v3(ctx, pm1, (long long)m * 81, lg, nullptr, nullptr, nullptr, st);

@@ -428,6 +428,186 @@ cell_prep_kernel(const uint8_t *__restrict__ cells, uint8_t *__restrict__ thr, f
     threshold_phase(s, thr ? thr + base : nullptr, pm1 ? pm1 + base : nullptr);
 }
 
+
+// ---- cv/grid_quality.py: assess_grid_quality (the gate of pipeline/run_v2.py:300-308) --------------------------------
+// qsum (per frame, 64-bit): [0] sum of the Laplacian (as signed), [1] sum of its square, [2..21] non-zero warped-mask
+// pixels in the 20 line bands; qhist: 256-bin histogram of the gray frame.
+constexpr int QSUM = 24;
+
+// compute_sharpness (:48-63): cv2.Laplacian(gray, CV_64F), aperture 1 = [0 1 0; 1 -4 1; 0 1 0], BORDER_REFLECT_101;
+// and the gray histogram of compute_contrast (:66-88) in the same pass over the frame
+__global__ void __launch_bounds__(256) quality_frame_kernel(const uint8_t *__restrict__ gray, int h, int w,
+                                                            unsigned long long *__restrict__ qsum, uint32_t *__restrict__ qhist) {
+    __shared__ uint32_t s_h[8][256];
+    const int f = blockIdx.y, tid = threadIdx.x, wid = tid >> 5;
+    for (int i = tid; i < 8 * 256; i += 256) (&s_h[0][0])[i] = 0;
+    __syncthreads();
+    const uint8_t *img = gray + (size_t)f * h * w;
+    const int px = h * w;
+    long long s1 = 0;
+    unsigned long long s2 = 0;
+    for (int i = blockIdx.x * 256 + tid; i < px; i += gridDim.x * 256) {
+        const int y = i / w, x = i - y * w;
+        const int c = img[i];
+        const int up = img[(size_t)(h > 1 ? reflect101(y - 1, h) : 0) * w + x], dn = img[(size_t)(h > 1 ? reflect101(y + 1, h) : 0) * w + x];
+        const int lf = img[(size_t)y * w + (w > 1 ? reflect101(x - 1, w) : 0)], rt = img[(size_t)y * w + (w > 1 ? reflect101(x + 1, w) : 0)];
+        const int L = up + dn + lf + rt - 4 * c;
+        s1 += L;
+        s2 += (unsigned long long)(L * L);
+        atomicAdd(&s_h[wid][c], 1u);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+    }
+    if ((tid & 31) == 0) {
+        atomicAdd(&qsum[(size_t)f * QSUM + 0], (unsigned long long)s1);
+        atomicAdd(&qsum[(size_t)f * QSUM + 1], s2);
+    }
+    __syncthreads();
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += s_h[k][tid];
+    if (v) atomicAdd(&qhist[(size_t)f * 256 + tid], v);
+}
+
+// compute_completeness (:91-141): the mask warped to 450x450 (same fixed-point warpPerspective as the board), sampled
+// only where the 20 line bands (rows / columns i*50 +- 2) need it; one CTA per frame
+__global__ void __launch_bounds__(256) quality_bands_kernel(const uint8_t *__restrict__ mask, int h, int w,
+                                                            const double *__restrict__ minv, const uint8_t *__restrict__ found,
+                                                            unsigned long long *__restrict__ qsum) {
+    __shared__ int s_cnt[20];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    if (found && found[f] != 1) return;
+    if (tid < 20) s_cnt[tid] = 0;
+    __syncthreads();
+    const uint8_t *img = mask + (size_t)f * h * w;
+    const double *mi = minv + (size_t)f * 9;
+    for (int b = 0; b < 20; ++b) {
+        const int c = min((b >> 1) * (BOARD / 9), BOARD - 1);
+        const int lo = max(0, c - 2), hi = min(BOARD, c + 3);
+        int cnt = 0;
+        for (int i = tid; i < (hi - lo) * BOARD; i += 256) {
+            const int a = lo + i / BOARD, o = i % BOARD;
+            const int x = (b & 1) ? a : o, y = (b & 1) ? o : a;  // even: horizontal band (rows lo..hi), odd: vertical
+            const Tap t = make_tap(mi, x, y, 64);
+            const bool x0 = (unsigned)t.ix < (unsigned)w, x1 = (unsigned)(t.ix + 1) < (unsigned)w;
+            const bool y0 = (unsigned)t.iy < (unsigned)h, y1 = (unsigned)(t.iy + 1) < (unsigned)h;
+            const uint8_t *p = img + (long long)t.iy * w + t.ix;
+            const int p00 = (x0 && y0) ? p[0] : 0, p01 = (x1 && y0) ? p[1] : 0;
+            const int p10 = (x0 && y1) ? p[w] : 0, p11 = (x1 && y1) ? p[w + 1] : 0;
+            cnt += ((t.w00 * p00 + t.w01 * p01 + t.w10 * p10 + t.w11 * p11 + 16384) >> 15) > 0;
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if ((tid & 31) == 0 && cnt) atomicAdd(&s_cnt[b], cnt);
+    }
+    __syncthreads();
+    if (tid < 20) qsum[(size_t)f * QSUM + 2 + tid] = (unsigned long long)s_cnt[tid];
+}
+
+// run_v2.py:305-308: frames whose overall score is below the threshold leave the pipeline (found: 1 -> 3)
+__global__ void quality_gate_kernel(const double *__restrict__ scores, uint8_t *__restrict__ found, int n, double min_score) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < n && found[f] == 1 && scores[(size_t)f * 6] < min_score) found[f] = 3;
+}
+
+// the five scores and their weighted sum (:228-271), numpy's dtypes: float64 for sharpness / contrast / completeness,
+// float32 for the corner arithmetic of compute_geometry (:144-186) and compute_size_score (:189-211).
+// scores: double [n][6] = overall, sharpness, contrast, completeness, geometry, size
+__global__ void quality_scores_kernel(const unsigned long long *__restrict__ qsum, const uint32_t *__restrict__ qhist,
+                                      const int32_t *__restrict__ corners, const uint8_t *__restrict__ found, int n, int px,
+                                      double *__restrict__ scores) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    double *o = scores + (size_t)f * 6;
+    if (found && found[f] != 1) {
+        for (int i = 0; i < 6; ++i) o[i] = 0.0;
+        return;
+    }
+    const unsigned long long *q = qsum + (size_t)f * QSUM;
+    const double N = (double)px;
+    // variance = E[L^2] - E[L]^2 from exact integer sums
+    const double mean = (double)(long long)q[0] / N;
+    const double var = (double)q[1] / N - mean * mean;
+    const double sharp = fmin(100.0, var / 10.0);
+    // 2.5 % / 97.5 % points of the cumulative histogram (float32 cumsum as np.cumsum of calcHist's float32 bins)
+    const uint32_t *hst = qhist + (size_t)f * 256;
+    const double lo_v = N * 0.025, hi_v = N * 0.975;
+    float cum = 0.f;
+    int lo_i = 256, hi_i = 256;
+    for (int i = 0; i < 256; ++i) {
+        cum = __fadd_rn(cum, (float)hst[i]);
+        if (lo_i == 256 && (double)cum >= lo_v) lo_i = i;
+        if (hi_i == 256 && (double)cum >= hi_v) hi_i = i;
+    }
+    const double contrast = fmin(100.0, (double)(hi_i - lo_i) / 2.0);
+    double cov = 0.0;
+    for (int b = 0; b < 20; ++b) {
+        const int c = min((b >> 1) * (BOARD / 9), BOARD - 1);
+        const int rows = min(BOARD, c + 3) - max(0, c - 2);
+        cov += (double)q[2 + b] / (double)(rows * BOARD);
+    }
+    const double compl_ = fmin(100.0, cov / 20.0 / 0.5 * 100.0);
+    // ordered corners (first index wins ties, as numpy's argmin / argmax)
+    const int32_t *c = corners + (size_t)f * 8;
+    int is_min = 0, is_max = 0, id_min = 0, id_max = 0;
+    for (int i = 1; i < 4; ++i) {
+        const int sm = c[2 * i] + c[2 * i + 1], d = c[2 * i + 1] - c[2 * i];
+        if (sm < c[2 * is_min] + c[2 * is_min + 1]) is_min = i;
+        if (sm > c[2 * is_max] + c[2 * is_max + 1]) is_max = i;
+        if (d < c[2 * id_min + 1] - c[2 * id_min]) id_min = i;
+        if (d > c[2 * id_max + 1] - c[2 * id_max]) id_max = i;
+    }
+    const int order[4] = {is_min, id_min, is_max, id_max};
+    float px_[4], py_[4];
+    for (int i = 0; i < 4; ++i) {
+        px_[i] = (float)c[2 * order[i]];
+        py_[i] = (float)c[2 * order[i] + 1];
+    }
+    auto norm2 = [](float dx, float dy) { return __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))); };
+    float side[4];
+    for (int i = 0; i < 4; ++i) side[i] = norm2(px_[(i + 1) & 3] - px_[i], py_[(i + 1) & 3] - py_[i]);
+    const float mean_side = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(side[0], side[1]), side[2]), side[3]), 4.0f);
+    float sq = 0.f;
+    for (int i = 0; i < 4; ++i) {
+        const float d = __fsub_rn(side[i], mean_side);
+        sq = __fadd_rn(sq, __fmul_rn(d, d));
+    }
+    const float sd = __fsqrt_rn(__fdiv_rn(sq, 4.0f));
+    const float side_var = mean_side > 0.f ? __fdiv_rn(sd, mean_side) : 1.0f;
+    float adev = 0.f;
+    for (int i = 0; i < 4; ++i) {
+        const int i1 = (i + 1) & 3, i2 = (i + 2) & 3;
+        const float v1x = px_[i] - px_[i1], v1y = py_[i] - py_[i1], v2x = px_[i2] - px_[i1], v2y = py_[i2] - py_[i1];
+        const float dot = __fadd_rn(__fmul_rn(v1x, v2x), __fmul_rn(v1y, v2y));
+        float cs = __fdiv_rn(dot, __fadd_rn(__fmul_rn(norm2(v1x, v1y), norm2(v2x, v2y)), 1e-6f));
+        cs = fminf(fmaxf(cs, -1.f), 1.f);
+        const float ang = __fmul_rn(acosf(cs), 57.29577951308232f);
+        adev = __fadd_rn(adev, fabsf(__fsub_rn(ang, 90.f)));
+    }
+    adev = __fdiv_rn(adev, 4.0f);
+    const float side_score = fmaxf(0.f, __fsub_rn(100.f, __fmul_rn(side_var, 200.f)));
+    const float angle_score = fmaxf(0.f, __fsub_rn(100.f, __fmul_rn(adev, 5.f)));
+    const float geometry = __fdiv_rn(__fadd_rn(side_score, angle_score), 2.0f);
+    const float cell = __fdiv_rn(mean_side, 9.0f);
+    float size;
+    if (cell < 15.f) size = __fmul_rn(__fdiv_rn(cell, 15.f), 30.f);
+    else if (cell < 30.f) size = __fadd_rn(30.f, __fmul_rn(__fdiv_rn(__fsub_rn(cell, 15.f), 15.f), 40.f));
+    else size = fminf(100.f, __fadd_rn(70.f, __fmul_rn(__fdiv_rn(__fsub_rn(cell, 30.f), 20.f), 30.f)));
+    // weights applied as Python floats: x float64 stays float64, x float32 stays float32 (NEP 50)
+    double overall = 0.25 * sharp + 0.15 * contrast;
+    overall += 0.25 * compl_;
+    overall += (double)__fmul_rn(0.2f, geometry);
+    overall += (double)__fmul_rn(0.15f, size);
+    o[0] = overall;
+    o[1] = sharp;
+    o[2] = contrast;
+    o[3] = compl_;
+    o[4] = (double)geometry;
+    o[5] = (double)size;
+}
+
 }  // namespace k4
 
 // ---- host side ---------------------------------------------------------------------------------------
@@ -493,6 +673,47 @@ int launch_cells_from_frames(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int
     dim3 grid(81, n);
     k4::cells_from_frames_kernel<<<grid, k4::NT, 0, st>>>(bgr, h, w, minv, found, rt, cells_u8, cells_pm1);
     return check_launch(ctx, "k4::cells_from_frames_kernel");
+}
+
+int launch_gray(svb_ctx *, const uint8_t *, int, int, int, uint8_t *, cudaStream_t);
+
+// assess_grid_quality(image, binary, corners) — cv/grid_quality.py:228-306.  frames: BGR (channels 3) or gray (1);
+// corners int32 [n][4][2] in any order; scores double [n][6] = overall, sharpness, contrast, completeness, geometry, size
+int launch_grid_quality(svb_ctx *ctx, const uint8_t *frames, int n, int h, int w, int channels, const uint8_t *binary,
+                        const int32_t *corners, const uint8_t *found, double *scores, cudaStream_t st) {
+    const size_t px = (size_t)h * w;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_hist = al((size_t)n * k4::QSUM * 8), o_gray = o_hist + al((size_t)n * 256 * 4);
+    const size_t total = o_gray + (channels == 3 ? al(px * n) : 0);
+    if (ctx->arena[AR_QUAL].reserve(total) != SVB_OK) return SVB_ERR_CUDA;
+    char *base = (char *)ctx->arena[AR_QUAL].ptr;
+    unsigned long long *qsum = (unsigned long long *)base;
+    uint32_t *qhist = (uint32_t *)(base + o_hist);
+    SVB_CUDA_OK(cudaMemsetAsync(base, 0, o_gray, st));
+    const uint8_t *gray = frames;
+    if (channels == 3) {
+        uint8_t *g = (uint8_t *)(base + o_gray);
+        int rc = launch_gray(ctx, frames, n, h, w, g, st);
+        if (rc) return rc;
+        gray = g;
+    }
+    const int blocks = (int)((px + 256 * 16 - 1) / (256 * 16));
+    k4::quality_frame_kernel<<<dim3(blocks < 1 ? 1 : (blocks > 512 ? 512 : blocks), n), 256, 0, st>>>(gray, h, w, qsum, qhist);
+    int rc = check_launch(ctx, "k4::quality_frame_kernel");
+    if (rc) return rc;
+    double *minv = nullptr;
+    rc = homography(ctx, corners, found, n, k4::BOARD, &minv, st);
+    if (rc) return rc;
+    k4::quality_bands_kernel<<<n, 256, 0, st>>>(binary, h, w, minv, found, qsum);
+    rc = check_launch(ctx, "k4::quality_bands_kernel");
+    if (rc) return rc;
+    k4::quality_scores_kernel<<<(n + 63) / 64, 64, 0, st>>>(qsum, qhist, corners, found, n, (int)px, scores);
+    return check_launch(ctx, "k4::quality_scores_kernel");
+}
+
+int launch_quality_gate(svb_ctx *ctx, const double *scores, uint8_t *found, int n, double min_score, cudaStream_t st) {
+    k4::quality_gate_kernel<<<(n + 127) / 128, 128, 0, st>>>(scores, found, n, min_score);
+    return check_launch(ctx, "k4::quality_gate_kernel");
 }
 
 }  // namespace svb

@@ -52,10 +52,11 @@ def seed_modules() -> None:
     sys.modules["grid"] = importlib.import_module("cv.grid")
     sys.modules["extract"] = importlib.import_module("cv.extract")
     sys.modules["model"] = ml_model
-    # v2 front ends (pipeline/run_v2.py:37-39, cv/grid_v2.py:534): preprocessing, detection method 1 and the classifier
-    # run on the GPU; cv/grid_quality.py is not built and stays the reference's own module
+    # v2 front ends (pipeline/run_v2.py:37-39, cv/grid_v2.py:534): preprocessing, detection method 1, the quality gate
+    # and the classifier run on the GPU
     sys.modules["preprocess_v2"] = importlib.import_module("cv.preprocess_v2")
     sys.modules["grid_v2"] = importlib.import_module("cv.grid_v2")
+    sys.modules["grid_quality"] = importlib.import_module("cv.grid_quality")
     try:
         sys.modules["model_v3"] = importlib.import_module("ml.model_v3")
     except ImportError:

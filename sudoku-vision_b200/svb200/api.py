@@ -339,9 +339,24 @@ class Scanner:
                                               self._stream()), "svb_scan_batch_v1")
         return out
 
-    def scan_batch_v2(self, bgr, want_logits: bool = False) -> dict:
-        """pipeline/run_v2.py:276-330 (--no-quality-check, detection method 1) for a device-resident batch (n,H,W,3) u8:
-        preprocess_multi_strategy -> contour + validity -> cells -> DigitCNNv3 -> top-3.  Needs load_weights_v3."""
+    QUALITY_FIELDS = ("overall", "sharpness", "contrast", "completeness", "geometry", "size")
+
+    def assess_grid_quality(self, frames, binary, corners, found=None):
+        """cv/grid_quality.py:228-306 for a batch: frames (n,H,W,3) BGR or (n,H,W) gray, binary (n,H,W), corners
+        (n,4,2) int32 -> scores (n,6) float64 in QUALITY_FIELDS order."""
+        torch = _torch()
+        n, h, w, ch = self._frames_nhw(frames, "assess_grid_quality")
+        self._chk_u8(binary, 3, "assess_grid_quality")
+        corners = corners.to(device=frames.device, dtype=torch.int32).contiguous()
+        scores = torch.empty((n, 6), dtype=torch.float64, device=frames.device)
+        _lib.check(self.lib.svb_assess_grid_quality(self._h, _ptr(frames), n, h, w, ch, _ptr(binary), _ptr(corners), _ptr(found),
+                                                    _ptr(scores), self._stream()), "svb_assess_grid_quality")
+        return scores
+
+    def scan_batch_v2(self, bgr, want_logits: bool = False, min_quality_score: float = -1.0) -> dict:
+        """pipeline/run_v2.py:276-330 (detection method 1) for a device-resident batch (n,H,W,3) u8:
+        preprocess_multi_strategy -> contour + validity -> assess_grid_quality [gate when min_quality_score >= 0; the
+        reference's default is 40, -1 = --no-quality-check] -> cells -> DigitCNNv3 -> top-3.  Needs load_weights_v3."""
         torch = _torch()
         self._chk_u8(bgr, 4, "scan_batch_v2")
         n, h, w, _ = bgr.shape
@@ -353,10 +368,12 @@ class Scanner:
                    logits=torch.empty((n, 81, 10), dtype=torch.float32, device=dev) if want_logits else None,
                    corners=torch.empty((n, 4, 2), dtype=torch.int32, device=dev),
                    found=torch.empty((n,), dtype=torch.uint8, device=dev),
-                   info=torch.empty((n, 4), dtype=torch.uint8, device=dev))
+                   info=torch.empty((n, 4), dtype=torch.uint8, device=dev),
+                   quality=torch.empty((n, 6), dtype=torch.float64, device=dev))
         _lib.check(self.lib.svb_scan_batch_v2(self._h, _ptr(bgr), n, h, w, _ptr(out["digits"]), _ptr(out["conf"]),
                                               _ptr(out["alt_digits"]), _ptr(out["alt_conf"]), _ptr(out["logits"]),
-                                              _ptr(out["corners"]), _ptr(out["found"]), _ptr(out["info"]), self._stream()),
+                                              _ptr(out["corners"]), _ptr(out["found"]), _ptr(out["info"]),
+                                              _ptr(out["quality"]), float(min_quality_score), self._stream()),
                    "svb_scan_batch_v2")
         return out
 

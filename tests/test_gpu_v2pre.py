@@ -266,3 +266,79 @@ def test_scan_batch_v2_whole_path(scanner, oracle):
         assert np.array_equal(got_idx[margin_ok], ti.numpy()[margin_ok].astype(np.uint8))
         assert np.abs(got_p - tp.numpy()).max() < 1e-4
     assert n_found >= 2
+
+
+QUALITY_TOL = 1e-3  # scores are 0..100 floats; float32 corner arithmetic (acos) may differ in the last bits
+
+
+def test_grid_quality_golden_and_full_size(scanner, oracle, golden, v2pre):
+    """svb_assess_grid_quality vs the reference's scores (golden) and vs the oracle on a 1080p frame."""
+    from oracle import oracle_quality as Q
+    from oracle import oracle_v2
+    from svb200 import frames as F
+
+    g = golden("quality")
+    for tag in ("a", "b"):
+        names = [c for c in CASES if c.startswith(tag + "_")]
+        frames = _t(np.stack([v2pre[c + "_bgr"] for c in names]))
+        binary = _t(np.stack([v2pre[c + "_ref_binary"] for c in names]))
+        corners = _t(np.stack([g[c + "_corners"].astype(np.int32) for c in names]))
+        got = _np(scanner.assess_grid_quality(frames, binary, corners))
+        for i, c in enumerate(names):
+            assert np.abs(got[i] - g[c + "_ref_scores"]).max() < QUALITY_TOL, (c, got[i], g[c + "_ref_scores"])
+        gray = _t(np.stack([v2pre[c + "_ref_gray"] for c in names]))  # gray input: same scores
+        assert np.abs(_np(scanner.assess_grid_quality(gray, binary, corners)) - got).max() < 1e-9
+    img = F.add_noise_host(F.make_frame(909, 1080, 1920, 10.0).image, 909)
+    r = oracle.preprocess_multi(img)
+    c = oracle_v2.detect_grid_contour(r["binary"])
+    assert c is not None
+    want = Q.assess(img, r["binary"], c)
+    got = _np(scanner.assess_grid_quality(_t(img[None]), _t(r["binary"][None]), _t(c.astype(np.int32)[None])))[0]
+    assert np.abs(got - np.array([want[f] for f in Q.FIELDS])).max() < QUALITY_TOL
+
+
+def test_scan_batch_v2_quality_gate(scanner, v2pre):
+    """min_quality_score: frames below it leave the pipeline as 'quality_failed' (found == 3, zeros), the others are
+    scanned exactly as without the gate (run_v2.py:300-308)."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "helpers"))
+    from v3_weights import make_v3_state
+
+    scanner.load_weights_v3(make_v3_state())
+    names = [c for c in CASES if c.startswith("a_")]
+    batch = _t(np.stack([v2pre[c + "_bgr"] for c in names]))
+    free = scanner.scan_batch_v2(batch)
+    q = _np(free["quality"])[:, 0]
+    found0 = _np(free["found"])
+    ok = found0 == 1
+    assert ok.any()
+    thr = float(np.median(q[ok])) + 1e-6 if ok.sum() > 1 else float(q[ok][0]) + 1.0
+    gated = scanner.scan_batch_v2(batch, min_quality_score=thr)
+    f1 = _np(gated["found"])
+    for i in range(len(names)):
+        if found0[i] == 1 and q[i] < thr:
+            assert f1[i] == 3 and not _np(gated["digits"])[i].any() and not _np(gated["conf"])[i].any()
+        else:
+            assert f1[i] == found0[i]
+            assert np.array_equal(_np(gated["digits"])[i], _np(free["digits"])[i])
+    assert (f1 == 3).any()
+
+
+def test_grid_quality_dropin(golden, v2pre):
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "sudoku-vision_b200", "dropin"))
+    from cv import grid_quality as GQ
+
+    g = golden("quality")
+    for c in ("a_flat", "b_plain"):
+        q = GQ.assess_grid_quality(v2pre[c + "_bgr"], v2pre[c + "_ref_binary"], g[c + "_corners"])
+        assert isinstance(q, GQ.QualityScore)
+        assert abs(q.overall - g[c + "_ref_scores"][0]) < QUALITY_TOL
+        assert GQ.get_user_feedback(q) == str(g[c + "_ref_feedback"])
+    with pytest.raises(NotImplementedError):
+        GQ.assess_grid_quality(v2pre["a_plain_bgr"], v2pre["a_plain_ref_binary"], g["a_plain_corners"] + 0.5)

@@ -90,3 +90,16 @@ def test_against_live_cv2(oracle):
         assert np.array_equal(oracle.morph_cleanup(m), c)
     g = cv2.GaussianBlur(rng.integers(0, 256, (96, 160)).astype(np.uint8), (3, 3), 0)
     assert np.array_equal(oracle.clahe_frame(g), cv2.createCLAHE(clipLimit=2.0, tileGridSize=(8, 8)).apply(g))
+
+
+def test_grid_quality_oracle_vs_reference_golden(golden, v2pre):
+    """oracle/oracle_quality.py vs the unmodified cv/grid_quality.py (tests/golden/make_quality_golden.py)."""
+    from oracle import oracle_quality as Q
+
+    g = golden("quality")
+    for case in CASES:
+        r = Q.assess(v2pre[case + "_bgr"], v2pre[case + "_ref_binary"], g[case + "_corners"])
+        got = np.array([r[f] for f in Q.FIELDS])
+        assert np.abs(got - g[case + "_ref_scores"]).max() < 1e-9, case
+    ov = np.array([g[c + "_ref_scores"][0] for c in CASES])
+    assert ov.min() < 55 < ov.max()
