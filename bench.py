@@ -179,6 +179,18 @@ def other_configs(sc, dev) -> dict:
         out["v2_path_" + tag] = {"frames": n, "frame": [hh, ww, 3], "ms": round(ms_all, 3), "frames_per_s": n / (ms_all * 1e-3),
                                  "preprocess_multi_ms": round(ms_pre, 3), "grids_found": int((r["found"] == 1).sum().item())}
         del batch, clean, r
+    # the step after the path: batched solve of recognised boards, puzzles of mixed difficulty
+    from svb200 import frames as _F  # noqa: F401
+    rng = np.random.default_rng(9)
+    base = np.array([[(3 * (r % 3) + r // 3 + c) % 9 + 1 for c in range(9)] for r in range(9)], np.uint8)
+    grids = np.stack([(rng.permutation(9) + 1).astype(np.uint8)[base - 1].reshape(-1) for _ in range(16384)])
+    for g_ in grids:
+        g_[rng.permutation(81)[: int(rng.integers(40, 58))]] = 0
+    gd = torch.from_numpy(grids).to(dev)
+    ms = timed(lambda: sc.solve_batch(gd), 2)
+    _, stt = sc.solve_batch(gd)
+    out["solve_batch"] = {"puzzles": len(grids), "ms": round(ms, 3), "puzzles_per_s": len(grids) / (ms * 1e-3),
+                          "solved": int((stt == 1).sum().item())}
     torch.cuda.empty_cache()
     return out
 

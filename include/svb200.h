@@ -210,6 +210,14 @@ int svb_scan_batch_v2(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uin
                       uint8_t *alt_digits, float *alt_conf, float *logits, int32_t *corners, uint8_t *found, uint8_t *info,
                       double *quality, double min_quality_score, void *stream);
 
+/* ---- after the path: solve_sudoku (solver/src/sudoku.c:72-87), batched -------------------------------------- */
+/* Replaces run_solver's one-subprocess-per-image call (pipeline/run.py:163-202) for n recognised boards at once.
+ * grids: uint8 [n][81], 0 = empty (the digits output of svb_scan_batch_*); solutions: uint8 [n][81] (the input grid
+ * when the puzzle is not solved, as run_solver returns); status: int8 [n] = 1 SOLVE_SUCCESS, 0 SOLVE_NOSOLUTION,
+ * -1 SOLVE_INVALID (solver/include/sudoku.h:12-15).  Same search order as the reference: identical results for
+ * every input, including grids with several solutions. */
+int svb_solve_batch(svb_ctx *ctx, const uint8_t *grids, int n, uint8_t *solutions, int8_t *status, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

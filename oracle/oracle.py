@@ -316,3 +316,32 @@ def preprocess_multi(bgr):
     assert rc == 0, "frame sides must divide by 8"
     return dict(binary=o[0], gray=o[1], enhanced=o[2], illumination_normalized=o[3], has_glare=bool(info[0]),
                 has_shadow=bool(info[1]), method_used=METHODS[info[2]], otsu_level=int(info[3]), scores=list(scores))
+
+
+# ---- S1: solver/src/sudoku.c ------------------------------------------------------------------------------
+def solve_sudoku(grid):
+    """solve_sudoku (solver/src/sudoku.c:72) restated: grid (81,) or (9,9) uint8 -> (status, solution (same shape))."""
+    g = _u8(grid)
+    out = np.empty_like(g)
+    lib().svo_solve_sudoku.restype = C.c_int
+    st = lib().svo_solve_sudoku(_p(g), _p(out))
+    return int(st), out
+
+
+_ref_solver = None
+
+
+def ref_solver_available() -> bool:
+    return os.path.exists(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libref_solver.so"))
+
+
+def ref_solve_sudoku(grid):
+    """The REFERENCE's own solve_sudoku, compiled from its sources by oracle/Makefile (kind = "reference")."""
+    global _ref_solver
+    if _ref_solver is None:
+        _ref_solver = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libref_solver.so"))
+        _ref_solver.solve_sudoku.restype = C.c_int
+    g = np.ascontiguousarray(np.asarray(grid).reshape(9, 9), dtype=np.int32)
+    work = g.copy()
+    st = _ref_solver.solve_sudoku(work.ctypes.data_as(C.c_void_p))
+    return int(st), (work if st == 1 else g).astype(np.uint8).reshape(np.asarray(grid).shape)

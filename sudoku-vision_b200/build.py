@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "svb200", "lib")
 OUT = os.path.join(OUT_DIR, "libsvb200.so")
-SOURCES = ["c_api.cu", "preprocess.cu", "preprocess_v2.cu", "contour.cu", "cells.cu", "digitcnn.cu", "digitcnn_tc.cu", "digitcnn_v3.cu", "digitcnn_v3_tc.cu"]
+SOURCES = ["c_api.cu", "preprocess.cu", "preprocess_v2.cu", "contour.cu", "cells.cu", "digitcnn.cu", "digitcnn_tc.cu", "digitcnn_v3.cu", "digitcnn_v3_tc.cu", "solver.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=true",  # exact-order arithmetic is spelled with __fmaf_rn/__fmul_rn/__fadd_rn, which never contract

@@ -63,6 +63,7 @@ int preprocess_multi_run(svb_ctx *, const uint8_t *, const uint8_t *, int, int, 
 int v2_stage(svb_ctx *, int, const uint8_t *, int, int, int, int, uint8_t *, uint8_t *, cudaStream_t);
 int launch_grid_quality(svb_ctx *, const uint8_t *, int, int, int, int, const uint8_t *, const int32_t *, const uint8_t *, double *, cudaStream_t);
 int launch_quality_gate(svb_ctx *, const double *, uint8_t *, int, double, cudaStream_t);
+int launch_solve(svb_ctx *, const uint8_t *, int, uint8_t *, int8_t *, cudaStream_t);
 int launch_top3(svb_ctx *, const float *, const uint8_t *, long long, uint8_t *, float *, uint8_t *, float *, cudaStream_t);
 bool digitcnn_v3_loaded(const svb_ctx *);
 int launch_mask_not_found(svb_ctx *, const uint8_t *, int, uint8_t *, float *, cudaStream_t);
@@ -408,6 +409,12 @@ API int svb_scan_batch_v2(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w,
         if (rc) return rc;
     }
     return SVB_OK;
+}
+
+API int svb_solve_batch(svb_ctx *ctx, const uint8_t *grids, int n, uint8_t *solutions, int8_t *status, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(grids && solutions && status && n > 0, SVB_ERR_INVALID, "svb_solve_batch: bad arguments");
+    return launch_solve(ctx, grids, n, solutions, status, (cudaStream_t)stream);
 }
 
 // Host-buffer path.  The frames are split into chunks that alternate between two worker contexts, each with

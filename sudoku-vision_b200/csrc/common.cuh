@@ -53,7 +53,7 @@ struct DigitCnnWeights {
 
 namespace svb {
 // context-owned scratch arenas, one per purpose so that chained stages never alias
-enum Arena { AR_ADAPT = 0, AR_STAGE, AR_CONTOUR, AR_HOMOG, AR_CNN, AR_PATH, AR_V2, AR_V2T, AR_QUAL, AR_COUNT };
+enum Arena { AR_ADAPT = 0, AR_STAGE, AR_CONTOUR, AR_HOMOG, AR_CNN, AR_PATH, AR_V2, AR_V2T, AR_QUAL, AR_SOLVE, AR_COUNT };
 }
 
 struct svb_ctx {

@@ -377,6 +377,18 @@ class Scanner:
                    "svb_scan_batch_v2")
         return out
 
+    def solve_batch(self, grids):
+        """solve_sudoku (solver/src/sudoku.c:72) for a batch: grids (n,81) or (n,9,9) uint8 CUDA, 0 = empty ->
+        (solutions same shape, status (n,) int8: 1 solved, 0 no solution, -1 invalid)."""
+        torch = _torch()
+        if not (grids.is_cuda and grids.dtype == torch.uint8 and grids.is_contiguous() and grids.numel() % 81 == 0):
+            raise ValueError("solve_batch: expected contiguous uint8 CUDA grids with 81 cells each")
+        n = grids.numel() // 81
+        sol = torch.empty_like(grids)
+        status = torch.empty((n,), dtype=torch.int8, device=grids.device)
+        _lib.check(self.lib.svb_solve_batch(self._h, _ptr(grids), n, _ptr(sol), _ptr(status), self._stream()), "svb_solve_batch")
+        return sol, status
+
     def scan_batch_host(self, frames: np.ndarray, out: dict | None = None) -> dict:
         """Same through HOST buffers (numpy or pinned torch CPU tensors): H2D + path + D2H, synchronous."""
         torch = _torch()

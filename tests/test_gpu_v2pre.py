@@ -342,3 +342,26 @@ def test_grid_quality_dropin(golden, v2pre):
         assert GQ.get_user_feedback(q) == str(g[c + "_ref_feedback"])
     with pytest.raises(NotImplementedError):
         GQ.assess_grid_quality(v2pre["a_plain_bgr"], v2pre["a_plain_ref_binary"], g["a_plain_corners"] + 0.5)
+
+
+def test_batched_solver_vs_reference_golden(scanner, oracle, golden):
+    """svb_solve_batch: same status and the same solution (also when several exist) as the reference's solver."""
+    g = golden("solver")
+    sol, st = scanner.solve_batch(_t(g["grids"]))
+    assert np.array_equal(_np(st), g["ref_status"])
+    assert np.array_equal(_np(sol), g["ref_solutions"])
+    # a large ragged batch against the oracle: 3000 puzzles incl. (9,9)-shaped input
+    rng = np.random.default_rng(5)
+    base = np.array([[(3 * (r % 3) + r // 3 + c) % 9 + 1 for c in range(9)] for r in range(9)], np.uint8)
+    grids = np.stack([(rng.permutation(9) + 1).astype(np.uint8)[base - 1] for _ in range(3000)])
+    for k in range(len(grids)):
+        flat = grids[k].reshape(-1)
+        flat[rng.permutation(81)[: int(rng.integers(35, 60))]] = 0
+        if k % 7 == 0:
+            idx = np.flatnonzero(flat)
+            flat[idx[-1]] = flat[idx[-1]] % 9 + 1
+    sol, st = scanner.solve_batch(_t(grids))
+    assert sol.shape == (3000, 9, 9)
+    for k in range(0, 3000, 13):
+        want_st, want = oracle.solve_sudoku(grids[k])
+        assert int(_np(st)[k]) == want_st and np.array_equal(_np(sol)[k], want)
