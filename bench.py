@@ -325,7 +325,7 @@ def main():
                        "l2": f"inputs {Fn * H * W * 3 / 1e9:.1f} GB per step >> 126 MB L2 (no flush needed)",
                        "sharding": f"image-sharded x{world}, no data-path collective", "grids_found": f"{found}/{Fn}"},
             "e2e": {"value": En * world * args.steps / e2e_s, "unit": "frames/s",
-                    "h2d_bytes_per_step": En * H * W * 3, "d2h_bytes_per_step": En * (81 + 81 * 4 + 32 + 1),
+                    "h2d_bytes_per_step": En * H * W * 3 * world, "d2h_bytes_per_step": En * (81 + 81 * 4 + 32 + 1) * world,
                     "frames_per_step": En, "matches_device_path": same},
             "gpu_launches": int(launches),
             "stage_ms_per_step": {k: round(v, 4) for k, v in stage_ms.items()},

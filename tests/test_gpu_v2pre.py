@@ -365,3 +365,22 @@ def test_batched_solver_vs_reference_golden(scanner, oracle, golden):
     for k in range(0, 3000, 13):
         want_st, want = oracle.solve_sudoku(grids[k])
         assert int(_np(st)[k]) == want_st and np.array_equal(_np(sol)[k], want)
+
+
+def test_v2_preprocess_on_a_reference_photo(scanner, oracle):
+    """One of the reference's own photos (2736 x 3648: k = 365 illumination kernel, two 2048-column strips) through
+    preprocess_for_grid_detection, against the oracle.  Needs the staged reference copy (baseline/_ref, git-ignored but
+    shipped to the GPU box) and cv2 for the JPEG decode only."""
+    import os
+
+    cv2 = pytest.importorskip("cv2")
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "sudoku-vision", "data",
+                     "test_images", "sample_3.jpg")
+    if not os.path.exists(p):
+        pytest.skip("staged reference copy not present")
+    img = cv2.imread(p)
+    assert img.shape[0] % 8 == 0 and img.shape[1] % 8 == 0
+    m, info = scanner.preprocess_v2(_t(img[None]))
+    want, glare, shadow = oracle.preprocess_v2(img)
+    assert np.array_equal(_np(m)[0], want)
+    assert [bool(x) for x in _np(info)[0, :2]] == [glare, shadow]
