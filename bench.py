@@ -96,15 +96,20 @@ def cpu_leg(frames_np, seconds: float, mode: str) -> dict:
         fp = os.path.join(td, "frames.npy")
         np.save(fp, frames_np)
         cmd = [sys.executable, os.path.join(ROOT, "oracle", "cpu_bench.py"), "--frames", fp, "--weights",
-               default_weights_path(), "--seconds", str(seconds), "--mode", mode]
-        out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+               default_weights_path(), "--seconds", str(seconds), "--mode", mode,
+               "--ref-root", os.path.join(ROOT, "baseline", "_ref", "sudoku-vision")]
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     if out.returncode != 0:
         raise RuntimeError("cpu_bench failed: " + out.stderr[-2000:])
     r = json.loads(out.stdout.strip().splitlines()[-1])
-    return {"value": r["frames_per_s"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
+    what = ("the UNMODIFIED reference (baseline/_ref/sudoku-vision): pipeline/run.py's own preprocess / find_grid_contour / "
+            "warp / extract_cells / predict_cells on cv2 + torch CPU" if r.get("kind") == "reference"
+            else "oracle/ref_port.py = the reference's cv2+torch-CPU call sequence")
+    return {"value": r["frames_per_s"], "unit": "frames/s", "cores": r["cores"], "kind": r.get("kind", "port"),
             "sample": f"{r['frames']} synthetic 1080p frames in {r['seconds']:.1f} s, {r['mode']} mode "
-                      f"({r['cores']} worker(s) on {r['host_cpus']} host CPUs), oracle/ref_port.py = the reference's "
-                      f"cv2+torch-CPU call sequence with the model load hoisted; grids found {r['found']}/{r['frames']}"}
+                      f"({r['cores']} worker(s) on {r['host_cpus']} host CPUs), {what}, model load hoisted; "
+                      f"grids found {r['found']}/{r['frames']}"}
 
 
 def host_frames(n_unique: int, seed0: int = 31000):
