@@ -12,6 +12,7 @@
 //           row pass = FMA chain left to right, column pass = k5*c then fma(k[5+j], up+down, acc)
 //   mask  = 255 if blur - mean <= -2 (BINARY_INV) / > -2 (BINARY)
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace svb {
 
@@ -557,6 +558,377 @@ fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ m
 }  // namespace k1
 
 // ================================================================================================
+// K1w — the same fused pass, re-cut so that a WARP is the unit of work and nothing is exchanged through
+// shared memory between threads: no CTA barrier anywhere in the loop.
+//
+// A warp owns a strip of 256 gray columns (240 output columns + an 8-px halo each side = one halo lane on
+// each side) and streams down its row segment 4 rows per iteration; every lane owns 8 adjacent columns.
+//   * raw BGR rows (272 px, 16-byte aligned at both ends) arrive by TMA bulk copies, two 4-row stages per warp;
+//   * gray: 16 dp2a on the raw words with the weights doubled, so the result is byte 2 of the sum (no shifts,
+//     no byte alignment: the dp2a halves fall on the pixel boundaries of the 24-byte group);
+//   * horizontal 5-tap: dp4a on funnel-shifted byte windows; the neighbour words come by warp shuffle;
+//   * vertical 5-tap: the binomial cascade (1 1)^4 on packed u16 lanes with four carried partial rows
+//     (16 adds per 8 columns x 4 rows instead of 40), rounding folded into the dp4a accumulator;
+//   * 11-tap row pass: two image rows per packed FMA (fma.rn.f32x2), neighbours by shuffle;
+//   * 11-tap column pass over a thread-private 12-row ring in shared memory, rint by the magic add, threshold
+//     per 16-bit lane and PRMT's sign-replicate mode to expand the four decision bits to 0x00/0xff bytes.
+// Borders: REFLECT_101 of the gray image in y is just the TMA source row; in x it is one PRMT on the edge lane;
+// REPLICATE of the blurred image is a byte broadcast on the edge lane (x), a one-off ring fill (top) and a saved
+// row (bottom).  Arithmetic order is unchanged, so the mask stays bit-exact.
+// ================================================================================================
+namespace k1w {
+using k1::mbar_expect_tx;
+using k1::mbar_init;
+using k1::mbar_wait;
+using k1::tma_load_1d;
+using k1::u8f;
+
+constexpr int CPL = 8;            // columns per lane
+constexpr int GW = 32 * CPL;      // 256 gray columns per strip
+constexpr int TW = GW - 2 * CPL;  // 240 output columns per strip (lanes 1..30)
+constexpr int LPAD = 16;          // staged pixels left of the first output column: keeps every TMA source 16-B aligned
+constexpr int SW = TW + 2 * LPAD; // 272 staged pixels per row
+constexpr int R = 4;
+constexpr int NSTAGE = 2;
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float4 lds128(const float4 *p) {  // a shared-memory load the compiler will not forward from registers
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(k1::smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+template <int CH>
+struct __align__(128) WarpSmem {
+    float4 rp[12][2][30];                // row-pass ring: [row % 12][column group][lane - 1], thread-private columns
+    uint8_t raw[NSTAGE][R][SW * CH];     // TMA destination
+    unsigned long long full[NSTAGE];     // mbarriers
+};
+
+// 11-tap row pass of two blurred rows (a, b) for this lane's 8 columns; packed lanes = (row a, row b)
+__device__ __forceinline__ void rowpass_pair(const uint32_t a0, const uint32_t a1, const uint32_t b0, const uint32_t b1,
+                                             const bool edge_strip, const bool left_lane, const bool right_lane, float2 (&o)[8]) {
+    uint32_t la0 = __shfl_up_sync(FULL, a0, 1), la1 = __shfl_up_sync(FULL, a1, 1);
+    uint32_t ra0 = __shfl_down_sync(FULL, a0, 1), ra1 = __shfl_down_sync(FULL, a1, 1);
+    uint32_t lb0 = __shfl_up_sync(FULL, b0, 1), lb1 = __shfl_up_sync(FULL, b1, 1);
+    uint32_t rb0 = __shfl_down_sync(FULL, b0, 1), rb1 = __shfl_down_sync(FULL, b1, 1);
+    if (edge_strip) {  // BORDER_REPLICATE of the blurred row in x
+        if (left_lane) {
+            la0 = la1 = __byte_perm(a0, 0, 0x0000);
+            lb0 = lb1 = __byte_perm(b0, 0, 0x0000);
+        }
+        if (right_lane) {
+            ra0 = ra1 = __byte_perm(a1, 0, 0x3333);
+            rb0 = rb1 = __byte_perm(b1, 0, 0x3333);
+        }
+    }
+    float2 f[18];  // f[i] = column (8 lane - 5 + i) of (row a, row b)
+    f[0] = make_float2(u8f(la0, 3), u8f(lb0, 3));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        f[1 + k] = make_float2(u8f(la1, k), u8f(lb1, k));
+        f[5 + k] = make_float2(u8f(a0, k), u8f(b0, k));
+        f[9 + k] = make_float2(u8f(a1, k), u8f(b1, k));
+        f[13 + k] = make_float2(u8f(ra0, k), u8f(rb0, k));
+    }
+    f[17] = make_float2(u8f(ra1, 0), u8f(rb1, 0));
+    const float2 k0 = make_float2(SVB_G11_0, SVB_G11_0), k1 = make_float2(SVB_G11_1, SVB_G11_1),
+                 k2 = make_float2(SVB_G11_2, SVB_G11_2), k3 = make_float2(SVB_G11_3, SVB_G11_3),
+                 k4 = make_float2(SVB_G11_4, SVB_G11_4), k5 = make_float2(SVB_G11_5, SVB_G11_5);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float2 acc = __fmul2_rn(k0, f[j]);
+        acc = __ffma2_rn(k1, f[j + 1], acc);
+        acc = __ffma2_rn(k2, f[j + 2], acc);
+        acc = __ffma2_rn(k3, f[j + 3], acc);
+        acc = __ffma2_rn(k4, f[j + 4], acc);
+        acc = __ffma2_rn(k5, f[j + 5], acc);
+        acc = __ffma2_rn(k4, f[j + 6], acc);
+        acc = __ffma2_rn(k3, f[j + 7], acc);
+        acc = __ffma2_rn(k2, f[j + 8], acc);
+        acc = __ffma2_rn(k1, f[j + 9], acc);
+        acc = __ffma2_rn(k0, f[j + 10], acc);
+        o[j] = acc;
+    }
+}
+
+// 11-tap column pass + rint + THRESH_BINARY_INV for 4 columns x 4 output rows; Rw = row-pass rows y0-5 .. y0+8
+__device__ __forceinline__ void colpass_group(const float4 (&Rw)[14], const uint32_t (&src)[4], uint32_t (&out)[4]) {
+    const float2 k0 = make_float2(SVB_G11_0, SVB_G11_0), k1 = make_float2(SVB_G11_1, SVB_G11_1),
+                 k2 = make_float2(SVB_G11_2, SVB_G11_2), k3 = make_float2(SVB_G11_3, SVB_G11_3),
+                 k4 = make_float2(SVB_G11_4, SVB_G11_4), k5 = make_float2(SVB_G11_5, SVB_G11_5);
+    const float2 magic = make_float2(12582912.0f, 12582912.0f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 c = Rw[i + 5];
+        float2 aL = __fmul2_rn(k5, make_float2(c.x, c.y)), aH = __fmul2_rn(k5, make_float2(c.z, c.w));
+#pragma unroll
+        for (int j = 1; j <= 5; ++j) {
+            const float4 u = Rw[i + 5 + j], d = Rw[i + 5 - j];
+            const float2 kk = (j == 1) ? k4 : (j == 2) ? k3 : (j == 3) ? k2 : (j == 4) ? k1 : k0;
+            aL = __ffma2_rn(kk, __fadd2_rn(make_float2(u.x, u.y), make_float2(d.x, d.y)), aL);
+            aH = __ffma2_rn(kk, __fadd2_rn(make_float2(u.z, u.w), make_float2(d.z, d.w)), aH);
+        }
+        // rint via the 1.5 * 2^23 magic add: the low byte of the float's bits is the rounded mean (0..255)
+        const float2 mL = __fadd2_rn(aL, magic), mH = __fadd2_rn(aH, magic);
+        const uint32_t m_even = __byte_perm(__float_as_uint(mL.x), __float_as_uint(mH.x), 0x5410);  // mean0 | mean2 << 16
+        const uint32_t m_odd = __byte_perm(__float_as_uint(mL.y), __float_as_uint(mH.y), 0x5410);   // mean1 | mean3 << 16
+        const uint32_t s_even = src[i] & 0x00FF00FFu, s_odd = __byte_perm(src[i], 0, 0x4341);
+        // 255 iff src - mean <= -2  <=>  mean + 0x7ffe - src has bit 15 set, per 16-bit lane
+        const uint32_t d_even = m_even + 0x7FFE7FFEu - s_even, d_odd = m_odd + 0x7FFE7FFEu - s_odd;
+        // PRMT sign-replicate (selector bit 3): byte k of the mask = sign of the high byte of pixel k's lane
+        out[i] = prmt(d_even, d_odd, 0xFBD9u);
+    }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(32, 12)
+fused_preprocess_warp_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ mask, int h, int w, int rows_per_seg) {
+    // one warp per CTA (12 resident per SM): everything the TMA issue needs is CTA-uniform, so it stays on the uniform datapath
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    WarpSmem<CH> &sm = *reinterpret_cast<WarpSmem<CH> *>(smem_raw);
+    const int lane = threadIdx.x;
+    const int strip = blockIdx.x, seg = blockIdx.y, fr = blockIdx.z;
+
+    const int X0 = strip * TW;                  // first output column
+    const int xs = X0 - LPAD;                   // first staged column (multiple of 16; negative in strip 0)
+    const int ys = seg * rows_per_seg, ye = min(ys + rows_per_seg, h);  // output rows [ys, ye)
+    const long long frame_px = (long long)h * w;
+    const uint8_t *frame = src + (long long)fr * frame_px * CH;
+    uint8_t *out = mask + (long long)fr * frame_px;
+
+    const int col_lo = max(xs, 0), col_hi = min(xs + SW, w);
+    const uint32_t row_bytes = (uint32_t)(col_hi - col_lo) * (uint32_t)CH;
+    const int dst_off = (col_lo - xs) * CH;
+
+    const int c0 = X0 - CPL + CPL * lane;       // this lane's first column
+    const bool edge_strip = (X0 == 0) || (X0 + TW + CPL >= w);
+    const bool left_lane = (c0 == 0), right_lane = (c0 + CPL == w);
+    const bool lane_mid = (lane >= 1) && (lane <= 30);  // lanes 0 and 31 only carry the halo columns
+    const bool lane_out = lane_mid && (c0 < w);
+    const int lm = lane_mid ? lane - 1 : 0;
+    const long long wl = w;
+
+    // block q handles gray rows 4q+2 .. 4q+5 -> blurred / row-pass rows 4q .. 4q+3 -> output rows 4q-5 .. 4q-2
+    const int b_first = max(ys - 5, 0);                 // first blurred row this segment needs
+    const int q_first = (b_first - 4) >> 2;             // its block - 1 (the first block only warms the 5-tap cascade)
+    const int q_last = (ye + 1 + 3) >> 2;               // 4q-2 >= ye-1
+    const int nblk = q_last - q_first + 1;
+
+    if (lane == 0) {
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&sm.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const long long pitch = (long long)w * CH;          // bytes per source row
+    const uint8_t *frame_lo = frame + (long long)col_lo * CH;
+    auto issue = [&](int k) {  // lane 0: stage block k's four gray rows (BORDER_REFLECT_101 in y = the source row)
+        if (k >= nblk) return;
+        const int stage = k & 1, r0 = 4 * (q_first + k) + 2;
+        mbar_expect_tx(&sm.full[stage], row_bytes * R);
+        uint8_t *dst = &sm.raw[stage][0][dst_off];
+        if (r0 >= 0 && r0 + R <= h) {  // interior block: four consecutive rows
+            const uint8_t *g = frame_lo + (long long)r0 * pitch;
+#pragma unroll
+            for (int r = 0; r < R; ++r) tma_load_1d(dst + r * (SW * CH), g + r * pitch, row_bytes, &sm.full[stage]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                int v = r0 + r;
+                v = (v < 0) ? -v : v;
+                v = (v >= h) ? 2 * (h - 1) - v : v;
+                v = clampi(v, 0, h - 1);
+                tma_load_1d(dst + r * (SW * CH), frame_lo + (long long)v * pitch, row_bytes, &sm.full[stage]);
+            }
+        }
+    };
+    if (lane == 0) {
+        issue(0);
+        issue(1);
+    }
+
+    constexpr uint32_t C_BG = 7470u | (38470u << 16), C_R = 19596u, C_B = 7470u << 16, C_GR = 38470u | (19596u << 16), RND = 32768u;
+    uint32_t cH[4], cA[4], cB[4], cC[4];  // cascade carries: H(N-1), a(N-2), b(N-3), c(N-4) as 4 x (u16 x 2)
+    uint32_t P[4][2], T[2] = {0u, 0u};    // blurred rows of the previous block and the row before them (threshold source)
+    uint32_t sv[2] = {0u, 0u};            // blurred row h-1 (BORDER_REPLICATE below the image)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        cH[j] = cA[j] = cB[j] = cC[j] = 0u;
+        P[j][0] = P[j][1] = 0u;
+    }
+
+    uint8_t *optr = out + c0 + (long long)(4 * q_first - 5) * wl;  // this lane's 8 bytes of output row 4q-5
+    for (int k = 0; k < nblk; ++k, optr += 4 * wl) {
+        const int q = q_first + k, stage = k & 1;
+        mbar_wait(&sm.full[stage], (uint32_t)((k >> 1) & 1));
+        // ---- phase 1: raw -> gray, 8 columns = 2 packed words per row ------------------------------------------
+        uint32_t G[R][2];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (CH == 1) {
+                const uint2 v = *reinterpret_cast<const uint2 *>(&sm.raw[stage][r][LPAD - CPL + CPL * lane]);
+                G[r][0] = v.x;
+                G[r][1] = v.y;
+            } else {
+                const uint2 *p = reinterpret_cast<const uint2 *>(&sm.raw[stage][r][3 * (LPAD - CPL + CPL * lane)]);
+                const uint2 v0 = p[0], v1 = p[1], v2 = p[2];
+                const uint32_t ww[6] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const uint32_t w0 = ww[3 * hh], w1 = ww[3 * hh + 1], w2 = ww[3 * hh + 2];
+                    const uint32_t g0 = __dp2a_hi(C_R, w0, __dp2a_lo(C_BG, w0, RND));
+                    const uint32_t g1 = __dp2a_lo(C_GR, w1, __dp2a_hi(C_B, w0, RND));
+                    const uint32_t g2 = __dp2a_lo(C_R, w2, __dp2a_hi(C_BG, w1, RND));
+                    const uint32_t g3 = __dp2a_hi(C_GR, w2, __dp2a_lo(C_B, w2, RND));
+                    G[r][hh] = __byte_perm(__byte_perm(g0, g1, 0x0062), __byte_perm(g2, g3, 0x0062), 0x5410);
+                }
+            }
+        }
+        __syncwarp();  // every lane has read this stage: refill it with the block after next
+        if (lane == 0) issue(k + 2);
+
+        // ---- phase 2: horizontal 5-tap (dp4a on byte windows), +8 per row sum = the +128 rounding of the 5x5 --------
+        uint32_t Hn[R][4];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            uint32_t gl = __shfl_up_sync(FULL, G[r][1], 1), gr = __shfl_down_sync(FULL, G[r][0], 1);
+            if (edge_strip) {  // BORDER_REFLECT_101 of the gray row in x: columns -2,-1 = 2,1 ; w, w+1 = w-2, w-3
+                if (left_lane) gl = __byte_perm(G[r][0], 0, 0x1200);
+                if (right_lane) gr = __byte_perm(G[r][1], 0, 0x0012);
+            }
+            const uint32_t g0 = G[r][0], g1 = G[r][1];
+            uint32_t win[9];  // win[s + 2] = bytes of columns s .. s+3 (relative to this lane's first column)
+            win[0] = __funnelshift_r(gl, g0, 16);
+            win[1] = __funnelshift_r(gl, g0, 24);
+            win[2] = g0;
+            win[3] = __funnelshift_r(g0, g1, 8);
+            win[4] = __funnelshift_r(g0, g1, 16);
+            win[5] = __funnelshift_r(g0, g1, 24);
+            win[6] = g1;
+            win[7] = __funnelshift_r(g1, gr, 8);
+            win[8] = __funnelshift_r(g1, gr, 16);
+            uint32_t hs[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hs[j] = __dp4a(win[j + 1], 0x01000000u, __dp4a(win[j], 0x04060401u, 8u));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Hn[r][j] = __byte_perm(hs[2 * j], hs[2 * j + 1], 0x5410);
+        }
+        // ---- phase 3: vertical 5-tap by the binomial cascade on packed u16 lanes -> blurred rows 4q .. 4q+3 ----------
+        uint32_t B[4][2];
+        {
+            uint32_t dd[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t am1 = cH[j] + Hn[0][j], a0 = Hn[0][j] + Hn[1][j], a1 = Hn[1][j] + Hn[2][j], a2 = Hn[2][j] + Hn[3][j];
+                const uint32_t bm2 = cA[j] + am1, bm1 = am1 + a0, b0 = a0 + a1, b1 = a1 + a2;
+                const uint32_t cm3 = cB[j] + bm2, cm2 = bm2 + bm1, cm1 = bm1 + b0, cc0 = b0 + b1;
+                dd[0][j] = cC[j] + cm3;
+                dd[1][j] = cm3 + cm2;
+                dd[2][j] = cm2 + cm1;
+                dd[3][j] = cm1 + cc0;
+                cH[j] = Hn[3][j];
+                cA[j] = a2;
+                cB[j] = b1;
+                cC[j] = cc0;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                B[i][0] = __byte_perm(dd[i][0], dd[i][1], 0x7531);
+                B[i][1] = __byte_perm(dd[i][2], dd[i][3], 0x7531);
+            }
+        }
+        if (4 * q + 3 >= h - 1) {  // BORDER_REPLICATE of the blurred image below the last row
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int b = 4 * q + i;
+                if (b == h - 1) {
+                    sv[0] = B[i][0];
+                    sv[1] = B[i][1];
+                } else if (b > h - 1) {
+                    B[i][0] = sv[0];
+                    B[i][1] = sv[1];
+                }
+            }
+        }
+        // ---- phase 4: horizontal 11-tap of the four new rows ---------------------------------------------------------
+        const int s0 = (q + 3) % 3, s1 = (q + 5) % 3, s2 = (q + 4) % 3;  // ring slots of blocks q (= q-3), q-1, q-2
+        float4 (*rp0)[2][30] = &sm.rp[4 * s0], (*rp1)[2][30] = &sm.rp[4 * s1], (*rp2)[2][30] = &sm.rp[4 * s2];
+        const bool do_out = (4 * q - 5 <= ye - 1) && (4 * q - 2 >= ys);
+        float4 old[2][2];  // rows 4q-10, 4q-9: still in the slot this block overwrites
+        if (do_out) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                old[0][g] = rp0[2][g][lm];
+                old[1][g] = rp0[3][g][lm];
+            }
+        }
+        float4 RPn[4][2];
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+            float2 o[8];
+            rowpass_pair(B[2 * pr][0], B[2 * pr][1], B[2 * pr + 1][0], B[2 * pr + 1][1], edge_strip, left_lane, right_lane, o);
+            RPn[2 * pr][0] = make_float4(o[0].x, o[1].x, o[2].x, o[3].x);
+            RPn[2 * pr][1] = make_float4(o[4].x, o[5].x, o[6].x, o[7].x);
+            RPn[2 * pr + 1][0] = make_float4(o[0].y, o[1].y, o[2].y, o[3].y);
+            RPn[2 * pr + 1][1] = make_float4(o[4].y, o[5].y, o[6].y, o[7].y);
+        }
+        if (lane_mid) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                rp0[i][0][lm] = RPn[i][0];
+                rp0[i][1][lm] = RPn[i][1];
+            }
+            if (q == 0) {  // BORDER_REPLICATE above the first row: row-pass rows -5 .. -1 = row 0
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    sm.rp[4 * 1 + 3][g][lm] = RPn[0][g];  // row -5: block -2 -> slot 1
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) sm.rp[4 * 2 + i][g][lm] = RPn[0][g];  // rows -4 .. -1: block -1 -> slot 2
+                }
+            }
+        }
+        // ---- phase 5: vertical 11-tap, rint, threshold -> output rows 4q-5 .. 4q-2 ------------------------------------
+        if (do_out) {
+            uint32_t o32[2][4];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                float4 Rw[14];  // row-pass rows 4q-10 .. 4q+3
+                Rw[0] = old[0][g];
+                Rw[1] = old[1][g];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    Rw[2 + j] = rp2[j][g][lm];
+                    Rw[6 + j] = rp1[j][g][lm];
+                    Rw[10 + j] = lds128(&rp0[j][g][lm]);  // this lane's own store above, read back as column pairs
+                }
+                const uint32_t srcw[4] = {T[g], P[0][g], P[1][g], P[2][g]};
+                colpass_group(Rw, srcw, o32[g]);
+            }
+            uint8_t *orow = optr;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (lane_out && (unsigned)(4 * q - 5 + i - ys) < (unsigned)(ye - ys))
+                    *reinterpret_cast<uint2 *>(orow) = make_uint2(o32[0][i], o32[1][i]);
+                orow += wl;
+            }
+        }
+        T[0] = P[3][0];
+        T[1] = P[3][1];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            P[i][0] = B[i][0];
+            P[i][1] = B[i][1];
+        }
+    }
+}
+}  // namespace k1w
+
+// ================================================================================================
 // Host launchers
 // ================================================================================================
 int launch_gray(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *gray, cudaStream_t st) {
@@ -587,9 +959,30 @@ int launch_adaptive(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, int i
 
 bool fused_preprocess_supported(int h, int w) { return (w % 16 == 0) && w >= 64 && h >= 8; }
 
+template <int CH>
+static int launch_k1w(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uint8_t *mask, cudaStream_t st) {
+    using namespace k1w;
+    const int smem = (int)sizeof(WarpSmem<CH>);
+    SVB_CUDA_OK(cudaFuncSetAttribute(fused_preprocess_warp_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int nstrips = (w + TW - 1) / TW;
+    // row segments: enough warps for ~8 waves of the 12 resident warps per SM, segments no shorter than 64 rows
+    const long long strips = (long long)nstrips * n;
+    long long want = (8LL * 12 * ctx->sm_count + strips - 1) / strips;
+    int nseg = (int)max(1LL, min(want, (long long)(h / 64)));
+    int rows_per_seg = (((h + nseg - 1) / nseg) + 3) & ~3;
+    nseg = (h + rows_per_seg - 1) / rows_per_seg;
+    if (n > 65535 || nseg > 65535) return SVB_ERR_UNSUPPORTED;
+    dim3 grid(nstrips, nseg, n);
+    fused_preprocess_warp_kernel<CH><<<grid, 32, smem, st>>>(src, mask, h, w, rows_per_seg);
+    return check_launch(ctx, "fused_preprocess_warp_kernel");
+}
+
 // ch = 3: BGR frames (cv/preprocess.py:57-65); ch = 1: gray input, i.e. GaussianBlur 5 + adaptive threshold only
 // (the tail of cv/preprocess_v2.py:233-239)
 int launch_fused_preprocess(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uint8_t *mask, cudaStream_t st, int ch) {
+    static const bool legacy = getenv("SVB_K1_LEGACY") != nullptr;  // A/B switch: the CTA-per-strip kernel (k1::)
+    if (!legacy && (((uintptr_t)mask) & 7) == 0 && h >= 16)
+        return ch == 1 ? launch_k1w<1>(ctx, src, n, h, w, mask, st) : launch_k1w<3>(ctx, src, n, h, w, mask, st);
     using namespace k1;
     SVB_CUDA_OK(cudaFuncSetAttribute(fused_preprocess_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
     SVB_CUDA_OK(cudaFuncSetAttribute(fused_preprocess_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
