@@ -12,6 +12,7 @@
 //           row pass = FMA chain left to right, column pass = k5*c then fma(k[5+j], up+down, acc)
 //   mask  = 255 if blur - mean <= -2 (BINARY_INV) / > -2 (BINARY)
 #include "common.cuh"
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <stdlib.h>
 
 namespace svb {
@@ -597,6 +598,13 @@ __device__ __forceinline__ float4 lds128(const float4 *p) {  // a shared-memory 
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(k1::smem_u32(p)) : "memory");
     return v;
 }
+// one 2-D tiled TMA copy: R rows x ROWB bytes (as u32 elements) of the frame stack; out-of-range columns arrive as zeros
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int x, int y, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     k1::smem_u32(dst)),
+                 "l"(tm), "r"(x), "r"(y), "r"(k1::smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
@@ -605,8 +613,10 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 
 template <int CH>
 struct __align__(128) WarpSmem {
+    static constexpr int ROWB = SW * CH;                             // bytes per staged row
+    static constexpr int STAGEB = (R * ROWB + 127) / 128 * 128;      // tensor TMA wants 128-byte aligned destinations
     float4 rp[12][2][30];                // row-pass ring: [row % 12][column group][lane - 1], thread-private columns
-    uint8_t raw[NSTAGE][R][SW * CH];     // TMA destination
+    uint8_t raw[NSTAGE][STAGEB];         // TMA destination: R rows of ROWB bytes per stage
     unsigned long long full[NSTAGE];     // mbarriers
 };
 
@@ -688,7 +698,8 @@ __device__ __forceinline__ void colpass_group(const float4 (&Rw)[14], const uint
 
 template <int CH>
 __global__ void __launch_bounds__(32, 12)
-fused_preprocess_warp_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ mask, int h, int w, int rows_per_seg) {
+fused_preprocess_warp_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ mask, int h, int w, int rows_per_seg,
+                             const __grid_constant__ CUtensorMap tmap, int use_tmap) {
     // one warp per CTA (12 resident per SM): everything the TMA issue needs is CTA-uniform, so it stays on the uniform datapath
     extern __shared__ __align__(128) uint8_t smem_raw[];
     WarpSmem<CH> &sm = *reinterpret_cast<WarpSmem<CH> *>(smem_raw);
@@ -711,7 +722,7 @@ fused_preprocess_warp_kernel(const uint8_t *__restrict__ src, uint8_t *__restric
     const bool left_lane = (c0 == 0), right_lane = (c0 + CPL == w);
     const bool lane_mid = (lane >= 1) && (lane <= 30);  // lanes 0 and 31 only carry the halo columns
     const bool lane_out = lane_mid && (c0 < w);
-    const int lm = lane_mid ? lane - 1 : 0;
+    const int lm = min(max(lane - 1, 0), 29);  // halo lanes alias their neighbour's slot for loads (same address = broadcast) and never store
     const long long wl = w;
 
     // block q handles gray rows 4q+2 .. 4q+5 -> blurred / row-pass rows 4q .. 4q+3 -> output rows 4q-5 .. 4q-2
@@ -727,24 +738,24 @@ fused_preprocess_warp_kernel(const uint8_t *__restrict__ src, uint8_t *__restric
     __syncwarp();
     const long long pitch = (long long)w * CH;          // bytes per source row
     const uint8_t *frame_lo = frame + (long long)col_lo * CH;
+    const int tm_x = xs * CH / 4;                       // first staged column in u32 elements (negative in strip 0: zero-filled)
     auto issue = [&](int k) {  // lane 0: stage block k's four gray rows (BORDER_REFLECT_101 in y = the source row)
         if (k >= nblk) return;
         const int stage = k & 1, r0 = 4 * (q_first + k) + 2;
+        if (use_tmap && r0 >= 0 && r0 + R <= h) {  // interior block: one tiled copy of four consecutive rows
+            mbar_expect_tx(&sm.full[stage], (uint32_t)(R * WarpSmem<CH>::ROWB));
+            tma_load_2d(&sm.raw[stage][0], &tmap, tm_x, fr * h + r0, &sm.full[stage]);
+            return;
+        }
         mbar_expect_tx(&sm.full[stage], row_bytes * R);
-        uint8_t *dst = &sm.raw[stage][0][dst_off];
-        if (r0 >= 0 && r0 + R <= h) {  // interior block: four consecutive rows
-            const uint8_t *g = frame_lo + (long long)r0 * pitch;
+        uint8_t *dst = &sm.raw[stage][dst_off];
 #pragma unroll
-            for (int r = 0; r < R; ++r) tma_load_1d(dst + r * (SW * CH), g + r * pitch, row_bytes, &sm.full[stage]);
-        } else {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                int v = r0 + r;
-                v = (v < 0) ? -v : v;
-                v = (v >= h) ? 2 * (h - 1) - v : v;
-                v = clampi(v, 0, h - 1);
-                tma_load_1d(dst + r * (SW * CH), frame_lo + (long long)v * pitch, row_bytes, &sm.full[stage]);
-            }
+        for (int r = 0; r < R; ++r) {
+            int v = r0 + r;
+            v = (v < 0) ? -v : v;
+            v = (v >= h) ? 2 * (h - 1) - v : v;
+            v = clampi(v, 0, h - 1);
+            tma_load_1d(dst + r * WarpSmem<CH>::ROWB, frame_lo + (long long)v * pitch, row_bytes, &sm.full[stage]);
         }
     };
     if (lane == 0) {
@@ -771,11 +782,11 @@ fused_preprocess_warp_kernel(const uint8_t *__restrict__ src, uint8_t *__restric
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (CH == 1) {
-                const uint2 v = *reinterpret_cast<const uint2 *>(&sm.raw[stage][r][LPAD - CPL + CPL * lane]);
+                const uint2 v = *reinterpret_cast<const uint2 *>(&sm.raw[stage][r * WarpSmem<CH>::ROWB + LPAD - CPL + CPL * lane]);
                 G[r][0] = v.x;
                 G[r][1] = v.y;
             } else {
-                const uint2 *p = reinterpret_cast<const uint2 *>(&sm.raw[stage][r][3 * (LPAD - CPL + CPL * lane)]);
+                const uint2 *p = reinterpret_cast<const uint2 *>(&sm.raw[stage][r * WarpSmem<CH>::ROWB + 3 * (LPAD - CPL + CPL * lane)]);
                 const uint2 v0 = p[0], v1 = p[1], v2 = p[2];
                 const uint32_t ww[6] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
 #pragma unroll
@@ -959,6 +970,20 @@ int launch_adaptive(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, int i
 
 bool fused_preprocess_supported(int h, int w) { return (w % 16 == 0) && w >= 64 && h >= 8; }
 
+typedef CUresult (*tensor_map_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tensor_map_encode_fn tensor_map_encoder() {
+    static tensor_map_encode_fn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (tensor_map_encode_fn)p;
+    }();
+    return fn;
+}
+
 template <int CH>
 static int launch_k1w(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uint8_t *mask, cudaStream_t st) {
     using namespace k1w;
@@ -969,11 +994,26 @@ static int launch_k1w(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uin
     const long long strips = (long long)nstrips * n;
     long long want = (8LL * 12 * ctx->sm_count + strips - 1) / strips;
     int nseg = (int)max(1LL, min(want, (long long)(h / 64)));
+    if (const char *e = getenv("SVB_K1_NSEG")) nseg = max(1, min(atoi(e), h / 16));  // tuning knob
     int rows_per_seg = (((h + nseg - 1) / nseg) + 3) & ~3;
     nseg = (h + rows_per_seg - 1) / rows_per_seg;
     if (n > 65535 || nseg > 65535) return SVB_ERR_UNSUPPORTED;
+    // the frame stack as a 2-D tensor of u32 elements: [n*h rows][w*CH/4]; box = 4 rows x one staged strip
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    int use_tmap = 0;
+    if (tensor_map_encoder() && (long long)n * h < (1LL << 31)) {
+        const cuuint64_t gdim[2] = {(cuuint64_t)w * CH / 4, (cuuint64_t)n * h};
+        const cuuint64_t gstride[1] = {(cuuint64_t)w * CH};
+        const cuuint32_t box[2] = {(cuuint32_t)(SW * CH / 4), (cuuint32_t)R};
+        const cuuint32_t estride[2] = {1, 1};
+        use_tmap = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void *)src, gdim, gstride, box, estride,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    if (getenv("SVB_K1_NO_TMAP")) use_tmap = 0;
     dim3 grid(nstrips, nseg, n);
-    fused_preprocess_warp_kernel<CH><<<grid, 32, smem, st>>>(src, mask, h, w, rows_per_seg);
+    fused_preprocess_warp_kernel<CH><<<grid, 32, smem, st>>>(src, mask, h, w, rows_per_seg, tmap, use_tmap);
     return check_launch(ctx, "fused_preprocess_warp_kernel");
 }
 
