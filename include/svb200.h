@@ -51,8 +51,9 @@ long long svb_launch_count(const svb_ctx *ctx);
  * timed region with these): when enabled, CUDA events are recorded on the launching stream between
  * the stages of every scan.  svb_last_stage_ms waits for the last scan's final event and returns the
  * elapsed milliseconds of its stages: [0] K1 fused preprocess, [1] K2 contour (reset+probe+select),
- * [2] K3+K4 homography + cells, [3] K5 classifier (+ not-found masking). */
-#define SVB_NUM_STAGES 4
+ * [2] K3+K4 homography + cells, [3] K5 convolution stack (conv1 + conv2 + pooling), [4] K5 fc1 + fc2 + softmax
+ * (+ not-found masking). */
+#define SVB_NUM_STAGES 5
 int svb_stage_timing(svb_ctx *ctx, int enable);
 int svb_last_stage_ms(svb_ctx *ctx, float *ms);
 

@@ -56,7 +56,7 @@ void digitcnn_free(svb_ctx *);
 void digitcnn_v3_free(svb_ctx *);
 int digitcnn_v3_load(svb_ctx *, const float *const *, int, cudaStream_t);
 int launch_digitcnn_v3(svb_ctx *, const float *, long long, float *, uint8_t *, float *, float *, cudaStream_t);
-int launch_digitcnn_tc(svb_ctx *, const float *, long long, float *, uint8_t *, float *, cudaStream_t);
+int launch_digitcnn_tc(svb_ctx *, const float *, long long, float *, uint8_t *, float *, cudaStream_t, cudaEvent_t mid = nullptr);
 int preprocess_v2_run(svb_ctx *, const uint8_t *, const uint8_t *, int, int, int, int, int, uint8_t *, uint8_t *, cudaStream_t);
 int preprocess_multi_run(svb_ctx *, const uint8_t *, const uint8_t *, int, int, int, uint8_t *, uint8_t *, uint8_t *, uint8_t *,
                          uint8_t *, cudaStream_t);
@@ -331,11 +331,15 @@ static int scan_batch(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uin
     if (rc) return rc;
     mark(3);
     // frames without a grid have all-zero cell tensors; their digits/conf are forced to 0 below
-    rc = (ctx->classifier_mode == 1) ? launch_digitcnn(ctx, pm1, (long long)cells, lg, digits, conf, st)
-                                     : launch_digitcnn_tc(ctx, pm1, (long long)cells, lg, digits, conf, st);
+    if (ctx->classifier_mode == 1) {
+        mark(4);  // fp32 cross-check kernels: not split, everything is booked on the convolution stage
+        rc = launch_digitcnn(ctx, pm1, (long long)cells, lg, digits, conf, st);
+    } else {
+        rc = launch_digitcnn_tc(ctx, pm1, (long long)cells, lg, digits, conf, st, tm ? ctx->ev[4] : nullptr);
+    }
     if (rc) return rc;
     rc = launch_mask_not_found(ctx, found, n, digits, conf, st);
-    mark(4);
+    mark(5);
     ctx->ev_valid = tm;
     return rc;
 }

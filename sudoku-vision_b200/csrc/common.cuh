@@ -71,7 +71,7 @@ struct svb_ctx {
     svb_ctx *worker[2] = {nullptr, nullptr};  // per-slot child contexts (own stream + arenas) for the chunked host path
     bool is_worker = false;                   // workers borrow the parent's weights and never free them
     bool stage_timing = false;
-    cudaEvent_t ev[SVB_NUM_STAGES + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[SVB_NUM_STAGES + 1] = {};
     bool ev_valid = false;
 };
 

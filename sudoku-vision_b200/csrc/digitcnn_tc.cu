@@ -154,12 +154,12 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
         mbar_init(&s.mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) tmem_alloc(&s.tmem_base, 256);
+    if (warp == 0) tmem_alloc(&s.tmem_base, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s.tmem_base;
-    const uint32_t idesc = make_idesc(128, 64);
+    const uint32_t idesc64 = make_idesc(128, 64), idesc128 = make_idesc(128, 128);
     const uint32_t s_base = smem_u32(&s.S[0][0][0]), wb_base = smem_u32(&s.WB[0][0]);
     uint32_t phase = 0;
 
@@ -190,12 +190,19 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
         for (int it = 0; it < ITEMS; ++it) {
             const int item = it * NWK + tid;
             if (item < 196 * 4) {
-                const int pp = item >> 2, cg = item & 3, py = pp / 14, px = pp - py * 14;
+                // channel group major, pooled pixel minor: consecutive lanes own consecutive rows of S (16-byte pitch), so
+                // the six 128-bit stores of write_S are conflict-free
+                const int cg = item / 196, pp = item - cg * 196, py = pp / 14, px = pp - py * 14;
                 float patch[16];
 #pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) patch[r * 4 + c] = s.inp[(2 * py + r) * 32 + 2 * px + c];
+                for (int r = 0; r < 4; ++r) {
+                    const float2 pa = *reinterpret_cast<const float2 *>(&s.inp[(2 * py + r) * 32 + 2 * px]);
+                    const float2 pb = *reinterpret_cast<const float2 *>(&s.inp[(2 * py + r) * 32 + 2 * px + 2]);
+                    patch[r * 4 + 0] = pa.x;
+                    patch[r * 4 + 1] = pa.y;
+                    patch[r * 4 + 2] = pb.x;
+                    patch[r * 4 + 3] = pb.y;
+                }
                 float2 acc[4][4];  // [channel pair][pool position]
 #pragma unroll
                 for (int cp = 0; cp < 4; ++cp) {
@@ -237,7 +244,7 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
         for (int it = 0; it < ITEMS; ++it) {
             const int item = it * NWK + tid;
             if (item < 196 * 4) {
-                const int pp = item >> 2, cg = item & 3, py = pp / 14, px = pp - py * 14;
+                const int cg = item / 196, pp = item - cg * 196, py = pp / 14, px = pp - py * 14;
                 const int rp = (py + 2) * 16 + px;  // row in the padded 16x16 grid (two halo rows on top)
 #pragma unroll
                 for (int dxi = 0; dxi < 3; ++dxi) {
@@ -263,27 +270,34 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
     auto epilogue = [&](long long cell_e, int buf) {
         const int j = (warp >> 2) & 1, q = warp & 3, half = warp >> 3;
         const int py = 4 * j + q - 1;  // pooled row produced by this warp (rows y_p = 2(4j+q), +1)
-        const bool writer = (lane < 14) && !(lane & 1) && py >= 0 && py < 7;
-        const int px = lane >> 1;
-        __half *fh = feat_hi + (cell_e * 49 + (long long)(py * 7 + px)) * 64;
-        __half *fl = feat_lo + (cell_e * 49 + (long long)(py * 7 + px)) * 64;
-        uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + j * 64 + half * 32), v);
-        __half hi[32], lo[32];
+        const int px = (lane & 15) >> 1;
+        const bool writer = (px < 7) && py >= 0 && py < 7;
+        const int chunk = (lane & 1) + 2 * (lane >> 4);  // which 8 of this warp's 32 channels this lane finishes and stores
+        __half *fh = feat_hi + (cell_e * 49 + (long long)(py * 7 + px)) * 64 + half * 32 + chunk * 8;
+        __half *fl = feat_lo + (cell_e * 49 + (long long)(py * 7 + px)) * 64 + half * 32 + chunk * 8;
+        uint32_t v[32], v2[32];
+        const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + j * 128 + half * 32);
+        tmem_ld32(ta, v);
+        tmem_ld32(ta + 64, v2);
+        // 2x2 max-pool as a butterfly that halves the data at each step: after the x exchange a lane keeps the two 8-channel
+        // chunks of its x parity, after the y exchange the one chunk it finishes (24 shuffles instead of 64)
+        const bool b0 = lane & 1, b1 = lane >> 4;
+        float g[16], pooled[8];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            float f = __uint_as_float(v[c]);
-            f = fmaxf(f, __shfl_xor_sync(0xffffffffu, f, 1));
-            f = fmaxf(f, __shfl_xor_sync(0xffffffffu, f, 16));
-            f = fmaxf(f + s.b2[half * 32 + c], 0.f);
-            split_hi_lo(f, hi[c], lo[c]);
+        for (int i = 0; i < 16; ++i) {
+            const int ca = (i < 8) ? i : 8 + i;  // columns of chunks 0 and 2; chunks 1 and 3 are 8 further
+            const float fa = __uint_as_float(v[ca]) + __uint_as_float(v2[ca]);
+            const float fb = __uint_as_float(v[ca + 8]) + __uint_as_float(v2[ca + 8]);
+            g[i] = fmaxf(b0 ? fb : fa, __shfl_xor_sync(0xffffffffu, b0 ? fa : fb, 1));
         }
-        if (writer) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                reinterpret_cast<uint4 *>(fh + half * 32)[k] = reinterpret_cast<const uint4 *>(hi)[k];
-                reinterpret_cast<uint4 *>(fl + half * 32)[k] = reinterpret_cast<const uint4 *>(lo)[k];
-            }
+        for (int i = 0; i < 8; ++i) pooled[i] = fmaxf(b1 ? g[8 + i] : g[i], __shfl_xor_sync(0xffffffffu, b1 ? g[i] : g[8 + i], 16));
+        __half hi[8], lo[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) split_hi_lo(fmaxf(pooled[c] + s.b2[half * 32 + chunk * 8 + c], 0.f), hi[c], lo[c]);
+        if (writer) {
+            *reinterpret_cast<uint4 *>(fh) = *reinterpret_cast<const uint4 *>(hi);
+            *reinterpret_cast<uint4 *>(fl) = *reinterpret_cast<const uint4 *>(lo);
         }
     };
 
@@ -313,22 +327,25 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
             // The whole warp runs the (uniform) descriptor arithmetic so it stays on the uniform datapath;
             // only the tcgen05 instructions themselves are predicated on one elected lane.
             tc_fence_after();
-            const uint32_t tacc = tmem + (uint32_t)(buf * 128);
+            // Per tile j, 128 accumulator columns: [0,64) = A_hi*B_hi + A_lo*B_hi, [64,128) = A_hi*B_lo (summed in the
+            // epilogue).  The lo image of the weights follows the hi image at exactly 8 row groups (WB_BYTES = 8 * WB_SBO),
+            // so one N = 128 descriptor starting at the hi image reads [B_hi | B_lo]: A_hi is fetched once for both products.
+            const uint32_t tacc = tmem + (uint32_t)(buf * 256);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
 #pragma unroll
-                for (int combo = 0; combo < 3; ++combo) {
-                    const int pa = (combo == 2) ? 1 : 0, pb = (combo == 1) ? 1 : 0;  // hi*hi, hi*lo, lo*hi
+                for (int combo = 0; combo < 2; ++combo) {  // 0: A_hi x [B_hi|B_lo] (N=128), 1: A_lo x B_hi (N=64)
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
                         const int dy = t / 3 - 1, dxi = t % 3;
-                        const uint32_t a_off = (uint32_t)((pa * 3 + dxi) * S_BYTES + ((128 * j + 16 * dy + PAD) >> 3) * 512);
-                        const uint32_t b_off = (uint32_t)(pb * WB_BYTES + t * 4 * 128);
+                        const uint32_t a_off = (uint32_t)((combo * 3 + dxi) * S_BYTES + ((128 * j + 16 * dy + PAD) >> 3) * 512);
+                        const uint32_t b_off = (uint32_t)(t * 4 * 128);
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks) {
                             const uint64_t ad = a_desc0 + (uint64_t)((a_off + ks * 256) >> 4);
                             const uint64_t bd = b_desc0 + (uint64_t)((b_off + ks * 256) >> 4);
-                            if (lane == 0) umma_f16(tacc + (uint32_t)(j * 64), ad, bd, idesc, (combo | t | ks) ? 1u : 0u);
+                            if (lane == 0)
+                                umma_f16(tacc + (uint32_t)(j * 128), ad, bd, combo ? idesc64 : idesc128, (combo | t | ks) ? 1u : 0u);
                         }
                     }
                 }
@@ -356,7 +373,7 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 // ================================================================================================
@@ -565,7 +582,7 @@ int digitcnn_tc_load(svb_ctx *ctx, const float *conv2_w, const float *fc1_w, cud
 }
 
 int launch_digitcnn_tc(svb_ctx *ctx, const float *x, long long n, float *logits, uint8_t *digits, float *conf,
-                       cudaStream_t st) {
+                       cudaStream_t st, cudaEvent_t mid) {
     using namespace k5tc;
     SVB_REQUIRE(ctx->cnn.loaded && ctx->cnn_tc, SVB_ERR_NOT_LOADED, "DigitCNN weights not loaded (svb_digitcnn_load)");
     const DigitCnnWeights &c = ctx->cnn;
@@ -580,6 +597,7 @@ int launch_digitcnn_tc(svb_ctx *ctx, const float *x, long long n, float *logits,
     tc_conv_kernel<<<grid, NTC, sizeof(ConvSmem), st>>>(x, n, c.conv1_w, c.conv1_b, t->wb_img, c.conv2_b, fh, fl);
     int rc = check_launch(ctx, "k5tc::tc_conv_kernel");
     if (rc) return rc;
+    if (mid) cudaEventRecord(mid, st);  // stage timing: convolution stack | fc head
     const long long tiles = (n + 127) / 128;
     tc_fc_kernel<<<(int)min((long long)ctx->sm_count, tiles), NT, sizeof(FcSmem), st>>>(fh, fl, n, t->w_hi, t->w_lo, c.fc1_b,
                                                                                        c.fc2_w, c.fc2_b, logits, digits, conf);

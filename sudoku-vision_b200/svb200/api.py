@@ -80,13 +80,13 @@ class Scanner:
     def launches(self) -> int:
         return int(self.lib.svb_launch_count(self._h))
 
-    STAGES = ("k1_preprocess", "k2_contour", "k34_cells", "k5_classifier")
+    STAGES = ("k1_preprocess", "k2_contour", "k34_cells", "k5_conv", "k5_fc")
 
     def stage_timing(self, enable: bool = True):
         _lib.check(self.lib.svb_stage_timing(self._h, int(enable)), "svb_stage_timing")
 
     def last_stage_ms(self) -> dict:
-        ms = (C.c_float * 4)()
+        ms = (C.c_float * len(self.STAGES))()
         _lib.check(self.lib.svb_last_stage_ms(self._h, ms), "svb_last_stage_ms")
         return dict(zip(self.STAGES, [float(x) for x in ms]))
 
