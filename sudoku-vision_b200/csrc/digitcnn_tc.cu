@@ -119,13 +119,13 @@ __device__ __forceinline__ void split_hi_lo(float v, __half &hi, __half &lo) {
 // conv stack
 // ================================================================================================
 struct ConvSmem {
-    alignas(1024) uint8_t S[2][3][S_BYTES];  // [hi/lo][dx+1] pooled conv1 activations, canonical layout
+    alignas(1024) uint8_t S[2][2][S_BYTES];  // [buffer][hi/lo] pooled conv1 activations, K-chunk-major rows (see below)
     alignas(128) uint8_t WB[2][WB_BYTES];    // conv2 weights [hi/lo], canonical layout (N=64 rows, K=288)
     float w1[9 * 32];                        // conv1 weights [tap][co]
     float b1[32];
     float b2[64];
     float inp[30 * 32];                      // zero-padded input, row pitch 32
-    alignas(8) unsigned long long mbar;
+    alignas(8) unsigned long long mbar[2];   // one per accumulator / activation buffer
     uint32_t tmem_base;
 };
 
@@ -143,7 +143,7 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---- one-time setup ------------------------------------------------------------------------------
-    for (int i = tid; i < 2 * 3 * S_BYTES / 16; i += NTC) reinterpret_cast<uint4 *>(&s.S[0][0][0])[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 2 * 2 * S_BYTES / 16; i += NTC) reinterpret_cast<uint4 *>(&s.S[0][0][0])[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < 2 * WB_BYTES / 16; i += NTC)
         reinterpret_cast<uint4 *>(&s.WB[0][0])[i] = reinterpret_cast<const uint4 *>(wb_img)[i];
     for (int i = tid; i < 9 * 32; i += NTC) s.w1[i] = w1[i];
@@ -151,7 +151,8 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
     if (tid < 64) s.b2[tid] = b2[tid];
     for (int i = tid; i < 30 * 32; i += NTC) s.inp[i] = 0.f;
     if (tid == 0) {
-        mbar_init(&s.mbar, 1);
+        mbar_init(&s.mbar[0], 1);
+        mbar_init(&s.mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(&s.tmem_base, 512);
@@ -161,7 +162,7 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
     const uint32_t tmem = s.tmem_base;
     const uint32_t idesc64 = make_idesc(128, 64), idesc128 = make_idesc(128, 128);
     const uint32_t s_base = smem_u32(&s.S[0][0][0]), wb_base = smem_u32(&s.WB[0][0]);
-    uint32_t phase = 0;
+    uint32_t phase[2] = {0, 0};
 
     // Software pipeline: while the tensor core works on cell i (asynchronously), the CUDA cores stage
     // and convolve cell i+1 into registers; S is rewritten only after cell i's MMAs have committed.
@@ -238,21 +239,21 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
             }
         }
     };
-    // registers -> S (three dx-shifted copies, hi and lo)
-    auto write_S = [&]() {
+    // registers -> S[buf] (hi and lo).  K-chunk-major: element (row r, channel c) at (c/8)*SROWS*16 + r*16 + (c%8)*2, i.e. the
+    // UMMA canonical K-major no-swizzle layout with SBO = 128 B (8-row groups contiguous) and LBO = SROWS*16.  Rows are a
+    // plain 16-byte-pitch array, so the im2col operand of tap (dy, dx) is the SAME buffer at a start address shifted by
+    // (16 dy + dx) rows: one copy of the activations serves all nine taps, and two buffers fit (the next cell's
+    // activations are written while the tensor core still reads this cell's).
+    auto write_S = [&](int buf) {
 #pragma unroll
         for (int it = 0; it < ITEMS; ++it) {
             const int item = it * NWK + tid;
             if (item < 196 * 4) {
                 const int cg = item / 196, pp = item - cg * 196, py = pp / 14, px = pp - py * 14;
-                const int rp = (py + 2) * 16 + px;  // row in the padded 16x16 grid (two halo rows on top)
-#pragma unroll
-                for (int dxi = 0; dxi < 3; ++dxi) {
-                    const int row = rp + PAD - (dxi - 1);  // S_dx[r] = P[r - PAD + dx]
-                    const int off = (row >> 3) * 512 + cg * 128 + (row & 7) * 16;
-                    *reinterpret_cast<uint4 *>(&s.S[0][dxi][off]) = rh[it];
-                    *reinterpret_cast<uint4 *>(&s.S[1][dxi][off]) = rl[it];
-                }
+                const int row = (py + 2) * 16 + px + PAD;  // padded 16x16 grid (two halo rows on top) after PAD zero rows
+                const int off = cg * (SROWS * 16) + row * 16;
+                *reinterpret_cast<uint4 *>(&s.S[buf][0][off]) = rh[it];
+                *reinterpret_cast<uint4 *>(&s.S[buf][1][off]) = rl[it];
             }
         }
     };
@@ -260,7 +261,7 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
     // descriptor halves that never change: LBO/SBO/version live in the high word
     // all smem addresses are < 256 KB, so adding (byte offset >> 4) to a descriptor never carries out of
     // the 14-bit start-address field
-    const uint64_t a_desc0 = make_desc(s_base, 128, 512), b_desc0 = make_desc(wb_base, 128, WB_SBO);
+    const uint64_t a_desc0 = make_desc(s_base, SROWS * 16, 128), b_desc0 = make_desc(wb_base, 128, WB_SBO);
 
     // warp 15 only issues MMAs (a ~5k-cycle serial instruction stream per cell); keeping it out of the conv1
     // barriers lets the 15 worker warps convolve the next cell at full speed meanwhile
@@ -301,8 +302,9 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
         }
     };
 
-    // Pipeline over cells (TMEM double-buffered: two accumulator sets of 128 columns):
-    //   wait MMA(i-1) -> write S(i) -> [barrier] -> MMA(i) issued (async)  ||  epilogue(i-1), then conv1(i+1) in registers
+    // Pipeline over cells; activations S and accumulators (TMEM) are both double-buffered:
+    //   write S(i) -> [barrier] -> MMAs(i) issued (async)  ||  wait MMAs(i-1), epilogue(i-1), conv1(i+1) in registers
+    // so the tensor core works on cell i while the CUDA cores finish cell i-1 and prepare cell i+1.
     long long cell = blockIdx.x, prev_cell = -1;
     int it = 0;
     if (cell < n_cells && !mma_warp) {
@@ -313,16 +315,13 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
     for (; cell < n_cells; cell += gridDim.x, ++it) {
         const int buf = it & 1;
         const long long next = cell + gridDim.x;
-        if (next < n_cells && !mma_warp) prefetch_input(next);  // lands while we wait, write S and run the epilogue
-        if (it > 0) {  // S is read by the previous cell's MMAs until they commit
-            mbar_wait(&s.mbar, phase);
-            phase ^= 1;
-        }
-        if (!mma_warp) write_S();
+        if (next < n_cells && !mma_warp) prefetch_input(next);  // lands while we write S and run the epilogue
+        // S[buf] was last read by the MMAs of cell i-2, whose commit every thread awaited in the previous iteration
+        if (!mma_warp) write_S(buf);
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
         tc_fence_before();
         __syncthreads();      // S(i) complete; every epilogue read of TMEM buffer `buf` (cell i-2) has retired
-        // ---- implicit-GEMM conv2 on tcgen05: 2 tiles x 3 splits x 9 taps x 2 k-steps, fully unrolled ------------
+        // ---- implicit-GEMM conv2 on tcgen05: 2 tiles x 2 products x 9 taps x 2 k-steps, fully unrolled ------------
         if (mma_warp) {
             // The whole warp runs the (uniform) descriptor arithmetic so it stays on the uniform datapath;
             // only the tcgen05 instructions themselves are predicated on one elected lane.
@@ -331,18 +330,19 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
             // epilogue).  The lo image of the weights follows the hi image at exactly 8 row groups (WB_BYTES = 8 * WB_SBO),
             // so one N = 128 descriptor starting at the hi image reads [B_hi | B_lo]: A_hi is fetched once for both products.
             const uint32_t tacc = tmem + (uint32_t)(buf * 256);
+            const uint64_t a_desc_buf = a_desc0 + (uint64_t)((uint32_t)(buf * 2 * S_BYTES) >> 4);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
 #pragma unroll
                 for (int combo = 0; combo < 2; ++combo) {  // 0: A_hi x [B_hi|B_lo] (N=128), 1: A_lo x B_hi (N=64)
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
-                        const int dy = t / 3 - 1, dxi = t % 3;
-                        const uint32_t a_off = (uint32_t)((combo * 3 + dxi) * S_BYTES + ((128 * j + 16 * dy + PAD) >> 3) * 512);
+                        const int dy = t / 3 - 1, dx = t % 3 - 1;
+                        const uint32_t a_off = (uint32_t)(combo * S_BYTES + (128 * j + 16 * dy + dx + PAD) * 16);
                         const uint32_t b_off = (uint32_t)(t * 4 * 128);
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks) {
-                            const uint64_t ad = a_desc0 + (uint64_t)((a_off + ks * 256) >> 4);
+                            const uint64_t ad = a_desc_buf + (uint64_t)((a_off + ks * 2 * SROWS * 16) >> 4);
                             const uint64_t bd = b_desc0 + (uint64_t)((b_off + ks * 256) >> 4);
                             if (lane == 0)
                                 umma_f16(tacc + (uint32_t)(j * 128), ad, bd, combo ? idesc64 : idesc128, (combo | t | ks) ? 1u : 0u);
@@ -350,11 +350,13 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
                     }
                 }
             }
-            if (lane == 0) umma_commit(&s.mbar);
+            if (lane == 0) umma_commit(&s.mbar[buf]);
             __syncwarp();
         }
-        // ---- overlapped with the MMAs: epilogue of the previous cell, then conv1 of the next one ---------------------
+        // ---- overlapped with the MMAs of cell i: epilogue of cell i-1, then conv1 of cell i+1 ---------------------------
         if (it > 0) {
+            mbar_wait(&s.mbar[buf ^ 1], phase[buf ^ 1]);
+            phase[buf ^ 1] ^= 1;
             tc_fence_after();
             epilogue(prev_cell, buf ^ 1);
         }
@@ -366,10 +368,11 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
         prev_cell = cell;
     }
     if (it > 0) {  // drain: last cell
-        mbar_wait(&s.mbar, phase);
-        phase ^= 1;
+        const int lb = (it - 1) & 1;
+        mbar_wait(&s.mbar[lb], phase[lb]);
+        phase[lb] ^= 1;
         tc_fence_after();
-        epilogue(prev_cell, (it - 1) & 1);
+        epilogue(prev_cell, lb);
     }
     tc_fence_before();
     __syncthreads();

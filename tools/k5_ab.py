@@ -1,0 +1,28 @@
+"""DigitCNN classifier alone (K5: tc_conv + tc_fc) on +-1 cells: ms per launch and cells/s.
+    python tools/k5_ab.py [cells] [iters]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "sudoku-vision_b200")):
+    sys.path.insert(0, p)
+import torch
+from svb200 import Scanner, load_digitcnn_weights
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 82944
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+dev = torch.device("cuda", 0)
+sc = Scanner(device=0, weights=load_digitcnn_weights())
+g = torch.Generator(device=dev).manual_seed(5)
+x = torch.where(torch.rand((n, 1, 28, 28), device=dev, generator=g) < 0.25, 1.0, -1.0)
+for _ in range(2):
+    sc.digitcnn_forward(x)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(iters):
+    sc.digitcnn_forward(x)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / iters
+print(f"K5: {n} cells {ms:.3f} ms/launch  {n / ms / 1e3:.2f} M cells/s")
