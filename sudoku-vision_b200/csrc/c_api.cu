@@ -44,8 +44,11 @@ int launch_gray(svb_ctx *, const uint8_t *, int, int, int, uint8_t *, cudaStream
 int launch_blur5(svb_ctx *, const uint8_t *, int, int, int, uint8_t *, cudaStream_t);
 int launch_adaptive(svb_ctx *, const uint8_t *, int, int, int, int, uint8_t *, cudaStream_t);
 bool fused_preprocess_supported(int h, int w);
-int launch_fused_preprocess(svb_ctx *, const uint8_t *, int, int, int, uint8_t *, cudaStream_t, int ch = 3);
-int launch_find_grid_contour(svb_ctx *, const uint8_t *, int, int, int, double, double, int32_t *, uint8_t *, cudaStream_t, int v2_mode = 0);
+int launch_fused_preprocess(svb_ctx *, const uint8_t *, int, int, int, uint8_t *, cudaStream_t, int ch = 3, uint32_t *bits = nullptr);
+bool fused_preprocess_writes_bits(int h, int w, const void *mask);
+int launch_find_grid_contour(svb_ctx *, const uint8_t *, int, int, int, double, double, int32_t *, uint8_t *, cudaStream_t, int v2_mode = 0,
+                             const uint32_t *ready_bits = nullptr);
+uint32_t *contour_bits_buffer(svb_ctx *, int n, int h, int w, cudaStream_t);
 int launch_warp_board(svb_ctx *, const uint8_t *, int, int, int, const int32_t *, const uint8_t *, int, uint8_t *, cudaStream_t);
 int launch_extract_cells(svb_ctx *, const uint8_t *, int, int, uint8_t *, cudaStream_t);
 int launch_cell_prep(svb_ctx *, const uint8_t *, long long, uint8_t *, float *, cudaStream_t);
@@ -169,9 +172,17 @@ API int svb_adaptive_threshold(svb_ctx *ctx, const uint8_t *gray, int n, int h, 
     return launch_adaptive(ctx, gray, n, h, w, inverted, out, (cudaStream_t)stream);
 }
 
-static int preprocess_any(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *mask, cudaStream_t st) {
-    if (fused_preprocess_supported(h, w) && ((uintptr_t)bgr % 16 == 0) && ((uintptr_t)mask % 4 == 0))
-        return launch_fused_preprocess(ctx, bgr, n, h, w, mask, st);
+// bits_out (optional): receives the tiled bit mask K1 wrote for K2 (context-owned), or nullptr if K2 has to pack it itself
+static int preprocess_any(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *mask, cudaStream_t st,
+                          const uint32_t **bits_out = nullptr) {
+    if (bits_out) *bits_out = nullptr;
+    if (fused_preprocess_supported(h, w) && ((uintptr_t)bgr % 16 == 0) && ((uintptr_t)mask % 4 == 0)) {
+        uint32_t *bits = nullptr;
+        if (bits_out && fused_preprocess_writes_bits(h, w, mask)) bits = contour_bits_buffer(ctx, n, h, w, st);
+        const int rc = launch_fused_preprocess(ctx, bgr, n, h, w, mask, st, 3, bits);
+        if (rc == SVB_OK && bits_out) *bits_out = bits;
+        return rc;
+    }
     // odd sizes: the three stage kernels back to back (still GPU; no CPU fallback)
     SVB_REQUIRE(h >= 3 && w >= 3, SVB_ERR_UNSUPPORTED, "preprocess: images smaller than 3x3 are not supported");
     size_t px = (size_t)n * h * w;
@@ -321,10 +332,11 @@ static int scan_batch(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uin
         if (tm) cudaEventRecord(ctx->ev[i], st);
     };
     mark(0);
-    int rc = preprocess_any(ctx, bgr, n, h, w, mask, st);
+    const uint32_t *bits = nullptr;  // K1 also emits the tiled bit mask K2 traces (saves K2's packing pass over the mask)
+    int rc = preprocess_any(ctx, bgr, n, h, w, mask, st, &bits);
     if (rc) return rc;
     mark(1);
-    rc = launch_find_grid_contour(ctx, mask, n, h, w, 0.1, 0.02, corners, found, st);
+    rc = launch_find_grid_contour(ctx, mask, n, h, w, 0.1, 0.02, corners, found, st, 0, bits);
     if (rc) return rc;
     mark(2);
     rc = launch_cells_from_frames(ctx, bgr, n, h, w, corners, found, nullptr, pm1, st);

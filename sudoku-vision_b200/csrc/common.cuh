@@ -53,7 +53,7 @@ struct DigitCnnWeights {
 
 namespace svb {
 // context-owned scratch arenas, one per purpose so that chained stages never alias
-enum Arena { AR_ADAPT = 0, AR_STAGE, AR_CONTOUR, AR_HOMOG, AR_CNN, AR_PATH, AR_V2, AR_V2T, AR_QUAL, AR_SOLVE, AR_COUNT };
+enum Arena { AR_ADAPT = 0, AR_STAGE, AR_CONTOUR, AR_HOMOG, AR_CNN, AR_PATH, AR_V2, AR_V2T, AR_QUAL, AR_SOLVE, AR_BITS, AR_COUNT };
 }
 
 struct svb_ctx {
@@ -70,6 +70,9 @@ struct svb_ctx {
     cudaStream_t own_stream = nullptr;
     svb_ctx *worker[2] = {nullptr, nullptr};  // per-slot child contexts (own stream + arenas) for the chunked host path
     bool is_worker = false;                   // workers borrow the parent's weights and never free them
+    // tiled bit mask written by K1 for K2 (AR_BITS): geometry whose pad tiles are known to be zero
+    const void *bits_ptr = nullptr;
+    int bits_n = 0, bits_h = 0, bits_w = 0;
     bool stage_timing = false;
     cudaEvent_t ev[SVB_NUM_STAGES + 1] = {};
     bool ev_valid = false;

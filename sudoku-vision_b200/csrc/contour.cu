@@ -245,8 +245,27 @@ select_quad_kernel(const void *__restrict__ mask, int n, int h, int w, int wp, i
 
 }  // namespace k2
 
+// The tiled bit mask of n frames for a producer other than pack_bits_kernel (K1 writes it while it writes the byte mask).
+// Pad tiles and the rows / columns past the image must be zero: the buffer is cleared whenever its geometry changes, and a
+// producer only ever rewrites the words inside the image.  Returns nullptr when the bit path does not apply.
+uint32_t *contour_bits_buffer(svb_ctx *ctx, int n, int h, int w, cudaStream_t st) {
+    if (w % 32 != 0) return nullptr;
+    const size_t words = (size_t)n * contour::bit_tiles_x(w) * contour::bit_tiles_y(h) * 32;
+    if (ctx->arena[AR_BITS].reserve(words * sizeof(uint32_t)) != SVB_OK) return nullptr;
+    uint32_t *p = (uint32_t *)ctx->arena[AR_BITS].ptr;
+    if (ctx->bits_ptr != p || ctx->bits_n < n || ctx->bits_h != h || ctx->bits_w != w) {
+        if (cudaMemsetAsync(p, 0, words * sizeof(uint32_t), st) != cudaSuccess) return nullptr;
+        ctx->bits_ptr = p;
+        ctx->bits_n = n;
+        ctx->bits_h = h;
+        ctx->bits_w = w;
+    }
+    return p;
+}
+
 int launch_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, int w, double min_area_ratio,
-                             double eps_ratio, int32_t *corners, uint8_t *found, cudaStream_t st, int v2_mode) {
+                             double eps_ratio, int32_t *corners, uint8_t *found, cudaStream_t st, int v2_mode,
+                             const uint32_t *ready_bits) {
     using namespace k2;
     const double min_area = min_area_ratio * (double)((long long)h * w);
     const int pitch = contour::probe_pitch(min_area);
@@ -267,10 +286,10 @@ int launch_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, in
     const size_t o_c = take(sizeof(Cand) * (size_t)n * MAXC);
     const size_t o_ch = take(sizeof(uint32_t) * (size_t)n * cap), o_po = take(sizeof(uint32_t) * (size_t)n * cap);
     // bit-packed copy of the mask (only when rows split evenly into 32-pixel words and are 16-B aligned)
-    const bool use_bits = (w % 32 == 0) && ((uintptr_t)mask % 16 == 0);
+    const bool use_bits = ready_bits || ((w % 32 == 0) && ((uintptr_t)mask % 16 == 0));
     const int tx = contour::bit_tiles_x(w), ty = contour::bit_tiles_y(h);
     const int wp = tx * ty;  // tiles per frame
-    const size_t o_bits = use_bits ? take(sizeof(uint32_t) * (size_t)n * wp * 32) : 0;
+    const size_t o_bits = (use_bits && !ready_bits) ? take(sizeof(uint32_t) * (size_t)n * wp * 32) : 0;
     const long long gcap_ll = std::min<long long>(std::max<long long>((long long)n * 512, 16384), (long long)n * (total / 2 + 1));
     const int gcap = (int)std::min<long long>(gcap_ll, 1ll << 26);
     const size_t o_gc = take(sizeof(int)), o_gl = take(sizeof(GEntry) * (size_t)gcap), o_sg = take(sizeof(Seg) * (size_t)gcap);
@@ -295,7 +314,9 @@ int launch_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, in
     int rc = check_launch(ctx, "k2::reset_kernel");
     if (rc) return rc;
     const void *view_ptr = mask;
-    if (use_bits) {
+    if (ready_bits) {
+        view_ptr = ready_bits;  // K1 wrote the tiled bit mask next to the byte mask
+    } else if (use_bits) {
         uint32_t *bits = (uint32_t *)(base + o_bits);
         const long long words = (long long)n * wp * 32;
         pack_bits_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(mask, bits, h, w, tx, ty, words);

@@ -699,7 +699,8 @@ __device__ __forceinline__ void colpass_group(const float4 (&Rw)[14], const uint
 template <int CH>
 __global__ void __launch_bounds__(32, 12)
 fused_preprocess_warp_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ mask, int h, int w, int rows_per_seg,
-                             const __grid_constant__ CUtensorMap tmap, int use_tmap) {
+                             const __grid_constant__ CUtensorMap tmap, int use_tmap, uint8_t *__restrict__ bits, int bits_tx,
+                             long long bits_frame_bytes) {
     // one warp per CTA (12 resident per SM): everything the TMA issue needs is CTA-uniform, so it stays on the uniform datapath
     extern __shared__ __align__(128) uint8_t smem_raw[];
     WarpSmem<CH> &sm = *reinterpret_cast<WarpSmem<CH> *>(smem_raw);
@@ -774,6 +775,9 @@ fused_preprocess_warp_kernel(const uint8_t *__restrict__ src, uint8_t *__restric
     }
 
     uint8_t *optr = out + c0 + (long long)(4 * q_first - 5) * wl;  // this lane's 8 bytes of output row 4q-5
+    // optional second output, the tiled bit mask K2 traces (contour_core.cuh BitMaskView: 32x32-px tiles of 32 words, one
+    // zero pad tile all around): this lane's 8 pixels are byte (c0 % 32) / 8 of word (y + 32) % 32 of tile (c0/32 + 1, (y+32)/32)
+    uint8_t *blane = bits ? bits + (long long)fr * bits_frame_bytes + (long long)(c0 / 32 + 1) * 128 + ((c0 & 31) >> 3) : nullptr;
     for (int k = 0; k < nblk; ++k, optr += 4 * wl) {
         const int q = q_first + k, stage = k & 1;
         mbar_wait(&sm.full[stage], (uint32_t)((k >> 1) & 1));
@@ -921,11 +925,26 @@ fused_preprocess_warp_kernel(const uint8_t *__restrict__ src, uint8_t *__restric
                 colpass_group(Rw, srcw, o32[g]);
             }
             uint8_t *orow = optr;
+            bool st_ok[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                if (lane_out && (unsigned)(4 * q - 5 + i - ys) < (unsigned)(ye - ys))
-                    *reinterpret_cast<uint2 *>(orow) = make_uint2(o32[0][i], o32[1][i]);
+                st_ok[i] = lane_out && (unsigned)(4 * q - 5 + i - ys) < (unsigned)(ye - ys);
+                if (st_ok[i]) *reinterpret_cast<uint2 *>(orow) = make_uint2(o32[0][i], o32[1][i]);
                 orow += wl;
+            }
+            if (bits) {  // mask bytes are 0x00 / 0xff: bit 0 of the eight bytes -> one byte of the tiled bit mask, pixel k -> bit k
+                int yp = 4 * q - 5 + 32;                                           // padded row of output row 4q-5
+                long long boff = ((long long)(yp >> 5) * bits_tx * 32 + (yp & 31)) * 4;  // its word in this lane's tile column
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t t = (o32[0][i] & 0x01010101u) | ((o32[1][i] << 4) & 0x10101010u);
+                    const uint32_t b = (t * 0x01020408u) >> 24;
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p st.global.u8 [%0], %1;\n}\n" ::"l"(blane + boff), "r"(b),
+                                 "r"((uint32_t)st_ok[i])
+                                 : "memory");
+                    boff += ((yp & 31) == 31) ? (long long)(bits_tx * 32 - 31) * 4 : 4;  // next row: next word, or the tile below
+                    ++yp;
+                }
             }
         }
         T[0] = P[3][0];
@@ -985,7 +1004,7 @@ static tensor_map_encode_fn tensor_map_encoder() {
 }
 
 template <int CH>
-static int launch_k1w(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uint8_t *mask, cudaStream_t st) {
+static int launch_k1w(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uint8_t *mask, cudaStream_t st, uint32_t *bits) {
     using namespace k1w;
     const int smem = (int)sizeof(WarpSmem<CH>);
     SVB_CUDA_OK(cudaFuncSetAttribute(fused_preprocess_warp_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1013,16 +1032,27 @@ static int launch_k1w(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uin
     }
     if (getenv("SVB_K1_NO_TMAP")) use_tmap = 0;
     dim3 grid(nstrips, nseg, n);
-    fused_preprocess_warp_kernel<CH><<<grid, 32, smem, st>>>(src, mask, h, w, rows_per_seg, tmap, use_tmap);
+    const int btx = w / 32 + 2, bty = (h + 31) / 32 + 2;  // contour::bit_tiles_x / _y
+    fused_preprocess_warp_kernel<CH><<<grid, 32, smem, st>>>(src, mask, h, w, rows_per_seg, tmap, use_tmap, (uint8_t *)bits, btx,
+                                                             (long long)btx * bty * 128);
     return check_launch(ctx, "fused_preprocess_warp_kernel");
 }
 
 // ch = 3: BGR frames (cv/preprocess.py:57-65); ch = 1: gray input, i.e. GaussianBlur 5 + adaptive threshold only
 // (the tail of cv/preprocess_v2.py:233-239)
-int launch_fused_preprocess(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uint8_t *mask, cudaStream_t st, int ch) {
+static bool k1_legacy() {
     static const bool legacy = getenv("SVB_K1_LEGACY") != nullptr;  // A/B switch: the CTA-per-strip kernel (k1::)
-    if (!legacy && (((uintptr_t)mask) & 7) == 0 && h >= 16)
-        return ch == 1 ? launch_k1w<1>(ctx, src, n, h, w, mask, st) : launch_k1w<3>(ctx, src, n, h, w, mask, st);
+    return legacy;
+}
+// true when launch_fused_preprocess will take the warp-per-strip kernel, which can also emit K2's tiled bit mask
+bool fused_preprocess_writes_bits(int h, int w, const void *mask) {
+    return !k1_legacy() && (((uintptr_t)mask) & 7) == 0 && h >= 16 && w % 32 == 0 && getenv("SVB_K1_NO_BITS") == nullptr;
+}
+
+int launch_fused_preprocess(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uint8_t *mask, cudaStream_t st, int ch, uint32_t *bits) {
+    if (!k1_legacy() && (((uintptr_t)mask) & 7) == 0 && h >= 16)
+        return ch == 1 ? launch_k1w<1>(ctx, src, n, h, w, mask, st, bits) : launch_k1w<3>(ctx, src, n, h, w, mask, st, bits);
+    if (bits) return SVB_ERR_INVALID;  // callers ask fused_preprocess_writes_bits first
     using namespace k1;
     SVB_CUDA_OK(cudaFuncSetAttribute(fused_preprocess_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
     SVB_CUDA_OK(cudaFuncSetAttribute(fused_preprocess_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));

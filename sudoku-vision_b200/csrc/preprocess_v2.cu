@@ -1095,7 +1095,7 @@ int launch_sauvola(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uint8_
 int launch_blur5(svb_ctx *, const uint8_t *, int, int, int, uint8_t *, cudaStream_t);
 int launch_adaptive(svb_ctx *, const uint8_t *, int, int, int, int, uint8_t *, cudaStream_t);
 bool fused_preprocess_supported(int h, int w);
-int launch_fused_preprocess(svb_ctx *, const uint8_t *, int, int, int, uint8_t *, cudaStream_t, int ch);
+int launch_fused_preprocess(svb_ctx *, const uint8_t *, int, int, int, uint8_t *, cudaStream_t, int ch, uint32_t *bits = nullptr);
 
 // GaussianBlur(5,5) + adaptiveThreshold(GAUSSIAN_C, BINARY_INV, 11, 2) of a gray image (cv/preprocess_v2.py:233-236):
 // K1's fused row-streaming kernel in its gray-input form when the frame qualifies, else the two stage kernels.

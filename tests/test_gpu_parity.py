@@ -140,6 +140,23 @@ def test_find_grid_contour_synthetic_frames(scanner, oracle):
             assert np.array_equal(c[i], want)
 
 
+@pytest.mark.parametrize("hw", [(270, 480), (200, 736), (300, 1920), (540, 960), (1080, 1920)])
+def test_scan_fused_bit_mask_matches_staged_path(scanner, hw):
+    """svb_scan_batch_v1 lets K1 write K2's tiled bit mask (no packing pass); the staged calls pack the byte mask inside
+    find_grid_contour.  Both must see the same contours: identical found flags and corners, including partial strips,
+    frames whose height is not a multiple of the 32-row tiles and repeated calls with a smaller batch."""
+    imgs, _, _ = _frames(5, hw[0], hw[1], 9300 + hw[0], rot=25.0)
+    imgs[3] = 127  # no grid
+    for n in (5, 2):
+        batch = _t(imgs[:n])
+        out = scanner.scan_batch(batch)
+        m = scanner.preprocess(batch)
+        c, f = scanner.find_grid_contour(m)
+        assert np.array_equal(out["found"].cpu().numpy(), f.cpu().numpy())
+        assert np.array_equal(out["corners"].cpu().numpy(), c.cpu().numpy())
+    assert int(f.sum()) >= 1
+
+
 def test_v2_contour_method(scanner, golden):
     """svb_detect_grid_contour_v2 vs the reference's cv/grid_v2.detect_grid_contour (golden)."""
     v = golden("v2")
