@@ -206,14 +206,19 @@ __global__ void warp_board_kernel(const uint8_t *__restrict__ bgr, int h, int w,
 }
 
 // ---- per-cell pipeline in shared memory --------------------------------------------------------------
-struct CellSmem {
+struct alignas(16) CellSmem {
     uint8_t crop[64 * 64];       // gray crop, up to 64x64 (40x40 for the 450 board)
     uint8_t cell[CELL * CELL];   // extract_cells output
     uint8_t eq[CELL * CELL];     // CLAHE output
     uint8_t lut[16][256];
     int hist[16][256];
-    float rp[CELL * CELL];       // Gaussian row pass
+    // Gaussian adaptive threshold: float copy of the CLAHE output with 5 replicated columns each side, and the row pass
+    // with 5 replicated rows above and below (BORDER_REPLICATE without index clamps); both alias the histograms, which are
+    // dead by then
 };
+constexpr int EQP = CELL + 10;   // padded row pitch of the float CLAHE output
+__device__ __forceinline__ float *eqf_of(CellSmem &s) { return reinterpret_cast<float *>(&s.hist[0][0]); }              // [28][38]
+__device__ __forceinline__ float *rpp_of(CellSmem &s) { return reinterpret_cast<float *>(&s.hist[0][0]) + CELL * EQP; }  // [38][28]
 
 // cv2.resize(crop, (28,28)) INTER_LINEAR, 11-bit fixed point
 __device__ __forceinline__ void resize_phase(CellSmem &s, const ResizeTab &rt) {
@@ -232,7 +237,7 @@ __device__ __forceinline__ void resize_phase(CellSmem &s, const ResizeTab &rt) {
 __device__ __forceinline__ void clahe_phase(CellSmem &s) {
     constexpr int TS = 7, NTL = 4, TA = 49;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    for (int i = tid; i < 16 * 256; i += blockDim.x) (&s.hist[0][0])[i] = 0;
+    for (int i = tid; i < 16 * 256 / 4; i += blockDim.x) reinterpret_cast<int4 *>(&s.hist[0][0])[i] = make_int4(0, 0, 0, 0);
     __syncthreads();
     for (int i = tid; i < CELL * CELL; i += blockDim.x) {
         const int y = i / CELL, x = i - y * CELL;
@@ -256,13 +261,17 @@ __device__ __forceinline__ void clahe_phase(CellSmem &s) {
         const int batch = excess / 256, resid = excess - batch * 256;
         const int step = resid > 0 ? max(256 / resid, 1) : 1;
         int run = 0;
+        int bq = (lane * 8) / step, br = (lane * 8) - bq * step;  // bin / step, bin % step: one division per lane, then counted up
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int bin = lane * 8 + k;
             int v = hv[k] + batch;
-            if (resid > 0 && (bin % step) == 0 && (bin / step) < resid) v += 1;
+            if (resid > 0 && br == 0 && bq < resid) v += 1;
             run += v;
             hv[k] = run;  // inclusive prefix inside the lane
+            if (++br == step) {
+                br = 0;
+                ++bq;
+            }
         }
         int incl = run;  // warp inclusive scan of lane totals
 #pragma unroll
@@ -305,21 +314,36 @@ __device__ __forceinline__ void clahe_phase(CellSmem &s) {
 __device__ __forceinline__ void threshold_phase(CellSmem &s, uint8_t *__restrict__ thr, float *__restrict__ pm1) {
     const float k[11] = {SVB_G11_0, SVB_G11_1, SVB_G11_2, SVB_G11_3, SVB_G11_4, SVB_G11_5,
                          SVB_G11_4, SVB_G11_3, SVB_G11_2, SVB_G11_1, SVB_G11_0};
-    for (int i = threadIdx.x; i < CELL * CELL; i += blockDim.x) {
-        const int y = i / CELL, x = i - y * CELL;
-        const uint8_t *row = s.eq + y * CELL;
-        float acc = __fmul_rn(k[0], (float)row[max(x - 5, 0)]);
-#pragma unroll
-        for (int t = 1; t < 11; ++t) acc = __fmaf_rn(k[t], (float)row[min(max(x - 5 + t, 0), CELL - 1)], acc);
-        s.rp[i] = acc;
+    float *eqf = eqf_of(s), *rpp = rpp_of(s);
+    // float copy of the CLAHE output, columns -5 .. 32 (replicated borders); the histograms' readers are behind a barrier
+    for (int i = threadIdx.x; i < CELL * EQP; i += blockDim.x) {
+        const int y = i / EQP, xp = i - y * EQP;
+        eqf[i] = (float)s.eq[y * CELL + min(max(xp - 5, 0), CELL - 1)];
     }
     __syncthreads();
     for (int i = threadIdx.x; i < CELL * CELL; i += blockDim.x) {
         const int y = i / CELL, x = i - y * CELL;
-        float acc = __fmul_rn(k[5], s.rp[i]);
+        const float *row = eqf + y * EQP + x;  // row[t] = column x - 5 + t
+        float acc = __fmul_rn(k[0], row[0]);
+#pragma unroll
+        for (int t = 1; t < 11; ++t) acc = __fmaf_rn(k[t], row[t], acc);
+        rpp[(y + 5) * CELL + x] = acc;
+        if (y == 0) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) rpp[j * CELL + x] = acc;
+        } else if (y == CELL - 1) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) rpp[(CELL + 5 + j) * CELL + x] = acc;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CELL * CELL; i += blockDim.x) {
+        const int y = i / CELL, x = i - y * CELL;
+        const float *col = rpp + (y + 5) * CELL + x;
+        float acc = __fmul_rn(k[5], col[0]);
 #pragma unroll
         for (int j = 1; j <= 5; ++j) {
-            const float sum = __fadd_rn(s.rp[min(y + j, CELL - 1) * CELL + x], s.rp[max(y - j, 0) * CELL + x]);
+            const float sum = __fadd_rn(col[j * CELL], col[-j * CELL]);
             if (x < 24) acc = __fmaf_rn(k[5 + j], sum, acc);
             else acc = __fadd_rn(acc, __fmul_rn(k[5 + j], sum));
         }
@@ -364,7 +388,9 @@ cells_from_frames_kernel(const uint8_t *__restrict__ bgr, int h, int w, const do
             const double Y0 = da(da(cy0, dm(mi[4], yd)), mi[5]);
             const double W0 = da(da(cw0, dm(mi[7], yd)), mi[8]);
             double Wd = da(W0, mw1);
-            Wd = (Wd != 0.0) ? 32.0 / Wd : 0.0;
+            // 32 / W == 32 * rn(1 / W) exactly (scaling by 2^5 commutes with rounding): the correctly rounded reciprocal is
+            // a shorter sequence than the general double division
+            Wd = (Wd != 0.0) ? dm(__drcp_rn(Wd), 32.0) : 0.0;
             double fx = dm(da(X0, mx1), Wd), fy = dm(da(Y0, my1), Wd);
             fx = fmin(fmax(fx, -2147483648.0), 2147483647.0);
             fy = fmin(fmax(fy, -2147483648.0), 2147483647.0);
