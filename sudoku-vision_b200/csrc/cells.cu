@@ -165,12 +165,12 @@ __device__ __forceinline__ uint32_t sample_bgr(const uint8_t *__restrict__ frame
 // S = (32-ay)*((32-ax)p00 + ax p01) + ay*((32-ax)p10 + ax p11), and the inner sums are 2-way dot products (dp2a).
 __device__ __forceinline__ uint32_t sample_gray_fast(const uint8_t *__restrict__ frame, int h, int w, int ix, int iy, int ax,
                                                      int ay) {
-    const long long a = ((long long)iy * w + ix) * 3;
+    const int a = (iy * w + ix) * 3;  // a frame is far smaller than 2 GB
     const uint32_t cx = (uint32_t)(32 - ax) | ((uint32_t)ax << 16);
     uint32_t rB[2], rG[2], rR[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-        const uintptr_t addr = reinterpret_cast<uintptr_t>(frame + a + (long long)r * w * 3);  // frames need not be 4-B aligned
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(frame + (a + r * w * 3));  // frames need not be 4-B aligned
         const uint32_t *p = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
         const uint32_t sh = (uint32_t)(addr & 3) * 8u;
         const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
@@ -233,6 +233,22 @@ __device__ __forceinline__ void resize_phase(CellSmem &s, const ResizeTab &rt) {
     }
 }
 
+// step = max(256 / resid, 1) and ceil(2^16 / step) (exact floor division of bins < 256 by step) for every residual count
+struct StepEntry {
+    int step, inv;
+};
+struct StepTab {
+    StepEntry e[256];
+    constexpr StepTab() : e{} {
+        for (int r = 0; r < 256; ++r) {
+            const int st = r > 0 ? (256 / r < 1 ? 1 : 256 / r) : 1;
+            e[r].step = st;
+            e[r].inv = (65536 + st - 1) / st;
+        }
+    }
+};
+__constant__ StepTab c_steptab = StepTab();
+
 // createCLAHE(2.0,(4,4)).apply on 28x28: 16 tiles of 7x7, clip 1
 __device__ __forceinline__ void clahe_phase(CellSmem &s) {
     constexpr int TS = 7, NTL = 4, TA = 49;
@@ -244,34 +260,33 @@ __device__ __forceinline__ void clahe_phase(CellSmem &s) {
         atomicAdd(&s.hist[(y / TS) * NTL + (x / TS)][s.cell[i]], 1);
     }
     __syncthreads();
-    int clip = (int)(2.0 * TA / 256.0);
-    clip = clip < 1 ? 1 : clip;
+    constexpr int clip = (2 * TA / 256) < 1 ? 1 : (2 * TA / 256);  // max(int(2.0 * 49 / 256), 1) = 1
+    static_assert(256 / (TA - clip) >= 4, "redistribution below assumes at most two incremented bins per 8-bin lane");
     const float lut_scale = 255.0f / (float)TA;
     for (int tile = warp; tile < 16; tile += nwarp) {
-        int hv[8];
-        int excess = 0;
+        const int4 ha = *reinterpret_cast<const int4 *>(&s.hist[tile][lane * 8]), hb = *reinterpret_cast<const int4 *>(&s.hist[tile][lane * 8 + 4]);
+        int hv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+        int kept = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            int v = s.hist[tile][lane * 8 + k];
-            if (v > clip) { excess += v - clip; v = clip; }
-            hv[k] = v;
+            hv[k] = min(hv[k], clip);
+            kept += hv[k];
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) excess += __shfl_xor_sync(0xffffffffu, excess, off);
-        const int batch = excess / 256, resid = excess - batch * 256;
-        const int step = resid > 0 ? max(256 / resid, 1) : 1;
+        for (int off = 16; off > 0; off >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, off);
+        const int excess = TA - kept;  // every pixel of the tile is in exactly one bin
+        const int batch = excess >> 8, resid = excess & 255;
+        // OpenCV hands the residual out to bins 0, step, 2 step, ... ((resid) of them), step = max(256 / resid, 1): at most two
+        // of them fall into this lane's 8 bins
+        const StepEntry se = c_steptab.e[resid];
+        const int lo = lane * 8, q = (lo * se.inv) >> 16, r = lo - q * se.step, m0 = q + (r != 0 ? 1 : 0);
+        const int p0 = m0 * se.step - lo, p1 = p0 + se.step;
+        const uint32_t incmask = ((p0 < 8 && m0 < resid) ? (1u << p0) : 0u) | ((p1 < 8 && m0 + 1 < resid) ? (1u << p1) : 0u);
         int run = 0;
-        int bq = (lane * 8) / step, br = (lane * 8) - bq * step;  // bin / step, bin % step: one division per lane, then counted up
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            int v = hv[k] + batch;
-            if (resid > 0 && br == 0 && bq < resid) v += 1;
-            run += v;
+            run += hv[k] + batch + (int)((incmask >> k) & 1u);
             hv[k] = run;  // inclusive prefix inside the lane
-            if (++br == step) {
-                br = 0;
-                ++bq;
-            }
         }
         int incl = run;  // warp inclusive scan of lane totals
 #pragma unroll
@@ -280,11 +295,13 @@ __device__ __forceinline__ void clahe_phase(CellSmem &s) {
             if (lane >= off) incl += t;
         }
         const int base = incl - run;
+        uint32_t lw[2] = {0u, 0u};
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float v = __fmul_rn((float)(base + hv[k]), lut_scale);
-            s.lut[tile][lane * 8 + k] = (uint8_t)min(max(__float2int_rn(v), 0), 255);
+        for (int k = 0; k < 8; ++k) {  // cumulative counts are <= TA, so the scaled value is already inside 0..255
+            const uint32_t b = (uint32_t)__float2int_rn(__fmul_rn((float)(base + hv[k]), lut_scale));
+            lw[k >> 2] |= b << (8 * (k & 3));
         }
+        *reinterpret_cast<uint2 *>(&s.lut[tile][lane * 8]) = make_uint2(lw[0], lw[1]);
     }
     __syncthreads();
     const float inv = 1.0f / (float)TS;
@@ -303,7 +320,20 @@ __device__ __forceinline__ void clahe_phase(CellSmem &s) {
         const float l21 = (float)s.lut[ty2 * NTL + tx1][v], l22 = (float)s.lut[ty2 * NTL + tx2][v];
         const float top = __fmul_rn(__fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa)), ya1);
         const float bot = __fmul_rn(__fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa)), ya);
-        s.eq[i] = (uint8_t)min(max(__float2int_rn(__fadd_rn(top, bot)), 0), 255);
+        const int ev = min(max(__float2int_rn(__fadd_rn(top, bot)), 0), 255);
+        s.eq[i] = (uint8_t)ev;
+        // the threshold phase reads a float copy with 5 replicated columns on each side (it aliases the histograms, which
+        // nobody reads any more: the LUTs were finished before the barrier above)
+        float *er = eqf_of(s) + y * EQP;
+        const float ef = (float)ev;
+        er[x + 5] = ef;
+        if (x == 0) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) er[j] = ef;
+        } else if (x == CELL - 1) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) er[CELL + 5 + j] = ef;
+        }
     }
     __syncthreads();
 }
@@ -315,12 +345,7 @@ __device__ __forceinline__ void threshold_phase(CellSmem &s, uint8_t *__restrict
     const float k[11] = {SVB_G11_0, SVB_G11_1, SVB_G11_2, SVB_G11_3, SVB_G11_4, SVB_G11_5,
                          SVB_G11_4, SVB_G11_3, SVB_G11_2, SVB_G11_1, SVB_G11_0};
     float *eqf = eqf_of(s), *rpp = rpp_of(s);
-    // float copy of the CLAHE output, columns -5 .. 32 (replicated borders); the histograms' readers are behind a barrier
-    for (int i = threadIdx.x; i < CELL * EQP; i += blockDim.x) {
-        const int y = i / EQP, xp = i - y * EQP;
-        eqf[i] = (float)s.eq[y * CELL + min(max(xp - 5, 0), CELL - 1)];
-    }
-    __syncthreads();
+    // eqf: float copy of the CLAHE output, columns -5 .. 32 (replicated borders), written by clahe_phase
     for (int i = threadIdx.x; i < CELL * CELL; i += blockDim.x) {
         const int y = i / CELL, x = i - y * CELL;
         const float *row = eqf + y * EQP + x;  // row[t] = column x - 5 + t
@@ -392,9 +417,9 @@ cells_from_frames_kernel(const uint8_t *__restrict__ bgr, int h, int w, const do
             // a shorter sequence than the general double division
             Wd = (Wd != 0.0) ? dm(__drcp_rn(Wd), 32.0) : 0.0;
             double fx = dm(da(X0, mx1), Wd), fy = dm(da(Y0, my1), Wd);
-            fx = fmin(fmax(fx, -2147483648.0), 2147483647.0);
-            fy = fmin(fmax(fy, -2147483648.0), 2147483647.0);
-            const int X = __double2int_rn(fx), Y = __double2int_rn(fy);
+            // cv2 clamps to [INT_MIN, INT_MAX] and rounds; cvt.rni.s32.f64 saturates to the same ends, and a NaN (degenerate
+            // homography) goes through fmax / fmin to INT_MIN
+            const int X = (fx != fx) ? (int)0x80000000 : __double2int_rn(fx), Y = (fy != fy) ? (int)0x80000000 : __double2int_rn(fy);
             const int ix = X >> 5, iy = Y >> 5, ax = X & 31, ay = Y & 31;
             uint32_t gv;
             // footprint inside the frame, and the 12-byte window of its second row inside the buffer

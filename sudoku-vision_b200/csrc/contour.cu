@@ -22,6 +22,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include <stdlib.h>
 #include "contour_core.cuh"
 
 namespace svb {
@@ -268,7 +269,8 @@ int launch_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, in
                              const uint32_t *ready_bits) {
     using namespace k2;
     const double min_area = min_area_ratio * (double)((long long)h * w);
-    const int pitch = contour::probe_pitch(min_area);
+    int pitch = contour::probe_pitch(min_area);
+    if (const char *e = getenv("SVB_K2_PITCH_DIV")) pitch = std::max(1, pitch / std::max(1, atoi(e)));  // tuning knob: denser probe lines
     const int nv = (w - 1) / pitch + 1, nh = (h - 1) / pitch + 1;
     const long long total = (long long)nv * h + (long long)nh * w;
     SVB_REQUIRE(total < (1ll << 30), SVB_ERR_UNSUPPORTED, "find_grid_contour: min_area_ratio too small for this image size");
