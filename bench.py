@@ -37,9 +37,9 @@ H, W = 1080, 1920
 METRIC = "frames/sec end-to-end (preprocess->warp->81-cell CNN) at 1080p"
 K1_BYTES_PER_FRAME = 3 * H * W + H * W  # 6,220,800 read + 2,073,600 written
 # dram__bytes_read.sum + dram__bytes_write.sum of k1w::fused_preprocess_warp_kernel per 1080p frame, from the ncu --set full
-# capture profiles/r1c_k1w_raw.csv (256 frames: 1.7692 GB read + 0.5114 GB written; the 32 staged halo/pad columns of every
+# capture profiles/r1d_k1w_raw.csv (256 frames: 1.7692 GB read + 0.5105 GB written; the 32 staged halo/pad columns of every
 # 240-column strip are the excess over the algorithmic 6.22 + 2.07 MB)
-K1_TRAFFIC_PER_FRAME = int((1.769187e9 + 0.511361e9) / 256)
+K1_TRAFFIC_PER_FRAME = int((1.769238e9 + 0.510463e9) / 256)
 # k5tc::tc_conv_kernel: conv1 + conv2 of ml/model.py:36-37, true MACs only: 225,792 + 3,612,672 per cell
 K5_CONV_FLOP_PER_CELL = 2 * (225792 + 3612672)
 
@@ -328,7 +328,7 @@ def main():
         value = Fn * world * args.steps / (ms_total * 1e-3)
         roof_k1 = {"bound": "hbm", "kernel": "k1w::fused_preprocess_warp_kernel", "achieved": achieved, "peak": peak,
                    "unit": "GB/s", "frac": achieved / peak, "traffic": K1_TRAFFIC_PER_FRAME * Fn,
-                   "traffic_source": "ncu --set full capture, profiles/r1c_k1w_raw.csv, scaled per frame",
+                   "traffic_source": "ncu --set full capture, profiles/r1d_k1w_raw.csv, scaled per frame",
                    "peak_source": how, "algorithmic_bytes_per_launch": K1_BYTES_PER_FRAME * Fn, "launch_ms": k1_ms}
         # the classifier's convolution kernel is the other large launch of a step: tensor-pipe bound, reported against the
         # sustained dense bf16 peak (it runs inside a long step); fp16 hi/lo split = 3 hardware MACs per algorithmic MAC
