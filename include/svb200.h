@@ -72,8 +72,7 @@ int svb_adaptive_threshold(svb_ctx *ctx, const uint8_t *gray, int n, int h, int 
 int svb_preprocess_v1(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *mask, void *stream);
 
 /* ---- V1: cv/preprocess_v2.py ------------------------------------------------------------------------- */
-/* Frame sides must divide by 8 (the 8x8 CLAHE tile grid; OpenCV pads other sizes, not implemented -> SVB_ERR_UNSUPPORTED),
- * be at least 32 px and at most 3990 px.  `channels` = 3 (BGR frames) or 1 (already gray: the reference's grayscale()
+/* Frame sides: at least 32 px, at most 3990 px; sides that do not divide by 8 get OpenCV's REFLECT_101-extended CLAHE tile grid.  `channels` = 3 (BGR frames) or 1 (already gray: the reference's grayscale()
  * passes 2-D input through, cv/preprocess_v2.py:33-37).
  * info (optional): uint8 [n][4] = {has_glare, has_shadow, method (0 adaptive, 1 otsu, 2 sauvola), Otsu level}.
  *

@@ -297,7 +297,7 @@ def preprocess_v2(bgr, use_illumination_norm: bool = True, use_shadow_removal: b
     out = np.empty((H, W), np.uint8)
     flags = (C.c_int * 2)()
     rc = lib().svo_preprocess_v2_opts(_p(bgr), H, W, int(use_illumination_norm), int(use_shadow_removal), _p(out), flags)
-    assert rc == 0, "frame sides must divide by 8"
+    assert rc == 0, "frame too small (minimum 32x32)"
     return out, bool(flags[0]), bool(flags[1])
 
 
@@ -313,7 +313,7 @@ def preprocess_multi(bgr):
     info = (C.c_int * 4)()
     scores = (C.c_double * 3)()
     rc = lib().svo_preprocess_multi(_p(bgr), H, W, _p(o[0]), _p(o[1]), _p(o[2]), _p(o[3]), info, scores)
-    assert rc == 0, "frame sides must divide by 8"
+    assert rc == 0, "frame too small (minimum 32x32)"
     return dict(binary=o[0], gray=o[1], enhanced=o[2], illumination_normalized=o[3], has_glare=bool(info[0]),
                 has_shadow=bool(info[1]), method_used=METHODS[info[2]], otsu_level=int(info[3]), scores=list(scores))
 

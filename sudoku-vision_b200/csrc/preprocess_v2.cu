@@ -475,21 +475,27 @@ __global__ void __launch_bounds__(NT, 2) ellipse_chords_kernel(const __grid_cons
 }  // namespace morph
 
 // ------------------------------------------------------------------------------------------------------------
-// CLAHE (createCLAHE(clip, (tiles, tiles)).apply) on frames whose sides divide by `tiles` — SURVEY App. A6
+// CLAHE (createCLAHE(clip, (tiles, tiles)).apply) — SURVEY App. A6.  th x tw is the tile size of the frame OpenCV works on:
+// the frame itself when both sides divide by `tiles`, else the frame extended at the bottom / right by tiles - side % tiles
+// (BORDER_REFLECT_101; both sides are extended as soon as one does not divide).  The histograms are taken over the extended
+// frame, the LUT blend runs over the original pixels with the extended tile size.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) clahe_lut_kernel(const u8 *__restrict__ src, u8 *__restrict__ lut, int h, int w,
-                                                        int tiles, int clip, float lut_scale) {
+                                                        int tiles, int th, int tw, int clip, float lut_scale) {
     __shared__ u32 s_h[8][256];
     __shared__ u32 s_red[8];
     const int f = blockIdx.y, tile = blockIdx.x, ty = tile / tiles, tx = tile - ty * tiles;
-    const int th = h / tiles, tw = w / tiles;
     const int tid = threadIdx.x, wid = tid >> 5;
     for (int i = tid; i < 8 * 256; i += 256) (&s_h[0][0])[i] = 0;
     __syncthreads();
-    const u8 *base = src + ((size_t)f * h + (size_t)ty * th) * w + (size_t)tx * tw;
+    const u8 *img = src + (size_t)f * h * w;
+    const int y0 = ty * th, x0 = tx * tw;
     for (int i = tid; i < th * tw; i += 256) {
         const int y = i / tw, x = i - y * tw;
-        atomicAdd(&s_h[wid][base[(size_t)y * w + x]], 1u);
+        int yy = y0 + y, xx = x0 + x;  // rows / columns past the frame: the REFLECT_101 extension
+        yy = yy >= h ? 2 * (h - 1) - yy : yy;
+        xx = xx >= w ? 2 * (w - 1) - xx : xx;
+        atomicAdd(&s_h[wid][img[(size_t)yy * w + xx]], 1u);
     }
     __syncthreads();
     u32 hv = 0;
@@ -1042,13 +1048,17 @@ int launch_dilate7(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uint8_
 
 int launch_clahe8(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uint8_t *lut, uint8_t *dst, cudaStream_t st) {
     const int tiles = 8;
-    SVB_REQUIRE(h % tiles == 0 && w % tiles == 0, SVB_ERR_UNSUPPORTED,
-                "CLAHE: frame sides must divide by the 8x8 tile grid (OpenCV pads other sizes; not implemented)");
-    const int th = h / tiles, tw = w / tiles, area = th * tw;
+    int he = h, we = w;
+    if (h % tiles || w % tiles) {  // OpenCV extends BOTH sides as soon as one does not divide
+        he = h + tiles - h % tiles;
+        we = w + tiles - w % tiles;
+    }
+    SVB_REQUIRE(he - h < h && we - w < w, SVB_ERR_UNSUPPORTED, "CLAHE: frame smaller than the 8x8 tile grid's padding");
+    const int th = he / tiles, tw = we / tiles, area = th * tw;
     int clip = (int)(2.0 * area / 256.0);
     if (clip < 1) clip = 1;
     const float lut_scale = 255.0f / (float)area;
-    clahe_lut_kernel<<<dim3(tiles * tiles, n), 256, 0, st>>>(src, lut, h, w, tiles, clip, lut_scale);
+    clahe_lut_kernel<<<dim3(tiles * tiles, n), 256, 0, st>>>(src, lut, h, w, tiles, th, tw, clip, lut_scale);
     int rc = check_launch(ctx, "clahe_lut_kernel");
     if (rc) return rc;
     clahe_apply_kernel<<<dim3((w + 255) / 256, h, n), 256, 0, st>>>(src, lut, dst, h, w, tiles, 1.0f / (float)tw, 1.0f / (float)th);
@@ -1197,8 +1207,6 @@ static int v2_front(svb_ctx *ctx, const uint8_t *bgr, const uint8_t *gray_in, in
 
 static int v2_size_ok(int n, int h, int w) {
     SVB_REQUIRE(n > 0 && n <= 65535 && h >= 32 && w >= 32 && h <= 65535, SVB_ERR_INVALID, "preprocess_v2: bad frame size (minimum 32x32)");
-    SVB_REQUIRE(h % 8 == 0 && w % 8 == 0, SVB_ERR_UNSUPPORTED,
-                "preprocess_v2: frame sides must divide by 8 (OpenCV pads the CLAHE tile grid otherwise; not implemented)");
     SVB_REQUIRE(illum_kernel_size(h, w) <= morph::MAXK, SVB_ERR_UNSUPPORTED, "preprocess_v2: frames above 3990 px are not supported");
     return SVB_OK;
 }

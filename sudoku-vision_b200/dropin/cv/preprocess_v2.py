@@ -1,7 +1,7 @@
 """Drop-in for cv/preprocess_v2.py — same names, arguments, defaults and return types; every function runs in
 libsvb200's CUDA kernels (svb_preprocess_v2 / svb_preprocess_multi_v2 / svb_v2_stage / svb_cell_prep), bit-identical
 to the OpenCV + numpy calls the reference makes.  Parameters the reference never varies raise NotImplementedError
-when changed (there is no CPU fallback); frame sides must divide by 8 for the CLAHE 8x8 grid."""
+when changed (there is no CPU fallback); frames of any size from 32x32 up (sides that do not divide by 8 get OpenCV's REFLECT_101-extended CLAHE tile grid)."""
 import os
 import sys
 from dataclasses import dataclass

@@ -63,10 +63,9 @@ def test_primitives_vs_oracle(scanner, oracle, hw):
         lvl, want = oracle.otsu_inv(imgs[i])
         assert int(_np(oinfo)[i, 3]) == lvl and np.array_equal(_np(ot)[i], want)
         assert np.array_equal(sv[i], oracle.sauvola(imgs[i]))
-    if hw[0] % 8 == 0 and hw[1] % 8 == 0:
-        cl = _np(scanner.v2_stage("clahe8", d)[0])
-        for i in range(2):
-            assert np.array_equal(cl[i], oracle.clahe_frame(imgs[i]))
+    cl = _np(scanner.v2_stage("clahe8", d)[0])  # sides that do not divide by 8: OpenCV's REFLECT_101-extended tile grid
+    for i in range(2):
+        assert np.array_equal(cl[i], oracle.clahe_frame(imgs[i]))
     masks = np.stack([((rng.random(hw) < p) * 255).astype(np.uint8) for p in (0.3, 0.7)])
     cu = _np(scanner.v2_stage("cleanup", _t(masks))[0])
     for i in range(2):
@@ -81,6 +80,37 @@ def test_ellipse_large_elements_and_wide_frames(scanner, oracle):
         for op, fn in (("dilate_ellipse", oracle.dilate_ellipse), ("erode_ellipse", oracle.erode_ellipse)):
             got = _np(scanner.v2_stage(op, _t(img), k)[0])[0]
             assert np.array_equal(got, fn(img[0], k)), f"{op} k={k} {h}x{w}"
+
+
+@pytest.mark.parametrize("hw", [(270, 484), (275, 480), (301, 517), (100, 203)])
+def test_whole_path_on_sides_that_do_not_divide_by_8(scanner, oracle, hw):
+    """preprocess_for_grid_detection / preprocess_multi_strategy on ragged frame sizes (CLAHE's padded tile grid, the
+    scalar column tails of the float Gaussian, unaligned rows everywhere): bit-exact against the oracle, which matches the
+    reference module on these sizes (checked in the build container)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sudoku-vision_b200"))
+    from svb200 import frames as F
+
+    h, w = hw
+    imgs = []
+    for k in range(2):
+        img = F.make_frame(7100 + h + k, h, w).image
+        if k:  # a shadow gradient and a glare patch, so both flags and another strategy come into play
+            xx = np.mgrid[0:h, 0:w][1]
+            img = (img.astype(np.float32) * (0.45 + 0.55 * xx[..., None] / w)).clip(0, 255).astype(np.uint8)
+            img[10:40, 10:60] = 255
+        imgs.append(img)
+    batch = _t(np.stack(imgs))
+    mask, info = scanner.preprocess_v2(batch)
+    r = scanner.preprocess_multi(batch)
+    for i, img in enumerate(imgs):
+        want, glare, shadow = oracle.preprocess_v2(img)
+        assert np.array_equal(_np(mask)[i], want)
+        assert _np(info)[i, :2].astype(bool).tolist() == [glare, shadow]
+        om = oracle.preprocess_multi(img)
+        for key in ("binary", "gray", "enhanced", "illumination_normalized"):
+            assert np.array_equal(_np(r[key])[i], om[key]), key
+        assert scanner.V2_METHODS[int(_np(r["info"])[i, 2])] == om["method_used"]
 
 
 def test_detect_glare_and_shadow(scanner, oracle, v2pre):
@@ -182,8 +212,10 @@ def test_full_size_4k(scanner, oracle):
 def test_unsupported_sizes_raise(scanner):
     import torch
 
-    with pytest.raises(NotImplementedError):
-        scanner.preprocess_v2(torch.zeros((1, 100, 100, 3), dtype=torch.uint8, device="cuda"))  # sides not / 8
+    m, _ = scanner.preprocess_v2(torch.zeros((1, 100, 100, 3), dtype=torch.uint8, device="cuda"))  # sides not / 8: supported
+    assert m.shape == (1, 100, 100)
+    with pytest.raises(NotImplementedError):  # the 4 x 4100-px illumination kernel is beyond the chord tables
+        scanner.preprocess_v2(torch.zeros((1, 64, 4104, 3), dtype=torch.uint8, device="cuda"))
     with pytest.raises(NotImplementedError):
         scanner.v2_stage("dilate_ellipse", torch.zeros((1, 64, 64), dtype=torch.uint8, device="cuda"), 401)
 

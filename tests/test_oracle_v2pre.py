@@ -88,8 +88,10 @@ def test_against_live_cv2(oracle):
         c = cv2.morphologyEx(m, cv2.MORPH_CLOSE, cv2.getStructuringElement(cv2.MORPH_RECT, (3, 3)))
         c = cv2.morphologyEx(c, cv2.MORPH_OPEN, cv2.getStructuringElement(cv2.MORPH_RECT, (2, 2)))
         assert np.array_equal(oracle.morph_cleanup(m), c)
-    g = cv2.GaussianBlur(rng.integers(0, 256, (96, 160)).astype(np.uint8), (3, 3), 0)
-    assert np.array_equal(oracle.clahe_frame(g), cv2.createCLAHE(clipLimit=2.0, tileGridSize=(8, 8)).apply(g))
+    # CLAHE incl. sides that do not divide by the 8x8 tile grid (OpenCV extends BOTH sides by REFLECT_101 then)
+    for hw in ((96, 160), (97, 160), (96, 163), (33, 47), (129, 131), (270, 484)):
+        g = cv2.GaussianBlur(rng.integers(0, 256, hw).astype(np.uint8), (3, 3), 0)
+        assert np.array_equal(oracle.clahe_frame(g), cv2.createCLAHE(clipLimit=2.0, tileGridSize=(8, 8)).apply(g)), hw
 
 
 def test_grid_quality_oracle_vs_reference_golden(golden, v2pre):
