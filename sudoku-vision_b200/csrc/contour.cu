@@ -98,19 +98,8 @@ find_crossings_kernel(const void *__restrict__ mask, int h, int w, int wp, int p
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= fs.nprobe) return;
     const View m = make_view<View>(mask, frame, h, w, wp);
-    int x, y;
-    if (id < nv * h) {  // vertical probe line x = k*pitch, scanning down: background above
-        x = (id / h) * pitch;
-        y = id % h;
-        if (!m.fg(x, y) || m.fg(x, y - 1)) return;
-    } else {            // horizontal probe line y = k*pitch, scanning right: background to the left
-        const int j = id - nv * h;
-        y = (j / w) * pitch;
-        x = j % w;
-        if (!m.fg(x, y) || m.fg(x - 1, y)) return;
-        // same walk state as the vertical crossing of this pixel: keep only that one
-        if (x % pitch == 0 && !m.fg(x, y - 1) && !m.fg(x - 1, y - 1)) return;
-    }
+    int x, y, dv;
+    if (!crossing_recorded(m, id, pitch, nv, x, y, dv)) return;
     const int g = atomicAdd(fs.gcount, 1);
     if (g >= fs.gcap) {
         atomicOr(&fs.status[frame], 1);
@@ -272,7 +261,7 @@ int launch_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, in
     int pitch = contour::probe_pitch(min_area);
     if (const char *e = getenv("SVB_K2_PITCH_DIV")) pitch = std::max(1, pitch / std::max(1, atoi(e)));  // tuning knob: denser probe lines
     const int nv = (w - 1) / pitch + 1, nh = (h - 1) / pitch + 1;
-    const long long total = (long long)nv * h + (long long)nh * w;
+    const long long total = 2 * ((long long)nv * h + (long long)nh * w);  // probe ids: four crossing kinds (contour_core.cuh)
     SVB_REQUIRE(total < (1ll << 30), SVB_ERR_UNSUPPORTED, "find_grid_contour: min_area_ratio too small for this image size");
     int cap = 4 * (h + w);
     cap = cap < 4096 ? 4096 : (cap > 65536 ? 65536 : cap);

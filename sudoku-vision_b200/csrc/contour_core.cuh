@@ -21,7 +21,7 @@ namespace contour {
 // (dx+1, dy+1) packed as 2-bit fields per direction: dx = {1,1,0,-1,-1,-1,0,1}, dy = {0,-1,-1,-1,0,1,1,1}
 SVB_HD int dir_dx(int d) { return (int)((0x901Au >> (2 * d)) & 3u) - 1; }
 SVB_HD int dir_dy(int d) { return (int)((0xA901u >> (2 * d)) & 3u) - 1; }
-constexpr int DIR_N = 2, DIR_W = 4;
+constexpr int DIR_E = 0, DIR_N = 2, DIR_W = 4, DIR_S = 6;
 
 struct MaskView {
     const uint8_t *p;
@@ -211,15 +211,39 @@ SVB_HD int trace_loop(const View &m, int qx, int qy, int dv, int max_steps, Visi
 }
 
 // ---- probe crossings and segments ----------------------------------------------------------------------------------
-// A "crossing" is a border-walk state on a probe line: pixel (x,y) foreground with x % P == 0 and the N neighbour
-// background (vertical, id = (x/P)*h + y), or y % P == 0 and the W neighbour background (horizontal,
-// id = nv*h + (y/P)*w + x).  Every border loop that matters passes through at least one crossing; walking from
-// each crossing only until the NEXT crossing splits every loop into independent segments, so each loop is walked
-// once in total (not once per crossing) and the longest dependent chain is a segment, not a loop.
-// A horizontal crossing whose N and NW neighbours are background too is the same walk state as the vertical
-// crossing of that pixel: it is an alias and is dropped.
-SVB_HD bool h_crossing_is_alias(unsigned nb, int x, int pitch) {
-    return (x % pitch == 0) && !(nb & (1u << DIR_N)) && !(nb & (1u << 3));
+// A "crossing" is a border-walk state on a probe line: a foreground pixel (x,y) visited with a background arc (the
+// background directions between the pixel the walk came from and the one it goes to) that contains
+//   N with x % P == 0  (kind 0, id =         (x/P)*h + y)      W with y % P == 0  (kind 1, id =     nv*h + (y/P)*w + x)
+//   S with x % P == 0  (kind 2, id = T +     (x/P)*h + y)      E with y % P == 0  (kind 3, id = T + nv*h + (y/P)*w + x)
+// with T = nv*h + nh*w.  Kinds 0/1 catch the top / left faces of a component, kinds 2/3 its bottom / right faces: without
+// them the whole lower-right half of a convex border is ONE segment however dense the probe lines are.  Every border loop
+// that matters passes through at least one crossing; walking from each crossing only until the NEXT crossing splits every
+// loop into independent segments, so each loop is walked once in total (not once per crossing) and the longest dependent
+// chain is a segment, not a loop.  One visit can satisfy several kinds (a corner pixel on two probe lines, a line end):
+// the lowest kind names the state, the others are aliases and are not recorded.
+SVB_HD int probe_total(int h, int w, int pitch, int nv) { return nv * h + ((h - 1) / pitch + 1) * w; }
+// background directions a and b belong to the same visit <=> one of the two ways round from a to b is all background
+SVB_HD bool same_bg_run(unsigned nb, int a, int b) {
+    const unsigned nb2 = nb | (nb << 8);
+    const unsigned ab = (nb2 >> a) & ((1u << ((b - a) & 7)) - 1u);  // directions a .. b-1 (counter-clockwise)
+    const unsigned ba = (nb2 >> b) & ((1u << ((a - b) & 7)) - 1u);  // directions b .. a-1
+    return ab == 0u || ba == 0u;
+}
+// Is probe id `id` a recorded crossing of this mask?  (x, y, dv) = its pixel and the background direction that defines it.
+SVB_HD void crossing_xy(int id, int h, int w, int pitch, int nv, int &x, int &y, int &dv);
+template <class View>
+SVB_HD bool crossing_recorded(const View &m, int id, int pitch, int nv, int &x, int &y, int &dv) {
+    crossing_xy(id, m.h, m.w, pitch, nv, x, y, dv);
+    if (!m.fg(x, y)) return false;
+    const unsigned nb = m.nbits(x, y);
+    if (nb & (1u << dv)) return false;  // the defining neighbour is foreground
+    const bool on_v = (x % pitch == 0), on_h = (y % pitch == 0);
+    const int kinds[4] = {DIR_N, DIR_W, DIR_S, DIR_E};
+    for (int k = 0; k < 4 && kinds[k] != dv; ++k) {  // a lower kind on this pixel in the same visit: this one is its alias
+        const bool on_line = (k & 1) ? on_h : on_v;
+        if (on_line && !(nb & (1u << kinds[k])) && same_bg_run(nb, kinds[k], dv)) return false;
+    }
+    return true;
 }
 struct Seg {
     long long area2;  // sum over the segment's steps of (x_i * y_{i+1} - x_{i+1} * y_i)
@@ -234,15 +258,18 @@ struct GEntry {       // one recorded crossing
     int frame, id;
 };
 SVB_HD void crossing_xy(int id, int h, int w, int pitch, int nv, int &x, int &y, int &dv) {
+    const int T = probe_total(h, w, pitch, nv);
+    const bool far_side = id >= T;  // kinds 2 / 3
+    if (far_side) id -= T;
     if (id < nv * h) {
         x = (id / h) * pitch;
         y = id % h;
-        dv = DIR_N;
+        dv = far_side ? DIR_S : DIR_N;
     } else {
         const int j = id - nv * h;
         y = (j / w) * pitch;
         x = j % w;
-        dv = DIR_W;
+        dv = far_side ? DIR_E : DIR_W;
     }
 }
 
@@ -251,7 +278,9 @@ SVB_HD void crossing_xy(int id, int h, int w, int pitch, int nv, int &x, int &y,
 // or -1 if max_steps was exceeded.
 template <class View, class Vis>
 SVB_HD int walk_segment(const View &m, int qx, int qy, int dv, int pitch, int nv, int max_steps, Vis &vis) {
-    const int self = (dv == DIR_N) ? (qx / pitch) * m.h + qy : nv * m.h + (qy / pitch) * m.w + qx;
+    const int T = probe_total(m.h, m.w, pitch, nv);
+    const int self = ((dv == DIR_N || dv == DIR_S) ? (qx / pitch) * m.h + qy : nv * m.h + (qy / pitch) * m.w + qx) +
+                     ((dv == DIR_S || dv == DIR_E) ? T : 0);
     typename CursorOf<View>::type cur;
     cur.init(m, qx, qy);
     unsigned nb = cur.nbits(qx, qy);
@@ -281,6 +310,8 @@ SVB_HD int walk_segment(const View &m, int qx, int qy, int dv, int pitch, int nv
         const int span = (dout - pd - 1) & 7;
         if (xr == 0 && ((DIR_N - pd - 1) & 7) < span) return xl * m.h + y;
         if (yr == 0 && ((DIR_W - pd - 1) & 7) < span) return nv * m.h + yl * m.w + x;
+        if (xr == 0 && ((DIR_S - pd - 1) & 7) < span) return T + xl * m.h + y;
+        if (yr == 0 && ((DIR_E - pd - 1) & 7) < span) return T + nv * m.h + yl * m.w + x;
     }
 }
 

@@ -41,7 +41,7 @@ static int run(const View &m, int h, int w, double min_area_ratio, double eps_ra
     const double min_area = min_area_ratio * (double)((long long)h * w);
     const int pitch = probe_pitch(min_area);
     const int nv = (w - 1) / pitch + 1, nh = (h - 1) / pitch + 1;
-    const int nprobe = nv * h + nh * w;
+    const int nprobe = 2 * (nv * h + nh * w);  // four crossing kinds
     const int max_steps = h * w * 2 + 16;
     int traces = 0;
     long long steps = 0;
@@ -50,16 +50,8 @@ static int run(const View &m, int h, int w, double min_area_ratio, double eps_ra
     std::vector<int> ids, map(nprobe, -1);
     std::vector<GEntry> glist;
     for (int id = 0; id < nprobe; ++id) {
-        int x, y;
-        if (id < nv * h) {
-            x = (id / h) * pitch; y = id % h;
-            if (!m.fg(x, y) || m.fg(x, y - 1)) continue;
-        } else {
-            int j = id - nv * h;
-            y = (j / w) * pitch; x = j % w;
-            if (!m.fg(x, y) || m.fg(x - 1, y)) continue;
-            if (x % pitch == 0 && !m.fg(x, y - 1) && !m.fg(x - 1, y - 1)) continue;  // alias of the vertical crossing
-        }
+        int x, y, dv;
+        if (!crossing_recorded(m, id, pitch, nv, x, y, dv)) continue;
         map[id] = (int)ids.size();
         ids.push_back(id);
         glist.push_back(GEntry{0, id});
