@@ -121,8 +121,16 @@ trace_segments_kernel(const void *__restrict__ mask, int h, int w, int wp, int p
     int x, y, dv;
     crossing_xy(id, h, w, pitch, nv, x, y, dv);
     Seg sg = trace_segment(m, x, y, dv, pitch, nv, max_steps);
-    if (sg.next_id < 0) atomicOr(&fs.status[frame], 4);
-    else sg.next_id = fs.map[(long long)frame * fs.nprobe + sg.next_id];  // probe id -> list index
+    if (sg.next_id < 0) {
+        atomicOr(&fs.status[frame], 4);
+    } else {
+        // probe id -> list index.  The map is only written at recorded crossings and never cleared: if the crossing list
+        // overflowed, the terminating crossing may be missing and its entry stale, so the entry is checked against the list.
+        const int nx = fs.map[(long long)frame * fs.nprobe + sg.next_id];
+        const bool ok = nx >= 0 && nx < min(*fs.gcount, fs.gcap) && fs.glist[nx].frame == frame && fs.glist[nx].id == sg.next_id;
+        if (!ok) atomicOr(&fs.status[frame], 1);
+        sg.next_id = ok ? nx : -1;
+    }
     fs.segs[g] = sg;
 }
 
@@ -281,7 +289,9 @@ int launch_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, in
     const int tx = contour::bit_tiles_x(w), ty = contour::bit_tiles_y(h);
     const int wp = tx * ty;  // tiles per frame
     const size_t o_bits = (use_bits && !ready_bits) ? take(sizeof(uint32_t) * (size_t)n * wp * 32) : 0;
-    const long long gcap_ll = std::min<long long>(std::max<long long>((long long)n * 512, 16384), (long long)n * (total / 2 + 1));
+    // crossings of the whole batch: 2048 per frame on average (a clean 1080p sudoku frame has a few hundred; masks full of
+    // small components have more), never more than the probe ids there are
+    const long long gcap_ll = std::min<long long>(std::max<long long>((long long)n * 2048, 16384), (long long)n * (total / 2 + 1));
     const int gcap = (int)std::min<long long>(gcap_ll, 1ll << 26);
     const size_t o_gc = take(sizeof(int)), o_gl = take(sizeof(GEntry) * (size_t)gcap), o_sg = take(sizeof(Seg) * (size_t)gcap);
     const size_t o_map = take(sizeof(int) * (size_t)n * total);

@@ -416,3 +416,31 @@ def test_v2_preprocess_on_a_reference_photo(scanner, oracle):
     want, glare, shadow = oracle.preprocess_v2(img)
     assert np.array_equal(_np(m)[0], want)
     assert [bool(x) for x in _np(info)[0, :2]] == [glare, shadow]
+
+
+def test_v2_contours_on_full_size_masks_are_complete_and_repeatable(scanner, oracle):
+    """The v2 masks of noisy 1080p frames hold thousands of small components, hence thousands of probe crossings per frame:
+    the crossing list must hold them (no frame may come back with status 2), and the result must not depend on the
+    order in which the crossings were packed (same corners on every repetition, equal to the oracle's)."""
+    from oracle import oracle_v2
+    from svb200 import frames as F
+    import torch
+
+    clean = _t(np.stack([F.make_frame(41000 + i, 1080, 1920).image for i in range(2)]))
+    batch = F.noisy_batch_device(clean, 24, seed=11)
+    r = scanner.preprocess_multi(batch, want_aux=False)
+    ref_c = ref_f = None
+    for rep in range(3):
+        c, f = scanner.detect_grid_contour_v2(r["binary"])
+        torch.cuda.synchronize()
+        c, f = _np(c), _np(f)
+        assert set(f.tolist()) <= {0, 1}, f"capacity status in {f.tolist()}"
+        if ref_c is None:
+            ref_c, ref_f = c, f
+        assert np.array_equal(c, ref_c) and np.array_equal(f, ref_f)
+    for i in (0, 23):
+        want = oracle_v2.detect_grid_contour(_np(r["binary"])[i])
+        assert (want is not None) == bool(ref_f[i] == 1)
+        if want is not None:
+            assert np.array_equal(ref_c[i].astype(np.float32), want)
+    assert int(ref_f.sum()) >= 20
