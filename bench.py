@@ -93,6 +93,40 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local: int) -> str:
+    """Pin this rank's host threads (and, by first touch, its pinned staging buffers) to the NUMA node its GPU hangs off:
+    with one rank per GPU all copying 55 GB/s from host memory at once, cross-socket traffic is what breaks e2e scaling."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(local).pci_bus_id  # e.g. 0000:1B:00.0 (older torch: absent)
+    except Exception:
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=20).stdout.strip()
+            bus = out[-12:] if len(out) >= 12 else out  # nvidia-smi prints an 8-digit domain
+        except Exception:
+            return "unbound"
+    try:
+        bus = bus.lower()
+        if len(bus.split(":")[0]) > 4:
+            bus = bus[-12:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return "unbound (no NUMA information)"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "unbound"
+        os.sched_setaffinity(0, cpus)
+        return f"numa node {node} ({len(cpus)} cpus)"
+    except Exception:
+        return "unbound"
+
+
 def cpu_leg(frames_np, seconds: float, mode: str) -> dict:
     """Runs oracle/cpu_bench.py in a clean subprocess on a bounded sample of the same workload."""
     import numpy as np
@@ -237,6 +271,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "unbound (single rank)"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -320,6 +356,7 @@ def main():
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host core, whatever this rank was bound to
         cpu = cpu_leg(batch[:16].cpu().numpy(), args.cpu_seconds, "pool")
     if rank == 0:
         peak, tpeak, how = measured_peaks()
@@ -347,7 +384,8 @@ def main():
                                    f"device-resident, whole path K1..K5 per step",
                        "frame": [H, W, 3], "frames_per_gpu": Fn, "classifier": "DigitCNN (ml/model.py) on tcgen05: fp16 hi+lo split operands, fp32 TMEM accumulators (logits within 1e-3 of fp32)",
                        "l2": f"inputs {Fn * H * W * 3 / 1e9:.1f} GB per step >> 126 MB L2 (no flush needed)",
-                       "sharding": f"image-sharded x{world}, no data-path collective", "grids_found": f"{found}/{Fn}"},
+                       "sharding": f"image-sharded x{world}, no data-path collective", "grids_found": f"{found}/{Fn}",
+                       "host_binding_rank0": numa},
             "e2e": {"value": En * world * args.steps / e2e_s, "unit": "frames/s",
                     "h2d_bytes_per_step": En * H * W * 3 * world, "d2h_bytes_per_step": En * (81 + 81 * 4 + 32 + 1) * world,
                     "frames_per_step": En, "matches_device_path": same},
