@@ -206,6 +206,14 @@ __global__ void warp_board_kernel(const uint8_t *__restrict__ bgr, int h, int w,
 }
 
 // ---- per-cell pipeline in shared memory --------------------------------------------------------------
+// The 28x28 pixels of a cell over the CTA: thread t < 112 owns column t % 28 and rows t / 28, +4, +8, ... (i = y*28 + x =
+// t + 112 k).  Seven full iterations, like a flat i += blockDim.x loop would need, but x is fixed per thread, so everything
+// that depends on the column only (resize taps, tile columns and blend weights, OpenCV's column classes) is computed once.
+static_assert(NT >= 4 * CELL, "the per-cell pixel loops need four rows of threads");
+#define SVB_FOR_CELL_PIXELS(x, y, i)                                                                          \
+    for (int x = (int)threadIdx.x % CELL, y = (int)threadIdx.x / CELL, i = (int)threadIdx.x; threadIdx.x < 4 * CELL && y < CELL; \
+         y += 4, i += 4 * CELL)
+
 struct alignas(16) CellSmem {
     uint8_t crop[64 * 64];       // gray crop, up to 64x64 (40x40 for the 450 board)
     uint8_t cell[CELL * CELL];   // extract_cells output
@@ -223,8 +231,7 @@ __device__ __forceinline__ float *rpp_of(CellSmem &s) { return reinterpret_cast<
 // cv2.resize(crop, (28,28)) INTER_LINEAR, 11-bit fixed point
 __device__ __forceinline__ void resize_phase(CellSmem &s, const ResizeTab &rt) {
     const int cw = rt.src;
-    for (int i = threadIdx.x; i < CELL * CELL; i += blockDim.x) {
-        const int y = i / CELL, x = i - y * CELL;
+    SVB_FOR_CELL_PIXELS(x, y, i) {
         const int sy = rt.s0[y], sy1 = min(sy + 1, cw - 1), sx = rt.s0[x], sx1 = min(sx + 1, cw - 1);
         const int b0 = rt.a0[y], b1 = rt.a1[y], a0 = rt.a0[x], a1 = rt.a1[x];
         const int h0 = s.crop[sy * cw + sx] * a0 + s.crop[sy * cw + sx1] * a1;
@@ -255,10 +262,7 @@ __device__ __forceinline__ void clahe_phase(CellSmem &s) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
     for (int i = tid; i < 16 * 256 / 4; i += blockDim.x) reinterpret_cast<int4 *>(&s.hist[0][0])[i] = make_int4(0, 0, 0, 0);
     __syncthreads();
-    for (int i = tid; i < CELL * CELL; i += blockDim.x) {
-        const int y = i / CELL, x = i - y * CELL;
-        atomicAdd(&s.hist[(y / TS) * NTL + (x / TS)][s.cell[i]], 1);
-    }
+    SVB_FOR_CELL_PIXELS(x, y, i) atomicAdd(&s.hist[(y / TS) * NTL + (x / TS)][s.cell[i]], 1);
     __syncthreads();
     constexpr int clip = (2 * TA / 256) < 1 ? 1 : (2 * TA / 256);  // max(int(2.0 * 49 / 256), 1) = 1
     static_assert(256 / (TA - clip) >= 4, "redistribution below assumes at most two incremented bins per 8-bin lane");
@@ -305,8 +309,7 @@ __device__ __forceinline__ void clahe_phase(CellSmem &s) {
     }
     __syncthreads();
     const float inv = 1.0f / (float)TS;
-    for (int i = tid; i < CELL * CELL; i += blockDim.x) {
-        const int y = i / CELL, x = i - y * CELL;
+    SVB_FOR_CELL_PIXELS(x, y, i) {
         const float tyf = __fadd_rn(__fmul_rn((float)y, inv), -0.5f);
         const float txf = __fadd_rn(__fmul_rn((float)x, inv), -0.5f);
         int ty1 = (int)floorf(tyf), tx1 = (int)floorf(txf);
@@ -346,8 +349,7 @@ __device__ __forceinline__ void threshold_phase(CellSmem &s, uint8_t *__restrict
                          SVB_G11_4, SVB_G11_3, SVB_G11_2, SVB_G11_1, SVB_G11_0};
     float *eqf = eqf_of(s), *rpp = rpp_of(s);
     // eqf: float copy of the CLAHE output, columns -5 .. 32 (replicated borders), written by clahe_phase
-    for (int i = threadIdx.x; i < CELL * CELL; i += blockDim.x) {
-        const int y = i / CELL, x = i - y * CELL;
+    SVB_FOR_CELL_PIXELS(x, y, i) {
         const float *row = eqf + y * EQP + x;  // row[t] = column x - 5 + t
         float acc = __fmul_rn(k[0], row[0]);
 #pragma unroll
@@ -362,8 +364,7 @@ __device__ __forceinline__ void threshold_phase(CellSmem &s, uint8_t *__restrict
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < CELL * CELL; i += blockDim.x) {
-        const int y = i / CELL, x = i - y * CELL;
+    SVB_FOR_CELL_PIXELS(x, y, i) {
         const float *col = rpp + (y + 5) * CELL + x;
         float acc = __fmul_rn(k[5], col[0]);
 #pragma unroll
