@@ -424,7 +424,7 @@ cells_from_frames_kernel(const uint8_t *__restrict__ bgr, int h, int w, const do
             const int ix = X >> 5, iy = Y >> 5, ax = X & 31, ay = Y & 31;
             uint32_t gv;
             // footprint inside the frame, and the 12-byte window of its second row inside the buffer
-            if (ix >= 0 && iy >= 0 && ix + 1 < w && iy + 1 < h && (iy + 2 < h || ix + 4 < w)) {
+            if ((unsigned)ix < (unsigned)(w - 1) && (unsigned)iy < (unsigned)(h - 1) && (iy + 2 < h || ix + 4 < w)) {
                 gv = sample_gray_fast(frame, h, w, ix, iy, ax, ay);
             } else {
                 Tap t;

@@ -90,16 +90,33 @@ __device__ __forceinline__ BitMaskView make_view<BitMaskView>(const void *base, 
     return BitMaskView{(const uint32_t *)base + (long long)frame * wp * 32, h, w, contour::bit_tiles_x(w)};
 }
 
-// K2a.1: one thread per probe-line pixel: record the crossings of every frame in ONE dense list
+// K2a.1: one thread per probe-line pixel and crossing kind: record the crossings of every frame in ONE dense list.
+// grid = (pixels along a line / 256, 2 * (nv + nh) lines x kinds, frames): no division to find the pixel.
 template <class View>
 __global__ void __launch_bounds__(256)
-find_crossings_kernel(const void *__restrict__ mask, int h, int w, int wp, int pitch, int nv, FrameScratch fs) {
-    const int frame = blockIdx.y;
-    const int id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= fs.nprobe) return;
+find_crossings_kernel(const void *__restrict__ mask, int h, int w, int wp, int pitch, int nv, int nh, FrameScratch fs) {
+    const int frame = blockIdx.z;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nl = nv + nh, T = nv * h + nh * w;
+    const bool far_side = (int)blockIdx.y >= nl;  // kinds S / E
+    const int l = (int)blockIdx.y - (far_side ? nl : 0);
+    int x, y, dv, id;
+    if (l < nv) {  // vertical probe line x = l * pitch
+        if (t >= h) return;
+        x = l * pitch;
+        y = t;
+        dv = far_side ? contour::DIR_S : contour::DIR_N;
+        id = l * h + t;
+    } else {       // horizontal probe line y = (l - nv) * pitch
+        if (t >= w) return;
+        y = (l - nv) * pitch;
+        x = t;
+        dv = far_side ? contour::DIR_E : contour::DIR_W;
+        id = nv * h + (l - nv) * w + t;
+    }
+    if (far_side) id += T;
     const View m = make_view<View>(mask, frame, h, w, wp);
-    int x, y, dv;
-    if (!crossing_recorded(m, id, pitch, nv, x, y, dv)) return;
+    if (!contour::crossing_recorded_at(m, x, y, dv, pitch)) return;
     const int g = atomicAdd(fs.gcount, 1);
     if (g >= fs.gcap) {
         atomicOr(&fs.status[frame], 1);
@@ -325,16 +342,16 @@ int launch_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, in
         if (rc) return rc;
         view_ptr = bits;
     }
-    dim3 grid1((unsigned)((total + 255) / 256), n);
+    dim3 grid1((unsigned)((std::max(h, w) + 255) / 256), (unsigned)(2 * (nv + nh)), n);
     const unsigned gblocks = (unsigned)((gcap + 127) / 128);
     if (use_bits) {
-        find_crossings_kernel<BitMaskView><<<grid1, 256, 0, st>>>(view_ptr, h, w, wp, pitch, nv, fs);
+        find_crossings_kernel<BitMaskView><<<grid1, 256, 0, st>>>(view_ptr, h, w, wp, pitch, nv, nh, fs);
         rc = check_launch(ctx, "k2::find_crossings_kernel<bits>");
         if (rc) return rc;
         trace_segments_kernel<BitMaskView><<<gblocks, 128, 0, st>>>(view_ptr, h, w, wp, pitch, nv, max_steps, fs);
         rc = check_launch(ctx, "k2::trace_segments_kernel<bits>");
     } else {
-        find_crossings_kernel<MaskView><<<grid1, 256, 0, st>>>(view_ptr, h, w, 0, pitch, nv, fs);
+        find_crossings_kernel<MaskView><<<grid1, 256, 0, st>>>(view_ptr, h, w, 0, pitch, nv, nh, fs);
         rc = check_launch(ctx, "k2::find_crossings_kernel");
         if (rc) return rc;
         trace_segments_kernel<MaskView><<<gblocks, 128, 0, st>>>(view_ptr, h, w, 0, pitch, nv, max_steps, fs);

@@ -231,9 +231,10 @@ SVB_HD bool same_bg_run(unsigned nb, int a, int b) {
 }
 // Is probe id `id` a recorded crossing of this mask?  (x, y, dv) = its pixel and the background direction that defines it.
 SVB_HD void crossing_xy(int id, int h, int w, int pitch, int nv, int &x, int &y, int &dv);
+// Is the walk state "pixel (x, y), background arc containing direction dv" a recorded crossing?  (x, y) lies on the probe
+// line that goes with dv (x % pitch == 0 for N / S, y % pitch == 0 for W / E).
 template <class View>
-SVB_HD bool crossing_recorded(const View &m, int id, int pitch, int nv, int &x, int &y, int &dv) {
-    crossing_xy(id, m.h, m.w, pitch, nv, x, y, dv);
+SVB_HD bool crossing_recorded_at(const View &m, int x, int y, int dv, int pitch) {
     if (!m.fg(x, y)) return false;
     const unsigned nb = m.nbits(x, y);
     if (nb & (1u << dv)) return false;  // the defining neighbour is foreground
@@ -244,6 +245,11 @@ SVB_HD bool crossing_recorded(const View &m, int id, int pitch, int nv, int &x, 
         if (on_line && !(nb & (1u << kinds[k])) && same_bg_run(nb, kinds[k], dv)) return false;
     }
     return true;
+}
+template <class View>
+SVB_HD bool crossing_recorded(const View &m, int id, int pitch, int nv, int &x, int &y, int &dv) {
+    crossing_xy(id, m.h, m.w, pitch, nv, x, y, dv);
+    return crossing_recorded_at(m, x, y, dv, pitch);
 }
 struct Seg {
     long long area2;  // sum over the segment's steps of (x_i * y_{i+1} - x_{i+1} * y_i)
