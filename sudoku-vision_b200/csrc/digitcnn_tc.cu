@@ -20,7 +20,9 @@
 //      (K order (pixel, channel); fc1's weights are permuted to match at pack time).
 // tc_fc_kernel: [cells x 3136] x [3136 x 128] with the same split, 128-cell tiles, cp.async double
 //   buffering into the canonical layout, then bias+ReLU, fc2 (128x10, CUDA cores), softmax-max/argmax.
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -527,6 +529,188 @@ tc_fc_kernel(const __half *__restrict__ feat_hi, const __half *__restrict__ feat
     if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
+// ================================================================================================
+// fc head, TMA edition: the same GEMM + epilogue as tc_fc_kernel, organised the Blackwell way.
+//   * operands arrive by TMA (cp.async.bulk.tensor.2d, 128 rows x 64 fp16 boxes, SWIZZLE_128B) into a 3-stage ring; one
+//     elected producer thread, full / empty mbarriers, nobody else touches the loads;
+//   * one elected thread issues the MMAs from swizzled K-major descriptors (SBO = 1024 B, +32 B per K = 16 step).  The lo
+//     weight tile follows the hi tile in shared memory, so A_hi x [W_hi | W_lo] is ONE N = 256 instruction: 8 MMAs per
+//     64-wide K chunk instead of 12, A_hi fetched once for two products;
+//   * accumulators are double-buffered in TMEM (2 x 256 columns): eight epilogue warps drain tile i while the MMAs of tile
+//     i+1 run.
+// ================================================================================================
+constexpr int FT_NS = 3;                      // smem stages
+constexpr int FT_TILE = 128 * FC_KC * 2;      // one 128-row x 64-k fp16 tile: 16 KB
+constexpr int FT_THREADS = 320;               // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
+
+struct FcTmaSmem {
+    alignas(1024) uint8_t A[FT_NS][2][FT_TILE];   // [stage][hi/lo] 128 cells x 64 k, 128B-swizzled rows
+    alignas(1024) uint8_t B[FT_NS][2][FT_TILE];   // [stage][hi/lo] 128 outputs x 64 k; lo directly after hi = rows 128..255
+    float fb1[128];
+    float fw2[128 * 10];
+    float fb2[16];
+    float part[2][128][10];
+    alignas(8) unsigned long long full[FT_NS], empty[FT_NS], acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int x, int y, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(tm), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
+// K-major operand tile with 128-byte swizzled rows (what TMA SWIZZLE_128B writes): 8-row groups are 1024 B apart, the
+// leading-dimension offset is unused, layout type 2 = SWIZZLE_128B.  The tile base must be 1024-byte aligned.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(FT_THREADS, 1)
+tc_fc_tma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                 const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, long long n_cells,
+                 const float *__restrict__ fb1, const float *__restrict__ fw2, const float *__restrict__ fb2,
+                 float *__restrict__ logits, uint8_t *__restrict__ digits, float *__restrict__ conf) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // the swizzle pattern TMA writes and the MMA reads is a function of the address bits: tiles must sit on 1024-byte boundaries
+    FcTmaSmem &s = *reinterpret_cast<FcTmaSmem *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < 128) s.fb1[tid] = fb1[tid];
+    for (int i = tid; i < 1280; i += FT_THREADS) s.fw2[i] = fw2[i];
+    if (tid < 10) s.fb2[tid] = fb2[tid];
+    if (tid == 0) {
+        for (int k = 0; k < FT_NS; ++k) {
+            mbar_init(&s.full[k], 1);
+            mbar_init(&s.empty[k], 1);
+        }
+        for (int k = 0; k < 2; ++k) {
+            mbar_init(&s.acc_full[k], 1);
+            mbar_init(&s.acc_empty[k], 8);  // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&s.tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s.tmem_base;
+    const long long n_tiles = (n_cells + 127) / 128;
+
+    if (warp == 8) {
+        // ---- TMA producer ------------------------------------------------------------------------------------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t ph = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m0 = (int)(tile * 128);
+                for (int c = 0; c < FC_NCHUNK; ++c) {
+                    mbar_wait(&s.empty[stage], ph ^ 1u);  // the MMAs that read this stage have committed
+                    mbar_expect_tx(&s.full[stage], 4u * FT_TILE);
+                    tma_load_2d(&s.A[stage][0][0], &tmA_hi, c * FC_KC, m0, &s.full[stage]);
+                    tma_load_2d(&s.A[stage][1][0], &tmA_lo, c * FC_KC, m0, &s.full[stage]);
+                    tma_load_2d(&s.B[stage][0][0], &tmW_hi, c * FC_KC, 0, &s.full[stage]);
+                    tma_load_2d(&s.B[stage][1][0], &tmW_lo, c * FC_KC, 0, &s.full[stage]);
+                    if (++stage == FT_NS) {
+                        stage = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ---- MMA issuer --------------------------------------------------------------------------------------------
+        if (lane == 0) {
+            const uint32_t idesc256 = make_idesc(128, 256), idesc128 = make_idesc(128, 128);
+            int stage = 0, it = 0;
+            uint32_t ph = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&s.acc_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));  // epilogue of tile it-2 has drained this buffer
+                tc_fence_after();
+                const uint32_t tacc = tmem + (uint32_t)(buf * 256);
+                for (int c = 0; c < FC_NCHUNK; ++c) {
+                    mbar_wait(&s.full[stage], ph);
+                    tc_fence_after();
+                    const uint64_t a_hi = make_desc_sw128(smem_u32(&s.A[stage][0][0])), a_lo = make_desc_sw128(smem_u32(&s.A[stage][1][0]));
+                    const uint64_t b_hl = make_desc_sw128(smem_u32(&s.B[stage][0][0]));  // rows 0..127 = W_hi, 128..255 = W_lo
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)  // [0,128) += A_hi W_hi ; [128,256) += A_hi W_lo
+                        umma_f16(tacc, a_hi + (uint64_t)(ks * 2), b_hl + (uint64_t)(ks * 2), idesc256, (c | ks) ? 1u : 0u);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)  // [0,128) += A_lo W_hi
+                        umma_f16(tacc, a_lo + (uint64_t)(ks * 2), b_hl + (uint64_t)(ks * 2), idesc128, 1u);
+                    umma_commit(&s.empty[stage]);
+                    if (++stage == FT_NS) {
+                        stage = 0;
+                        ph ^= 1u;
+                    }
+                }
+                umma_commit(&s.acc_full[buf]);
+            }
+        }
+    } else {
+        // ---- epilogue warps 0..7: TMEM -> fc1 bias + ReLU -> fc2 -> softmax-max / argmax ---------------------------------
+        const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const long long m0 = tile * 128;
+            mbar_wait(&s.acc_full[buf], (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            float acc10[10];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) acc10[k] = 0.f;
+#pragma unroll 1
+            for (int blk = 0; blk < 2; ++blk) {
+                uint32_t v[32], v2[32];
+                const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + half * 64 + blk * 32);
+                tmem_ld32(ta, v);
+                tmem_ld32(ta + 128, v2);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int k = half * 64 + blk * 32 + c;
+                    const float hsum = __uint_as_float(v[c]) + __uint_as_float(v2[c]);
+                    const float h = fmaxf(hsum + s.fb1[k], 0.f);
+#pragma unroll
+                    for (int o = 0; o < 10; ++o) acc10[o] = fmaf(s.fw2[k * 10 + o], h, acc10[o]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.acc_empty[buf]);  // this warp no longer reads the accumulator
+#pragma unroll
+            for (int o = 0; o < 10; ++o) s.part[half][row][o] = acc10[o];
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (tid < 128 && m0 + tid < n_cells) {
+                float l[10];
+                float mx = -INFINITY;
+                int am = 0;
+#pragma unroll
+                for (int o = 0; o < 10; ++o) {
+                    l[o] = s.part[0][tid][o] + s.part[1][tid][o] + s.fb2[o];
+                    logits[(m0 + tid) * 10 + o] = l[o];
+                    if (l[o] > mx) { mx = l[o]; am = o; }
+                }
+                float den = 0.f;
+#pragma unroll
+                for (int o = 0; o < 10; ++o) den += expf(l[o] - mx);
+                if (digits) digits[m0 + tid] = (uint8_t)am;
+                if (conf) conf[m0 + tid] = 1.0f / den;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 // ---- weight packing ---------------------------------------------------------------------------------------
 // conv2.weight (64,32,3,3) -> two canonical K-major images (hi, lo): element (n, k = tap*32 + ci) at
 // (n/8)*WB_SBO + (k/8)*128 + (n%8)*16 + (k%8)*2.   fc1.weight (128, 3136 [c*49+p]) -> [o][p*64 + c] hi/lo.
@@ -584,6 +768,35 @@ int digitcnn_tc_load(svb_ctx *ctx, const float *conv2_w, const float *fc1_w, cud
     return check_launch(ctx, "k5tc::pack_tc_kernel");
 }
 
+// [rows][3136] fp16 matrices as 2-D tensors with 128-row x 64-column boxes written in the 128-byte swizzle
+static bool fc_tensor_maps(const __half *a_hi, const __half *a_lo, const __half *w_hi, const __half *w_lo, long long n, CUtensorMap *tm) {
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn enc = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (encode_fn)p;
+    }();
+    if (!enc) return false;
+    const void *ptr[4] = {a_hi, a_lo, w_hi, w_lo};
+    const cuuint64_t rows[4] = {(cuuint64_t)n, (cuuint64_t)n, 128, 128};
+    for (int i = 0; i < 4; ++i) {
+        const cuuint64_t gdim[2] = {3136, rows[i]};
+        const cuuint64_t gstride[1] = {3136 * sizeof(__half)};
+        const cuuint32_t box[2] = {(cuuint32_t)k5tc::FC_KC, 128};
+        const cuuint32_t estride[2] = {1, 1};
+        memset(&tm[i], 0, sizeof(CUtensorMap));
+        if (enc(&tm[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr[i]), gdim, gstride, box, estride,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
+}
+
 int launch_digitcnn_tc(svb_ctx *ctx, const float *x, long long n, float *logits, uint8_t *digits, float *conf,
                        cudaStream_t st, cudaEvent_t mid) {
     using namespace k5tc;
@@ -602,6 +815,14 @@ int launch_digitcnn_tc(svb_ctx *ctx, const float *x, long long n, float *logits,
     if (rc) return rc;
     if (mid) cudaEventRecord(mid, st);  // stage timing: convolution stack | fc head
     const long long tiles = (n + 127) / 128;
+    static const bool fc_legacy = getenv("SVB_FC_LEGACY") != nullptr;  // A/B switch: the cp.async kernel
+    CUtensorMap tm[4];
+    if (!fc_legacy && n < (1LL << 31) && fc_tensor_maps(fh, fl, t->w_hi, t->w_lo, n, tm)) {
+        SVB_CUDA_OK(cudaFuncSetAttribute(tc_fc_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FcTmaSmem) + 1024));
+        tc_fc_tma_kernel<<<(int)min((long long)ctx->sm_count, tiles), FT_THREADS, sizeof(FcTmaSmem) + 1024, st>>>(
+            tm[0], tm[1], tm[2], tm[3], n, c.fc1_b, c.fc2_w, c.fc2_b, logits, digits, conf);
+        return check_launch(ctx, "k5tc::tc_fc_tma_kernel");
+    }
     tc_fc_kernel<<<(int)min((long long)ctx->sm_count, tiles), NT, sizeof(FcSmem), st>>>(fh, fl, n, t->w_hi, t->w_lo, c.fc1_b,
                                                                                        c.fc2_w, c.fc2_b, logits, digits, conf);
     return check_launch(ctx, "k5tc::tc_fc_kernel");
