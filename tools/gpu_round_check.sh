@@ -12,4 +12,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KN" -
 if [ "$1" != "quick" ]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_preprocess_warp -s 2 -c 1 -f -o gpurun_out/k1w python tools/k1_ab.py 256 1 > gpurun_out/ncu_k1.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:tc_conv -s 1 -c 1 -f -o gpurun_out/k5conv python tools/k5_ab.py 20736 1 > gpurun_out/ncu_k5.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:tc_fc_tma -s 1 -c 1 -f -o gpurun_out/k5fc python tools/k5_ab.py 82944 1 > gpurun_out/ncu_k5fc.log 2>&1
 fi
