@@ -933,17 +933,19 @@ fused_preprocess_warp_kernel(const uint8_t *__restrict__ src, uint8_t *__restric
                 orow += wl;
             }
             if (bits) {  // mask bytes are 0x00 / 0xff: bit 0 of the eight bytes -> one byte of the tiled bit mask, pixel k -> bit k
-                int yp = 4 * q - 5 + 32;                                           // padded row of output row 4q-5
-                long long boff = ((long long)(yp >> 5) * bits_tx * 32 + (yp & 31)) * 4;  // its word in this lane's tile column
+                // padded rows 4q+27 .. 4q+30: the first one is word 3, 7, .. or 31 of its tile, so the four rows are consecutive
+                // words of one tile unless the first is word 31 — then rows 1..3 are words 0..2 of the tile below
+                const int yp = 4 * q - 5 + 32;
+                const long long boff = ((long long)(yp >> 5) * bits_tx * 32 + (yp & 31)) * 4;
+                const long long below = ((yp & 31) == 31) ? (long long)(bits_tx * 32 - 32) * 4 : 0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const uint32_t t = (o32[0][i] & 0x01010101u) | ((o32[1][i] << 4) & 0x10101010u);
                     const uint32_t b = (t * 0x01020408u) >> 24;
-                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p st.global.u8 [%0], %1;\n}\n" ::"l"(blane + boff), "r"(b),
-                                 "r"((uint32_t)st_ok[i])
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p st.global.u8 [%0], %1;\n}\n" ::"l"(
+                                     blane + boff + 4 * i + (i ? below : 0)),
+                                 "r"(b), "r"((uint32_t)st_ok[i])
                                  : "memory");
-                    boff += ((yp & 31) == 31) ? (long long)(bits_tx * 32 - 31) * 4 : 4;  // next row: next word, or the tile below
-                    ++yp;
                 }
             }
         }
