@@ -131,8 +131,8 @@ struct ConvSmem {
     uint32_t tmem_base;
 };
 
-constexpr int NTC = 512;  // conv kernel: 15 worker warps (conv1, S writes) + 1 MMA-issue warp; all 16 run the epilogue
-constexpr int NWK = 480;  // worker threads
+constexpr int NTC = 512;  // conv kernel: 14 worker warps (conv1, S writes) + 2 MMA-issue warps (one per M tile); all 16 run the epilogue
+constexpr int NWK = 448;  // worker threads
 
 __device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(NWK) : "memory"); }
 
@@ -153,8 +153,8 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
     if (tid < 64) s.b2[tid] = b2[tid];
     for (int i = tid; i < 30 * 32; i += NTC) s.inp[i] = 0.f;
     if (tid == 0) {
-        mbar_init(&s.mbar[0], 1);
-        mbar_init(&s.mbar[1], 1);
+        mbar_init(&s.mbar[0], 2);  // both MMA-issue warps commit
+        mbar_init(&s.mbar[1], 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(&s.tmem_base, 512);
@@ -265,9 +265,10 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
     // the 14-bit start-address field
     const uint64_t a_desc0 = make_desc(s_base, SROWS * 16, 128), b_desc0 = make_desc(wb_base, 128, WB_SBO);
 
-    // warp 15 only issues MMAs (a ~5k-cycle serial instruction stream per cell); keeping it out of the conv1
-    // barriers lets the 15 worker warps convolve the next cell at full speed meanwhile
-    const bool mma_warp = (warp == 15);
+    // warps 14 and 15 only issue MMAs, one M tile each (the issue stream of a tile is ~550 serial instructions per cell, and
+    // the two tiles' accumulators are independent); keeping them out of the conv1 barriers lets the 14 worker warps convolve
+    // the next cell at full speed meanwhile
+    const bool mma_warp = (warp >= 14);
     // epilogue of one cell from TMEM buffer `buf`: TMEM -> 2x2 max-pool (shuffles) -> bias/ReLU -> fp16 hi/lo features.
     // 16 warps: TMEM lane quarter q = warp % 4 (hardware rule), tile j, 32-column half of the 64 channels.
     auto epilogue = [&](long long cell_e, int buf) {
@@ -335,6 +336,7 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
             const uint64_t a_desc_buf = a_desc0 + (uint64_t)((uint32_t)(buf * 2 * S_BYTES) >> 4);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
+                if (j != warp - 14) continue;  // this warp's tile
 #pragma unroll
                 for (int combo = 0; combo < 2; ++combo) {  // 0: A_hi x [B_hi|B_lo] (N=128), 1: A_lo x B_hi (N=64)
 #pragma unroll
