@@ -267,7 +267,11 @@ __device__ __forceinline__ void clahe_phase(CellSmem &s) {
     constexpr int clip = (2 * TA / 256) < 1 ? 1 : (2 * TA / 256);  // max(int(2.0 * 49 / 256), 1) = 1
     static_assert(256 / (TA - clip) >= 4, "redistribution below assumes at most two incremented bins per 8-bin lane");
     const float lut_scale = 255.0f / (float)TA;
-    for (int tile = warp; tile < 16; tile += nwarp) {
+    // four tiles per warp (the per-cell kernels run NT = 128 threads), unrolled so that the four independent reduce / scan
+    // chains overlap
+#pragma unroll
+    for (int tk = 0; tk < 16 / (NT / 32); ++tk) {
+        const int tile = warp + tk * (NT / 32);
         const int4 ha = *reinterpret_cast<const int4 *>(&s.hist[tile][lane * 8]), hb = *reinterpret_cast<const int4 *>(&s.hist[tile][lane * 8 + 4]);
         int hv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
         int kept = 0;
