@@ -215,6 +215,11 @@ struct WarpReduce {
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
         return v;
     }
+    static __device__ __forceinline__ double sumd(double v) {  // exact for the arc-length terms: the order does not matter
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, off));
+        return v;
+    }
     static __device__ __forceinline__ void sync() { __syncwarp(); }
 };
 

@@ -461,6 +461,25 @@ SVB_HD double arc_length_closed(const uint32_t *P, int n) {
     return s;
 }
 
+// The same sum, the segments dealt out to the lanes.  Every term is a float >= 1 (distinct pixels) below 2^13 carried in a
+// double, so any partial sum is a multiple of 2^-23 below 2^30: it is exact in 53 bits, hence the total does not depend
+// on the order of the additions and equals the sequential loop above bit for bit.  The result is returned to every lane.
+template <class Red>
+SVB_HD double arc_length_closed_lanes(const uint32_t *P, int n) {
+    if (n <= 1) return 0.0;
+    double s = 0.0;
+    for (int i = Red::lane(); i < n; i += Red::lanes()) {
+        const uint32_t a = P[i], b = P[i ? i - 1 : n - 1];
+        const float dx = (float)pt_x(a) - (float)pt_x(b), dy = (float)pt_y(a) - (float)pt_y(b);
+#if defined(__CUDA_ARCH__)
+        s += (double)__fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+#else
+        s += (double)sqrtf(dx * dx + dy * dy);
+#endif
+    }
+    return Red::sumd(s);
+}
+
 // ---- closed-curve approxPolyDP ------------------------------------------------------------------
 // Lane-cooperative: NL lanes scan index ranges in strides and reduce to the FIRST maximum (strict
 // '>' in index order, as cv2 does).  NL = 1 on the host.  `Red` supplies the reduction.
@@ -472,6 +491,7 @@ struct SerialReduce {
     static SVB_HD int bcast(int v) { return v; }
     static SVB_HD double bcast(double v) { return v; }
     static SVB_HD int sum(int v) { return v; }
+    static SVB_HD double sumd(double v) { return v; }
     static SVB_HD void sync() {}
 };
 
@@ -795,9 +815,7 @@ SVB_HD int select_quad(const View &m, const Cand *raw, int raw_count, Cand *list
         Red::sync();
         if (npts < 0) break;        // scratch capacity hit: give up on this frame, status says why
         if (nested[ci]) continue;   // inside another component's hole: RETR_EXTERNAL never returns it
-        double eps = 0.0;
-        if (lane == 0) eps = eps_ratio * arc_length_closed(chain, npts);
-        eps = Red::bcast(eps);
+        const double eps = eps_ratio * arc_length_closed_lanes<Red>(chain, npts);
         bool so = false;
         int mv = approx_poly_dp_closed<Red>(chain, npts, eps, poly, stack, STACK_CAP, &so);
         if (so) {
