@@ -313,6 +313,7 @@ SVB_HD int walk_segment(const View &m, int qx, int qy, int dv, int pitch, int nv
         nb = cur.nbits(x, y);
         dout = next_ccw(nb, pd);
         // is this visit a crossing state?  its background arc is the directions strictly between pd and dout (CCW)
+        if (xr != 0 && yr != 0) continue;  // not on a probe line (almost every step)
         const int span = (dout - pd - 1) & 7;
         if (xr == 0 && ((DIR_N - pd - 1) & 7) < span) return xl * m.h + y;
         if (yr == 0 && ((DIR_W - pd - 1) & 7) < span) return nv * m.h + yl * m.w + x;
