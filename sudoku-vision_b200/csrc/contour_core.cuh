@@ -343,10 +343,7 @@ struct SegStats {
         }
         if (keep) ++sg.kept;
         ++sg.steps;
-        if (dout >= 0) {
-            const int nx = x + dir_dx(dout), ny = y + dir_dy(dout);
-            sg.area2 += (long long)x * ny - (long long)nx * y;
-        }
+        if (dout >= 0) sg.area2 += x * dir_dy(dout) - y * dir_dx(dout);  // x*(y+dy) - (x+dx)*y, a step is one pixel
     }
 };
 
