@@ -134,7 +134,7 @@ struct BitCursor {
     uint32_t h0, h1, h2, h3, h4;   //                  bits [32*wq + 32, 32*wq + 64)
     SVB_HD void fetch(int yy, uint32_t &lo, uint32_t &hi) const {  // row yy in [-2, h+1]: zero pad rows exist
         const int yp = yy + 32;
-        const long long i = ((long long)(yp >> 5) * tx + wq) * 32 + (yp & 31);
+        const int i = ((yp >> 5) * tx + wq) * 32 + (yp & 31);  // words of ONE frame: far below 2^31
         lo = p[i];
         hi = p[i + 32];
     }
