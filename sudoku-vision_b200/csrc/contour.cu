@@ -289,7 +289,8 @@ int launch_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, in
     using namespace k2;
     const double min_area = min_area_ratio * (double)((long long)h * w);
     int pitch = contour::probe_pitch(min_area);
-    if (const char *e = getenv("SVB_K2_PITCH_DIV")) pitch = std::max(1, pitch / std::max(1, atoi(e)));  // tuning knob: denser probe lines
+    static const int pitch_div = [] { const char *e = getenv("SVB_K2_PITCH_DIV"); return e ? std::max(1, atoi(e)) : 1; }();  // tuning knob: denser probe lines
+    pitch = std::max(1, pitch / pitch_div);
     const int nv = (w - 1) / pitch + 1, nh = (h - 1) / pitch + 1;
     const long long total = 2 * ((long long)nv * h + (long long)nh * w);  // probe ids: four crossing kinds (contour_core.cuh)
     SVB_REQUIRE(total < (1ll << 30), SVB_ERR_UNSUPPORTED, "find_grid_contour: min_area_ratio too small for this image size");

@@ -1015,7 +1015,8 @@ static int launch_k1w(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uin
     const long long strips = (long long)nstrips * n;
     long long want = (8LL * 12 * ctx->sm_count + strips - 1) / strips;
     int nseg = (int)max(1LL, min(want, (long long)(h / 64)));
-    if (const char *e = getenv("SVB_K1_NSEG")) nseg = max(1, min(atoi(e), h / 16));  // tuning knob
+    static const int nseg_env = [] { const char *e = getenv("SVB_K1_NSEG"); return e ? atoi(e) : 0; }();  // tuning knob
+    if (nseg_env > 0) nseg = max(1, min(nseg_env, h / 16));
     int rows_per_seg = (((h + nseg - 1) / nseg) + 3) & ~3;
     nseg = (h + rows_per_seg - 1) / rows_per_seg;
     if (n > 65535 || nseg > 65535) return SVB_ERR_UNSUPPORTED;
@@ -1032,7 +1033,8 @@ static int launch_k1w(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uin
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     }
-    if (getenv("SVB_K1_NO_TMAP")) use_tmap = 0;
+    static const bool no_tmap = getenv("SVB_K1_NO_TMAP") != nullptr;  // A/B switch: 1-D bulk copies only
+    if (no_tmap) use_tmap = 0;
     dim3 grid(nstrips, nseg, n);
     const int btx = w / 32 + 2, bty = (h + 31) / 32 + 2;  // contour::bit_tiles_x / _y
     fused_preprocess_warp_kernel<CH><<<grid, 32, smem, st>>>(src, mask, h, w, rows_per_seg, tmap, use_tmap, (uint8_t *)bits, btx,
@@ -1048,7 +1050,8 @@ static bool k1_legacy() {
 }
 // true when launch_fused_preprocess will take the warp-per-strip kernel, which can also emit K2's tiled bit mask
 bool fused_preprocess_writes_bits(int h, int w, const void *mask) {
-    return !k1_legacy() && (((uintptr_t)mask) & 7) == 0 && h >= 16 && w % 32 == 0 && getenv("SVB_K1_NO_BITS") == nullptr;
+    static const bool no_bits = getenv("SVB_K1_NO_BITS") != nullptr;  // A/B switch: K2 packs the byte mask itself
+    return !k1_legacy() && !no_bits && (((uintptr_t)mask) & 7) == 0 && h >= 16 && w % 32 == 0;
 }
 
 int launch_fused_preprocess(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uint8_t *mask, cudaStream_t st, int ch, uint32_t *bits) {
