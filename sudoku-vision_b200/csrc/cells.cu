@@ -259,7 +259,7 @@ __constant__ StepTab c_steptab = StepTab();
 // createCLAHE(2.0,(4,4)).apply on 28x28: 16 tiles of 7x7, clip 1
 __device__ __forceinline__ void clahe_phase(CellSmem &s) {
     constexpr int TS = 7, NTL = 4, TA = 49;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 16 * 256 / 4; i += blockDim.x) reinterpret_cast<int4 *>(&s.hist[0][0])[i] = make_int4(0, 0, 0, 0);
     __syncthreads();
     SVB_FOR_CELL_PIXELS(x, y, i) atomicAdd(&s.hist[(y / TS) * NTL + (x / TS)][s.cell[i]], 1);
