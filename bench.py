@@ -365,7 +365,9 @@ def main():
         value = Fn * world * args.steps / (ms_total * 1e-3)
         roof_k1 = {"bound": "hbm", "kernel": "k1w::fused_preprocess_warp_kernel", "achieved": achieved, "peak": peak,
                    "unit": "GB/s", "frac": achieved / peak, "traffic": K1_TRAFFIC_PER_FRAME * Fn,
-                   "traffic_source": "ncu --set full capture, profiles/r1d_k1w_raw.csv, scaled per frame",
+                   "traffic_source": "ncu --set full capture of the same kernel through svb_preprocess_v1, profiles/r1d_k1w_raw.csv, scaled per "
+                                     "frame; in the whole-path call it also writes the 0.27 MB/frame bit mask K2 traces (not in `traffic`, "
+                                     "nor in the algorithmic bytes)",
                    "peak_source": how, "algorithmic_bytes_per_launch": K1_BYTES_PER_FRAME * Fn, "launch_ms": k1_ms}
         # the classifier's convolution kernel is the other large launch of a step: tensor-pipe bound, reported against the
         # sustained dense bf16 peak (it runs inside a long step); fp16 hi/lo split = 3 hardware MACs per algorithmic MAC
