@@ -105,6 +105,37 @@ def test_find_grid_contour_oracle_and_product_core(oracle, contour_host):
     assert hits > 40
 
 
+def test_product_core_on_noisy_masks_and_dense_probe_grids(oracle, contour_host):
+    """Salt noise, full-width / full-height lines and tiny area floors: thousands of small loops, single-pixel loops and line
+    ends ON the probe lines, i.e. every alias case of the four crossing kinds (contour_core.cuh).  The product core must
+    either agree with the oracle or report the candidate-capacity status (2), never a different quad."""
+    rng = _rng(2024)
+    n = hits = cap = 0
+    for s in range(240):
+        bits = s % 2 == 1
+        h = int(rng.integers(24, 160))
+        w = 32 * int(rng.integers(1, 7)) if bits else int(rng.integers(24, 200))
+        m = _shapes_mask(rng, h, w)
+        if s % 3 == 0:
+            m[rng.random((h, w)) < 0.03] = 255
+            m[int(rng.integers(0, h)), :] = 255
+            m[:, int(rng.integers(0, w))] = 255
+        if s % 5 == 0:
+            m[rng.random((h, w)) < 0.5] = 0
+        for ratio in (0.0005, 0.004, 0.02, 0.1):
+            want = oracle.find_grid_contour(m, ratio, 0.02)
+            f, c = contour_host(m, ratio, 0.02, use_bits=bits)
+            n += 1
+            if f == 2:
+                cap += 1
+                continue
+            assert f in (0, 1) and (f == 1) == (want is not None), (s, ratio)
+            if want is not None:
+                hits += 1
+                assert np.array_equal(want, c), (s, ratio)
+    assert hits > 150 and cap < n // 10
+
+
 def test_warp_extract_cellprep(oracle):
     rng = _rng(17)
     img = cv2.GaussianBlur(rng.integers(0, 256, (300, 400, 3)).astype(np.uint8), (5, 5), 0)
