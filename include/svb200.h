@@ -109,6 +109,23 @@ int svb_v2_stage(svb_ctx *ctx, int op, const uint8_t *src, int n, int h, int w, 
  * corners: int32 [n][4][2] (x, y) in approxPolyDP output order; found: uint8 [n] (0 = None). */
 int svb_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, int w, double min_area_ratio,
                           double eps_ratio, int32_t *corners, uint8_t *found, void *stream);
+
+/* find_contours(binary)  cv/grid.py:16-21  (cv2.findContours RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) for ONE mask [h][w]:
+ * EVERY top-level contour in cv2's order (reverse raster order of the start pixels), each starting at its component's
+ * raster-first pixel.  A debug / tooling helper (cv/test_pipeline.py:21-23); the scan path never materialises this list.
+ * Two calls: _count floods the outer background, finds the start pixels and walks every border once; it SYNCHRONISES
+ * `stream` and returns the totals through the two host pointers.  _fetch (same ctx, same mask, right after) writes
+ * points int32 [n_points][2] = (x, y) and offsets int64 [n_contours + 1] (device pointers; contour i is
+ * points[offsets[i] .. offsets[i+1])) asynchronously. */
+int svb_find_contours_count(svb_ctx *ctx, const uint8_t *mask, int h, int w, long long *host_n_contours,
+                            long long *host_n_points, void *stream);
+int svb_find_contours_fetch(svb_ctx *ctx, const uint8_t *mask, int h, int w, int32_t *points, long long *offsets, void *stream);
+/* approximate_polygon(contour, epsilon_ratio=0.02)  cv/grid.py:24-34  (cv2.arcLength(closed) and the closed-curve
+ * cv2.approxPolyDP of OpenCV 4.13: point-to-segment distances, first-maximum ties, final clean-up pass).
+ * contour int32 [n_points][2] with coordinates in [0, 65535]; out int32 [n_points][2] (capacity); n_out (device int32):
+ * vertex count, -1 = a coordinate outside [0, 65535], -2 = scratch exhausted. */
+int svb_approx_poly_dp(svb_ctx *ctx, const int32_t *contour, int n_points, double epsilon_ratio, int32_t *out, int32_t *n_out,
+                       void *stream);
 /* v2 contour method: detect_grid_contour(binary, min_area_ratio=0.1)  cv/grid_v2.py:102-128 — as above, but a
  * 4-gon must also pass is_valid_quadrilateral (cv/grid_v2.py:64-95: angles in [45,135] deg, longest side <= 2x
  * shortest) or the search continues with the next contour; corners come back ORDERED (order_points,
@@ -135,6 +152,11 @@ int svb_extract_cells(svb_ctx *ctx, const uint8_t *board, int n, int size, uint8
  *   pm1     float [n_cells][1][28][28] = the tensor fed to the model (exactly -1 / +1) */
 int svb_cell_prep(svb_ctx *ctx, const uint8_t *cells, long long n_cells, uint8_t *thresh, float *pm1,
                   void *stream);
+/* is_cell_empty(cell, threshold=0.02)  cv/extract.py:59-79: cv2.threshold(THRESH_BINARY_INV + THRESH_OTSU), countNonZero,
+ * (non_zero / total) < threshold.  cells uint8 [n_cells][cell_h][cell_w]; empty uint8 [n_cells] (1 = empty);
+ * info (optional) int32 [n_cells][2] = {Otsu level, non-zero count}. */
+int svb_is_cell_empty(svb_ctx *ctx, const uint8_t *cells, int n_cells, int cell_h, int cell_w, double threshold, uint8_t *empty,
+                      int32_t *info, void *stream);
 
 /* Fused G3+G4+E1+C1+C2 for the batched path: frames + corners -> cells, no 450x450 board in HBM.
  * cells_u8 (optional): uint8 [n][81][28][28] = extract_cells output.

@@ -53,7 +53,7 @@ class _StagedReference:
         warped = R.warp_perspective(image, corners)           # run.py:278
         cells = R.extract_cells(warped)                       # run.py:286
         preds = R.predict_cells(cells, self.model, self.device)  # run.py:302
-        return dict(found=True, grid=R.build_grid(preds))     # run.py:306
+        return dict(found=True, grid=R.build_grid(preds), corners=corners)     # run.py:306
 
 
 def _init(frames_path, weights_path, threads, ref_root=None):
@@ -84,6 +84,15 @@ def _work(args):
     return count, found
 
 
+def _result_of(i):
+    """what the scanner reads off sample frame i: (found, corners (4,2) int32 in approxPolyDP order, 9x9 grid)"""
+    r = _G["scanner"].scan(np.ascontiguousarray(_G["frames"][i]))
+    if not r["found"]:
+        return 0, np.zeros((4, 2), np.int32), np.zeros((9, 9), np.uint8)
+    grid = r["grid"] if "grid" in r else r["digits"]  # the staged reference builds a 9x9 list, the port keeps 81 digits
+    return 1, np.asarray(r["corners"], np.int32).reshape(4, 2), np.asarray(grid, np.uint8).reshape(9, 9)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", required=True, help=".npy of (n,H,W,3) uint8 frames")
@@ -92,6 +101,7 @@ def main():
     ap.add_argument("--workers", type=int, default=0, help="0 = os.cpu_count()")
     ap.add_argument("--mode", choices=["pool", "single"], default="pool")
     ap.add_argument("--ref-root", default=None, help="staged copy of the reference tree (baseline/_ref/sudoku-vision)")
+    ap.add_argument("--results", default=None, help="write found / corners / grid of every sample frame to this .npz (untimed)")
     a = ap.parse_args()
     os.environ["CUDA_VISIBLE_DEVICES"] = ""  # the CPU baseline: the reference's load_model must not find a GPU
     kind = "reference" if ref_root_usable(a.ref_root) else "port"
@@ -101,6 +111,10 @@ def main():
     if a.mode == "single":
         _init(a.frames, a.weights, 0, a.ref_root)
         _work((0, 2))  # warm-up
+        if a.results:
+            res = [_result_of(i) for i in range(len(_G["frames"]))]
+            np.savez(a.results, found=np.array([r[0] for r in res], np.uint8), corners=np.stack([r[1] for r in res]),
+                     grid=np.stack([r[2] for r in res]))
         done = found = 0
         t0 = time.perf_counter()
         while time.perf_counter() - t0 < a.seconds:
@@ -118,6 +132,11 @@ def main():
         ctx = mp.get_context("fork")
         with ctx.Pool(workers, initializer=_init, initargs=(a.frames, a.weights, 1, a.ref_root)) as pool:
             pool.map(_work, [(i, 1) for i in range(workers)])  # warm-up: import + first frame per worker
+            if a.results:  # untimed: the boards of the sample frames, for bench.py's parity block
+                nfr = len(np.load(a.frames, mmap_mode="r"))
+                res = pool.map(_result_of, range(nfr))
+                np.savez(a.results, found=np.array([r[0] for r in res], np.uint8), corners=np.stack([r[1] for r in res]),
+                         grid=np.stack([r[2] for r in res]))
             done = found = 0
             chunk = 2
             t0 = time.perf_counter()

@@ -70,6 +70,11 @@ int launch_solve(svb_ctx *, const uint8_t *, int, uint8_t *, int8_t *, cudaStrea
 int launch_top3(svb_ctx *, const float *, const uint8_t *, long long, uint8_t *, float *, uint8_t *, float *, cudaStream_t);
 bool digitcnn_v3_loaded(const svb_ctx *);
 int launch_mask_not_found(svb_ctx *, const uint8_t *, int, uint8_t *, float *, cudaStream_t);
+int find_contours_count(svb_ctx *, const uint8_t *, int, int, long long *, long long *, cudaStream_t);
+int find_contours_fetch(svb_ctx *, const uint8_t *, int, int, int32_t *, long long *, cudaStream_t);
+void find_contours_free(svb_ctx *);
+int launch_approx_poly(svb_ctx *, const int32_t *, int, double, int32_t *, int *, cudaStream_t);
+int launch_cell_empty(svb_ctx *, const uint8_t *, int, int, double, uint8_t *, int32_t *, cudaStream_t);
 
 }  // namespace svb
 
@@ -117,11 +122,13 @@ API void svb_destroy(svb_ctx *ctx) {
             wk = nullptr;
         }
     for (int i = 0; i < AR_COUNT; ++i) ctx->arena[i].release();
+    find_contours_free(ctx);
     if (!ctx->is_worker) {
         digitcnn_free(ctx);
         digitcnn_v3_free(ctx);
     }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->weights_ready) cudaEventDestroy(ctx->weights_ready);
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -176,7 +183,7 @@ API int svb_adaptive_threshold(svb_ctx *ctx, const uint8_t *gray, int n, int h, 
 static int preprocess_any(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *mask, cudaStream_t st,
                           const uint32_t **bits_out = nullptr) {
     if (bits_out) *bits_out = nullptr;
-    if (fused_preprocess_supported(h, w) && ((uintptr_t)bgr % 16 == 0) && ((uintptr_t)mask % 4 == 0)) {
+    if (fused_preprocess_supported(h, w) && ((uintptr_t)bgr % 16 == 0) && ((uintptr_t)mask % 8 == 0)) {
         uint32_t *bits = nullptr;
         if (bits_out && fused_preprocess_writes_bits(h, w, mask)) bits = contour_bits_buffer(ctx, n, h, w, st);
         const int rc = launch_fused_preprocess(ctx, bgr, n, h, w, mask, st, 3, bits);
@@ -245,6 +252,35 @@ API int svb_detect_grid_contour_v2(svb_ctx *ctx, const uint8_t *mask, int n, int
     return launch_find_grid_contour(ctx, mask, n, h, w, min_area_ratio, 0.02, corners, found, (cudaStream_t)stream, 1);
 }
 
+API int svb_find_contours_count(svb_ctx *ctx, const uint8_t *mask, int h, int w, long long *host_n_contours,
+                                long long *host_n_points, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(mask && host_n_contours && host_n_points && dims_ok(1, h, w) && w <= 65535, SVB_ERR_INVALID,
+                "svb_find_contours_count: bad arguments");
+    return find_contours_count(ctx, mask, h, w, host_n_contours, host_n_points, (cudaStream_t)stream);
+}
+
+API int svb_find_contours_fetch(svb_ctx *ctx, const uint8_t *mask, int h, int w, int32_t *points, long long *offsets, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(mask && offsets && dims_ok(1, h, w), SVB_ERR_INVALID, "svb_find_contours_fetch: bad arguments");
+    return find_contours_fetch(ctx, mask, h, w, points, offsets, (cudaStream_t)stream);
+}
+
+API int svb_approx_poly_dp(svb_ctx *ctx, const int32_t *contour, int n_points, double epsilon_ratio, int32_t *out, int32_t *n_out,
+                           void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(contour && out && n_out && n_points > 0 && epsilon_ratio >= 0.0, SVB_ERR_INVALID, "svb_approx_poly_dp: bad arguments");
+    return launch_approx_poly(ctx, contour, n_points, epsilon_ratio, out, n_out, (cudaStream_t)stream);
+}
+
+API int svb_is_cell_empty(svb_ctx *ctx, const uint8_t *cells, int n_cells, int cell_h, int cell_w, double threshold, uint8_t *empty,
+                          int32_t *info, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(cells && empty && n_cells > 0 && cell_h > 0 && cell_w > 0 && (long long)cell_h * cell_w < (1 << 30), SVB_ERR_INVALID,
+                "svb_is_cell_empty: bad arguments");
+    return launch_cell_empty(ctx, cells, n_cells, cell_h * cell_w, threshold, empty, info, (cudaStream_t)stream);
+}
+
 API int svb_warp_perspective(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, const int32_t *corners,
                              const uint8_t *found, int out_size, uint8_t *board, void *stream) {
     GUARD(ctx);
@@ -278,7 +314,12 @@ API int svb_digitcnn_load(svb_ctx *ctx, const float *conv1_w, const float *conv1
     GUARD(ctx);
     const float *w[8] = {conv1_w, conv1_b, conv2_w, conv2_b, fc1_w, fc1_b, fc2_w, fc2_b};
     for (int i = 0; i < 8; ++i) SVB_REQUIRE(w[i] != nullptr, SVB_ERR_INVALID, "svb_digitcnn_load: null weight pointer");
-    return digitcnn_load(ctx, w, (cudaStream_t)stream);
+    const int rc = digitcnn_load(ctx, w, (cudaStream_t)stream);
+    if (rc) return rc;
+    // the host-buffer path runs on the library's own streams: they wait for this event instead of a device-wide sync
+    if (!ctx->weights_ready) SVB_CUDA_OK(cudaEventCreateWithFlags(&ctx->weights_ready, cudaEventDisableTiming));
+    SVB_CUDA_OK(cudaEventRecord(ctx->weights_ready, (cudaStream_t)stream));
+    return SVB_OK;
 }
 
 API int svb_digitcnn_forward(svb_ctx *ctx, const float *x, long long n, float *logits, uint8_t *digits, float *conf,
@@ -471,28 +512,36 @@ API int svb_scan_batch_v1_host(svb_ctx *ctx, const uint8_t *host_bgr, int n, int
     for (int s = 0; s < 2; ++s) {
         int rc = get_worker(ctx, s, &wk[s]);
         if (rc) return rc;
-        if (wk[s]->arena[AR_STAGE].reserve(total) != SVB_OK) return SVB_ERR_CUDA;
+        // the staged frames live in their own arena: preprocess_any's stage-kernel fallback (odd frame sizes) takes its
+        // gray / blur planes from AR_STAGE of the same worker and must not overwrite the input
+        if (wk[s]->arena[AR_HOSTIN].reserve(total) != SVB_OK) return SVB_ERR_CUDA;
+        // the weights may have been packed on another stream just before this call
+        if (ctx->weights_ready) SVB_CUDA_OK(cudaStreamWaitEvent(wk[s]->own_stream, ctx->weights_ready, 0));
     }
-    // the weights may have been packed on another stream just before this call
-    SVB_CUDA_OK(cudaDeviceSynchronize());
-    int i = 0;
-    for (int f0 = 0; f0 < n; f0 += chunk, ++i) {
+    // every exit, error or not, first drains both worker streams: copies already enqueued write into the caller's buffers
+    int rc = SVB_OK, i = 0;
+    for (int f0 = 0; f0 < n && rc == SVB_OK; f0 += chunk, ++i) {
         const int m = (n - f0 < chunk) ? n - f0 : chunk;
         svb_ctx *k = wk[i & 1];
         cudaStream_t st = k->own_stream;
-        char *d = (char *)k->arena[AR_STAGE].ptr;
-        SVB_CUDA_OK(cudaMemcpyAsync(d, host_bgr + (size_t)f0 * frame_bytes, frame_bytes * m, cudaMemcpyHostToDevice, st));
-        int rc = scan_batch(k, (const uint8_t *)d, m, h, w, (uint8_t *)(d + o_dig), (float *)(d + o_conf), nullptr,
-                            (int32_t *)(d + o_cor), (uint8_t *)(d + o_fnd), st);
-        if (rc) return rc;
-        ctx->launches += k->launches;
-        k->launches = 0;
-        SVB_CUDA_OK(cudaMemcpyAsync(host_digits + (size_t)f0 * 81, d + o_dig, (size_t)m * 81, cudaMemcpyDeviceToHost, st));
-        SVB_CUDA_OK(cudaMemcpyAsync(host_conf + (size_t)f0 * 81, d + o_conf, (size_t)m * 81 * 4, cudaMemcpyDeviceToHost, st));
-        SVB_CUDA_OK(cudaMemcpyAsync(host_corners + (size_t)f0 * 8, d + o_cor, (size_t)m * 32, cudaMemcpyDeviceToHost, st));
-        SVB_CUDA_OK(cudaMemcpyAsync(host_found + f0, d + o_fnd, (size_t)m, cudaMemcpyDeviceToHost, st));
+        char *d = (char *)k->arena[AR_HOSTIN].ptr;
+        rc = [&]() -> int {
+            SVB_CUDA_OK(cudaMemcpyAsync(d, host_bgr + (size_t)f0 * frame_bytes, frame_bytes * m, cudaMemcpyHostToDevice, st));
+            const int r = scan_batch(k, (const uint8_t *)d, m, h, w, (uint8_t *)(d + o_dig), (float *)(d + o_conf), nullptr,
+                                     (int32_t *)(d + o_cor), (uint8_t *)(d + o_fnd), st);
+            ctx->launches += k->launches;
+            k->launches = 0;
+            if (r) return r;
+            SVB_CUDA_OK(cudaMemcpyAsync(host_digits + (size_t)f0 * 81, d + o_dig, (size_t)m * 81, cudaMemcpyDeviceToHost, st));
+            SVB_CUDA_OK(cudaMemcpyAsync(host_conf + (size_t)f0 * 81, d + o_conf, (size_t)m * 81 * 4, cudaMemcpyDeviceToHost, st));
+            SVB_CUDA_OK(cudaMemcpyAsync(host_corners + (size_t)f0 * 8, d + o_cor, (size_t)m * 32, cudaMemcpyDeviceToHost, st));
+            SVB_CUDA_OK(cudaMemcpyAsync(host_found + f0, d + o_fnd, (size_t)m, cudaMemcpyDeviceToHost, st));
+            return SVB_OK;
+        }();
     }
-    SVB_CUDA_OK(cudaStreamSynchronize(wk[0]->own_stream));
-    SVB_CUDA_OK(cudaStreamSynchronize(wk[1]->own_stream));
+    const cudaError_t e0 = cudaStreamSynchronize(wk[0]->own_stream), e1 = cudaStreamSynchronize(wk[1]->own_stream);
+    if (rc) return rc;
+    SVB_CUDA_OK(e0);
+    SVB_CUDA_OK(e1);
     return SVB_OK;
 }

@@ -70,8 +70,9 @@ __global__ void pack_bits_kernel(const uint8_t *__restrict__ mask, uint32_t *__r
         const uint32_t q[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            // each byte is 0 or 255: bit 0 of the four bytes -> 4 mask bits, byte j -> bit j
-            const uint32_t t = q[k] & 0x01010101u;
+            // any non-zero byte is foreground (cv2.findContours' rule, and MaskView::fg's): 0x01 per non-zero byte, then
+            // bit 0 of the four bytes -> 4 mask bits, byte j -> bit j
+            const uint32_t t = __vcmpne4(q[k], 0u) & 0x01010101u;
             v |= (((t * 0x01020408u) >> 24) & 0xFu) << (4 * k);
         }
     }
@@ -288,9 +289,7 @@ int launch_find_grid_contour(svb_ctx *ctx, const uint8_t *mask, int n, int h, in
                              const uint32_t *ready_bits) {
     using namespace k2;
     const double min_area = min_area_ratio * (double)((long long)h * w);
-    int pitch = contour::probe_pitch(min_area);
-    static const int pitch_div = [] { const char *e = getenv("SVB_K2_PITCH_DIV"); return e ? std::max(1, atoi(e)) : 1; }();  // tuning knob: denser probe lines
-    pitch = std::max(1, pitch / pitch_div);
+    const int pitch = contour::probe_pitch(min_area);
     const int nv = (w - 1) / pitch + 1, nh = (h - 1) / pitch + 1;
     const long long total = 2 * ((long long)nv * h + (long long)nh * w);  // probe ids: four crossing kinds (contour_core.cuh)
     SVB_REQUIRE(total < (1ll << 30), SVB_ERR_UNSUPPORTED, "find_grid_contour: min_area_ratio too small for this image size");

@@ -18,8 +18,8 @@
 //   3. epilogue: tcgen05.ld (32 lanes x 32 columns per warp), 2x2 max-pool by warp shuffles,
 //      +bias, ReLU, fp16 hi/lo split, 128-byte stores of the 49x64 feature block of the cell
 //      (K order (pixel, channel); fc1's weights are permuted to match at pack time).
-// tc_fc_kernel: [cells x 3136] x [3136 x 128] with the same split, 128-cell tiles, cp.async double
-//   buffering into the canonical layout, then bias+ReLU, fc2 (128x10, CUDA cores), softmax-max/argmax.
+// tc_fc_tma_kernel: [cells x 3136] x [3136 x 128] with the same split, 128-cell tiles fed by TMA, then bias+ReLU,
+//   fc2 (128x10, CUDA cores), softmax-max/argmax.
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -387,152 +387,10 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
 // fc1 (tcgen05) + fc2 + softmax/argmax epilogue
 // ================================================================================================
 constexpr int FC_KC = 64;                       // K chunk per stage (4 MMAs of K=16)
-constexpr int FC_TILE_BYTES = 128 * FC_KC * 2;  // one operand part per stage: 16 KB
 constexpr int FC_NCHUNK = 3136 / FC_KC;         // 49
 
-struct FcSmem {
-    alignas(1024) uint8_t A[2][2][FC_TILE_BYTES];  // [stage][hi/lo]  128 cells x 64 k
-    alignas(1024) uint8_t B[2][2][FC_TILE_BYTES];  // [stage][hi/lo]  128 outputs x 64 k
-    float fb1[128];
-    float fw2[128 * 10];
-    float fb2[16];
-    float part[2][128][10];                        // fc2 partial sums per column half
-    alignas(8) unsigned long long mbar[2];
-    uint32_t tmem_base;
-};
-
-__global__ void __launch_bounds__(NT, 1)
-tc_fc_kernel(const __half *__restrict__ feat_hi, const __half *__restrict__ feat_lo, long long n_cells,
-             const __half *__restrict__ w_hi, const __half *__restrict__ w_lo, const float *__restrict__ fb1,
-             const float *__restrict__ fw2, const float *__restrict__ fb2, float *__restrict__ logits,
-             uint8_t *__restrict__ digits, float *__restrict__ conf) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    FcSmem &s = *reinterpret_cast<FcSmem *>(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid < 128) s.fb1[tid] = fb1[tid];
-    for (int i = tid; i < 1280; i += NT) s.fw2[i] = fw2[i];
-    if (tid < 10) s.fb2[tid] = fb2[tid];
-    if (tid == 0) {
-        mbar_init(&s.mbar[0], 1);
-        mbar_init(&s.mbar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) tmem_alloc(&s.tmem_base, 128);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = s.tmem_base;
-    const uint32_t idesc = make_idesc(128, 128);
-    uint32_t ph[2] = {0, 0};
-    const long long n_tiles = (n_cells + 127) / 128;
-
-    // each thread moves 16 x 16-byte pieces per chunk: piece id p = it*256 + tid -> (operand, part, row, kc)
-    auto load_chunk = [&](long long m0, int chunk, int stage) {
-#pragma unroll
-        for (int it = 0; it < 16; ++it) {
-            const int p = it * NT + tid;
-            const int opnd = p >> 11, part = (p >> 10) & 1, row = (p >> 3) & 127, kc = p & 7;
-            const int off = (row >> 3) * 1024 + kc * 128 + (row & 7) * 16;
-            if (opnd == 0) {
-                long long r = m0 + row;
-                if (r >= n_cells) r = n_cells - 1;  // clamp: rows past the end are computed and discarded
-                const __half *src = (part ? feat_lo : feat_hi) + r * 3136 + chunk * FC_KC + kc * 8;
-                cp_async16(&s.A[stage][part][off], src);
-            } else {
-                const __half *src = (part ? w_lo : w_hi) + (long long)row * 3136 + chunk * FC_KC + kc * 8;
-                cp_async16(&s.B[stage][part][off], src);
-            }
-        }
-        cp_async_commit();
-    };
-
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long m0 = tile * 128;
-        load_chunk(m0, 0, 0);
-        for (int c = 0; c < FC_NCHUNK; ++c) {
-            const int st = c & 1;
-            if (c + 1 < FC_NCHUNK) {
-                // stage (c+1)&1 was last read by the MMAs of chunk c-1: wait for their commit
-                if (c >= 1) {
-                    mbar_wait(&s.mbar[st ^ 1], ph[st ^ 1]);
-                    ph[st ^ 1] ^= 1;
-                }
-                load_chunk(m0, c + 1, st ^ 1);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
-            }
-            fence_proxy_async();
-            __syncthreads();
-            if (warp == 0) {
-                if (lane == 0) {
-                    tc_fence_after();
-                    const uint32_t a0 = smem_u32(&s.A[st][0][0]), b0 = smem_u32(&s.B[st][0][0]);
-#pragma unroll 1
-                    for (int combo = 0; combo < 3; ++combo) {
-                        const int pa = (combo == 2) ? 1 : 0, pb = (combo == 1) ? 1 : 0;
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            umma_f16(tmem, make_desc(a0 + pa * FC_TILE_BYTES + ks * 256, 128, 1024),
-                                     make_desc(b0 + pb * FC_TILE_BYTES + ks * 256, 128, 1024), idesc,
-                                     (c | combo | ks) ? 1u : 0u);
-                    }
-                    umma_commit(&s.mbar[st]);
-                }
-                __syncwarp();
-            }
-        }
-        // drain: the last two commits (chunks 47 and 48) are still pending
-        mbar_wait(&s.mbar[(FC_NCHUNK - 2) & 1], ph[(FC_NCHUNK - 2) & 1]);
-        ph[(FC_NCHUNK - 2) & 1] ^= 1;
-        mbar_wait(&s.mbar[(FC_NCHUNK - 1) & 1], ph[(FC_NCHUNK - 1) & 1]);
-        ph[(FC_NCHUNK - 1) & 1] ^= 1;
-        tc_fence_after();
-        // ---- epilogue --------------------------------------------------------------------------------------
-        const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
-        float acc10[10];
-#pragma unroll
-        for (int k = 0; k < 10; ++k) acc10[k] = 0.f;
-#pragma unroll 1
-        for (int blk = 0; blk < 2; ++blk) {
-            uint32_t v[32];
-            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64 + blk * 32), v);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const int k = half * 64 + blk * 32 + c;
-                const float h = fmaxf(__uint_as_float(v[c]) + s.fb1[k], 0.f);
-#pragma unroll
-                for (int o = 0; o < 10; ++o) acc10[o] = fmaf(s.fw2[k * 10 + o], h, acc10[o]);
-            }
-        }
-#pragma unroll
-        for (int o = 0; o < 10; ++o) s.part[half][row][o] = acc10[o];
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        if (tid < 128 && m0 + tid < n_cells) {
-            float l[10];
-            float mx = -INFINITY;
-            int am = 0;
-#pragma unroll
-            for (int o = 0; o < 10; ++o) {
-                l[o] = s.part[0][tid][o] + s.part[1][tid][o] + s.fb2[o];
-                logits[(m0 + tid) * 10 + o] = l[o];
-                if (l[o] > mx) { mx = l[o]; am = o; }
-            }
-            float den = 0.f;
-#pragma unroll
-            for (int o = 0; o < 10; ++o) den += expf(l[o] - mx);
-            if (digits) digits[m0 + tid] = (uint8_t)am;
-            if (conf) conf[m0 + tid] = 1.0f / den;
-        }
-        __syncthreads();
-    }
-    if (warp == 0) tmem_dealloc(tmem, 128);
-}
-
 // ================================================================================================
-// fc head, TMA edition: the same GEMM + epilogue as tc_fc_kernel, organised the Blackwell way.
+// fc head: [cells x 3136] x [3136 x 128] with the hi/lo split, organised the Blackwell way.
 //   * operands arrive by TMA (cp.async.bulk.tensor.2d, 128 rows x 64 fp16 boxes, SWIZZLE_128B) into a 3-stage ring; one
 //     elected producer thread, full / empty mbarriers, nobody else touches the loads;
 //   * one elected thread issues the MMAs from swizzled K-major descriptors (SBO = 1024 B, +32 B per K = 16 step).  The lo
@@ -810,24 +668,19 @@ int launch_digitcnn_tc(svb_ctx *ctx, const float *x, long long n, float *logits,
     __half *fh = (__half *)ctx->arena[AR_CNN].ptr;
     __half *fl = (__half *)((char *)ctx->arena[AR_CNN].ptr + ((feat_bytes + 255) & ~(size_t)255));
     SVB_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem)));
-    SVB_CUDA_OK(cudaFuncSetAttribute(tc_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FcSmem)));
     const int grid = (int)min((long long)ctx->sm_count, n);
     tc_conv_kernel<<<grid, NTC, sizeof(ConvSmem), st>>>(x, n, c.conv1_w, c.conv1_b, t->wb_img, c.conv2_b, fh, fl);
     int rc = check_launch(ctx, "k5tc::tc_conv_kernel");
     if (rc) return rc;
     if (mid) cudaEventRecord(mid, st);  // stage timing: convolution stack | fc head
     const long long tiles = (n + 127) / 128;
-    static const bool fc_legacy = getenv("SVB_FC_LEGACY") != nullptr;  // A/B switch: the cp.async kernel
     CUtensorMap tm[4];
-    if (!fc_legacy && n < (1LL << 31) && fc_tensor_maps(fh, fl, t->w_hi, t->w_lo, n, tm)) {
-        SVB_CUDA_OK(cudaFuncSetAttribute(tc_fc_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FcTmaSmem) + 1024));
-        tc_fc_tma_kernel<<<(int)min((long long)ctx->sm_count, tiles), FT_THREADS, sizeof(FcTmaSmem) + 1024, st>>>(
-            tm[0], tm[1], tm[2], tm[3], n, c.fc1_b, c.fc2_w, c.fc2_b, logits, digits, conf);
-        return check_launch(ctx, "k5tc::tc_fc_tma_kernel");
-    }
-    tc_fc_kernel<<<(int)min((long long)ctx->sm_count, tiles), NT, sizeof(FcSmem), st>>>(fh, fl, n, t->w_hi, t->w_lo, c.fc1_b,
-                                                                                       c.fc2_w, c.fc2_b, logits, digits, conf);
-    return check_launch(ctx, "k5tc::tc_fc_kernel");
+    SVB_REQUIRE(n < (1LL << 31) && fc_tensor_maps(fh, fl, t->w_hi, t->w_lo, n, tm), SVB_ERR_CUDA,
+                "DigitCNN fc head: cuTensorMapEncodeTiled unavailable or failed");
+    SVB_CUDA_OK(cudaFuncSetAttribute(tc_fc_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FcTmaSmem) + 1024));
+    tc_fc_tma_kernel<<<(int)min((long long)ctx->sm_count, tiles), FT_THREADS, sizeof(FcTmaSmem) + 1024, st>>>(
+        tm[0], tm[1], tm[2], tm[3], n, c.fc1_b, c.fc2_w, c.fc2_b, logits, digits, conf);
+    return check_launch(ctx, "k5tc::tc_fc_tma_kernel");
 }
 
 }  // namespace svb

@@ -259,6 +259,7 @@ struct V3State {
     const float *p[V3_NT] = {};
     uint8_t *tc_blob = nullptr;          // prepacked fp16 hi/lo weight slices of the ten block convolutions
     const uint8_t *tc_img[V3_NT] = {};   // indexed by the weight tensor's index in p[]
+    bool loaded = false;                 // set only after every copy and pack of a load has been enqueued without error
 };
 
 void digitcnn_v3_free(svb_ctx *ctx) {
@@ -283,6 +284,7 @@ int digitcnn_v3_load(svb_ctx *ctx, const float *const *tensors, int count, cudaS
         SVB_CUDA_OK(cudaMalloc(&s->tc_blob, tc_total));
         ctx->cnn_v3 = s;
     }
+    s->loaded = false;  // a failed (re)load must not leave partially written weights usable
     size_t off = 0;
     for (int i = 0; i < V3_NT; ++i) {
         SVB_REQUIRE(tensors[i] != nullptr, SVB_ERR_INVALID, "svb_digitcnn_v3_load: null tensor");
@@ -297,6 +299,7 @@ int digitcnn_v3_load(svb_ctx *ctx, const float *const *tensors, int count, cudaS
         s->tc_img[c[0]] = s->tc_blob + tc_off;
         tc_off += (size_t)36 * c[1] * c[2];
     }
+    s->loaded = true;
     return SVB_OK;
 }
 
@@ -304,7 +307,7 @@ int launch_digitcnn_v3(svb_ctx *ctx, const float *x, long long n, float *logits,
                        float *features, cudaStream_t st) {
     using namespace k6;
     V3State *s = reinterpret_cast<V3State *>(ctx->cnn_v3);
-    SVB_REQUIRE(s != nullptr, SVB_ERR_NOT_LOADED, "DigitCNNv3 weights not loaded (svb_digitcnn_v3_load)");
+    SVB_REQUIRE(s != nullptr && s->loaded, SVB_ERR_NOT_LOADED, "DigitCNNv3 weights not loaded (svb_digitcnn_v3_load)");
     // cells per chunk: 16 per SM = whole waves for the tensor-core kernels (1, 2, 4 cells per pass) while the three
     // activation buffers (32x28x28 floats per cell each) stay bounded (0.7 GB)
     const long long CHUNK = (long long)ctx->sm_count * 16;
@@ -370,6 +373,9 @@ int launch_top3(svb_ctx *ctx, const float *logits, const uint8_t *found, long lo
     return check_launch(ctx, "k6::top3_kernel");
 }
 
-bool digitcnn_v3_loaded(const svb_ctx *ctx) { return ctx->cnn_v3 != nullptr; }
+bool digitcnn_v3_loaded(const svb_ctx *ctx) {
+    const V3State *s = reinterpret_cast<const V3State *>(ctx->cnn_v3);
+    return s != nullptr && s->loaded;
+}
 
 }  // namespace svb

@@ -91,37 +91,9 @@ __global__ void g11_colpass_thresh_kernel(const uint8_t *__restrict__ src, const
 }
 
 // ================================================================================================
-// K1 — fused, row-streaming preprocess.
-//
-// One CTA of 128 threads owns a vertical strip: 512 gray columns (480 output columns + 16-px
-// halo on each side) and walks down the rows R = 4 at a time.  Raw BGR row segments
-// (512 px * 3 B = 1536 B, 16-byte aligned because strips start at multiples of 16 px) are
-// staged into shared memory by TMA bulk copies (cp.async.bulk + mbarrier), three stages deep,
-// so HBM latency is hidden behind arithmetic.  Every thread owns 4 adjacent columns; the only
-// data exchanged between threads are the gray row (for the horizontal 5-tap) and the blurred row
-// (for the horizontal 11-tap) — two __syncthreads per 4 rows.  All vertical windows (hblur
-// ring, rowpass ring) are thread-private slices of shared memory, read back with 64/128-bit
-// loads, so nothing is recomputed vertically and HBM sees each byte once.
+// PTX helpers shared by the fused kernel below (mbarrier, 1-D TMA bulk copy)
 // ================================================================================================
 namespace k1 {
-constexpr int NT = 128;               // threads per CTA
-constexpr int CPT = 4;                // columns per thread
-constexpr int GW = NT * CPT;          // 512 gray columns staged per strip
-constexpr int HALO = 16;              // px, each side (>= 7 needed; 16 keeps TMA 16-B aligned)
-constexpr int TW = GW - 2 * HALO;     // 480 output columns per strip
-constexpr int R = 4;                  // rows per block iteration
-constexpr int NSTAGE = 2;
-constexpr int RAW_ROW = GW * 3;       // bytes per staged row
-
-struct __align__(128) Smem {
-    uint8_t raw[NSTAGE][R][RAW_ROW];  // TMA destination (18 KB)
-    float4 rp[12][NT];                // rowpass ring (index (row + 2) % 12), thread-private columns (24 KB)
-    uint2 hb[8][NT];                  // horizontal 5-tap sums (4 x u16), thread-private (8 KB)
-    uint32_t bx[16][NT];              // blurred rows, packed u8x4: ring + exchange (8 KB)
-    uint32_t g[R][NT];                // gray rows, packed u8x4: exchange (2 KB)
-    unsigned long long full[NSTAGE];  // mbarriers
-};
-
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
@@ -152,410 +124,6 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 
 __device__ __forceinline__ float u8f(uint32_t word, int byte) { return (float)((word >> (8 * byte)) & 0xffu); }
 
-// ---- fast path: one interior block of 4 rows, ring slots at compile-time offsets from per-block slot bases ----
-// Same rings and row bookkeeping as the generic block above, so the kernel can switch per block; differences:
-// byte arithmetic through dp2a / dp4a, the vertical 5-tap over 8 shared hb rows, both 11-tap passes in
-// packed fma.rn.f32x2 (row pass pairs two image rows, column pass pairs two columns), the threshold in
-// 16-bit SIMD lanes, and no clamps (the caller guarantees rows r0-12 .. r0+3 are inside the image).
-template <int CH>
-__device__ __forceinline__ void fast_block(Smem &sm, const int q /* r0 >> 2 */, const int stage, const int t, const bool cols_inside,
-                                           const bool edge_strip, const bool is_out, const int c0, const int w,
-                                           const int xg0, const int col_lo, const int col_hi, const int t_left,
-                                           const int t_right, uint8_t *__restrict__ out_y0 /* &out[(r0-7)*w + c0] */) {
-    constexpr uint32_t W_BG = 3735u | (19235u << 16), W_R = 9798u;
-    // Rings are addressed in 4-row "block slots": hb by gray row (8 rows = 2 slots), bx / rp by blurred row + 2
-    // (16 rows = 4 slots), so that everything this block touches sits at a compile-time offset from a handful
-    // of slot bases computed once here (one code copy for all ring phases keeps the loop inside the I-cache).
-    uint2 (*hb_cur)[NT] = &sm.hb[4 * (q & 1)], (*hb_old)[NT] = &sm.hb[4 * ((q + 1) & 1)];
-    uint32_t (*bx0)[NT] = &sm.bx[4 * (q & 3)], (*bx1)[NT] = &sm.bx[4 * ((q + 3) & 3)], (*bx2)[NT] = &sm.bx[4 * ((q + 2) & 3)];
-    // rp ring: 3 slots; the slot written now also still holds rows r0-12, r0-11 (entries 2,3), read first
-    const int q3 = q % 3;
-    float4 (*rp0)[NT] = &sm.rp[4 * q3], (*rp1)[NT] = &sm.rp[4 * ((q3 + 2) % 3)], (*rp2)[NT] = &sm.rp[4 * ((q3 + 1) % 3)];
-    // ---- phase 1: raw BGR -> gray -----------------------------------------------------------------------
-    uint32_t gq[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        if (CH == 1) {  // gray input (the v2 tail: CLAHE output -> blur -> threshold): nothing to convert
-            if (cols_inside) {
-                gq[r] = *reinterpret_cast<const uint32_t *>(&sm.raw[stage][r][4 * t]);
-            } else {
-                uint32_t v = 0;
-#pragma unroll
-                for (int j = 0; j < CPT; ++j) {
-                    const int c = c0 + j;
-                    int cc = (c < 0) ? -c : ((c >= w) ? 2 * (w - 1) - c : c);
-                    cc = clampi(cc, col_lo, col_hi - 1);
-                    v |= (uint32_t)sm.raw[stage][r][cc - xg0] << (8 * j);
-                }
-                gq[r] = v;
-            }
-        } else if (cols_inside) {
-            const uint32_t *p = reinterpret_cast<const uint32_t *>(&sm.raw[stage][r][12 * t]);
-            const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
-            const uint32_t p1 = __funnelshift_r(w0, w1, 24), p2 = __funnelshift_r(w1, w2, 16), p3 = w2 >> 8;
-            const uint32_t g0 = __dp2a_hi(W_R, w0, __dp2a_lo(W_BG, w0, 16384u)) >> 15;
-            const uint32_t g1 = __dp2a_hi(W_R, p1, __dp2a_lo(W_BG, p1, 16384u)) >> 15;
-            const uint32_t g2 = __dp2a_hi(W_R, p2, __dp2a_lo(W_BG, p2, 16384u)) >> 15;
-            const uint32_t g3 = __dp2a_hi(W_R, p3, __dp2a_lo(W_BG, p3, 16384u)) >> 15;
-            gq[r] = __byte_perm(__byte_perm(g0, g1, 0x0040), __byte_perm(g2, g3, 0x0040), 0x5410);
-        } else {
-            uint32_t v = 0;
-#pragma unroll
-            for (int j = 0; j < CPT; ++j) {
-                const int c = c0 + j;
-                int cc = (c < 0) ? -c : ((c >= w) ? 2 * (w - 1) - c : c);
-                cc = clampi(cc, col_lo, col_hi - 1);
-                const uint8_t *p = &sm.raw[stage][r][(cc - xg0) * 3];
-                v |= gray_of(p[0], p[1], p[2]) << (8 * j);
-            }
-            gq[r] = v;
-        }
-        sm.g[r][t] = gq[r];
-    }
-    __syncthreads();  // (A)
-    // ---- phase 2: horizontal 5-tap (dp4a on byte windows) ----------------------------------------------------
-    uint2 H[8];  // hb rows r0-4 .. r0+3 for this thread's 4 columns (u16 x 4 each)
-    const int tl = max(t - 1, 0), tr = min(t + 1, NT - 1);
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const uint32_t gl = sm.g[r][tl], gc = gq[r], gr = sm.g[r][tr];
-        const uint32_t n0 = __funnelshift_r(gl, gc, 16), n1 = __funnelshift_r(gl, gc, 24), n3 = __funnelshift_r(gc, gr, 8),
-                       n4 = __funnelshift_r(gc, gr, 16);
-        const uint32_t h0 = __dp4a(n1, 0x01000000u, __dp4a(n0, 0x04060401u, 0u));
-        const uint32_t h1 = __dp4a(gc, 0x01000000u, __dp4a(n1, 0x04060401u, 0u));
-        const uint32_t h2 = __dp4a(n3, 0x01000000u, __dp4a(gc, 0x04060401u, 0u));
-        const uint32_t h3 = __dp4a(n4, 0x01000000u, __dp4a(n3, 0x04060401u, 0u));
-        H[4 + r] = make_uint2(__byte_perm(h0, h1, 0x5410), __byte_perm(h2, h3, 0x5410));
-        hb_cur[r][t] = H[4 + r];
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) H[j] = hb_old[j][t];  // rows r0-4 .. r0-1 (previous block)
-    // ---- phase 3: vertical 5-tap on packed u16 lanes -> blurred rows b = r0-2 .. r0+1 ---------------------------
-    uint32_t Bq[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t lo = H[i].x + H[i + 4].x + 4u * (H[i + 1].x + H[i + 3].x) + 6u * H[i + 2].x + 0x00800080u;
-        const uint32_t hi = H[i].y + H[i + 4].y + 4u * (H[i + 1].y + H[i + 3].y) + 6u * H[i + 2].y + 0x00800080u;
-        Bq[i] = __byte_perm(lo, hi, 0x7531);
-        bx0[i][t] = Bq[i];  // blurred row r0-2+i lives at ring index (row + 2)
-    }
-    __syncthreads();  // (B)
-    if (edge_strip) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (c0 < 0) {
-                Bq[i] = (bx0[i][t_left] & 0xffu) * 0x01010101u;
-                bx0[i][t] = Bq[i];
-            } else if (c0 >= w) {
-                Bq[i] = (bx0[i][t_right] >> 24) * 0x01010101u;
-                bx0[i][t] = Bq[i];
-            }
-        }
-        __syncthreads();
-    }
-    if (!is_out) return;
-    // ---- phase 4: horizontal 11-tap, two rows per packed FMA ------------------------------------------------------
-    const float2 k0 = make_float2(SVB_G11_0, SVB_G11_0), k1 = make_float2(SVB_G11_1, SVB_G11_1),
-                 k2 = make_float2(SVB_G11_2, SVB_G11_2), k3 = make_float2(SVB_G11_3, SVB_G11_3),
-                 k4 = make_float2(SVB_G11_4, SVB_G11_4), k5 = make_float2(SVB_G11_5, SVB_G11_5);
-    float4 Rw[14];  // row-pass rows r0-12 .. r0+1
-    Rw[0] = rp0[2][t];  // rows r0-12, r0-11: loaded before this block's rows overwrite the slot
-    Rw[1] = rp0[3][t];
-    float4 RPn[4];  // row-pass results of rows r0-2 .. r0+1
-#pragma unroll
-    for (int pr = 0; pr < 2; ++pr) {
-        const uint32_t *ra = bx0[2 * pr], *rb = bx0[2 * pr + 1];
-        const uint32_t a0 = ra[t - 2], a1 = ra[t - 1], a2 = Bq[2 * pr], a3 = ra[t + 1], a4 = ra[t + 2];
-        const uint32_t b0 = rb[t - 2], b1 = rb[t - 1], b2 = Bq[2 * pr + 1], b3 = rb[t + 1], b4 = rb[t + 2];
-        float2 f[14];  // f[i] = (row a, row b) at column 4t - 5 + i
-        f[0] = make_float2(u8f(a0, 3), u8f(b0, 3));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            f[1 + k] = make_float2(u8f(a1, k), u8f(b1, k));
-            f[5 + k] = make_float2(u8f(a2, k), u8f(b2, k));
-            f[9 + k] = make_float2(u8f(a3, k), u8f(b3, k));
-        }
-        f[13] = make_float2(u8f(a4, 0), u8f(b4, 0));
-        float2 o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float2 acc = __fmul2_rn(k0, f[j]);
-            acc = __ffma2_rn(k1, f[j + 1], acc);
-            acc = __ffma2_rn(k2, f[j + 2], acc);
-            acc = __ffma2_rn(k3, f[j + 3], acc);
-            acc = __ffma2_rn(k4, f[j + 4], acc);
-            acc = __ffma2_rn(k5, f[j + 5], acc);
-            acc = __ffma2_rn(k4, f[j + 6], acc);
-            acc = __ffma2_rn(k3, f[j + 7], acc);
-            acc = __ffma2_rn(k2, f[j + 8], acc);
-            acc = __ffma2_rn(k1, f[j + 9], acc);
-            acc = __ffma2_rn(k0, f[j + 10], acc);
-            o[j] = acc;
-        }
-        RPn[2 * pr] = make_float4(o[0].x, o[1].x, o[2].x, o[3].x);
-        RPn[2 * pr + 1] = make_float4(o[0].y, o[1].y, o[2].y, o[3].y);
-        rp0[2 * pr][t] = RPn[2 * pr];
-        rp0[2 * pr + 1][t] = RPn[2 * pr + 1];
-    }
-    // ---- phase 5: vertical 11-tap (symmetric), rint, threshold -> 4 output rows y = r0-7 .. r0-4 -------------------
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        Rw[2 + j] = rp2[j][t];
-        Rw[6 + j] = rp1[j][t];
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) Rw[10 + j] = RPn[j];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float4 c = Rw[i + 5];
-        float2 aL = __fmul2_rn(k5, make_float2(c.x, c.y)), aH = __fmul2_rn(k5, make_float2(c.z, c.w));
-#pragma unroll
-        for (int j = 1; j <= 5; ++j) {
-            const float4 u = Rw[i + 5 + j], d = Rw[i + 5 - j];
-            const float2 kk = (j == 1) ? k4 : (j == 2) ? k3 : (j == 3) ? k2 : (j == 4) ? k1 : k0;
-            aL = __ffma2_rn(kk, __fadd2_rn(make_float2(u.x, u.y), make_float2(d.x, d.y)), aL);
-            aH = __ffma2_rn(kk, __fadd2_rn(make_float2(u.z, u.w), make_float2(d.z, d.w)), aH);
-        }
-        // rint via the 1.5*2^23 magic add: the low byte of the float's bits is the rounded mean (0..255)
-        const float2 magic = make_float2(12582912.0f, 12582912.0f);
-        const float2 mL = __fadd2_rn(aL, magic), mH = __fadd2_rn(aH, magic);
-        const uint32_t m_even = __byte_perm(__float_as_uint(mL.x), __float_as_uint(mH.x), 0x5410);  // mean0 | mean2 << 16
-        const uint32_t m_odd = __byte_perm(__float_as_uint(mL.y), __float_as_uint(mH.y), 0x5410);   // mean1 | mean3 << 16
-        const uint32_t src = (i == 0) ? bx2[3][t] : bx1[i - 1][t];  // blurred row r0-7+i at ring index r0-5+i
-        const uint32_t s_even = src & 0x00FF00FFu, s_odd = (src >> 8) & 0x00FF00FFu;
-        // THRESH_BINARY_INV: 255 iff src - mean <= -2  <=>  mean - src - 2 >= 0; per 16-bit lane with a 0x8000 guard
-        const uint32_t d_even = m_even + 0x7FFE7FFEu - s_even, d_odd = m_odd + 0x7FFE7FFEu - s_odd;
-        const uint32_t o = ((d_even >> 15) & 0x00010001u) * 0xFFu + ((d_odd >> 15) & 0x00010001u) * 0xFF00u;
-        *reinterpret_cast<uint32_t *>(out_y0 + (long long)i * w) = o;
-    }
-}
-
-template <bool INVERTED, int CH>
-__global__ void __launch_bounds__(NT, 4)
-fused_preprocess_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ mask, int h, int w, int rows_per_seg) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
-
-    const int t = threadIdx.x;
-    const int X0 = blockIdx.x * TW;            // first output column of this strip
-    const int xg0 = X0 - HALO;                 // first staged gray column (may be negative)
-    const int ys = blockIdx.y * rows_per_seg;  // output rows [ys, ye)
-    const int ye = min(ys + rows_per_seg, h);
-    const long long frame_px = (long long)h * w;
-    const uint8_t *frame = bgr + (long long)blockIdx.z * frame_px * CH;
-    uint8_t *out = mask + (long long)blockIdx.z * frame_px;
-
-    const int bs = max(ys - 5, 0), be = min(ye + 5, h);  // blurred rows needed [bs, be)
-    const int gs = max(bs - 2, 0) & ~3, ge = min(be + 2, h);  // gray rows staged [gs, ge); gs % 4 == 0 keeps ring phases to 4
-    const int nblocks = (ge - gs + R - 1) / R;
-
-    // staged column range actually inside the image
-    const int col_lo = max(xg0, 0), col_hi = min(xg0 + GW, w);
-    const uint32_t row_bytes = (uint32_t)(col_hi - col_lo) * (uint32_t)CH;
-    const int dst_off = (col_lo - xg0) * CH;
-
-    if (t == 0) {
-        for (int s = 0; s < NSTAGE; ++s) mbar_init(&sm.full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    auto issue = [&](int blk) {
-        if (blk >= nblocks) return;
-        const int stage = blk % NSTAGE;
-        const int r0 = gs + blk * R;
-        const int nrows = min(R, ge - r0);
-        mbar_expect_tx(&sm.full[stage], row_bytes * (uint32_t)nrows);
-        for (int r = 0; r < nrows; ++r)
-            tma_load_1d(&sm.raw[stage][r][dst_off], frame + ((long long)(r0 + r) * w + col_lo) * CH, row_bytes,
-                        &sm.full[stage]);
-    };
-    if (t == 0) issue(0);
-
-    // my 4 columns
-    const int c0 = xg0 + CPT * t;
-    const bool cols_inside = (c0 >= 0) && (c0 + CPT <= w);
-    const bool edge_strip = (xg0 < 0) || (xg0 + GW > w);
-    // thread / byte that holds image column 0 and w-1 (for BORDER_REPLICATE of the blurred row)
-    const int t_left = (0 - xg0) / CPT;
-    const int t_right = (w - 1 - xg0) / CPT;
-    const bool is_out = (t >= 2) && (t < NT - 2) && (c0 >= X0) && (c0 < min(X0 + TW, w));
-
-    const float kf[6] = {SVB_G11_0, SVB_G11_1, SVB_G11_2, SVB_G11_3, SVB_G11_4, SVB_G11_5};
-
-    int b_next = bs;  // next blurred row to produce
-    int y_next = ys;  // next output row to produce
-
-    for (int blk = 0; blk < nblocks; ++blk) {
-        const int stage = blk % NSTAGE;
-        const int r0 = gs + blk * R;
-        const int nrows = min(R, ge - r0);
-        if (t == 0) issue(blk + 1);
-        mbar_wait(&sm.full[stage], (uint32_t)((blk / NSTAGE) & 1));
-
-        // interior block: every row it touches is inside the image and inside this segment's schedule
-        if (INVERTED && nrows == R && blk + 1 < nblocks && r0 >= 12 && b_next == r0 - 2 && y_next == r0 - 7 && r0 + 1 <= be - 1 &&
-            r0 - 4 <= ye - 1 && r0 - 7 >= ys && r0 + 3 <= h - 1) {
-            uint8_t *o0 = out + (long long)(r0 - 7) * w + c0;
-            fast_block<CH>(sm, r0 >> 2, stage, t, cols_inside, edge_strip, is_out, c0, w, xg0, col_lo, col_hi, t_left, t_right, o0);
-            b_next = r0 + 2;
-            y_next = r0 - 3;
-            continue;
-        }
-        // ---- phase 1: raw BGR -> gray (packed u8x4) ------------------------------------------
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (r < nrows) {
-                uint32_t gq;
-                if (CH == 1) {
-                    if (cols_inside) {
-                        gq = *reinterpret_cast<const uint32_t *>(&sm.raw[stage][r][4 * t]);
-                    } else {
-                        gq = 0;
-#pragma unroll
-                        for (int j = 0; j < CPT; ++j) {
-                            int c = c0 + j;
-                            int cc = (c < 0) ? -c : ((c >= w) ? 2 * (w - 1) - c : c);
-                            cc = clampi(cc, col_lo, col_hi - 1);
-                            gq |= (uint32_t)sm.raw[stage][r][cc - xg0] << (8 * j);
-                        }
-                    }
-                } else if (cols_inside) {
-                    const uint32_t *p = reinterpret_cast<const uint32_t *>(&sm.raw[stage][r][12 * t]);
-                    uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
-                    uint32_t g0 = gray_of(w0 & 0xff, (w0 >> 8) & 0xff, (w0 >> 16) & 0xff);
-                    uint32_t g1 = gray_of(w0 >> 24, w1 & 0xff, (w1 >> 8) & 0xff);
-                    uint32_t g2 = gray_of((w1 >> 16) & 0xff, w1 >> 24, w2 & 0xff);
-                    uint32_t g3 = gray_of((w2 >> 8) & 0xff, (w2 >> 16) & 0xff, w2 >> 24);
-                    gq = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
-                } else {
-                    gq = 0;  // columns outside the image: BORDER_REFLECT_101 of the gray row
-#pragma unroll
-                    for (int j = 0; j < CPT; ++j) {
-                        int c = c0 + j;
-                        int cc = (c < 0) ? -c : ((c >= w) ? 2 * (w - 1) - c : c);
-                        cc = clampi(cc, col_lo, col_hi - 1);
-                        const uint8_t *p = &sm.raw[stage][r][(cc - xg0) * 3];
-                        gq |= gray_of(p[0], p[1], p[2]) << (8 * j);
-                    }
-                }
-                sm.g[r][t] = gq;
-            }
-        }
-        __syncthreads();  // (A) gray rows visible
-
-        // ---- phase 2: horizontal 5-tap on gray -> hb ring (u16 x 4) ----------------------------
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (r < nrows) {
-                uint32_t gl = sm.g[r][max(t - 1, 0)], gc = sm.g[r][t], gr = sm.g[r][min(t + 1, NT - 1)];
-                // bytes: v[0..1] = last two of left word, v[2..5] = centre, v[6..7] = first two of right
-                uint32_t v[8];
-                v[0] = (gl >> 16) & 0xff; v[1] = gl >> 24;
-                v[2] = gc & 0xff; v[3] = (gc >> 8) & 0xff; v[4] = (gc >> 16) & 0xff; v[5] = gc >> 24;
-                v[6] = gr & 0xff; v[7] = (gr >> 8) & 0xff;
-                uint32_t hsum[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) hsum[j] = v[j] + v[j + 4] + 4u * (v[j + 1] + v[j + 3]) + 6u * v[j + 2];
-                sm.hb[(r0 + r) & 7][t] = make_uint2(hsum[0] | (hsum[1] << 16), hsum[2] | (hsum[3] << 16));
-            }
-        }
-
-        // ---- phase 3: vertical 5-tap -> blurred rows (packed u8x4) into the bx ring -------------
-        const int r_hi = r0 + nrows - 1;                          // newest gray row available
-        const int b_hi = (r_hi >= h - 1) ? (be - 1) : min(be - 1, r_hi - 2);
-        const int b_first = b_next;
-        for (int b = b_first; b <= b_hi; ++b) {
-            uint2 a0 = sm.hb[reflect101(b - 2, h) & 7][t];
-            uint2 a1 = sm.hb[reflect101(b - 1, h) & 7][t];
-            uint2 a2 = sm.hb[b & 7][t];
-            uint2 a3 = sm.hb[reflect101(b + 1, h) & 7][t];
-            uint2 a4 = sm.hb[reflect101(b + 2, h) & 7][t];
-            // packed 2 x u16 arithmetic: max lane value 16*4080 + 128 = 65408 < 65536
-            uint32_t lo = a0.x + a4.x + 4u * (a1.x + a3.x) + 6u * a2.x + 0x00800080u;
-            uint32_t hi = a0.y + a4.y + 4u * (a1.y + a3.y) + 6u * a2.y + 0x00800080u;
-            // >> 8 per lane and pack to u8x4: bytes 1,3 of lo and 1,3 of hi
-            sm.bx[(b + 2) & 15][t] = __byte_perm(lo, hi, 0x7531);
-        }
-        b_next = max(b_next, b_hi + 1);
-        __syncthreads();  // (B) blurred rows visible
-        if (edge_strip) {
-            // BORDER_REPLICATE of the blurred image in x: columns < 0 take column 0, >= w take w-1
-            for (int b = b_first; b <= b_hi; ++b) {
-                if (c0 < 0) {
-                    uint32_t e = sm.bx[(b + 2) & 15][t_left] & 0xffu;
-                    sm.bx[(b + 2) & 15][t] = e * 0x01010101u;
-                } else if (c0 >= w) {
-                    uint32_t e = sm.bx[(b + 2) & 15][t_right] >> 24;
-                    sm.bx[(b + 2) & 15][t] = e * 0x01010101u;
-                }
-            }
-            __syncthreads();
-        }
-
-        // ---- phases 4+5: per new blurred row: horizontal 11-tap -> rowpass ring, then every output row whose
-        //      11-row window is complete (at most 11 ring rows are live at any time: the ring holds 12)
-        const int b_last = b_hi;
-        const int y_hi = (b_last >= h - 1) ? (ye - 1) : min(ye - 1, b_last - 5);
-        if (is_out) {
-            int yo = y_next;
-            for (int b = b_first; b <= b_hi; ++b) {
-                const uint32_t *brow = sm.bx[(b + 2) & 15];
-                uint32_t q0 = brow[t - 2], q1 = brow[t - 1], q2 = brow[t], q3 = brow[t + 1], q4 = brow[t + 2];
-                // f[i] = blurred column (4t - 5 + i), i = 0..13
-                float f[14];
-                f[0] = u8f(q0, 3);
-                f[1] = u8f(q1, 0); f[2] = u8f(q1, 1); f[3] = u8f(q1, 2); f[4] = u8f(q1, 3);
-                f[5] = u8f(q2, 0); f[6] = u8f(q2, 1); f[7] = u8f(q2, 2); f[8] = u8f(q2, 3);
-                f[9] = u8f(q3, 0); f[10] = u8f(q3, 1); f[11] = u8f(q3, 2); f[12] = u8f(q3, 3);
-                f[13] = u8f(q4, 0);
-                float o[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float acc = __fmul_rn(kf[0], f[j]);
-                    acc = __fmaf_rn(kf[1], f[j + 1], acc);
-                    acc = __fmaf_rn(kf[2], f[j + 2], acc);
-                    acc = __fmaf_rn(kf[3], f[j + 3], acc);
-                    acc = __fmaf_rn(kf[4], f[j + 4], acc);
-                    acc = __fmaf_rn(kf[5], f[j + 5], acc);
-                    acc = __fmaf_rn(kf[4], f[j + 6], acc);
-                    acc = __fmaf_rn(kf[3], f[j + 7], acc);
-                    acc = __fmaf_rn(kf[2], f[j + 8], acc);
-                    acc = __fmaf_rn(kf[1], f[j + 9], acc);
-                    acc = __fmaf_rn(kf[0], f[j + 10], acc);
-                    o[j] = acc;
-                }
-                sm.rp[(b + 2) % 12][t] = make_float4(o[0], o[1], o[2], o[3]);
-                // vertical 11-tap (symmetric FMA) + rint + threshold for the rows that became computable
-                while (yo <= y_hi && min(yo + 5, h - 1) <= b) {
-                    const int y = yo++;
-                    float4 c = sm.rp[(y + 2) % 12][t];
-                    float a0 = __fmul_rn(kf[5], c.x), a1 = __fmul_rn(kf[5], c.y), a2 = __fmul_rn(kf[5], c.z), a3 = __fmul_rn(kf[5], c.w);
-#pragma unroll
-                    for (int j = 1; j <= 5; ++j) {
-                        float4 u = sm.rp[(clampi(y + j, 0, h - 1) + 2) % 12][t];
-                        float4 d = sm.rp[(clampi(y - j, 0, h - 1) + 2) % 12][t];
-                        const float kk = kf[5 - j];
-                        a0 = __fmaf_rn(kk, __fadd_rn(u.x, d.x), a0);
-                        a1 = __fmaf_rn(kk, __fadd_rn(u.y, d.y), a1);
-                        a2 = __fmaf_rn(kk, __fadd_rn(u.z, d.z), a2);
-                        a3 = __fmaf_rn(kk, __fadd_rn(u.w, d.w), a3);
-                    }
-                    uint32_t src = sm.bx[(y + 2) & 15][t];
-                    int m0 = rint_pos(a0), m1 = rint_pos(a1), m2 = rint_pos(a2), m3 = rint_pos(a3);
-                    // BINARY_INV: 255 iff src - mean <= -2 ; BINARY: 255 iff src - mean > -2
-                    bool p0 = (int)(src & 0xff) - m0 <= -2, p1 = (int)((src >> 8) & 0xff) - m1 <= -2;
-                    bool p2 = (int)((src >> 16) & 0xff) - m2 <= -2, p3 = (int)(src >> 24) - m3 <= -2;
-                    if (!INVERTED) { p0 = !p0; p1 = !p1; p2 = !p2; p3 = !p3; }
-                    uint32_t o32 = (p0 ? 0xffu : 0u) | (p1 ? 0xff00u : 0u) | (p2 ? 0xff0000u : 0u) | (p3 ? 0xff000000u : 0u);
-                    *reinterpret_cast<uint32_t *>(out + (long long)y * w + c0) = o32;
-                }
-            }
-        }
-        y_next = max(y_next, y_hi + 1);
-        // next iteration's phase 1 writes sm.g, whose readers (phase 2) all passed barrier (B).
-    }
-}
 }  // namespace k1
 
 // ================================================================================================
@@ -989,7 +557,8 @@ int launch_adaptive(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, int i
     return check_launch(ctx, "g11_colpass_thresh_kernel");
 }
 
-bool fused_preprocess_supported(int h, int w) { return (w % 16 == 0) && w >= 64 && h >= 8; }
+// the warp-per-strip kernel needs 16-px aligned rows, at least one full strip interior and 8-byte aligned mask rows
+bool fused_preprocess_supported(int h, int w) { return (w % 16 == 0) && w >= 64 && h >= 16; }
 
 typedef CUresult (*tensor_map_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                         const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1015,8 +584,6 @@ static int launch_k1w(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uin
     const long long strips = (long long)nstrips * n;
     long long want = (8LL * 12 * ctx->sm_count + strips - 1) / strips;
     int nseg = (int)max(1LL, min(want, (long long)(h / 64)));
-    static const int nseg_env = [] { const char *e = getenv("SVB_K1_NSEG"); return e ? atoi(e) : 0; }();  // tuning knob
-    if (nseg_env > 0) nseg = max(1, min(nseg_env, h / 16));
     int rows_per_seg = (((h + nseg - 1) / nseg) + 3) & ~3;
     nseg = (h + rows_per_seg - 1) / rows_per_seg;
     if (n > 65535 || nseg > 65535) return SVB_ERR_UNSUPPORTED;
@@ -1033,8 +600,6 @@ static int launch_k1w(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uin
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     }
-    static const bool no_tmap = getenv("SVB_K1_NO_TMAP") != nullptr;  // A/B switch: 1-D bulk copies only
-    if (no_tmap) use_tmap = 0;
     dim3 grid(nstrips, nseg, n);
     const int btx = w / 32 + 2, bty = (h + 31) / 32 + 2;  // contour::bit_tiles_x / _y
     fused_preprocess_warp_kernel<CH><<<grid, 32, smem, st>>>(src, mask, h, w, rows_per_seg, tmap, use_tmap, (uint8_t *)bits, btx,
@@ -1042,35 +607,18 @@ static int launch_k1w(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uin
     return check_launch(ctx, "fused_preprocess_warp_kernel");
 }
 
-// ch = 3: BGR frames (cv/preprocess.py:57-65); ch = 1: gray input, i.e. GaussianBlur 5 + adaptive threshold only
-// (the tail of cv/preprocess_v2.py:233-239)
-static bool k1_legacy() {
-    static const bool legacy = getenv("SVB_K1_LEGACY") != nullptr;  // A/B switch: the CTA-per-strip kernel (k1::)
-    return legacy;
-}
-// true when launch_fused_preprocess will take the warp-per-strip kernel, which can also emit K2's tiled bit mask
+// true when the fused kernel can also emit K2's tiled bit mask (whole 32-px tiles only)
 bool fused_preprocess_writes_bits(int h, int w, const void *mask) {
-    static const bool no_bits = getenv("SVB_K1_NO_BITS") != nullptr;  // A/B switch: K2 packs the byte mask itself
-    return !k1_legacy() && !no_bits && (((uintptr_t)mask) & 7) == 0 && h >= 16 && w % 32 == 0;
+    return fused_preprocess_supported(h, w) && (((uintptr_t)mask) & 7) == 0 && w % 32 == 0;
 }
 
+// ch = 3: BGR frames (cv/preprocess.py:57-65); ch = 1: gray input, i.e. GaussianBlur 5 + adaptive threshold only
+// (the tail of cv/preprocess_v2.py:233-239).  Callers check fused_preprocess_supported and the alignment of both
+// pointers (source 16 B, mask 8 B) first and otherwise take the three stage kernels.
 int launch_fused_preprocess(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uint8_t *mask, cudaStream_t st, int ch, uint32_t *bits) {
-    if (!k1_legacy() && (((uintptr_t)mask) & 7) == 0 && h >= 16)
-        return ch == 1 ? launch_k1w<1>(ctx, src, n, h, w, mask, st, bits) : launch_k1w<3>(ctx, src, n, h, w, mask, st, bits);
-    if (bits) return SVB_ERR_INVALID;  // callers ask fused_preprocess_writes_bits first
-    using namespace k1;
-    SVB_CUDA_OK(cudaFuncSetAttribute(fused_preprocess_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-    SVB_CUDA_OK(cudaFuncSetAttribute(fused_preprocess_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-    const int nstrips = (w + TW - 1) / TW;
-    // enough CTAs to fill the machine ~4x over; segments no shorter than 64 rows (14-row warm-up)
-    int want = (ctx->sm_count * 3 * 4 + nstrips * n - 1) / (nstrips * n);
-    int nseg = max(1, min(want, h / 64));
-    int rows_per_seg = (h + nseg - 1) / nseg;
-    nseg = (h + rows_per_seg - 1) / rows_per_seg;
-    dim3 grid(nstrips, nseg, n);
-    if (ch == 1) fused_preprocess_kernel<true, 1><<<grid, NT, sizeof(Smem), st>>>(src, mask, h, w, rows_per_seg);
-    else fused_preprocess_kernel<true, 3><<<grid, NT, sizeof(Smem), st>>>(src, mask, h, w, rows_per_seg);
-    return check_launch(ctx, "fused_preprocess_kernel");
+    SVB_REQUIRE(fused_preprocess_supported(h, w) && (((uintptr_t)mask) & 7) == 0 && (((uintptr_t)src) & 15) == 0, SVB_ERR_INVALID,
+                "fused preprocess: unsupported geometry or alignment");
+    return ch == 1 ? launch_k1w<1>(ctx, src, n, h, w, mask, st, bits) : launch_k1w<3>(ctx, src, n, h, w, mask, st, bits);
 }
 
 }  // namespace svb

@@ -1111,7 +1111,7 @@ int launch_fused_preprocess(svb_ctx *, const uint8_t *, int, int, int, uint8_t *
 // K1's fused row-streaming kernel in its gray-input form when the frame qualifies, else the two stage kernels.
 // `blurred_tmp` is only used by the stage-kernel path.
 static int blur_threshold(svb_ctx *ctx, const uint8_t *gray, int n, int h, int w, uint8_t *blurred_tmp, uint8_t *mask, cudaStream_t st) {
-    if (fused_preprocess_supported(h, w) && (((size_t)gray) & 15) == 0 && (((size_t)mask) & 3) == 0)
+    if (fused_preprocess_supported(h, w) && (((size_t)gray) & 15) == 0 && (((size_t)mask) & 7) == 0)
         return launch_fused_preprocess(ctx, gray, n, h, w, mask, st, 1);
     int rc = launch_blur5(ctx, gray, n, h, w, blurred_tmp, st);
     if (rc) return rc;

@@ -1,4 +1,4 @@
-"""Drop-in for cv/extract.py.  extract_cells runs on the GPU (svb_extract_cells)."""
+"""Drop-in for cv/extract.py.  extract_cells and is_cell_empty run on the GPU (svb_extract_cells, svb_is_cell_empty)."""
 import os
 import sys
 
@@ -20,8 +20,11 @@ def extract_cells(grid_image: NDArray[np.uint8], cell_size: int = 28, margin_rat
 
 
 def is_cell_empty(cell: NDArray[np.uint8], threshold: float = 0.02) -> bool:
-    """cv/extract.py:59-79 — debug/tooling helper outside the scan path."""
-    raise NotImplementedError("is_cell_empty is not part of the B200 scan path")
+    """cv/extract.py:59-79: Otsu (THRESH_BINARY_INV) + countNonZero ratio, on the GPU (svb_is_cell_empty)."""
+    if cell.ndim != 2 or cell.dtype != np.uint8:
+        raise NotImplementedError("is_cell_empty: only 2-D uint8 cells are implemented")
+    empty = rt.scanner().is_cell_empty(rt.to_device_u8(cell)[None], threshold)
+    return bool(int(empty.cpu()[0]))
 
 
 def preprocess_cell_for_model(cell: NDArray[np.uint8]) -> NDArray[np.float32]:

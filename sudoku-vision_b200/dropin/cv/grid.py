@@ -1,5 +1,6 @@
-"""Drop-in for cv/grid.py.  find_grid_contour / warp_perspective run on the GPU (svb_find_grid_contour,
-svb_warp_perspective); order_points is four-point host bookkeeping exactly as the reference's numpy."""
+"""Drop-in for cv/grid.py.  find_contours / approximate_polygon / find_grid_contour / warp_perspective run on the GPU
+(svb_find_contours_*, svb_approx_poly_dp, svb_find_grid_contour, svb_warp_perspective); order_points is four-point host
+bookkeeping exactly as the reference's numpy."""
 import os
 import sys
 
@@ -10,15 +11,22 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import _runtime as rt  # noqa: E402
 
 
-def find_contours(binary: NDArray[np.uint8]) -> list:
-    """cv/grid.py:16-21.  The batched path never materialises the full contour list (it traces only
-    borders that can reach min_area), so this debug helper is not provided."""
-    raise NotImplementedError("find_contours: the B200 path does not materialise all contours; use find_grid_contour")
+def find_contours(binary: NDArray[np.uint8]) -> tuple:
+    """cv/grid.py:16-21 -> tuple of (n_i,1,2) int32 arrays: every RETR_EXTERNAL / CHAIN_APPROX_SIMPLE contour, in
+    cv2's order (svb_find_contours_count / _fetch: flood of the outer background + one border walk per component)."""
+    pts, offs = rt.scanner().find_contours(rt.to_device_u8(binary))
+    pts, offs = rt.to_host(pts), rt.to_host(offs)
+    return tuple(pts[offs[i]:offs[i + 1]].reshape(-1, 1, 2).copy() for i in range(len(offs) - 1))
 
 
 def approximate_polygon(contour: NDArray, epsilon_ratio: float = 0.02) -> NDArray:
-    """cv/grid.py:24-34 — fused inside find_grid_contour on the GPU; not exposed per contour."""
-    raise NotImplementedError("approximate_polygon: fused into find_grid_contour on the GPU")
+    """cv/grid.py:24-34 -> (m,1,2) int32 (svb_approx_poly_dp: arcLength + closed approxPolyDP in one warp)."""
+    import torch
+
+    c = np.ascontiguousarray(np.asarray(contour).reshape(-1, 2))
+    if c.dtype != np.int32:
+        raise NotImplementedError("approximate_polygon: only int32 contours (what find_contours returns) are implemented")
+    return rt.to_host(rt.scanner().approx_poly_dp(torch.from_numpy(c), epsilon_ratio)).reshape(-1, 1, 2)
 
 
 def find_grid_contour(binary: NDArray[np.uint8], min_area_ratio: float = 0.1) -> NDArray | None:

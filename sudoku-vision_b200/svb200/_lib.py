@@ -32,6 +32,10 @@ SIGNATURES = {
     "svb_v2_stage": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p]),
     "svb_find_grid_contour": (_i, [_p, _p, _i, _i, _i, _d, _d, _p, _p, _p]),
     "svb_detect_grid_contour_v2": (_i, [_p, _p, _i, _i, _i, _d, _p, _p, _p]),
+    "svb_find_contours_count": (_i, [_p, _p, _i, _i, _p, _p, _p]),
+    "svb_find_contours_fetch": (_i, [_p, _p, _i, _i, _p, _p, _p]),
+    "svb_approx_poly_dp": (_i, [_p, _p, _i, _d, _p, _p, _p]),
+    "svb_is_cell_empty": (_i, [_p, _p, _i, _i, _i, _d, _p, _p, _p]),
     "svb_warp_perspective": (_i, [_p, _p, _i, _i, _i, _p, _p, _i, _p, _p]),
     "svb_extract_cells": (_i, [_p, _p, _i, _i, _p, _p]),
     "svb_cell_prep": (_i, [_p, _p, _ll, _p, _p, _p]),

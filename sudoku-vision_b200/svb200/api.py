@@ -19,6 +19,12 @@ def default_weights_path() -> str:
     return os.path.join(_HERE, "weights", "digitcnn_synth.npz")
 
 
+def coreml_weights_path() -> str:
+    """the only trained DigitCNN weights the reference ships (fp16, recovered from its iOS CoreML package: SURVEY.md 8c;
+    tests/golden/make_helpers_golden.py): MNIST-era, brittle margins — the stress set for argmax parity"""
+    return os.path.join(_HERE, "weights", "digitcnn_coreml.npz")
+
+
 def load_digitcnn_weights(path: str | None = None) -> dict:
     """state_dict-shaped dict of float32 numpy arrays (keys of ml/model.py:22-32)."""
     z = np.load(path or default_weights_path())
@@ -262,6 +268,47 @@ class Scanner:
                                                   float(eps_ratio), _ptr(corners), _ptr(found), self._stream()),
                    "svb_find_grid_contour")
         return corners, found
+
+    def find_contours(self, mask):
+        """cv/grid.py:16-21 for ONE mask (H,W) u8 CUDA: (points (P,2) int32, offsets (C+1,) int64), cv2's order."""
+        self._chk_u8(mask, 2, "find_contours")
+        torch = _torch()
+        h, w = mask.shape
+        nc, npnt = C.c_longlong(0), C.c_longlong(0)
+        _lib.check(self.lib.svb_find_contours_count(self._h, _ptr(mask), h, w, C.byref(nc), C.byref(npnt), self._stream()),
+                   "svb_find_contours_count")
+        pts = torch.empty((max(npnt.value, 1), 2), dtype=torch.int32, device=mask.device)
+        offs = torch.empty((nc.value + 1,), dtype=torch.int64, device=mask.device)
+        _lib.check(self.lib.svb_find_contours_fetch(self._h, _ptr(mask), h, w, _ptr(pts), _ptr(offs), self._stream()),
+                   "svb_find_contours_fetch")
+        return pts[:npnt.value], offs
+
+    def approx_poly_dp(self, contour, epsilon_ratio: float = 0.02):
+        """cv/grid.py:24-34 for one contour (n,2) int32 CUDA -> polygon (m,2) int32."""
+        torch = _torch()
+        contour = contour.to(device=self._dev(), dtype=torch.int32).contiguous().view(-1, 2)
+        n = contour.shape[0]
+        out = torch.empty((n, 2), dtype=torch.int32, device=contour.device)
+        m = torch.zeros((1,), dtype=torch.int32, device=contour.device)
+        _lib.check(self.lib.svb_approx_poly_dp(self._h, _ptr(contour), n, float(epsilon_ratio), _ptr(out), _ptr(m),
+                                               self._stream()), "svb_approx_poly_dp")
+        mv = int(m.item())
+        if mv == -1:
+            raise NotImplementedError("approx_poly_dp: coordinates outside [0, 65535] are not implemented")
+        if mv < 0:
+            raise _lib.SvbError("approx_poly_dp: scratch exhausted on the GPU")
+        return out[:mv]
+
+    def is_cell_empty(self, cells, threshold: float = 0.02, want_info: bool = False):
+        """cv/extract.py:59-79 for a batch of gray cells (n,h,w) u8 CUDA -> empty (n,) u8 [, info (n,2) int32]."""
+        self._chk_u8(cells, 3, "is_cell_empty")
+        torch = _torch()
+        n, ch, cw = cells.shape
+        empty = torch.empty((n,), dtype=torch.uint8, device=cells.device)
+        info = torch.empty((n, 2), dtype=torch.int32, device=cells.device) if want_info else None
+        _lib.check(self.lib.svb_is_cell_empty(self._h, _ptr(cells), n, ch, cw, float(threshold), _ptr(empty), _ptr(info),
+                                              self._stream()), "svb_is_cell_empty")
+        return (empty, info) if want_info else empty
 
     def detect_grid_contour_v2(self, mask, min_area_ratio: float = 0.1):
         """cv/grid_v2.py:102-128 (method 1 of detect_grid): ordered corners (n,4,2) int32 + found (n,)."""

@@ -52,8 +52,8 @@ def contour_host():
     out_dir = os.path.join(ROOT, "tests", "helpers", "_build")
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libcontour_host.so")
-    dep = os.path.join(PKG, "csrc", "contour_core.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(dep)):
+    deps = [os.path.join(PKG, "csrc", "contour_core.cuh"), os.path.join(PKG, "csrc", "contours_all_core.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(d) for d in deps]):
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-ffp-contract=off", "-o", so, src])
     lib = C.CDLL(so)
 
@@ -65,6 +65,20 @@ def contour_host():
                                        c.ctypes.data_as(C.c_void_p), None, None, int(use_bits) | (2 if v2 else 0))
         return f, c
 
+    def find_all(mask):
+        """cv/grid.py:16-21 through the product's contours_all core: list of (n,2) int32 arrays, cv2's order"""
+        mask = np.ascontiguousarray(mask, np.uint8)
+        max_pts, max_c = int(mask.size) + 16, int(mask.size) // 2 + 16
+        pts = np.empty((max_pts, 2), np.int32)
+        offs = np.empty(max_c + 1, np.int64)
+        rounds = C.c_int(0)
+        lib.svbh_find_contours.restype = C.c_longlong
+        n = lib.svbh_find_contours(mask.ctypes.data_as(C.c_void_p), mask.shape[0], mask.shape[1], pts.ctypes.data_as(C.c_void_p),
+                                   C.c_longlong(max_pts), offs.ctypes.data_as(C.c_void_p), C.c_longlong(max_c), C.byref(rounds))
+        assert n >= 0, n
+        return [pts[offs[i]:offs[i + 1]].copy() for i in range(n)], rounds.value
+
+    find.find_all = find_all
     return find
 
 

@@ -3,6 +3,7 @@
 // (probe lines -> loop stats -> candidate selection), so the K2 logic is checked against the
 // oracle in the CPU test tier.  Not part of the product; never loaded by it.
 #include <stdlib.h>
+#include <algorithm>
 #include <vector>
 
 #include "../../sudoku-vision_b200/csrc/contour_core.cuh"
@@ -110,4 +111,69 @@ static int run(const View &m, int h, int w, double min_area_ratio, double eps_ra
                                         SegTables{segs.data(), glist.data(), pitch, nv, segl, segoff});
     status |= st2;
     return got ? 1 : (status ? 2 : 0);
+}
+
+// ---- cv/grid.py:16-21 find_contours: the orchestration of contours_all.cu, serially ---------------------------------
+#include "../../sudoku-vision_b200/csrc/contours_all_core.cuh"
+
+// pts: int32 [max_pts][2]; offs: int64 [max_contours + 1].  Returns the number of contours, -1 on capacity overflow.
+extern "C" __attribute__((visibility("default")))
+long long svbh_find_contours(const uint8_t *mask, int h, int w, int32_t *pts, long long max_pts, long long *offs,
+                             long long max_contours, int *flood_rounds) {
+    const int wp = (w + 31) / 32;
+    std::vector<uint32_t> fg((size_t)h * wp), bg((size_t)h * wp), outer((size_t)h * wp);
+    for (int y = 0; y < h; ++y)
+        for (int c = 0; c < wp; ++c) {  // pack_rows_kernel
+            const int x0 = c * 32;
+            uint32_t f = 0, valid = 0;
+            for (int k = 0; k < 32 && x0 + k < w; ++k) {
+                valid |= 1u << k;
+                if (mask[(size_t)y * w + x0 + k]) f |= 1u << k;
+            }
+            const uint32_t b = ~f & valid;
+            uint32_t seed = 0;
+            if (y == 0 || y == h - 1) seed = b;
+            if (c == 0) seed |= b & 1u;
+            if (x0 <= w - 1 && w - 1 < x0 + 32) seed |= b & (1u << ((w - 1) & 31));
+            fg[(size_t)y * wp + c] = f;
+            bg[(size_t)y * wp + c] = b;
+            outer[(size_t)y * wp + c] = seed;
+        }
+    int rounds = 0;
+    for (;; ++rounds) {
+        bool changed = false;
+        for (int y = 0; y < h; ++y) changed |= flood_row(&bg[(size_t)y * wp], &outer[(size_t)y * wp], wp);
+        for (int c = 0; c < wp; ++c) changed |= flood_col(bg.data(), outer.data(), h, wp, c);
+        if (!changed) break;
+    }
+    if (flood_rounds) *flood_rounds = rounds;
+    const MaskView m{mask, h, w};
+    const int max_steps = h * w * 2 + 16;
+    std::vector<std::pair<int, int>> acc;
+    for (int y = 0; y < h; ++y)
+        for (int c = 0; c < wp; ++c) {  // candidates_kernel + walk_count_kernel
+            const size_t i = (size_t)y * wp + c;
+            const uint32_t west = (outer[i] << 1) | (c == 0 ? 1u : (outer[i - 1] >> 31));
+            uint32_t cand = fg[i] & west;
+            while (cand) {
+                const int k = __builtin_ctz(cand);
+                cand &= cand - 1;
+                SimpleCounter sc;
+                const int r = trace_loop_if_first(m, c * 32 + k, y, max_steps, sc);
+                if (r == -1) return -3;
+                if (r >= 0) acc.push_back({y * w + c * 32 + k, sc.n});
+            }
+        }
+    if ((long long)acc.size() > max_contours) return -1;
+    std::sort(acc.begin(), acc.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.first > b.first; });
+    long long used = 0;
+    offs[0] = 0;
+    for (size_t i = 0; i < acc.size(); ++i) {
+        if (used + acc[i].second > max_pts) return -1;
+        SimpleWriter sw(pts + 2 * used, acc[i].second);  // walk_write_kernel
+        trace_loop_if_first(m, acc[i].first % w, acc[i].first / w, max_steps, sw);
+        used += acc[i].second;
+        offs[i + 1] = used;
+    }
+    return (long long)acc.size();
 }

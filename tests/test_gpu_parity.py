@@ -345,14 +345,34 @@ def test_scan_batch_vs_oracle(scanner, oracle, weights):
     assert found[-1] == 0
 
 
-def test_scan_batch_host_equals_device(scanner):
-    imgs, _, _ = _frames(3, 1080, 1920, 6600)
+@pytest.mark.parametrize("hw", [(1080, 1920), (750, 1000), (300, 500), (96, 48)])
+def test_scan_batch_host_equals_device(scanner, hw):
+    """fused K1 geometry, two sizes that take the stage-kernel fallback inside the host path (w % 16 != 0: ADVICE r1, the
+    staged frames must not alias the fallback's scratch) and w < 64"""
+    imgs, _, _ = _frames(3, hw[0], hw[1], 6600)
     dev = scanner.scan_batch(_t(imgs))
     host = scanner.scan_batch_host(imgs)
     assert np.array_equal(host["digits"], dev["digits"].cpu().numpy())
     assert np.array_equal(host["corners"], dev["corners"].cpu().numpy())
     assert np.array_equal(host["found"], dev["found"].cpu().numpy())
     assert np.array_equal(host["conf"], dev["conf"].cpu().numpy())
+    if hw[0] >= 300:
+        assert int(host["found"].sum()) == 3
+
+
+def test_scan_batch_host_multi_chunk_ragged_tail(scanner):
+    """more than two ~200 MB chunks with a short last one: both workers are reused and the tail chunk is exercised"""
+    import torch
+    from svb200 import frames as F
+
+    clean = np.stack([F.make_frame(6700 + i, 540, 960).image for i in range(3)])
+    n = 2 * ((200 << 20) // (540 * 960 * 3)) + 37
+    big = F.noisy_batch_device(torch.from_numpy(clean).cuda(), n, seed=5)
+    dev = scanner.scan_batch(big)
+    host = scanner.scan_batch_host(big.cpu().numpy())
+    for k in ("digits", "corners", "found", "conf"):
+        assert np.array_equal(host[k], dev[k].cpu().numpy()), k
+    assert int(host["found"].sum()) == n
 
 
 def test_scan_batch_properties_full_size(scanner):
