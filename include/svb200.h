@@ -163,6 +163,13 @@ int svb_is_cell_empty(svb_ctx *ctx, const uint8_t *cells, int n_cells, int cell_
  * cells_pm1 (required): float [n][81][28][28] = model input.  Frames with found == 0 are zero-filled. */
 int svb_cells_from_frames(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, const int32_t *corners,
                           const uint8_t *found, uint8_t *cells_u8, float *cells_pm1, void *stream);
+/* The same without the float tensor: the classifier input of the batched path, cells_bits uint32 [n][81][28] — one word
+ * per cell row, bit x = 1 <=> pixel (x, y) is +1 (ink), 0 <=> -1; bits 28..31 are 0.  (pipeline/run.py:129-135 maps the
+ * thresholded cell to exactly {-1, +1}, so 28 bits per row carry the whole tensor: 112 B per cell instead of 3136.) */
+int svb_cells_from_frames_bits(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, const int32_t *corners,
+                               const uint8_t *found, uint32_t *cells_bits, void *stream);
+/* +-1 float cells [n_cells][28][28] -> bit rows [n_cells][28] (x > 0 <=> bit set) */
+int svb_pack_cells_bits(svb_ctx *ctx, const float *cells_pm1, long long n_cells, uint32_t *cells_bits, void *stream);
 
 /* ---- M1/M2: ml/model.py, pipeline/run.py:139-150 --------------------------------------------- */
 /* DigitCNN parameters (ml/model.py:22-32), PyTorch layouts, fp32, DEVICE pointers:
@@ -177,6 +184,11 @@ int svb_digitcnn_load(svb_ctx *ctx, const float *conv1_w, const float *conv1_b, 
  * softmax(logits)[argmax]; either may be NULL. */
 int svb_digitcnn_forward(svb_ctx *ctx, const float *x, long long n, float *logits, uint8_t *digits,
                          float *conf, void *stream);
+/* DigitCNN.forward on +-1 cells given as bit rows (svb_cells_from_frames_bits / svb_pack_cells_bits): conv1 + bias of a
+ * pixel is looked up by its 9-bit neighbourhood pattern (512 x 32 table built by svb_digitcnn_load) instead of computed;
+ * everything downstream is the same tcgen05 path.  Same outputs as svb_digitcnn_forward. */
+int svb_digitcnn_forward_bits(svb_ctx *ctx, const uint32_t *cells_bits, long long n, float *logits, uint8_t *digits, float *conf,
+                              void *stream);
 
 /* ---- M3: ml/model_v3.py ------------------------------------------------------------------------------ */
 /* DigitCNNv3 (ml/model_v3.py:95-184), eval mode.  `folded` is a HOST array of 38 DEVICE pointers to fp32 tensors

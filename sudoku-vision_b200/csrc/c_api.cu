@@ -51,15 +51,17 @@ int launch_find_grid_contour(svb_ctx *, const uint8_t *, int, int, int, double, 
 uint32_t *contour_bits_buffer(svb_ctx *, int n, int h, int w, cudaStream_t);
 int launch_warp_board(svb_ctx *, const uint8_t *, int, int, int, const int32_t *, const uint8_t *, int, uint8_t *, cudaStream_t);
 int launch_extract_cells(svb_ctx *, const uint8_t *, int, int, uint8_t *, cudaStream_t);
-int launch_cell_prep(svb_ctx *, const uint8_t *, long long, uint8_t *, float *, cudaStream_t);
-int launch_cells_from_frames(svb_ctx *, const uint8_t *, int, int, int, const int32_t *, const uint8_t *, uint8_t *, float *, cudaStream_t);
+int launch_cell_prep(svb_ctx *, const uint8_t *, long long, uint8_t *, float *, uint32_t *, cudaStream_t);
+int launch_cells_from_frames(svb_ctx *, const uint8_t *, int, int, int, const int32_t *, const uint8_t *, uint8_t *, float *, uint32_t *, cudaStream_t);
+int launch_pack_pm1(svb_ctx *, const float *, long long, uint32_t *, cudaStream_t);
+void cell_tables_free(svb_ctx *);
 int digitcnn_load(svb_ctx *, const float *const w[8], cudaStream_t);
 int launch_digitcnn(svb_ctx *, const float *, long long, float *, uint8_t *, float *, cudaStream_t);
 void digitcnn_free(svb_ctx *);
 void digitcnn_v3_free(svb_ctx *);
 int digitcnn_v3_load(svb_ctx *, const float *const *, int, cudaStream_t);
 int launch_digitcnn_v3(svb_ctx *, const float *, long long, float *, uint8_t *, float *, float *, cudaStream_t);
-int launch_digitcnn_tc(svb_ctx *, const float *, long long, float *, uint8_t *, float *, cudaStream_t, cudaEvent_t mid = nullptr);
+int launch_digitcnn_tc(svb_ctx *, const void *, bool bits, long long, float *, uint8_t *, float *, cudaStream_t, cudaEvent_t mid = nullptr);
 int preprocess_v2_run(svb_ctx *, const uint8_t *, const uint8_t *, int, int, int, int, int, uint8_t *, uint8_t *, cudaStream_t);
 int preprocess_multi_run(svb_ctx *, const uint8_t *, const uint8_t *, int, int, int, uint8_t *, uint8_t *, uint8_t *, uint8_t *,
                          uint8_t *, cudaStream_t);
@@ -123,6 +125,7 @@ API void svb_destroy(svb_ctx *ctx) {
         }
     for (int i = 0; i < AR_COUNT; ++i) ctx->arena[i].release();
     find_contours_free(ctx);
+    cell_tables_free(ctx);
     if (!ctx->is_worker) {
         digitcnn_free(ctx);
         digitcnn_v3_free(ctx);
@@ -298,14 +301,27 @@ API int svb_extract_cells(svb_ctx *ctx, const uint8_t *board, int n, int size, u
 API int svb_cell_prep(svb_ctx *ctx, const uint8_t *cells, long long n_cells, uint8_t *thresh, float *pm1, void *stream) {
     GUARD(ctx);
     SVB_REQUIRE(cells && n_cells > 0 && (thresh || pm1), SVB_ERR_INVALID, "svb_cell_prep: bad arguments");
-    return launch_cell_prep(ctx, cells, n_cells, thresh, pm1, (cudaStream_t)stream);
+    return launch_cell_prep(ctx, cells, n_cells, thresh, pm1, nullptr, (cudaStream_t)stream);
 }
 
 API int svb_cells_from_frames(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, const int32_t *corners,
                               const uint8_t *found, uint8_t *cells_u8, float *cells_pm1, void *stream) {
     GUARD(ctx);
     SVB_REQUIRE(bgr && corners && cells_pm1 && dims_ok(n, h, w), SVB_ERR_INVALID, "svb_cells_from_frames: bad arguments");
-    return launch_cells_from_frames(ctx, bgr, n, h, w, corners, found, cells_u8, cells_pm1, (cudaStream_t)stream);
+    return launch_cells_from_frames(ctx, bgr, n, h, w, corners, found, cells_u8, cells_pm1, nullptr, (cudaStream_t)stream);
+}
+
+API int svb_cells_from_frames_bits(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, const int32_t *corners,
+                                   const uint8_t *found, uint32_t *cells_bits, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(bgr && corners && cells_bits && dims_ok(n, h, w), SVB_ERR_INVALID, "svb_cells_from_frames_bits: bad arguments");
+    return launch_cells_from_frames(ctx, bgr, n, h, w, corners, found, nullptr, nullptr, cells_bits, (cudaStream_t)stream);
+}
+
+API int svb_pack_cells_bits(svb_ctx *ctx, const float *cells_pm1, long long n_cells, uint32_t *cells_bits, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(cells_pm1 && cells_bits && n_cells > 0 && n_cells < (1ll << 31), SVB_ERR_INVALID, "svb_pack_cells_bits: bad arguments");
+    return launch_pack_pm1(ctx, cells_pm1, n_cells, cells_bits, (cudaStream_t)stream);
 }
 
 API int svb_digitcnn_load(svb_ctx *ctx, const float *conv1_w, const float *conv1_b, const float *conv2_w,
@@ -327,7 +343,15 @@ API int svb_digitcnn_forward(svb_ctx *ctx, const float *x, long long n, float *l
     GUARD(ctx);
     SVB_REQUIRE(x && logits && n > 0, SVB_ERR_INVALID, "svb_digitcnn_forward: bad arguments");
     if (ctx->classifier_mode == 1) return launch_digitcnn(ctx, x, n, logits, digits, conf, (cudaStream_t)stream);
-    return launch_digitcnn_tc(ctx, x, n, logits, digits, conf, (cudaStream_t)stream);
+    return launch_digitcnn_tc(ctx, x, false, n, logits, digits, conf, (cudaStream_t)stream);
+}
+
+API int svb_digitcnn_forward_bits(svb_ctx *ctx, const uint32_t *cells_bits, long long n, float *logits, uint8_t *digits, float *conf,
+                                  void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(cells_bits && logits && n > 0, SVB_ERR_INVALID, "svb_digitcnn_forward_bits: bad arguments");
+    SVB_REQUIRE(ctx->classifier_mode == 0, SVB_ERR_UNSUPPORTED, "svb_digitcnn_forward_bits: the fp32 cross-check kernels take float cells");
+    return launch_digitcnn_tc(ctx, cells_bits, true, n, logits, digits, conf, (cudaStream_t)stream);
 }
 
 API int svb_digitcnn_v3_load(svb_ctx *ctx, const float *const *folded, int count, void *stream) {
@@ -362,11 +386,15 @@ static int scan_batch(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uin
         off += (bytes + 255) & ~(size_t)255;
         return o;
     };
-    const size_t o_mask = take(px), o_pm1 = take(cells * 784 * sizeof(float)), o_log = take(cells * 10 * sizeof(float));
+    // the classifier input: 28 bit rows per cell for the tensor-core path, +-1 floats for the fp32 cross-check kernels
+    const bool fp32_mode = ctx->classifier_mode == 1;
+    const size_t o_mask = take(px), o_in = take(fp32_mode ? cells * 784 * sizeof(float) : cells * 28 * sizeof(uint32_t));
+    const size_t o_log = take(cells * 10 * sizeof(float));
     if (ctx->arena[AR_PATH].reserve(off) != SVB_OK) return SVB_ERR_CUDA;
     char *base = (char *)ctx->arena[AR_PATH].ptr;
     uint8_t *mask = (uint8_t *)(base + o_mask);
-    float *pm1 = (float *)(base + o_pm1);
+    float *pm1 = fp32_mode ? (float *)(base + o_in) : nullptr;
+    uint32_t *cbits = fp32_mode ? nullptr : (uint32_t *)(base + o_in);
     float *lg = logits ? logits : (float *)(base + o_log);
     const bool tm = ctx->stage_timing;
     auto mark = [&](int i) {
@@ -380,7 +408,7 @@ static int scan_batch(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uin
     rc = launch_find_grid_contour(ctx, mask, n, h, w, 0.1, 0.02, corners, found, st, 0, bits);
     if (rc) return rc;
     mark(2);
-    rc = launch_cells_from_frames(ctx, bgr, n, h, w, corners, found, nullptr, pm1, st);
+    rc = launch_cells_from_frames(ctx, bgr, n, h, w, corners, found, nullptr, pm1, cbits, st);
     if (rc) return rc;
     mark(3);
     // frames without a grid have all-zero cell tensors; their digits/conf are forced to 0 below
@@ -388,7 +416,7 @@ static int scan_batch(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uin
         mark(4);  // fp32 cross-check kernels: not split, everything is booked on the convolution stage
         rc = launch_digitcnn(ctx, pm1, (long long)cells, lg, digits, conf, st);
     } else {
-        rc = launch_digitcnn_tc(ctx, pm1, (long long)cells, lg, digits, conf, st, tm ? ctx->ev[4] : nullptr);
+        rc = launch_digitcnn_tc(ctx, cbits, true, (long long)cells, lg, digits, conf, st, tm ? ctx->ev[4] : nullptr);
     }
     if (rc) return rc;
     rc = launch_mask_not_found(ctx, found, n, digits, conf, st);
@@ -457,7 +485,7 @@ API int svb_scan_batch_v2(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w,
                 if (rc) return rc;
             }
         }
-        rc = launch_cells_from_frames(ctx, fr, m, h, w, corners + (size_t)f0 * 8, found + f0, nullptr, pm1, st);
+        rc = launch_cells_from_frames(ctx, fr, m, h, w, corners + (size_t)f0 * 8, found + f0, nullptr, pm1, nullptr, st);
         if (rc) return rc;
         rc = launch_digitcnn_v3(ctx, pm1, (long long)m * 81, lg, nullptr, nullptr, nullptr, st);
         if (rc) return rc;

@@ -12,6 +12,7 @@
 //                                writes the +-1 classifier input.  The 450x450 board never exists.
 //   stage kernels for the drop-in functions: warp_board_kernel, extract_cells_kernel, cell_prep_kernel
 //   (the latter two are the same device code as K4, entered at a later phase).
+#include "cells_core.cuh"
 #include "common.cuh"
 
 namespace svb {
@@ -20,17 +21,13 @@ namespace k4 {
 constexpr int BOARD = 450;
 constexpr int CELL = 28;
 constexpr int NT = 128;
-
-struct ResizeTab {  // cv2.resize INTER_LINEAR coefficients for `src` -> 28 (SURVEY App. A5)
-    int src;
-    short s0[CELL], a0[CELL], a1[CELL];
-};
+static_assert(BOARD == cellcore::BOARD && CELL == cellcore::CELL && NT == cellcore::NT, "cells_core.cuh constants");
 
 // ---- K3 -----------------------------------------------------------------------------------------
 __device__ __forceinline__ double dm(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double da(double a, double b) { return __dadd_rn(a, b); }
 
-// cv/grid.py:74-91 order_points + :123-130 getPerspectiveTransform(src -> [0,s]x[0,s]) + inversion.
+// cv/grid.py:74-91 order_points + :123-130 getPerspectiveTransform(src -> [0,s]x[0,s]) + inversion (cells_core.cuh).
 // One thread per frame.  minv: [n][9] doubles (maps board pixel -> source pixel, homogeneous).
 __global__ void homography_kernel(const int32_t *__restrict__ corners, const uint8_t *__restrict__ found, int n,
                                   int out_size, double *__restrict__ minv) {
@@ -41,72 +38,7 @@ __global__ void homography_kernel(const int32_t *__restrict__ corners, const uin
         for (int i = 0; i < 9; ++i) o[i] = 0.0;
         return;
     }
-    const int32_t *c = corners + (long long)f * 8;
-    // numpy argmin/argmax: first index wins ties
-    int is_min = 0, is_max = 0, id_min = 0, id_max = 0;
-    for (int i = 1; i < 4; ++i) {
-        const int s = c[2 * i] + c[2 * i + 1], d = c[2 * i + 1] - c[2 * i];
-        if (s < c[2 * is_min] + c[2 * is_min + 1]) is_min = i;
-        if (s > c[2 * is_max] + c[2 * is_max + 1]) is_max = i;
-        if (d < c[2 * id_min + 1] - c[2 * id_min]) id_min = i;
-        if (d > c[2 * id_max + 1] - c[2 * id_max]) id_max = i;
-    }
-    const int order[4] = {is_min, id_min, is_max, id_max};  // TL, TR, BR, BL
-    const double e = (double)(out_size - 1);
-    const double du[4] = {0.0, e, e, 0.0}, dv[4] = {0.0, 0.0, e, e};
-    double A[8][9];
-    for (int i = 0; i < 4; ++i) {
-        const double x = (double)(float)c[2 * order[i]], y = (double)(float)c[2 * order[i] + 1];
-        const double u = du[i], v = dv[i];
-        A[i][0] = x; A[i][1] = y; A[i][2] = 1; A[i][3] = 0; A[i][4] = 0; A[i][5] = 0;
-        A[i][6] = dm(-x, u); A[i][7] = dm(-y, u); A[i][8] = u;
-        A[i + 4][0] = 0; A[i + 4][1] = 0; A[i + 4][2] = 0; A[i + 4][3] = x; A[i + 4][4] = y; A[i + 4][5] = 1;
-        A[i + 4][6] = dm(-x, v); A[i + 4][7] = dm(-y, v); A[i + 4][8] = v;
-    }
-    double M[9];
-    bool singular = false;
-    for (int col = 0; col < 8 && !singular; ++col) {
-        int piv = col;
-        for (int r = col + 1; r < 8; ++r)
-            if (fabs(A[r][col]) > fabs(A[piv][col])) piv = r;
-        if (fabs(A[piv][col]) < 2.220446049250313e-16) { singular = true; break; }
-        if (piv != col)
-            for (int k = 0; k < 9; ++k) { const double t = A[col][k]; A[col][k] = A[piv][k]; A[piv][k] = t; }
-        const double d = -1.0 / A[col][col];
-        for (int r = col + 1; r < 8; ++r) {
-            const double a = dm(A[r][col], d);
-            for (int k = col + 1; k < 9; ++k) A[r][k] = da(A[r][k], dm(a, A[col][k]));
-        }
-    }
-    if (singular) {
-        for (int i = 0; i < 8; ++i) M[i] = 0.0;
-    } else {
-        for (int r = 7; r >= 0; --r) {
-            double s = A[r][8];
-            for (int k = r + 1; k < 8; ++k) s = da(s, -dm(A[r][k], M[k]));
-            M[r] = s / A[r][r];
-        }
-    }
-    M[8] = 1.0;
-    // 3x3 inverse: adjugate / determinant (cv::invert's closed form for 3x3)
-    const double c00 = da(dm(M[4], M[8]), -dm(M[5], M[7]));
-    const double c01 = da(dm(M[3], M[8]), -dm(M[5], M[6]));
-    const double c02 = da(dm(M[3], M[7]), -dm(M[4], M[6]));
-    double det = da(da(dm(M[0], c00), -dm(M[1], c01)), dm(M[2], c02));
-    if (det == 0.0) {
-        for (int i = 0; i < 9; ++i) o[i] = 0.0;
-        return;
-    }
-    det = 1.0 / det;
-    o[0] = dm(c00, det);
-    o[1] = dm(da(dm(M[2], M[7]), -dm(M[1], M[8])), det);
-    o[2] = dm(da(dm(M[1], M[5]), -dm(M[2], M[4])), det);
-    o[3] = dm(da(dm(M[5], M[6]), -dm(M[3], M[8])), det);
-    o[4] = dm(da(dm(M[0], M[8]), -dm(M[2], M[6])), det);
-    o[5] = dm(da(dm(M[2], M[3]), -dm(M[0], M[5])), det);
-    o[6] = dm(c02, det);
-    o[7] = dm(da(dm(M[1], M[6]), -dm(M[0], M[7])), det);
-    o[8] = dm(da(dm(M[0], M[4]), -dm(M[1], M[3])), det);
+    cellcore::homography_inverse(corners + (long long)f * 8, out_size, o);
 }
 
 // ---- warpPerspective sampling (INTER_LINEAR, BORDER_CONSTANT 0), SURVEY App. A4 -----------------------
@@ -205,258 +137,81 @@ __global__ void warp_board_kernel(const uint8_t *__restrict__ bgr, int h, int w,
     o[2] = (v >> 16) & 0xff;
 }
 
-// ---- per-cell pipeline in shared memory --------------------------------------------------------------
-// The 28x28 pixels of a cell over the CTA: thread t < 112 owns column t % 28 and rows t / 28, +4, +8, ... (i = y*28 + x =
-// t + 112 k).  Seven full iterations, like a flat i += blockDim.x loop would need, but x is fixed per thread, so everything
-// that depends on the column only (resize taps, tile columns and blend weights, OpenCV's column classes) is computed once.
-static_assert(NT >= 4 * CELL, "the per-cell pixel loops need four rows of threads");
-#define SVB_FOR_CELL_PIXELS(x, y, i)                                                                          \
-    for (int x = (int)threadIdx.x % CELL, y = (int)threadIdx.x / CELL, i = (int)threadIdx.x; threadIdx.x < 4 * CELL && y < CELL; \
-         y += 4, i += 4 * CELL)
+// ---- per-cell pipeline: phases of cells_core.cuh with a CTA barrier between them -----------------------------------------
+using cellcore::Smem;
+using cellcore::Tables;
 
-struct alignas(16) CellSmem {
-    uint8_t crop[64 * 64];       // gray crop, up to 64x64 (40x40 for the 450 board)
-    uint8_t cell[CELL * CELL];   // extract_cells output
-    uint8_t eq[CELL * CELL];     // CLAHE output
-    uint8_t lut[16][256];
-    int hist[16][256];
-    // Gaussian adaptive threshold: float copy of the CLAHE output with 5 replicated columns each side, and the row pass
-    // with 5 replicated rows above and below (BORDER_REPLICATE without index clamps); both alias the histograms, which are
-    // dead by then
-};
-constexpr int EQP = CELL + 10;   // padded row pitch of the float CLAHE output
-__device__ __forceinline__ float *eqf_of(CellSmem &s) { return reinterpret_cast<float *>(&s.hist[0][0]); }              // [28][38]
-__device__ __forceinline__ float *rpp_of(CellSmem &s) { return reinterpret_cast<float *>(&s.hist[0][0]) + CELL * EQP; }  // [38][28]
-
-// cv2.resize(crop, (28,28)) INTER_LINEAR, 11-bit fixed point
-__device__ __forceinline__ void resize_phase(CellSmem &s, const ResizeTab &rt) {
-    const int cw = rt.src;
-    SVB_FOR_CELL_PIXELS(x, y, i) {
-        const int sy = rt.s0[y], sy1 = min(sy + 1, cw - 1), sx = rt.s0[x], sx1 = min(sx + 1, cw - 1);
-        const int b0 = rt.a0[y], b1 = rt.a1[y], a0 = rt.a0[x], a1 = rt.a1[x];
-        const int h0 = s.crop[sy * cw + sx] * a0 + s.crop[sy * cw + sx1] * a1;
-        const int h1 = s.crop[sy1 * cw + sx] * a0 + s.crop[sy1 * cw + sx1] * a1;
-        s.cell[i] = (uint8_t)(((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16)) + 2) >> 2);
+// everything after the 28x28 u8 cell is in shared memory: CLAHE, threshold, outputs
+template <bool WANT_FLOAT>
+__device__ __forceinline__ void cell_tail(Smem &s, int tid, uint8_t *thr, float *pm1, uint32_t *bits_out) {
+    __syncthreads();
+    cellcore::phase_clahe_a(s, tid);
+    __syncthreads();
+    cellcore::phase_clahe_b(s, tid);
+    __syncthreads();
+    cellcore::phase_clahe_c(s, tid);
+    __syncthreads();
+    cellcore::phase_clahe_blend(s, tid);
+    __syncthreads();
+    cellcore::phase_rowpass(s, tid);
+    __syncthreads();
+    cellcore::phase_colpass(s, tid, WANT_FLOAT ? thr : nullptr, WANT_FLOAT ? pm1 : nullptr);
+    if (bits_out) {
+        __syncthreads();
+        if (tid < CELL) bits_out[tid] = s.bits[tid];
     }
 }
 
-// step = max(256 / resid, 1) and ceil(2^16 / step) (exact floor division of bins < 256 by step) for every residual count
-struct StepEntry {
-    int step, inv;
-};
-struct StepTab {
-    StepEntry e[256];
-    constexpr StepTab() : e{} {
-        for (int r = 0; r < 256; ++r) {
-            const int st = r > 0 ? (256 / r < 1 ? 1 : 256 / r) : 1;
-            e[r].step = st;
-            e[r].inv = (65536 + st - 1) / st;
-        }
-    }
-};
-__constant__ StepTab c_steptab = StepTab();
-
-// createCLAHE(2.0,(4,4)).apply on 28x28: 16 tiles of 7x7, clip 1
-__device__ __forceinline__ void clahe_phase(CellSmem &s) {
-    constexpr int TS = 7, NTL = 4, TA = 49;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 16 * 256 / 4; i += blockDim.x) reinterpret_cast<int4 *>(&s.hist[0][0])[i] = make_int4(0, 0, 0, 0);
-    __syncthreads();
-    SVB_FOR_CELL_PIXELS(x, y, i) atomicAdd(&s.hist[(y / TS) * NTL + (x / TS)][s.cell[i]], 1);
-    __syncthreads();
-    constexpr int clip = (2 * TA / 256) < 1 ? 1 : (2 * TA / 256);  // max(int(2.0 * 49 / 256), 1) = 1
-    static_assert(256 / (TA - clip) >= 4, "redistribution below assumes at most two incremented bins per 8-bin lane");
-    const float lut_scale = 255.0f / (float)TA;
-    // four tiles per warp (the per-cell kernels run NT = 128 threads), unrolled so that the four independent reduce / scan
-    // chains overlap
-#pragma unroll
-    for (int tk = 0; tk < 16 / (NT / 32); ++tk) {
-        const int tile = warp + tk * (NT / 32);
-        const int4 ha = *reinterpret_cast<const int4 *>(&s.hist[tile][lane * 8]), hb = *reinterpret_cast<const int4 *>(&s.hist[tile][lane * 8 + 4]);
-        int hv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
-        int kept = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            hv[k] = min(hv[k], clip);
-            kept += hv[k];
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, off);
-        const int excess = TA - kept;  // every pixel of the tile is in exactly one bin
-        const int batch = excess >> 8, resid = excess & 255;
-        // OpenCV hands the residual out to bins 0, step, 2 step, ... ((resid) of them), step = max(256 / resid, 1): at most two
-        // of them fall into this lane's 8 bins
-        const StepEntry se = c_steptab.e[resid];
-        const int lo = lane * 8, q = (lo * se.inv) >> 16, r = lo - q * se.step, m0 = q + (r != 0 ? 1 : 0);
-        const int p0 = m0 * se.step - lo, p1 = p0 + se.step;
-        const uint32_t incmask = ((p0 < 8 && m0 < resid) ? (1u << p0) : 0u) | ((p1 < 8 && m0 + 1 < resid) ? (1u << p1) : 0u);
-        int run = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            run += hv[k] + batch + (int)((incmask >> k) & 1u);
-            hv[k] = run;  // inclusive prefix inside the lane
-        }
-        int incl = run;  // warp inclusive scan of lane totals
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= off) incl += t;
-        }
-        const int base = incl - run;
-        uint32_t lw[2] = {0u, 0u};
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {  // cumulative counts are <= TA, so the scaled value is already inside 0..255
-            const uint32_t b = (uint32_t)__float2int_rn(__fmul_rn((float)(base + hv[k]), lut_scale));
-            lw[k >> 2] |= b << (8 * (k & 3));
-        }
-        *reinterpret_cast<uint2 *>(&s.lut[tile][lane * 8]) = make_uint2(lw[0], lw[1]);
-    }
-    __syncthreads();
-    const float inv = 1.0f / (float)TS;
-    SVB_FOR_CELL_PIXELS(x, y, i) {
-        const float tyf = __fadd_rn(__fmul_rn((float)y, inv), -0.5f);
-        const float txf = __fadd_rn(__fmul_rn((float)x, inv), -0.5f);
-        int ty1 = (int)floorf(tyf), tx1 = (int)floorf(txf);
-        const float ya = __fadd_rn(tyf, -(float)ty1), xa = __fadd_rn(txf, -(float)tx1);
-        const float ya1 = __fadd_rn(1.0f, -ya), xa1 = __fadd_rn(1.0f, -xa);
-        const int ty2 = min(max(ty1 + 1, 0), NTL - 1), tx2 = min(max(tx1 + 1, 0), NTL - 1);
-        ty1 = min(max(ty1, 0), NTL - 1);
-        tx1 = min(max(tx1, 0), NTL - 1);
-        const int v = s.cell[i];
-        const float l11 = (float)s.lut[ty1 * NTL + tx1][v], l12 = (float)s.lut[ty1 * NTL + tx2][v];
-        const float l21 = (float)s.lut[ty2 * NTL + tx1][v], l22 = (float)s.lut[ty2 * NTL + tx2][v];
-        const float top = __fmul_rn(__fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa)), ya1);
-        const float bot = __fmul_rn(__fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa)), ya);
-        const int ev = min(max(__float2int_rn(__fadd_rn(top, bot)), 0), 255);
-        s.eq[i] = (uint8_t)ev;
-        // the threshold phase reads a float copy with 5 replicated columns on each side (it aliases the histograms, which
-        // nobody reads any more: the LUTs were finished before the barrier above)
-        float *er = eqf_of(s) + y * EQP;
-        const float ef = (float)ev;
-        er[x + 5] = ef;
-        if (x == 0) {
-#pragma unroll
-            for (int j = 0; j < 5; ++j) er[j] = ef;
-        } else if (x == CELL - 1) {
-#pragma unroll
-            for (int j = 0; j < 5; ++j) er[CELL + 5 + j] = ef;
-        }
-    }
-    __syncthreads();
-}
-
-// adaptiveThreshold(GAUSSIAN_C, BINARY, 11, 2) on the 28x28 CLAHE output, OpenCV's column classes
-// for W = 28 (x < 24: vector body; 24..27: 4x-unrolled scalar -> column pass without FMA).
-// thr (optional) = preprocess_cell's return; pm1 (optional) = (255 - thr)/255 normalised to -1/+1.
-__device__ __forceinline__ void threshold_phase(CellSmem &s, uint8_t *__restrict__ thr, float *__restrict__ pm1) {
-    const float k[11] = {SVB_G11_0, SVB_G11_1, SVB_G11_2, SVB_G11_3, SVB_G11_4, SVB_G11_5,
-                         SVB_G11_4, SVB_G11_3, SVB_G11_2, SVB_G11_1, SVB_G11_0};
-    float *eqf = eqf_of(s), *rpp = rpp_of(s);
-    // eqf: float copy of the CLAHE output, columns -5 .. 32 (replicated borders), written by clahe_phase
-    SVB_FOR_CELL_PIXELS(x, y, i) {
-        const float *row = eqf + y * EQP + x;  // row[t] = column x - 5 + t
-        float acc = __fmul_rn(k[0], row[0]);
-#pragma unroll
-        for (int t = 1; t < 11; ++t) acc = __fmaf_rn(k[t], row[t], acc);
-        rpp[(y + 5) * CELL + x] = acc;
-        if (y == 0) {
-#pragma unroll
-            for (int j = 0; j < 5; ++j) rpp[j * CELL + x] = acc;
-        } else if (y == CELL - 1) {
-#pragma unroll
-            for (int j = 0; j < 5; ++j) rpp[(CELL + 5 + j) * CELL + x] = acc;
-        }
-    }
-    __syncthreads();
-    SVB_FOR_CELL_PIXELS(x, y, i) {
-        const float *col = rpp + (y + 5) * CELL + x;
-        float acc = __fmul_rn(k[5], col[0]);
-#pragma unroll
-        for (int j = 1; j <= 5; ++j) {
-            const float sum = __fadd_rn(col[j * CELL], col[-j * CELL]);
-            if (x < 24) acc = __fmaf_rn(k[5 + j], sum, acc);
-            else acc = __fadd_rn(acc, __fmul_rn(k[5 + j], sum));
-        }
-        const int mean = min(rint_pos(acc), 255);
-        const bool white = ((int)s.eq[i] - mean) > -2;  // THRESH_BINARY
-        if (thr) thr[i] = white ? 255 : 0;
-        if (pm1) pm1[i] = white ? -1.0f : 1.0f;  // invert, /255, (x - 0.5) / 0.5
-    }
-}
-
-// K4: one CTA per (frame, cell)
+// K4: one CTA per (frame, cell).  Outputs (each optional): the u8 cell (extract_cells), the +-1 float tensor
+// (the drop-in's view), the 28 bit rows the batched classifier reads.
+template <bool WANT_FLOAT>
 __global__ void __launch_bounds__(NT)
 cells_from_frames_kernel(const uint8_t *__restrict__ bgr, int h, int w, const double *__restrict__ minv,
-                         const uint8_t *__restrict__ found, ResizeTab rt, uint8_t *__restrict__ cells_u8,
-                         float *__restrict__ cells_pm1) {
-    __shared__ CellSmem s;
-    const int f = blockIdx.y, cell = blockIdx.x;
-    const long long obase = ((long long)f * 81 + cell) * (CELL * CELL);
-    if (found && found[f] != 1) {
-        for (int i = threadIdx.x; i < CELL * CELL; i += blockDim.x) {
+                         const uint8_t *__restrict__ found, const Tables *__restrict__ tb, uint8_t *__restrict__ cells_u8,
+                         float *__restrict__ cells_pm1, uint32_t *__restrict__ cells_bits) {
+    __shared__ Smem s;
+    const int f = blockIdx.y, cell = blockIdx.x, tid = threadIdx.x;
+    const long long cidx = (long long)f * 81 + cell, obase = cidx * (CELL * CELL);
+    if (found && found[f] != 1) {  // no grid: all-zero tensors (the classifier's results for this frame are masked later)
+        for (int i = tid; i < CELL * CELL; i += NT) {
             if (cells_u8) cells_u8[obase + i] = 0;
-            cells_pm1[obase + i] = 0.0f;
+            if (WANT_FLOAT && cells_pm1) cells_pm1[obase + i] = 0.0f;
         }
+        if (cells_bits && tid < CELL) cells_bits[cidx * CELL + tid] = 0u;
         return;
     }
-    const int r = cell / 9, c = cell - r * 9;
-    const int cs = BOARD / 9, margin = 5, cw = rt.src;  // 50, int(50*0.1), 40
-    const uint8_t *frame = bgr + (long long)f * h * w * 3;
-    __shared__ double mi[9];
-    if (threadIdx.x < 9) mi[threadIdx.x] = minv[(long long)f * 9 + threadIdx.x];
+    cellcore::phase_setup(s, tid, tb);
+    double mi[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) mi[i] = __ldg(minv + (long long)f * 9 + i);
     __syncthreads();
-    // thread -> one crop column (fixed x: its block/offset terms of the map are hoisted) and every third row
-    if (threadIdx.x < 3 * cw) {
-        const int xx = threadIdx.x % cw, rg = threadIdx.x / cw;
-        const int x = c * cs + margin + xx, bx = (x / 64) * 64;
-        const double bxd = (double)bx, x1d = (double)(x - bx);
-        const double cx0 = dm(mi[0], bxd), cy0 = dm(mi[3], bxd), cw0 = dm(mi[6], bxd);
-        const double mx1 = dm(mi[0], x1d), my1 = dm(mi[3], x1d), mw1 = dm(mi[6], x1d);
-        for (int yy = rg; yy < cw; yy += 3) {
-            const double yd = (double)(r * cs + margin + yy);
-            const double X0 = da(da(cx0, dm(mi[1], yd)), mi[2]);
-            const double Y0 = da(da(cy0, dm(mi[4], yd)), mi[5]);
-            const double W0 = da(da(cw0, dm(mi[7], yd)), mi[8]);
-            double Wd = da(W0, mw1);
-            // 32 / W == 32 * rn(1 / W) exactly (scaling by 2^5 commutes with rounding): the correctly rounded reciprocal is
-            // a shorter sequence than the general double division
-            Wd = (Wd != 0.0) ? dm(__drcp_rn(Wd), 32.0) : 0.0;
-            double fx = dm(da(X0, mx1), Wd), fy = dm(da(Y0, my1), Wd);
-            // cv2 clamps to [INT_MIN, INT_MAX] and rounds; cvt.rni.s32.f64 saturates to the same ends, and a NaN (degenerate
-            // homography) goes through fmax / fmin to INT_MIN
-            const int X = (fx != fx) ? (int)0x80000000 : __double2int_rn(fx), Y = (fy != fy) ? (int)0x80000000 : __double2int_rn(fy);
-            const int ix = X >> 5, iy = Y >> 5, ax = X & 31, ay = Y & 31;
-            uint32_t gv;
-            // footprint inside the frame, and the 12-byte window of its second row inside the buffer
-            if ((unsigned)ix < (unsigned)(w - 1) && (unsigned)iy < (unsigned)(h - 1) && (iy + 2 < h || ix + 4 < w)) {
-                gv = sample_gray_fast(frame, h, w, ix, iy, ax, ay);
-            } else {
-                Tap t;
-                t.ix = ix;
-                t.iy = iy;
-                t.w00 = (32 - ax) * (32 - ay) * 32;
-                t.w01 = ax * (32 - ay) * 32;
-                t.w10 = (32 - ax) * ay * 32;
-                t.w11 = ax * ay * 32;
-                const uint32_t v = sample_bgr(frame, h, w, t);
-                gv = gray_of(v & 0xff, (v >> 8) & 0xff, (v >> 16) & 0xff);
-            }
-            s.crop[yy * cw + xx] = (uint8_t)gv;
-        }
-    }
+    cellcore::phase_sample(s, tid, bgr + (long long)f * h * w * 3, h, w, mi, cell / 9, cell % 9);
     __syncthreads();
-    resize_phase(s, rt);
-    __syncthreads();
-    if (cells_u8)
-        for (int i = threadIdx.x; i < CELL * CELL; i += blockDim.x) cells_u8[obase + i] = s.cell[i];
-    clahe_phase(s);
-    threshold_phase(s, nullptr, cells_pm1 + obase);
+    cellcore::phase_resize(s, tid, cells_u8 ? cells_u8 + obase : nullptr);
+    cell_tail<WANT_FLOAT>(s, tid, nullptr, cells_pm1 ? cells_pm1 + obase : nullptr, cells_bits ? cells_bits + cidx * CELL : nullptr);
 }
 
-// drop-in extract_cells: board [n][size][size][3] -> cells
+// drop-in preprocess_cell (+ tensor prep): cells [n][28][28]
+__global__ void __launch_bounds__(NT)
+cell_prep_kernel(const uint8_t *__restrict__ cells, const Tables *__restrict__ tb, uint8_t *__restrict__ thr, float *__restrict__ pm1,
+                 uint32_t *__restrict__ bits) {
+    __shared__ Smem s;
+    const int tid = threadIdx.x;
+    const long long base = (long long)blockIdx.x * (CELL * CELL);
+    cellcore::phase_setup(s, tid, tb);
+    __syncthreads();
+    cellcore::phase_load_cell(s, tid, cells + base);
+    cell_tail<true>(s, tid, thr ? thr + base : nullptr, pm1 ? pm1 + base : nullptr, bits ? bits + (long long)blockIdx.x * CELL : nullptr);
+}
+
+// drop-in extract_cells: board [n][size][size][3] -> cells, any crop size cv2's INTER_LINEAR path handles (2..64, not 56)
+struct ResizeTab {  // cv2.resize INTER_LINEAR coefficients for `src` -> 28 (SURVEY App. A5)
+    int src;
+    short s0[CELL], a0[CELL], a1[CELL];
+};
 __global__ void __launch_bounds__(NT)
 extract_cells_kernel(const uint8_t *__restrict__ board, int size, ResizeTab rt, uint8_t *__restrict__ cells) {
-    __shared__ CellSmem s;
+    __shared__ uint8_t crop[64 * 64];
     const int f = blockIdx.y, cell = blockIdx.x;
     const int r = cell / 9, c = cell - r * 9;
     const int cs = size / 9, margin = (int)(cs * 0.1), cw = rt.src;
@@ -464,24 +219,29 @@ extract_cells_kernel(const uint8_t *__restrict__ board, int size, ResizeTab rt, 
     for (int i = threadIdx.x; i < cw * cw; i += blockDim.x) {
         const int yy = i / cw, xx = i - yy * cw;
         const uint8_t *p = b + ((long long)(r * cs + margin + yy) * size + (c * cs + margin + xx)) * 3;
-        s.crop[i] = (uint8_t)gray_of(p[0], p[1], p[2]);
+        crop[i] = (uint8_t)gray_of(p[0], p[1], p[2]);
     }
     __syncthreads();
-    resize_phase(s, rt);
-    __syncthreads();
     const long long obase = ((long long)f * 81 + cell) * (CELL * CELL);
-    for (int i = threadIdx.x; i < CELL * CELL; i += blockDim.x) cells[obase + i] = s.cell[i];
+    for (int i = threadIdx.x; i < CELL * CELL; i += blockDim.x) {
+        const int y = i / CELL, x = i - y * CELL;
+        const int sy = rt.s0[y], sy1 = min(sy + 1, cw - 1), sx = rt.s0[x], sx1 = min(sx + 1, cw - 1);
+        const int b0 = rt.a0[y], b1 = rt.a1[y], a0 = rt.a0[x], a1 = rt.a1[x];
+        const int h0 = crop[sy * cw + sx] * a0 + crop[sy * cw + sx1] * a1;
+        const int h1 = crop[sy1 * cw + sx] * a0 + crop[sy1 * cw + sx1] * a1;
+        cells[obase + i] = (uint8_t)(((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16)) + 2) >> 2);
+    }
 }
 
-// drop-in preprocess_cell (+ tensor prep): cells [n][28][28]
-__global__ void __launch_bounds__(NT)
-cell_prep_kernel(const uint8_t *__restrict__ cells, uint8_t *__restrict__ thr, float *__restrict__ pm1) {
-    __shared__ CellSmem s;
-    const long long base = (long long)blockIdx.x * (CELL * CELL);
-    for (int i = threadIdx.x; i < CELL * CELL; i += blockDim.x) s.cell[i] = cells[base + i];
-    __syncthreads();
-    clahe_phase(s);
-    threshold_phase(s, thr ? thr + base : nullptr, pm1 ? pm1 + base : nullptr);
+// +-1 floats -> bit rows (the classifier's batched input format) for callers that hold float cells
+__global__ void pack_pm1_kernel(const float *__restrict__ x, long long n_rows, uint32_t *__restrict__ bits) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    const float *r = x + i * CELL;
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < CELL; ++k) v |= (r[k] > 0.0f ? 1u : 0u) << k;
+    bits[i] = v;
 }
 
 
@@ -712,23 +472,71 @@ int launch_extract_cells(svb_ctx *ctx, const uint8_t *board, int n, int size, ui
     return check_launch(ctx, "k4::extract_cells_kernel");
 }
 
-int launch_cell_prep(svb_ctx *ctx, const uint8_t *cells, long long n_cells, uint8_t *thr, float *pm1, cudaStream_t st) {
+// cv2.resize taps 40 -> 28 and the byte prefix-popcount table, once per context, in device memory
+static int cell_tables(svb_ctx *ctx, const cellcore::Tables **out, cudaStream_t st) {
+    if (!ctx->cell_tables) {
+        cellcore::Tables t;
+        memset(&t, 0, sizeof t);
+        k4::ResizeTab rt;
+        make_resize_tab(cellcore::CROP, &rt);
+        for (int d = 0; d < k4::CELL; ++d) {
+            t.s0[d] = rt.s0[d];
+            t.a0[d] = rt.a0[d];
+            t.a1[d] = rt.a1[d];
+        }
+        for (int b = 0; b < 256; ++b) {
+            uint64_t v = 0;
+            int c = 0;
+            for (int k = 0; k < 8; ++k) {
+                c += (b >> k) & 1;
+                v |= (uint64_t)c << (8 * k);
+            }
+            t.byteprefix[b] = v;
+        }
+        void *d = nullptr;
+        SVB_CUDA_OK(cudaMalloc(&d, sizeof t));
+        // pageable source: the runtime stages the copy before returning, so the local may go out of scope
+        SVB_CUDA_OK(cudaMemcpyAsync(d, &t, sizeof t, cudaMemcpyHostToDevice, st));
+        SVB_CUDA_OK(cudaStreamSynchronize(st));
+        ctx->cell_tables = d;
+    }
+    *out = (const cellcore::Tables *)ctx->cell_tables;
+    return SVB_OK;
+}
+
+int launch_cell_prep(svb_ctx *ctx, const uint8_t *cells, long long n_cells, uint8_t *thr, float *pm1, uint32_t *bits, cudaStream_t st) {
     SVB_REQUIRE(n_cells < (1ll << 31), SVB_ERR_INVALID, "cell_prep: too many cells for one launch");
-    k4::cell_prep_kernel<<<(unsigned)n_cells, k4::NT, 0, st>>>(cells, thr, pm1);
+    const cellcore::Tables *tb = nullptr;
+    int rc = cell_tables(ctx, &tb, st);
+    if (rc) return rc;
+    k4::cell_prep_kernel<<<(unsigned)n_cells, k4::NT, 0, st>>>(cells, tb, thr, pm1, bits);
     return check_launch(ctx, "k4::cell_prep_kernel");
 }
 
-// minv_out (optional): where the per-frame inverse homographies were put (for chaining)
+// cells_u8 / cells_pm1 / cells_bits: each optional
 int launch_cells_from_frames(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, const int32_t *corners,
-                             const uint8_t *found, uint8_t *cells_u8, float *cells_pm1, cudaStream_t st) {
+                             const uint8_t *found, uint8_t *cells_u8, float *cells_pm1, uint32_t *cells_bits, cudaStream_t st) {
     double *minv = nullptr;
     int rc = homography(ctx, corners, found, n, k4::BOARD, &minv, st);
     if (rc) return rc;
-    k4::ResizeTab rt;
-    make_resize_tab(40, &rt);
+    const cellcore::Tables *tb = nullptr;
+    rc = cell_tables(ctx, &tb, st);
+    if (rc) return rc;
     dim3 grid(81, n);
-    k4::cells_from_frames_kernel<<<grid, k4::NT, 0, st>>>(bgr, h, w, minv, found, rt, cells_u8, cells_pm1);
+    if (cells_pm1) k4::cells_from_frames_kernel<true><<<grid, k4::NT, 0, st>>>(bgr, h, w, minv, found, tb, cells_u8, cells_pm1, cells_bits);
+    else k4::cells_from_frames_kernel<false><<<grid, k4::NT, 0, st>>>(bgr, h, w, minv, found, tb, cells_u8, nullptr, cells_bits);
     return check_launch(ctx, "k4::cells_from_frames_kernel");
+}
+
+int launch_pack_pm1(svb_ctx *ctx, const float *x, long long n_cells, uint32_t *bits, cudaStream_t st) {
+    const long long rows = n_cells * k4::CELL;
+    k4::pack_pm1_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(x, rows, bits);
+    return check_launch(ctx, "k4::pack_pm1_kernel");
+}
+
+void cell_tables_free(svb_ctx *ctx) {
+    if (ctx->cell_tables) cudaFree(ctx->cell_tables);
+    ctx->cell_tables = nullptr;
 }
 
 int launch_gray(svb_ctx *, const uint8_t *, int, int, int, uint8_t *, cudaStream_t);

@@ -64,6 +64,7 @@ struct svb_ctx {
     svb::DigitCnnWeights cnn;
     void *cnn_tc = nullptr;    // tensor-core operand images (digitcnn_tc.cu)
     void *cnn_v3 = nullptr;    // folded DigitCNNv3 parameters (digitcnn_v3.cu)
+    void *cell_tables = nullptr;  // cellcore::Tables in device memory (cells.cu)
     void *fc_state = nullptr;  // svb_find_contours_count -> svb_find_contours_fetch (contours_all.cu)
     int classifier_mode = 0;   // 0 = tcgen05 (fp16 hi/lo split), 1 = fp32 CUDA cores
     void *pinned = nullptr;    // host staging for *_host calls

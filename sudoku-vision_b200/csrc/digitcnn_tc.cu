@@ -24,14 +24,18 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
+#include "digitcnn_bits_core.cuh"
 
 namespace svb {
 namespace k5tc {
 
 constexpr int NT = 256;
-constexpr int PAD = 24;                 // zero rows before/after the 256-row padded grid (>= 17, multiple of 8)
-constexpr int SROWS = 256 + 2 * PAD;    // 304
+constexpr int PAD = 25;                 // zero rows before/after the 256-row padded grid (>= 17); 25 makes the K-chunk stride
+                                        // SROWS * 16 B = 8 banks mod 32, so lanes that differ in channel group store conflict-free
+constexpr int SROWS = 256 + 2 * PAD;    // 306
 constexpr int S_BYTES = SROWS * 64;     // 32 fp16 channels per row
 constexpr int WB_BYTES = 64 * 288 * 2;  // conv2 weights, one fp16 part
 constexpr int WB_SBO = 36 * 128;        // 288/8 k-chunks of 128 B per 8-row group
@@ -131,27 +135,69 @@ struct ConvSmem {
     uint32_t tmem_base;
 };
 
+// conv1 of a +-1 input (the batched path: cells arrive as 28 bit rows, cells_core.cuh): conv1 + bias of a pixel is a
+// function of its 9-bit neighbourhood pattern, so it is a 512-entry x 32-channel fp32 table (built at load time with the
+// FMA chain of the float path: bias, then taps 0..8) instead of 288 FMAs.  Taps outside the image are 0, not -1: their
+// pattern bits are 0 and the 9 pixel classes (interior, 4 edges, 4 corners) add back the weights the table subtracted.
+using bitscore::T1_BYTES;
+using bitscore::T1_ENTRY;
+struct ConvSmemBits {
+    alignas(1024) uint8_t S[2][2][S_BYTES];
+    alignas(128) uint8_t WB[2][WB_BYTES];
+    alignas(128) uint8_t T1[T1_BYTES];
+    float C1[9][32];                          // per pixel class: sum of the weights of the taps outside the image
+    float b2[64];
+    uint32_t rows[2][32];                     // bit rows of the cell being convolved: [0][1 + y]; rows 0 and 29 stay zero
+    alignas(8) unsigned long long mbar[2];
+    uint32_t tmem_base;
+};
+
 constexpr int NTC = 512;  // conv kernel: 14 worker warps (conv1, S writes) + 2 MMA-issue warps (one per M tile); all 16 run the epilogue
 constexpr int NWK = 448;  // worker threads
 
 __device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(NWK) : "memory"); }
 
+// item -> (channel group, pooled pixel).  Float input: channel group major (a warp holds one group, 32 pooled pixels).
+// Bit input: channel group minor and the 144 interior pooled pixels before the 52 that touch the image border, so that
+// a warp is either all interior (pure table look-ups) or all border (look-up + class correction).
+template <bool BITS>
+__device__ __forceinline__ void item_coords(int item, int &cg, int &py, int &px) {
+    if (!BITS) {
+        cg = item / 196;
+        const int pp = item - cg * 196;
+        py = pp / 14;
+        px = pp - py * 14;
+    } else {
+        bitscore::item_coords(item, cg, py, px);
+    }
+}
+
+template <bool BITS>
 __global__ void __launch_bounds__(NTC, 1)
-tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__restrict__ w1, const float *__restrict__ b1,
-               const uint8_t *__restrict__ wb_img, const float *__restrict__ b2, __half *__restrict__ feat_hi,
-               __half *__restrict__ feat_lo) {
+tc_conv_kernel(const void *__restrict__ xin_any, long long n_cells, const float *__restrict__ w1, const float *__restrict__ b1,
+               const uint8_t *__restrict__ wb_img, const float *__restrict__ b2, const uint8_t *__restrict__ t1_img,
+               const float *__restrict__ c1_img, __half *__restrict__ feat_hi, __half *__restrict__ feat_lo) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    ConvSmem &s = *reinterpret_cast<ConvSmem *>(smem_raw);
+    using SmemT = typename std::conditional<BITS, ConvSmemBits, ConvSmem>::type;
+    SmemT &s = *reinterpret_cast<SmemT *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float *x = reinterpret_cast<const float *>(xin_any);          // !BITS: [n][784] floats
+    const uint32_t *xb = reinterpret_cast<const uint32_t *>(xin_any);   //  BITS: [n][28] bit rows
 
     // ---- one-time setup ------------------------------------------------------------------------------
     for (int i = tid; i < 2 * 2 * S_BYTES / 16; i += NTC) reinterpret_cast<uint4 *>(&s.S[0][0][0])[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < 2 * WB_BYTES / 16; i += NTC)
         reinterpret_cast<uint4 *>(&s.WB[0][0])[i] = reinterpret_cast<const uint4 *>(wb_img)[i];
-    for (int i = tid; i < 9 * 32; i += NTC) s.w1[i] = w1[i];
-    if (tid < 32) s.b1[tid] = b1[tid];
+    if constexpr (BITS) {
+        for (int i = tid; i < T1_BYTES / 16; i += NTC) reinterpret_cast<uint4 *>(&s.T1[0])[i] = reinterpret_cast<const uint4 *>(t1_img)[i];
+        for (int i = tid; i < 9 * 32; i += NTC) (&s.C1[0][0])[i] = c1_img[i];
+        if (tid < 64) (&s.rows[0][0])[tid] = 0u;
+    } else {
+        for (int i = tid; i < 9 * 32; i += NTC) s.w1[i] = w1[i];
+        if (tid < 32) s.b1[tid] = b1[tid];
+        for (int i = tid; i < 30 * 32; i += NTC) s.inp[i] = 0.f;
+    }
     if (tid < 64) s.b2[tid] = b2[tid];
-    for (int i = tid; i < 30 * 32; i += NTC) s.inp[i] = 0.f;
     if (tid == 0) {
         mbar_init(&s.mbar[0], 2);  // both MMA-issue warps commit
         mbar_init(&s.mbar[1], 2);
@@ -172,30 +218,60 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
     uint4 rh[ITEMS], rl[ITEMS];
 
     auto stage_input = [&](long long cell) {
-        const float *xin = x + cell * 784;
-        for (int i = tid; i < 784; i += NWK) s.inp[(i / 28 + 1) * 32 + (i % 28) + 1] = xin[i];
+        if constexpr (BITS) {
+            if (tid < 28) s.rows[0][1 + tid] = __ldg(xb + cell * 28 + tid);
+        } else {
+            const float *xin = x + cell * 784;
+            for (int i = tid; i < 784; i += NWK) s.inp[(i / 28 + 1) * 32 + (i % 28) + 1] = xin[i];
+        }
     };
     // the same in two halves, so that the global-load latency hides behind other work: each worker thread
-    // owns pixels tid and tid + 480 of the 784
+    // owns pixels tid and tid + 480 of the 784 (float input) / bit row tid (bit input)
     float pre0 = 0.f, pre1 = 0.f;
+    uint32_t preb = 0u;
     auto prefetch_input = [&](long long cell) {
-        const float *xin = x + cell * 784;
-        pre0 = __ldg(xin + tid);
-        if (tid + NWK < 784) pre1 = __ldg(xin + tid + NWK);
+        if constexpr (BITS) {
+            if (tid < 28) preb = __ldg(xb + cell * 28 + tid);
+        } else {
+            const float *xin = x + cell * 784;
+            pre0 = __ldg(xin + tid);
+            if (tid + NWK < 784) pre1 = __ldg(xin + tid + NWK);
+        }
     };
     auto commit_input = [&]() {
-        s.inp[(tid / 28 + 1) * 32 + (tid % 28) + 1] = pre0;
-        if (tid + NWK < 784) s.inp[((tid + NWK) / 28 + 1) * 32 + ((tid + NWK) % 28) + 1] = pre1;
+        if constexpr (BITS) {
+            if (tid < 28) s.rows[0][1 + tid] = preb;
+        } else {
+            s.inp[(tid / 28 + 1) * 32 + (tid % 28) + 1] = pre0;
+            if (tid + NWK < 784) s.inp[((tid + NWK) / 28 + 1) * 32 + ((tid + NWK) % 28) + 1] = pre1;
+        }
     };
     // conv1 + bias + ReLU + 2x2 max-pool for this thread's items -> fp16 hi/lo in registers
     auto conv1_regs = [&]() {
 #pragma unroll
         for (int it = 0; it < ITEMS; ++it) {
             const int item = it * NWK + tid;
-            if (item < 196 * 4) {
+            if constexpr (BITS) {
+                const bool valid = item < 196 * 4;
+                int cg = 0, py = 1, px = 1;
+                if (valid) item_coords<true>(item, cg, py, px);
+                const bool border = valid && ((py == 0) | (py == 13) | (px == 0) | (px == 13));
+                const bool warp_border = __any_sync(0xffffffffu, border);  // every lane of a worker warp gets here
+                if (valid) {
+                    float m[8];
+                    if (warp_border) bitscore::pooled_item(&s.rows[0][0], &s.T1[0], &s.C1[0][0], cg, py, px, true, m);
+                    else bitscore::pooled_item(&s.rows[0][0], &s.T1[0], &s.C1[0][0], cg, py, px, false, m);
+                    __half hi[8], lo[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) split_hi_lo(m[c], hi[c], lo[c]);
+                    rh[it] = *reinterpret_cast<const uint4 *>(hi);
+                    rl[it] = *reinterpret_cast<const uint4 *>(lo);
+                }
+            } else if (item < 196 * 4) {
                 // channel group major, pooled pixel minor: consecutive lanes own consecutive rows of S (16-byte pitch), so
                 // the six 128-bit stores of write_S are conflict-free
-                const int cg = item / 196, pp = item - cg * 196, py = pp / 14, px = pp - py * 14;
+                int cg, py, px;
+                item_coords<false>(item, cg, py, px);
                 float patch[16];
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
@@ -251,7 +327,8 @@ tc_conv_kernel(const float *__restrict__ x, long long n_cells, const float *__re
         for (int it = 0; it < ITEMS; ++it) {
             const int item = it * NWK + tid;
             if (item < 196 * 4) {
-                const int cg = item / 196, pp = item - cg * 196, py = pp / 14, px = pp - py * 14;
+                int cg, py, px;
+                item_coords<BITS>(item, cg, py, px);
                 const int row = (py + 2) * 16 + px + PAD;  // padded 16x16 grid (two halo rows on top) after PAD zero rows
                 const int off = cg * (SROWS * 16) + row * 16;
                 *reinterpret_cast<uint4 *>(&s.S[buf][0][off]) = rh[it];
@@ -594,12 +671,22 @@ __global__ void pack_tc_kernel(const float *__restrict__ c2w, const float *__res
     }
 }
 
+// conv1 + bias for every 3x3 +-1 pattern (bit t = 1 <=> tap t = ky*3+kx is +1), in the FMA order of the float path, and
+// the per-class corrections for taps outside the image.  conv1_w: [9][32] tap-major (DigitCnnWeights), grid 512 x 32 threads.
+__global__ void pack_conv1_table_kernel(const float *__restrict__ w1, const float *__restrict__ b1, uint8_t *__restrict__ t1,
+                                        float *__restrict__ c1) {
+    const int p = blockIdx.x, ch = threadIdx.x;
+    *reinterpret_cast<float *>(t1 + bitscore::t1_offset(p, ch)) = bitscore::t1_value(w1, b1, p, ch);
+    if (p < 9) c1[p * 32 + ch] = bitscore::c1_value(w1, p, ch);
+}
+
 }  // namespace k5tc
 
 // ---- host side ------------------------------------------------------------------------------------------------
 struct TcWeights {
     uint8_t *wb_img = nullptr;  // 2 * WB_BYTES
     __half *w_hi = nullptr, *w_lo = nullptr;
+    uint8_t *t1_img = nullptr;  // conv1 pattern table (T1_BYTES) + class corrections (9 x 32 floats)
 };
 static TcWeights *tcw(svb_ctx *ctx) { return reinterpret_cast<TcWeights *>(ctx->cnn_tc); }
 
@@ -609,11 +696,12 @@ void digitcnn_tc_free(svb_ctx *ctx) {
     if (t->wb_img) cudaFree(t->wb_img);
     if (t->w_hi) cudaFree(t->w_hi);
     if (t->w_lo) cudaFree(t->w_lo);
+    if (t->t1_img) cudaFree(t->t1_img);
     delete t;
     ctx->cnn_tc = nullptr;
 }
 
-// conv2_w / fc1_w: PyTorch layouts, device pointers (called from digitcnn_load)
+// conv2_w / fc1_w: PyTorch layouts, device pointers (called from digitcnn_load, after ctx->cnn's own fp32 images are packed)
 int digitcnn_tc_load(svb_ctx *ctx, const float *conv2_w, const float *fc1_w, cudaStream_t st) {
     using namespace k5tc;
     if (!ctx->cnn_tc) {
@@ -621,11 +709,16 @@ int digitcnn_tc_load(svb_ctx *ctx, const float *conv2_w, const float *fc1_w, cud
         SVB_CUDA_OK(cudaMalloc(&t->wb_img, 2 * WB_BYTES));
         SVB_CUDA_OK(cudaMalloc(&t->w_hi, sizeof(__half) * 128 * 3136));
         SVB_CUDA_OK(cudaMalloc(&t->w_lo, sizeof(__half) * 128 * 3136));
+        SVB_CUDA_OK(cudaMalloc(&t->t1_img, T1_BYTES + 9 * 32 * sizeof(float)));
         ctx->cnn_tc = t;
     }
     TcWeights *t = tcw(ctx);
     pack_tc_kernel<<<(128 * 3136 + 255) / 256, 256, 0, st>>>(conv2_w, fc1_w, t->wb_img, t->w_hi, t->w_lo);
-    return check_launch(ctx, "k5tc::pack_tc_kernel");
+    int rc = check_launch(ctx, "k5tc::pack_tc_kernel");
+    if (rc) return rc;
+    // ctx->cnn.conv1_w is the tap-major [9][32] image digitcnn_load packed on the same stream just before
+    pack_conv1_table_kernel<<<512, 32, 0, st>>>(ctx->cnn.conv1_w, ctx->cnn.conv1_b, t->t1_img, (float *)(t->t1_img + T1_BYTES));
+    return check_launch(ctx, "k5tc::pack_conv1_table_kernel");
 }
 
 // [rows][3136] fp16 matrices as 2-D tensors with 128-row x 64-column boxes written in the 128-byte swizzle
@@ -657,7 +750,8 @@ static bool fc_tensor_maps(const __half *a_hi, const __half *a_lo, const __half 
     return true;
 }
 
-int launch_digitcnn_tc(svb_ctx *ctx, const float *x, long long n, float *logits, uint8_t *digits, float *conf,
+// x: [n][784] floats (any values: the drop-in forward), or with `bits` [n][28] bit rows of +-1 cells (the batched path)
+int launch_digitcnn_tc(svb_ctx *ctx, const void *x, bool bits, long long n, float *logits, uint8_t *digits, float *conf,
                        cudaStream_t st, cudaEvent_t mid) {
     using namespace k5tc;
     SVB_REQUIRE(ctx->cnn.loaded && ctx->cnn_tc, SVB_ERR_NOT_LOADED, "DigitCNN weights not loaded (svb_digitcnn_load)");
@@ -667,9 +761,15 @@ int launch_digitcnn_tc(svb_ctx *ctx, const float *x, long long n, float *logits,
     if (ctx->arena[AR_CNN].reserve(2 * feat_bytes + 512) != SVB_OK) return SVB_ERR_CUDA;
     __half *fh = (__half *)ctx->arena[AR_CNN].ptr;
     __half *fl = (__half *)((char *)ctx->arena[AR_CNN].ptr + ((feat_bytes + 255) & ~(size_t)255));
-    SVB_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem)));
     const int grid = (int)min((long long)ctx->sm_count, n);
-    tc_conv_kernel<<<grid, NTC, sizeof(ConvSmem), st>>>(x, n, c.conv1_w, c.conv1_b, t->wb_img, c.conv2_b, fh, fl);
+    const float *c1 = (const float *)(t->t1_img + T1_BYTES);
+    if (bits) {
+        SVB_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmemBits)));
+        tc_conv_kernel<true><<<grid, NTC, sizeof(ConvSmemBits), st>>>(x, n, c.conv1_w, c.conv1_b, t->wb_img, c.conv2_b, t->t1_img, c1, fh, fl);
+    } else {
+        SVB_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem)));
+        tc_conv_kernel<false><<<grid, NTC, sizeof(ConvSmem), st>>>(x, n, c.conv1_w, c.conv1_b, t->wb_img, c.conv2_b, t->t1_img, c1, fh, fl);
+    }
     int rc = check_launch(ctx, "k5tc::tc_conv_kernel");
     if (rc) return rc;
     if (mid) cudaEventRecord(mid, st);  // stage timing: convolution stack | fc head

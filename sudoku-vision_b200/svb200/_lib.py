@@ -40,6 +40,9 @@ SIGNATURES = {
     "svb_extract_cells": (_i, [_p, _p, _i, _i, _p, _p]),
     "svb_cell_prep": (_i, [_p, _p, _ll, _p, _p, _p]),
     "svb_cells_from_frames": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "svb_cells_from_frames_bits": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "svb_pack_cells_bits": (_i, [_p, _p, _ll, _p, _p]),
+    "svb_digitcnn_forward_bits": (_i, [_p, _p, _ll, _p, _p, _p, _p]),
     "svb_digitcnn_load": (_i, [_p] + [_p] * 8 + [_p]),
     "svb_digitcnn_forward": (_i, [_p, _p, _ll, _p, _p, _p, _p]),
     "svb_set_classifier_mode": (_i, [_p, _i]),

@@ -128,6 +128,28 @@ class Scanner:
                                                  self._stream()), "svb_digitcnn_forward")
         return (logits, digits, conf) if want_digits else logits
 
+    def digitcnn_forward_bits(self, bits, want_digits: bool = False):
+        """bits: (B,28) or (...,28) int32/uint32 CUDA bit rows of +-1 cells -> logits (B,10) [, digits, conf]."""
+        torch = _torch()
+        if not (bits.is_cuda and bits.dtype in (torch.int32, torch.uint32) and bits.is_contiguous() and bits.shape[-1] == 28):
+            raise ValueError("digitcnn_forward_bits: expected contiguous int32 CUDA bit rows (..., 28)")
+        n = bits.numel() // 28
+        logits = torch.empty((n, 10), dtype=torch.float32, device=bits.device)
+        digits = torch.empty((n,), dtype=torch.uint8, device=bits.device) if want_digits else None
+        conf = torch.empty((n,), dtype=torch.float32, device=bits.device) if want_digits else None
+        _lib.check(self.lib.svb_digitcnn_forward_bits(self._h, _ptr(bits), n, _ptr(logits), _ptr(digits), _ptr(conf),
+                                                      self._stream()), "svb_digitcnn_forward_bits")
+        return (logits, digits, conf) if want_digits else logits
+
+    def pack_cells_bits(self, pm1):
+        """+-1 float cells (..., 28, 28) CUDA -> bit rows (..., 28) int32 (bit x of row y set <=> pixel > 0)."""
+        torch = _torch()
+        pm1 = pm1.to(device=self._dev(), dtype=torch.float32).contiguous()
+        n = pm1.numel() // 784
+        bits = torch.empty(tuple(pm1.shape[:-1]), dtype=torch.int32, device=pm1.device)
+        _lib.check(self.lib.svb_pack_cells_bits(self._h, _ptr(pm1), n, _ptr(bits), self._stream()), "svb_pack_cells_bits")
+        return bits
+
     # -- DigitCNNv3 ------------------------------------------------------------------------------------
     def load_weights_v3(self, sd: dict):
         """sd: state_dict of ml/model_v3.DigitCNNv3 (torch tensors or numpy).  Folds BatchNorm (running stats,
@@ -362,6 +384,17 @@ class Scanner:
         _lib.check(self.lib.svb_cells_from_frames(self._h, _ptr(bgr), n, h, w, _ptr(corners), _ptr(found), _ptr(u8),
                                                   _ptr(pm1), self._stream()), "svb_cells_from_frames")
         return u8, pm1
+
+    def cells_from_frames_bits(self, bgr, corners, found=None):
+        """the batched path's K4: (n,H,W,3) frames + corners -> classifier input as bit rows (n,81,28) int32."""
+        self._chk_u8(bgr, 4, "cells_from_frames_bits")
+        torch = _torch()
+        n, h, w, _ = bgr.shape
+        corners = corners.to(device=bgr.device, dtype=torch.int32).contiguous()
+        bits = torch.empty((n, 81, 28), dtype=torch.int32, device=bgr.device)
+        _lib.check(self.lib.svb_cells_from_frames_bits(self._h, _ptr(bgr), n, h, w, _ptr(corners), _ptr(found), _ptr(bits),
+                                                       self._stream()), "svb_cells_from_frames_bits")
+        return bits
 
     # -- whole path ------------------------------------------------------------------------------
     def alloc_outputs(self, n: int, want_logits: bool = False):

@@ -83,6 +83,61 @@ def contour_host():
 
 
 @pytest.fixture(scope="session")
+def cells_host():
+    """The product's per-cell pipeline (csrc/cells_core.cuh) compiled for the host: tests/helpers/cells_host.cpp."""
+    import ctypes as C
+
+    src = os.path.join(ROOT, "tests", "helpers", "cells_host.cpp")
+    out_dir = os.path.join(ROOT, "tests", "helpers", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libcells_host.so")
+    dep = os.path.join(PKG, "csrc", "cells_core.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(dep)):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-ffp-contract=off", "-o", so, src])
+    lib = C.CDLL(so)
+    lib.svbh_map_check.restype = C.c_long
+
+    class H:
+        @staticmethod
+        def cells_from_frame(bgr, corners):
+            bgr = np.ascontiguousarray(bgr, np.uint8)
+            c = np.ascontiguousarray(corners, np.int32).reshape(4, 2)
+            u8 = np.empty((81, 28, 28), np.uint8)
+            bits = np.empty((81, 28), np.uint32)
+            pm1 = np.empty((81, 28, 28), np.float32)
+            lib.svbh_cells_from_frame(bgr.ctypes.data_as(C.c_void_p), bgr.shape[0], bgr.shape[1], c.ctypes.data_as(C.c_void_p),
+                                      u8.ctypes.data_as(C.c_void_p), bits.ctypes.data_as(C.c_void_p), pm1.ctypes.data_as(C.c_void_p))
+            return u8, bits, pm1
+
+        @staticmethod
+        def cell_prep(cells):
+            cells = np.ascontiguousarray(cells, np.uint8).reshape(-1, 28, 28)
+            n = len(cells)
+            thr = np.empty((n, 28, 28), np.uint8)
+            bits = np.empty((n, 28), np.uint32)
+            pm1 = np.empty((n, 28, 28), np.float32)
+            lib.svbh_cell_prep(cells.ctypes.data_as(C.c_void_p), n, thr.ctypes.data_as(C.c_void_p), pm1.ctypes.data_as(C.c_void_p),
+                               bits.ctypes.data_as(C.c_void_p))
+            return thr, bits, pm1
+
+        @staticmethod
+        def map_check(corners):
+            c = np.ascontiguousarray(corners, np.int32).reshape(4, 2)
+            ex = C.c_long(0)
+            bad = lib.svbh_map_check(c.ctypes.data_as(C.c_void_p), C.byref(ex))
+            return int(bad), int(ex.value)
+
+    H.lib = lib
+    return H
+
+
+def bits_to_pm1(bits):
+    """bit rows (..., 28) -> +-1 float cells (..., 28, 28): bit x of row y set <=> +1"""
+    b = (np.asarray(bits).astype(np.uint32)[..., None] >> np.arange(28, dtype=np.uint32)) & 1
+    return np.where(b == 1, 1.0, -1.0).astype(np.float32)
+
+
+@pytest.fixture(scope="session")
 def scanner():
     if not has_cuda():
         pytest.skip("no CUDA device")

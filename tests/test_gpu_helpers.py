@@ -79,7 +79,7 @@ def test_approx_poly_dp_golden_and_oracle(scanner, golden, oracle):
         n = int(rng.integers(3, 400))
         ang = np.sort(rng.random(n)) * 2 * np.pi
         rad = 200 + 150 * rng.random(n) * (t % 3)
-        c = np.stack([400 + rad * np.cos(ang), 400 + rad * np.sin(ang)], 1).astype(np.int32)
+        c = np.stack([600 + rad * np.cos(ang), 600 + rad * np.sin(ang)], 1).astype(np.int32)
         for r in (0.0, 0.01, 0.05):
             eps = r * oracle.arc_length_closed(c)
             want = oracle.approx_poly_dp_closed(c, eps)

@@ -212,6 +212,51 @@ def test_cells_from_frames_vs_oracle_1080p(scanner, oracle):
         assert np.array_equal(pm1[i].cpu().numpy(), want)
 
 
+def test_cells_bits_vs_oracle_and_float_path(scanner, oracle):
+    """the batched path's K4 output (28 bit rows per cell) carries exactly the +-1 tensor of the float path / the oracle"""
+    from conftest import bits_to_pm1
+
+    imgs, _, _ = _frames(3, 1080, 1920, 9100, rot=25.0)
+    imgs = np.concatenate([imgs, np.zeros((1, 1080, 1920, 3), np.uint8)])  # a frame without a grid
+    d = _t(imgs)
+    corners, found = scanner.find_grid_contour(scanner.preprocess(d))
+    bits = scanner.cells_from_frames_bits(d, corners, found).cpu().numpy().astype(np.uint32)
+    _, pm1 = scanner.cells_from_frames(d, corners, found, want_u8=False)
+    pm1 = pm1.cpu().numpy()
+    assert int(found[-1]) == 0 and (bits[-1] == 0).all()
+    for i in range(3):
+        r = oracle.scan_frame(imgs[i])
+        assert r["found"] and int(found[i]) == 1
+        want = (r["cells_in"].astype(np.float32) / 255.0 - 0.5) / 0.5
+        assert np.array_equal(pm1[i], want)
+        assert np.array_equal(bits_to_pm1(bits[i]), want)
+        assert (bits[i] >> 28).max() == 0
+
+
+@pytest.mark.parametrize("n", [1, 81, 500, 20000])
+def test_digitcnn_bits_path_equals_float_path(scanner, oracle, weights, n):
+    """svb_digitcnn_forward_bits (conv1 by 512-pattern table) against svb_digitcnn_forward on the same +-1 cells and the oracle"""
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = torch.where(torch.rand((n, 1, 28, 28), device="cuda", generator=g) < 0.3, 1.0, -1.0)
+    if n >= 81:  # structured cells: borders, full / empty, diagonals exercise every pixel class
+        x[0] = 1.0
+        x[1] = -1.0
+        x[2] = -1.0
+        x[2, 0, 0, :] = x[2, 0, -1, :] = x[2, 0, :, 0] = x[2, 0, :, -1] = 1.0
+        x[3] = torch.where(torch.eye(28, device="cuda") > 0, 1.0, -1.0)
+    bits = scanner.pack_cells_bits(x.view(n, 28, 28))
+    lb, db, cb = scanner.digitcnn_forward_bits(bits, want_digits=True)
+    lf, df, _ = scanner.digitcnn_forward(x, want_digits=True)
+    assert float((lb - lf).abs().max()) < 2e-4
+    k = min(n, 300)
+    want = oracle.digitcnn_forward(weights, x[:k].cpu().numpy())
+    assert np.abs(lb[:k].cpu().numpy() - want).max() < LOGIT_TOL
+    assert np.array_equal(db[:k].cpu().numpy(), want.argmax(1).astype(np.uint8))
+    assert torch.equal(db, df)
+
+
 def test_not_found_frames_are_zero_filled(scanner):
     import torch
 

@@ -1,5 +1,6 @@
 """Profiling driver: runs one stage (or the whole path) a few times on a device-resident synthetic batch.
-    python tools/prof_stage.py [all|k1|k2|k4|k5] [frames] [iters]"""
+    python tools/prof_stage.py [all|k1|k2|k4|k5|k5f] [frames] [iters]
+k4 = the batched cells kernel (bit-row output), k5 = the classifier on bit rows, k5f = the classifier on float cells."""
 import os
 import sys
 
@@ -19,9 +20,14 @@ clean = torch.from_numpy(np.stack([F.make_frame(31000 + i, 1080, 1920).image for
 batch = F.noisy_batch_device(clean, n, seed=7)
 mask = sc.preprocess(batch)
 corners, found = sc.find_grid_contour(mask)
-_, pm1 = sc.cells_from_frames(batch, corners, found, want_u8=False)
-x5 = pm1.view(-1, 1, 28, 28)
-sc.digitcnn_forward(x5)  # warm-up: arenas, function attributes
+bits = sc.cells_from_frames_bits(batch, corners, found)
+xb = bits.view(-1, 28)
+sc.digitcnn_forward_bits(xb)  # warm-up: arenas, function attributes
+x5 = None
+if what == "k5f":
+    _, pm1 = sc.cells_from_frames(batch, corners, found, want_u8=False)
+    x5 = pm1.view(-1, 1, 28, 28)
+    sc.digitcnn_forward(x5)
 out = sc.scan_batch(batch)
 torch.cuda.synchronize()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -32,8 +38,10 @@ for _ in range(iters):
     elif what == "k2":
         sc.find_grid_contour(mask)
     elif what == "k4":
-        sc.cells_from_frames(batch, corners, found, want_u8=False)
+        sc.cells_from_frames_bits(batch, corners, found)
     elif what == "k5":
+        sc.digitcnn_forward_bits(xb)
+    elif what == "k5f":
         sc.digitcnn_forward(x5)
     else:
         sc.scan_batch(batch, out)
