@@ -53,6 +53,12 @@ long long svb_launch_count(const svb_ctx *ctx);
  * elapsed milliseconds of its stages: [0] K1 fused preprocess, [1] K2 contour (reset+probe+select),
  * [2] K3+K4 homography + cells, [3] K5 convolution stack (conv1 + conv2 + pooling), [4] K5 fc1 + fc2 + softmax
  * (+ not-found masking). */
+/* Context options.  SVB_OPT_OVERLAP (default 1): svb_scan_batch_v1 cuts a batch of >= 64 frames into four parts that
+ * alternate between two internal streams, so the latency-bound contour stage of one part runs under the other part's
+ * kernels; 0 = all stages in order on the caller's stream.  Stage timing (below) implies the in-order form. */
+#define SVB_OPT_OVERLAP 1
+int svb_set_option(svb_ctx *ctx, int option, int value);
+
 #define SVB_NUM_STAGES 5
 int svb_stage_timing(svb_ctx *ctx, int enable);
 int svb_last_stage_ms(svb_ctx *ctx, float *ms);

@@ -134,6 +134,8 @@ API void svb_destroy(svb_ctx *ctx) {
     if (ctx->weights_ready) cudaEventDestroy(ctx->weights_ready);
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->ev_fork)
+        if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -425,13 +427,93 @@ static int scan_batch(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uin
     return rc;
 }
 
+// Worker contexts: children of a context with their own stream and scratch arenas, borrowing the parent's weights.  The
+// device-resident call runs sub-batches on two of them so that the latency-bound contour stage of one sub-batch overlaps
+// the bandwidth / tensor-bound stages of the other; the host-buffer call alternates ~200 MB chunks between them so that
+// chunk i+1 crosses PCIe while chunk i is scanned.
+static int get_worker(svb_ctx *ctx, int slot, svb_ctx **out) {
+    if (!ctx->worker[slot]) {
+        svb_ctx *w = new svb_ctx();
+        w->device = ctx->device;
+        w->sm_count = ctx->sm_count;
+        w->is_worker = true;
+        SVB_CUDA_OK(cudaStreamCreateWithFlags(&w->own_stream, cudaStreamNonBlocking));
+        ctx->worker[slot] = w;
+    }
+    svb_ctx *w = ctx->worker[slot];
+    w->cnn = ctx->cnn;        // borrowed device pointers (read-only)
+    w->cnn_tc = ctx->cnn_tc;
+    w->classifier_mode = ctx->classifier_mode;
+    *out = w;
+    return SVB_OK;
+}
+
+
+// Device-resident whole path with the stages of neighbouring sub-batches overlapped: the batch is cut into four parts that
+// alternate between the two worker contexts (own stream + arenas each).  K2 — border walks, a few warps per frame, bound
+// by the latency of dependent steps — then runs under K1 / K4 / K5 of the other stream's part instead of leaving the SMs
+// idle.  The caller's stream is forked and joined with events, so ordering against the caller's other work is unchanged;
+// results are bit-identical to the single-stream path (every frame is processed independently).
+static int scan_batch_overlapped(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *digits, float *conf,
+                                 float *logits, int32_t *corners, uint8_t *found, cudaStream_t st) {
+    constexpr int PARTS = 4;
+    const int per = (n + PARTS - 1) / PARTS;
+    const size_t frame_bytes = (size_t)h * w * 3;
+    svb_ctx *wk[2];
+    for (int s = 0; s < 2; ++s) {
+        int rc = get_worker(ctx, s, &wk[s]);
+        if (rc) return rc;
+    }
+    for (auto &e : ctx->ev_fork)
+        if (!e) SVB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    SVB_CUDA_OK(cudaEventRecord(ctx->ev_fork[0], st));
+    for (int s = 0; s < 2; ++s) {
+        SVB_CUDA_OK(cudaStreamWaitEvent(wk[s]->own_stream, ctx->ev_fork[0], 0));
+        if (ctx->weights_ready) SVB_CUDA_OK(cudaStreamWaitEvent(wk[s]->own_stream, ctx->weights_ready, 0));
+    }
+    int rc = SVB_OK, i = 0;
+    for (int f0 = 0; f0 < n && rc == SVB_OK; f0 += per, ++i) {
+        const int m = n - f0 < per ? n - f0 : per;
+        svb_ctx *k = wk[i & 1];
+        rc = scan_batch(k, bgr + (size_t)f0 * frame_bytes, m, h, w, digits + (size_t)f0 * 81, conf + (size_t)f0 * 81,
+                        logits ? logits + (size_t)f0 * 810 : nullptr, corners + (size_t)f0 * 8, found + f0, k->own_stream);
+        ctx->launches += k->launches;
+        k->launches = 0;
+    }
+    // join even after an error: work already enqueued on the worker streams writes into the caller's buffers
+    for (int s = 0; s < 2; ++s) {
+        if (cudaEventRecord(ctx->ev_fork[1 + s], wk[s]->own_stream) != cudaSuccess || cudaStreamWaitEvent(st, ctx->ev_fork[1 + s], 0) != cudaSuccess) {
+            if (rc == SVB_OK) {
+                set_error("svb_scan_batch_v1: joining the worker streams failed");
+                rc = SVB_ERR_CUDA;
+            }
+        }
+    }
+    return rc;
+}
+
 API int svb_scan_batch_v1(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *digits, float *conf,
                           float *logits, int32_t *corners, uint8_t *found, void *stream) {
     GUARD(ctx);
     SVB_REQUIRE(bgr && digits && conf && corners && found && dims_ok(n, h, w), SVB_ERR_INVALID,
                 "svb_scan_batch_v1: bad arguments");
     SVB_REQUIRE(ctx->cnn.loaded, SVB_ERR_NOT_LOADED, "svb_scan_batch_v1: DigitCNN weights not loaded");
+    // per-stage events need the stages one after the other on one stream; tiny batches have nothing to overlap
+    if (ctx->overlap && !ctx->stage_timing && n >= 64)
+        return scan_batch_overlapped(ctx, bgr, n, h, w, digits, conf, logits, corners, found, (cudaStream_t)stream);
     return scan_batch(ctx, bgr, n, h, w, digits, conf, logits, corners, found, (cudaStream_t)stream);
+}
+
+API int svb_set_option(svb_ctx *ctx, int option, int value) {
+    GUARD(ctx);
+    switch (option) {
+    case SVB_OPT_OVERLAP:
+        ctx->overlap = value != 0;
+        return SVB_OK;
+    default:
+        set_error("svb_set_option: unknown option %d", option);
+        return SVB_ERR_INVALID;
+    }
 }
 
 // v2 whole path (pipeline/run_v2.py:276-330 with --no-quality-check): frames are processed in chunks so that the
@@ -500,26 +582,6 @@ API int svb_solve_batch(svb_ctx *ctx, const uint8_t *grids, int n, uint8_t *solu
     GUARD(ctx);
     SVB_REQUIRE(grids && solutions && status && n > 0, SVB_ERR_INVALID, "svb_solve_batch: bad arguments");
     return launch_solve(ctx, grids, n, solutions, status, (cudaStream_t)stream);
-}
-
-// Host-buffer path.  The frames are split into chunks that alternate between two worker contexts, each with
-// its own stream and scratch arenas: while chunk i is being scanned, chunk i+1 is already crossing PCIe
-// (pinned host memory makes the copies truly asynchronous; pageable memory still works, just serialised).
-static int get_worker(svb_ctx *ctx, int slot, svb_ctx **out) {
-    if (!ctx->worker[slot]) {
-        svb_ctx *w = new svb_ctx();
-        w->device = ctx->device;
-        w->sm_count = ctx->sm_count;
-        w->is_worker = true;
-        SVB_CUDA_OK(cudaStreamCreateWithFlags(&w->own_stream, cudaStreamNonBlocking));
-        ctx->worker[slot] = w;
-    }
-    svb_ctx *w = ctx->worker[slot];
-    w->cnn = ctx->cnn;        // borrowed device pointers (read-only)
-    w->cnn_tc = ctx->cnn_tc;
-    w->classifier_mode = ctx->classifier_mode;
-    *out = w;
-    return SVB_OK;
 }
 
 API int svb_scan_batch_v1_host(svb_ctx *ctx, const uint8_t *host_bgr, int n, int h, int w, uint8_t *host_digits,

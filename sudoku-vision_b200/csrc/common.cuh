@@ -75,6 +75,8 @@ struct svb_ctx {
     // tiled bit mask written by K1 for K2 (AR_BITS): geometry whose pad tiles are known to be zero
     const void *bits_ptr = nullptr;
     int bits_n = 0, bits_h = 0, bits_w = 0;
+    bool overlap = true;                      // svb_scan_batch_v1: sub-batches on two worker streams (SVB_OPT_OVERLAP)
+    cudaEvent_t ev_fork[3] = {};              // fork / join events of the overlapped scan
     cudaEvent_t weights_ready = nullptr;      // recorded on the stream svb_digitcnn_load packed the weights on
     bool stage_timing = false;
     cudaEvent_t ev[SVB_NUM_STAGES + 1] = {};

@@ -580,7 +580,9 @@ static int launch_k1w(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uin
     const int smem = (int)sizeof(WarpSmem<CH>);
     SVB_CUDA_OK(cudaFuncSetAttribute(fused_preprocess_warp_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int nstrips = (w + TW - 1) / TW;
-    // row segments: enough warps for ~8 waves of the 12 resident warps per SM, segments no shorter than 64 rows
+    // row segments: enough warps for ~8 waves of the 12 resident warps per SM (every segment re-computes ~16 warm-up rows,
+    // so more, shorter segments cost work; fewer, longer ones leave a longer idle tail behind the last wave), segments no
+    // shorter than 64 rows
     const long long strips = (long long)nstrips * n;
     long long want = (8LL * 12 * ctx->sm_count + strips - 1) / strips;
     int nseg = (int)max(1LL, min(want, (long long)(h / 64)));

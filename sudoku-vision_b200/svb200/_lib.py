@@ -21,6 +21,7 @@ SIGNATURES = {
     "svb_last_error": (C.c_char_p, []),
     "svb_abi_version": (_i, []),
     "svb_launch_count": (_ll, [_p]),
+    "svb_set_option": (_i, [_p, _i, _i]),
     "svb_stage_timing": (_i, [_p, _i]),
     "svb_last_stage_ms": (_i, [_p, _p]),
     "svb_grayscale": (_i, [_p, _p, _i, _i, _i, _p, _p]),

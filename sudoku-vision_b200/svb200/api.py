@@ -86,6 +86,12 @@ class Scanner:
     def launches(self) -> int:
         return int(self.lib.svb_launch_count(self._h))
 
+    OPTIONS = dict(overlap=1)
+
+    def set_option(self, name: str, value: int):
+        """'overlap' (default 1): scan_batch runs sub-batches on two internal streams (see include/svb200.h)."""
+        _lib.check(self.lib.svb_set_option(self._h, self.OPTIONS[name], int(value)), "svb_set_option")
+
     STAGES = ("k1_preprocess", "k2_contour", "k34_cells", "k5_conv", "k5_fc")
 
     def stage_timing(self, enable: bool = True):

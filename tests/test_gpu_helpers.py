@@ -144,13 +144,16 @@ def test_unchanged_cv_test_pipeline(tmp_path):
 
 
 def test_unchanged_benchmark_py():
-    """pipeline/benchmark.py (byte-identical, the script BASELINE.json's north star names) on the drop-in."""
+    """pipeline/benchmark.py (byte-identical, the script BASELINE.json's north star names) on the drop-in: the same report,
+    line for line, as the unmodified reference printed on cv2 + torch CPU in the build container
+    (tests/golden/benchmark_py_stdout.txt: with the synthetic-trained fixture weights no photo solves — the reference's own
+    outcome — so every line is a detection / recognition result and none carries a timing)."""
     _staged()
     r = _launch("pipeline/benchmark.py")
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "Testing 5 images" in r.stdout
-    assert r.stdout.count("--- sample_") == 5
-    assert "sample_2.jpg" in r.stdout and "Grid detection failed: no quadrilateral found" in r.stdout
+    want = open(ROOT / "tests" / "golden" / "benchmark_py_stdout.txt").read().splitlines()
+    got = [ln for ln in r.stdout.splitlines() if "Testing 5 images" not in ln]
+    assert got == want, "\n".join(got[-40:]) + r.stderr[-1500:]
+    assert r.returncode == 1  # benchmark.py:110 returns 0 only if at least one photo solved
 
 
 def test_unchanged_run_v2_cv_section(golden):

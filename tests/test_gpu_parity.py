@@ -420,6 +420,29 @@ def test_scan_batch_host_multi_chunk_ragged_tail(scanner):
     assert int(host["found"].sum()) == n
 
 
+def test_scan_batch_overlapped_equals_in_order(scanner):
+    """svb_scan_batch_v1 cuts batches of >= 64 frames into four parts on two internal streams (SVB_OPT_OVERLAP): every
+    output must be bit-identical to the in-order single-stream form, including a ragged part and a no-grid frame."""
+    import torch
+    from svb200 import frames as F
+
+    clean = np.stack([F.make_frame(5200 + i, 1080, 1920).image for i in range(3)])
+    big = F.noisy_batch_device(torch.from_numpy(clean).cuda(), 131, seed=4)
+    big[77] = 0
+    try:
+        scanner.set_option("overlap", 1)
+        a = scanner.scan_batch(big, want_logits=True)
+        torch.cuda.synchronize()
+        scanner.set_option("overlap", 0)
+        b = scanner.scan_batch(big, want_logits=True)
+        torch.cuda.synchronize()
+    finally:
+        scanner.set_option("overlap", 1)
+    for k in ("digits", "conf", "corners", "found", "logits"):
+        assert torch.equal(a[k], b[k]), k
+    assert int(a["found"][77]) == 0 and int((a["found"] == 1).sum()) == 130
+
+
 def test_scan_batch_properties_full_size(scanner):
     """BASELINE config 2 shape (1080p, a large batch): size-independent properties — determinism,
     batch-composition independence (frame i's result does not depend on its neighbours), and
