@@ -531,8 +531,7 @@ def main():
     barrier()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     launches = sc.launches - launches0
-    # per-stage times: K more steps with the library's stage events on.  That is the in-order form of the same launches (the
-    # timed steps above overlap sub-batches on two internal streams, so no per-stage interval exists there); kept out of `value`
+    # per-stage times: K more steps with the library's stage events on: the same launches in the same order (kept out of `value`)
     sc.stage_timing(True)
     sc.scan_batch(batch, out)
     es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -583,6 +582,58 @@ def main():
     h2d_s = max_over_ranks(time.perf_counter() - t0)
     h2d_ceiling = 4 * nb * H * W * 3 * world / h2d_s / 1e9
     del dst
+    # ---- e2e_jpeg: the same frames arrive COMPRESSED (cv2.imwrite's encoder, quality 95, one restart marker per 8 MCUs): H2D of
+    # the JPEG bytes, GPU decode (svb_scan_batch_v1_jpeg_host), whole path, D2H of the boards.  Reported beside `e2e`, with its
+    # own parity counters: the decoder is lossless against cv2.imdecode, but JPEG itself changes the pixels of the raw frames
+    e2e_jpeg = None
+    try:
+        import cv2
+
+        uniq = min(args.unique, 16)
+        raw_u = batch[:uniq].cpu().numpy()
+        files = []
+        for i in range(uniq):
+            ok, buf = cv2.imencode(".jpg", raw_u[i], [cv2.IMWRITE_JPEG_QUALITY, 95, cv2.IMWRITE_JPEG_RST_INTERVAL, 8])
+            files.append(buf.tobytes())
+        blob_u, offs_u = Scanner.pack_jpegs([files[i % uniq] for i in range(En)])
+        jblob = torch.from_numpy(blob_u).pin_memory()
+        joffs = torch.from_numpy(offs_u)
+        jout = dict(digits=torch.empty((En, 81), dtype=torch.uint8).pin_memory(), conf=torch.empty((En, 81), dtype=torch.float32).pin_memory(),
+                    corners=torch.empty((En, 4, 2), dtype=torch.int32).pin_memory(), found=torch.empty((En,), dtype=torch.uint8).pin_memory())
+        for _ in range(2):
+            sc.scan_batch_jpeg_host(jblob, joffs, H, W, jout)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            sc.scan_batch_jpeg_host(jblob, joffs, H, W, jout)
+        barrier()
+        jpeg_s = max_over_ranks(time.perf_counter() - t0)
+        e2e_jpeg = {"value": En * world * args.steps / jpeg_s, "unit": "frames/s", "h2d_bytes_per_step": int(offs_u[-1]) * world,
+                    "d2h_bytes_per_step": En * (81 + 81 * 4 + 32 + 1) * world, "frames_per_step": En,
+                    "compressed_bytes_per_frame": int(offs_u[-1]) // En,
+                    "what": "svb_scan_batch_v1_jpeg_host: pinned JPEG bytes (cv2 encoder, quality 95, DRI 8 MCUs) -> GPU Huffman + IDCT + "
+                            "colour -> K1..K5 -> boards in host memory"}
+        if rank == 0:
+            # parity of the ingest path: GPU-decoded frames vs cv2.imdecode of the same files, and the boards vs the device path
+            dec = sc.jpeg_decode(blob_u[:int(offs_u[uniq]) + 64], offs_u[:uniq + 1], H, W)
+            ref = np.stack([cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_COLOR) for f in files])
+            dref = torch.from_numpy(ref).to(dev)
+            a, b = sc.scan_batch(dec), sc.scan_batch(dref)
+            raw = sc.scan_batch(batch[:uniq].contiguous())
+            torch.cuda.synchronize()
+            ok_f = (raw["found"] == 1) & (a["found"] == 1)
+            e2e_jpeg["parity"] = {
+                "frames": uniq, "decoded_px_equal_cv2_imdecode": float((dec == dref).float().mean().item()),
+                "digits_identical_vs_cv2_decoded": float((a["digits"] == b["digits"]).float().mean().item()),
+                "corners_exact_vs_cv2_decoded": int((a["corners"] == b["corners"]).all(-1).all(-1).sum().item()),
+                "found_vs_raw_frames": int((a["found"] == raw["found"]).sum().item()),
+                "corners_le1px_vs_raw_frames": int(((a["corners"] - raw["corners"]).abs().amax((1, 2)) <= 1)[ok_f].sum().item()),
+                "digits_identical_vs_raw_frames": float((a["digits"] == raw["digits"])[ok_f].float().mean().item()) if bool(ok_f.any()) else None,
+                "note": "vs cv2.imdecode: the decoder's own parity (same files); vs raw frames: what JPEG quality 95 itself changes"}
+            del dec, dref
+        del jblob
+    except ImportError:
+        e2e_jpeg = {"unavailable": "cv2 (the encoder for the synthetic JPEG frames) is not importable here"}
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- BASELINE configs[4]: sustained streaming ------------------------------------------------------------------------
@@ -697,11 +748,11 @@ def main():
                     "h2d_gbs": En * H * W * 3 * world * args.steps / e2e_s / 1e9, "h2d_ceiling_gbs": h2d_ceiling,
                     "frac_of_ceiling": (En * H * W * 3 * world * args.steps / e2e_s / 1e9) / h2d_ceiling,
                     "ceiling_how": f"plain pinned cudaMemcpyAsync host->device of {nb} frames x4, all {world} rank(s) at once, wall clock max over ranks"},
+            "e2e_jpeg": e2e_jpeg,
             "gpu_launches": int(launches),
             "stage_ms_per_step": {k: round(v, 4) for k, v in stage_ms.items()},
-            "stage_ms_how": "CUDA events between the stages of K extra steps run in order on one stream (svb_stage_timing); the timed "
-                            "steps behind `value` run four sub-batches on two internal streams so that the contour stage overlaps the others",
-            "ms_per_step_in_order": ms_serial,
+            "stage_ms_how": "CUDA events the library records between the stages (svb_stage_timing) of K extra steps, same launches as the timed steps",
+            "ms_per_step_with_stage_events": ms_serial,
             "roofline": dominant, "rooflines": roofs, "parity": parity, "parity_coreml_weights": coreml,
             "stream": stream, "cpu_baseline": cpu, "clocks": clocks, "other_configs": other_cfg,
         }

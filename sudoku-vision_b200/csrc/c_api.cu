@@ -55,6 +55,8 @@ int launch_cell_prep(svb_ctx *, const uint8_t *, long long, uint8_t *, float *, 
 int launch_cells_from_frames(svb_ctx *, const uint8_t *, int, int, int, const int32_t *, const uint8_t *, uint8_t *, float *, uint32_t *, cudaStream_t);
 int launch_pack_pm1(svb_ctx *, const float *, long long, uint32_t *, cudaStream_t);
 void cell_tables_free(svb_ctx *);
+int jpeg_decode_batch(svb_ctx *, const uint8_t *, const long long *, const uint8_t *, int, int, int, uint8_t *, uint8_t *, cudaStream_t);
+void jpeg_free(svb_ctx *);
 int digitcnn_load(svb_ctx *, const float *const w[8], cudaStream_t);
 int launch_digitcnn(svb_ctx *, const float *, long long, float *, uint8_t *, float *, cudaStream_t);
 void digitcnn_free(svb_ctx *);
@@ -126,6 +128,7 @@ API void svb_destroy(svb_ctx *ctx) {
     for (int i = 0; i < AR_COUNT; ++i) ctx->arena[i].release();
     find_contours_free(ctx);
     cell_tables_free(ctx);
+    jpeg_free(ctx);
     if (!ctx->is_worker) {
         digitcnn_free(ctx);
         digitcnn_v3_free(ctx);
@@ -449,14 +452,14 @@ static int get_worker(svb_ctx *ctx, int slot, svb_ctx **out) {
 }
 
 
-// Device-resident whole path with the stages of neighbouring sub-batches overlapped: the batch is cut into four parts that
+// Device-resident whole path with the stages of neighbouring sub-batches overlapped: the batch is cut into `overlap` parts that
 // alternate between the two worker contexts (own stream + arenas each).  K2 — border walks, a few warps per frame, bound
 // by the latency of dependent steps — then runs under K1 / K4 / K5 of the other stream's part instead of leaving the SMs
 // idle.  The caller's stream is forked and joined with events, so ordering against the caller's other work is unchanged;
 // results are bit-identical to the single-stream path (every frame is processed independently).
 static int scan_batch_overlapped(svb_ctx *ctx, const uint8_t *bgr, int n, int h, int w, uint8_t *digits, float *conf,
                                  float *logits, int32_t *corners, uint8_t *found, cudaStream_t st) {
-    constexpr int PARTS = 4;
+    const int PARTS = ctx->overlap < 2 ? 2 : (ctx->overlap > 16 ? 16 : ctx->overlap);
     const int per = (n + PARTS - 1) / PARTS;
     const size_t frame_bytes = (size_t)h * w * 3;
     svb_ctx *wk[2];
@@ -508,7 +511,7 @@ API int svb_set_option(svb_ctx *ctx, int option, int value) {
     GUARD(ctx);
     switch (option) {
     case SVB_OPT_OVERLAP:
-        ctx->overlap = value != 0;
+        ctx->overlap = value < 0 ? 0 : value;
         return SVB_OK;
     default:
         set_error("svb_set_option: unknown option %d", option);
@@ -619,6 +622,65 @@ API int svb_scan_batch_v1_host(svb_ctx *ctx, const uint8_t *host_bgr, int n, int
             SVB_CUDA_OK(cudaMemcpyAsync(d, host_bgr + (size_t)f0 * frame_bytes, frame_bytes * m, cudaMemcpyHostToDevice, st));
             const int r = scan_batch(k, (const uint8_t *)d, m, h, w, (uint8_t *)(d + o_dig), (float *)(d + o_conf), nullptr,
                                      (int32_t *)(d + o_cor), (uint8_t *)(d + o_fnd), st);
+            ctx->launches += k->launches;
+            k->launches = 0;
+            if (r) return r;
+            SVB_CUDA_OK(cudaMemcpyAsync(host_digits + (size_t)f0 * 81, d + o_dig, (size_t)m * 81, cudaMemcpyDeviceToHost, st));
+            SVB_CUDA_OK(cudaMemcpyAsync(host_conf + (size_t)f0 * 81, d + o_conf, (size_t)m * 81 * 4, cudaMemcpyDeviceToHost, st));
+            SVB_CUDA_OK(cudaMemcpyAsync(host_corners + (size_t)f0 * 8, d + o_cor, (size_t)m * 32, cudaMemcpyDeviceToHost, st));
+            SVB_CUDA_OK(cudaMemcpyAsync(host_found + f0, d + o_fnd, (size_t)m, cudaMemcpyDeviceToHost, st));
+            return SVB_OK;
+        }();
+    }
+    const cudaError_t e0 = cudaStreamSynchronize(wk[0]->own_stream), e1 = cudaStreamSynchronize(wk[1]->own_stream);
+    if (rc) return rc;
+    SVB_CUDA_OK(e0);
+    SVB_CUDA_OK(e1);
+    return SVB_OK;
+}
+
+// ---- frame ingest: cv2.imread's decode step (pipeline/run.py:250) on the GPU -------------------------------------------------
+API int svb_jpeg_decode_host(svb_ctx *ctx, const uint8_t *host_jpeg, const long long *host_offsets, int n, int h, int w, uint8_t *bgr,
+                             uint8_t *status, void *stream) {
+    GUARD(ctx);
+    SVB_REQUIRE(host_jpeg && host_offsets && bgr && dims_ok(n, h, w), SVB_ERR_INVALID, "svb_jpeg_decode_host: bad arguments");
+    return jpeg_decode_batch(ctx, host_jpeg, host_offsets, nullptr, n, h, w, bgr, status, (cudaStream_t)stream);
+}
+
+// compressed frames in host memory -> boards in host memory: chunks alternate between the two worker contexts, each chunk is
+// copied (compressed), decoded into that worker's frame buffer, scanned, and its boards copied back
+API int svb_scan_batch_v1_jpeg_host(svb_ctx *ctx, const uint8_t *host_jpeg, const long long *host_offsets, int n, int h, int w,
+                                    uint8_t *host_digits, float *host_conf, int32_t *host_corners, uint8_t *host_found) {
+    GUARD(ctx);
+    SVB_REQUIRE(host_jpeg && host_offsets && host_digits && host_conf && host_corners && host_found && dims_ok(n, h, w), SVB_ERR_INVALID,
+                "svb_scan_batch_v1_jpeg_host: bad arguments");
+    SVB_REQUIRE(ctx->cnn.loaded, SVB_ERR_NOT_LOADED, "svb_scan_batch_v1_jpeg_host: DigitCNN weights not loaded");
+    const size_t frame_bytes = (size_t)h * w * 3;
+    // chunks of up to ~800 MB of decoded frames: enough restart intervals in flight to fill the machine's thread slots
+    int chunk = (int)((size_t)(800u << 20) / frame_bytes);
+    chunk = chunk < 1 ? 1 : (chunk > n ? n : chunk);
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_dig = al(frame_bytes * chunk), o_conf = o_dig + al((size_t)chunk * 81);
+    const size_t o_cor = o_conf + al((size_t)chunk * 81 * 4), o_fnd = o_cor + al((size_t)chunk * 32);
+    const size_t total = o_fnd + al((size_t)chunk);
+    svb_ctx *wk[2];
+    for (int s = 0; s < 2; ++s) {
+        int rc = get_worker(ctx, s, &wk[s]);
+        if (rc) return rc;
+        if (wk[s]->arena[AR_HOSTIN].reserve(total) != SVB_OK) return SVB_ERR_CUDA;
+        if (ctx->weights_ready) SVB_CUDA_OK(cudaStreamWaitEvent(wk[s]->own_stream, ctx->weights_ready, 0));
+    }
+    int rc = SVB_OK, i = 0;
+    for (int f0 = 0; f0 < n && rc == SVB_OK; f0 += chunk, ++i) {
+        const int m = (n - f0 < chunk) ? n - f0 : chunk;
+        svb_ctx *k = wk[i & 1];
+        cudaStream_t st = k->own_stream;
+        char *d = (char *)k->arena[AR_HOSTIN].ptr;
+        rc = [&]() -> int {
+            int r = jpeg_decode_batch(k, host_jpeg, host_offsets + f0, nullptr, m, h, w, (uint8_t *)d, nullptr, st);
+            if (r) return r;
+            r = scan_batch(k, (const uint8_t *)d, m, h, w, (uint8_t *)(d + o_dig), (float *)(d + o_conf), nullptr,
+                           (int32_t *)(d + o_cor), (uint8_t *)(d + o_fnd), st);
             ctx->launches += k->launches;
             k->launches = 0;
             if (r) return r;

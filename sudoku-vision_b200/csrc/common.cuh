@@ -53,7 +53,7 @@ struct DigitCnnWeights {
 
 namespace svb {
 // context-owned scratch arenas, one per purpose so that chained stages never alias
-enum Arena { AR_ADAPT = 0, AR_STAGE, AR_CONTOUR, AR_HOMOG, AR_CNN, AR_PATH, AR_V2, AR_V2T, AR_QUAL, AR_SOLVE, AR_BITS, AR_HOSTIN, AR_FC, AR_FCP, AR_COUNT };
+enum Arena { AR_ADAPT = 0, AR_STAGE, AR_CONTOUR, AR_HOMOG, AR_CNN, AR_PATH, AR_V2, AR_V2T, AR_QUAL, AR_SOLVE, AR_BITS, AR_HOSTIN, AR_FC, AR_FCP, AR_JPEG, AR_COUNT };
 }
 
 struct svb_ctx {
@@ -65,6 +65,7 @@ struct svb_ctx {
     void *cnn_tc = nullptr;    // tensor-core operand images (digitcnn_tc.cu)
     void *cnn_v3 = nullptr;    // folded DigitCNNv3 parameters (digitcnn_v3.cu)
     void *cell_tables = nullptr;  // cellcore::Tables in device memory (cells.cu)
+    void *jpeg_state = nullptr;   // pinned header staging of svb_jpeg_decode_host (jpeg.cu)
     void *fc_state = nullptr;  // svb_find_contours_count -> svb_find_contours_fetch (contours_all.cu)
     int classifier_mode = 0;   // 0 = tcgen05 (fp16 hi/lo split), 1 = fp32 CUDA cores
     void *pinned = nullptr;    // host staging for *_host calls
@@ -75,7 +76,7 @@ struct svb_ctx {
     // tiled bit mask written by K1 for K2 (AR_BITS): geometry whose pad tiles are known to be zero
     const void *bits_ptr = nullptr;
     int bits_n = 0, bits_h = 0, bits_w = 0;
-    bool overlap = true;                      // svb_scan_batch_v1: sub-batches on two worker streams (SVB_OPT_OVERLAP)
+    int overlap = 0;                          // svb_scan_batch_v1: > 1 = that many sub-batches on two worker streams (SVB_OPT_OVERLAP)
     cudaEvent_t ev_fork[3] = {};              // fork / join events of the overlapped scan
     cudaEvent_t weights_ready = nullptr;      // recorded on the stream svb_digitcnn_load packed the weights on
     bool stage_timing = false;

@@ -54,6 +54,8 @@ SIGNATURES = {
     "svb_scan_batch_v2": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _d, _p]),
     "svb_solve_batch": (_i, [_p, _p, _i, _p, _p, _p]),
     "svb_scan_batch_v1_host": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "svb_jpeg_decode_host": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
+    "svb_scan_batch_v1_jpeg_host": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
 }
 
 _lib = None

@@ -89,7 +89,7 @@ class Scanner:
     OPTIONS = dict(overlap=1)
 
     def set_option(self, name: str, value: int):
-        """'overlap' (default 1): scan_batch runs sub-batches on two internal streams (see include/svb200.h)."""
+        """'overlap' (default 0): p >= 2 makes scan_batch run p sub-batches on two internal streams (see include/svb200.h)."""
         _lib.check(self.lib.svb_set_option(self._h, self.OPTIONS[name], int(value)), "svb_set_option")
 
     STAGES = ("k1_preprocess", "k2_contour", "k34_cells", "k5_conv", "k5_fc")
@@ -496,3 +496,46 @@ class Scanner:
         _lib.check(self.lib.svb_scan_batch_v1_host(self._h, src, n, h, w, hp(out["digits"]), hp(out["conf"]),
                                                    hp(out["corners"]), hp(out["found"])), "svb_scan_batch_v1_host")
         return out
+
+    # -- frame ingest (cv2.imread's decode step on the GPU) -------------------------------------------------------------
+    @staticmethod
+    def pack_jpegs(files) -> tuple:
+        """list of bytes-like JPEG files -> (blob uint8 ndarray, offsets int64 ndarray of len n + 1)"""
+        offs = np.zeros(len(files) + 1, np.int64)
+        for i, f in enumerate(files):
+            offs[i + 1] = offs[i] + len(f)
+        blob = np.empty(int(offs[-1]) + 64, np.uint8)
+        for i, f in enumerate(files):
+            blob[offs[i]:offs[i + 1]] = np.frombuffer(f, np.uint8)
+        blob[offs[-1]:] = 0
+        return blob, offs
+
+    def jpeg_decode(self, blob, offsets, h: int, w: int, want_status: bool = False):
+        """blob / offsets: host arrays from pack_jpegs (or pinned torch CPU tensors) -> BGR frames (n,h,w,3) uint8 CUDA."""
+        torch = _torch()
+        n = len(offsets) - 1
+        out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=self._dev())
+        status = torch.empty((n,), dtype=torch.uint8, device=self._dev()) if want_status else None
+        _lib.check(self.lib.svb_jpeg_decode_host(self._h, _hptr(blob), _hptr(offsets), n, h, w, _ptr(out), _ptr(status), self._stream()),
+                   "svb_jpeg_decode_host")
+        return (out, status) if want_status else out
+
+    def scan_batch_jpeg_host(self, blob, offsets, h: int, w: int, out: dict | None = None) -> dict:
+        """scan_batch_host for compressed frames: H2D of the JPEG bytes + decode + path + D2H, synchronous."""
+        n = len(offsets) - 1
+        if out is None:
+            out = dict(digits=np.empty((n, 81), np.uint8), conf=np.empty((n, 81), np.float32),
+                       corners=np.empty((n, 4, 2), np.int32), found=np.empty((n,), np.uint8))
+        _lib.check(self.lib.svb_scan_batch_v1_jpeg_host(self._h, _hptr(blob), _hptr(offsets), n, h, w, _hptr(out["digits"]),
+                                                        _hptr(out["conf"]), _hptr(out["corners"]), _hptr(out["found"])),
+                   "svb_scan_batch_v1_jpeg_host")
+        return out
+
+
+def _hptr(a):
+    """host pointer of a numpy array or a CPU torch tensor"""
+    if hasattr(a, "data_ptr"):
+        assert a.device.type == "cpu" and a.is_contiguous()
+        return C.c_void_p(a.data_ptr())
+    a = np.ascontiguousarray(a)
+    return a.ctypes.data_as(C.c_void_p)

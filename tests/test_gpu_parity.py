@@ -421,7 +421,7 @@ def test_scan_batch_host_multi_chunk_ragged_tail(scanner):
 
 
 def test_scan_batch_overlapped_equals_in_order(scanner):
-    """svb_scan_batch_v1 cuts batches of >= 64 frames into four parts on two internal streams (SVB_OPT_OVERLAP): every
+    """with SVB_OPT_OVERLAP = 4 svb_scan_batch_v1 cuts batches of >= 64 frames into four parts on two internal streams: every
     output must be bit-identical to the in-order single-stream form, including a ragged part and a no-grid frame."""
     import torch
     from svb200 import frames as F
@@ -430,14 +430,14 @@ def test_scan_batch_overlapped_equals_in_order(scanner):
     big = F.noisy_batch_device(torch.from_numpy(clean).cuda(), 131, seed=4)
     big[77] = 0
     try:
-        scanner.set_option("overlap", 1)
+        scanner.set_option("overlap", 4)
         a = scanner.scan_batch(big, want_logits=True)
         torch.cuda.synchronize()
         scanner.set_option("overlap", 0)
         b = scanner.scan_batch(big, want_logits=True)
         torch.cuda.synchronize()
     finally:
-        scanner.set_option("overlap", 1)
+        scanner.set_option("overlap", 0)
     for k in ("digits", "conf", "corners", "found", "logits"):
         assert torch.equal(a[k], b[k]), k
     assert int(a["found"][77]) == 0 and int((a["found"] == 1).sum()) == 130
