@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(NT) huff_idct_kernel(const uint8_t *__restrict
                                                        const long long *__restrict__ seg_start, uint8_t *__restrict__ planes,
                                                        long long plane_bytes) {
     __shared__ Image im;
-    __shared__ int16_t scratch[64 * NT];
+    __shared__ __align__(16) int16_t scratch[64 * NT];
     const int img = blockIdx.y, tid = threadIdx.x;
     {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&images[img]);
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(NT) huff_idct_kernel(const uint8_t *__restrict
     pl[1] = pl[0] + (long long)pw[0] * (im.mcuy * 8 * im.vs);
     pl[2] = pl[1] + (long long)pw[1] * (im.mcuy * 8);
     const long long b = seg_start[im.seg_base + seg], e = seg_start[im.seg_base + seg + 1];
-    jpeg::decode_segment<NT>(im, blob + b, blob + (e > b ? e : b), first, n, pl, pw, scratch + tid);
+    jpeg::decode_segment<1>(im, blob + b, blob + (e > b ? e : b), first, n, pl, pw, scratch + 64 * tid, tid & 7);
 }
 
 // two horizontally adjacent pixels (one chroma column in 4:2:0) per thread

@@ -22,6 +22,14 @@
 #define SVB_JHD __host__ __device__ __forceinline__
 #else
 #define SVB_JHD inline
+struct alignas(16) uint4 {
+    uint32_t x, y, z, w;
+};
+struct alignas(8) uint2 {
+    uint32_t x, y;
+};
+inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return uint4{a, b, c, d}; }
+inline uint2 make_uint2(uint32_t a, uint32_t b) { return uint2{a, b}; }
 #endif
 
 namespace svb {
@@ -73,7 +81,7 @@ struct BitReader {
         cnt = 0;
         hit_marker = false;
     }
-    SVB_JHD void refill() {  // top up to at least 32 valid bits (> 16 + 11: one code and one value without refilling)
+    SVB_JHD void refill_bytes() {  // byte by byte: stuffed zeros, markers, the end of the segment
         while (cnt <= 56) {
             uint32_t c = 0;
             if (!hit_marker && p < end) {
@@ -95,6 +103,21 @@ struct BitReader {
             buf |= (uint64_t)c << (56 - cnt);
             cnt += 8;
         }
+    }
+    // at least 32 valid bits afterwards: one Huffman code (<= 16 bits) and one value (<= 16 bits) without another refill.
+    // Fast path: four bytes at once when none of them is 0xFF (an 0xFF is a stuffed pair or a marker: 1 byte in 256).
+    SVB_JHD void refill() {
+        if (cnt >= 32) return;
+        if (!hit_marker && p + 4 <= end) {
+            const uint32_t w = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+            if ((((~w) - 0x01010101u) & w & 0x80808080u) == 0) {  // no byte of w is 0xFF
+                buf |= (uint64_t)w << (32 - cnt);
+                cnt += 32;
+                p += 4;
+                return;
+            }
+        }
+        refill_bytes();
     }
     SVB_JHD uint32_t peek(int n) const { return (uint32_t)(buf >> (64 - n)); }
     SVB_JHD void skip(int n) {
@@ -131,8 +154,14 @@ SVB_JHD int decode_symbol(BitReader &br, const HuffTable &t) {
 
 // one 8x8 block: coefficients in natural order, NOT yet dequantised; block must be zeroed by the caller.  Returns the
 // index of the last non-zero coefficient in zigzag order (0 if only DC).
-template <int BS>
-SVB_JHD int decode_block(BitReader &br, const HuffTable &dc, const HuffTable &ac, int &last_dc, int16_t *block) {
+// Where coefficient i (natural order) of a thread's block lives.  SW = 0: plain array (host harness).  SW != 0 (kernel, shared
+// memory): every thread owns 128 contiguous bytes whose 16-byte chunks (= block rows) are permuted by the thread's low bits,
+// so that a quarter-warp's 128-bit accesses to the same row — zeroing, the IDCT's row loads — fall on different banks.
+template <int SW>
+SVB_JHD int coef_at(int i, int key) { return SW ? ((((i >> 3) ^ key) << 3) | (i & 7)) : i; }
+
+template <int SW>
+SVB_JHD int decode_block(BitReader &br, const HuffTable &dc, const HuffTable &ac, int &last_dc, int16_t *block, int key) {
     br.refill();
     int s = decode_symbol(br, dc);
     int diff = 0;
@@ -141,7 +170,7 @@ SVB_JHD int decode_block(BitReader &br, const HuffTable &dc, const HuffTable &ac
         diff = extend(br.get(s), s);
     }
     last_dc += diff;
-    block[0] = (int16_t)last_dc;  // element i of the block lives at block[i * BS]
+    block[coef_at<SW>(0, key)] = (int16_t)last_dc;
     int last = 0;
     for (int k = 1; k < 64;) {
         br.refill();
@@ -152,7 +181,7 @@ SVB_JHD int decode_block(BitReader &br, const HuffTable &dc, const HuffTable &ac
             k += r;
             const int v = extend(br.get(s), s);
             if (k < 64) {
-                block[zigzag_natural(k) * BS] = (int16_t)v;
+                block[coef_at<SW>(zigzag_natural(k), key)] = (int16_t)v;
                 last = k;
             }
             ++k;
@@ -226,20 +255,31 @@ SVB_JHD void idct_1d(const int *in, int *o) {
     o[4] = tmp13 - t0;
 }
 
-// coef: natural order (element i at coef[i * BS]), not dequantised; q: natural order; out: 8 rows of 8 samples, `stride` bytes apart
-template <int BS>
-SVB_JHD void idct_islow(const int16_t *coef, const uint16_t *q, uint8_t *out, int stride) {
+// coef: natural order through coef_at<SW>, not dequantised; q: natural order; out: 8 rows of 8 samples, `stride` bytes apart
+// (8-byte aligned: written as one 64-bit store per row)
+template <int SW>
+SVB_JHD void idct_islow(const int16_t *coef, int key, const uint16_t *q, uint8_t *out, int stride) {
     int ws[64];
+    int16_t cf[64];
+    for (int r = 0; r < 8; ++r) {  // one 16-byte row per load
+        const uint4 v = *reinterpret_cast<const uint4 *>(coef + coef_at<SW>(r * 8, key));
+        *reinterpret_cast<uint4 *>(&cf[r * 8]) = v;
+    }
     for (int c = 0; c < 8; ++c) {  // pass 1: columns, results scaled up by 2^PASS1_BITS
         int in[8], o[8];
-        for (int r = 0; r < 8; ++r) in[r] = (int)coef[(r * 8 + c) * BS] * (int)q[r * 8 + c];
+        for (int r = 0; r < 8; ++r) in[r] = (int)cf[r * 8 + c] * (int)q[r * 8 + c];
         idct_1d(in, o);
         for (int r = 0; r < 8; ++r) ws[r * 8 + c] = (o[r] + (1 << 10)) >> 11;  // DESCALE(x, CONST_BITS - PASS1_BITS)
     }
     for (int r = 0; r < 8; ++r) {  // pass 2: rows
         int o[8];
         idct_1d(&ws[r * 8], o);
-        for (int c = 0; c < 8; ++c) out[r * stride + c] = range_limit((o[c] + (1 << 17)) >> 18);  // CONST_BITS + PASS1_BITS + 3
+        uint32_t lo = 0, hi = 0;
+        for (int c = 0; c < 4; ++c) {
+            lo |= (uint32_t)range_limit((o[c] + (1 << 17)) >> 18) << (8 * c);  // DESCALE(x, CONST_BITS + PASS1_BITS + 3)
+            hi |= (uint32_t)range_limit((o[c + 4] + (1 << 17)) >> 18) << (8 * c);
+        }
+        *reinterpret_cast<uint2 *>(out + (long long)r * stride) = make_uint2(lo, hi);
     }
 }
 
@@ -281,10 +321,10 @@ SVB_JHD void h2v2_fancy_pair(const uint8_t *plane, int pw, int cw, int chh, int 
 
 // ---- one restart interval: Huffman decode + IDCT of its MCUs into the component planes ----------------------------------------
 // planes[c]: component c's plane, padded to whole MCUs (pw[c] bytes per row).  seg: the segment's bytes [b, e).
-// block: 64 int16 of scratch, element i at block[i * BS] (shared memory, thread-minor, in the kernel).
-template <int BS>
+// block: this thread's 64 int16 of scratch (16-byte aligned), addressed through coef_at<SW>(i, key).
+template <int SW>
 SVB_JHD void decode_segment(const Image &im, const uint8_t *b, const uint8_t *e, int first_mcu, int n_mcu, uint8_t *const *planes,
-                            const int *pw, int16_t *block) {
+                            const int *pw, int16_t *block, int key) {
     BitReader br;
     br.init(b, e);
     int last_dc[3] = {0, 0, 0};
@@ -294,10 +334,10 @@ SVB_JHD void decode_segment(const Image &im, const uint8_t *b, const uint8_t *e,
             const int hs = c == 0 ? im.hs : 1, vs = c == 0 ? im.vs : 1;
             for (int by = 0; by < vs; ++by)
                 for (int bx = 0; bx < hs; ++bx) {
-                    for (int i = 0; i < 64; ++i) block[i * BS] = 0;
-                    decode_block<BS>(br, im.dc[im.dc_tab[c]], im.ac[im.ac_tab[c]], last_dc[c], block);
+                    for (int i = 0; i < 8; ++i) reinterpret_cast<uint4 *>(block)[i] = make_uint4(0, 0, 0, 0);
+                    decode_block<SW>(br, im.dc[im.dc_tab[c]], im.ac[im.ac_tab[c]], last_dc[c], block, key);
                     uint8_t *out = planes[c] + (long long)((my * vs + by) * 8) * pw[c] + (mx * hs + bx) * 8;
-                    idct_islow<BS>(block, im.quant[im.q_tab[c]], out, pw[c]);
+                    idct_islow<SW>(block, key, im.quant[im.q_tab[c]], out, pw[c]);
                 }
         }
     }

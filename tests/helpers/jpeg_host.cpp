@@ -37,10 +37,12 @@ int svbh_jpeg_decode(const uint8_t *data, long long len, uint8_t *bgr) {
         planes[c] = store[c].data();
     }
     const int total = im.mcux * im.mcuy, ri = im.restart_interval ? im.restart_interval : total;
-    int16_t block[64];
+    alignas(16) int16_t block[64];
     for (int s = 0; s < im.nseg; ++s) {
         const int first = s * ri, n = first + ri <= total ? ri : total - first;
-        decode_segment<1>(im, data + im.data_off + seg[s], data + im.data_off + seg[s + 1], first, n, planes, pw, block);
+        decode_segment<0>(im, data + im.data_off + seg[s], data + im.data_off + seg[s + 1], first, n, planes, pw, block, 0);
+        // the kernel's shared-memory addressing (rows permuted by a per-thread key) must give the same pixels
+        if (s == 0 && im.nseg > 1) decode_segment<1>(im, data + im.data_off + seg[s], data + im.data_off + seg[s + 1], first, n, planes, pw, block, 5);
     }
     const int cw = (im.width + im.hs - 1) / im.hs, chh = (im.height + im.vs - 1) / im.vs;  // real chroma samples
     for (int y = 0; y < im.height; ++y)
