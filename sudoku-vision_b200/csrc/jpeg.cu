@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) rst_scan_kernel(const uint8_t *__restrict
     if (tid == 0 && running != want && status) status[blockIdx.x] |= 1;
 }
 
-// planes: per image a block of plane_bytes: Y (pw0 x ph0), then Cb, Cr (pw1 x ph1 each)
+// planes: per image a block of plane_bytes: Y (pw0 x ph0), then Cb, Cr (pw1 x ph1 each), block-linear (jpeg::plane_index)
 __global__ void __launch_bounds__(NT) huff_idct_kernel(const uint8_t *__restrict__ blob, const Image *__restrict__ images,
                                                        const long long *__restrict__ seg_start, uint8_t *__restrict__ planes,
                                                        long long plane_bytes) {
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) color_kernel(const Image *__restrict__ im
     const uint8_t *p0 = planes + (long long)img * plane_bytes;
     const uint8_t *p1 = p0 + (long long)pw0 * (im.mcuy * 8 * im.vs), *p2 = p1 + (long long)pw1 * (im.mcuy * 8);
     uint8_t *o = bgr + (((long long)img * h + y) * w + x) * 3;
-    const int y0 = p0[(long long)y * pw0 + x], y1 = (x + 1 < w) ? p0[(long long)y * pw0 + x + 1] : 0;
+    const int y0 = p0[jpeg::plane_index(pw0, x, y)], y1 = (x + 1 < w) ? p0[jpeg::plane_index(pw0, x + 1, y)] : 0;
     uint8_t px[6];
     if (im.ncomp == 1) {
         px[0] = px[1] = px[2] = (uint8_t)y0;
@@ -124,8 +124,8 @@ __global__ void __launch_bounds__(256) color_kernel(const Image *__restrict__ im
         jpeg::ycc_to_bgr(y0, bl, rl, px);
         jpeg::ycc_to_bgr(y1, br, rr, px + 3);
     } else {
-        jpeg::ycc_to_bgr(y0, p1[(long long)y * pw1 + x], p2[(long long)y * pw1 + x], px);
-        if (x + 1 < w) jpeg::ycc_to_bgr(y1, p1[(long long)y * pw1 + x + 1], p2[(long long)y * pw1 + x + 1], px + 3);
+        jpeg::ycc_to_bgr(y0, p1[jpeg::plane_index(pw1, x, y)], p2[jpeg::plane_index(pw1, x, y)], px);
+        if (x + 1 < w) jpeg::ycc_to_bgr(y1, p1[jpeg::plane_index(pw1, x + 1, y)], p2[jpeg::plane_index(pw1, x + 1, y)], px + 3);
     }
     o[0] = px[0];
     o[1] = px[1];

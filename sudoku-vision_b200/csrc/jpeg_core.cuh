@@ -255,10 +255,10 @@ SVB_JHD void idct_1d(const int *in, int *o) {
     o[4] = tmp13 - t0;
 }
 
-// coef: natural order through coef_at<SW>, not dequantised; q: natural order; out: 8 rows of 8 samples, `stride` bytes apart
-// (8-byte aligned: written as one 64-bit store per row)
+// coef: natural order through coef_at<SW>, not dequantised; q: natural order; out: the block's 64 contiguous samples
+// (16-byte aligned: written as four 128-bit stores)
 template <int SW>
-SVB_JHD void idct_islow(const int16_t *coef, int key, const uint16_t *q, uint8_t *out, int stride) {
+SVB_JHD void idct_islow(const int16_t *coef, int key, const uint16_t *q, uint8_t *out) {
     int ws[64];
     int16_t cf[64];
     for (int r = 0; r < 8; ++r) {  // one 16-byte row per load
@@ -271,15 +271,20 @@ SVB_JHD void idct_islow(const int16_t *coef, int key, const uint16_t *q, uint8_t
         idct_1d(in, o);
         for (int r = 0; r < 8; ++r) ws[r * 8 + c] = (o[r] + (1 << 10)) >> 11;  // DESCALE(x, CONST_BITS - PASS1_BITS)
     }
-    for (int r = 0; r < 8; ++r) {  // pass 2: rows
-        int o[8];
-        idct_1d(&ws[r * 8], o);
-        uint32_t lo = 0, hi = 0;
-        for (int c = 0; c < 4; ++c) {
-            lo |= (uint32_t)range_limit((o[c] + (1 << 17)) >> 18) << (8 * c);  // DESCALE(x, CONST_BITS + PASS1_BITS + 3)
-            hi |= (uint32_t)range_limit((o[c + 4] + (1 << 17)) >> 18) << (8 * c);
+    for (int rp = 0; rp < 4; ++rp) {  // pass 2: rows, two per 16-byte store
+        uint32_t w4[4];
+        for (int k = 0; k < 2; ++k) {
+            int o[8];
+            idct_1d(&ws[(2 * rp + k) * 8], o);
+            uint32_t lo = 0, hi = 0;
+            for (int c = 0; c < 4; ++c) {
+                lo |= (uint32_t)range_limit((o[c] + (1 << 17)) >> 18) << (8 * c);  // DESCALE(x, CONST_BITS + PASS1_BITS + 3)
+                hi |= (uint32_t)range_limit((o[c + 4] + (1 << 17)) >> 18) << (8 * c);
+            }
+            w4[2 * k] = lo;
+            w4[2 * k + 1] = hi;
         }
-        *reinterpret_cast<uint2 *>(out + (long long)r * stride) = make_uint2(lo, hi);
+        reinterpret_cast<uint4 *>(out)[rp] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
     }
 }
 
@@ -295,32 +300,36 @@ SVB_JHD void ycc_to_bgr(int y, int cb, int cr, uint8_t *bgr) {
     bgr[2] = clamp255(r);
 }
 
+// ---- component planes are BLOCK-LINEAR: the 64 samples of an 8x8 block are contiguous (row-major inside the block), blocks in
+// raster order, pw = plane width in samples (a multiple of 8).  A decoding thread then writes whole 32-byte sectors (a
+// row-major plane would take 8 bytes of 8 different sectors per block: partial-sector writes, read-modify-write in HBM) ------
+SVB_JHD long long plane_index(int pw, int x, int y) { return ((long long)(y >> 3) * (pw >> 3) + (x >> 3)) * 64 + ((y & 7) << 3) + (x & 7); }
+
 // ---- jdsample.c h2v2_fancy_upsample: the two output samples of chroma column cx in output row y ------------------------------
-// plane: the component's plane (stride pw bytes), cw x chh real samples; edge rows replicate (jdmainct.c context rows)
+// plane: the component's plane, cw x chh real samples; edge rows replicate (jdmainct.c context rows)
 SVB_JHD void h2v2_fancy_pair(const uint8_t *plane, int pw, int cw, int chh, int y, int cx, int &left, int &right) {
     const int cy = y >> 1;
     if (cw <= 2) {  // jdsample.c jinit_upsampler: fancy upsampling needs downsampled_width > 2, else plain replication
-        left = right = plane[(long long)cy * pw + cx];
+        left = right = plane[plane_index(pw, cx, cy)];
         return;
     }
     int ny = (y & 1) ? cy + 1 : cy - 1;  // the nearer neighbour row
     ny = ny < 0 ? 0 : (ny >= chh ? chh - 1 : ny);
-    const uint8_t *r0 = plane + (long long)cy * pw, *r1 = plane + (long long)ny * pw;
-    const int cur = r0[cx] * 3 + r1[cx];
+    const int cur = plane[plane_index(pw, cx, cy)] * 3 + plane[plane_index(pw, cx, ny)];
     if (cx == 0) {
         left = (cur * 4 + 8) >> 4;
     } else {
-        left = (cur * 3 + (r0[cx - 1] * 3 + r1[cx - 1]) + 8) >> 4;
+        left = (cur * 3 + (plane[plane_index(pw, cx - 1, cy)] * 3 + plane[plane_index(pw, cx - 1, ny)]) + 8) >> 4;
     }
     if (cx == cw - 1) {
         right = (cur * 4 + 7) >> 4;
     } else {
-        right = (cur * 3 + (r0[cx + 1] * 3 + r1[cx + 1]) + 7) >> 4;
+        right = (cur * 3 + (plane[plane_index(pw, cx + 1, cy)] * 3 + plane[plane_index(pw, cx + 1, ny)]) + 7) >> 4;
     }
 }
 
 // ---- one restart interval: Huffman decode + IDCT of its MCUs into the component planes ----------------------------------------
-// planes[c]: component c's plane, padded to whole MCUs (pw[c] bytes per row).  seg: the segment's bytes [b, e).
+// planes[c]: component c's block-linear plane, padded to whole MCUs (pw[c] samples per row).  seg: the segment's bytes [b, e).
 // block: this thread's 64 int16 of scratch (16-byte aligned), addressed through coef_at<SW>(i, key).
 template <int SW>
 SVB_JHD void decode_segment(const Image &im, const uint8_t *b, const uint8_t *e, int first_mcu, int n_mcu, uint8_t *const *planes,
@@ -336,8 +345,8 @@ SVB_JHD void decode_segment(const Image &im, const uint8_t *b, const uint8_t *e,
                 for (int bx = 0; bx < hs; ++bx) {
                     for (int i = 0; i < 8; ++i) reinterpret_cast<uint4 *>(block)[i] = make_uint4(0, 0, 0, 0);
                     decode_block<SW>(br, im.dc[im.dc_tab[c]], im.ac[im.ac_tab[c]], last_dc[c], block, key);
-                    uint8_t *out = planes[c] + (long long)((my * vs + by) * 8) * pw[c] + (mx * hs + bx) * 8;
-                    idct_islow<SW>(block, key, im.quant[im.q_tab[c]], out, pw[c]);
+                    uint8_t *out = planes[c] + plane_index(pw[c], (mx * hs + bx) * 8, (my * vs + by) * 8);
+                    idct_islow<SW>(block, key, im.quant[im.q_tab[c]], out);
                 }
         }
     }

@@ -33,8 +33,8 @@ int svbh_jpeg_decode(const uint8_t *data, long long len, uint8_t *bgr) {
     for (int c = 0; c < im.ncomp; ++c) {
         pw[c] = im.mcux * 8 * (c == 0 ? im.hs : 1);
         ph[c] = im.mcuy * 8 * (c == 0 ? im.vs : 1);
-        store[c].assign((size_t)pw[c] * ph[c], 0);
-        planes[c] = store[c].data();
+        store[c].assign((size_t)pw[c] * ph[c] + 16, 0);
+        planes[c] = store[c].data() + ((16 - ((uintptr_t)store[c].data() & 15)) & 15);  // 16-byte aligned, as the arena is
     }
     const int total = im.mcux * im.mcuy, ri = im.restart_interval ? im.restart_interval : total;
     alignas(16) int16_t block[64];
@@ -48,7 +48,7 @@ int svbh_jpeg_decode(const uint8_t *data, long long len, uint8_t *bgr) {
     for (int y = 0; y < im.height; ++y)
         for (int x = 0; x < im.width; ++x) {
             uint8_t *o = bgr + ((size_t)y * im.width + x) * 3;
-            const int Y = planes[0][(size_t)y * pw[0] + x];
+            const int Y = planes[0][plane_index(pw[0], x, y)];
             if (im.ncomp == 1) {
                 o[0] = o[1] = o[2] = (uint8_t)Y;
                 continue;
@@ -61,8 +61,8 @@ int svbh_jpeg_decode(const uint8_t *data, long long len, uint8_t *bgr) {
                 h2v2_fancy_pair(planes[2], pw[2], cw, chh, y, x >> 1, l, r);
                 cr = (x & 1) ? r : l;
             } else {
-                cb = planes[1][(size_t)y * pw[1] + x];
-                cr = planes[2][(size_t)y * pw[2] + x];
+                cb = planes[1][plane_index(pw[1], x, y)];
+                cr = planes[2][plane_index(pw[2], x, y)];
             }
             ycc_to_bgr(Y, cb, cr, o);
         }
