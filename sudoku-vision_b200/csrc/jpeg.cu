@@ -100,41 +100,87 @@ __global__ void __launch_bounds__(NT) huff_idct_kernel(const uint8_t *__restrict
     jpeg::decode_segment<1>(im, blob + b, blob + (e > b ? e : b), first, n, pl, pw, scratch + 64 * tid, tid & 7);
 }
 
-// two horizontally adjacent pixels (one chroma column in 4:2:0) per thread
+// one pixel, any geometry (image edges, tiny images): the reference form of the conversion
+__device__ __forceinline__ void color_pixel(const Image &im, const uint8_t *p0, const uint8_t *p1, const uint8_t *p2, int pw0, int pw1,
+                                            int h, int w, int x, int y, uint8_t *o) {
+    const int Y = p0[jpeg::plane_index(pw0, x, y)];
+    if (im.ncomp == 1) {
+        o[0] = o[1] = o[2] = (uint8_t)Y;
+    } else if (im.hs == 2) {
+        int l, r, cb, cr;
+        jpeg::h2v2_fancy_pair(p1, pw1, (w + 1) / 2, (h + 1) / 2, y, x >> 1, l, r);
+        cb = (x & 1) ? r : l;
+        jpeg::h2v2_fancy_pair(p2, pw1, (w + 1) / 2, (h + 1) / 2, y, x >> 1, l, r);
+        cr = (x & 1) ? r : l;
+        jpeg::ycc_to_bgr(Y, cb, cr, o);
+    } else {
+        jpeg::ycc_to_bgr(Y, p1[jpeg::plane_index(pw1, x, y)], p2[jpeg::plane_index(pw1, x, y)], o);
+    }
+}
+
+// eight horizontally adjacent pixels per thread = one row of a luma block: one 64-bit luma load, the four chroma columns
+// under it as 32-bit loads (+ one neighbour byte each side for the triangle filter) from two chroma rows, three 64-bit
+// stores.  Groups that touch the right edge and images whose chroma plane is too narrow for the fancy filter take color_pixel.
 __global__ void __launch_bounds__(256) color_kernel(const Image *__restrict__ images, const uint8_t *__restrict__ planes,
                                                     long long plane_bytes, int h, int w, uint8_t *__restrict__ bgr) {
-    const int img = blockIdx.z, y = blockIdx.y, xp = blockIdx.x * blockDim.x + threadIdx.x;
-    const int x = 2 * xp;
+    const int img = blockIdx.z, y = blockIdx.y, xg = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x = 8 * xg;
     if (x >= w) return;
     const Image &im = images[img];
     const int pw0 = im.mcux * 8 * im.hs, pw1 = im.mcux * 8;
     const uint8_t *p0 = planes + (long long)img * plane_bytes;
     const uint8_t *p1 = p0 + (long long)pw0 * (im.mcuy * 8 * im.vs), *p2 = p1 + (long long)pw1 * (im.mcuy * 8);
     uint8_t *o = bgr + (((long long)img * h + y) * w + x) * 3;
-    const int y0 = p0[jpeg::plane_index(pw0, x, y)], y1 = (x + 1 < w) ? p0[jpeg::plane_index(pw0, x + 1, y)] : 0;
-    uint8_t px[6];
-    if (im.ncomp == 1) {
-        px[0] = px[1] = px[2] = (uint8_t)y0;
-        px[3] = px[4] = px[5] = (uint8_t)y1;
-    } else if (im.hs == 2) {
-        const int cw = (w + 1) / 2, chh = (h + 1) / 2;
-        int bl, br, rl, rr;
-        jpeg::h2v2_fancy_pair(p1, pw1, cw, chh, y, xp, bl, br);
-        jpeg::h2v2_fancy_pair(p2, pw1, cw, chh, y, xp, rl, rr);
-        jpeg::ycc_to_bgr(y0, bl, rl, px);
-        jpeg::ycc_to_bgr(y1, br, rr, px + 3);
+    const int cw = (w + 1) / 2, chh = (h + 1) / 2;
+    const bool fast = (x + 8 <= w) && (w % 8 == 0) && im.ncomp == 3 && (im.hs == 1 || cw > 2) && ((reinterpret_cast<uintptr_t>(bgr) & 7) == 0);
+    if (!fast) {
+        for (int k = 0; k < 8 && x + k < w; ++k) color_pixel(im, p0, p1, p2, pw0, pw1, h, w, x + k, y, o + 3 * k);
+        return;
+    }
+    const uint2 yv = *reinterpret_cast<const uint2 *>(p0 + jpeg::plane_index(pw0, x, y));
+    int cb[8], cr[8];
+    if (im.hs == 2) {
+        const int cx = x >> 1, cy = y >> 1;
+        int ny = (y & 1) ? cy + 1 : cy - 1;
+        ny = ny < 0 ? 0 : (ny >= chh ? chh - 1 : ny);
+        const int xl = cx > 0 ? cx - 1 : 0, xr = cx + 4 < cw ? cx + 4 : cw - 1;  // clamped: the edge samples use the *4 form below
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+            const uint8_t *p = pl ? p2 : p1;
+            const uint32_t a = *reinterpret_cast<const uint32_t *>(p + jpeg::plane_index(pw1, cx, cy));
+            const uint32_t bq = *reinterpret_cast<const uint32_t *>(p + jpeg::plane_index(pw1, cx, ny));
+            int s[6];  // column sums 3 * near row + far row for chroma columns cx-1 .. cx+4
+            s[0] = p[jpeg::plane_index(pw1, xl, cy)] * 3 + p[jpeg::plane_index(pw1, xl, ny)];
+            s[5] = p[jpeg::plane_index(pw1, xr, cy)] * 3 + p[jpeg::plane_index(pw1, xr, ny)];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s[1 + k] = (int)((a >> (8 * k)) & 255u) * 3 + (int)((bq >> (8 * k)) & 255u);
+            int *c = pl ? cr : cb;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int col = cx + k;
+                c[2 * k] = col == 0 ? (s[1 + k] * 4 + 8) >> 4 : (s[1 + k] * 3 + s[k] + 8) >> 4;
+                c[2 * k + 1] = col == cw - 1 ? (s[1 + k] * 4 + 7) >> 4 : (s[1 + k] * 3 + s[2 + k] + 7) >> 4;
+            }
+        }
     } else {
-        jpeg::ycc_to_bgr(y0, p1[jpeg::plane_index(pw1, x, y)], p2[jpeg::plane_index(pw1, x, y)], px);
-        if (x + 1 < w) jpeg::ycc_to_bgr(y1, p1[jpeg::plane_index(pw1, x + 1, y)], p2[jpeg::plane_index(pw1, x + 1, y)], px + 3);
+        const uint2 bv = *reinterpret_cast<const uint2 *>(p1 + jpeg::plane_index(pw1, x, y));
+        const uint2 rv = *reinterpret_cast<const uint2 *>(p2 + jpeg::plane_index(pw1, x, y));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            cb[k] = (bv.x >> (8 * k)) & 255u;
+            cb[4 + k] = (bv.y >> (8 * k)) & 255u;
+            cr[k] = (rv.x >> (8 * k)) & 255u;
+            cr[4 + k] = (rv.y >> (8 * k)) & 255u;
+        }
     }
-    o[0] = px[0];
-    o[1] = px[1];
-    o[2] = px[2];
-    if (x + 1 < w) {
-        o[3] = px[3];
-        o[4] = px[4];
-        o[5] = px[5];
-    }
+    alignas(8) uint8_t px[24];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) jpeg::ycc_to_bgr((int)(((k < 4 ? yv.x : yv.y) >> (8 * (k & 3))) & 255u), cb[k], cr[k], px + 3 * k);
+    uint2 *o8 = reinterpret_cast<uint2 *>(o);
+    const uint2 *s8 = reinterpret_cast<const uint2 *>(px);
+    o8[0] = s8[0];
+    o8[1] = s8[1];
+    o8[2] = s8[2];
 }
 
 }  // namespace k9
@@ -224,7 +270,7 @@ int jpeg_decode_batch(svb_ctx *ctx, const uint8_t *host_blob, const long long *h
     huff_idct_kernel<<<dim3((max_seg + NT - 1) / NT, n), NT, 0, st>>>(d_blob, d_images, d_seg, (uint8_t *)(ab + o_planes), plane_bytes);
     rc = check_launch(ctx, "k9::huff_idct_kernel");
     if (rc) return rc;
-    color_kernel<<<dim3(((w + 1) / 2 + 255) / 256, h, n), 256, 0, st>>>(d_images, (const uint8_t *)(ab + o_planes), plane_bytes, h, w, bgr);
+    color_kernel<<<dim3(((w + 7) / 8 + 255) / 256, h, n), 256, 0, st>>>(d_images, (const uint8_t *)(ab + o_planes), plane_bytes, h, w, bgr);
     return check_launch(ctx, "k9::color_kernel");
 }
 
