@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) rst_scan_kernel(const uint8_t *__restrict
 }
 
 // planes: per image a block of plane_bytes: Y (pw0 x ph0), then Cb, Cr (pw1 x ph1 each), block-linear (jpeg::plane_index)
-__global__ void __launch_bounds__(NT) huff_idct_kernel(const uint8_t *__restrict__ blob, const Image *__restrict__ images,
+__global__ void __launch_bounds__(NT, 5) huff_idct_kernel(const uint8_t *__restrict__ blob, const Image *__restrict__ images,
                                                        const long long *__restrict__ seg_start, uint8_t *__restrict__ planes,
                                                        long long plane_bytes) {
     __shared__ Image im;

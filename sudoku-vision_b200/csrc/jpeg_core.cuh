@@ -56,6 +56,7 @@ struct Image {                      // one parsed file (host fills it, the kerne
     int seg_base;                   // index of this image's first segment in the batch-wide segment table
     int dc_tab[3], ac_tab[3], q_tab[3];
     uint16_t quant[4][64];          // natural (row-major) order
+    uint8_t zz[64];                 // jutils.c jpeg_natural_order: zigzag position -> natural index
     HuffTable dc[2], ac[2];
 };
 
@@ -80,6 +81,7 @@ struct BitReader {
         buf = 0;
         cnt = 0;
         hit_marker = false;
+        prime();
     }
     SVB_JHD void refill_bytes() {  // byte by byte: stuffed zeros, markers, the end of the segment
         while (cnt <= 56) {
@@ -106,6 +108,39 @@ struct BitReader {
     }
     // at least 32 valid bits afterwards: one Huffman code (<= 16 bits) and one value (<= 16 bits) without another refill.
     // Fast path: four bytes at once when none of them is 0xFF (an 0xFF is a stuffed pair or a marker: 1 byte in 256).
+#if defined(__CUDA_ARCH__)
+    // The next four bytes are fetched one refill AHEAD (aligned 32-bit words + a funnel shift), so the load's latency is
+    // spent decoding the bits already in the buffer, not waiting.  Words may be read up to 7 bytes past `end`: they are
+    // inside the blob (the next segment, or the slack every blob carries) and are never consumed past `end`.
+    const uint32_t *wp;  // aligned word holding byte p + 4 (the next one to fetch)
+    uint32_t w_lo, w_hi; // the aligned words holding bytes p .. p + 7
+    SVB_JHD void prime() {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3;
+        wp = reinterpret_cast<const uint32_t *>(a);
+        w_lo = __ldg(wp);
+        w_hi = __ldg(wp + 1);
+        wp += 2;
+    }
+    SVB_JHD void refill() {
+        if (cnt >= 32) return;
+        if (!hit_marker && p + 4 <= end) {
+            const uint32_t sh = ((uint32_t)reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
+            const uint32_t le = __funnelshift_r(w_lo, w_hi, sh);  // bytes p .. p+3, little-endian
+            const uint32_t w = __byte_perm(le, 0, 0x0123);        // big-endian: first byte on top
+            if ((((~w) - 0x01010101u) & w & 0x80808080u) == 0) {  // no byte of w is 0xFF
+                buf |= (uint64_t)w << (32 - cnt);
+                cnt += 32;
+                p += 4;
+                w_lo = w_hi;
+                w_hi = __ldg(wp++);  // consumed by the refill after next
+                return;
+            }
+        }
+        refill_bytes();
+        prime();
+    }
+#else
+    SVB_JHD void prime() {}
     SVB_JHD void refill() {
         if (cnt >= 32) return;
         if (!hit_marker && p + 4 <= end) {
@@ -119,6 +154,7 @@ struct BitReader {
         }
         refill_bytes();
     }
+#endif
     SVB_JHD uint32_t peek(int n) const { return (uint32_t)(buf >> (64 - n)); }
     SVB_JHD void skip(int n) {
         buf <<= n;
@@ -161,7 +197,7 @@ template <int SW>
 SVB_JHD int coef_at(int i, int key) { return SW ? ((((i >> 3) ^ key) << 3) | (i & 7)) : i; }
 
 template <int SW>
-SVB_JHD int decode_block(BitReader &br, const HuffTable &dc, const HuffTable &ac, int &last_dc, int16_t *block, int key) {
+SVB_JHD int decode_block(BitReader &br, const HuffTable &dc, const HuffTable &ac, const uint8_t *zz, int &last_dc, int16_t *block, int key) {
     br.refill();
     int s = decode_symbol(br, dc);
     int diff = 0;
@@ -181,7 +217,7 @@ SVB_JHD int decode_block(BitReader &br, const HuffTable &dc, const HuffTable &ac
             k += r;
             const int v = extend(br.get(s), s);
             if (k < 64) {
-                block[coef_at<SW>(zigzag_natural(k), key)] = (int16_t)v;
+                block[coef_at<SW>(zz[k], key)] = (int16_t)v;
                 last = k;
             }
             ++k;
@@ -344,7 +380,7 @@ SVB_JHD void decode_segment(const Image &im, const uint8_t *b, const uint8_t *e,
             for (int by = 0; by < vs; ++by)
                 for (int bx = 0; bx < hs; ++bx) {
                     for (int i = 0; i < 8; ++i) reinterpret_cast<uint4 *>(block)[i] = make_uint4(0, 0, 0, 0);
-                    decode_block<SW>(br, im.dc[im.dc_tab[c]], im.ac[im.ac_tab[c]], last_dc[c], block, key);
+                    decode_block<SW>(br, im.dc[im.dc_tab[c]], im.ac[im.ac_tab[c]], im.zz, last_dc[c], block, key);
                     uint8_t *out = planes[c] + plane_index(pw[c], (mx * hs + bx) * 8, (my * vs + by) * 8);
                     idct_islow<SW>(block, key, im.quant[im.q_tab[c]], out);
                 }
@@ -484,6 +520,7 @@ inline int parse(const uint8_t *d, long long len, Image *im) {
         }
         i += L;
     }
+    for (int k = 0; k < 64; ++k) im->zz[k] = (uint8_t)zigzag_natural(k);
     im->mcux = (im->width + 8 * im->hs - 1) / (8 * im->hs);
     im->mcuy = (im->height + 8 * im->vs - 1) / (8 * im->vs);
     const int total = im->mcux * im->mcuy;
