@@ -159,8 +159,6 @@ constexpr int LPAD = 16;          // staged pixels left of the first output colu
 constexpr int SW = TW + 2 * LPAD; // 272 staged pixels per row
 constexpr int R = 4;
 constexpr int NSTAGE = 2;
-constexpr int RS = R / NSTAGE;     // rows per TMA stage: a block's four gray rows arrive as two half-blocks, so the staging
-                                  // buffer is 6.5 KB smaller per warp and 14-15 warps fit an SM instead of 12 (shared memory was the limit)
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ float4 lds128(const float4 *p) {  // a shared-memory load the compiler will not forward from registers
@@ -184,9 +182,9 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 template <int CH>
 struct __align__(128) WarpSmem {
     static constexpr int ROWB = SW * CH;                             // bytes per staged row
-    static constexpr int STAGEB = (RS * ROWB + 127) / 128 * 128;     // tensor TMA wants 128-byte aligned destinations
+    static constexpr int STAGEB = (R * ROWB + 127) / 128 * 128;      // tensor TMA wants 128-byte aligned destinations
     float4 rp[12][2][30];                // row-pass ring: [row % 12][column group][lane - 1], thread-private columns
-    uint8_t raw[NSTAGE][STAGEB];         // TMA destination: RS rows of ROWB bytes per stage (stage s = rows 2s, 2s+1 of a block)
+    uint8_t raw[NSTAGE][STAGEB];         // TMA destination: R rows of ROWB bytes per stage
     unsigned long long full[NSTAGE];     // mbarriers
 };
 
@@ -267,11 +265,11 @@ __device__ __forceinline__ void colpass_group(const float4 (&Rw)[14], const uint
 }
 
 template <int CH>
-__global__ void __launch_bounds__(32, 14)
+__global__ void __launch_bounds__(32, 12)
 fused_preprocess_warp_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ mask, int h, int w, int rows_per_seg,
                              const __grid_constant__ CUtensorMap tmap, int use_tmap, uint8_t *__restrict__ bits, int bits_tx,
                              long long bits_frame_bytes) {
-    // one warp per CTA (14 resident per SM): everything the TMA issue needs is CTA-uniform, so it stays on the uniform datapath
+    // one warp per CTA (12 resident per SM): everything the TMA issue needs is CTA-uniform, so it stays on the uniform datapath
     extern __shared__ __align__(128) uint8_t smem_raw[];
     WarpSmem<CH> &sm = *reinterpret_cast<WarpSmem<CH> *>(smem_raw);
     const int lane = threadIdx.x;
@@ -310,28 +308,28 @@ fused_preprocess_warp_kernel(const uint8_t *__restrict__ src, uint8_t *__restric
     const long long pitch = (long long)w * CH;          // bytes per source row
     const uint8_t *frame_lo = frame + (long long)col_lo * CH;
     const int tm_x = xs * CH / 4;                       // first staged column in u32 elements (negative in strip 0: zero-filled)
-    auto issue = [&](int k, int half) {  // lane 0: stage rows 2*half, 2*half+1 of block k's four gray rows (BORDER_REFLECT_101 in y = the source row)
+    auto issue = [&](int k) {  // lane 0: stage block k's four gray rows (BORDER_REFLECT_101 in y = the source row)
         if (k >= nblk) return;
-        const int r0 = 4 * (q_first + k) + 2 + RS * half;
-        if (use_tmap && r0 >= 0 && r0 + RS <= h) {  // interior: one tiled copy of two consecutive rows
-            mbar_expect_tx(&sm.full[half], (uint32_t)(RS * WarpSmem<CH>::ROWB));
-            tma_load_2d(&sm.raw[half][0], &tmap, tm_x, fr * h + r0, &sm.full[half]);
+        const int stage = k & 1, r0 = 4 * (q_first + k) + 2;
+        if (use_tmap && r0 >= 0 && r0 + R <= h) {  // interior block: one tiled copy of four consecutive rows
+            mbar_expect_tx(&sm.full[stage], (uint32_t)(R * WarpSmem<CH>::ROWB));
+            tma_load_2d(&sm.raw[stage][0], &tmap, tm_x, fr * h + r0, &sm.full[stage]);
             return;
         }
-        mbar_expect_tx(&sm.full[half], row_bytes * RS);
-        uint8_t *dst = &sm.raw[half][dst_off];
+        mbar_expect_tx(&sm.full[stage], row_bytes * R);
+        uint8_t *dst = &sm.raw[stage][dst_off];
 #pragma unroll
-        for (int r = 0; r < RS; ++r) {
+        for (int r = 0; r < R; ++r) {
             int v = r0 + r;
             v = (v < 0) ? -v : v;
             v = (v >= h) ? 2 * (h - 1) - v : v;
             v = clampi(v, 0, h - 1);
-            tma_load_1d(dst + r * WarpSmem<CH>::ROWB, frame_lo + (long long)v * pitch, row_bytes, &sm.full[half]);
+            tma_load_1d(dst + r * WarpSmem<CH>::ROWB, frame_lo + (long long)v * pitch, row_bytes, &sm.full[stage]);
         }
     };
     if (lane == 0) {
-        issue(0, 0);
-        issue(0, 1);
+        issue(0);
+        issue(1);
     }
 
     constexpr uint32_t C_BG = 7470u | (38470u << 16), C_R = 19596u, C_B = 7470u << 16, C_GR = 38470u | (19596u << 16), RND = 32768u;
@@ -349,38 +347,33 @@ fused_preprocess_warp_kernel(const uint8_t *__restrict__ src, uint8_t *__restric
     // zero pad tile all around): this lane's 8 pixels are byte (c0 % 32) / 8 of word (y + 32) % 32 of tile (c0/32 + 1, (y+32)/32)
     uint8_t *blane = bits ? bits + (long long)fr * bits_frame_bytes + (long long)(c0 / 32 + 1) * 128 + ((c0 & 31) >> 3) : nullptr;
     for (int k = 0; k < nblk; ++k, optr += 4 * wl) {
-        const int q = q_first + k;
-        // ---- phase 1: raw -> gray, 8 columns = 2 packed words per row; each half-block is re-armed for block k+1 as soon as
-        // every lane has read it ------------------------------------------------------------------------------------------------
+        const int q = q_first + k, stage = k & 1;
+        mbar_wait(&sm.full[stage], (uint32_t)((k >> 1) & 1));
+        // ---- phase 1: raw -> gray, 8 columns = 2 packed words per row ------------------------------------------
         uint32_t G[R][2];
 #pragma unroll
-        for (int half = 0; half < NSTAGE; ++half) {
-            mbar_wait(&sm.full[half], (uint32_t)(k & 1));
+        for (int r = 0; r < R; ++r) {
+            if (CH == 1) {
+                const uint2 v = *reinterpret_cast<const uint2 *>(&sm.raw[stage][r * WarpSmem<CH>::ROWB + LPAD - CPL + CPL * lane]);
+                G[r][0] = v.x;
+                G[r][1] = v.y;
+            } else {
+                const uint2 *p = reinterpret_cast<const uint2 *>(&sm.raw[stage][r * WarpSmem<CH>::ROWB + 3 * (LPAD - CPL + CPL * lane)]);
+                const uint2 v0 = p[0], v1 = p[1], v2 = p[2];
+                const uint32_t ww[6] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
 #pragma unroll
-            for (int rr = 0; rr < RS; ++rr) {
-                const int r = half * RS + rr;
-                if (CH == 1) {
-                    const uint2 v = *reinterpret_cast<const uint2 *>(&sm.raw[half][rr * WarpSmem<CH>::ROWB + LPAD - CPL + CPL * lane]);
-                    G[r][0] = v.x;
-                    G[r][1] = v.y;
-                } else {
-                    const uint2 *p = reinterpret_cast<const uint2 *>(&sm.raw[half][rr * WarpSmem<CH>::ROWB + 3 * (LPAD - CPL + CPL * lane)]);
-                    const uint2 v0 = p[0], v1 = p[1], v2 = p[2];
-                    const uint32_t ww[6] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const uint32_t w0 = ww[3 * hh], w1 = ww[3 * hh + 1], w2 = ww[3 * hh + 2];
-                        const uint32_t g0 = __dp2a_hi(C_R, w0, __dp2a_lo(C_BG, w0, RND));
-                        const uint32_t g1 = __dp2a_lo(C_GR, w1, __dp2a_hi(C_B, w0, RND));
-                        const uint32_t g2 = __dp2a_lo(C_R, w2, __dp2a_hi(C_BG, w1, RND));
-                        const uint32_t g3 = __dp2a_hi(C_GR, w2, __dp2a_lo(C_B, w2, RND));
-                        G[r][hh] = __byte_perm(__byte_perm(g0, g1, 0x0062), __byte_perm(g2, g3, 0x0062), 0x5410);
-                    }
+                for (int hh = 0; hh < 2; ++hh) {
+                    const uint32_t w0 = ww[3 * hh], w1 = ww[3 * hh + 1], w2 = ww[3 * hh + 2];
+                    const uint32_t g0 = __dp2a_hi(C_R, w0, __dp2a_lo(C_BG, w0, RND));
+                    const uint32_t g1 = __dp2a_lo(C_GR, w1, __dp2a_hi(C_B, w0, RND));
+                    const uint32_t g2 = __dp2a_lo(C_R, w2, __dp2a_hi(C_BG, w1, RND));
+                    const uint32_t g3 = __dp2a_hi(C_GR, w2, __dp2a_lo(C_B, w2, RND));
+                    G[r][hh] = __byte_perm(__byte_perm(g0, g1, 0x0062), __byte_perm(g2, g3, 0x0062), 0x5410);
                 }
             }
-            __syncwarp();  // every lane has read this half: refill it with the next block's
-            if (lane == 0) issue(k + 1, half);
         }
+        __syncwarp();  // every lane has read this stage: refill it with the block after next
+        if (lane == 0) issue(k + 2);
 
         // ---- phase 2: horizontal 5-tap (dp4a on byte windows), +8 per row sum = the +128 rounding of the 5x5 --------
         uint32_t Hn[R][4];
@@ -587,23 +580,23 @@ static int launch_k1w(svb_ctx *ctx, const uint8_t *src, int n, int h, int w, uin
     const int smem = (int)sizeof(WarpSmem<CH>);
     SVB_CUDA_OK(cudaFuncSetAttribute(fused_preprocess_warp_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int nstrips = (w + TW - 1) / TW;
-    // row segments: enough warps for ~8 waves of the 14 resident warps per SM (every segment re-computes ~16 warm-up rows,
+    // row segments: enough warps for ~8 waves of the 12 resident warps per SM (every segment re-computes ~16 warm-up rows,
     // so more, shorter segments cost work; fewer, longer ones leave a longer idle tail behind the last wave), segments no
     // shorter than 64 rows
     const long long strips = (long long)nstrips * n;
-    long long want = (8LL * 14 * ctx->sm_count + strips - 1) / strips;
+    long long want = (8LL * 12 * ctx->sm_count + strips - 1) / strips;
     int nseg = (int)max(1LL, min(want, (long long)(h / 64)));
     int rows_per_seg = (((h + nseg - 1) / nseg) + 3) & ~3;
     nseg = (h + rows_per_seg - 1) / rows_per_seg;
     if (n > 65535 || nseg > 65535) return SVB_ERR_UNSUPPORTED;
-    // the frame stack as a 2-D tensor of u32 elements: [n*h rows][w*CH/4]; box = one half-block (2 rows) x one staged strip
+    // the frame stack as a 2-D tensor of u32 elements: [n*h rows][w*CH/4]; box = 4 rows x one staged strip
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     int use_tmap = 0;
     if (tensor_map_encoder() && (long long)n * h < (1LL << 31)) {
         const cuuint64_t gdim[2] = {(cuuint64_t)w * CH / 4, (cuuint64_t)n * h};
         const cuuint64_t gstride[1] = {(cuuint64_t)w * CH};
-        const cuuint32_t box[2] = {(cuuint32_t)(SW * CH / 4), (cuuint32_t)RS};
+        const cuuint32_t box[2] = {(cuuint32_t)(SW * CH / 4), (cuuint32_t)R};
         const cuuint32_t estride[2] = {1, 1};
         use_tmap = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void *)src, gdim, gstride, box, estride,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
