@@ -43,7 +43,8 @@ METRIC = "frames/sec end-to-end (preprocess->warp->81-cell CNN) at 1080p"
 K1_BYTES_PER_FRAME = 3 * H * W + H * W  # 6,220,800 read + 2,073,600 written
 # dram__bytes_read.sum + dram__bytes_write.sum per 1080p frame from the ncu --set full captures under profiles/ (see
 # profiles/README.md for the capture each constant comes from); None = no capture of the current kernel yet
-NCU_TRAFFIC_PER_FRAME = {"k1": int((1.769238e9 + 0.510463e9) / 256), "k4": None}
+NCU_TRAFFIC_PER_FRAME = {"k1": int((1.769238e9 + 0.510463e9) / 256),            # profiles/r1d_k1w_raw.csv (kernel unchanged since)
+                         "k4": int((435.669504e6 + 6.6816e6) / 256)}              # profiles/r2b_k4_summary.csv
 # true MACs only, per cell: conv1 225,792 + conv2 3,612,672; fc1 401,408 + fc2 1,280
 K5_CONV_FLOP_PER_CELL = 2 * (225792 + 3612672)
 K5_FC_FLOP_PER_CELL = 2 * (401408 + 1280)
@@ -358,7 +359,14 @@ def other_configs(sc, dev, tpeak: float) -> dict:
             "workload": "BASELINE configs[2]: 1,000,000 synthetic 28x28 +-1 cells, classifier only, one call", "cells": n_cells,
             "ms": round(ms, 3), "cells_per_s": n_cells / (ms * 1e-3), "algorithmic_tflops": tf, "tensor_frac": tf / tpeak,
             "peak_tflops": tpeak}
-    del x
+    # the batched path's own form of the DigitCNN input: 28 bit rows per cell (conv1 by pattern table)
+    xb = sc.pack_cells_bits(x.view(n_cells, 28, 28))
+    ms = timed(lambda: sc.digitcnn_forward_bits(xb), 2)
+    tf = (K5_CONV_FLOP_PER_CELL + K5_FC_FLOP_PER_CELL) * n_cells / (ms * 1e-3) / 1e12
+    out["config3_classifier_only_digitcnn_bit_rows"] = {
+        "workload": "the same 1,000,000 cells as 28 bit rows each (svb_digitcnn_forward_bits, what svb_scan_batch_v1 runs)", "cells": n_cells,
+        "ms": round(ms, 3), "cells_per_s": n_cells / (ms * 1e-3), "algorithmic_tflops": tf, "tensor_frac": tf / tpeak, "peak_tflops": tpeak}
+    del x, xb
     torch.cuda.empty_cache()
     # configs[3]: 4096 4K frames = 101.9 GB of BGR: 16 resident chunks of 256 frames (6.4 GB each), regenerated per chunk
     hh, ww, total, chunk = 2160, 3840, 4096, 256

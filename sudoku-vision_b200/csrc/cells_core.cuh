@@ -260,15 +260,16 @@ SVB_CHD uint32_t sample_bgr_checked(const uint8_t *frame, int h, int w, int ix, 
     return out;
 }
 // footprint fully inside the frame: the two pixels of a footprint row are 6 contiguous bytes = three aligned words +
-// funnel shifts; (sum w p + 2^14) >> 15 == (S + 512) >> 10 with S = cy0 (cx0 p00 + cx1 p01) + cy1 (cx0 p10 + cx1 p11)
-SVB_CHD uint32_t sample_gray_inside(const uint8_t *frame, int w, int ix, int iy, int ax, int ay) {
-    const int a = (iy * w + ix) * 3;
+// funnel shifts; (sum w p + 2^14) >> 15 == (S + 512) >> 10 with S = cy0 (cx0 p00 + cx1 p01) + cy1 (cx0 p10 + cx1 p11).
+// fb = the frame's address rounded down to a word, mis = the bytes that took (0..3): all offsets stay 32-bit.
+SVB_CHD uint32_t sample_gray_inside(const uint32_t *fb, uint32_t mis, int w, int ix, int iy, int ax, int ay) {
+    const uint32_t a0 = (uint32_t)(iy * w + ix) * 3u + mis;
     const uint32_t cx = (uint32_t)(32 - ax) | ((uint32_t)ax << 16);
     uint32_t rB[2], rG[2], rR[2];
     for (int r = 0; r < 2; ++r) {
-        const uintptr_t addr = reinterpret_cast<uintptr_t>(frame + (a + r * w * 3));
-        const uint32_t *p = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
-        const uint32_t sh = (uint32_t)(addr & 3) * 8u;
+        const uint32_t a = a0 + (uint32_t)(r * w * 3);
+        const uint32_t *p = fb + (a >> 2);
+        const uint32_t sh = (a & 3u) * 8u;
         const uint32_t w0 = ldg32(p), w1 = ldg32(p + 1), w2 = ldg32(p + 2);
         const uint32_t lo = funnel_r(w0, w1, sh), hi = funnel_r(w1, w2, sh);  // B0 G0 R0 B1 | G1 R1 . .
         const uint32_t bg = byte_perm(lo, hi, 0x4130);                         // B0 B1 G0 G1
@@ -309,9 +310,11 @@ SVB_CHD void phase_sample(Smem &s, int tid, const uint8_t *frame, int h, int w, 
     double fin = 0.0;
     for (int i = 0; i < 9; ++i) fin = dfma(mi[i], 0.0, fin);
     const bool finite = fin == 0.0;
-    for (int yy = rg; yy < CROP; yy += 3) {
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(frame) & 3u);
+    const uint32_t *fb = reinterpret_cast<const uint32_t *>(frame - mis);
+    double yd = (double)(cell_r * (BOARD / 9) + 5 + rg);
+    for (int yy = rg; yy < CROP; yy += 3, yd += 3.0) {  // small integers: the increment is exact
         const int y = cell_r * (BOARD / 9) + 5 + yy;
-        const double yd = (double)y;
         const double D = dfma(dy, yd, d0);
         const float df = (float)D;
         const float r0 = rcp_approx(df);
@@ -333,9 +336,10 @@ SVB_CHD void phase_sample(Smem &s, int tid, const uint8_t *frame, int h, int w, 
         }
         const int ix = X >> 5, iy = Y >> 5, ax = X & 31, ay = Y & 31;
         uint32_t gv;
-        // footprint inside the frame, and the 12-byte window of its second row inside the buffer
-        if ((unsigned)ix < (unsigned)(w - 1) && (unsigned)iy < (unsigned)(h - 1) && (iy + 2 < h || ix + 4 < w)) {
-            gv = sample_gray_inside(frame, w, ix, iy, ax, ay);
+        // footprint inside the frame with a whole row below it, so the 12-byte windows stay inside the frame (the last row
+        // pair of a frame takes the checked form)
+        if ((unsigned)ix < (unsigned)(w - 1) && (unsigned)iy < (unsigned)(h - 2)) {
+            gv = sample_gray_inside(fb, mis, w, ix, iy, ax, ay);
         } else {
             const uint32_t v = sample_bgr_checked(frame, h, w, ix, iy, ax, ay);
             gv = gray_of(v & 0xff, (v >> 8) & 0xff, (v >> 16) & 0xff);
