@@ -224,6 +224,10 @@ struct alignas(16) Smem {
     uint8_t cell[CELL * CELL], eq[CELL * CELL];
     float tlut[52];            // rint(c * 255/49): the CLAHE LUT value of cumulative count c
     int16_t rs0[CELL], ra0[CELL], ra1[CELL];
+    // per-row constants of the resize and the CLAHE blend, one 16-byte load per row instead of per-pixel index arithmetic:
+    // rowr[y] = {first | second source row offset (x 40) in the low / high half, b0, b1, 4 * (y / 7)};
+    // rowb[y] = {256 * 4 * ty1, 256 * 4 * ty2 (byte offsets of the two tile rows in lutc), bits of ya1, bits of ya}
+    int32_t rowr[CELL][4], rowb[CELL][4];
     uint32_t bits[CELL];       // classifier input, one 28-bit row per word: bit x = 1 <=> +1 (ink)
 };
 
@@ -239,6 +243,23 @@ SVB_CHD void phase_setup(Smem &s, int tid, const Tables *tb) {
         s.bits[tid] = 0u;
     }
     if (tid < 52) s.tlut[tid] = (float)f2i_rn(fmul((float)tid, 255.0f / 49.0f));
+    if (tid < CELL) {
+        const int y = tid, sy = tb->s0[y], sy1 = sy + 1 < CROP ? sy + 1 : CROP - 1;
+        s.rowr[y][0] = (sy * CROP) | ((sy1 * CROP) << 16);
+        s.rowr[y][1] = tb->a0[y];
+        s.rowr[y][2] = tb->a1[y];
+        s.rowr[y][3] = 4 * (y / 7);
+        const float tyf = fadd(fmul((float)y, 1.0f / 7.0f), -0.5f);
+        int ty1 = (int)floorf(tyf);
+        const float ya = fadd(tyf, -(float)ty1), ya1 = fadd(1.0f, -ya);
+        int ty2 = ty1 + 1;
+        ty1 = ty1 < 0 ? 0 : (ty1 > 3 ? 3 : ty1);
+        ty2 = ty2 < 0 ? 0 : (ty2 > 3 ? 3 : ty2);
+        s.rowb[y][0] = 1024 * ty1;
+        s.rowb[y][1] = 1024 * ty2;
+        memcpy(&s.rowb[y][2], &ya1, 4);
+        memcpy(&s.rowb[y][3], &ya, 4);
+    }
 }
 
 // ---- phase 1: warpPerspective samples of the 40x40 crop, gray ----------------------------------------------------------
@@ -356,15 +377,16 @@ SVB_CHD void note_value(Smem &s, int x, int y, uint32_t v) {
 SVB_CHD void phase_resize(Smem &s, int tid, uint8_t *cells_u8 /* optional: this cell's 784 bytes in global memory */) {
     if (tid >= 4 * CELL) return;
     const int x = tid % CELL, rg = tid / CELL;
-    const int sx = s.rs0[x], sx1 = sx + 1 < CROP ? sx + 1 : CROP - 1, a0 = s.ra0[x], a1 = s.ra1[x];
+    const int sx = s.rs0[x], sx1 = sx + 1 < CROP ? sx + 1 : CROP - 1, a0 = s.ra0[x], a1 = s.ra1[x], tcol = x / 7;
+    const uint8_t *cs = &s.u.a.crop[sx], *cs1 = &s.u.a.crop[sx1];
     for (int y = rg; y < CELL; y += 4) {
-        const int sy = s.rs0[y], sy1 = sy + 1 < CROP ? sy + 1 : CROP - 1, b0 = s.ra0[y], b1 = s.ra1[y];
-        const uint8_t *c0 = &s.u.a.crop[sy * CROP], *c1 = &s.u.a.crop[sy1 * CROP];
-        const int h0 = c0[sx] * a0 + c0[sx1] * a1, h1 = c1[sx] * a0 + c1[sx1] * a1;
+        const int r0 = s.rowr[y][0], b0 = s.rowr[y][1], b1 = s.rowr[y][2], trow = s.rowr[y][3];
+        const int o0 = r0 & 0xffff, o1 = r0 >> 16;
+        const int h0 = cs[o0] * a0 + cs1[o0] * a1, h1 = cs[o1] * a0 + cs1[o1] * a1;
         const uint32_t v = (uint32_t)(((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16)) + 2) >> 2);
         s.cell[y * CELL + x] = (uint8_t)v;
         if (cells_u8) cells_u8[y * CELL + x] = (uint8_t)v;
-        note_value(s, x, y, v);
+        or_shared(&s.pres[trow + tcol][v >> 5], 1u << (v & 31u));
     }
 }
 // the same bookkeeping for a cell that arrives already resized (drop-in preprocess_cell)
@@ -416,23 +438,21 @@ SVB_CHD void phase_clahe_c(Smem &s, int tid) {
 SVB_CHD void phase_clahe_blend(Smem &s, int tid) {
     if (tid >= 4 * CELL) return;
     const int x = tid % CELL, rg = tid / CELL;
-    const float inv = 1.0f / 7.0f;
-    const float txf = fadd(fmul((float)x, inv), -0.5f);
+    const float txf = fadd(fmul((float)x, 1.0f / 7.0f), -0.5f);
     int tx1 = (int)floorf(txf);
     const float xa = fadd(txf, -(float)tx1), xa1 = fadd(1.0f, -xa);
     int tx2 = tx1 + 1;
     tx1 = tx1 < 0 ? 0 : (tx1 > 3 ? 3 : tx1);
     tx2 = tx2 < 0 ? 0 : (tx2 > 3 ? 3 : tx2);
+    const uint8_t *l1 = &s.u.a.lutc[tx1][0], *l2 = &s.u.a.lutc[tx2][0];  // tile column's LUT; the row adds 1024 * ty
     for (int y = rg; y < CELL; y += 4) {
-        const float tyf = fadd(fmul((float)y, inv), -0.5f);
-        int ty1 = (int)floorf(tyf);
-        const float ya = fadd(tyf, -(float)ty1), ya1 = fadd(1.0f, -ya);
-        int ty2 = ty1 + 1;
-        ty1 = ty1 < 0 ? 0 : (ty1 > 3 ? 3 : ty1);
-        ty2 = ty2 < 0 ? 0 : (ty2 > 3 ? 3 : ty2);
+        const int o1 = s.rowb[y][0], o2 = s.rowb[y][1];
+        float ya1, ya;
+        memcpy(&ya1, &s.rowb[y][2], 4);
+        memcpy(&ya, &s.rowb[y][3], 4);
         const int v = s.cell[y * CELL + x];
-        const float l11 = s.tlut[s.u.a.lutc[ty1 * 4 + tx1][v]], l12 = s.tlut[s.u.a.lutc[ty1 * 4 + tx2][v]];
-        const float l21 = s.tlut[s.u.a.lutc[ty2 * 4 + tx1][v]], l22 = s.tlut[s.u.a.lutc[ty2 * 4 + tx2][v]];
+        const float l11 = s.tlut[l1[o1 + v]], l12 = s.tlut[l2[o1 + v]];
+        const float l21 = s.tlut[l1[o2 + v]], l22 = s.tlut[l2[o2 + v]];
         const float top = fmul(fadd(fmul(l11, xa1), fmul(l12, xa)), ya1);
         const float bot = fmul(fadd(fmul(l21, xa1), fmul(l22, xa)), ya);
         int ev = f2i_rn(fadd(top, bot));
