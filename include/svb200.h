@@ -60,9 +60,6 @@ long long svb_launch_count(const svb_ctx *ctx);
  * each fill the machine on their own, so interleaving them costs more than hiding K2 gains; hence off by default.
  * Stage timing (below) implies the in-order form. */
 #define SVB_OPT_OVERLAP 1
-/* SVB_OPT_K5_GROUPS (default 1): the bit-row classifier's convolution kernel runs two independent cell pipelines per CTA
- * (k5tc::tc_conv_groups_kernel); 0 = one software-pipelined cell stream per CTA (k5tc::tc_conv_kernel<true>).  Same results. */
-#define SVB_OPT_K5_GROUPS 2
 int svb_set_option(svb_ctx *ctx, int option, int value);
 
 #define SVB_NUM_STAGES 5

@@ -447,7 +447,6 @@ static int get_worker(svb_ctx *ctx, int slot, svb_ctx **out) {
     w->cnn = ctx->cnn;        // borrowed device pointers (read-only)
     w->cnn_tc = ctx->cnn_tc;
     w->classifier_mode = ctx->classifier_mode;
-    w->k5_groups = ctx->k5_groups;
     *out = w;
     return SVB_OK;
 }
@@ -513,11 +512,6 @@ API int svb_set_option(svb_ctx *ctx, int option, int value) {
     switch (option) {
     case SVB_OPT_OVERLAP:
         ctx->overlap = value < 0 ? 0 : value;
-        return SVB_OK;
-    case SVB_OPT_K5_GROUPS:
-        ctx->k5_groups = value != 0;
-        for (auto &wk : ctx->worker)
-            if (wk) wk->k5_groups = ctx->k5_groups;
         return SVB_OK;
     default:
         set_error("svb_set_option: unknown option %d", option);

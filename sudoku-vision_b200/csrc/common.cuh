@@ -68,7 +68,6 @@ struct svb_ctx {
     void *jpeg_state = nullptr;   // pinned header staging of svb_jpeg_decode_host (jpeg.cu)
     void *fc_state = nullptr;  // svb_find_contours_count -> svb_find_contours_fetch (contours_all.cu)
     int classifier_mode = 0;   // 0 = tcgen05 (fp16 hi/lo split), 1 = fp32 CUDA cores
-    int k5_groups = 0;         // bit-row classifier: two cell pipelines per CTA (SVB_OPT_K5_GROUPS)
     void *pinned = nullptr;    // host staging for *_host calls
     size_t pinned_bytes = 0;
     cudaStream_t own_stream = nullptr;

@@ -461,175 +461,6 @@ tc_conv_kernel(const void *__restrict__ xin_any, long long n_cells, const float 
 }
 
 // ================================================================================================
-// conv stack, two cell pipelines per CTA (bit-row input).
-//
-// tc_conv_kernel's period per cell is its WORKER phase — operands -> barrier -> epilogue of the previous cell -> conv1 of the
-// next: chains of dependent shared-memory look-ups, shuffles and tcgen05.ld round trips at 0.37 IPC per scheduler with one CTA
-// per SM — not its 72 MMAs (ncu, profiles/r2b_k5conv_summary.csv: tensor pipe 62 % active).  Shared memory (conv2 weights 74 KB
-// + conv1 table 64 KB + operands) rules out a second CTA, so the second, independent instruction stream lives INSIDE the CTA:
-// two groups of 8 warps (7 conv1 / epilogue warps + 1 MMA-issue warp) each run a strictly serial pipeline
-//     rows -> conv1 by table straight into the group's operand image -> MMAs (2 tiles) -> wait -> epilogue
-// on alternate cells, with their own operand buffer (the two halves of the old double buffer), accumulators (256 TMEM columns
-// each), mbarrier and named barriers.  While one group waits for the tensor core, the other one convolves or pools.
-// ================================================================================================
-constexpr int NGRP = 2;
-constexpr int GTHREADS = 256;  // threads per group
-constexpr int GWORKERS = 224;  // warps 0..6 of a group; warp 7 issues the MMAs
-
-struct ConvSmemGroups {
-    alignas(1024) uint8_t S[NGRP][2][S_BYTES];  // [group][hi/lo] pooled conv1 activations
-    alignas(128) uint8_t WB[2][WB_BYTES];
-    alignas(128) uint8_t T1[T1_BYTES];
-    float C1[9][32];
-    float b2[64];
-    uint32_t rows[NGRP][32];                    // [group][1 + y]; rows 0 and 29 stay zero
-    alignas(8) unsigned long long mbar[NGRP];
-    uint32_t tmem_base;
-};
-
-__device__ __forceinline__ void bar_group(int g) { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); }
-__device__ __forceinline__ void bar_group_workers(int g) { asm volatile("bar.sync %0, 224;" ::"r"(3 + g) : "memory"); }
-
-__global__ void __launch_bounds__(NGRP * GTHREADS, 1)
-tc_conv_groups_kernel(const uint32_t *__restrict__ xb, long long n_cells, const uint8_t *__restrict__ wb_img,
-                      const float *__restrict__ b2, const uint8_t *__restrict__ t1_img, const float *__restrict__ c1_img,
-                      __half *__restrict__ feat_hi, __half *__restrict__ feat_lo) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    ConvSmemGroups &s = *reinterpret_cast<ConvSmemGroups *>(smem_raw);
-    constexpr int NTH = NGRP * GTHREADS;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int grp = warp >> 3, wg = warp & 7, gtid = tid & (GTHREADS - 1);
-    const bool mma_warp = (wg == 7);
-
-    // ---- one-time setup (whole CTA) ---------------------------------------------------------------------------------
-    for (int i = tid; i < NGRP * 2 * S_BYTES / 16; i += NTH) reinterpret_cast<uint4 *>(&s.S[0][0][0])[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < 2 * WB_BYTES / 16; i += NTH) reinterpret_cast<uint4 *>(&s.WB[0][0])[i] = reinterpret_cast<const uint4 *>(wb_img)[i];
-    for (int i = tid; i < T1_BYTES / 16; i += NTH) reinterpret_cast<uint4 *>(&s.T1[0])[i] = reinterpret_cast<const uint4 *>(t1_img)[i];
-    for (int i = tid; i < 9 * 32; i += NTH) (&s.C1[0][0])[i] = c1_img[i];
-    if (tid < 64) {
-        s.b2[tid] = b2[tid];
-        (&s.rows[0][0])[tid] = 0u;
-    }
-    if (tid == 0) {
-        for (int g = 0; g < NGRP; ++g) mbar_init(&s.mbar[g], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) tmem_alloc(&s.tmem_base, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = s.tmem_base + (uint32_t)(grp * 256);
-    const uint32_t idesc64 = make_idesc(128, 64), idesc128 = make_idesc(128, 128);
-    const uint32_t s_base = smem_u32(&s.S[grp][0][0]), wb_base = smem_u32(&s.WB[0][0]);
-    const uint64_t a_desc0 = make_desc(s_base, SROWS * 16, 128), b_desc0 = make_desc(wb_base, 128, WB_SBO);
-    uint32_t phase = 0, preb = 0u;
-    bool have_pre = false;
-
-    for (long long cell = blockIdx.x + (long long)grp * gridDim.x; cell < n_cells; cell += (long long)NGRP * gridDim.x) {
-        if (!mma_warp) {
-            // ---- the cell's bit rows, then conv1 + bias + ReLU + pool by table, written straight into the operand image ----
-            if (gtid < 28) s.rows[grp][1 + gtid] = have_pre ? preb : __ldg(xb + cell * 28 + gtid);
-            bar_group_workers(grp);
-#pragma unroll 1
-            for (int it = 0; it < (196 * 4 + GWORKERS - 1) / GWORKERS; ++it) {
-                const int item = it * GWORKERS + gtid;
-                const bool valid = item < 196 * 4;
-                int cg = 0, py = 1, px = 1;
-                if (valid) bitscore::item_coords(item, cg, py, px);
-                const bool border = valid && ((py == 0) | (py == 13) | (px == 0) | (px == 13));
-                const bool warp_border = __any_sync(0xffffffffu, border);  // every lane of a worker warp gets here
-                if (valid) {
-                    float m[8];
-                    if (warp_border) bitscore::pooled_item(&s.rows[grp][0], &s.T1[0], &s.C1[0][0], cg, py, px, true, m);
-                    else bitscore::pooled_item(&s.rows[grp][0], &s.T1[0], &s.C1[0][0], cg, py, px, false, m);
-                    __half hi[8], lo[8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) split_hi_lo(m[c], hi[c], lo[c]);
-                    const int row = (py + 2) * 16 + px + PAD;
-                    const int off = cg * (SROWS * 16) + row * 16;
-                    *reinterpret_cast<uint4 *>(&s.S[grp][0][off]) = *reinterpret_cast<const uint4 *>(hi);
-                    *reinterpret_cast<uint4 *>(&s.S[grp][1][off]) = *reinterpret_cast<const uint4 *>(lo);
-                }
-            }
-        }
-        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        tc_fence_before();
-        bar_group(grp);       // the operand image is complete
-        if (mma_warp) {
-            tc_fence_after();
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-#pragma unroll
-                for (int combo = 0; combo < 2; ++combo) {  // 0: A_hi x [B_hi|B_lo] (N=128), 1: A_lo x B_hi (N=64)
-#pragma unroll
-                    for (int t = 0; t < 9; ++t) {
-                        const int dy = t / 3 - 1, dx = t % 3 - 1;
-                        const uint32_t a_off = (uint32_t)(combo * S_BYTES + (128 * j + 16 * dy + dx + PAD) * 16);
-                        const uint32_t b_off = (uint32_t)(t * 4 * 128);
-#pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
-                            const uint64_t ad = a_desc0 + (uint64_t)((a_off + ks * 2 * SROWS * 16) >> 4);
-                            const uint64_t bd = b_desc0 + (uint64_t)((b_off + ks * 256) >> 4);
-                            if (lane == 0)
-                                umma_f16(tmem + (uint32_t)(j * 128), ad, bd, combo ? idesc64 : idesc128, (combo | t | ks) ? 1u : 0u);
-                        }
-                    }
-                }
-            }
-            if (lane == 0) umma_commit(&s.mbar[grp]);
-            __syncwarp();
-        }
-        // the next cell's rows travel while the tensor core works
-        const long long next = cell + (long long)NGRP * gridDim.x;
-        have_pre = next < n_cells;
-        if (!mma_warp && gtid < 28 && have_pre) preb = __ldg(xb + next * 28 + gtid);
-        mbar_wait(&s.mbar[grp], phase);
-        phase ^= 1;
-        tc_fence_after();
-        // ---- epilogue: TMEM -> 2x2 max-pool (shuffles) -> bias / ReLU -> fp16 hi / lo features.  8 warps: tile j, lane quarter q ----
-        {
-            const int j = wg >> 2, q = wg & 3;
-            const int py = 4 * j + q - 1;  // pooled row produced by this warp (grid rows y_p = 2(4j+q), +1)
-            const int px = (lane & 15) >> 1;
-            const bool writer = (px < 7) && py >= 0 && py < 7;
-            const int chunk = (lane & 1) + 2 * (lane >> 4);  // which 8 of a half's 32 channels this lane finishes and stores
-            const bool b0 = lane & 1, b1 = lane >> 4;
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                __half *fh = feat_hi + (cell * 49 + (long long)(py * 7 + px)) * 64 + half * 32 + chunk * 8;
-                __half *fl = feat_lo + (cell * 49 + (long long)(py * 7 + px)) * 64 + half * 32 + chunk * 8;
-                uint32_t v[32], v2[32];
-                const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 128 + half * 32);
-                tmem_ld32(ta, v);
-                tmem_ld32(ta + 64, v2);
-                float g[16], pooled[8];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int ca = (i < 8) ? i : 8 + i;  // columns of chunks 0 and 2; chunks 1 and 3 are 8 further
-                    const float fa = __uint_as_float(v[ca]) + __uint_as_float(v2[ca]);
-                    const float fb = __uint_as_float(v[ca + 8]) + __uint_as_float(v2[ca + 8]);
-                    g[i] = fmaxf(b0 ? fb : fa, __shfl_xor_sync(0xffffffffu, b0 ? fa : fb, 1));
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) pooled[i] = fmaxf(b1 ? g[8 + i] : g[i], __shfl_xor_sync(0xffffffffu, b1 ? g[i] : g[8 + i], 16));
-                __half hi[8], lo[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) split_hi_lo(fmaxf(pooled[c] + s.b2[half * 32 + chunk * 8 + c], 0.f), hi[c], lo[c]);
-                if (writer) {
-                    *reinterpret_cast<uint4 *>(fh) = *reinterpret_cast<const uint4 *>(hi);
-                    *reinterpret_cast<uint4 *>(fl) = *reinterpret_cast<const uint4 *>(lo);
-                }
-            }
-        }
-        tc_fence_before();
-        bar_group(grp);  // every TMEM read of this cell has retired before the group's next MMAs overwrite the accumulators
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(s.tmem_base, 512);
-}
-
-// ================================================================================================
 // fc1 (tcgen05) + fc2 + softmax/argmax epilogue
 // ================================================================================================
 constexpr int FC_KC = 64;                       // K chunk per stage (4 MMAs of K=16)
@@ -932,11 +763,7 @@ int launch_digitcnn_tc(svb_ctx *ctx, const void *x, bool bits, long long n, floa
     __half *fl = (__half *)((char *)ctx->arena[AR_CNN].ptr + ((feat_bytes + 255) & ~(size_t)255));
     const int grid = (int)min((long long)ctx->sm_count, n);
     const float *c1 = (const float *)(t->t1_img + T1_BYTES);
-    if (bits && ctx->k5_groups) {
-        SVB_CUDA_OK(cudaFuncSetAttribute(tc_conv_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmemGroups)));
-        const int g2 = (int)min((long long)ctx->sm_count, (n + NGRP - 1) / NGRP);
-        tc_conv_groups_kernel<<<g2, NGRP * GTHREADS, sizeof(ConvSmemGroups), st>>>((const uint32_t *)x, n, t->wb_img, c.conv2_b, t->t1_img, c1, fh, fl);
-    } else if (bits) {
+    if (bits) {
         SVB_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmemBits)));
         tc_conv_kernel<true><<<grid, NTC, sizeof(ConvSmemBits), st>>>(x, n, c.conv1_w, c.conv1_b, t->wb_img, c.conv2_b, t->t1_img, c1, fh, fl);
     } else {

@@ -86,7 +86,7 @@ class Scanner:
     def launches(self) -> int:
         return int(self.lib.svb_launch_count(self._h))
 
-    OPTIONS = dict(overlap=1, k5_groups=2)
+    OPTIONS = dict(overlap=1)
 
     def set_option(self, name: str, value: int):
         """'overlap' (default 0): p >= 2 makes scan_batch run p sub-batches on two internal streams (see include/svb200.h)."""
