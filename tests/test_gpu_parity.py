@@ -367,6 +367,17 @@ def test_digitcnn_v3_tensor_core_vs_fp32_and_oracle(scanner, n):
     assert np.array_equal(digits.cpu().numpy()[:m][clear], want.argmax(1).astype(np.uint8)[clear])
     feats = scanner.digitcnn_v3_forward(xd[:m], want_features=True).cpu().numpy()
     assert np.abs(feats - M.forward(sd, x[:m], return_features=True)).max() < LOGIT_TOL
+    if n > 2000:  # a wider oracle sample across both chunks of the batch: 384 cells, checked in parallel (numpy oracle)
+        import concurrent.futures as cf
+
+        idx = np.concatenate([np.arange(48, 176), np.arange(n // 2 - 64, n // 2 + 64), np.arange(n - 128, n)])
+        with cf.ThreadPoolExecutor(max_workers=8) as ex:
+            parts = list(ex.map(lambda ii: M.forward(sd, x[ii]), np.array_split(idx, 12)))
+        want = np.concatenate(parts)
+        assert np.abs(got[idx] - want).max() < LOGIT_TOL
+        top2 = np.sort(want, 1)
+        clear = (top2[:, -1] - top2[:, -2]) > 10 * LOGIT_TOL
+        assert np.array_equal(digits.cpu().numpy()[idx][clear], want.argmax(1).astype(np.uint8)[clear])
 
 
 # ---- whole path -----------------------------------------------------------------------------------
@@ -388,6 +399,49 @@ def test_scan_batch_vs_oracle(scanner, oracle, weights):
         assert np.array_equal(out["digits"][i].cpu().numpy(), want.argmax(1).astype(np.uint8))
         assert (out["digits"][i].cpu().numpy().reshape(9, 9) == digits_gt[i]).mean() > 0.95  # and it reads the board
     assert found[-1] == 0
+
+
+def test_scan_batch_1024_frames_vs_oracle(scanner, oracle, weights):
+    """BASELINE configs[1] at its stated size: all 1024 frames of a bench-style batch (16 rendered frames x device noise, three
+    frames without a grid) against the C oracle: found, corners exact, digits identical (the benched batch itself
+    was never compared with anything).  The oracle runs on all host cores (ctypes releases the GIL)."""
+    import concurrent.futures as cf
+    import os
+
+    import torch
+    from svb200 import frames as F
+
+    n = 1024
+    clean = np.stack([F.make_frame(31000 + i, 1080, 1920).image for i in range(16)])
+    batch = F.noisy_batch_device(torch.from_numpy(clean).cuda(), n, seed=7)
+    batch[5] = 0
+    batch[500] = 255
+    batch[1023] = torch.from_numpy(np.random.default_rng(1).integers(0, 256, (1080, 1920, 3)).astype(np.uint8)).cuda()
+    out = scanner.scan_batch(batch, want_logits=True)
+    torch.cuda.synchronize()
+    got = {k: v.cpu().numpy() for k, v in out.items()}
+    frames = batch.cpu().numpy()
+
+    def one(i):
+        r = oracle.scan_frame(frames[i])
+        if not r["found"]:
+            return i, False, None, None
+        lg = oracle.digitcnn_forward(weights, (r["cells_in"].astype(np.float32) / 255.0 - 0.5) / 0.5)
+        return i, True, r["corners"], lg
+
+    with cf.ThreadPoolExecutor(max_workers=max(1, len(os.sched_getaffinity(0)))) as ex:
+        res = list(ex.map(one, range(n)))
+    nfound = 0
+    for i, f, corners, lg in res:
+        assert bool(got["found"][i] == 1) == f, i
+        if not f:
+            assert (got["digits"][i] == 0).all()
+            continue
+        nfound += 1
+        assert np.array_equal(got["corners"][i], corners), i
+        assert np.abs(got["logits"][i] - lg).max() < LOGIT_TOL, i
+        assert np.array_equal(got["digits"][i], lg.argmax(1).astype(np.uint8)), i
+    assert nfound == n - 3
 
 
 @pytest.mark.parametrize("hw", [(1080, 1920), (750, 1000), (300, 500), (96, 48)])
