@@ -107,7 +107,12 @@ SVB_CHD F2 f2add(F2 a, F2 b) {
     const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
     return F2{r.x, r.y};
 }
+// multiply, round, then add (OpenCV's scalar tail): spelled with the SCALAR intrinsics on purpose — ptxas 12.9 contracts
+// mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 despite the explicit rounding modifiers (seen in SASS; it cost 4 cells in
+// 82,944 one pixel each against the oracle), whereas mul.rn.f32 + add.rn.f32 are never fused.
+SVB_CHD F2 f2mul_add(float k, F2 a, F2 c) { return F2{__fadd_rn(c.x, __fmul_rn(k, a.x)), __fadd_rn(c.y, __fmul_rn(k, a.y))}; }
 #else
+SVB_CHD F2 f2mul_add(float k, F2 a, F2 c) { return F2{c.x + k * a.x, c.y + k * a.y}; }
 SVB_CHD F2 f2mul(float k, F2 a) { return F2{k * a.x, k * a.y}; }
 SVB_CHD F2 f2fma(float k, F2 a, F2 c) { return F2{fmaf(k, a.x, c.x), fmaf(k, a.y, c.y)}; }
 SVB_CHD F2 f2add(F2 a, F2 b) { return F2{a.x + b.x, a.y + b.y}; }
@@ -507,7 +512,7 @@ SVB_CHD void phase_colpass(Smem &s, int tid, uint8_t *thr /* optional, global */
 #pragma unroll
         for (int j = 1; j <= 5; ++j) {
             const F2 sum = f2add(r[o + 5 + j], r[o + 5 - j]);
-            acc = body ? f2fma(k[5 + j], sum, acc) : f2add(acc, f2mul(k[5 + j], sum));
+            acc = body ? f2fma(k[5 + j], sum, acc) : f2mul_add(k[5 + j], sum, acc);
         }
         const int y = y0 + o, i0 = y * CELL + x;
         int m0 = rint_pos(acc.x), m1 = rint_pos(acc.y);

@@ -198,6 +198,24 @@ def test_cell_prep_unit_vectors(scanner, golden):
     assert np.array_equal(thr.cpu().numpy(), u["ref_cells_thresh"])
 
 
+def test_cell_prep_tail_columns_regression(scanner, oracle):
+    """Columns 24..27 of a cell take OpenCV's scalar tail (multiply, round, add).  ptxas contracted the packed form of that
+    into FFMA2 and 4 cells of a 1024-frame batch lost one pixel each (round 2): those four cells, and 60,000 textured cells
+    (a rounding tie in the tail is a 1-in-20,000-cells event)."""
+    import os
+
+    reg = np.load(os.path.join(os.path.dirname(__file__), "golden", "tail_cells.npz"))["cells"]
+    rng = np.random.default_rng(5)
+    n = 60000
+    tex = (rng.normal(150, 25, (n, 1, 1)) + rng.normal(0, 1, (n, 28, 28)) * rng.uniform(2, 30, (n, 1, 1))
+           + np.linspace(-20, 20, 28)[None, None, :] * rng.normal(0, 1, (n, 1, 1)))
+    cells = np.concatenate([reg, np.clip(tex, 0, 255).astype(np.uint8)])
+    thr, pm1 = scanner.cell_prep(_t(cells))
+    ink = oracle.cell_prep(cells)
+    assert np.array_equal(thr.cpu().numpy(), 255 - ink)
+    assert np.array_equal(pm1.cpu().numpy(), np.where(ink == 255, 1.0, -1.0).astype(np.float32))
+
+
 def test_cells_from_frames_vs_oracle_1080p(scanner, oracle):
     imgs, _, _ = _frames(4, 1080, 1920, 7700)
     res = [oracle.scan_frame(im) for im in imgs]
