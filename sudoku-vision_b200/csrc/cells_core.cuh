@@ -288,18 +288,29 @@ SVB_CHD uint32_t sample_bgr_checked(const uint8_t *frame, int h, int w, int ix, 
 // footprint fully inside the frame: the two pixels of a footprint row are 6 contiguous bytes = three aligned words +
 // funnel shifts; (sum w p + 2^14) >> 15 == (S + 512) >> 10 with S = cy0 (cx0 p00 + cx1 p01) + cy1 (cx0 p10 + cx1 p11).
 // fb = the frame's address rounded down to a word, mis = the bytes that took (0..3): all offsets stay 32-bit.
-SVB_CHD uint32_t sample_gray_inside(const uint32_t *fb, uint32_t mis, int w, int ix, int iy, int ax, int ay) {
-    const uint32_t a0 = (uint32_t)(iy * w + ix) * 3u + mis;
+// Split into the six loads and the arithmetic so that a thread can have the loads of two samples in flight at once.
+struct Foot {
+    uint32_t w[2][3], sh;  // three words per footprint row; both rows share the shift when the row pitch is a multiple of 4
+    uint32_t sh1;
+};
+SVB_CHD Foot foot_load(const uint32_t *fb, uint32_t mis, int w, int ix, int iy) {
+    Foot f;
+    const uint32_t a0 = (uint32_t)(iy * w + ix) * 3u + mis, a1 = a0 + (uint32_t)(w * 3);
+    const uint32_t *p0 = fb + (a0 >> 2), *p1 = fb + (a1 >> 2);
+    f.sh = (a0 & 3u) * 8u;
+    f.sh1 = (a1 & 3u) * 8u;
+    f.w[0][0] = ldg32(p0); f.w[0][1] = ldg32(p0 + 1); f.w[0][2] = ldg32(p0 + 2);
+    f.w[1][0] = ldg32(p1); f.w[1][1] = ldg32(p1 + 1); f.w[1][2] = ldg32(p1 + 2);
+    return f;
+}
+SVB_CHD uint32_t foot_gray(const Foot &f, int ax, int ay) {
     const uint32_t cx = (uint32_t)(32 - ax) | ((uint32_t)ax << 16);
     uint32_t rB[2], rG[2], rR[2];
     for (int r = 0; r < 2; ++r) {
-        const uint32_t a = a0 + (uint32_t)(r * w * 3);
-        const uint32_t *p = fb + (a >> 2);
-        const uint32_t sh = (a & 3u) * 8u;
-        const uint32_t w0 = ldg32(p), w1 = ldg32(p + 1), w2 = ldg32(p + 2);
-        const uint32_t lo = funnel_r(w0, w1, sh), hi = funnel_r(w1, w2, sh);  // B0 G0 R0 B1 | G1 R1 . .
-        const uint32_t bg = byte_perm(lo, hi, 0x4130);                         // B0 B1 G0 G1
-        const uint32_t rr = byte_perm(lo, hi, 0x0052);                         // R0 R1 . .
+        const uint32_t sh = r ? f.sh1 : f.sh;
+        const uint32_t lo = funnel_r(f.w[r][0], f.w[r][1], sh), hi = funnel_r(f.w[r][1], f.w[r][2], sh);  // B0 G0 R0 B1 | G1 R1 . .
+        const uint32_t bg = byte_perm(lo, hi, 0x4130);                                                    // B0 B1 G0 G1
+        const uint32_t rr = byte_perm(lo, hi, 0x0052);                                                    // R0 R1 . .
         rB[r] = dp2a_lo(cx, bg, 0u);
         rG[r] = dp2a_hi(cx, bg, 0u);
         rR[r] = dp2a_lo(cx, rr, 0u);
@@ -307,6 +318,9 @@ SVB_CHD uint32_t sample_gray_inside(const uint32_t *fb, uint32_t mis, int w, int
     const uint32_t cy0 = (uint32_t)(32 - ay), cy1 = (uint32_t)ay;
     return gray_of((cy0 * rB[0] + cy1 * rB[1] + 512u) >> 10, (cy0 * rG[0] + cy1 * rG[1] + 512u) >> 10,
                    (cy0 * rR[0] + cy1 * rR[1] + 512u) >> 10);
+}
+SVB_CHD uint32_t sample_gray_inside(const uint32_t *fb, uint32_t mis, int w, int ix, int iy, int ax, int ay) {
+    return foot_gray(foot_load(fb, mis, w, ix, iy), ax, ay);
 }
 // cv2's own evaluation order of the map at board pixel (x, y): per block of 64 destination columns
 SVB_CHD void map_exact(const double *mi, int x, int y, int &X, int &Y) {
@@ -322,55 +336,90 @@ SVB_CHD void map_exact(const double *mi, int x, int y, int &X, int &Y) {
     Y = (fy != fy) ? (int)0x80000000 : d2i_rn(fy);
 }
 
-// thread -> crop column xx = tid % 40 (its x terms are hoisted) and rows tid / 40, +3, +6, ...
-SVB_CHD void phase_sample(Smem &s, int tid, const uint8_t *frame, int h, int w, const double *mi, int cell_r, int cell_c) {
-    if (tid >= 3 * CROP) return;
-    const int xx = tid % CROP, rg = tid / CROP;
-    const int x = cell_c * (BOARD / 9) + 5 + xx;
-    const double SC = (double)(32 << QSH);
-    const double xd = (double)x;
-    const double nx0 = dfma(dmul(mi[0], SC), xd, dmul(mi[2], SC)), ny0 = dfma(dmul(mi[3], SC), xd, dmul(mi[5], SC));
-    const double d0 = dfma(mi[6], xd, mi[8]);
-    const double nxy = dmul(mi[1], SC), nyy = dmul(mi[4], SC), dy = mi[7];
+// the column terms of a thread's fast map evaluation (its board column x is fixed)
+struct MapCol {
+    double nx0, ny0, d0, nxy, nyy, dy;
+    bool finite;
+};
+SVB_CHD MapCol map_col(const double *mi, int x) {
+    MapCol m;
+    const double SC = (double)(32 << QSH), xd = (double)x;
+    m.nx0 = dfma(dmul(mi[0], SC), xd, dmul(mi[2], SC));
+    m.ny0 = dfma(dmul(mi[3], SC), xd, dmul(mi[5], SC));
+    m.d0 = dfma(mi[6], xd, mi[8]);
+    m.nxy = dmul(mi[1], SC);
+    m.nyy = dmul(mi[4], SC);
+    m.dy = mi[7];
     // a non-finite matrix entry (degenerate quadrilateral) must take cv2's own path: cvt.rni of a NaN would look like 0
     double fin = 0.0;
     for (int i = 0; i < 9; ++i) fin = dfma(mi[i], 0.0, fin);
-    const bool finite = fin == 0.0;
+    m.finite = fin == 0.0;
+    return m;
+}
+// source coordinate of board pixel (x, y) in 1/32 px: FMAs + a Newton-refined fp32 reciprocal in 1/(32 * 2^13) px fixed point
+SVB_CHD void map_fast(const MapCol &m, const double *mi, int x, int y, int &X, int &Y) {
+    const double yd = (double)y;  // small integer: exact
+    const double D = dfma(m.dy, yd, m.d0);
+    const float df = (float)D;
+    const float r0 = rcp_approx(df);
+    const double rd = (double)r0;
+    const double r = dfma(rd, dfma(-D, rd, 1.0), rd);  // one Newton step: relative error ~ 1e-14
+    const int Qx = d2i_rn(dmul(dfma(m.nxy, yd, m.nx0), r)), Qy = d2i_rn(dmul(dfma(m.nyy, yd, m.ny0), r));
+    const float adf = fabsf(df);
+    // fast result is trusted unless: |D| leaves the range where the fp32 seed is a normal number, a coordinate is beyond
+    // +-2^30 / 2^13 (saturation), or a fraction lies within 2 units (2^-12 of 1/32 px) of the rounding tie
+    const bool ok = m.finite && adf > 1e-30f && adf < 1e30f && (unsigned)(Qx + (1 << 30)) < (1u << 31) && (unsigned)(Qy + (1 << 30)) < (1u << 31) &&
+                    (unsigned)((Qx & ((1 << QSH) - 1)) - ((1 << (QSH - 1)) - 2)) > 4u &&
+                    (unsigned)((Qy & ((1 << QSH) - 1)) - ((1 << (QSH - 1)) - 2)) > 4u;
+    if (ok) {
+        X = (Qx + (1 << (QSH - 1))) >> QSH;
+        Y = (Qy + (1 << (QSH - 1))) >> QSH;
+    } else {
+        map_exact(mi, x, y, X, Y);
+    }
+}
+SVB_CHD uint32_t sample_gray_any(const uint8_t *frame, const uint32_t *fb, uint32_t mis, int h, int w, int X, int Y) {
+    const int ix = X >> 5, iy = Y >> 5, ax = X & 31, ay = Y & 31;
+    // footprint inside the frame with a whole row below it, so the 12-byte windows stay inside the frame (the last row
+    // pair of a frame takes the checked form)
+    if ((unsigned)ix < (unsigned)(w - 1) && (unsigned)iy < (unsigned)(h - 2)) return sample_gray_inside(fb, mis, w, ix, iy, ax, ay);
+    const uint32_t v = sample_bgr_checked(frame, h, w, ix, iy, ax, ay);
+    return gray_of(v & 0xff, (v >> 8) & 0xff, (v >> 16) & 0xff);
+}
+
+// thread -> crop column xx = tid % 40 (its x terms are hoisted) and rows tid / 40, +3, +6, ...; two rows per iteration, so
+// that the twelve loads of two footprints are in flight together (the loop was waiting on one footprint at a time: a third
+// of K4's stall samples, ncu round 2)
+SVB_CHD void phase_sample(Smem &s, int tid, const uint8_t *frame, int h, int w, const double *mi, int cell_r, int cell_c) {
+    if (tid >= 3 * CROP) return;
+    const int xx = tid % CROP, rg = tid / CROP;
+    const int x = cell_c * (BOARD / 9) + 5 + xx, ybase = cell_r * (BOARD / 9) + 5;
+    const MapCol m = map_col(mi, x);
     const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(frame) & 3u);
     const uint32_t *fb = reinterpret_cast<const uint32_t *>(frame - mis);
-    double yd = (double)(cell_r * (BOARD / 9) + 5 + rg);
-    for (int yy = rg; yy < CROP; yy += 3, yd += 3.0) {  // small integers: the increment is exact
-        const int y = cell_r * (BOARD / 9) + 5 + yy;
-        const double D = dfma(dy, yd, d0);
-        const float df = (float)D;
-        const float r0 = rcp_approx(df);
-        const double rd = (double)r0;
-        const double r = dfma(rd, dfma(-D, rd, 1.0), rd);  // one Newton step: relative error ~ 1e-14
-        const int Qx = d2i_rn(dmul(dfma(nxy, yd, nx0), r)), Qy = d2i_rn(dmul(dfma(nyy, yd, ny0), r));
-        const float adf = fabsf(df);
-        // fast result is trusted unless: |D| leaves the range where the fp32 seed is a normal number, a coordinate is beyond
-        // +-2^30 / 2^13 (saturation), or a fraction lies within 2 units (2^-12 of 1/32 px) of the rounding tie
-        const bool ok = finite && adf > 1e-30f && adf < 1e30f && (unsigned)(Qx + (1 << 30)) < (1u << 31) && (unsigned)(Qy + (1 << 30)) < (1u << 31) &&
-                        (unsigned)((Qx & ((1 << QSH) - 1)) - ((1 << (QSH - 1)) - 2)) > 4u &&
-                        (unsigned)((Qy & ((1 << QSH) - 1)) - ((1 << (QSH - 1)) - 2)) > 4u;
-        int X, Y;
-        if (ok) {
-            X = (Qx + (1 << (QSH - 1))) >> QSH;
-            Y = (Qy + (1 << (QSH - 1))) >> QSH;
+    for (int yy = rg; yy < CROP; yy += 6) {
+        const bool two = yy + 3 < CROP;
+        int X0, Y0, X1, Y1;
+        map_fast(m, mi, x, ybase + yy, X0, Y0);
+        if (two) {
+            map_fast(m, mi, x, ybase + yy + 3, X1, Y1);
         } else {
-            map_exact(mi, x, y, X, Y);
+            X1 = X0;
+            Y1 = Y0;
         }
-        const int ix = X >> 5, iy = Y >> 5, ax = X & 31, ay = Y & 31;
-        uint32_t gv;
-        // footprint inside the frame with a whole row below it, so the 12-byte windows stay inside the frame (the last row
-        // pair of a frame takes the checked form)
-        if ((unsigned)ix < (unsigned)(w - 1) && (unsigned)iy < (unsigned)(h - 2)) {
-            gv = sample_gray_inside(fb, mis, w, ix, iy, ax, ay);
+        const int ix0 = X0 >> 5, iy0 = Y0 >> 5, ix1 = X1 >> 5, iy1 = Y1 >> 5;
+        uint32_t g0, g1;
+        if ((unsigned)ix0 < (unsigned)(w - 1) && (unsigned)iy0 < (unsigned)(h - 2) && (unsigned)ix1 < (unsigned)(w - 1) &&
+            (unsigned)iy1 < (unsigned)(h - 2)) {
+            const Foot f0 = foot_load(fb, mis, w, ix0, iy0), f1 = foot_load(fb, mis, w, ix1, iy1);
+            g0 = foot_gray(f0, X0 & 31, Y0 & 31);
+            g1 = foot_gray(f1, X1 & 31, Y1 & 31);
         } else {
-            const uint32_t v = sample_bgr_checked(frame, h, w, ix, iy, ax, ay);
-            gv = gray_of(v & 0xff, (v >> 8) & 0xff, (v >> 16) & 0xff);
+            g0 = sample_gray_any(frame, fb, mis, h, w, X0, Y0);
+            g1 = two ? sample_gray_any(frame, fb, mis, h, w, X1, Y1) : g0;
         }
-        s.u.a.crop[yy * CROP + xx] = (uint8_t)gv;
+        s.u.a.crop[yy * CROP + xx] = (uint8_t)g0;
+        if (two) s.u.a.crop[(yy + 3) * CROP + xx] = (uint8_t)g1;
     }
 }
 

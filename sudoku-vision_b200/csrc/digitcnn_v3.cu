@@ -5,9 +5,8 @@
 //   conv3x3_kernel   direct convolution, one CTA per (cell, 16 output channels): the cell's whole input
 //                    (all channels, zero-padded) is staged in shared memory once and reused for 16 x 9 x Cin
 //                    multiply-adds per output pixel; stride 1 or 2; optional ReLU
-//   conv1x1s2_kernel the strided 1x1 projection shortcut of layers 2 and 4
-//   se_kernel        squeeze-excite gate: global average -> fc (c -> c/4) -> ReLU -> fc -> sigmoid
-//   combine_kernel   out = ReLU(conv2_out * gate + shortcut)
+//   se_combine_kernel squeeze-excite gate (global average -> fc c -> c/4 -> ReLU -> fc -> sigmoid), the shortcut (identity
+//                    or the strided 1x1 projection of layers 2 and 4) and out = ReLU(conv2_out * gate + shortcut), one pass
 //   head_kernel      global average pool -> fc 128 -> 10 (+ softmax-max / argmax epilogue)
 // Activations live in the context's arena, processed in chunks of cells so the footprint stays bounded.
 // CUDA cores, fp32: parity first (logits within 1e-3 of PyTorch-CPU); the tcgen05 version follows the
@@ -70,54 +69,33 @@ conv3x3_kernel(const float *__restrict__ in, const float *__restrict__ w, const 
     }
 }
 
-// 1x1 convolution, stride 2, no padding (+ folded BN): out[n][co][y][x] = b[co] + sum_ci w[co][ci] * in[n][ci][2y][2x].
-// One CTA per cell: the subsampled input [cin][hout^2] and the transposed weights [cin][cout] sit in shared memory;
-// every thread produces 4 output channels of one pixel per step.
+// The tail of a residual block in ONE pass per cell (ml/model_v3.py:20-37, 71-77): squeeze-excite gate of conv2's output y
+//   gate[c] = sigmoid(W2 relu(W1 mean_hw(y)))
+// the shortcut — identity, or the strided 1x1 projection (+ folded BN) sc[co][p] = b[co] + sum_ci w[co][ci] x[ci][2y][2x] —
+// and out = relu(y * gate + shortcut).  One CTA per cell: y is read from HBM once for the means (one warp per channel,
+// coalesced, shuffle reduction in a fixed order) and again, out of L2, for the combine; x once; out written once.  Round 1
+// ran this as three kernels (se, conv1x1s2, combine: 4-6 passes over the activations, a third of the forward pass).
+// Every sum keeps the order of those kernels, so the results are bit-identical to them.
 __global__ void __launch_bounds__(256)
-conv1x1s2_kernel(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ bias,
-                 float *__restrict__ out, int cin, int cout, int hin) {
-    extern __shared__ float smem[];
-    const int hout = (hin - 1) / 2 + 1, hw = hout * hout;
-    float *s_in = smem;             // [cin][hw]
-    float *s_w = smem + cin * hw;   // [cin][cout]
-    const int cell = blockIdx.x, tid = threadIdx.x;
-    const float *src = in + (long long)cell * cin * hin * hin;
-    for (int i = tid; i < cin * hw; i += 256) {
-        const int ci = i / hw, p = i - ci * hw, y = p / hout, x = p - y * hout;
-        s_in[i] = src[(ci * hin + 2 * y) * hin + 2 * x];
-    }
-    for (int i = tid; i < cin * cout; i += 256) {
-        const int co = i / cin, ci = i - co * cin;
-        s_w[ci * cout + co] = w[i];
-    }
-    __syncthreads();
-    float *dst = out + (long long)cell * cout * hw;
-    for (int o = tid; o < (cout / 4) * hw; o += 256) {
-        const int cg = o / hw, p = o - cg * hw;
-        float4 acc = *reinterpret_cast<const float4 *>(bias + cg * 4);
-        for (int ci = 0; ci < cin; ++ci) {
-            const float v = s_in[ci * hw + p];
-            const float4 ww = *reinterpret_cast<const float4 *>(s_w + ci * cout + cg * 4);
-            acc.x = fmaf(ww.x, v, acc.x);
-            acc.y = fmaf(ww.y, v, acc.y);
-            acc.z = fmaf(ww.z, v, acc.z);
-            acc.w = fmaf(ww.w, v, acc.w);
-        }
-        dst[(cg * 4 + 0) * hw + p] = acc.x;
-        dst[(cg * 4 + 1) * hw + p] = acc.y;
-        dst[(cg * 4 + 2) * hw + p] = acc.z;
-        dst[(cg * 4 + 3) * hw + p] = acc.w;
-    }
-}
-
-// squeeze-excite gate per cell: gate[c] = sigmoid(W2 relu(W1 mean_hw(x)))   (ml/model_v3.py:20-37).
-// One warp per channel for the spatial mean (coalesced reads, shuffle reduction in a fixed order).
-__global__ void __launch_bounds__(256)
-se_kernel(const float *__restrict__ x, const float *__restrict__ w1, const float *__restrict__ w2, float *__restrict__ gate, int c,
-          int hw) {
-    __shared__ float mean[128], hid[32];
+se_combine_kernel(const float *__restrict__ y, const float *__restrict__ xin, const float *__restrict__ w1, const float *__restrict__ w2,
+                  const float *__restrict__ scw, const float *__restrict__ scb, float *__restrict__ out, int c, int hw, int cin, int hin) {
+    extern __shared__ float smem[];  // projection only: subsampled input [cin][hw], transposed weights [cin][c]
+    __shared__ float mean[128], hid[32], gate[128];
     const int cell = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const float *src = x + (long long)cell * c * hw;
+    const float *src = y + (long long)cell * c * hw;
+    float *s_in = smem, *s_w = smem + cin * hw;
+    if (scw) {
+        const int hout = (hin - 1) / 2 + 1;
+        const float *xs = xin + (long long)cell * cin * hin * hin;
+        for (int i = tid; i < cin * hw; i += 256) {
+            const int ci = i / hw, p = i - ci * hw, yy = p / hout, xx = p - yy * hout;
+            s_in[i] = xs[(ci * hin + 2 * yy) * hin + 2 * xx];
+        }
+        for (int i = tid; i < cin * c; i += 256) {
+            const int co = i / cin, ci = i - co * cin;
+            s_w[ci * c + co] = scw[i];
+        }
+    }
     for (int ch = warp; ch < c; ch += 8) {
         float s = 0.f;
         for (int i = lane; i < hw; i += 32) s += src[(long long)ch * hw + i];
@@ -133,19 +111,49 @@ se_kernel(const float *__restrict__ x, const float *__restrict__ w1, const float
         hid[tid] = fmaxf(s, 0.f);
     }
     __syncthreads();
-    for (int ch = tid; ch < c; ch += 256) {
+    if (tid < c) {
         float s = 0.f;
-        for (int k = 0; k < cr; ++k) s = fmaf(w2[ch * cr + k], hid[k], s);
-        gate[(long long)cell * c + ch] = 1.0f / (1.0f + expf(-s));
+        for (int k = 0; k < cr; ++k) s = fmaf(w2[tid * cr + k], hid[k], s);
+        gate[tid] = 1.0f / (1.0f + expf(-s));
     }
-}
-
-// out = relu(y * gate + shortcut)
-__global__ void combine_kernel(const float *__restrict__ y, const float *__restrict__ gate, const float *__restrict__ shortcut,
-                               float *__restrict__ out, int hw, long long total) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    out[i] = fmaxf(fmaf(y[i], gate[i / hw], shortcut[i]), 0.f);
+    __syncthreads();
+    float *dst = out + (long long)cell * c * hw;
+    if (!scw) {  // identity shortcut: same shape as y
+        const float *xs = xin + (long long)cell * c * hw;
+        if ((hw & 3) == 0) {
+            const int n4 = c * hw / 4, hw4 = hw / 4;
+            for (int i = tid; i < n4; i += 256) {
+                const float4 a = reinterpret_cast<const float4 *>(src)[i], b = reinterpret_cast<const float4 *>(xs)[i];
+                const float g = gate[i / hw4];
+                float4 o;
+                o.x = fmaxf(fmaf(a.x, g, b.x), 0.f);
+                o.y = fmaxf(fmaf(a.y, g, b.y), 0.f);
+                o.z = fmaxf(fmaf(a.z, g, b.z), 0.f);
+                o.w = fmaxf(fmaf(a.w, g, b.w), 0.f);
+                reinterpret_cast<float4 *>(dst)[i] = o;
+            }
+        } else {
+            for (int i = tid; i < c * hw; i += 256) dst[i] = fmaxf(fmaf(src[i], gate[i / hw], xs[i]), 0.f);
+        }
+        return;
+    }
+    for (int o = tid; o < (c / 4) * hw; o += 256) {  // 4 output channels of one pixel per step
+        const int cg = o / hw, p = o - cg * hw;
+        float4 acc = *reinterpret_cast<const float4 *>(scb + cg * 4);
+        for (int ci = 0; ci < cin; ++ci) {
+            const float v = s_in[ci * hw + p];
+            const float4 ww = *reinterpret_cast<const float4 *>(s_w + ci * c + cg * 4);
+            acc.x = fmaf(ww.x, v, acc.x);
+            acc.y = fmaf(ww.y, v, acc.y);
+            acc.z = fmaf(ww.z, v, acc.z);
+            acc.w = fmaf(ww.w, v, acc.w);
+        }
+        const int i0 = (cg * 4) * hw + p;
+        dst[i0] = fmaxf(fmaf(src[i0], gate[cg * 4 + 0], acc.x), 0.f);
+        dst[i0 + hw] = fmaxf(fmaf(src[i0 + hw], gate[cg * 4 + 1], acc.y), 0.f);
+        dst[i0 + 2 * hw] = fmaxf(fmaf(src[i0 + 2 * hw], gate[cg * 4 + 2], acc.z), 0.f);
+        dst[i0 + 3 * hw] = fmaxf(fmaf(src[i0 + 3 * hw], gate[cg * 4 + 3], acc.w), 0.f);
+    }
 }
 
 // global average pool (7x7) -> fc -> logits (+ argmax / softmax-max)
@@ -313,8 +321,8 @@ int launch_digitcnn_v3(svb_ctx *ctx, const float *x, long long n, float *logits,
     const long long CHUNK = (long long)ctx->sm_count * 16;
     const size_t plane = (size_t)32 * 784;
     const size_t buf = (size_t)CHUNK * plane;
-    if (ctx->arena[AR_CNN].reserve((3 * buf + (size_t)CHUNK * 128) * sizeof(float)) != SVB_OK) return SVB_ERR_CUDA;
-    float *A = (float *)ctx->arena[AR_CNN].ptr, *B = A + buf, *Cb = B + buf, *gate = Cb + buf;
+    if (ctx->arena[AR_CNN].reserve(3 * buf * sizeof(float)) != SVB_OK) return SVB_ERR_CUDA;
+    float *A = (float *)ctx->arena[AR_CNN].ptr, *B = A + buf, *Cb = B + buf;
     SVB_CUDA_OK(cudaFuncSetAttribute(conv3x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     SVB_CUDA_OK(cudaFuncSetAttribute(conv3x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     int rc = SVB_OK;
@@ -336,20 +344,13 @@ int launch_digitcnn_v3(svb_ctx *ctx, const float *x, long long n, float *logits,
         const int hout = (hin - 1) / stride + 1, hw = hout * hout;
         conv(X, wi, T1, cin, cout, hin, stride, 1, m);           // conv1 + bn1 + relu
         conv(T1, wi + 2, T2, cout, cout, hout, 1, 0, m);         // conv2 + bn2
-        se_kernel<<<(unsigned)m, 256, 0, st>>>(T2, s->p[wi + 4], s->p[wi + 5], gate, cout, hw);
-        if (!rc) rc = check_launch(ctx, "k6::se_kernel");
-        const float *shortcut = X;
-        if (sc_wi >= 0) {  // projection shortcut into T1 (conv1's output is no longer needed)
-            const size_t sm1 = ((size_t)cin * hw + (size_t)cin * cout) * sizeof(float);
-            conv1x1s2_kernel<<<(unsigned)m, 256, sm1, st>>>(X, s->p[sc_wi], s->p[sc_wi + 1], T1, cin, cout, hin);
-            if (!rc) rc = check_launch(ctx, "k6::conv1x1s2_kernel");
-            shortcut = T1;
-        }
-        const long long tot = (long long)m * cout * hw;
-        float *dst = (sc_wi >= 0) ? X : T1;  // never alias an input that is still being read elementwise-shifted
-        combine_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(T2, gate, shortcut, dst, hw, tot);
-        if (!rc) rc = check_launch(ctx, "k6::combine_kernel");
-        if (dst != X) { float *t = X; X = T1; T1 = t; }
+        // SE gate + shortcut + residual + ReLU into T1 (conv1's output is no longer needed); X and T1 swap roles
+        const bool proj = sc_wi >= 0;
+        const size_t sm1 = proj ? ((size_t)cin * hw + (size_t)cin * cout) * sizeof(float) : 0;
+        se_combine_kernel<<<(unsigned)m, 256, sm1, st>>>(T2, X, s->p[wi + 4], s->p[wi + 5], proj ? s->p[sc_wi] : nullptr,
+                                                        proj ? s->p[sc_wi + 1] : nullptr, T1, cout, hw, cin, hin);
+        if (!rc) rc = check_launch(ctx, "k6::se_combine_kernel");
+        { float *t = X; X = T1; T1 = t; }
     };
     for (long long c0 = 0; c0 < n && !rc; c0 += CHUNK) {
         const int m = (int)((n - c0 < CHUNK) ? n - c0 : CHUNK);

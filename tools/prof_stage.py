@@ -9,6 +9,10 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "sudoku-vision_b200"))
 import numpy as np
 import torch
+import svb200._lib as _L
+
+if os.environ.get("SVB_LIB"):  # A/B of two builds (tools/build_variant.py); a tool-side override, the product loader has none
+    _L.LIB_PATH = os.path.abspath(os.environ["SVB_LIB"])
 from svb200 import Scanner, load_digitcnn_weights
 from svb200 import frames as F
 
