@@ -11,6 +11,8 @@
 // Activations live in the context's arena, processed in chunks of cells so the footprint stays bounded.
 // CUDA cores, fp32: parity first (logits within 1e-3 of PyTorch-CPU); the tcgen05 version follows the
 // DigitCNN kernels' pattern (digitcnn_tc.cu) and is the next step for this row.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace svb {
@@ -72,88 +74,146 @@ conv3x3_kernel(const float *__restrict__ in, const float *__restrict__ w, const 
 // The tail of a residual block in ONE pass per cell (ml/model_v3.py:20-37, 71-77): squeeze-excite gate of conv2's output y
 //   gate[c] = sigmoid(W2 relu(W1 mean_hw(y)))
 // the shortcut — identity, or the strided 1x1 projection (+ folded BN) sc[co][p] = b[co] + sum_ci w[co][ci] x[ci][2y][2x] —
-// and out = relu(y * gate + shortcut).  One CTA per cell: y is read from HBM once for the means (one warp per channel,
-// coalesced, shuffle reduction in a fixed order) and again, out of L2, for the combine; x once; out written once.  Round 1
-// ran this as three kernels (se, conv1x1s2, combine: 4-6 passes over the activations, a third of the forward pass).
-// Every sum keeps the order of those kernels, so the results are bit-identical to them.
-__global__ void __launch_bounds__(256)
+// and out = relu(y * gate + shortcut).  One CTA of NW warps per cell; a warp owns C / NW channels and a lane the pixels
+// lane, lane + 32, ... of each, so y is read from HBM exactly once into registers (coalesced), reduced by shuffles for the
+// means and reused for the combine; x is read once, out written once.  Round 1 ran this as three kernels (se, conv1x1s2,
+// combine: 4-6 passes over the activations, a third of the forward pass).  Every sum keeps the order of those kernels
+// (lane-strided partial sums + xor-shuffle tree; projection: bias, then input channels in ascending order), so the results
+// are bit-identical to them.
+template <int C, int HW, int NW, int CIN /* 0: identity shortcut */>
+struct SeGeo {
+    static constexpr int CR = C / 4;
+    static constexpr size_t SMEM = ((size_t)2 * C * CR + (CIN ? (size_t)C * CIN + (size_t)CIN * HW : 0)) * sizeof(float);
+};
+// Persistent CTAs (the weights are staged in shared memory once, the FC matrices transposed so that the one-thread-per-output
+// dot products read conflict-free; with one CTA per cell every cell paid L2 latency for them again: 256 us for layer 2).
+template <int C, int HW, int NW, int CIN>
+__global__ void __launch_bounds__(32 * NW)
 se_combine_kernel(const float *__restrict__ y, const float *__restrict__ xin, const float *__restrict__ w1, const float *__restrict__ w2,
-                  const float *__restrict__ scw, const float *__restrict__ scb, float *__restrict__ out, int c, int hw, int cin, int hin) {
-    extern __shared__ float smem[];  // projection only: subsampled input [cin][hw], transposed weights [cin][c]
-    __shared__ float mean[128], hid[32], gate[128];
-    const int cell = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const float *src = y + (long long)cell * c * hw;
-    float *s_in = smem, *s_w = smem + cin * hw;
-    if (scw) {
-        const int hout = (hin - 1) / 2 + 1;
-        const float *xs = xin + (long long)cell * cin * hin * hin;
-        for (int i = tid; i < cin * hw; i += 256) {
-            const int ci = i / hw, p = i - ci * hw, yy = p / hout, xx = p - yy * hout;
-            s_in[i] = xs[(ci * hin + 2 * yy) * hin + 2 * xx];
-        }
-        for (int i = tid; i < cin * c; i += 256) {
-            const int co = i / cin, ci = i - co * cin;
-            s_w[ci * c + co] = scw[i];
-        }
+                  const float *__restrict__ scw, const float *__restrict__ scb, float *__restrict__ out, int n_cells) {
+    constexpr int CPW = C / NW, VPL = (HW + 31) / 32, CR = C / 4, NT = 32 * NW;
+    constexpr bool PROJ = CIN > 0;
+    static_assert(C % NW == 0 && CR <= NT && C <= NT, "se_combine geometry");
+    extern __shared__ float dsm[];
+    __shared__ float mean[C], hid[CR], gate[C];
+    float *w1t = dsm;                            // [C][CR]:  w1t[k * CR + j] = w1[j * C + k]
+    float *w2t = w1t + C * CR;                   // [CR][C]:  w2t[k * C + ch] = w2[ch * CR + k]
+    float *s_w = w2t + CR * C;                   // projection weights [C][CIN]
+    float *s_in = s_w + (PROJ ? C * CIN : 0);    // projection: the input subsampled to the output grid, [CIN][HW]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < C * CR; i += NT) {
+        const int j = i / C, k = i - j * C;      // w1 is [CR][C]
+        w1t[k * CR + j] = w1[i];
+        const int ch = i / CR, kk = i - ch * CR;  // w2 is [C][CR]
+        w2t[kk * C + ch] = w2[i];
     }
-    for (int ch = warp; ch < c; ch += 8) {
-        float s = 0.f;
-        for (int i = lane; i < hw; i += 32) s += src[(long long)ch * hw + i];
+    if constexpr (PROJ)
+        for (int i = tid; i < C * CIN; i += NT) s_w[i] = scw[i];
+    for (int cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
+        const float *src = y + (long long)cell * C * HW;
+        float v[CPW][VPL];
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-        if (lane == 0) mean[ch] = s / (float)hw;
-    }
-    __syncthreads();
-    const int cr = c / 4;
-    if (tid < cr) {
-        float s = 0.f;
-        for (int k = 0; k < c; ++k) s = fmaf(w1[tid * c + k], mean[k], s);
-        hid[tid] = fmaxf(s, 0.f);
-    }
-    __syncthreads();
-    if (tid < c) {
-        float s = 0.f;
-        for (int k = 0; k < cr; ++k) s = fmaf(w2[tid * cr + k], hid[k], s);
-        gate[tid] = 1.0f / (1.0f + expf(-s));
-    }
-    __syncthreads();
-    float *dst = out + (long long)cell * c * hw;
-    if (!scw) {  // identity shortcut: same shape as y
-        const float *xs = xin + (long long)cell * c * hw;
-        if ((hw & 3) == 0) {
-            const int n4 = c * hw / 4, hw4 = hw / 4;
-            for (int i = tid; i < n4; i += 256) {
-                const float4 a = reinterpret_cast<const float4 *>(src)[i], b = reinterpret_cast<const float4 *>(xs)[i];
-                const float g = gate[i / hw4];
-                float4 o;
-                o.x = fmaxf(fmaf(a.x, g, b.x), 0.f);
-                o.y = fmaxf(fmaf(a.y, g, b.y), 0.f);
-                o.z = fmaxf(fmaf(a.z, g, b.z), 0.f);
-                o.w = fmaxf(fmaf(a.w, g, b.w), 0.f);
-                reinterpret_cast<float4 *>(dst)[i] = o;
+        for (int k = 0; k < CPW; ++k)
+#pragma unroll
+            for (int e = 0; e < VPL; ++e) {
+                const int idx = lane + 32 * e;
+                v[k][e] = (idx < HW) ? src[(warp * CPW + k) * HW + idx] : 0.f;
+            }
+        if constexpr (PROJ) {
+            constexpr int HOUT = (HW == 196) ? 14 : 7, HIN = 2 * HOUT;
+            const float *xs = xin + (long long)cell * CIN * HIN * HIN;
+            for (int i = tid; i < CIN * HW; i += NT) {
+                const int ci = i / HW, p = i - ci * HW, yy = p / HOUT, xx = p - yy * HOUT;
+                s_in[i] = xs[(ci * HIN + 2 * yy) * HIN + 2 * xx];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CPW; ++k) {
+            float s = 0.f;
+#pragma unroll
+            for (int e = 0; e < VPL; ++e)
+                if (lane + 32 * e < HW) s += v[k][e];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+            if (lane == 0) mean[warp * CPW + k] = s / (float)HW;
+        }
+        __syncthreads();  // also: the staged weights (first cell) and s_in are complete
+        if (tid < CR) {
+            float s = 0.f;
+            for (int k = 0; k < C; ++k) s = fmaf(w1t[k * CR + tid], mean[k], s);
+            hid[tid] = fmaxf(s, 0.f);
+        }
+        __syncthreads();
+        if (tid < C) {
+            float s = 0.f;
+            for (int k = 0; k < CR; ++k) s = fmaf(w2t[k * C + tid], hid[k], s);
+            gate[tid] = 1.0f / (1.0f + expf(-s));
+        }
+        __syncthreads();
+        float *dst = out + (long long)cell * C * HW;
+        if constexpr (!PROJ) {  // identity shortcut: same shape as y
+            const float *xs = xin + (long long)cell * C * HW;
+#pragma unroll
+            for (int k = 0; k < CPW; ++k) {
+                const int ch = warp * CPW + k;
+                const float g = gate[ch];
+                float xv[VPL];
+#pragma unroll
+                for (int e = 0; e < VPL; ++e) xv[e] = (lane + 32 * e < HW) ? xs[ch * HW + lane + 32 * e] : 0.f;
+#pragma unroll
+                for (int e = 0; e < VPL; ++e)
+                    if (lane + 32 * e < HW) dst[ch * HW + lane + 32 * e] = fmaxf(fmaf(v[k][e], g, xv[e]), 0.f);
             }
         } else {
-            for (int i = tid; i < c * hw; i += 256) dst[i] = fmaxf(fmaf(src[i], gate[i / hw], xs[i]), 0.f);
+            float acc[CPW][VPL];
+#pragma unroll
+            for (int k = 0; k < CPW; ++k)
+#pragma unroll
+                for (int e = 0; e < VPL; ++e) acc[k][e] = scb[warp * CPW + k];
+            for (int ci = 0; ci < CIN; ci += 4) {  // the weights of 4 input channels per (warp-uniform) 16-byte load
+                float xv[4][VPL];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int e = 0; e < VPL; ++e) xv[j][e] = (lane + 32 * e < HW) ? s_in[(ci + j) * HW + lane + 32 * e] : 0.f;
+#pragma unroll
+                for (int k = 0; k < CPW; ++k) {
+                    const float4 w = *reinterpret_cast<const float4 *>(s_w + (warp * CPW + k) * CIN + ci);
+#pragma unroll
+                    for (int e = 0; e < VPL; ++e) {
+                        float a = acc[k][e];
+                        a = fmaf(w.x, xv[0][e], a);
+                        a = fmaf(w.y, xv[1][e], a);
+                        a = fmaf(w.z, xv[2][e], a);
+                        a = fmaf(w.w, xv[3][e], a);
+                        acc[k][e] = a;
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < CPW; ++k) {
+                const int ch = warp * CPW + k;
+                const float g = gate[ch];
+#pragma unroll
+                for (int e = 0; e < VPL; ++e)
+                    if (lane + 32 * e < HW) dst[ch * HW + lane + 32 * e] = fmaxf(fmaf(v[k][e], g, acc[k][e]), 0.f);
+            }
         }
-        return;
+        __syncthreads();  // mean / hid / gate / s_in are rewritten by the next cell
     }
-    for (int o = tid; o < (c / 4) * hw; o += 256) {  // 4 output channels of one pixel per step
-        const int cg = o / hw, p = o - cg * hw;
-        float4 acc = *reinterpret_cast<const float4 *>(scb + cg * 4);
-        for (int ci = 0; ci < cin; ++ci) {
-            const float v = s_in[ci * hw + p];
-            const float4 ww = *reinterpret_cast<const float4 *>(s_w + ci * c + cg * 4);
-            acc.x = fmaf(ww.x, v, acc.x);
-            acc.y = fmaf(ww.y, v, acc.y);
-            acc.z = fmaf(ww.z, v, acc.z);
-            acc.w = fmaf(ww.w, v, acc.w);
-        }
-        const int i0 = (cg * 4) * hw + p;
-        dst[i0] = fmaxf(fmaf(src[i0], gate[cg * 4 + 0], acc.x), 0.f);
-        dst[i0 + hw] = fmaxf(fmaf(src[i0 + hw], gate[cg * 4 + 1], acc.y), 0.f);
-        dst[i0 + 2 * hw] = fmaxf(fmaf(src[i0 + 2 * hw], gate[cg * 4 + 2], acc.z), 0.f);
-        dst[i0 + 3 * hw] = fmaxf(fmaf(src[i0 + 3 * hw], gate[cg * 4 + 3], acc.w), 0.f);
-    }
+}
+
+template <int C, int HW, int NW, int CIN>
+static int launch_se_combine(svb_ctx *ctx, const float *y, const float *x, const float *f1, const float *f2, const float *pw, const float *pb,
+                             float *out, int m, cudaStream_t st) {
+    auto kern = se_combine_kernel<C, HW, NW, CIN>;
+    constexpr size_t smem = SeGeo<C, HW, NW, CIN>::SMEM;
+    SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    SVB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * NW, smem));
+    const int grid = std::min(m, ctx->sm_count * std::max(per_sm, 1));
+    kern<<<grid, 32 * NW, smem, st>>>(y, x, f1, f2, pw, pb, out, m);
+    return check_launch(ctx, "k6::se_combine_kernel");
 }
 
 // global average pool (7x7) -> fc -> logits (+ argmax / softmax-max)
@@ -345,11 +405,15 @@ int launch_digitcnn_v3(svb_ctx *ctx, const float *x, long long n, float *logits,
         conv(X, wi, T1, cin, cout, hin, stride, 1, m);           // conv1 + bn1 + relu
         conv(T1, wi + 2, T2, cout, cout, hout, 1, 0, m);         // conv2 + bn2
         // SE gate + shortcut + residual + ReLU into T1 (conv1's output is no longer needed); X and T1 swap roles
-        const bool proj = sc_wi >= 0;
-        const size_t sm1 = proj ? ((size_t)cin * hw + (size_t)cin * cout) * sizeof(float) : 0;
-        se_combine_kernel<<<(unsigned)m, 256, sm1, st>>>(T2, X, s->p[wi + 4], s->p[wi + 5], proj ? s->p[sc_wi] : nullptr,
-                                                        proj ? s->p[sc_wi + 1] : nullptr, T1, cout, hw, cin, hin);
-        if (!rc) rc = check_launch(ctx, "k6::se_combine_kernel");
+        const float *f1 = s->p[wi + 4], *f2 = s->p[wi + 5], *pw = sc_wi >= 0 ? s->p[sc_wi] : nullptr, *pb = sc_wi >= 0 ? s->p[sc_wi + 1] : nullptr;
+        int r2 = SVB_OK;
+        if (cout == 32 && hw == 784 && sc_wi < 0) r2 = launch_se_combine<32, 784, 16, 0>(ctx, T2, X, f1, f2, pw, pb, T1, m, st);
+        else if (cout == 64 && hw == 196 && sc_wi >= 0 && cin == 32) r2 = launch_se_combine<64, 196, 16, 32>(ctx, T2, X, f1, f2, pw, pb, T1, m, st);
+        else if (cout == 64 && hw == 196 && sc_wi < 0) r2 = launch_se_combine<64, 196, 8, 0>(ctx, T2, X, f1, f2, pw, pb, T1, m, st);
+        else if (cout == 128 && hw == 49 && sc_wi >= 0 && cin == 64) r2 = launch_se_combine<128, 49, 16, 64>(ctx, T2, X, f1, f2, pw, pb, T1, m, st);
+        else if (cout == 128 && hw == 49 && sc_wi < 0) r2 = launch_se_combine<128, 49, 8, 0>(ctx, T2, X, f1, f2, pw, pb, T1, m, st);
+        else { set_error("se_combine: no kernel for c=%d hw=%d", cout, hw); r2 = SVB_ERR_UNSUPPORTED; }
+        if (!rc) rc = r2;
         { float *t = X; X = T1; T1 = t; }
     };
     for (long long c0 = 0; c0 < n && !rc; c0 += CHUNK) {

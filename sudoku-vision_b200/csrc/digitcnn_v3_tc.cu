@@ -26,6 +26,9 @@ namespace k6tc {
 
 constexpr int NT = 512;
 constexpr int OFF = 8;  // zero rows before the first grid row
+#ifndef SVB_V3_ROWPAD
+#define SVB_V3_ROWPAD 0
+#endif
 
 // ---- PTX helpers (same conventions as digitcnn_tc.cu) ----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -112,7 +115,9 @@ struct Geo {
     static constexpr int CB = (H + 1) * GW;                         // rows per cell block (bottom halo shared with the next top halo)
     static constexpr int MROWS = (G - 1) * CB + (H - 1) * GW + H;   // output rows that can be valid
     static constexpr int MT = (MROWS + 127) / 128;                  // M tiles of 128 rows
-    static constexpr int ROWS = (MT * 128 + 2 * GW + 1 + OFF + 7) & ~7;  // rows of the activation buffer
+    // rows of the activation buffer; SVB_V3_ROWPAD extra rows make the K-chunk stride (LBO = ROWS * 16 B) fall on other
+    // shared-memory banks than a multiple of 128 B would
+    static constexpr int ROWS = ((MT * 128 + 2 * GW + 1 + OFF + 7) & ~7) + SVB_V3_ROWPAD;
     static constexpr int NKC = CIN / 8;                             // K chunks
     static constexpr int PARTB = NKC * ROWS * 16;                   // bytes of one fp16 part of the activations
     static constexpr int KS = CIN < 64 ? CIN : 64;                  // K of one weight slice
@@ -149,9 +154,9 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
 
     for (int i = tid; i < 2 * PARTB / 16; i += NT) reinterpret_cast<uint4 *>(sA)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < COUT; i += NT) s_bias[i] = bias[i];
-    if (tid == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
+    if (tid == 0) {  // one arrival per issuing warp (each commits its own MMAs)
+        mbar_init(&mbar[0], MT);
+        mbar_init(&mbar[1], MT);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(s_tmem, GEO::TALLOC);
@@ -175,33 +180,30 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
         for (int s = 0; s < NSLICE; ++s) load_slice(s, s);
         cp_async_wait<0>();
     }
-    // the MMAs of one weight slice (one tap x KS input channels) for every M tile of the pass
-    // The MMAs are issued by ONE thread, so the issue loop is a serial instruction stream: everything that does not
-    // depend on the slice is a compile-time constant added to two per-slice base descriptors (all shared-memory
-    // addresses are below 256 KB, so adding (byte offset >> 4) never carries out of the 14-bit start-address field).
-    auto issue_slice = [&](int s, int buf, uint32_t tacc) {
+    // the MMAs of one weight slice (one tap x KS input channels) for ONE M tile of the pass.  An issue is a serial
+    // instruction stream of ~9 instructions with an ELECT / R2UR round trip (~80 cycles per MMA measured with one issuing
+    // warp: 378 MMAs = the whole 31 k-cycle pass of the 32-channel layers, tensor pipe 15 % active), so every M tile has
+    // its own issuing warp (warps 0..MT-1): the tiles are independent accumulators, each warp commits its own MMAs.
+    // Everything that does not depend on the slice is a compile-time constant added to two per-slice base descriptors (all
+    // shared-memory addresses are below 256 KB, so adding (byte offset >> 4) never carries out of the 14-bit field).
+    auto issue_slice = [&](int s, int buf, uint32_t tacc, int tile) {
         const int t = s / (CIN / KS), kb = s % (CIN / KS);
         const int dy = t / 3 - 1, dx = t % 3 - 1;
         const uint64_t ad0 = make_desc(a_base + (uint32_t)(kb * (KS / 8) * ROWS * 16) + (uint32_t)((1 + dy) * GW + dx + OFF) * 16u,
                                        ROWS * 16, 128);
         const uint64_t bd0 = make_desc(b_base + (uint32_t)(buf * 2 * SLB), 128, (KS / 8) * 128);
         const uint32_t acc0 = s ? 1u : 0u;
-        // consecutive MMAs go to DIFFERENT accumulator tiles: back-to-back MMAs into the same TMEM tile serialise on
-        // the accumulator (with N = 32..128 one MMA is short compared with the pipeline's latency)
+        const uint64_t ad1 = ad0 + (uint64_t)((uint32_t)(tile * 128 * 16) >> 4);
+        const uint32_t td = tacc + (uint32_t)(tile * COUT);
 #pragma unroll
         for (int combo = 0; combo < 3; ++combo) {
             const int pa = (combo == 2) ? 1 : 0, pb = (combo == 1) ? 1 : 0;  // hi*hi, hi*lo, lo*hi
 #pragma unroll
             for (int ks = 0; ks < KS / 16; ++ks) {
-#pragma unroll
-                for (int tile = 0; tile < MT; ++tile) {
-                    const uint32_t a_off = (uint32_t)(pa * PARTB + ks * 2 * ROWS * 16 + tile * 128 * 16);
-                    const uint32_t b_off = (uint32_t)(pb * SLB + ks * 256);
-                    // the whole warp runs the (uniform) descriptor arithmetic; only the MMA itself is predicated on one lane
-                    if (lane == 0)
-                        umma_f16(tacc + (uint32_t)(tile * COUT), ad0 + (uint64_t)(a_off >> 4), bd0 + (uint64_t)(b_off >> 4), idesc,
-                                 (combo | ks) ? 1u : acc0);
-                }
+                const uint32_t a_off = (uint32_t)(pa * PARTB + ks * 2 * ROWS * 16);
+                const uint32_t b_off = (uint32_t)(pb * SLB + ks * 256);
+                // the whole warp runs the (uniform) descriptor arithmetic; only the MMA itself is predicated on one lane
+                if (lane == 0) umma_f16(td, ad1 + (uint64_t)(a_off >> 4), bd0 + (uint64_t)(b_off >> 4), idesc, (combo | ks) ? 1u : acc0);
             }
         }
     };
@@ -279,10 +281,10 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
             fence_proxy_async();
             tc_fence_before();
             __syncthreads();
-            if (warp == 0) {
+            if (warp < MT) {
                 tc_fence_after();
 #pragma unroll 1
-                for (int s = 0; s < NSLICE; ++s) issue_slice(s, s, tacc);
+                for (int s = 0; s < NSLICE; ++s) issue_slice(s, s, tacc, warp);
                 if (lane == 0) umma_commit(&mbar[0]);
                 __syncwarp();
             }
@@ -309,9 +311,9 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
                 fence_proxy_async();
                 tc_fence_before();
                 __syncthreads();
-                if (warp == 0) {
+                if (warp < MT) {
                     tc_fence_after();
-                    issue_slice(s, st, tacc);
+                    issue_slice(s, st, tacc, warp);
                     if (lane == 0) umma_commit(&mbar[st]);
                     __syncwarp();
                 }
