@@ -32,7 +32,7 @@
 namespace svb {
 namespace k5tc {
 
-constexpr int NT = 256;
+
 constexpr int PAD = 25;                 // zero rows before/after the 256-row padded grid (>= 17); 25 makes the K-chunk stride
                                         // SROWS * 16 B = 8 banks mod 32, so lanes that differ in channel group store conflict-free
 constexpr int SROWS = 256 + 2 * PAD;    // 306
@@ -79,6 +79,17 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(p));
+    return p != 0;
 }
 __device__ __forceinline__ void umma_commit(unsigned long long *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -152,11 +163,14 @@ struct ConvSmemBits {
     uint32_t tmem_base;
 };
 
-constexpr int NTC = 512;  // conv kernel: 14 worker warps (conv1, S writes) + 2 MMA-issue warps (one per M tile); all 16 run the epilogue
-constexpr int NWK = 448;  // worker threads
+// conv kernel: 14 worker warps (conv1, S writes) + 2 MMA-issue warps (one per M tile); all 16 run the epilogue.  (A 1024-
+// thread form — 64 registers, one conv1 item per thread, 16 accumulator columns per warp in the epilogue — was measured in
+// round 2 and is slower, 1.895 against 1.855 ms: the worker phase is bound by issue slots in bursts, not by warps in flight.)
+constexpr int NTC = 512;
+constexpr int NWK = NTC - 64;  // worker threads
 
+template <int NWK>
 __device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(NWK) : "memory"); }
-
 // item -> (channel group, pooled pixel).  Float input: channel group major (a warp holds one group, 32 pooled pixels).
 // Bit input: channel group minor and the 144 interior pooled pixels before the 52 that touch the image border, so that
 // a warp is either all interior (pure table look-ups) or all border (look-up + class correction).
@@ -180,6 +194,7 @@ tc_conv_kernel(const void *__restrict__ xin_any, long long n_cells, const float 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     using SmemT = typename std::conditional<BITS, ConvSmemBits, ConvSmem>::type;
     SmemT &s = *reinterpret_cast<SmemT *>(smem_raw);
+    constexpr int NWARP = NTC / 32;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float *x = reinterpret_cast<const float *>(xin_any);          // !BITS: [n][784] floats
     const uint32_t *xb = reinterpret_cast<const uint32_t *>(xin_any);   //  BITS: [n][28] bit rows
@@ -208,6 +223,7 @@ tc_conv_kernel(const void *__restrict__ xin_any, long long n_cells, const float 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s.tmem_base;
+    if (tmem != 0u) __trap();  // the kernel allocates the whole TMEM (512 columns), so the base is lane 0 / column 0; the MMA issue relies on it
     const uint32_t idesc64 = make_idesc(128, 64), idesc128 = make_idesc(128, 128);
     const uint32_t s_base = smem_u32(&s.S[0][0][0]), wb_base = smem_u32(&s.WB[0][0]);
     uint32_t phase[2] = {0, 0};
@@ -345,14 +361,16 @@ tc_conv_kernel(const void *__restrict__ xin_any, long long n_cells, const float 
     // warps 14 and 15 only issue MMAs, one M tile each (the issue stream of a tile is ~550 serial instructions per cell, and
     // the two tiles' accumulators are independent); keeping them out of the conv1 barriers lets the 14 worker warps convolve
     // the next cell at full speed meanwhile
-    const bool mma_warp = (warp >= 14);
+    const bool mma_warp = (warp >= NWARP - 2);
     // epilogue of one cell from TMEM buffer `buf`: TMEM -> 2x2 max-pool (shuffles) -> bias/ReLU -> fp16 hi/lo features.
     // 16 warps: TMEM lane quarter q = warp % 4 (hardware rule), tile j, 32-column half of the 64 channels.
     auto epilogue = [&](long long cell_e, int buf) {
-        const int j = (warp >> 2) & 1, q = warp & 3, half = warp >> 3;
+        const int j = (warp >> 2) & 1, q = warp & 3;
         const int py = 4 * j + q - 1;  // pooled row produced by this warp (rows y_p = 2(4j+q), +1)
         const int px = (lane & 15) >> 1;
         const bool writer = (px < 7) && py >= 0 && py < 7;
+        const bool b0 = lane & 1, b1 = lane >> 4;
+        const int half = warp >> 3;
         const int chunk = (lane & 1) + 2 * (lane >> 4);  // which 8 of this warp's 32 channels this lane finishes and stores
         __half *fh = feat_hi + (cell_e * 49 + (long long)(py * 7 + px)) * 64 + half * 32 + chunk * 8;
         __half *fl = feat_lo + (cell_e * 49 + (long long)(py * 7 + px)) * 64 + half * 32 + chunk * 8;
@@ -362,7 +380,6 @@ tc_conv_kernel(const void *__restrict__ xin_any, long long n_cells, const float 
         tmem_ld32(ta + 64, v2);
         // 2x2 max-pool as a butterfly that halves the data at each step: after the x exchange a lane keeps the two 8-channel
         // chunks of its x parity, after the y exchange the one chunk it finishes (24 shuffles instead of 64)
-        const bool b0 = lane & 1, b1 = lane >> 4;
         float g[16], pooled[8];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -389,7 +406,7 @@ tc_conv_kernel(const void *__restrict__ xin_any, long long n_cells, const float 
     int it = 0;
     if (cell < n_cells && !mma_warp) {
         stage_input(cell);
-        bar_workers();
+        bar_workers<NWK>();
         conv1_regs();
     }
     for (; cell < n_cells; cell += gridDim.x, ++it) {
@@ -403,36 +420,46 @@ tc_conv_kernel(const void *__restrict__ xin_any, long long n_cells, const float 
         __syncthreads();      // S(i) complete; every epilogue read of TMEM buffer `buf` (cell i-2) has retired
         // ---- implicit-GEMM conv2 on tcgen05: 2 tiles x 2 products x 9 taps x 2 k-steps, fully unrolled ------------
         if (mma_warp) {
-            // The whole warp runs the (uniform) descriptor arithmetic so it stays on the uniform datapath;
-            // only the tcgen05 instructions themselves are predicated on one elected lane.
             tc_fence_after();
             // Per tile j, 128 accumulator columns: [0,64) = A_hi*B_hi + A_lo*B_hi, [64,128) = A_hi*B_lo (summed in the
             // epilogue).  The lo image of the weights follows the hi image at exactly 8 row groups (WB_BYTES = 8 * WB_SBO),
             // so one N = 128 descriptor starting at the hi image reads [B_hi | B_lo]: A_hi is fetched once for both products.
-            const uint32_t tacc = tmem + (uint32_t)(buf * 256);
-            const uint64_t a_desc_buf = a_desc0 + (uint64_t)((uint32_t)(buf * 2 * S_BYTES) >> 4);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                if (j != warp - 14) continue;  // this warp's tile
-#pragma unroll
-                for (int combo = 0; combo < 2; ++combo) {  // 0: A_hi x [B_hi|B_lo] (N=128), 1: A_lo x B_hi (N=64)
-#pragma unroll
-                    for (int t = 0; t < 9; ++t) {
-                        const int dy = t / 3 - 1, dx = t % 3 - 1;
-                        const uint32_t a_off = (uint32_t)(combo * S_BYTES + (128 * j + 16 * dy + dx + PAD) * 16);
-                        const uint32_t b_off = (uint32_t)(t * 4 * 128);
-#pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
-                            const uint64_t ad = a_desc_buf + (uint64_t)((a_off + ks * 2 * SROWS * 16) >> 4);
-                            const uint64_t bd = b_desc0 + (uint64_t)((b_off + ks * 256) >> 4);
-                            if (lane == 0)
-                                umma_f16(tacc + (uint32_t)(j * 128), ad, bd, combo ? idesc64 : idesc128, (combo | t | ks) ? 1u : 0u);
+            // The issue stream of a tile is this warp's whole job and was the cell's critical path (ncu round 2: the fully
+            // unrolled form kept 54 descriptors in VECTOR registers and paid five R2UR round trips + an ELECT waterfall per MMA,
+            // ~140 cycles each): tile and buffer are compile-time constants here, the TMEM address is a literal (the kernel owns
+            // all 512 columns, base 0, checked at start-up), and the tap loop is rolled inside ONE elected thread, so the
+            // descriptor arithmetic stays in uniform registers.
+            auto issue_tile = [&](auto jc, auto bc) {
+                constexpr int J = decltype(jc)::value, B = decltype(bc)::value;
+                constexpr uint32_t tacc = (uint32_t)(B * 256 + J * 128);
+                const uint64_t a_tile = a_desc0 + (uint64_t)(((uint32_t)(B * 2 * S_BYTES) + (uint32_t)((128 * J + PAD) * 16)) >> 4);
+                if (elect_one()) {
+#pragma unroll 1
+                    for (int combo = 0; combo < 2; ++combo) {  // 0: A_hi x [B_hi|B_lo] (N=128), 1: A_lo x B_hi (N=64)
+                        const uint64_t a_c = a_tile + (uint64_t)((uint32_t)(combo * S_BYTES) >> 4);
+                        const uint32_t idesc = combo ? idesc64 : idesc128;
+#pragma unroll 1
+                        for (int t = 0; t < 9; ++t) {
+                            const int ty = t / 3, dy = ty - 1, dx = t - 3 * ty - 1;
+                            const uint64_t ad = a_c + (uint64_t)(long long)(16 * dy + dx);  // rows of 16 B: the >> 4 is the row count
+                            const uint64_t bd = b_desc0 + (uint64_t)(t * 32);
+                            umma_f16(tacc, ad, bd, idesc, (combo | t) ? 1u : 0u);
+                            umma_f16(tacc, ad + (uint64_t)((2 * SROWS * 16) >> 4), bd + 16u, idesc, 1u);
                         }
                     }
+                    umma_commit(&s.mbar[B]);
                 }
+                __syncwarp();
+            };
+            using I0 = std::integral_constant<int, 0>;
+            using I1 = std::integral_constant<int, 1>;
+            if (warp == NWARP - 2) {
+                if (buf) issue_tile(I0{}, I1{});
+                else issue_tile(I0{}, I0{});
+            } else {
+                if (buf) issue_tile(I1{}, I1{});
+                else issue_tile(I1{}, I0{});
             }
-            if (lane == 0) umma_commit(&s.mbar[buf]);
-            __syncwarp();
         }
         // ---- overlapped with the MMAs of cell i: epilogue of cell i-1, then conv1 of cell i+1 ---------------------------
         if (it > 0) {
@@ -443,7 +470,7 @@ tc_conv_kernel(const void *__restrict__ xin_any, long long n_cells, const float 
         }
         if (next < n_cells && !mma_warp) {
             commit_input();
-            bar_workers();
+            bar_workers<NWK>();
             conv1_regs();
         }
         prev_cell = cell;

@@ -7,6 +7,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "sudoku-vision_b200")):
     sys.path.insert(0, p)
 import torch
+import svb200._lib as _L
+
+if os.environ.get("SVB_LIB"):  # A/B of two builds (tools/build_variant.py)
+    _L.LIB_PATH = os.path.abspath(os.environ["SVB_LIB"])
 from svb200 import Scanner, load_digitcnn_weights
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 82944
