@@ -21,7 +21,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--frames-per-size", type=int, default=192)
 ap.add_argument("--unique", type=int, default=24)
 ap.add_argument("--cells", type=int, default=300000)
-ap.add_argument("--sections", default="v1,cells,k1,jpeg")
+ap.add_argument("--v2-frames", type=int, default=48)
+ap.add_argument("--sections", default="v1,cells,k1,jpeg,v2")
 args = ap.parse_args()
 sections = args.sections.split(",")
 NCPU = max(1, len(os.sched_getaffinity(0)))
@@ -171,6 +172,72 @@ def jpeg_section():
     return nbad
 
 
+def v2_section():
+    """svb_scan_batch_v2's CV stages (preprocess_multi_strategy with per-frame glare / shadow flags, contour + validity) against
+    the oracle's composition on frames with synthetic shadows and glare spots"""
+    from oracle import oracle_v2 as O2
+
+    t0 = time.time()
+    nbad = tot = 0
+    rng = np.random.default_rng(21)
+    for (h, wd) in [(544, 960), (720, 1280)]:
+        n = args.v2_frames
+        base = list(pool.map(lambda i: F.make_frame(7000 + h + i, h, wd, max_rot_deg=25).image, range(n)))
+        yy, xx = np.mgrid[0:h, 0:wd].astype(np.float32)
+        imgs = []
+        for i, im in enumerate(base):
+            f = im.astype(np.float32)
+            kind = i % 4
+            if kind in (1, 3):  # shadow: a smooth darkening ramp across the frame
+                ang = rng.uniform(0, 6.28)
+                ramp = ((xx - wd / 2) * np.cos(ang) + (yy - h / 2) * np.sin(ang)) / max(h, wd)
+                f *= np.clip(0.75 + rng.uniform(0.6, 1.0) * ramp, 0.35, 1.0)[..., None]
+            if kind in (2, 3):  # glare: a saturating blob
+                cx, cy, rad = rng.uniform(0.2, 0.8) * wd, rng.uniform(0.2, 0.8) * h, rng.uniform(0.05, 0.15) * wd
+                f += 200.0 * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * rad * rad))[..., None]
+            f += rng.normal(0, 2.0, f.shape)
+            imgs.append(np.clip(f, 0, 255).astype(np.uint8))
+        imgs = np.stack(imgs)
+        out = sc.scan_batch_v2(torch.from_numpy(imgs).cuda(), want_logits=False)
+        pm = sc.preprocess_multi(torch.from_numpy(imgs).cuda(), want_aux=False)
+        torch.cuda.synchronize()
+        got = {k: v.cpu().numpy() for k, v in out.items() if hasattr(v, "cpu")}
+        gbin = pm["binary"].cpu().numpy()
+
+        def one(i):
+            r = O.preprocess_multi(imgs[i])
+            return r, O2.detect_grid_contour(r["binary"])
+
+        res = list(pool.map(one, range(n)))
+        st = dict(frames=n, found=0, glare=0, shadow=0, method_bad=0, binary_bad=0, found_bad=0, corners_bad=0)
+        for i, (r, c) in enumerate(res):
+            tot += 1
+            st["glare"] += int(bool(r.get("has_glare", False)))
+            st["shadow"] += int(bool(r.get("has_shadow", False)))
+            bad = False
+            if sc.V2_METHODS[int(got["info"][i][2])] != r["method_used"]:
+                st["method_bad"] += 1
+                bad = True
+            if not np.array_equal(gbin[i], r["binary"]):
+                st["binary_bad"] += 1
+                bad = True
+            if bool(got["found"][i] == 1) != (c is not None):
+                st["found_bad"] += 1
+                bad = True
+            elif c is not None:
+                st["found"] += 1
+                if not np.array_equal(got["corners"][i].astype(np.float32), c):
+                    st["corners_bad"] += 1
+                    bad = True
+            if bad:
+                nbad += 1
+                if nbad <= 3:
+                    np.savez_compressed(os.path.join(OUT, f"soak_v2_{h}x{wd}_{i}.npz"), frame=imgs[i])
+        print(f"v2 {h}x{wd}: {st}", flush=True)
+    print(f"v2: {tot} frames with shadows / glare, {nbad} differ from the oracle ({time.time() - t0:.0f} s)", flush=True)
+    return nbad
+
+
 total = 0
 if "v1" in sections:
     for k, (h, wd, rot) in enumerate([(1080, 1920, 15.0), (1080, 1920, 40.0), (720, 1280, 30.0), (540, 960, 25.0), (480, 640, 35.0),
@@ -182,4 +249,7 @@ if "k1" in sections:
     total += k1_section()
 if "jpeg" in sections:
     total += jpeg_section()
+if "v2" in sections:
+    sc.load_weights_v3(__import__("svb200.v3_init", fromlist=["random_v3_state"]).random_v3_state())
+    total += v2_section()
 print(f"soak: {total} mismatches in total")
