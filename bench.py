@@ -43,8 +43,8 @@ METRIC = "frames/sec end-to-end (preprocess->warp->81-cell CNN) at 1080p"
 K1_BYTES_PER_FRAME = 3 * H * W + H * W  # 6,220,800 read + 2,073,600 written
 # dram__bytes_read.sum + dram__bytes_write.sum per 1080p frame from the ncu --set full captures under profiles/ (see
 # profiles/README.md for the capture each constant comes from); None = no capture of the current kernel yet
-NCU_TRAFFIC_PER_FRAME = {"k1": int((1.769238e9 + 0.510463e9) / 256),            # profiles/r1d_k1w_raw.csv (kernel unchanged since)
-                         "k4": int((435.669504e6 + 6.6816e6) / 256)}              # profiles/r2b_k4_summary.csv
+NCU_TRAFFIC_PER_FRAME = {"k1": int((1.769889e9 + 0.513172992e9) / 256),         # profiles/r2s_k1w_summary.csv
+                         "k4": int((435.445504e6 + 5.876224e6) / 256)}            # profiles/r2s_k4_summary.csv
 # true MACs only, per cell: conv1 225,792 + conv2 3,612,672; fc1 401,408 + fc2 1,280
 K5_CONV_FLOP_PER_CELL = 2 * (225792 + 3612672)
 K5_FC_FLOP_PER_CELL = 2 * (401408 + 1280)
@@ -453,7 +453,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip BASELINE configs[2..3] (N = 1 only anyway)")
-    ap.add_argument("--parity-frames", type=int, default=64, help="benched frames checked against the oracle (0 = skip)")
+    ap.add_argument("--parity-frames", type=int, default=128, help="benched frames checked against the oracle (0 = skip)")
     ap.add_argument("--stream-seconds", type=float, default=30.0, help="BASELINE configs[4]: sustained streaming (0 = skip)")
     args = ap.parse_args()
 
