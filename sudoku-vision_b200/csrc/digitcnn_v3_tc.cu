@@ -18,6 +18,7 @@
 // cp.async double buffer while the previous slice's MMAs run; the epilogue reads TMEM with tcgen05.ld, adds the bias,
 // applies ReLU and writes fp32 NCHW.
 #include <cuda_fp16.h>
+#include <cstdio>
 
 #include "common.cuh"
 
@@ -25,6 +26,12 @@ namespace svb {
 namespace k6tc {
 
 constexpr int NT = 512;
+// phase timestamps of one steady-state pass (tools: build with -DSVB_K6_TRACE, prints from CTA 0)
+#ifdef SVB_K6_TRACE
+#define K6T(i) do { if (blockIdx.x == 0 && it == 3 && (tid == 0 || tid == NT - 1)) tr[i] = clock64(); } while (0)
+#else
+#define K6T(i) do { } while (0)
+#endif
 constexpr int OFF = 8;  // zero rows before the first grid row
 #ifndef SVB_V3_ROWPAD
 #define SVB_V3_ROWPAD 0
@@ -149,14 +156,29 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
     uint8_t *sB = sA + 2 * (size_t)PARTB;            // [NBUF buffers][2 parts][SLB]
     float *s_bias = (float *)(sB + (size_t)GEO::NBUF * 2 * SLB);
     unsigned long long *mbar = (unsigned long long *)(s_bias + COUT);
-    uint32_t *s_tmem = (uint32_t *)(mbar + 2);
+    uint32_t *s_tmem = (uint32_t *)(mbar + 5);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // Roles (round 2, from per-phase clock64 traces): the MMA issue of a pass blocks on the tensor pipe's queue for the whole
+    // MMA phase (15.6 k of a 21.5 k-cycle pass of the 32-channel layers), so a warp that issues must not owe the pass any
+    // other serial work.  Layers whose weights are resident: warps 12..15 issue (tile = warp - 12, + 4), fire their share of
+    // the next pass's loads between the slices (free: they are waiting for the queue anyway) and skip the epilogue when it
+    // runs under the MMAs.  Layers whose weights stream: warps 12, 13 issue, one thread of warp 14 is the PRODUCER of a
+    // two-buffer weight ring (cp.async.bulk + full / empty mbarriers, running across pass boundaries) — the first form
+    // re-synchronised the whole CTA for every slice (9..18 times per pass), which idled the tensor pipe half of the time.
+    // Warps 0..11 (three groups x four TMEM lane quarters) do the epilogue that runs under the MMAs.
+    constexpr int WISSUE = NT / 32 - 4, NIW = GEO::RESIDENT ? 4 : 2, NISSUE = MT < NIW ? MT : NIW;
+    const bool issuer = warp >= WISSUE && warp - WISSUE < NISSUE;
+    const bool producer = !GEO::RESIDENT && warp == WISSUE + 2;
+    unsigned long long *fbar = mbar + 2, *dbar = mbar + 4;  // full[2] (weight ring), done (all MMAs of a pass)
 
     for (int i = tid; i < 2 * PARTB / 16; i += NT) reinterpret_cast<uint4 *>(sA)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < COUT; i += NT) s_bias[i] = bias[i];
     if (tid == 0) {  // one arrival per issuing warp (each commits its own MMAs)
-        mbar_init(&mbar[0], MT);
-        mbar_init(&mbar[1], MT);
+        mbar_init(&mbar[0], NISSUE);  // resident: MMAs of a pass done; streaming: ring buffer 0 / 1 free again ("empty")
+        mbar_init(&mbar[1], NISSUE);
+        mbar_init(&fbar[0], 1);
+        mbar_init(&fbar[1], 1);
+        mbar_init(dbar, NISSUE);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(s_tmem, GEO::TALLOC);
@@ -175,10 +197,23 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
         cp_async_commit();
     };
 
+    auto load_slice_bulk = [&](int s, int buf) {  // the same by one bulk copy that completes on the buffer's full barrier
+        const uint32_t dst = smem_u32(sB + (size_t)buf * 2 * SLB), bar = smem_u32(&fbar[buf]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(2 * SLB)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(wimg + (size_t)s * 2 * SLB), "r"((uint32_t)(2 * SLB)), "r"(bar)
+                     : "memory");
+    };
+
     const int n_pass = (n_cells + G - 1) / G;
+    const int my_passes = (int)blockIdx.x < n_pass ? (n_pass - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int total_slices = my_passes * NSLICE;
     if (GEO::RESIDENT) {  // all weight slices once
         for (int s = 0; s < NSLICE; ++s) load_slice(s, s);
         cp_async_wait<0>();
+    } else if (producer && lane == 0 && total_slices > 0) {  // ring prologue: slices 0 and 1
+        load_slice_bulk(0, 0);
+        load_slice_bulk(1 % NSLICE, 1);
     }
     // the MMAs of one weight slice (one tap x KS input channels) for ONE M tile of the pass.  An issue is a serial
     // instruction stream of ~9 instructions with an ELECT / R2UR round trip (~80 cycles per MMA measured with one issuing
@@ -186,15 +221,13 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
     // its own issuing warp (warps 0..MT-1): the tiles are independent accumulators, each warp commits its own MMAs.
     // Everything that does not depend on the slice is a compile-time constant added to two per-slice base descriptors (all
     // shared-memory addresses are below 256 KB, so adding (byte offset >> 4) never carries out of the 14-bit field).
-    auto issue_slice = [&](int s, int buf, uint32_t tacc, int tile) {
+    auto issue_slice = [&](int s, int buf, uint32_t tacc) {
         const int t = s / (CIN / KS), kb = s % (CIN / KS);
         const int dy = t / 3 - 1, dx = t % 3 - 1;
         const uint64_t ad0 = make_desc(a_base + (uint32_t)(kb * (KS / 8) * ROWS * 16) + (uint32_t)((1 + dy) * GW + dx + OFF) * 16u,
                                        ROWS * 16, 128);
         const uint64_t bd0 = make_desc(b_base + (uint32_t)(buf * 2 * SLB), 128, (KS / 8) * 128);
         const uint32_t acc0 = s ? 1u : 0u;
-        const uint64_t ad1 = ad0 + (uint64_t)((uint32_t)(tile * 128 * 16) >> 4);
-        const uint32_t td = tacc + (uint32_t)(tile * COUT);
 #pragma unroll
         for (int combo = 0; combo < 3; ++combo) {
             const int pa = (combo == 2) ? 1 : 0, pb = (combo == 1) ? 1 : 0;  // hi*hi, hi*lo, lo*hi
@@ -202,8 +235,14 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
             for (int ks = 0; ks < KS / 16; ++ks) {
                 const uint32_t a_off = (uint32_t)(pa * PARTB + ks * 2 * ROWS * 16);
                 const uint32_t b_off = (uint32_t)(pb * SLB + ks * 256);
-                // the whole warp runs the (uniform) descriptor arithmetic; only the MMA itself is predicated on one lane
-                if (lane == 0) umma_f16(td, ad1 + (uint64_t)(a_off >> 4), bd0 + (uint64_t)(b_off >> 4), idesc, (combo | ks) ? 1u : acc0);
+                // consecutive MMAs of a warp go to different accumulator tiles where it owns two
+#pragma unroll
+                for (int tt = 0; tt < (MT + NIW - 1) / NIW; ++tt) {
+                    const int tile = warp - WISSUE + NIW * tt;
+                    if (tile < MT && lane == 0)
+                        umma_f16(tacc + (uint32_t)(tile * COUT), ad0 + (uint64_t)((a_off + (uint32_t)(tile * 128 * 16)) >> 4),
+                                 bd0 + (uint64_t)(b_off >> 4), idesc, (combo | ks) ? 1u : acc0);
+                }
             }
         }
     };
@@ -214,18 +253,20 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
     constexpr int IPT = (NITEMS + NT - 1) / NT;          // per thread
     constexpr bool DB = GEO::DB;
     float pre[IPT][8];
-    auto prefetch = [&](int c0) {  // fp32 activations of the pass starting at cell c0: 8 channels of one pixel per item
+    auto prefetch_k = [&](int c0, int k) {  // fp32 activations of the pass starting at cell c0: 8 channels of one pixel per item
+        const int it = k * NT + tid;
+        const int p = it % HH, kc = (it / HH) % NKC, j = it / (HH * NKC);
+        if (it < NITEMS && c0 + j < n_cells) {
+            const float *src = in + ((size_t)(c0 + j) * CIN + kc * 8) * HH + p;
 #pragma unroll
-        for (int k = 0; k < IPT; ++k) {
-            const int it = k * NT + tid;
-            const int p = it % HH, kc = (it / HH) % NKC, j = it / (HH * NKC);
-            if (it < NITEMS && c0 + j < n_cells) {
-                const float *src = in + ((size_t)(c0 + j) * CIN + kc * 8) * HH + p;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) pre[k][e] = __ldg(src + (size_t)e * HH);
-            }
+            for (int e = 0; e < 8; ++e) pre[k][e] = __ldg(src + (size_t)e * HH);
         }
     };
+    auto prefetch = [&](int c0) {
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) prefetch_k(c0, k);
+    };
+    static_assert(IPT <= NSLICE, "the issuing warps spread their loads over the slices");
     auto write_A = [&](int c0) {  // registers -> fp16 hi/lo rows of the activation buffer
 #pragma unroll
         for (int k = 0; k < IPT; ++k) {
@@ -244,10 +285,11 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
         }
     };
     // TMEM -> + bias -> [ReLU] -> fp32 NCHW (stride-2 layers keep the even rows / columns)
-    auto epilogue = [&](int c0, uint32_t tacc) {
+    auto epilogue = [&](int c0, uint32_t tacc, int ngroups) {  // ngroups = 3: warps 0..11 only (the issuing warps are busy)
         const int q = warp & 3, grp = warp >> 2;  // TMEM lane quarter (hardware rule: warp % 4), work group
         constexpr int NCB = COUT / 32;
-        for (int blk = grp; blk < MT * NCB; blk += NT / 128) {
+        if (grp >= ngroups) return;
+        for (int blk = grp; blk < MT * NCB; blk += ngroups) {
             const int tile = blk / NCB, cb = blk - tile * NCB;
             uint32_t v[32];
             tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * COUT + cb * 32), v);
@@ -269,76 +311,100 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
     };
 
     int it = 0, prev_c0 = -1;
+#ifdef SVB_K6_TRACE
+    long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     if ((int)blockIdx.x < n_pass) prefetch((int)blockIdx.x * G);
     for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x, ++it) {
         const int c0 = pass * G;
         const uint32_t tacc = tmem + (DB ? (uint32_t)((it & 1) * GEO::TCOLS) : 0u);
         const uint32_t tacc_prev = tmem + (DB ? (uint32_t)(((it & 1) ^ 1) * GEO::TCOLS) : 0u);
         const int next = pass + gridDim.x;
-        if (!GEO::RESIDENT) load_slice(0, 0);
+        K6T(0);
         write_A(c0);
+        K6T(1);
         if (GEO::RESIDENT) {
             fence_proxy_async();
             tc_fence_before();
             __syncthreads();
-            if (warp < MT) {
+            K6T(2);
+            if (issuer) {
                 tc_fence_after();
-#pragma unroll 1
-                for (int s = 0; s < NSLICE; ++s) issue_slice(s, s, tacc, warp);
+#pragma unroll
+                for (int s = 0; s < NSLICE; ++s) {
+                    issue_slice(s, s, tacc);
+                    if (s < IPT && next < n_pass) prefetch_k(next * G, s);
+                }
                 if (lane == 0) umma_commit(&mbar[0]);
                 __syncwarp();
             }
-            if (next < n_pass) prefetch(next * G);
+            K6T(3);
+            if (next < n_pass && !issuer) prefetch(next * G);
+            K6T(4);
             if (DB && it > 0) {
                 tc_fence_after();
-                epilogue(prev_c0, tacc_prev);
+                epilogue(prev_c0, tacc_prev, 3);
             }
+            K6T(5);
             mbar_wait(&mbar[0], ph[0]);
             ph[0] ^= 1;
+            K6T(6);
         } else {
-            for (int s = 0; s < NSLICE; ++s) {
-                const int st = s & 1;
-                if (s + 1 < NSLICE) {
-                    if (s >= 1) {  // buffer st^1 was last read by the MMAs of slice s-1
-                        mbar_wait(&mbar[st ^ 1], ph[st ^ 1]);
-                        ph[st ^ 1] ^= 1;
-                    }
-                    load_slice(s + 1, st ^ 1);
-                    cp_async_wait<1>();
-                } else {
-                    cp_async_wait<0>();
-                }
-                fence_proxy_async();
-                tc_fence_before();
-                __syncthreads();
-                if (warp < MT) {
+            // A(i) is written; the ring needs no CTA-wide synchronisation
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            const int gs0 = it * NSLICE;  // global index of this pass's first slice (this CTA's count)
+            if (issuer) {
+                tc_fence_after();
+#pragma unroll 1
+                for (int s = 0; s < NSLICE; ++s) {
+                    const int g = gs0 + s, b = g & 1;
+                    mbar_wait(&fbar[b], (uint32_t)((g >> 1) & 1));
                     tc_fence_after();
-                    issue_slice(s, st, tacc, warp);
-                    if (lane == 0) umma_commit(&mbar[st]);
+                    issue_slice(s, b, tacc);
+                    if (lane == 0) umma_commit(&mbar[b]);  // buffer b is free again once these MMAs have read it
                     __syncwarp();
                 }
-                if (s == 0) {  // overlapped with the tensor core: next pass's loads, previous pass's epilogue
-                    if (next < n_pass) prefetch(next * G);
-                    if (DB && it > 0) {
-                        tc_fence_after();
-                        epilogue(prev_c0, tacc_prev);
+                if (lane == 0) umma_commit(dbar);
+                __syncwarp();
+                if (next < n_pass) prefetch(next * G);
+            } else if (producer) {
+                if (lane == 0) {
+#pragma unroll 1
+                    for (int s = 0; s < NSLICE; ++s) {  // slice g + 2 goes into the buffer slice g is being read from
+                        const int g = gs0 + s, b = g & 1;
+                        if (g + 2 < total_slices) {
+                            mbar_wait(&mbar[b], (uint32_t)((g >> 1) & 1));
+                            load_slice_bulk((s + 2) % NSLICE, b);
+                        }
                     }
                 }
+                __syncwarp();
+                if (next < n_pass) prefetch(next * G);
+            } else {  // overlapped with the tensor core: next pass's loads, previous pass's epilogue
+                if (next < n_pass) prefetch(next * G);
+                if (DB && it > 0) {
+                    tc_fence_after();
+                    epilogue(prev_c0, tacc_prev, 3);
+                }
             }
-            // drain: the commits of the last two slices are still pending
-            mbar_wait(&mbar[(NSLICE - 2) & 1], ph[(NSLICE - 2) & 1]);
-            ph[(NSLICE - 2) & 1] ^= 1;
-            mbar_wait(&mbar[(NSLICE - 1) & 1], ph[(NSLICE - 1) & 1]);
-            ph[(NSLICE - 1) & 1] ^= 1;
+            mbar_wait(dbar, (uint32_t)(it & 1));
         }
         tc_fence_after();
-        if (!DB) epilogue(c0, tacc);
+        if (!DB) epilogue(c0, tacc, 4);
         prev_c0 = c0;
         tc_fence_before();
         __syncthreads();  // the activation buffer (and, single-buffered, TMEM) is free for the next pass
         tc_fence_after();
+        K6T(7);
+#ifdef SVB_K6_TRACE
+        if (blockIdx.x == 0 && it == 3 && (tid == 0 || tid == NT - 1))
+            printf("K6T <%d,%d,%d> tid %d: write_A %lld  sync %lld  issue %lld  prefetch %lld  epilogue %lld  mma_wait %lld  end_sync %lld  pass %lld\n", CIN,
+                   COUT, H, tid, tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[7] - tr[6], tr[7] - tr[0]);
+#endif
     }
-    if (DB && it > 0) epilogue(prev_c0, tmem + (uint32_t)(((it - 1) & 1) * GEO::TCOLS));
+    if (DB && it > 0) epilogue(prev_c0, tmem + (uint32_t)(((it - 1) & 1) * GEO::TCOLS), 4);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, GEO::TALLOC);
