@@ -13,7 +13,7 @@
 // (c/8)*ROWS*16 + r*16 + (c%8)*2.  That is the UMMA canonical K-major no-swizzle layout with SBO = 128 B (8-row groups
 // contiguous) and LBO = ROWS*16 (between the K chunks), so rows are a plain 16-byte-pitch array and the operand of tap
 // (dy, dx) for output rows m0..m0+127 is the SAME buffer viewed at start address + ((1+dy)*GW + dx + m0)*16: nine
-// descriptors, no copies.  Stride-2 convolutions are evaluated at stride 1 and subsampled in the epilogue.
+// descriptors, no copies.  The two stride-2 layers read four parity planes of their input laid out on the output grid (Geo).
 // Weights are prepacked (hi/lo, canonical layout) in slices of one tap x 64 input channels and streamed through a
 // cp.async double buffer while the previous slice's MMAs run; the epilogue reads TMEM with tcgen05.ld, adds the bias,
 // applies ReLU and writes fp32 NCHW.
@@ -117,17 +117,26 @@ __device__ __forceinline__ void split_hi_lo(float v, __half &hi, __half &lo) {
 // ---- compile-time geometry of one layer shape ---------------------------------------------------------------------------
 template <int CIN, int COUT, int H>
 struct Geo {
-    static constexpr int GW = (H == 28) ? 32 : (H == 14 ? 16 : 8);  // grid width (>= H + 1)
-    static constexpr int G = (H == 28) ? 1 : (H == 14 ? 2 : 4);     // cells per pass
-    static constexpr int CB = (H + 1) * GW;                         // rows per cell block (bottom halo shared with the next top halo)
-    static constexpr int MROWS = (G - 1) * CB + (H - 1) * GW + H;   // output rows that can be valid
+    // The two stride-2 layers (the ones that change the channel count, ml/model_v3.py:147-149) read their input as FOUR parity
+    // planes (y & 1, x & 1), each laid out on the zero-haloed OUTPUT grid: output (oy, ox) reads input (2 oy + dy, 2 ox + dx)
+    // = plane (dy & 1, dx & 1) at (oy + floor(dy / 2), ox + floor(dx / 2)), so a tap is again one buffer viewed at a shifted
+    // start address and only the outputs that exist are computed (round 1 evaluated these layers at stride 1 and threw three
+    // quarters of the MMAs away in the epilogue).
+    static constexpr bool S2 = CIN != COUT;
+    static constexpr int HO = S2 ? H / 2 : H;                       // output side = side of the row grid
+    static constexpr int NPL = S2 ? 4 : 1;                          // parity planes of the input
+    static constexpr int GW = (HO == 28) ? 32 : (HO == 14 ? 16 : 8);  // grid width (>= HO + 1)
+    static constexpr int G = S2 ? (H == 28 ? 1 : 2) : ((H == 28) ? 1 : (H == 14 ? 2 : 4));  // cells per pass
+    static constexpr int CB = (HO + 1) * GW;                        // rows per cell block (bottom halo shared with the next top halo)
+    static constexpr int MROWS = (G - 1) * CB + (HO - 1) * GW + HO; // output rows that can be valid
     static constexpr int MT = (MROWS + 127) / 128;                  // M tiles of 128 rows
-    // rows of the activation buffer; SVB_V3_ROWPAD extra rows make the K-chunk stride (LBO = ROWS * 16 B) fall on other
-    // shared-memory banks than a multiple of 128 B would
-    static constexpr int ROWS = ((MT * 128 + 2 * GW + 1 + OFF + 7) & ~7) + SVB_V3_ROWPAD;
+    // rows of one plane of the activation buffer; SVB_V3_ROWPAD extra rows make the K-chunk stride (LBO = ROWS * 16 B) fall on
+    // other shared-memory banks than a multiple of 128 B would (measured: no effect)
+    static constexpr int PROWS = ((MT * 128 + 2 * GW + 1 + OFF + 7) & ~7) + SVB_V3_ROWPAD;
+    static constexpr int ROWS = NPL * PROWS;
     static constexpr int NKC = CIN / 8;                             // K chunks
     static constexpr int PARTB = NKC * ROWS * 16;                   // bytes of one fp16 part of the activations
-    static constexpr int KS = CIN < 64 ? CIN : 64;                  // K of one weight slice
+    static constexpr int KS = CIN < 64 ? CIN : ((S2 && CIN == 64) ? 32 : 64);  // K of one weight slice (shared memory budget)
     static constexpr int NSLICE = 9 * (CIN / KS);
     static constexpr int SLB = COUT * KS * 2;                       // bytes of one part of one weight slice
     static constexpr int TCOLS = MT * COUT;                         // TMEM columns used
@@ -139,7 +148,7 @@ struct Geo {
     static constexpr int NBUF = RESIDENT ? NSLICE : 2;
     static constexpr size_t SMEM = 1024 + 2 * (size_t)PARTB + (size_t)NBUF * 2 * SLB + COUT * 4 + 64;
     static_assert(TCOLS <= 512, "accumulators exceed TMEM");
-    static_assert(H < GW, "grid needs a zero column");
+    static_assert(HO < GW, "grid needs a zero column");
 };
 
 // in: fp32 [n][CIN][H][H]; out: fp32 [n][COUT][HO][HO], HO = (H-1)/STRIDE + 1; wimg: prepacked weight slices
@@ -149,7 +158,8 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
                   float *__restrict__ out, int n_cells, int relu) {
     using GEO = Geo<CIN, COUT, H>;
     constexpr int GW = GEO::GW, G = GEO::G, CB = GEO::CB, MT = GEO::MT, ROWS = GEO::ROWS, NKC = GEO::NKC, PARTB = GEO::PARTB;
-    constexpr int KS = GEO::KS, NSLICE = GEO::NSLICE, SLB = GEO::SLB, HH = H * H, HO = (H - 1) / STRIDE + 1;
+    constexpr int KS = GEO::KS, NSLICE = GEO::NSLICE, SLB = GEO::SLB, HH = H * H, HO = GEO::HO, PROWS = GEO::PROWS;
+    static_assert(GEO::S2 == (STRIDE == 2) && HO == (H - 1) / STRIDE + 1, "stride-2 layers are the ones that change the channel count");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = base;                              // [2 parts][NKC][ROWS][8 fp16]
@@ -224,8 +234,10 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
     auto issue_slice = [&](int s, int buf, uint32_t tacc) {
         const int t = s / (CIN / KS), kb = s % (CIN / KS);
         const int dy = t / 3 - 1, dx = t % 3 - 1;
-        const uint64_t ad0 = make_desc(a_base + (uint32_t)(kb * (KS / 8) * ROWS * 16) + (uint32_t)((1 + dy) * GW + dx + OFF) * 16u,
-                                       ROWS * 16, 128);
+        // stride 2: plane (dy & 1, dx & 1) at grid offset (floor(dy / 2), floor(dx / 2))
+        const int row0 = GEO::S2 ? ((dy & 1) * 2 + (dx & 1)) * PROWS + (1 + (dy < 0 ? -1 : 0)) * GW + (dx < 0 ? -1 : 0) + OFF
+                                 : (1 + dy) * GW + dx + OFF;
+        const uint64_t ad0 = make_desc(a_base + (uint32_t)(kb * (KS / 8) * ROWS * 16) + (uint32_t)row0 * 16u, ROWS * 16, 128);
         const uint64_t bd0 = make_desc(b_base + (uint32_t)(buf * 2 * SLB), 128, (KS / 8) * 128);
         const uint32_t acc0 = s ? 1u : 0u;
 #pragma unroll
@@ -277,14 +289,15 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
 #pragma unroll
                 for (int e = 0; e < 8; ++e) split_hi_lo(pre[k][e], hi[e], lo[e]);
                 const int y = p / H, x = p - y * H;
-                const int row = j * CB + (y + 1) * GW + x + OFF;
+                const int row = GEO::S2 ? ((y & 1) * 2 + (x & 1)) * PROWS + j * CB + ((y >> 1) + 1) * GW + (x >> 1) + OFF
+                                        : j * CB + (y + 1) * GW + x + OFF;
                 const size_t o = (size_t)kc * ROWS * 16 + (size_t)row * 16;
                 *reinterpret_cast<uint4 *>(sA + o) = *reinterpret_cast<const uint4 *>(hi);
                 *reinterpret_cast<uint4 *>(sA + PARTB + o) = *reinterpret_cast<const uint4 *>(lo);
             }
         }
     };
-    // TMEM -> + bias -> [ReLU] -> fp32 NCHW (stride-2 layers keep the even rows / columns)
+    // TMEM -> + bias -> [ReLU] -> fp32 NCHW
     auto epilogue = [&](int c0, uint32_t tacc, int ngroups) {  // ngroups = 3: warps 0..11 only (the issuing warps are busy)
         const int q = warp & 3, grp = warp >> 2;  // TMEM lane quarter (hardware rule: warp % 4), work group
         constexpr int NCB = COUT / 32;
@@ -296,10 +309,9 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
             const int m = tile * 128 + q * 32 + lane;
             const int j = m / CB, rem = m - j * CB, y = rem / GW, x = rem - y * GW;
             const int cell = c0 + j;
-            bool ok = (j < G) && (cell < n_cells) && (y < H) && (x < H);
-            if (STRIDE == 2) ok = ok && !(y & 1) && !(x & 1);
+            const bool ok = (j < G) && (cell < n_cells) && (y < HO) && (x < HO);
             if (ok) {
-                float *dst = out + ((size_t)cell * COUT + cb * 32) * (HO * HO) + (y / STRIDE) * HO + (x / STRIDE);
+                float *dst = out + ((size_t)cell * COUT + cb * 32) * (HO * HO) + y * HO + x;
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
                     float f = __uint_as_float(v[c]) + s_bias[cb * 32 + c];
@@ -416,7 +428,7 @@ __global__ void pack_v3_kernel(const float *__restrict__ w, uint8_t *__restrict_
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cout * cin * 9) return;
     const int t = i % 9, ci = (i / 9) % cin, n = i / (9 * cin);
-    const int ks = cin < 64 ? cin : 64, kb = ci / ks, kk = ci % ks;
+    const int ks = cin < 64 ? cin : ((cin != cout && cin == 64) ? 32 : 64), kb = ci / ks, kk = ci % ks;  // = Geo::KS
     const int s = t * (cin / ks) + kb;
     const size_t slb = (size_t)cout * ks * 2;
     const size_t off = (size_t)(n >> 3) * (ks / 8 * 128) + (size_t)(kk >> 3) * 128 + (n & 7) * 16 + (kk & 7) * 2;
