@@ -28,7 +28,7 @@ namespace k6tc {
 constexpr int NT = 512;
 // phase timestamps of one steady-state pass (tools: build with -DSVB_K6_TRACE, prints from CTA 0)
 #ifdef SVB_K6_TRACE
-#define K6T(i) do { if (blockIdx.x == 0 && it == 3 && (tid == 0 || tid == NT - 1)) tr[i] = clock64(); } while (0)
+#define K6T(i) do { if (blockIdx.x == 0 && it == 3 && (tid == 0 || tid == NT - 128)) tr[i] = clock64(); } while (0)
 #else
 #define K6T(i) do { } while (0)
 #endif
@@ -75,6 +75,17 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(p));
+    return p != 0;
 }
 __device__ __forceinline__ void umma_commit(unsigned long long *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -231,7 +242,7 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
     // its own issuing warp (warps 0..MT-1): the tiles are independent accumulators, each warp commits its own MMAs.
     // Everything that does not depend on the slice is a compile-time constant added to two per-slice base descriptors (all
     // shared-memory addresses are below 256 KB, so adding (byte offset >> 4) never carries out of the 14-bit field).
-    auto issue_slice = [&](int s, int buf, uint32_t tacc) {
+    auto issue_slice = [&](int s, int buf, uint32_t tacc, bool single) {  // single: called by one elected thread
         const int t = s / (CIN / KS), kb = s % (CIN / KS);
         const int dy = t / 3 - 1, dx = t % 3 - 1;
         // stride 2: plane (dy & 1, dx & 1) at grid offset (floor(dy / 2), floor(dx / 2))
@@ -251,7 +262,7 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
 #pragma unroll
                 for (int tt = 0; tt < (MT + NIW - 1) / NIW; ++tt) {
                     const int tile = warp - WISSUE + NIW * tt;
-                    if (tile < MT && lane == 0)
+                    if (tile < MT && (single || lane == 0))
                         umma_f16(tacc + (uint32_t)(tile * COUT), ad0 + (uint64_t)((a_off + (uint32_t)(tile * 128 * 16)) >> 4),
                                  bd0 + (uint64_t)(b_off >> 4), idesc, (combo | ks) ? 1u : acc0);
                 }
@@ -344,7 +355,7 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
                 tc_fence_after();
 #pragma unroll
                 for (int s = 0; s < NSLICE; ++s) {
-                    issue_slice(s, s, tacc);
+                    issue_slice(s, s, tacc, false);
                     if (s < IPT && next < n_pass) prefetch_k(next * G, s);
                 }
                 if (lane == 0) umma_commit(&mbar[0]);
@@ -367,20 +378,29 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
             tc_fence_before();
             __syncthreads();
             const int gs0 = it * NSLICE;  // global index of this pass's first slice (this CTA's count)
+            K6T(2);
             if (issuer) {
                 tc_fence_after();
+                // ONE elected thread runs the whole slice loop (MMAs and commits must come from the same thread): inside a
+                // single-thread region the compiler moves the TMEM address and the descriptors to the uniform datapath with
+                // plain R2UR; predicated on `lane == 0` every MMA paid an ELECT + R2UR.BROADCAST waterfall, ~160 cycles per
+                // MMA and warp (traces: the streamed layers ran at 74-136 cycles per MMA, issue-bound, not at their 48-64)
+                if (elect_one()) {
 #pragma unroll 1
-                for (int s = 0; s < NSLICE; ++s) {
-                    const int g = gs0 + s, b = g & 1;
-                    mbar_wait(&fbar[b], (uint32_t)((g >> 1) & 1));
-                    tc_fence_after();
-                    issue_slice(s, b, tacc);
-                    if (lane == 0) umma_commit(&mbar[b]);  // buffer b is free again once these MMAs have read it
-                    __syncwarp();
+                    for (int s = 0; s < NSLICE; ++s) {
+                        const int g = gs0 + s, b = g & 1;
+                        mbar_wait(&fbar[b], (uint32_t)((g >> 1) & 1));
+                        tc_fence_after();
+                        issue_slice(s, b, tacc, true);
+                        umma_commit(&mbar[b]);  // buffer b is free again once these MMAs have read it
+                    }
+                    umma_commit(dbar);
                 }
-                if (lane == 0) umma_commit(dbar);
                 __syncwarp();
+                K6T(3);
                 if (next < n_pass) prefetch(next * G);
+                K6T(4);
+                K6T(5);
             } else if (producer) {
                 if (lane == 0) {
 #pragma unroll 1
@@ -395,13 +415,17 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
                 __syncwarp();
                 if (next < n_pass) prefetch(next * G);
             } else {  // overlapped with the tensor core: next pass's loads, previous pass's epilogue
+                K6T(3);
                 if (next < n_pass) prefetch(next * G);
+                K6T(4);
                 if (DB && it > 0) {
                     tc_fence_after();
                     epilogue(prev_c0, tacc_prev, 3);
                 }
+                K6T(5);
             }
             mbar_wait(dbar, (uint32_t)(it & 1));
+            K6T(6);
         }
         tc_fence_after();
         if (!DB) epilogue(c0, tacc, 4);
@@ -411,7 +435,7 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
         tc_fence_after();
         K6T(7);
 #ifdef SVB_K6_TRACE
-        if (blockIdx.x == 0 && it == 3 && (tid == 0 || tid == NT - 1))
+        if (blockIdx.x == 0 && it == 3 && (tid == 0 || tid == NT - 128))
             printf("K6T <%d,%d,%d> tid %d: write_A %lld  sync %lld  issue %lld  prefetch %lld  epilogue %lld  mma_wait %lld  end_sync %lld  pass %lld\n", CIN,
                    COUT, H, tid, tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[7] - tr[6], tr[7] - tr[0]);
 #endif
