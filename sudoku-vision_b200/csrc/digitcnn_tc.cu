@@ -364,13 +364,14 @@ tc_conv_kernel(const void *__restrict__ xin_any, long long n_cells, const float 
     const bool mma_warp = (warp >= NWARP - 2);
     // epilogue of one cell from TMEM buffer `buf`: TMEM -> 2x2 max-pool (shuffles) -> bias/ReLU -> fp16 hi/lo features.
     // 16 warps: TMEM lane quarter q = warp % 4 (hardware rule), tile j, 32-column half of the 64 channels.
-    auto epilogue = [&](long long cell_e, int buf) {
-        const int j = (warp >> 2) & 1, q = warp & 3;
+    // `wid` = the warp slot whose (tile, lane quarter, channel half) is handled; wid % 4 == warp % 4 (TMEM lane-quarter rule)
+    auto epilogue_as = [&](long long cell_e, int buf, int wid) {
+        const int j = (wid >> 2) & 1, q = wid & 3;
         const int py = 4 * j + q - 1;  // pooled row produced by this warp (rows y_p = 2(4j+q), +1)
         const int px = (lane & 15) >> 1;
         const bool writer = (px < 7) && py >= 0 && py < 7;
         const bool b0 = lane & 1, b1 = lane >> 4;
-        const int half = warp >> 3;
+        const int half = wid >> 3;
         const int chunk = (lane & 1) + 2 * (lane >> 4);  // which 8 of this warp's 32 channels this lane finishes and stores
         __half *fh = feat_hi + (cell_e * 49 + (long long)(py * 7 + px)) * 64 + half * 32 + chunk * 8;
         __half *fl = feat_lo + (cell_e * 49 + (long long)(py * 7 + px)) * 64 + half * 32 + chunk * 8;
@@ -397,6 +398,16 @@ tc_conv_kernel(const void *__restrict__ xin_any, long long n_cells, const float 
             *reinterpret_cast<uint4 *>(fh) = *reinterpret_cast<const uint4 *>(hi);
             *reinterpret_cast<uint4 *>(fl) = *reinterpret_cast<const uint4 *>(lo);
         }
+    };
+
+    // The MMA-issuing warps stay out of the epilogue: their issue blocks on the tensor pipe's queue for the whole MMA phase of
+    // a cell (~4 k cycles), and with their share of the epilogue behind it they were the last to reach the per-cell barrier
+    // (6 k-cycle period at a 4 k-cycle tensor phase; workers waiting: barrier stalls 2.6 per issue).  Their two slots (14, 15)
+    // go to warps 10 and 11 — same lane quarters, and the warps with the fewest conv1 items.
+    auto epilogue = [&](long long cell_e, int buf) {
+        if (mma_warp) return;
+        epilogue_as(cell_e, buf, warp);
+        if (warp == NWARP - 6 || warp == NWARP - 5) epilogue_as(cell_e, buf, warp + 4);
     };
 
     // Pipeline over cells; activations S and accumulators (TMEM) are both double-buffered:
