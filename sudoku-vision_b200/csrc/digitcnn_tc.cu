@@ -23,6 +23,7 @@
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <cstdio>
 
 #include <type_traits>
 
@@ -167,6 +168,12 @@ struct ConvSmemBits {
 // thread form — 64 registers, one conv1 item per thread, 16 accumulator columns per warp in the epilogue — was measured in
 // round 2 and is slower, 1.895 against 1.855 ms: the worker phase is bound by issue slots in bursts, not by warps in flight.)
 constexpr int NTC = 512;
+// phase timestamps of one steady-state cell (tools: build with -DSVB_K5_TRACE, prints from CTA 0)
+#ifdef SVB_K5_TRACE
+#define K5T(i) do { if (blockIdx.x == 0 && it == 20 && (tid == 0 || tid == 320 || tid == 448)) tr[i] = clock64(); } while (0)
+#else
+#define K5T(i) do { } while (0)
+#endif
 constexpr int NWK = NTC - 64;  // worker threads
 
 template <int NWK>
@@ -420,15 +427,21 @@ tc_conv_kernel(const void *__restrict__ xin_any, long long n_cells, const float 
         bar_workers<NWK>();
         conv1_regs();
     }
+#ifdef SVB_K5_TRACE
+    long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     for (; cell < n_cells; cell += gridDim.x, ++it) {
         const int buf = it & 1;
         const long long next = cell + gridDim.x;
+        K5T(0);
         if (next < n_cells && !mma_warp) prefetch_input(next);  // lands while we write S and run the epilogue
         // S[buf] was last read by the MMAs of cell i-2, whose commit every thread awaited in the previous iteration
         if (!mma_warp) write_S(buf);
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
         tc_fence_before();
+        K5T(1);
         __syncthreads();      // S(i) complete; every epilogue read of TMEM buffer `buf` (cell i-2) has retired
+        K5T(2);
         // ---- implicit-GEMM conv2 on tcgen05: 2 tiles x 2 products x 9 taps x 2 k-steps, fully unrolled ------------
         if (mma_warp) {
             tc_fence_after();
@@ -473,17 +486,26 @@ tc_conv_kernel(const void *__restrict__ xin_any, long long n_cells, const float 
             }
         }
         // ---- overlapped with the MMAs of cell i: epilogue of cell i-1, then conv1 of cell i+1 ---------------------------
+        K5T(3);
         if (it > 0) {
             mbar_wait(&s.mbar[buf ^ 1], phase[buf ^ 1]);
             phase[buf ^ 1] ^= 1;
             tc_fence_after();
+            K5T(4);
             epilogue(prev_cell, buf ^ 1);
         }
+        K5T(5);
         if (next < n_cells && !mma_warp) {
             commit_input();
             bar_workers<NWK>();
             conv1_regs();
         }
+        K5T(6);
+#ifdef SVB_K5_TRACE
+        if (blockIdx.x == 0 && it == 20 && (tid == 0 || tid == 320 || tid == 448))
+            printf("K5T tid %d: write_S %lld  barrier %lld  issue %lld  mma_wait %lld  epilogue %lld  conv1 %lld  cell %lld\n", tid, tr[1] - tr[0],
+                   tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[6] - tr[0]);
+#endif
         prev_cell = cell;
     }
     if (it > 0) {  // drain: last cell
