@@ -43,8 +43,8 @@ METRIC = "frames/sec end-to-end (preprocess->warp->81-cell CNN) at 1080p"
 K1_BYTES_PER_FRAME = 3 * H * W + H * W  # 6,220,800 read + 2,073,600 written
 # dram__bytes_read.sum + dram__bytes_write.sum per 1080p frame from the ncu --set full captures under profiles/ (see
 # profiles/README.md for the capture each constant comes from); None = no capture of the current kernel yet
-NCU_TRAFFIC_PER_FRAME = {"k1": int((1.769889e9 + 0.513172992e9) / 256),         # profiles/r2s_k1w_summary.csv
-                         "k4": int((435.445504e6 + 5.876224e6) / 256)}            # profiles/r2s_k4_summary.csv
+NCU_TRAFFIC_PER_FRAME = {"k1": int((1.769168e9 + 0.510258176e9) / 256),         # profiles/r2w_k1w_summary.csv
+                         "k4": int((435.430656e6 + 6.659072e6) / 256)}            # profiles/r2w_k4_summary.csv
 # true MACs only, per cell: conv1 225,792 + conv2 3,612,672; fc1 401,408 + fc2 1,280
 K5_CONV_FLOP_PER_CELL = 2 * (225792 + 3612672)
 K5_FC_FLOP_PER_CELL = 2 * (401408 + 1280)
