@@ -12,6 +12,8 @@
 //                                writes the +-1 classifier input.  The 450x450 board never exists.
 //   stage kernels for the drop-in functions: warp_board_kernel, extract_cells_kernel, cell_prep_kernel
 //   (the latter two are the same device code as K4, entered at a later phase).
+#include <cstdio>
+
 #include "cells_core.cuh"
 #include "common.cuh"
 
@@ -180,15 +182,32 @@ cells_from_frames_kernel(const uint8_t *__restrict__ bgr, int h, int w, const do
         if (cells_bits && tid < CELL) cells_bits[cidx * CELL + tid] = 0u;
         return;
     }
+#ifdef SVB_K4_TRACE
+    long long t0 = clock64();
+#endif
     cellcore::phase_setup(s, tid, tb);
     double mi[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) mi[i] = __ldg(minv + (long long)f * 9 + i);
     __syncthreads();
+#ifdef SVB_K4_TRACE
+    long long t1 = clock64();
+#endif
     cellcore::phase_sample(s, tid, bgr + (long long)f * h * w * 3, h, w, mi, cell / 9, cell % 9);
     __syncthreads();
+#ifdef SVB_K4_TRACE
+    long long t2 = clock64();
+#endif
     cellcore::phase_resize(s, tid, cells_u8 ? cells_u8 + obase : nullptr);
+#ifdef SVB_K4_TRACE
+    __syncthreads();
+    long long t3 = clock64();
+#endif
     cell_tail<WANT_FLOAT>(s, tid, nullptr, cells_pm1 ? cells_pm1 + obase : nullptr, cells_bits ? cells_bits + cidx * CELL : nullptr);
+#ifdef SVB_K4_TRACE
+    long long t4 = clock64();
+    if (tid == 0 && f == 100 && (cell % 20) == 0) printf("K4T cell %d: setup %lld  sample %lld  resize %lld  tail %lld  total %lld\n", cell, t1 - t0, t2 - t1, t3 - t2, t4 - t3, t4 - t0);
+#endif
 }
 
 // drop-in preprocess_cell (+ tensor prep): cells [n][28][28]
