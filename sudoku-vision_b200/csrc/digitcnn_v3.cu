@@ -315,12 +315,15 @@ static const int V3_COUNTS[V3_NT] = {
 static int v3_count(int i) { return V3_COUNTS[i]; }
 
 // tensor-core path (digitcnn_v3_tc.cu)
-int launch_conv3x3_tc(svb_ctx *, const float *, const uint8_t *, const float *, float *, int, int, int, int, int, int, cudaStream_t);
-int pack_conv3x3_tc(svb_ctx *, const float *, uint8_t *, int, int, cudaStream_t);
+int launch_conv3x3_tc(svb_ctx *, const float *, const uint8_t *, const float *, float *, int, int, int, int, int, int, const float *, float *,
+                      cudaStream_t);
+int pack_conv3x3_tc(svb_ctx *, const float *, uint8_t *, int, int, int, cudaStream_t);
 
 // the ten 3x3 convolutions of the residual blocks: index of the weight tensor in p[], cin, cout
-static const int V3_TC_CONV[10][3] = {{2, 32, 32}, {4, 32, 32}, {8, 32, 64}, {10, 64, 64}, {16, 64, 64}, {18, 64, 64},
-                                      {22, 64, 128}, {24, 128, 128}, {30, 128, 128}, {32, 128, 128}};
+// 4th entry: index of the block's projection-shortcut weight (1x1, stride 2), packed right behind the stride-2 convolution's
+// slices because the tensor-core kernel computes it from the same input, or -1
+static const int V3_TC_CONV[10][4] = {{2, 32, 32, -1}, {4, 32, 32, -1}, {8, 32, 64, 14}, {10, 64, 64, -1}, {16, 64, 64, -1}, {18, 64, 64, -1},
+                                      {22, 64, 128, 28}, {24, 128, 128, -1}, {30, 128, 128, -1}, {32, 128, 128, -1}};
 
 struct V3State {
     float *blob = nullptr;
@@ -348,7 +351,7 @@ int digitcnn_v3_load(svb_ctx *ctx, const float *const *tensors, int count, cudaS
         s = new V3State();
         SVB_CUDA_OK(cudaMalloc(&s->blob, total * sizeof(float)));
         size_t tc_total = 0;
-        for (auto &c : V3_TC_CONV) tc_total += (size_t)36 * c[1] * c[2];
+        for (auto &c : V3_TC_CONV) tc_total += (size_t)(c[3] >= 0 ? 40 : 36) * c[1] * c[2];
         SVB_CUDA_OK(cudaMalloc(&s->tc_blob, tc_total));
         ctx->cnn_v3 = s;
     }
@@ -362,10 +365,15 @@ int digitcnn_v3_load(svb_ctx *ctx, const float *const *tensors, int count, cudaS
     }
     size_t tc_off = 0;
     for (auto &c : V3_TC_CONV) {
-        int rc = pack_conv3x3_tc(ctx, s->p[c[0]], s->tc_blob + tc_off, c[1], c[2], st);
+        int rc = pack_conv3x3_tc(ctx, s->p[c[0]], s->tc_blob + tc_off, c[1], c[2], 9, st);
         if (rc) return rc;
         s->tc_img[c[0]] = s->tc_blob + tc_off;
         tc_off += (size_t)36 * c[1] * c[2];
+        if (c[3] >= 0) {
+            rc = pack_conv3x3_tc(ctx, s->p[c[3]], s->tc_blob + tc_off, c[1], c[2], 1, st);
+            if (rc) return rc;
+            tc_off += (size_t)4 * c[1] * c[2];
+        }
     }
     s->loaded = true;
     return SVB_OK;
@@ -387,9 +395,10 @@ int launch_digitcnn_v3(svb_ctx *ctx, const float *x, long long n, float *logits,
     SVB_CUDA_OK(cudaFuncSetAttribute(conv3x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     int rc = SVB_OK;
     const bool use_tc = ctx->classifier_mode == 0;
-    auto conv = [&](const float *in, int wi, float *out, int cin, int cout, int hin, int stride, int relu, int m) {
+    auto conv = [&](const float *in, int wi, float *out, int cin, int cout, int hin, int stride, int relu, int m, const float *sc_bias,
+                    float *sc_out) {
         if (use_tc && s->tc_img[wi]) {  // block convolutions: tcgen05 implicit GEMM (the 1-channel stem stays on the CUDA cores)
-            const int r = launch_conv3x3_tc(ctx, in, s->tc_img[wi], s->p[wi + 1], out, cin, cout, hin, stride, relu, m, st);
+            const int r = launch_conv3x3_tc(ctx, in, s->tc_img[wi], s->p[wi + 1], out, cin, cout, hin, stride, relu, m, sc_bias, sc_out, st);
             if (!rc) rc = r;
             return;
         }
@@ -402,11 +411,18 @@ int launch_digitcnn_v3(svb_ctx *ctx, const float *x, long long n, float *logits,
     // one residual block: X (cin,hin) -> result in X's buffer slot returned via pointer swap
     auto block = [&](float *&X, float *&T1, float *&T2, int wi, int cin, int cout, int hin, int stride, int sc_wi, int m) {
         const int hout = (hin - 1) / stride + 1, hw = hout * hout;
-        conv(X, wi, T1, cin, cout, hin, stride, 1, m);           // conv1 + bn1 + relu
-        conv(T1, wi + 2, T2, cout, cout, hout, 1, 0, m);         // conv2 + bn2
+        // tensor-core path: the stride-2 convolution also produces the block's projection shortcut (second half of T1's slot)
+        const bool sc_tc = use_tc && sc_wi >= 0;
+        float *SC = T1 + buf / 2;
+        conv(X, wi, T1, cin, cout, hin, stride, 1, m, sc_tc ? s->p[sc_wi + 1] : nullptr, sc_tc ? SC : nullptr);  // conv1 + bn1 + relu
+        conv(T1, wi + 2, T2, cout, cout, hout, 1, 0, m, nullptr, nullptr);                                        // conv2 + bn2
         // SE gate + shortcut + residual + ReLU into T1 (conv1's output is no longer needed); X and T1 swap roles
         const float *f1 = s->p[wi + 4], *f2 = s->p[wi + 5], *pw = sc_wi >= 0 ? s->p[sc_wi] : nullptr, *pb = sc_wi >= 0 ? s->p[sc_wi + 1] : nullptr;
         int r2 = SVB_OK;
+        if (sc_tc) {  // the shortcut is a tensor like y: the identity form of the kernel
+            if (cout == 64) r2 = launch_se_combine<64, 196, 8, 0>(ctx, T2, SC, f1, f2, nullptr, nullptr, T1, m, st);
+            else r2 = launch_se_combine<128, 49, 8, 0>(ctx, T2, SC, f1, f2, nullptr, nullptr, T1, m, st);
+        } else
         if (cout == 32 && hw == 784 && sc_wi < 0) r2 = launch_se_combine<32, 784, 16, 0>(ctx, T2, X, f1, f2, pw, pb, T1, m, st);
         else if (cout == 64 && hw == 196 && sc_wi >= 0 && cin == 32) r2 = launch_se_combine<64, 196, 16, 32>(ctx, T2, X, f1, f2, pw, pb, T1, m, st);
         else if (cout == 64 && hw == 196 && sc_wi < 0) r2 = launch_se_combine<64, 196, 8, 0>(ctx, T2, X, f1, f2, pw, pb, T1, m, st);
@@ -419,7 +435,7 @@ int launch_digitcnn_v3(svb_ctx *ctx, const float *x, long long n, float *logits,
     for (long long c0 = 0; c0 < n && !rc; c0 += CHUNK) {
         const int m = (int)((n - c0 < CHUNK) ? n - c0 : CHUNK);
         float *X = A, *T1 = B, *T2 = Cb;
-        conv(x + c0 * 784, 0, X, 1, 32, 28, 1, 1, m);             // stem
+        conv(x + c0 * 784, 0, X, 1, 32, 28, 1, 1, m, nullptr, nullptr);  // stem
         block(X, T1, T2, 2, 32, 32, 28, 1, -1, m);                // layer1
         block(X, T1, T2, 8, 32, 64, 28, 2, 14, m);                // layer2 (+ shortcut 14,15)
         block(X, T1, T2, 16, 64, 64, 14, 1, -1, m);               // layer3

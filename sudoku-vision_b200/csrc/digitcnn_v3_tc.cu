@@ -148,9 +148,12 @@ struct Geo {
     static constexpr int NKC = CIN / 8;                             // K chunks
     static constexpr int PARTB = NKC * ROWS * 16;                   // bytes of one fp16 part of the activations
     static constexpr int KS = CIN < 64 ? CIN : ((S2 && CIN == 64) ? 32 : 64);  // K of one weight slice (shared memory budget)
-    static constexpr int NSLICE = 9 * (CIN / KS);
+    // the stride-2 layers also compute their block's projection shortcut (1x1, stride 2, ml/model_v3.py:62-67): its input is
+    // parity plane (0, 0) = the centre tap's operand, so it is CIN / KS more weight slices into COUT more accumulator columns
+    static constexpr int NMAIN = 9 * (CIN / KS);
+    static constexpr int NSLICE = NMAIN + (S2 ? CIN / KS : 0);
     static constexpr int SLB = COUT * KS * 2;                       // bytes of one part of one weight slice
-    static constexpr int TCOLS = MT * COUT;                         // TMEM columns used
+    static constexpr int TCOLS = (S2 ? 2 : 1) * MT * COUT;          // TMEM columns used (stride 2: main + shortcut accumulators)
     static constexpr bool DB = 2 * TCOLS <= 512;                    // two accumulator sets: epilogue(i-1) under the MMAs of pass i
     static constexpr int TUSED = DB ? 2 * TCOLS : TCOLS;
     static constexpr int TALLOC = TUSED <= 32 ? 32 : (TUSED <= 64 ? 64 : (TUSED <= 128 ? 128 : (TUSED <= 256 ? 256 : 512)));
@@ -166,10 +169,10 @@ struct Geo {
 template <int CIN, int COUT, int H, int STRIDE>
 __global__ void __launch_bounds__(NT, 1)
 conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg, const float *__restrict__ bias,
-                  float *__restrict__ out, int n_cells, int relu) {
+                  float *__restrict__ out, int n_cells, int relu, const float *__restrict__ sc_bias, float *__restrict__ sc_out) {
     using GEO = Geo<CIN, COUT, H>;
     constexpr int GW = GEO::GW, G = GEO::G, CB = GEO::CB, MT = GEO::MT, ROWS = GEO::ROWS, NKC = GEO::NKC, PARTB = GEO::PARTB;
-    constexpr int KS = GEO::KS, NSLICE = GEO::NSLICE, SLB = GEO::SLB, HH = H * H, HO = GEO::HO, PROWS = GEO::PROWS;
+    constexpr int KS = GEO::KS, NSLICE = GEO::NSLICE, NMAIN = GEO::NMAIN, SLB = GEO::SLB, HH = H * H, HO = GEO::HO, PROWS = GEO::PROWS;
     static_assert(GEO::S2 == (STRIDE == 2) && HO == (H - 1) / STRIDE + 1, "stride-2 layers are the ones that change the channel count");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -243,14 +246,16 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
     // Everything that does not depend on the slice is a compile-time constant added to two per-slice base descriptors (all
     // shared-memory addresses are below 256 KB, so adding (byte offset >> 4) never carries out of the 14-bit field).
     auto issue_slice = [&](int s, int buf, uint32_t tacc, bool single) {  // single: called by one elected thread
-        const int t = s / (CIN / KS), kb = s % (CIN / KS);
+        const bool sc = s >= NMAIN;  // a slice of the projection shortcut: centre tap, its own accumulators
+        const int t = sc ? 4 : s / (CIN / KS), kb = sc ? s - NMAIN : s % (CIN / KS);
         const int dy = t / 3 - 1, dx = t % 3 - 1;
         // stride 2: plane (dy & 1, dx & 1) at grid offset (floor(dy / 2), floor(dx / 2))
         const int row0 = GEO::S2 ? ((dy & 1) * 2 + (dx & 1)) * PROWS + (1 + (dy < 0 ? -1 : 0)) * GW + (dx < 0 ? -1 : 0) + OFF
                                  : (1 + dy) * GW + dx + OFF;
         const uint64_t ad0 = make_desc(a_base + (uint32_t)(kb * (KS / 8) * ROWS * 16) + (uint32_t)row0 * 16u, ROWS * 16, 128);
         const uint64_t bd0 = make_desc(b_base + (uint32_t)(buf * 2 * SLB), 128, (KS / 8) * 128);
-        const uint32_t acc0 = s ? 1u : 0u;
+        const uint32_t acc0 = (s == 0 || s == NMAIN) ? 0u : 1u;
+        const uint32_t tsc = sc ? (uint32_t)(MT * COUT) : 0u;
 #pragma unroll
         for (int combo = 0; combo < 3; ++combo) {
             const int pa = (combo == 2) ? 1 : 0, pb = (combo == 1) ? 1 : 0;  // hi*hi, hi*lo, lo*hi
@@ -263,7 +268,7 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
                 for (int tt = 0; tt < (MT + NIW - 1) / NIW; ++tt) {
                     const int tile = warp - WISSUE + NIW * tt;
                     if (tile < MT && (single || lane == 0))
-                        umma_f16(tacc + (uint32_t)(tile * COUT), ad0 + (uint64_t)((a_off + (uint32_t)(tile * 128 * 16)) >> 4),
+                        umma_f16(tacc + tsc + (uint32_t)(tile * COUT), ad0 + (uint64_t)((a_off + (uint32_t)(tile * 128 * 16)) >> 4),
                                  bd0 + (uint64_t)(b_off >> 4), idesc, (combo | ks) ? 1u : acc0);
                 }
             }
@@ -311,22 +316,25 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
     // TMEM -> + bias -> [ReLU] -> fp32 NCHW
     auto epilogue = [&](int c0, uint32_t tacc, int ngroups) {  // ngroups = 3: warps 0..11 only (the issuing warps are busy)
         const int q = warp & 3, grp = warp >> 2;  // TMEM lane quarter (hardware rule: warp % 4), work group
-        constexpr int NCB = COUT / 32;
+        constexpr int NCB = COUT / 32, NBLK = (GEO::S2 ? 2 : 1) * MT * NCB;
         if (grp >= ngroups) return;
-        for (int blk = grp; blk < MT * NCB; blk += ngroups) {
-            const int tile = blk / NCB, cb = blk - tile * NCB;
+        for (int blk = grp; blk < NBLK; blk += ngroups) {
+            const bool sc = blk >= MT * NCB;  // second half: the shortcut's accumulators -> sc_out (+ its folded-BN bias, no ReLU)
+            const int b2 = sc ? blk - MT * NCB : blk, tile = b2 / NCB, cb = b2 - tile * NCB;
             uint32_t v[32];
-            tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * COUT + cb * 32), v);
+            tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)((sc ? MT * COUT : 0) + tile * COUT + cb * 32), v);
             const int m = tile * 128 + q * 32 + lane;
             const int j = m / CB, rem = m - j * CB, y = rem / GW, x = rem - y * GW;
             const int cell = c0 + j;
             const bool ok = (j < G) && (cell < n_cells) && (y < HO) && (x < HO);
             if (ok) {
-                float *dst = out + ((size_t)cell * COUT + cb * 32) * (HO * HO) + y * HO + x;
+                float *dst = (sc ? sc_out : out) + ((size_t)cell * COUT + cb * 32) * (HO * HO) + y * HO + x;
+                const float *bb = sc ? sc_bias : s_bias;
+                const bool rl = relu && !sc;
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
-                    float f = __uint_as_float(v[c]) + s_bias[cb * 32 + c];
-                    if (relu) f = fmaxf(f, 0.f);
+                    float f = __uint_as_float(v[c]) + bb[cb * 32 + c];
+                    if (rl) f = fmaxf(f, 0.f);
                     dst[(size_t)c * (HO * HO)] = f;
                 }
             }
@@ -448,10 +456,10 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
 
 // weights: folded conv weight w[COUT][CIN][3][3] -> slices s = tap * (CIN/KS) + kblock, each [part][canonical (n, kk)]:
 // element (n, kk) of a part at (n/8)*(KS/8*128) + (kk/8)*128 + (n%8)*16 + (kk%8)*2
-__global__ void pack_v3_kernel(const float *__restrict__ w, uint8_t *__restrict__ img, int cin, int cout) {
+__global__ void pack_v3_kernel(const float *__restrict__ w, uint8_t *__restrict__ img, int cin, int cout, int ntaps) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cout * cin * 9) return;
-    const int t = i % 9, ci = (i / 9) % cin, n = i / (9 * cin);
+    if (i >= cout * cin * ntaps) return;
+    const int t = i % ntaps, ci = (i / ntaps) % cin, n = i / (ntaps * cin);
     const int ks = cin < 64 ? cin : ((cin != cout && cin == 64) ? 32 : 64), kb = ci / ks, kk = ci % ks;  // = Geo::KS
     const int s = t * (cin / ks) + kb;
     const size_t slb = (size_t)cout * ks * 2;
@@ -464,13 +472,14 @@ __global__ void pack_v3_kernel(const float *__restrict__ w, uint8_t *__restrict_
 
 template <int CIN, int COUT, int H, int STRIDE>
 static int launch_one(svb_ctx *ctx, const float *in, const uint8_t *wimg, const float *bias, float *out, int n, int relu,
-                      cudaStream_t st) {
+                      const float *sc_bias, float *sc_out, cudaStream_t st) {
     using GEO = Geo<CIN, COUT, H>;
     auto kern = conv3x3_tc_kernel<CIN, COUT, H, STRIDE>;
     SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEO::SMEM));
     const int n_pass = (n + GEO::G - 1) / GEO::G;
     const int grid = n_pass < ctx->sm_count ? n_pass : ctx->sm_count;
-    kern<<<grid, NT, GEO::SMEM, st>>>(in, wimg, bias, out, n, relu);
+    SVB_REQUIRE(!GEO::S2 || (sc_bias != nullptr && sc_out != nullptr), SVB_ERR_INVALID, "conv3x3_tc: the stride-2 layers also produce the projection shortcut");
+    kern<<<grid, NT, GEO::SMEM, st>>>(in, wimg, bias, out, n, relu, sc_bias, sc_out);
     return check_launch(ctx, "k6tc::conv3x3_tc_kernel");
 }
 
@@ -478,20 +487,20 @@ static int launch_one(svb_ctx *ctx, const float *in, const uint8_t *wimg, const 
 
 // dispatch on the five layer shapes DigitCNNv3 has (ml/model_v3.py:113-150); anything else -> SVB_ERR_UNSUPPORTED
 int launch_conv3x3_tc(svb_ctx *ctx, const float *in, const uint8_t *wimg, const float *bias, float *out, int cin, int cout,
-                      int hin, int stride, int relu, int n, cudaStream_t st) {
+                      int hin, int stride, int relu, int n, const float *sc_bias, float *sc_out, cudaStream_t st) {
     using namespace k6tc;
-    if (cin == 32 && cout == 32 && hin == 28 && stride == 1) return launch_one<32, 32, 28, 1>(ctx, in, wimg, bias, out, n, relu, st);
-    if (cin == 32 && cout == 64 && hin == 28 && stride == 2) return launch_one<32, 64, 28, 2>(ctx, in, wimg, bias, out, n, relu, st);
-    if (cin == 64 && cout == 64 && hin == 14 && stride == 1) return launch_one<64, 64, 14, 1>(ctx, in, wimg, bias, out, n, relu, st);
-    if (cin == 64 && cout == 128 && hin == 14 && stride == 2) return launch_one<64, 128, 14, 2>(ctx, in, wimg, bias, out, n, relu, st);
-    if (cin == 128 && cout == 128 && hin == 7 && stride == 1) return launch_one<128, 128, 7, 1>(ctx, in, wimg, bias, out, n, relu, st);
+    if (cin == 32 && cout == 32 && hin == 28 && stride == 1) return launch_one<32, 32, 28, 1>(ctx, in, wimg, bias, out, n, relu, nullptr, nullptr, st);
+    if (cin == 32 && cout == 64 && hin == 28 && stride == 2) return launch_one<32, 64, 28, 2>(ctx, in, wimg, bias, out, n, relu, sc_bias, sc_out, st);
+    if (cin == 64 && cout == 64 && hin == 14 && stride == 1) return launch_one<64, 64, 14, 1>(ctx, in, wimg, bias, out, n, relu, nullptr, nullptr, st);
+    if (cin == 64 && cout == 128 && hin == 14 && stride == 2) return launch_one<64, 128, 14, 2>(ctx, in, wimg, bias, out, n, relu, sc_bias, sc_out, st);
+    if (cin == 128 && cout == 128 && hin == 7 && stride == 1) return launch_one<128, 128, 7, 1>(ctx, in, wimg, bias, out, n, relu, nullptr, nullptr, st);
     set_error("conv3x3_tc: no tensor-core kernel for cin=%d cout=%d h=%d stride=%d", cin, cout, hin, stride);
     return SVB_ERR_UNSUPPORTED;
 }
 
-int pack_conv3x3_tc(svb_ctx *ctx, const float *w, uint8_t *img, int cin, int cout, cudaStream_t st) {
-    const int tot = cout * cin * 9;
-    k6tc::pack_v3_kernel<<<(tot + 255) / 256, 256, 0, st>>>(w, img, cin, cout);
+int pack_conv3x3_tc(svb_ctx *ctx, const float *w, uint8_t *img, int cin, int cout, int ntaps, cudaStream_t st) {
+    const int tot = cout * cin * ntaps;
+    k6tc::pack_v3_kernel<<<(tot + 255) / 256, 256, 0, st>>>(w, img, cin, cout, ntaps);
     return check_launch(ctx, "k6tc::pack_v3_kernel");
 }
 
