@@ -3,21 +3,20 @@
 //
 // Precision.  The north star asks for logits within 1e-3 of the fp32 reference.  fp16 operands alone
 // (11-bit mantissa) give ~1e-2; so every operand is split x = hi + lo (two fp16 numbers, 22 bits) and
-// each product is issued as three MMAs hi*hi + hi*lo + lo*hi into the same fp32 TMEM accumulator.
-// conv1 (K = 9, 5 % of the MACs) runs in fp32 on the CUDA cores with packed fma.rn.f32x2.
+// each product is the sum of three MMAs hi*hi + hi*lo + lo*hi in fp32 TMEM accumulators.
+// conv1 (K = 9, 5 % of the MACs) runs in fp32 on the CUDA cores.
 //
-// tc_conv_kernel (persistent, one CTA per SM, 256 threads), per cell:
-//   1. conv1+bias+ReLU+2x2 max-pool in registers -> pooled activations P[16x16 padded grid][32 ch]
-//      written as fp16 hi/lo into shared memory in the UMMA canonical K-major (no-swizzle) layout,
-//      THREE times, pre-shifted by dx = -1,0,+1 rows.  With the grid flattened to rows m = y*16 + x
-//      (zero halo columns/rows), the im2col operand of tap (dy,dx) is then just the dx-copy viewed
-//      at a row offset of 16*dy (a multiple of the 8-row core matrix): the implicit GEMM needs no
-//      per-tap copies, only a different descriptor start address.
-//   2. one elected thread issues 2 tiles x 3 splits x 9 taps x 2 k-steps = 108 tcgen05.mma
-//      (M=128, N=64, K=16) and one tcgen05.commit; accumulators: 2 x 64 TMEM columns.
-//   3. epilogue: tcgen05.ld (32 lanes x 32 columns per warp), 2x2 max-pool by warp shuffles,
-//      +bias, ReLU, fp16 hi/lo split, 128-byte stores of the 49x64 feature block of the cell
-//      (K order (pixel, channel); fc1's weights are permuted to match at pack time).
+// tc_conv_kernel<BITS> (persistent, one CTA per SM, 512 threads: 14 worker warps + 2 MMA-issuing warps), per cell:
+//   1. conv1+bias+ReLU+2x2 max-pool in registers (BITS: by a 512-pattern table from the cell's 28 bit rows; floats: packed
+//      FMAs) -> pooled activations P[16x16 zero-haloed grid][32 ch] written ONCE as fp16 hi/lo into shared memory in the UMMA
+//      canonical K-major (no-swizzle) layout, K-chunk-major: with the grid flattened to rows m = y*16 + x the im2col operand
+//      of tap (dy,dx) is the same buffer at a start address shifted by 16 dy + dx rows — no per-tap copies.  Two buffers.
+//   2. warps 14 / 15 issue one M tile each: 9 taps x 2 k-steps x (A_hi x [B_hi|B_lo] (N=128) + A_lo x B_hi (N=64)) = 36
+//      tcgen05.mma per tile, as a rolled loop inside one elected thread (uniform-datapath descriptors), then tcgen05.commit;
+//      accumulators: 2 buffers x 2 tiles x 128 TMEM columns.
+//   3. epilogue (worker warps, under the MMAs of the next cell): tcgen05.ld (32 lanes x 32 columns per warp), sum of the two
+//      accumulator halves, 2x2 max-pool as a shuffle butterfly, +bias, ReLU, fp16 hi/lo split, 128-bit stores of the 49x64
+//      feature block of the cell (K order (pixel, channel); fc1's weights are permuted to match at pack time).
 // tc_fc_tma_kernel: [cells x 3136] x [3136 x 128] with the same split, 128-cell tiles fed by TMA, then bias+ReLU,
 //   fc2 (128x10, CUDA cores), softmax-max/argmax.
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)

@@ -6,6 +6,7 @@
 //
 // Precision: as in digitcnn_tc.cu, every operand is split x = hi + lo (two fp16 numbers) and each product is issued as
 // three MMAs (hi hi + hi lo + lo hi) into the same accumulator — fp32-grade results (logits within 1e-3).
+// The rest of the forward pass (stem, SE gate + residual: k6::se_combine_kernel, head) is in digitcnn_v3.cu.
 //
 // Implicit GEMM without im2col.  A pass handles G cells (1 / 2 / 4 for 28^2 / 14^2 / 7^2 inputs).  Their activations
 // are converted to fp16 hi/lo and laid out in shared memory as a zero-haloed grid of width GW (32 / 16 / 8, at least
@@ -14,9 +15,12 @@
 // contiguous) and LBO = ROWS*16 (between the K chunks), so rows are a plain 16-byte-pitch array and the operand of tap
 // (dy, dx) for output rows m0..m0+127 is the SAME buffer viewed at start address + ((1+dy)*GW + dx + m0)*16: nine
 // descriptors, no copies.  The two stride-2 layers read four parity planes of their input laid out on the output grid (Geo).
-// Weights are prepacked (hi/lo, canonical layout) in slices of one tap x 64 input channels and streamed through a
-// cp.async double buffer while the previous slice's MMAs run; the epilogue reads TMEM with tcgen05.ld, adds the bias,
-// applies ReLU and writes fp32 NCHW.
+// (and also produce their block's 1x1 projection shortcut: the centre tap's operand with its own weights and accumulators).
+// Weights are prepacked (hi/lo, canonical layout) in slices of one tap x 32 / 64 input channels: resident in shared memory
+// for the 32 -> 32 layers, otherwise streamed through a two-buffer ring (one producer thread, cp.async.bulk onto `full`
+// mbarriers; tcgen05.commit frees a buffer through its `empty` mbarrier).  Warps 12..15 issue the MMAs / feed the ring, warps
+// 0..11 run the epilogue of the previous pass under them (tcgen05.ld, + bias, ReLU, fp32 NCHW); all warps convert the next
+// pass's activations.
 #include <cuda_fp16.h>
 #include <cstdio>
 
