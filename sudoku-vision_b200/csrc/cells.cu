@@ -166,8 +166,11 @@ __device__ __forceinline__ void cell_tail(Smem &s, int tid, uint8_t *thr, float 
 
 // K4: one CTA per (frame, cell).  Outputs (each optional): the u8 cell (extract_cells), the +-1 float tensor
 // (the drop-in's view), the 28 bit rows the batched classifier reads.
+#ifndef SVB_K4_MINB
+#define SVB_K4_MINB 7  // 72 registers: no spills in the sampling loop; 1.340 ms against 1.364 (8) and 1.448 (6) per 1024 frames
+#endif
 template <bool WANT_FLOAT>
-__global__ void __launch_bounds__(NT, 8)
+__global__ void __launch_bounds__(NT, SVB_K4_MINB)
 cells_from_frames_kernel(const uint8_t *__restrict__ bgr, int h, int w, const double *__restrict__ minv,
                          const uint8_t *__restrict__ found, const Tables *__restrict__ tb, uint8_t *__restrict__ cells_u8,
                          float *__restrict__ cells_pm1, uint32_t *__restrict__ cells_bits) {
