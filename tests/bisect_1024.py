@@ -1,6 +1,6 @@
 """GPU-side bisect of a whole-path parity failure on a bench-style batch: every frame against the C oracle, stage by stage
 (corners -> u8 cells -> +-1 bits -> logits); frames that differ are dumped to gpurun_out/ for CPU reproduction with the
-host-compiled cores.  Usage (GPU box): python tools/dbg_1024.py [n_frames]"""
+host-compiled cores.  Usage (GPU box): python tests/bisect_1024.py [n_frames]"""
 import concurrent.futures as cf
 import os
 import sys

@@ -1,7 +1,7 @@
 """Parity soak on the GPU box: many frames of several sizes / rotations through the product path, every stage against the
 C oracle (test infrastructure) on all host cores.  Rare-event hunting — the 1024-frame sweep of round 2 found a one-pixel
 difference in 4 of 82,944 cells that no smaller test saw.  Prints one summary line per section; mismatching inputs are
-dumped to gpurun_out/soak_*.npz.  Usage: python tools/soak.py [--frames-per-size 192] [--cells 300000] [--sections v1,cells,k1,jpeg]"""
+dumped to gpurun_out/soak_*.npz.  Usage: python tests/soak.py [--frames-per-size 192] [--cells 300000] [--sections v1,cells,k1,jpeg]"""
 import argparse
 import concurrent.futures as cf
 import os
