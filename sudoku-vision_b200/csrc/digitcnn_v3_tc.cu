@@ -40,6 +40,9 @@ constexpr int OFF = 8;  // zero rows before the first grid row
 #ifndef SVB_V3_ROWPAD
 #define SVB_V3_ROWPAD 0
 #endif
+#ifndef SVB_V3_ND
+#define SVB_V3_ND 1
+#endif
 
 // ---- PTX helpers (same conventions as digitcnn_tc.cu) ----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -141,7 +144,13 @@ struct Geo {
     static constexpr int HO = S2 ? H / 2 : H;                       // output side = side of the row grid
     static constexpr int NPL = S2 ? 4 : 1;                          // parity planes of the input
     static constexpr int GW = (HO == 28) ? 32 : (HO == 14 ? 16 : 8);  // grid width (>= HO + 1)
-    static constexpr int G = S2 ? (H == 28 ? 1 : 2) : ((H == 28) ? 1 : (H == 14 ? 2 : 4));  // cells per pass
+    // N-doubling (the 64 -> 64 layers): [W_hi | W_lo] lie side by side in a weight slice, so ONE N = 2 COUT MMA computes
+    // A_hi x W_hi and A_hi x W_lo with a single fetch of A_hi (these layers are bound by the A-operand fetch: 50 cycles per
+    // M128 N64 K16 MMA for 32 of math): 2 MMAs (64 + 48 cycles) per product instead of 3 x 50.  The accumulators double
+    // (2 COUT columns per tile, summed in the epilogue), so a pass takes one cell instead of two to keep two accumulator
+    // sets in TMEM, and the weight ring gets four buffers because a slice's MMAs are then shorter than a load.
+    static constexpr bool ND = !S2 && CIN == 64 && COUT == 64 && SVB_V3_ND;
+    static constexpr int G = ND ? 1 : (S2 ? (H == 28 ? 1 : 2) : ((H == 28) ? 1 : (H == 14 ? 2 : 4)));  // cells per pass
     static constexpr int CB = (HO + 1) * GW;                        // rows per cell block (bottom halo shared with the next top halo)
     static constexpr int MROWS = (G - 1) * CB + (HO - 1) * GW + HO; // output rows that can be valid
     static constexpr int MT = (MROWS + 127) / 128;                  // M tiles of 128 rows
@@ -157,14 +166,16 @@ struct Geo {
     static constexpr int NMAIN = 9 * (CIN / KS);
     static constexpr int NSLICE = NMAIN + (S2 ? CIN / KS : 0);
     static constexpr int SLB = COUT * KS * 2;                       // bytes of one part of one weight slice
-    static constexpr int TCOLS = (S2 ? 2 : 1) * MT * COUT;          // TMEM columns used (stride 2: main + shortcut accumulators)
+    static constexpr int TW = (ND ? 2 : 1) * COUT;                  // accumulator columns of one M tile
+    static constexpr int TCOLS = (S2 ? 2 : 1) * MT * TW;            // TMEM columns used (stride 2: main + shortcut accumulators)
     static constexpr bool DB = 2 * TCOLS <= 512;                    // two accumulator sets: epilogue(i-1) under the MMAs of pass i
     static constexpr int TUSED = DB ? 2 * TCOLS : TCOLS;
     static constexpr int TALLOC = TUSED <= 32 ? 32 : (TUSED <= 64 ? 64 : (TUSED <= 128 ? 128 : (TUSED <= 256 ? 256 : 512)));
     // small layers keep every weight slice resident in shared memory; the others stream them through two buffers
     static constexpr bool RESIDENT = 2 * (size_t)PARTB + (size_t)NSLICE * 2 * SLB <= 200 * 1024;
-    static constexpr int NBUF = RESIDENT ? NSLICE : 2;
-    static constexpr size_t SMEM = 1024 + 2 * (size_t)PARTB + (size_t)NBUF * 2 * SLB + COUT * 4 + 64;
+    static constexpr int RING = ND ? 4 : 2;                         // buffers of the weight ring (streamed layers)
+    static constexpr int NBUF = RESIDENT ? NSLICE : RING;
+    static constexpr size_t SMEM = 1024 + 2 * (size_t)PARTB + (size_t)NBUF * 2 * SLB + COUT * 4 + 128;
     static_assert(TCOLS <= 512, "accumulators exceed TMEM");
     static_assert(HO < GW, "grid needs a zero column");
 };
@@ -184,7 +195,8 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
     uint8_t *sB = sA + 2 * (size_t)PARTB;            // [NBUF buffers][2 parts][SLB]
     float *s_bias = (float *)(sB + (size_t)GEO::NBUF * 2 * SLB);
     unsigned long long *mbar = (unsigned long long *)(s_bias + COUT);
-    uint32_t *s_tmem = (uint32_t *)(mbar + 5);
+    constexpr int RING = GEO::RING, TW = GEO::TW;
+    uint32_t *s_tmem = (uint32_t *)(mbar + 2 * RING + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // Roles (round 2, from per-phase clock64 traces): the MMA issue of a pass blocks on the tensor pipe's queue for the whole
     // MMA phase (15.6 k of a 21.5 k-cycle pass of the 32-channel layers), so a warp that issues must not owe the pass any
@@ -197,15 +209,15 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
     constexpr int WISSUE = NT / 32 - 4, NIW = GEO::RESIDENT ? 4 : 2, NISSUE = MT < NIW ? MT : NIW;
     const bool issuer = warp >= WISSUE && warp - WISSUE < NISSUE;
     const bool producer = !GEO::RESIDENT && warp == WISSUE + 2;
-    unsigned long long *fbar = mbar + 2, *dbar = mbar + 4;  // full[2] (weight ring), done (all MMAs of a pass)
+    unsigned long long *fbar = mbar + RING, *dbar = mbar + 2 * RING;  // empty[RING] = mbar, full[RING], done (all MMAs of a pass)
 
     for (int i = tid; i < 2 * PARTB / 16; i += NT) reinterpret_cast<uint4 *>(sA)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < COUT; i += NT) s_bias[i] = bias[i];
     if (tid == 0) {  // one arrival per issuing warp (each commits its own MMAs)
-        mbar_init(&mbar[0], NISSUE);  // resident: MMAs of a pass done; streaming: ring buffer 0 / 1 free again ("empty")
-        mbar_init(&mbar[1], NISSUE);
-        mbar_init(&fbar[0], 1);
-        mbar_init(&fbar[1], 1);
+        for (int b = 0; b < RING; ++b) {
+            mbar_init(&mbar[b], NISSUE);  // resident: [0] = MMAs of a pass done; streaming: ring buffer b free again ("empty")
+            mbar_init(&fbar[b], 1);
+        }
         mbar_init(dbar, NISSUE);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -214,7 +226,7 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
-    const uint32_t idesc = make_idesc(128, COUT);
+    const uint32_t idesc = make_idesc(128, COUT), idesc2 = make_idesc(128, 2 * COUT);
     const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
     uint32_t ph[2] = {0, 0};
 
@@ -240,8 +252,7 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
         for (int s = 0; s < NSLICE; ++s) load_slice(s, s);
         cp_async_wait<0>();
     } else if (producer && lane == 0 && total_slices > 0) {  // ring prologue: slices 0 and 1
-        load_slice_bulk(0, 0);
-        load_slice_bulk(1 % NSLICE, 1);
+        for (int g = 0; g < RING && g < total_slices; ++g) load_slice_bulk(g % NSLICE, g);
     }
     // the MMAs of one weight slice (one tap x KS input channels) for ONE M tile of the pass.  An issue is a serial
     // instruction stream of ~9 instructions with an ELECT / R2UR round trip (~80 cycles per MMA measured with one issuing
@@ -259,10 +270,12 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
         const uint64_t ad0 = make_desc(a_base + (uint32_t)(kb * (KS / 8) * ROWS * 16) + (uint32_t)row0 * 16u, ROWS * 16, 128);
         const uint64_t bd0 = make_desc(b_base + (uint32_t)(buf * 2 * SLB), 128, (KS / 8) * 128);
         const uint32_t acc0 = (s == 0 || s == NMAIN) ? 0u : 1u;
-        const uint32_t tsc = sc ? (uint32_t)(MT * COUT) : 0u;
+        const uint32_t tsc = sc ? (uint32_t)(MT * TW) : 0u;
 #pragma unroll
-        for (int combo = 0; combo < 3; ++combo) {
-            const int pa = (combo == 2) ? 1 : 0, pb = (combo == 1) ? 1 : 0;  // hi*hi, hi*lo, lo*hi
+        for (int combo = 0; combo < (GEO::ND ? 2 : 3); ++combo) {
+            // three products hi*hi, hi*lo, lo*hi; N-doubling: A_hi x [W_hi | W_lo] (N = 2 COUT), then A_lo x W_hi
+            const int pa = GEO::ND ? combo : ((combo == 2) ? 1 : 0), pb = GEO::ND ? 0 : ((combo == 1) ? 1 : 0);
+            const uint32_t id = (GEO::ND && combo == 0) ? idesc2 : idesc;
 #pragma unroll
             for (int ks = 0; ks < KS / 16; ++ks) {
                 const uint32_t a_off = (uint32_t)(pa * PARTB + ks * 2 * ROWS * 16);
@@ -272,8 +285,8 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
                 for (int tt = 0; tt < (MT + NIW - 1) / NIW; ++tt) {
                     const int tile = warp - WISSUE + NIW * tt;
                     if (tile < MT && (single || lane == 0))
-                        umma_f16(tacc + tsc + (uint32_t)(tile * COUT), ad0 + (uint64_t)((a_off + (uint32_t)(tile * 128 * 16)) >> 4),
-                                 bd0 + (uint64_t)(b_off >> 4), idesc, (combo | ks) ? 1u : acc0);
+                        umma_f16(tacc + tsc + (uint32_t)(tile * TW), ad0 + (uint64_t)((a_off + (uint32_t)(tile * 128 * 16)) >> 4),
+                                 bd0 + (uint64_t)(b_off >> 4), id, (combo | ks) ? 1u : acc0);
                 }
             }
         }
@@ -326,7 +339,13 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
             const bool sc = blk >= MT * NCB;  // second half: the shortcut's accumulators -> sc_out (+ its folded-BN bias, no ReLU)
             const int b2 = sc ? blk - MT * NCB : blk, tile = b2 / NCB, cb = b2 - tile * NCB;
             uint32_t v[32];
-            tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)((sc ? MT * COUT : 0) + tile * COUT + cb * 32), v);
+            tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)((sc ? MT * TW : 0) + tile * TW + cb * 32), v);
+            if (GEO::ND) {  // the A_hi x W_lo product sits COUT columns further
+                uint32_t v2[32];
+                tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * TW + COUT + cb * 32), v2);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(v2[c]));
+            }
             const int m = tile * 128 + q * 32 + lane;
             const int j = m / CB, rem = m - j * CB, y = rem / GW, x = rem - y * GW;
             const int cell = c0 + j;
@@ -400,8 +419,8 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
                 if (elect_one()) {
 #pragma unroll 1
                     for (int s = 0; s < NSLICE; ++s) {
-                        const int g = gs0 + s, b = g & 1;
-                        mbar_wait(&fbar[b], (uint32_t)((g >> 1) & 1));
+                        const int g = gs0 + s, b = g % RING;
+                        mbar_wait(&fbar[b], (uint32_t)((g / RING) & 1));
                         tc_fence_after();
                         issue_slice(s, b, tacc, true);
                         umma_commit(&mbar[b]);  // buffer b is free again once these MMAs have read it
@@ -416,11 +435,11 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
             } else if (producer) {
                 if (lane == 0) {
 #pragma unroll 1
-                    for (int s = 0; s < NSLICE; ++s) {  // slice g + 2 goes into the buffer slice g is being read from
-                        const int g = gs0 + s, b = g & 1;
-                        if (g + 2 < total_slices) {
-                            mbar_wait(&mbar[b], (uint32_t)((g >> 1) & 1));
-                            load_slice_bulk((s + 2) % NSLICE, b);
+                    for (int s = 0; s < NSLICE; ++s) {  // slice g + RING goes into the buffer slice g is being read from
+                        const int g = gs0 + s, b = g % RING;
+                        if (g + RING < total_slices) {
+                            mbar_wait(&mbar[b], (uint32_t)((g / RING) & 1));
+                            load_slice_bulk((s + RING) % NSLICE, b);
                         }
                     }
                 }
