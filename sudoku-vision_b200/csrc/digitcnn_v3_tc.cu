@@ -404,6 +404,9 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
             ph[0] ^= 1;
             K6T(6);
         } else {
+            // the issuing / producing warps fire their share of the next pass's loads now: after their loops they would be
+            // the last to reach the end-of-pass barrier (traces: ~2 k cycles per pass)
+            if ((issuer || producer) && next < n_pass) prefetch(next * G);
             // A(i) is written; the ring needs no CTA-wide synchronisation
             fence_proxy_async();
             tc_fence_before();
@@ -429,7 +432,6 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
                 }
                 __syncwarp();
                 K6T(3);
-                if (next < n_pass) prefetch(next * G);
                 K6T(4);
                 K6T(5);
             } else if (producer) {
@@ -444,7 +446,6 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
                     }
                 }
                 __syncwarp();
-                if (next < n_pass) prefetch(next * G);
             } else {  // overlapped with the tensor core: next pass's loads, previous pass's epilogue
                 K6T(3);
                 if (next < n_pass) prefetch(next * G);
