@@ -9,6 +9,10 @@ for p in (ROOT, os.path.join(ROOT, "sudoku-vision_b200")):
 import cv2
 import numpy as np
 import torch
+import svb200._lib as _L
+
+if os.environ.get("SVB_LIB"):  # A/B of two builds (tools/build_variant.py)
+    _L.LIB_PATH = os.path.abspath(os.environ["SVB_LIB"])
 from svb200 import Scanner, load_digitcnn_weights
 from svb200 import frames as F
 
