@@ -324,6 +324,19 @@ SVB_JHD void idct_islow(const int16_t *coef, int key, const uint16_t *q, uint8_t
     }
 }
 
+// a block whose AC coefficients are all zero: every step of the routine above collapses (columns 1..7 of pass 1 are zero,
+// column 0 is in0 << 2 in every row, every row of pass 2 is a constant), so the 64 samples are one value — computed with the
+// same integer expressions, hence the same bits.  In a 4:2:0 file the two chroma blocks of most MCUs are like this, and the
+// lanes of a warp are at the same block of their MCUs, so the branch is warp-uniform there.
+SVB_JHD void idct_dc_only(int dc, const uint16_t *q, uint8_t *out) {
+    const int in0 = dc * (int)q[0];
+    const int t = (int)((unsigned)in0 << 13);
+    const int w = (t + (1 << 10)) >> 11;
+    const int o = (int)((unsigned)w << 13);
+    const uint32_t v = (uint32_t)range_limit((o + (1 << 17)) >> 18) * 0x01010101u;
+    for (int rp = 0; rp < 4; ++rp) reinterpret_cast<uint4 *>(out)[rp] = make_uint4(v, v, v, v);
+}
+
 // ---- jdcolor.c ycc_rgb_convert (one pixel) ----------------------------------------------------------------------------------
 SVB_JHD uint8_t clamp255(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
 SVB_JHD void ycc_to_bgr(int y, int cb, int cr, uint8_t *bgr) {
@@ -380,9 +393,10 @@ SVB_JHD void decode_segment(const Image &im, const uint8_t *b, const uint8_t *e,
             for (int by = 0; by < vs; ++by)
                 for (int bx = 0; bx < hs; ++bx) {
                     for (int i = 0; i < 8; ++i) reinterpret_cast<uint4 *>(block)[i] = make_uint4(0, 0, 0, 0);
-                    decode_block<SW>(br, im.dc[im.dc_tab[c]], im.ac[im.ac_tab[c]], im.zz, last_dc[c], block, key);
+                    const int last = decode_block<SW>(br, im.dc[im.dc_tab[c]], im.ac[im.ac_tab[c]], im.zz, last_dc[c], block, key);
                     uint8_t *out = planes[c] + plane_index(pw[c], (mx * hs + bx) * 8, (my * vs + by) * 8);
-                    idct_islow<SW>(block, key, im.quant[im.q_tab[c]], out);
+                    if (last == 0) idct_dc_only(last_dc[c], im.quant[im.q_tab[c]], out);
+                    else idct_islow<SW>(block, key, im.quant[im.q_tab[c]], out);
                 }
         }
     }
