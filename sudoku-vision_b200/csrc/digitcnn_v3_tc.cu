@@ -43,6 +43,9 @@ constexpr int OFF = 8;  // zero rows before the first grid row
 #ifndef SVB_V3_ND
 #define SVB_V3_ND 1
 #endif
+#ifndef SVB_V3_ND32
+#define SVB_V3_ND32 1
+#endif
 
 // ---- PTX helpers (same conventions as digitcnn_tc.cu) ----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -149,8 +152,12 @@ struct Geo {
     // M128 N64 K16 MMA for 32 of math): 2 MMAs (64 + 48 cycles) per product instead of 3 x 50.  The accumulators double
     // (2 COUT columns per tile, summed in the epilogue), so a pass takes one cell instead of two to keep two accumulator
     // sets in TMEM, and the weight ring gets four buffers because a slice's MMAs are then shorter than a load.
-    static constexpr bool ND = !S2 && CIN == 64 && COUT == 64 && SVB_V3_ND;
-    static constexpr int G = ND ? 1 : (S2 ? (H == 28 ? 1 : 2) : ((H == 28) ? 1 : (H == 14 ? 2 : 4)));  // cells per pass
+    static constexpr bool ND = !S2 && ((CIN == 64 && COUT == 64) || (CIN == 32 && COUT == 32 && SVB_V3_ND32)) && SVB_V3_ND;
+    // the 32 -> 32 layers (28^2: seven M tiles of 64 accumulator columns = 448, no room for a second set): a cell is issued as
+    // TWO passes over the same activation buffer, tiles 0..3 and 4..6, each into its own 256-column accumulator set, so the
+    // epilogue of one half still runs under the MMAs of the other
+    static constexpr bool HALF = ND && CIN == 32;
+    static constexpr int G = (ND && CIN == 64) ? 1 : (S2 ? (H == 28 ? 1 : 2) : ((H == 28) ? 1 : (H == 14 ? 2 : 4)));  // cells per pass
     static constexpr int CB = (HO + 1) * GW;                        // rows per cell block (bottom halo shared with the next top halo)
     static constexpr int MROWS = (G - 1) * CB + (HO - 1) * GW + HO; // output rows that can be valid
     static constexpr int MT = (MROWS + 127) / 128;                  // M tiles of 128 rows
@@ -167,7 +174,8 @@ struct Geo {
     static constexpr int NSLICE = NMAIN + (S2 ? CIN / KS : 0);
     static constexpr int SLB = COUT * KS * 2;                       // bytes of one part of one weight slice
     static constexpr int TW = (ND ? 2 : 1) * COUT;                  // accumulator columns of one M tile
-    static constexpr int TCOLS = (S2 ? 2 : 1) * MT * TW;            // TMEM columns used (stride 2: main + shortcut accumulators)
+    static constexpr int MTP = HALF ? 4 : MT;                       // M tiles per pass
+    static constexpr int TCOLS = (S2 ? 2 : 1) * MTP * TW;           // TMEM columns used (stride 2: main + shortcut accumulators)
     static constexpr bool DB = 2 * TCOLS <= 512;                    // two accumulator sets: epilogue(i-1) under the MMAs of pass i
     static constexpr int TUSED = DB ? 2 * TCOLS : TCOLS;
     static constexpr int TALLOC = TUSED <= 32 ? 32 : (TUSED <= 64 ? 64 : (TUSED <= 128 ? 128 : (TUSED <= 256 ? 256 : 512)));
@@ -195,7 +203,8 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
     uint8_t *sB = sA + 2 * (size_t)PARTB;            // [NBUF buffers][2 parts][SLB]
     float *s_bias = (float *)(sB + (size_t)GEO::NBUF * 2 * SLB);
     unsigned long long *mbar = (unsigned long long *)(s_bias + COUT);
-    constexpr int RING = GEO::RING, TW = GEO::TW;
+    constexpr int RING = GEO::RING, TW = GEO::TW, MTP = GEO::MTP;
+    constexpr bool HALF = GEO::HALF;
     uint32_t *s_tmem = (uint32_t *)(mbar + 2 * RING + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // Roles (round 2, from per-phase clock64 traces): the MMA issue of a pass blocks on the tensor pipe's queue for the whole
@@ -206,7 +215,7 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
     // two-buffer weight ring (cp.async.bulk + full / empty mbarriers, running across pass boundaries) — the first form
     // re-synchronised the whole CTA for every slice (9..18 times per pass), which idled the tensor pipe half of the time.
     // Warps 0..11 (three groups x four TMEM lane quarters) do the epilogue that runs under the MMAs.
-    constexpr int WISSUE = NT / 32 - 4, NIW = GEO::RESIDENT ? 4 : 2, NISSUE = MT < NIW ? MT : NIW;
+    constexpr int WISSUE = NT / 32 - 4, NIW = GEO::RESIDENT ? 4 : 2, NISSUE = GEO::MTP < NIW ? GEO::MTP : NIW;
     const bool issuer = warp >= WISSUE && warp - WISSUE < NISSUE;
     const bool producer = !GEO::RESIDENT && warp == WISSUE + 2;
     unsigned long long *fbar = mbar + RING, *dbar = mbar + 2 * RING;  // empty[RING] = mbar, full[RING], done (all MMAs of a pass)
@@ -260,7 +269,7 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
     // its own issuing warp (warps 0..MT-1): the tiles are independent accumulators, each warp commits its own MMAs.
     // Everything that does not depend on the slice is a compile-time constant added to two per-slice base descriptors (all
     // shared-memory addresses are below 256 KB, so adding (byte offset >> 4) never carries out of the 14-bit field).
-    auto issue_slice = [&](int s, int buf, uint32_t tacc, bool single) {  // single: called by one elected thread
+    auto issue_slice = [&](int s, int buf, uint32_t tacc, bool single, int half) {  // single: called by one elected thread
         const bool sc = s >= NMAIN;  // a slice of the projection shortcut: centre tap, its own accumulators
         const int t = sc ? 4 : s / (CIN / KS), kb = sc ? s - NMAIN : s % (CIN / KS);
         const int dy = t / 3 - 1, dx = t % 3 - 1;
@@ -270,7 +279,7 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
         const uint64_t ad0 = make_desc(a_base + (uint32_t)(kb * (KS / 8) * ROWS * 16) + (uint32_t)row0 * 16u, ROWS * 16, 128);
         const uint64_t bd0 = make_desc(b_base + (uint32_t)(buf * 2 * SLB), 128, (KS / 8) * 128);
         const uint32_t acc0 = (s == 0 || s == NMAIN) ? 0u : 1u;
-        const uint32_t tsc = sc ? (uint32_t)(MT * TW) : 0u;
+        const uint32_t tsc = sc ? (uint32_t)(MTP * TW) : 0u;
 #pragma unroll
         for (int combo = 0; combo < (GEO::ND ? 2 : 3); ++combo) {
             // three products hi*hi, hi*lo, lo*hi; N-doubling: A_hi x [W_hi | W_lo] (N = 2 COUT), then A_lo x W_hi
@@ -282,10 +291,10 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
                 const uint32_t b_off = (uint32_t)(pb * SLB + ks * 256);
                 // consecutive MMAs of a warp go to different accumulator tiles where it owns two
 #pragma unroll
-                for (int tt = 0; tt < (MT + NIW - 1) / NIW; ++tt) {
-                    const int tile = warp - WISSUE + NIW * tt;
-                    if (tile < MT && (single || lane == 0))
-                        umma_f16(tacc + tsc + (uint32_t)(tile * TW), ad0 + (uint64_t)((a_off + (uint32_t)(tile * 128 * 16)) >> 4),
+                for (int tt = 0; tt < (MTP + NIW - 1) / NIW; ++tt) {
+                    const int tl = warp - WISSUE + NIW * tt, tile = half * MTP + tl;  // tile of this pass, tile of the cell
+                    if (tl < MTP && tile < MT && (single || lane == 0))
+                        umma_f16(tacc + tsc + (uint32_t)(tl * TW), ad0 + (uint64_t)((a_off + (uint32_t)(tile * 128 * 16)) >> 4),
                                  bd0 + (uint64_t)(b_off >> 4), id, (combo | ks) ? 1u : acc0);
                 }
             }
@@ -331,18 +340,19 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
         }
     };
     // TMEM -> + bias -> [ReLU] -> fp32 NCHW
-    auto epilogue = [&](int c0, uint32_t tacc, int ngroups) {  // ngroups = 3: warps 0..11 only (the issuing warps are busy)
+    auto epilogue = [&](int c0, uint32_t tacc, int ngroups, int half) {  // ngroups = 3: warps 0..11 only (the issuing warps are busy)
         const int q = warp & 3, grp = warp >> 2;  // TMEM lane quarter (hardware rule: warp % 4), work group
-        constexpr int NCB = COUT / 32, NBLK = (GEO::S2 ? 2 : 1) * MT * NCB;
+        constexpr int NCB = COUT / 32, NBLK = (GEO::S2 ? 2 : 1) * MTP * NCB;
         if (grp >= ngroups) return;
         for (int blk = grp; blk < NBLK; blk += ngroups) {
-            const bool sc = blk >= MT * NCB;  // second half: the shortcut's accumulators -> sc_out (+ its folded-BN bias, no ReLU)
-            const int b2 = sc ? blk - MT * NCB : blk, tile = b2 / NCB, cb = b2 - tile * NCB;
+            const bool sc = blk >= MTP * NCB;  // second half: the shortcut's accumulators -> sc_out (+ its folded-BN bias, no ReLU)
+            const int b2 = sc ? blk - MTP * NCB : blk, tl = b2 / NCB, cb = b2 - tl * NCB, tile = half * MTP + tl;
+            if (tile >= MT) continue;
             uint32_t v[32];
-            tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)((sc ? MT * TW : 0) + tile * TW + cb * 32), v);
+            tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)((sc ? MTP * TW : 0) + tl * TW + cb * 32), v);
             if (GEO::ND) {  // the A_hi x W_lo product sits COUT columns further
                 uint32_t v2[32];
-                tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * TW + COUT + cb * 32), v2);
+                tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * TW + COUT + cb * 32), v2);
 #pragma unroll
                 for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(v2[c]));
             }
@@ -364,18 +374,22 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
         }
     };
 
-    int it = 0, prev_c0 = -1;
+    int it = 0, prev_c0 = -1, prev_half = 0;
 #ifdef SVB_K6_TRACE
     long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
     if ((int)blockIdx.x < n_pass) prefetch((int)blockIdx.x * G);
-    for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x, ++it) {
+    for (;; ++it) {
+        // HALF: iterations 2k, 2k + 1 are the two tile halves of this CTA's k-th cell (same activation buffer)
+        const int pass = HALF ? (int)blockIdx.x + (it >> 1) * (int)gridDim.x : (int)blockIdx.x + it * (int)gridDim.x;
+        if (pass >= n_pass) break;
+        const int half = HALF ? (it & 1) : 0;
         const int c0 = pass * G;
         const uint32_t tacc = tmem + (DB ? (uint32_t)((it & 1) * GEO::TCOLS) : 0u);
         const uint32_t tacc_prev = tmem + (DB ? (uint32_t)(((it & 1) ^ 1) * GEO::TCOLS) : 0u);
         const int next = pass + gridDim.x;
         K6T(0);
-        write_A(c0);
+        if (half == 0) write_A(c0);
         K6T(1);
         if (GEO::RESIDENT) {
             fence_proxy_async();
@@ -386,18 +400,18 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
                 tc_fence_after();
 #pragma unroll
                 for (int s = 0; s < NSLICE; ++s) {
-                    issue_slice(s, s, tacc, false);
-                    if (s < IPT && next < n_pass) prefetch_k(next * G, s);
+                    issue_slice(s, s, tacc, false, half);
+                    if (half == 0 && s < IPT && next < n_pass) prefetch_k(next * G, s);
                 }
                 if (lane == 0) umma_commit(&mbar[0]);
                 __syncwarp();
             }
             K6T(3);
-            if (next < n_pass && !issuer) prefetch(next * G);
+            if (half == 0 && next < n_pass && !issuer) prefetch(next * G);
             K6T(4);
             if (DB && it > 0) {
                 tc_fence_after();
-                epilogue(prev_c0, tacc_prev, 3);
+                epilogue(prev_c0, tacc_prev, 3, prev_half);
             }
             K6T(5);
             mbar_wait(&mbar[0], ph[0]);
@@ -425,7 +439,7 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
                         const int g = gs0 + s, b = g % RING;
                         mbar_wait(&fbar[b], (uint32_t)((g / RING) & 1));
                         tc_fence_after();
-                        issue_slice(s, b, tacc, true);
+                        issue_slice(s, b, tacc, true, 0);
                         umma_commit(&mbar[b]);  // buffer b is free again once these MMAs have read it
                     }
                     umma_commit(dbar);
@@ -452,7 +466,7 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
                 K6T(4);
                 if (DB && it > 0) {
                     tc_fence_after();
-                    epilogue(prev_c0, tacc_prev, 3);
+                    epilogue(prev_c0, tacc_prev, 3, 0);
                 }
                 K6T(5);
             }
@@ -460,8 +474,9 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
             K6T(6);
         }
         tc_fence_after();
-        if (!DB) epilogue(c0, tacc, 4);
+        if (!DB) epilogue(c0, tacc, 4, half);
         prev_c0 = c0;
+        prev_half = half;
         tc_fence_before();
         __syncthreads();  // the activation buffer (and, single-buffered, TMEM) is free for the next pass
         tc_fence_after();
@@ -472,7 +487,7 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
                    COUT, H, tid, tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[7] - tr[6], tr[7] - tr[0]);
 #endif
     }
-    if (DB && it > 0) epilogue(prev_c0, tmem + (uint32_t)(((it - 1) & 1) * GEO::TCOLS), 4);
+    if (DB && it > 0) epilogue(prev_c0, tmem + (uint32_t)(((it - 1) & 1) * GEO::TCOLS), 4, prev_half);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, GEO::TALLOC);
