@@ -22,6 +22,7 @@ ap.add_argument("--frames-per-size", type=int, default=192)
 ap.add_argument("--unique", type=int, default=24)
 ap.add_argument("--cells", type=int, default=300000)
 ap.add_argument("--v2-frames", type=int, default=48)
+ap.add_argument("--seed-offset", type=int, default=0, help="shifts every seed: another draw of frames, cells and noise")
 ap.add_argument("--sections", default="v1,cells,k1,jpeg,v2")
 args = ap.parse_args()
 sections = args.sections.split(",")
@@ -103,7 +104,7 @@ def v1_size(h, wd, rot, seed):
 
 def cells_section():
     t0 = time.time()
-    rng = np.random.default_rng(77)
+    rng = np.random.default_rng(77 + args.seed_offset)
     n = args.cells
     nbad = 0
     for s in range(0, n, 50000):
@@ -179,10 +180,10 @@ def v2_section():
 
     t0 = time.time()
     nbad = tot = 0
-    rng = np.random.default_rng(21)
+    rng = np.random.default_rng(21 + args.seed_offset)
     for (h, wd) in [(544, 960), (720, 1280)]:
         n = args.v2_frames
-        base = list(pool.map(lambda i: F.make_frame(7000 + h + i, h, wd, max_rot_deg=25).image, range(n)))
+        base = list(pool.map(lambda i: F.make_frame(7000 + h + i + 100000 * args.seed_offset, h, wd, max_rot_deg=25).image, range(n)))
         yy, xx = np.mgrid[0:h, 0:wd].astype(np.float32)
         imgs = []
         for i, im in enumerate(base):
@@ -242,7 +243,7 @@ total = 0
 if "v1" in sections:
     for k, (h, wd, rot) in enumerate([(1080, 1920, 15.0), (1080, 1920, 40.0), (720, 1280, 30.0), (540, 960, 25.0), (480, 640, 35.0),
                                       (750, 1000, 20.0), (1200, 1600, 30.0), (2160, 3840, 20.0)]):
-        total += v1_size(h, wd, rot, 41000 + 1000 * k)
+        total += v1_size(h, wd, rot, 41000 + 1000 * k + 100000 * args.seed_offset)
 if "cells" in sections:
     total += cells_section()
 if "k1" in sections:
