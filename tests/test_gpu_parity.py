@@ -348,10 +348,11 @@ def test_digitcnn_v3_logits(scanner, golden):
     assert np.array_equal(pred.cpu().numpy(), g["ref_logits"].argmax(1))
 
 
-@pytest.mark.parametrize("n", [1, 3, 301, 2051])
+@pytest.mark.parametrize("n", [1, 3, 301, 2051, 5003])
 def test_digitcnn_v3_tensor_core_vs_fp32_and_oracle(scanner, n):
     """K6 on tcgen05 (fp16 hi/lo split, digitcnn_v3_tc.cu) against the fp32 CUDA-core kernels (svb_set_classifier_mode)
-    and the CPU oracle: ragged cell counts (partial passes of 1 / 2 / 4 cells, more than one 2048-cell chunk)."""
+    and the CPU oracle: ragged cell counts (partial passes of 1 / 2 / 4 cells; 5003 cells = three chunks of 2,368, the weight
+    ring running across many passes)."""
     import os
     import sys
 
