@@ -183,7 +183,7 @@ struct Geo {
     static constexpr bool RESIDENT = 2 * (size_t)PARTB + (size_t)NSLICE * 2 * SLB <= 200 * 1024;
     static constexpr int RING = ND ? 4 : 2;                         // buffers of the weight ring (streamed layers)
     static constexpr int NBUF = RESIDENT ? NSLICE : RING;
-    static constexpr size_t SMEM = 1024 + 2 * (size_t)PARTB + (size_t)NBUF * 2 * SLB + COUT * 4 + 128;
+    static constexpr size_t SMEM = 1024 + 2 * (size_t)PARTB + (size_t)NBUF * 2 * SLB + 2 * COUT * 4 + 128;
     static_assert(TCOLS <= 512, "accumulators exceed TMEM");
     static_assert(HO < GW, "grid needs a zero column");
 };
@@ -202,7 +202,7 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
     uint8_t *sA = base;                              // [2 parts][NKC][ROWS][8 fp16]
     uint8_t *sB = sA + 2 * (size_t)PARTB;            // [NBUF buffers][2 parts][SLB]
     float *s_bias = (float *)(sB + (size_t)GEO::NBUF * 2 * SLB);
-    unsigned long long *mbar = (unsigned long long *)(s_bias + COUT);
+    unsigned long long *mbar = (unsigned long long *)(s_bias + 2 * COUT);  // s_bias: [COUT] conv bias, [COUT] shortcut bias (stride 2)
     constexpr int RING = GEO::RING, TW = GEO::TW, MTP = GEO::MTP;
     constexpr bool HALF = GEO::HALF;
     uint32_t *s_tmem = (uint32_t *)(mbar + 2 * RING + 1);
@@ -221,7 +221,10 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
     unsigned long long *fbar = mbar + RING, *dbar = mbar + 2 * RING;  // empty[RING] = mbar, full[RING], done (all MMAs of a pass)
 
     for (int i = tid; i < 2 * PARTB / 16; i += NT) reinterpret_cast<uint4 *>(sA)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < COUT; i += NT) s_bias[i] = bias[i];
+    for (int i = tid; i < COUT; i += NT) {
+        s_bias[i] = bias[i];
+        s_bias[COUT + i] = GEO::S2 ? sc_bias[i] : 0.f;
+    }
     if (tid == 0) {  // one arrival per issuing warp (each commits its own MMAs)
         for (int b = 0; b < RING; ++b) {
             mbar_init(&mbar[b], NISSUE);  // resident: [0] = MMAs of a pass done; streaming: ring buffer b free again ("empty")
@@ -362,11 +365,11 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
             const bool ok = (j < G) && (cell < n_cells) && (y < HO) && (x < HO);
             if (ok) {
                 float *dst = (sc ? sc_out : out) + ((size_t)cell * COUT + cb * 32) * (HO * HO) + y * HO + x;
-                const float *bb = sc ? sc_bias : s_bias;
+                const float *bb = s_bias + (sc ? COUT : 0) + cb * 32;  // shared memory either way (a pointer select made these generic loads)
                 const bool rl = relu && !sc;
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
-                    float f = __uint_as_float(v[c]) + bb[cb * 32 + c];
+                    float f = __uint_as_float(v[c]) + bb[c];
                     if (rl) f = fmaxf(f, 0.f);
                     dst[(size_t)c * (HO * HO)] = f;
                 }
