@@ -198,7 +198,9 @@ conv3x3_tc_kernel(const float *__restrict__ in, const uint8_t *__restrict__ wimg
     constexpr int KS = GEO::KS, NSLICE = GEO::NSLICE, NMAIN = GEO::NMAIN, SLB = GEO::SLB, HH = H * H, HO = GEO::HO, PROWS = GEO::PROWS;
     static_assert(GEO::S2 == (STRIDE == 2) && HO == (H - 1) / STRIDE + 1, "stride-2 layers are the ones that change the channel count");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // no round trip through an integer: that made every access to this buffer a GENERIC load / store (LD.E / ST.E in SASS)
+    // instead of LDS / STS.  The no-swizzle descriptors need 16-byte alignment only, which the declaration guarantees.
+    uint8_t *base = smem_raw;
     uint8_t *sA = base;                              // [2 parts][NKC][ROWS][8 fp16]
     uint8_t *sB = sA + 2 * (size_t)PARTB;            // [NBUF buffers][2 parts][SLB]
     float *s_bias = (float *)(sB + (size_t)GEO::NBUF * 2 * SLB);
